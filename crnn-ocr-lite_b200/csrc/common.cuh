@@ -1,0 +1,65 @@
+// common.cuh -- shared helpers for the sm_100a kernels of the CRNN-OCR hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifndef CRNN_OK   // same values as include/crnn_b200.h
+#define CRNN_OK 0
+#define CRNN_ERR_INVALID (-1)
+#define CRNN_ERR_CUDA (-2)
+#define CRNN_ERR_NOMEM (-3)
+#define CRNN_ERR_UNKNOWN_NAME (-4)
+#define CRNN_ERR_INFEASIBLE (-5)
+#endif
+
+void crnn_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            crnn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return CRNN_ERR_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+#define LAUNCH_CHECK() CUDA_TRY(cudaGetLastError())
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+#define NEG_INF (__int_as_float(0xff800000))
+
+__device__ __forceinline__ float lse2(float a, float b) {
+    // TF ctc_loss_util.h LogSumExp, fp32, accurate (non fast-math) expf/log1pf
+    if (a == NEG_INF && b == NEG_INF) return NEG_INF;
+    return (a > b) ? a + log1pf(expf(b - a)) : b + log1pf(expf(a - b));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6.f); }
+__device__ __forceinline__ float hard_sigmoid(float v) { return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, v), 0.5f), 0.f), 1.f); }
+
+// Stateless dropout RNG: keep mask for element `idx` of dropout layer `layer` at optimiser step `step`.
+// (murmur3-style 64-bit finaliser; the same function is restated in tests for dropout-on parity.)
+__host__ __device__ __forceinline__ uint32_t crnn_hash(uint64_t seed, uint32_t layer, uint64_t idx) {
+    uint64_t x = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(layer + 1)) ^ (idx * 0xD6E8FEB86659FD93ull);
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)(x >> 32);
+}
+// returns 0 or 1/(1-rate)
+__host__ __device__ __forceinline__ float crnn_dropout_mask(uint64_t seed, uint32_t layer, uint64_t idx, float rate, float inv_keep) {
+    uint32_t thr = (uint32_t)((double)rate * 4294967296.0);
+    return crnn_hash(seed, layer, idx) >= thr ? inv_keep : 0.f;
+}
+#endif

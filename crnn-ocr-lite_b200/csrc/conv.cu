@@ -1,0 +1,462 @@
+// conv.cu -- HBM-bound stages of the depthwise-separable conv stack (reference utils.py:43-56):
+// DepthwiseConv2D 3x3 'same' (fwd, bwd-data, bwd-weight), BatchNormalization statistics / finalize / backward,
+// ReLU6 + MaxPooling + Dropout (fwd / bwd), and the small element-wise glue of the recurrent head.
+// All tensors NHWC fp32; channel counts are 1 or multiples of 4 (float4 path).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, const float4 x, const float4 k) {
+    a.x = fmaf(x.x, k.x, a.x); a.y = fmaf(x.y, k.y, a.y); a.z = fmaf(x.z, k.z, a.z); a.w = fmaf(x.w, k.w, a.w);
+}
+
+// ------------------------------------------------------------------ depthwise 3x3 forward / backward-data
+// FLIP=false: y[h,w] = sum_{i,j} x[h+i-1, w+j-1] * k[i][j]        (forward, cross-correlation like Keras)
+// FLIP=true : dx[h,w] = sum_{i,j} dy[h-i+1, w-j+1] * k[i][j]      (backward wrt input)
+template <bool FLIP>
+__global__ void dwconv3x3_vec4(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
+                               int B, int H, int W, int C4, long long total)
+{
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(idx % C4); long long r = idx / C4;
+        int w = (int)(r % W); r /= W;
+        int h = (int)(r % H); int b = (int)(r / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            int hh = FLIP ? h - i + 1 : h + i - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                int ww = FLIP ? w - j + 1 : w + j - 1;
+                if (ww < 0 || ww >= W) continue;
+                float4 xv = ldg4(x + (((size_t)b * H + hh) * W + ww) * (size_t)(C4 * 4) + c4 * 4);
+                float4 kv = ldg4(k + (size_t)(i * 3 + j) * (C4 * 4) + c4 * 4);
+                fma4(acc, xv, kv);
+            }
+        }
+        *reinterpret_cast<float4*>(y + (size_t)idx * 4) = acc;
+    }
+}
+template <bool FLIP>
+__global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
+                             int B, int H, int W, long long total)
+{
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int w = (int)(idx % W); long long r = idx / W;
+        int h = (int)(r % H); int b = (int)(r / H);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            int hh = FLIP ? h - i + 1 : h + i - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                int ww = FLIP ? w - j + 1 : w + j - 1;
+                if (ww < 0 || ww >= W) continue;
+                acc = fmaf(__ldg(x + ((size_t)b * H + hh) * W + ww), __ldg(k + i * 3 + j), acc);
+            }
+        }
+        y[idx] = acc;
+    }
+}
+
+// ------------------------------------------------------------------ depthwise 3x3 backward-weight
+// dk[i][j][c] = sum_{b,h,w} x[b,h+i-1,w+j-1,c] * dy[b,h,w,c].  blockDim = (CT channels, PY pixel lanes)
+__global__ void dwconv3x3_bwd_weight(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
+                                     int B, int H, int W, int C, long long npix)
+{
+    extern __shared__ float red[];   // [PY][9][CT]
+    const int CT = blockDim.x, PY = blockDim.y;
+    const int c = blockIdx.x * CT + threadIdx.x;
+    float acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0.f;
+    if (c < C) {
+        for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < npix; p += (long long)gridDim.y * PY) {
+            int w = (int)(p % W); long long r = p / W;
+            int h = (int)(r % H); int b = (int)(r / H);
+            float g = __ldg(dy + (size_t)p * C + c);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                int hh = h + i - 1;
+                if (hh < 0 || hh >= H) continue;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    int ww = w + j - 1;
+                    if (ww < 0 || ww >= W) continue;
+                    acc[i * 3 + j] = fmaf(__ldg(x + (((size_t)b * H + hh) * W + ww) * C + c), g, acc[i * 3 + j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) red[(threadIdx.y * 9 + q) * CT + threadIdx.x] = acc[q];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            float s = 0.f;
+            for (int y = 0; y < PY; ++y) s += red[(y * 9 + q) * CT + threadIdx.x];
+            atomicAdd(dk + (size_t)q * C + c, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ per-channel statistics
+// blockDim = (CT, PY); stats[c] += sum y, stats[C+c] += sum y^2 (double)
+__global__ void colstats_kernel(const float* __restrict__ y, long long M, int C, double* __restrict__ stats)
+{
+    extern __shared__ double dred[];  // [PY][2][CT]
+    const int CT = blockDim.x, PY = blockDim.y;
+    const int c = blockIdx.x * CT + threadIdx.x;
+    double s = 0.0, q = 0.0;
+    if (c < C)
+        for (long long m = blockIdx.y * (long long)PY + threadIdx.y; m < M; m += (long long)gridDim.y * PY) {
+            double v = (double)__ldg(y + (size_t)m * C + c);
+            s += v; q = fma(v, v, q);
+        }
+    dred[(threadIdx.y * 2 + 0) * CT + threadIdx.x] = s;
+    dred[(threadIdx.y * 2 + 1) * CT + threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double ts = 0.0, tq = 0.0;
+        for (int i = 0; i < PY; ++i) { ts += dred[(i * 2) * CT + threadIdx.x]; tq += dred[(i * 2 + 1) * CT + threadIdx.x]; }
+        atomicAdd(stats + c, ts); atomicAdd(stats + C + c, tq);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double M, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ mm, float* __restrict__ mv,
+                                   float eps, float momentum, int training, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mean, var;
+    if (training) {
+        mean = stats[c] / M;
+        var = stats[C + c] / M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        // Keras 2.2.2 moving-average update: fused-op Bessel correction times n/(n-(1+eps))
+        double var_mov = var * (M / (M - 1.0)) * (M / (M - (1.0 + (double)eps)));
+        float om = 1.0f - momentum;
+        mm[c] = mm[c] - (mm[c] - (float)mean) * om;
+        mv[c] = mv[c] - (mv[c] - (float)var_mov) * om;
+    } else {
+        mean = mm[c]; var = mv[c];
+    }
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = invstd; }
+}
+
+// ------------------------------------------------------------------ BN + ReLU6 + MaxPool + Dropout forward
+__global__ void act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    float* __restrict__ a, int B, int H, int W, int C4, int ph, int pw,
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long total)
+{
+    const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(idx % C4); long long r = idx / C4;
+        int wo = (int)(r % Wo); r /= Wo;
+        int ho = (int)(r % Ho); int b = (int)(r / Ho);
+        float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int i = 0; i < ph; ++i)
+            for (int j = 0; j < pw; ++j) {
+                float4 v = ldg4(y + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4);
+                m.x = fmaxf(m.x, relu6f(fmaf(v.x, sc.x, sh.x))); m.y = fmaxf(m.y, relu6f(fmaf(v.y, sc.y, sh.y)));
+                m.z = fmaxf(m.z, relu6f(fmaf(v.z, sc.z, sh.z))); m.w = fmaxf(m.w, relu6f(fmaf(v.w, sc.w, sh.w)));
+            }
+        if (rate > 0.f) {
+            m.x *= crnn_dropout_mask(seed, layer, idx * 4 + 0, rate, inv_keep); m.y *= crnn_dropout_mask(seed, layer, idx * 4 + 1, rate, inv_keep);
+            m.z *= crnn_dropout_mask(seed, layer, idx * 4 + 2, rate, inv_keep); m.w *= crnn_dropout_mask(seed, layer, idx * 4 + 3, rate, inv_keep);
+        }
+        *reinterpret_cast<float4*>(a + (size_t)idx * 4) = m;
+    }
+}
+
+// backward of the above (thread per pooled output x 4 channels); writes dz for the whole window and
+// accumulates sum(dz), sum(dz*xhat) per channel (smem float atomics -> global double atomics).
+__global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    float* __restrict__ dz, double* __restrict__ red, int B, int H, int W, int C4, int ph, int pw,
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long total)
+{
+    extern __shared__ float sred[];   // [2][C]
+    const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(idx % C4); long long r = idx / C4;
+        int wo = (int)(r % Wo); r /= Wo;
+        int ho = (int)(r % Ho); int b = (int)(r / Ho);
+        float sc[4], sh[4], mu[4], is[4], g[4];
+        { float4 t = ldg4(scale + c4 * 4); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
+        { float4 t = ldg4(shift + c4 * 4); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
+        { float4 t = ldg4(mean + c4 * 4); mu[0] = t.x; mu[1] = t.y; mu[2] = t.z; mu[3] = t.w; }
+        { float4 t = ldg4(invstd + c4 * 4); is[0] = t.x; is[1] = t.y; is[2] = t.z; is[3] = t.w; }
+        { float4 t = ldg4(da + (size_t)idx * 4); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+        if (rate > 0.f)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[q] *= crnn_dropout_mask(seed, layer, idx * 4 + q, rate, inv_keep);
+        float yv[4][4], best[4]; int arg[4];   // window <= 4 elements
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { best[q] = -INFINITY; arg[q] = 0; }
+        int n = 0;
+        for (int i = 0; i < ph; ++i)
+            for (int j = 0; j < pw; ++j, ++n) {
+                float4 t = ldg4(y + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4);
+                yv[n][0] = t.x; yv[n][1] = t.y; yv[n][2] = t.z; yv[n][3] = t.w;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float aq = relu6f(fmaf(yv[n][q], sc[q], sh[q]));
+                    if (aq > best[q]) { best[q] = aq; arg[q] = n; }   // first max wins (TF / torch max-pool grad)
+                }
+            }
+        float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+        n = 0;
+        for (int i = 0; i < ph; ++i)
+            for (int j = 0; j < pw; ++j, ++n) {
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float z = fmaf(yv[n][q], sc[q], sh[q]);
+                    float d = (arg[q] == n && z >= 0.f && z <= 6.f) ? g[q] : 0.f;
+                    o[q] = d; s1[q] += d; s2[q] = fmaf(d, (yv[n][q] - mu[q]) * is[q], s2[q]);
+                }
+                *reinterpret_cast<float4*>(dz + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (s1[q] != 0.f) atomicAdd(&sred[c4 * 4 + q], s1[q]);
+            if (s2[q] != 0.f) atomicAdd(&sred[C + c4 * 4 + q], s2[q]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) if (sred[i] != 0.f) atomicAdd(red + i, (double)sred[i]);
+}
+
+// relu6 backward only (BN after the depthwise conv): y,da,dz [M][C]
+__global__ void relu6_bwd_kernel(const float* da /* may alias dz */, const float* __restrict__ y, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                 float* dz, double* __restrict__ red, long long M, int C)
+{
+    extern __shared__ float sred[];   // [PY][2][CT]
+    const int CT = blockDim.x, PY = blockDim.y;
+    const int c = blockIdx.x * CT + threadIdx.x;
+    float s1 = 0.f, s2 = 0.f;
+    if (c < C) {
+        const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+        for (long long m = blockIdx.y * (long long)PY + threadIdx.y; m < M; m += (long long)gridDim.y * PY) {
+            float yv = __ldg(y + (size_t)m * C + c);
+            float z = fmaf(yv, sc, sh);
+            float d = (z >= 0.f && z <= 6.f) ? da[(size_t)m * C + c] : 0.f;
+            dz[(size_t)m * C + c] = d;
+            s1 += d; s2 = fmaf(d, (yv - mu) * is, s2);
+        }
+    }
+    sred[(threadIdx.y * 2 + 0) * CT + threadIdx.x] = s1;
+    sred[(threadIdx.y * 2 + 1) * CT + threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < PY; ++i) { t1 += sred[(i * 2) * CT + threadIdx.x]; t2 += sred[(i * 2 + 1) * CT + threadIdx.x]; }
+        atomicAdd(red + c, t1); atomicAdd(red + C + c, t2);
+    }
+}
+
+// dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))  (in place);  block 0 also emits dgamma/dbeta
+__global__ void bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restrict__ y, const double* __restrict__ red,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C, long long total)
+{
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] += (float)red[c]; dgamma[c] += (float)red[C + c]; }
+    const double invM = 1.0 / (double)M;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % C);
+        float m1 = (float)(red[c] * invM), m2 = (float)(red[C + c] * invM);
+        float is = invstd[c];
+        float xh = (y[idx] - mean[c]) * is;
+        dz[idx] = gamma[c] * is * (dz[idx] - m1 - xh * m2);
+    }
+}
+
+// ------------------------------------------------------------------ misc element-wise
+__global__ void colsum_kernel(const float* __restrict__ y, long long M, int C, int ldy, float* __restrict__ out)
+{
+    extern __shared__ float sred[];   // [PY][CT]
+    const int CT = blockDim.x, PY = blockDim.y;
+    const int c = blockIdx.x * CT + threadIdx.x;
+    float s = 0.f;
+    if (c < C)
+        for (long long m = blockIdx.y * (long long)PY + threadIdx.y; m < M; m += (long long)gridDim.y * PY) s += __ldg(y + (size_t)m * ldy + c);
+    sred[threadIdx.y * CT + threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+        for (int i = 0; i < PY; ++i) t += sred[i * CT + threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+__global__ void relu_dropout_bwd_kernel(float* __restrict__ g, const float* __restrict__ act, long long n, float inv_keep)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        g[i] = act[i] > 0.f ? g[i] * inv_keep : 0.f;
+}
+__global__ void dropout_kernel(float* __restrict__ x, long long n, float rate, float inv_keep, uint64_t seed, uint32_t layer)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] *= crnn_dropout_mask(seed, layer, (uint64_t)i, rate, inv_keep);
+}
+__global__ void sum_dirs_kernel(const float* __restrict__ hs, float* __restrict__ out, long long rows, int U)
+{
+    long long n = rows * U;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / U; int u = (int)(i % U);
+        out[i] = hs[(r * 2) * U + u] + hs[(r * 2 + 1) * U + u];
+    }
+}
+__global__ void dup_dirs_kernel(const float* __restrict__ g, float* __restrict__ out, long long rows, int U)
+{
+    long long n = rows * U;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / U; int u = (int)(i % U);
+        float v = g[i];
+        out[(r * 2) * U + u] = v; out[(r * 2 + 1) * U + u] = v;
+    }
+}
+// softmax over the last axis, one warp per row (same formula as Keras softmax: exp(z-max)/sum)
+__global__ void softmax_rows_kernel(const float* __restrict__ z, float* __restrict__ p, long long rows, int V)
+{
+    const int lane = threadIdx.x & 31;
+    long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* zr = z + (size_t)row * V; float* pr = p + (size_t)row * V;
+    float mx = -INFINITY;
+    for (int k = lane; k < V; k += 32) mx = fmaxf(mx, zr[k]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int k = lane; k < V; k += 32) s += expf(zr[k] - mx);
+    s = warp_sum(s);
+    for (int k = lane; k < V; k += 32) pr[k] = expf(zr[k] - mx) / s;
+}
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C)
+{
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) { int r = r0 + i; if (r < R && c < C) tile[i][threadIdx.x] = in[(size_t)r * C + c]; }
+    __syncthreads();
+    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) { int cc = c0 + i; if (r < R && cc < C) out[(size_t)cc * R + r] = tile[threadIdx.x][i]; }
+}
+
+inline int grid1d(long long total, int threads, int max_blocks = 148 * 16) {
+    long long b = (total + threads - 1) / threads;
+    if (b > max_blocks) b = max_blocks;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+// 2-D (channel, pixel-lane) block: CT channels x PY lanes = 256 threads, grid.y sized for ~4 CTAs/SM
+inline void chan_block(int C, long long M, dim3& grid, dim3& block) {
+    int CT = C >= 64 ? 64 : (C >= 32 ? 32 : (C >= 16 ? 16 : (C >= 8 ? 8 : (C >= 4 ? 4 : (C >= 2 ? 2 : 1)))));
+    int PY = 256 / CT;
+    int gx = (C + CT - 1) / CT;
+    long long gy = (148 * 4 + gx - 1) / gx;
+    long long maxy = (M + PY - 1) / PY;
+    if (gy > maxy) gy = maxy;
+    if (gy < 1) gy = 1;
+    grid = dim3(gx, (unsigned)gy); block = dim3(CT, PY);
+}
+
+}  // namespace
+
+int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st) {
+    if (C % 4 == 0) { long long total = (long long)B * H * W * (C / 4); dwconv3x3_vec4<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, C / 4, total); }
+    else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, total); }
+    else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
+    if (accumulate) { crnn_set_error("dwconv_bwd_data: accumulate unsupported"); return CRNN_ERR_INVALID; }
+    if (C % 4 == 0) { long long total = (long long)B * H * W * (C / 4); dwconv3x3_vec4<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, C / 4, total); }
+    else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, total); }
+    else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk, int B, int H, int W, int C, cudaStream_t st) {
+    dim3 grid, block; long long npix = (long long)B * H * W;
+    chan_block(C, npix, grid, block);
+    size_t smem = sizeof(float) * block.y * 9 * block.x;
+    dwconv3x3_bwd_weight<<<grid, block, smem, st>>>(x, dy, dk, B, H, W, C, npix);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_colstats(const float* y, long long M, int C, double* stats, cudaStream_t st) {
+    dim3 grid, block; chan_block(C, M, grid, block);
+    colstats_kernel<<<grid, block, sizeof(double) * 2 * 256, st>>>(y, M, C, stats);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_bn_finalize(const double* stats, long long M, int C, const float* gamma, const float* beta, float* mm, float* mv,
+                       float eps, float momentum, int training, float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(stats, (double)M, C, gamma, beta, mm, mv, eps, momentum, training, scale, shift, save_mean, save_invstd);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C, int ph, int pw,
+                        float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
+    if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
+    long long total = (long long)B * (H / ph) * (W / pw) * (C / 4);
+    act_pool_fwd_kernel<<<grid1d(total, 256), 256, 0, st>>>(y, scale, shift, a, B, H, W, C / 4, ph, pw, rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, total);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_act_pool_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                        float* dz, double* red, int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
+    if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
+    long long total = (long long)B * (H / ph) * (W / pw) * (C / 4);
+    act_pool_bwd_kernel<<<grid1d(total, 256, 148 * 4), 256, sizeof(float) * 2 * C, st>>>(da, y, scale, shift, mean, invstd, dz, red, B, H, W, C / 4, ph, pw,
+                                                                                         rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, total);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_relu6_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                     float* dz, double* red, long long M, int C, cudaStream_t st) {
+    dim3 grid, block; chan_block(C, M, grid, block);
+    relu6_bwd_kernel<<<grid, block, sizeof(float) * 2 * 256, st>>>(da, y, scale, shift, mean, invstd, dz, red, M, C);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_bn_bwd_apply(float* dz, const float* y, const double* red, const float* gamma, const float* mean, const float* invstd,
+                        float* dgamma, float* dbeta, long long M, int C, cudaStream_t st) {
+    long long total = M * C;
+    bn_bwd_apply_kernel<<<grid1d(total, 256), 256, 0, st>>>(dz, y, red, gamma, mean, invstd, dgamma, dbeta, M, C, total);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_colsum(const float* y, long long M, int C, int ldy, float* out, cudaStream_t st) {
+    dim3 grid, block; chan_block(C, M, grid, block);
+    colsum_kernel<<<grid, block, sizeof(float) * 256, st>>>(y, M, C, ldy, out);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_relu_dropout_bwd(float* g, const float* act, long long n, float rate, uint64_t, uint32_t, cudaStream_t st) {
+    relu_dropout_bwd_kernel<<<grid1d(n, 256), 256, 0, st>>>(g, act, n, rate > 0.f ? 1.f / (1.f - rate) : 1.f);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_dropout_fwd(float* x, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
+    if (rate <= 0.f) return CRNN_OK;
+    dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(x, n, rate, 1.f / (1.f - rate), seed, layer);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_sum_dirs(const float* hs, float* out, long long rows, int U, cudaStream_t st) {
+    sum_dirs_kernel<<<grid1d(rows * U, 256), 256, 0, st>>>(hs, out, rows, U); LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_dup_dirs(const float* g, float* out, long long rows, int U, cudaStream_t st) {
+    dup_dirs_kernel<<<grid1d(rows * U, 256), 256, 0, st>>>(g, out, rows, U); LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_softmax_rows(const float* z, float* p, long long rows, int V, cudaStream_t st) {
+    softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, p, rows, V); LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st) {
+    transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32)), dim3(32, 8), 0, st>>>(in, out, R, C); LAUNCH_CHECK(); return CRNN_OK;
+}

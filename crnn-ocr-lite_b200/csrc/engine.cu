@@ -1,0 +1,531 @@
+// engine.cu -- the CRNN hot path as a fixed launch sequence over one caller-owned workspace, plus the C ABI
+// (include/crnn_b200.h).  Mirrors CRNN.get_model (reference utils.py:58-96): STN -> ZeroPadding2D -> 7 depthwise-
+// separable blocks -> dense1 -> 2 x Bidirectional GRU/LSTM -> dense2 -> softmax -> CTC (utils.py:98-103), the full
+// backward of that graph and the Keras optimiser step (train.py:187-192).
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/crnn_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+static thread_local char g_err[512] = "";
+void crnn_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+#define TRY(expr) do { int _s = (expr); if (_s != CRNN_OK) return _s; } while (0)
+
+namespace {
+struct BlockPlan { int cin, cout, ph, pw; };
+const BlockPlan kBlocks[7] = {{1, 64, 1, 1}, {64, 128, 1, 1}, {128, 256, 2, 2}, {256, 256, 1, 1}, {256, 512, 1, 2}, {512, 512, 1, 1}, {512, 512, 1, 1}};
+constexpr float kBnEps = 1e-3f, kBnMomentum = 0.99f, kKerasEps = 1e-7f;
+constexpr float kDropBlock = 0.1f, kDropDense1 = 0.4f, kDropRnn = 0.2f;
+
+struct Tensor { std::string name; int64_t offset; int64_t numel; int is_int; };
+
+struct Layout {
+    std::vector<Tensor> tensors;
+    std::map<std::string, int> index;
+    int64_t cursor = 0;
+    int64_t add(const std::string& name, int64_t numel, int elem = 4, int is_int = 0) {
+        cursor = (cursor + 255) & ~(int64_t)255;
+        int64_t off = cursor;
+        index[name] = (int)tensors.size();
+        tensors.push_back({name, off, numel, is_int});
+        cursor += numel * elem;
+        return off;
+    }
+    // view into an existing arena (no allocation)
+    void alias(const std::string& name, int64_t offset, int64_t numel) {
+        index[name] = (int)tensors.size();
+        tensors.push_back({name, offset, numel, 0});
+    }
+};
+}  // namespace
+
+struct crnn_handle {
+    crnn_config cfg;
+    char* base = nullptr;
+    size_t bytes = 0;
+    Layout L;
+    int H, W, Hp, Wp, T, V, U, G, GS, TD, FEAT, maxB;
+    StnDims sd;
+    int64_t n_params = 0;
+    int64_t iterations = 0;
+    std::vector<std::pair<std::string, int64_t>> weights;   // trainable, Keras order
+    std::vector<std::pair<std::string, int64_t>> stats;     // BN moving statistics
+
+    float* f(const std::string& name) const {
+        auto it = L.index.find(name);
+        if (it == L.index.end()) { crnn_set_error("internal: unknown tensor %s", name.c_str()); return nullptr; }
+        return reinterpret_cast<float*>(base + L.tensors[it->second].offset);
+    }
+    float* w(const std::string& n) const { return f(n); }
+    float* g(const std::string& n) const { return f("grad/" + n); }
+    float* a(const std::string& n) const { return f("act/" + n); }
+    std::string rnn(int layer, int dir) const {
+        const char* c = cfg.cell == CRNN_CELL_GRU ? "gru" : "lstm";
+        char buf[96]; snprintf(buf, sizeof(buf), "bidirectional_%d/%s_%s_%d", layer, dir ? "backward" : "forward", c, layer);
+        return buf;
+    }
+};
+
+namespace {
+
+int validate(const crnn_config* c) {
+    if (!c) { crnn_set_error("null config"); return CRNN_ERR_INVALID; }
+    if (c->imgw != 32) { crnn_set_error("imgW must be 32 (the conv stack reduces it to 9 columns)"); return CRNN_ERR_INVALID; }
+    if (c->imgh < 40 || c->imgh % 2) { crnn_set_error("imgh must be even and >= 40"); return CRNN_ERR_INVALID; }
+    if (c->n_units != 256) { crnn_set_error("n_units must be 256"); return CRNN_ERR_INVALID; }
+    if (c->num_classes < 2 || c->num_classes > 1024) { crnn_set_error("num_classes out of range"); return CRNN_ERR_INVALID; }
+    if (c->cell != CRNN_CELL_GRU && c->cell != CRNN_CELL_LSTM) { crnn_set_error("bad cell"); return CRNN_ERR_INVALID; }
+    if (c->time_dense < 4 || c->time_dense % 4) { crnn_set_error("time_dense must be a multiple of 4"); return CRNN_ERR_INVALID; }
+    if (c->max_batch < 1 || c->max_len < 1) { crnn_set_error("bad max_batch/max_len"); return CRNN_ERR_INVALID; }
+    return CRNN_OK;
+}
+
+void plan(crnn_handle* h) {
+    const crnn_config& c = h->cfg;
+    h->H = c.imgh; h->W = c.imgw; h->Hp = c.imgh + 4; h->Wp = c.imgw + 4;
+    h->T = h->Hp / 2; h->V = c.num_classes; h->U = c.n_units; h->TD = c.time_dense;
+    h->G = c.cell == CRNN_CELL_GRU ? 3 : 4; h->GS = c.cell == CRNN_CELL_GRU ? 3 : 5;
+    h->FEAT = (h->Wp / 4) * 512; h->maxB = c.max_batch;
+    h->sd = stn_dims(h->H, h->W);
+    Layout& L = h->L;
+    auto W = [&](const std::string& n, int64_t numel) { h->weights.push_back({n, numel}); };
+    auto S = [&](const std::string& n, int64_t numel) { h->stats.push_back({n, numel}); };
+    // Keras layer_names / weight_names order (models/<name>/final_weights.h5)
+    W("conv2d_1/kernel", 25 * 20); W("conv2d_1/bias", 20);
+    W("conv2d_2/kernel", 25 * 20 * 20); W("conv2d_2/bias", 20);
+    W("dense_1/kernel", (int64_t)h->sd.F * 50); W("dense_1/bias", 50);
+    W("dense_2/kernel", 300); W("dense_2/bias", 6);
+    for (int i = 1; i <= 7; ++i) {
+        const BlockPlan& b = kBlocks[i - 1];
+        char n[96];
+        snprintf(n, sizeof(n), "depthwise_conv2d_%d/depthwise_kernel", i); W(n, 9 * b.cin);
+        for (int k = 0; k < 2; ++k) {
+            int bn = 2 * i - 1 + k, ch = k ? b.cout : b.cin;
+            if (k == 1) { snprintf(n, sizeof(n), "conv2d_%d/kernel", i + 2); W(n, (int64_t)b.cin * b.cout); }
+            snprintf(n, sizeof(n), "batch_normalization_%d/gamma", bn); W(n, ch);
+            snprintf(n, sizeof(n), "batch_normalization_%d/beta", bn); W(n, ch);
+            snprintf(n, sizeof(n), "batch_normalization_%d/moving_mean", bn); S(n, ch);
+            snprintf(n, sizeof(n), "batch_normalization_%d/moving_variance", bn); S(n, ch);
+        }
+    }
+    W("dense1/kernel", (int64_t)h->FEAT * h->TD); W("dense1/bias", h->TD);
+    for (int layer = 1; layer <= 2; ++layer)
+        for (int d = 0; d < 2; ++d) {
+            int kin = layer == 1 ? h->TD : h->U;
+            W(h->rnn(layer, d) + "/kernel", (int64_t)kin * h->G * h->U);
+            W(h->rnn(layer, d) + "/recurrent_kernel", (int64_t)h->U * h->G * h->U);
+            W(h->rnn(layer, d) + "/bias", h->G * h->U);
+        }
+    W("dense2/kernel", 2 * h->U * h->V); W("dense2/bias", h->V);
+
+    // arenas: every weight padded to a multiple of 4 floats so that all tensors stay 16-byte aligned
+    int64_t n = 0;
+    std::vector<int64_t> offs;
+    for (auto& p : h->weights) { offs.push_back(n); n += (p.second + 3) & ~(int64_t)3; }
+    h->n_params = n;
+    const char* arenas[4] = {"arena/params", "arena/grads", "arena/opt_m", "arena/opt_v"};
+    const char* prefix[4] = {"", "grad/", "adam_m/", "adam_v/"};
+    for (int a = 0; a < 4; ++a) {
+        int64_t base = L.add(arenas[a], n);
+        for (size_t i = 0; i < h->weights.size(); ++i) L.alias(std::string(prefix[a]) + h->weights[i].first, base + offs[i] * 4, h->weights[i].second);
+    }
+    for (auto& p : h->stats) L.add(p.first, p.second);
+
+    // activations (sized for max_batch)
+    const int64_t B = h->maxB;
+    auto A = [&](const std::string& nm, int64_t numel) { L.add("act/" + nm, numel); };
+    A("x", B * h->H * h->W);
+    A("p1", B * h->sd.P1h * h->sd.P1w); A("p2", B * h->sd.P2h * h->sd.P2w * 20);
+    L.add("act/p2arg", B * h->sd.P2h * h->sd.P2w * 20, 4, 1);
+    A("flat", B * h->sd.F); A("loc_d1", B * 50); A("theta", B * 6);
+    A("a0", B * h->Hp * h->Wp);
+    int hh = h->Hp, ww = h->Wp;
+    int64_t max_act = 0;
+    for (int i = 1; i <= 7; ++i) {
+        const BlockPlan& b = kBlocks[i - 1];
+        char nm[32];
+        snprintf(nm, sizeof(nm), "dw%d", i); A(nm, B * hh * ww * b.cin);
+        snprintf(nm, sizeof(nm), "pw%d", i); A(nm, B * hh * ww * b.cout);
+        if (B * hh * ww * b.cout > max_act) max_act = B * hh * ww * b.cout;
+        hh /= b.ph; ww /= b.pw;
+        snprintf(nm, sizeof(nm), "block%d", i); A(nm, B * hh * ww * b.cout);
+        for (int k = 0; k < 2; ++k) {
+            int bn = 2 * i - 1 + k, ch = k ? b.cout : b.cin;
+            const char* parts[4] = {"scale", "shift", "mean", "invstd"};
+            for (auto pt : parts) { char t[48]; snprintf(t, sizeof(t), "bn%d/%s", bn, pt); A(t, ch); }
+        }
+    }
+    const int64_t M = B * h->T;
+    if (M * h->FEAT > max_act) max_act = M * h->FEAT;
+    A("dense1", M * h->TD);
+    for (int layer = 1; layer <= 2; ++layer) {
+        char nm[32];
+        snprintf(nm, sizeof(nm), "xp%d", layer); A(nm, M * 2 * h->G * h->U);
+        snprintf(nm, sizeof(nm), "hs%d", layer); A(nm, M * 2 * h->U);
+        snprintf(nm, sizeof(nm), "gates%d", layer); A(nm, M * 2 * h->GS * h->U);
+    }
+    A("rnn1", M * h->U); A("rnn2drop", M * 2 * h->U);
+    A("logits", M * h->V); A("softmax", M * h->V); A("dlogits", M * h->V); A("loss", B);
+    // backward scratch
+    A("gA", max_act); A("gB", max_act);
+    A("dxp", M * 2 * h->G * h->U); A("hprev", M * 2 * h->U); A("rh", M * 2 * h->U);
+    A("UT", (int64_t)2 * h->G * h->U * h->U);
+    A("dtheta", B * 6); A("dd1", B * 50); A("dflat", B * h->sd.F);
+    L.add("act/stats", 2 * 512, 8); L.add("act/red", 2 * 512, 8); L.add("act/sumsq", 1, 8);
+    L.add("act/status", 1, 4, 1);
+    L.add("act/labels", B * c.max_len, 4, 1); L.add("act/label_len", B, 4, 1); L.add("act/input_len", B, 4, 1);
+    L.cursor = (L.cursor + 255) & ~(int64_t)255;
+}
+
+int pick_split(int M, int N, int K) {
+    long long ctas = (long long)ceil_div(M, 64) * ceil_div(N, 64);
+    int ktiles = ceil_div(K, 16);
+    long long s = (148 * 3 + ctas - 1) / ctas;
+    if (s > ktiles / 8) s = ktiles / 8;
+    if (s < 1) s = 1;
+    if (s > 256) s = 256;
+    return (int)s;
+}
+
+// C = A(MxK) @ B(KxN) + bias (, relu)
+int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias, int relu,
+            const float* sc, const float* sh, cudaStream_t st) {
+    GemmArgs g; g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.bias = bias; g.relu = relu; g.a_scale = sc; g.a_shift = sh;
+    return launch_gemm_simt(g, st);
+}
+// dW(KinxN) += X(MxKin)^T @ dY(MxN)   (reduction over rows M; split-K atomics into pre-zeroed dW)
+int gemm_tn(const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, int Kin, int N, int M, const float* sc, const float* sh, cudaStream_t st) {
+    GemmArgs g; g.A = X; g.B = dY; g.C = dW; g.M = Kin; g.N = N; g.K = M; g.lda = ldx; g.ldb = ldy; g.ldc = ldw;
+    g.transA = 1; g.a_scale = sc; g.a_shift = sh; g.split_k = pick_split(Kin, N, M);
+    if (g.split_k == 1) g.accumulate = 1;   // grads arena is pre-zeroed; keep += semantics either way
+    return launch_gemm_simt(g, st);
+}
+// dX(MxKin) (+)= dY(MxN) @ W(KinxN)^T
+int gemm_nt(const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int Kin, int N, int accumulate, cudaStream_t st) {
+    GemmArgs g; g.A = dY; g.B = Wt; g.C = dX; g.M = M; g.N = Kin; g.K = N; g.lda = ldy; g.ldb = ldw; g.ldc = ldx;
+    g.transB = 1; g.accumulate = accumulate;
+    return launch_gemm_simt(g, st);
+}
+
+std::string bnname(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b), "batch_normalization_%d/%s", bn, leaf); return b; }
+std::string actbn(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b), "bn%d/%s", bn, leaf); return b; }
+std::string nm(const char* fmt, int i) { char b[64]; snprintf(b, sizeof(b), fmt, i); return b; }
+
+int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool training, cudaStream_t st) {
+    double* stats = reinterpret_cast<double*>(h->a("stats"));
+    if (training) {
+        CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
+        TRY(launch_colstats(y, M, C, stats, st));
+    }
+    return launch_bn_finalize(stats, M, C, h->w(bnname(bn, "gamma")), h->w(bnname(bn, "beta")), h->w(bnname(bn, "moving_mean")),
+                              h->w(bnname(bn, "moving_variance")), kBnEps, kBnMomentum, training ? 1 : 0,
+                              h->a(actbn(bn, "scale")), h->a(actbn(bn, "shift")), h->a(actbn(bn, "mean")), h->a(actbn(bn, "invstd")), st);
+}
+
+int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed, cudaStream_t st) {
+    if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
+    const bool drop = training && seed != 0;
+    const int H = h->H, W = h->W, U = h->U, G = h->G, T = h->T, V = h->V;
+    // ---- STN (utils.py:247-258)
+    TRY(launch_stn_trunk_fwd(x, h->w("conv2d_1/kernel"), h->w("conv2d_1/bias"), h->w("conv2d_2/kernel"), h->w("conv2d_2/bias"),
+                             h->a("p1"), h->a("p2"), reinterpret_cast<int*>(h->a("p2arg")), h->a("flat"), B, H, W, st));
+    TRY(gemm_nn(h->a("flat"), h->sd.F, h->w("dense_1/kernel"), 50, h->a("loc_d1"), 50, B, 50, h->sd.F, h->w("dense_1/bias"), 1, nullptr, nullptr, st));
+    TRY(gemm_nn(h->a("loc_d1"), 50, h->w("dense_2/kernel"), 6, h->a("theta"), 6, B, 6, 50, h->w("dense_2/bias"), 0, nullptr, nullptr, st));
+    TRY(launch_stn_sample_fwd(x, h->a("theta"), h->a("a0"), B, H, W, 2, st));
+    // ---- depthwise-separable stack (utils.py:43-56, 64-70)
+    const float* in = h->a("a0");
+    int hh = h->Hp, ww = h->Wp;
+    for (int i = 1; i <= 7; ++i) {
+        const BlockPlan& b = kBlocks[i - 1];
+        const long long M = (long long)B * hh * ww;
+        float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
+        TRY(launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st));
+        TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st));
+        TRY(gemm_nn(dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
+                    h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), st));
+        TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st));
+        TRY(launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
+                                drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
+        hh /= b.ph; ww /= b.pw; in = out;
+    }
+    // ---- dense1 (utils.py:72-75): (B,T,9,512) is already (B*T, 4608) with feature = w*512+c
+    const int M = B * T;
+    TRY(gemm_nn(in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
+    if (drop) TRY(launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st));
+    // ---- two bidirectional recurrent layers (utils.py:77-82)
+    const float* rin = h->a("dense1"); int kin = h->TD;
+    for (int layer = 1; layer <= 2; ++layer) {
+        float* xp = h->a(nm("xp%d", layer)); float* hs = h->a(nm("hs%d", layer));
+        for (int d = 0; d < 2; ++d)
+            TRY(gemm_nn(rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
+                        h->w(h->rnn(layer, d) + "/bias"), 0, nullptr, nullptr, st));
+        TRY(launch_rnn_fwd(h->cfg.cell, xp, h->w(h->rnn(layer, 0) + "/recurrent_kernel"), h->w(h->rnn(layer, 1) + "/recurrent_kernel"),
+                           hs, training ? h->a(nm("gates%d", layer)) : nullptr, B, T, U, st));
+        if (layer == 1) { TRY(launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
+    }
+    const float* head_in = h->a("hs2");                                                                      // merge_mode='concat'
+    if (drop) {
+        CUDA_TRY(cudaMemcpyAsync(h->a("rnn2drop"), h->a("hs2"), sizeof(float) * (size_t)M * 2 * U, cudaMemcpyDeviceToDevice, st));
+        TRY(launch_dropout_fwd(h->a("rnn2drop"), (long long)M * 2 * U, kDropRnn, seed, 9, st));
+        head_in = h->a("rnn2drop");
+    }
+    // ---- dense2 + softmax (utils.py:85-86)
+    TRY(gemm_nn(head_in, 2 * U, h->w("dense2/kernel"), V, h->a("logits"), V, M, V, 2 * U, h->w("dense2/bias"), 0, nullptr, nullptr, st));
+    TRY(launch_softmax_rows(h->a("logits"), h->a("softmax"), M, V, st));
+    return CRNN_OK;
+}
+
+int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const float* rin, int kin, float* dx /*(M,kin)*/, int B, cudaStream_t st) {
+    const int U = h->U, G = h->G, T = h->T, M = B * T;
+    float* UT = h->a("UT"); float* dxp = h->a("dxp"); float* hprev = h->a("hprev"); float* rh = h->a("rh");
+    for (int d = 0; d < 2; ++d)
+        TRY(launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
+    TRY(launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
+    for (int d = 0; d < 2; ++d) {
+        const std::string base = h->rnn(layer, d);
+        const float* dxd = dxp + d * G * U;
+        float* gU = h->g(base + "/recurrent_kernel");
+        if (h->cfg.cell == CRNN_CELL_GRU) {
+            TRY(gemm_tn(hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, 2 * U, M, nullptr, nullptr, st));
+            TRY(gemm_tn(rh + d * U, 2 * U, dxd + 2 * U, 2 * G * U, gU + 2 * U, G * U, U, U, M, nullptr, nullptr, st));
+        } else {
+            TRY(gemm_tn(hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, G * U, M, nullptr, nullptr, st));
+        }
+        TRY(gemm_tn(rin, kin, dxd, 2 * G * U, h->g(base + "/kernel"), G * U, kin, G * U, M, nullptr, nullptr, st));
+        TRY(launch_colsum(dxd, M, G * U, 2 * G * U, h->g(base + "/bias"), st));
+        TRY(gemm_nt(dxd, 2 * G * U, h->w(base + "/kernel"), G * U, dx, kin, M, kin, G * U, d, st));
+    }
+    return CRNN_OK;
+}
+
+int backward(crnn_handle* h, const float* x, const int* labels, const int* label_len, const int* input_len, int B,
+             float* loss, uint64_t seed, cudaStream_t st) {
+    const bool drop = seed != 0;
+    const int U = h->U, T = h->T, V = h->V, M = B * T;
+    CUDA_TRY(cudaMemsetAsync(h->f("arena/grads"), 0, sizeof(float) * (size_t)h->n_params, st));
+    // ---- CTC (utils.py:98-103); mean over the batch (identity Keras loss, train.py:192) => scale 1/B
+    TRY(launch_ctc_loss_grad(h->a("softmax"), 2, labels, h->cfg.max_len, label_len, input_len, B, T, V, kKerasEps, loss, nullptr,
+                             h->a("dlogits"), 1.f / (float)B, reinterpret_cast<int*>(h->a("status")), st));
+    float* gA = h->a("gA"); float* gB = h->a("gB");
+    // ---- dense2
+    const float* head_in = drop ? h->a("rnn2drop") : h->a("hs2");
+    TRY(gemm_tn(head_in, 2 * U, h->a("dlogits"), V, h->g("dense2/kernel"), V, 2 * U, V, M, nullptr, nullptr, st));
+    TRY(launch_colsum(h->a("dlogits"), M, V, V, h->g("dense2/bias"), st));
+    TRY(gemm_nt(h->a("dlogits"), V, h->w("dense2/kernel"), V, gA, 2 * U, M, 2 * U, V, 0, st));
+    if (drop) TRY(launch_dropout_fwd(gA, (long long)M * 2 * U, kDropRnn, seed, 9, st));
+    // ---- recurrent layers
+    TRY(rnn_backward(h, 2, gA, h->a("rnn1"), U, gB, B, st));            // gB = d rnn1 (M,U)
+    TRY(launch_dup_dirs(gB, gA, M, U, st));                              // 'sum' merge: same gradient to both directions
+    TRY(rnn_backward(h, 1, gA, h->a("dense1"), h->TD, gB, B, st));      // gB = d dense1 (M,TD)
+    // ---- dense1
+    TRY(launch_relu_dropout_bwd(gB, h->a("dense1"), (long long)M * h->TD, drop ? kDropDense1 : 0.f, seed, 8, st));
+    TRY(gemm_tn(h->a("block7"), h->FEAT, gB, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, st));
+    TRY(launch_colsum(gB, M, h->TD, h->TD, h->g("dense1/bias"), st));
+    TRY(gemm_nt(gB, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
+    // ---- conv stack, reverse
+    float* cur = gA; float* other = gB;
+    int dims_h[8], dims_w[8];
+    dims_h[1] = h->Hp; dims_w[1] = h->Wp;
+    for (int i = 1; i < 7; ++i) { dims_h[i + 1] = dims_h[i] / kBlocks[i - 1].ph; dims_w[i + 1] = dims_w[i] / kBlocks[i - 1].pw; }
+    double* red = reinterpret_cast<double*>(h->a("red"));
+    for (int i = 7; i >= 1; --i) {
+        const BlockPlan& b = kBlocks[i - 1];
+        const int hh = dims_h[i], ww = dims_w[i];
+        const long long Mi = (long long)B * hh * ww;
+        const float* dw = h->a(nm("dw%d", i)); const float* pw = h->a(nm("pw%d", i));
+        const int bn1 = 2 * i - 1, bn2 = 2 * i;
+        CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cout, st));
+        TRY(launch_act_pool_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
+                                other, red, B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
+        TRY(launch_bn_bwd_apply(other, pw, red, h->w(bnname(bn2, "gamma")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
+                                h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")), Mi, b.cout, st));
+        TRY(gemm_tn(dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
+                    h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
+        TRY(gemm_nt(other, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, cur, b.cin, (int)Mi, b.cin, b.cout, 0, st));
+        CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cin, st));
+        TRY(launch_relu6_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+                             cur, red, Mi, b.cin, st));
+        TRY(launch_bn_bwd_apply(cur, dw, red, h->w(bnname(bn1, "gamma")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+                                h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
+        const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
+        TRY(launch_dwconv_bwd_weight(bin, cur, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, st));
+        TRY(launch_dwconv_bwd_data(cur, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
+        float* t = cur; cur = other; other = t;
+    }
+    // ---- STN: sampler -> theta -> localisation net
+    CUDA_TRY(cudaMemsetAsync(h->a("dtheta"), 0, sizeof(float) * 6 * B, st));
+    TRY(launch_stn_sample_bwd(x, h->a("theta"), cur, h->a("dtheta"), B, h->H, h->W, 2, st));
+    TRY(gemm_tn(h->a("loc_d1"), 50, h->a("dtheta"), 6, h->g("dense_2/kernel"), 6, 50, 6, B, nullptr, nullptr, st));
+    TRY(launch_colsum(h->a("dtheta"), B, 6, 6, h->g("dense_2/bias"), st));
+    TRY(gemm_nt(h->a("dtheta"), 6, h->w("dense_2/kernel"), 6, h->a("dd1"), 50, B, 50, 6, 0, st));
+    TRY(launch_relu_dropout_bwd(h->a("dd1"), h->a("loc_d1"), (long long)B * 50, 0.f, 0, 0, st));
+    TRY(gemm_tn(h->a("flat"), h->sd.F, h->a("dd1"), 50, h->g("dense_1/kernel"), 50, h->sd.F, 50, B, nullptr, nullptr, st));
+    TRY(launch_colsum(h->a("dd1"), B, 50, 50, h->g("dense_1/bias"), st));
+    TRY(gemm_nt(h->a("dd1"), 50, h->w("dense_1/kernel"), 50, h->a("dflat"), h->sd.F, B, h->sd.F, 50, 0, st));
+    TRY(launch_stn_trunk_bwd(h->a("dflat"), h->a("p1"), h->a("p2"), reinterpret_cast<const int*>(h->a("p2arg")), h->w("conv2d_2/kernel"),
+                             h->g("conv2d_1/kernel"), h->g("conv2d_1/bias"), h->g("conv2d_2/kernel"), h->g("conv2d_2/bias"), nullptr, B, h->H, h->W, st));
+    return CRNN_OK;
+}
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+const char* crnn_last_error(void) { return g_err; }
+const char* crnn_version(void) { return "crnn_b200 0.1 (sm_100a)"; }
+
+int crnn_workspace_bytes(const crnn_config* cfg, size_t* bytes) {
+    TRY(validate(cfg));
+    crnn_handle tmp; tmp.cfg = *cfg; plan(&tmp);
+    *bytes = (size_t)tmp.L.cursor;
+    return CRNN_OK;
+}
+
+int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes, crnn_handle** out) {
+    TRY(validate(cfg));
+    if (!workspace || !out) { crnn_set_error("null workspace/out"); return CRNN_ERR_INVALID; }
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) { crnn_set_error("workspace must be 256-byte aligned"); return CRNN_ERR_INVALID; }
+    crnn_handle* h = new crnn_handle(); h->cfg = *cfg; plan(h);
+    if ((size_t)h->L.cursor > workspace_bytes) { crnn_set_error("workspace too small: need %lld bytes", (long long)h->L.cursor); delete h; return CRNN_ERR_NOMEM; }
+    h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
+    *out = h;
+    return CRNN_OK;
+}
+int crnn_destroy(crnn_handle* h) { delete h; return CRNN_OK; }
+int crnn_num_tensors(const crnn_handle* h) { return h ? (int)h->L.tensors.size() : 0; }
+const char* crnn_tensor_name(const crnn_handle* h, int i) { return (h && i >= 0 && i < (int)h->L.tensors.size()) ? h->L.tensors[i].name.c_str() : nullptr; }
+int crnn_tensor_lookup(const crnn_handle* h, const char* name, crnn_tensor_info* out) {
+    if (!h || !name || !out) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    auto it = h->L.index.find(name);
+    if (it == h->L.index.end()) { crnn_set_error("unknown tensor '%s'", name); return CRNN_ERR_UNKNOWN_NAME; }
+    const Tensor& t = h->L.tensors[it->second];
+    out->offset = t.offset; out->numel = t.numel; out->is_int = t.is_int;
+    return CRNN_OK;
+}
+
+int crnn_forward(crnn_handle* h, const float* x_dev, int B, float* softmax_dev, void* stream) {
+    if (!h || !x_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(forward(h, x_dev, B, false, 0, st));
+    if (softmax_dev && softmax_dev != h->a("softmax"))
+        CUDA_TRY(cudaMemcpyAsync(softmax_dev, h->a("softmax"), sizeof(float) * (size_t)B * h->T * h->V, cudaMemcpyDeviceToDevice, st));
+    return CRNN_OK;
+}
+int crnn_forward_host(crnn_handle* h, const float* x_host, int B, float* softmax_host, void* stream) {
+    if (!h || !x_host || !softmax_host) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(h->a("x"), x_host, sizeof(float) * (size_t)B * h->H * h->W, cudaMemcpyHostToDevice, st));
+    TRY(forward(h, h->a("x"), B, false, 0, st));
+    CUDA_TRY(cudaMemcpyAsync(softmax_host, h->a("softmax"), sizeof(float) * (size_t)B * h->T * h->V, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CRNN_OK;
+}
+
+int crnn_train_fwd_bwd(crnn_handle* h, const float* x_dev, const int32_t* labels_dev, const int32_t* label_len_dev,
+                       const int32_t* input_len_dev, int B, float* loss_dev, uint64_t dropout_seed, void* stream) {
+    if (!h || !x_dev || !labels_dev || !label_len_dev || !input_len_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(forward(h, x_dev, B, true, dropout_seed, st));
+    return backward(h, x_dev, labels_dev, label_len_dev, input_len_dev, B, loss_dev ? loss_dev : h->a("loss"), dropout_seed, st);
+}
+
+int crnn_adam_step(crnn_handle* h, float lr, float b1, float b2, float eps, float clipnorm, float grad_scale, void* stream) {
+    if (!h) { crnn_set_error("null handle"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* ss = reinterpret_cast<double*>(h->a("sumsq"));
+    CUDA_TRY(cudaMemsetAsync(ss, 0, sizeof(double), st));
+    TRY(launch_sumsq(h->f("arena/grads"), h->n_params, ss, st));
+    const double t = (double)(h->iterations + 1);
+    const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+    TRY(launch_adam(h->f("arena/params"), h->f("arena/grads"), h->f("arena/opt_m"), h->f("arena/opt_v"), h->n_params, ss, clipnorm, lr_t, b1, b2, eps, grad_scale, st));
+    h->iterations += 1;
+    return CRNN_OK;
+}
+int crnn_sgd_step(crnn_handle* h, float lr, float decay, float momentum, float clipnorm, float grad_scale, void* stream) {
+    if (!h) { crnn_set_error("null handle"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* ss = reinterpret_cast<double*>(h->a("sumsq"));
+    CUDA_TRY(cudaMemsetAsync(ss, 0, sizeof(double), st));
+    TRY(launch_sumsq(h->f("arena/grads"), h->n_params, ss, st));
+    const float lr_i = (float)((double)lr * (1.0 / (1.0 + (double)decay * (double)h->iterations)));
+    TRY(launch_sgd_nesterov(h->f("arena/params"), h->f("arena/grads"), h->f("arena/opt_m"), h->n_params, ss, clipnorm, lr_i, momentum, grad_scale, st));
+    h->iterations += 1;
+    return CRNN_OK;
+}
+int crnn_get_iterations(const crnn_handle* h, int64_t* it) { if (!h || !it) return CRNN_ERR_INVALID; *it = h->iterations; return CRNN_OK; }
+int crnn_set_iterations(crnn_handle* h, int64_t it) { if (!h) return CRNN_ERR_INVALID; h->iterations = it; return CRNN_OK; }
+int crnn_ctc_status(crnn_handle* h, int32_t* status_host, void* stream) {
+    if (!h || !status_host) return CRNN_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(status_host, h->a("status"), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CRNN_OK;
+}
+
+int crnn_ctc_loss_grad(const float* probs_dev, int B, int T, int V, int t_off, const int32_t* labels_dev, int max_len,
+                       const int32_t* label_len_dev, const int32_t* input_len_dev, float eps, float* loss_dev, float* grad_u_dev,
+                       float* grad_logits_dev, float scale, int32_t* status_dev, void* stream) {
+    if (!probs_dev || !labels_dev || !label_len_dev || !input_len_dev || !loss_dev || !status_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    return launch_ctc_loss_grad(probs_dev, t_off, labels_dev, max_len, label_len_dev, input_len_dev, B, T, V, eps, loss_dev, grad_u_dev,
+                                grad_logits_dev, scale, status_dev, static_cast<cudaStream_t>(stream));
+}
+int crnn_ctc_greedy(const float* probs_dev, const int32_t* seq_len_dev, int B, int T, int V, float eps, int32_t* out_dev, int32_t* out_len_dev,
+                    float* score_dev, void* stream) {
+    if (!probs_dev || !out_dev || !out_len_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    return launch_ctc_greedy(probs_dev, seq_len_dev, B, T, V, eps, out_dev, out_len_dev, score_dev, static_cast<cudaStream_t>(stream));
+}
+int crnn_ctc_beam(const float* probs_dev, const int32_t* seq_len_dev, int B, int T, int V, float eps, int beam_width, int merge_repeated,
+                  int32_t* out_dev, int32_t* out_len_dev, float* logprob_dev, void* stream) {
+    if (!probs_dev || !out_dev || !out_len_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    return launch_ctc_beam(probs_dev, seq_len_dev, B, T, V, eps, beam_width, merge_repeated, out_dev, out_len_dev, logprob_dev, static_cast<cudaStream_t>(stream));
+}
+
+static int decode_host(bool beam, const float* probs_host, int B, int T, int V, float eps, int beam_width, int merge_repeated,
+                       int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream) {
+    if (!probs_host || !out_host || !out_len_host) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    if (B <= 0) return CRNN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t np = (size_t)B * T * V, no = (size_t)B * T;
+    float* dp = nullptr; int32_t* dout = nullptr; int32_t* dlen = nullptr; float* dsc = nullptr;
+    CUDA_TRY(cudaMallocAsync(&dp, sizeof(float) * np, st));
+    CUDA_TRY(cudaMallocAsync(&dout, sizeof(int32_t) * no, st));
+    CUDA_TRY(cudaMallocAsync(&dlen, sizeof(int32_t) * B, st));
+    CUDA_TRY(cudaMallocAsync(&dsc, sizeof(float) * B, st));
+    CUDA_TRY(cudaMemcpyAsync(dp, probs_host, sizeof(float) * np, cudaMemcpyHostToDevice, st));
+    int rc = beam ? launch_ctc_beam(dp, nullptr, B, T, V, eps, beam_width, merge_repeated, dout, dlen, dsc, st)
+                  : launch_ctc_greedy(dp, nullptr, B, T, V, eps, dout, dlen, dsc, st);
+    if (rc == CRNN_OK) {
+        CUDA_TRY(cudaMemcpyAsync(out_host, dout, sizeof(int32_t) * no, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out_len_host, dlen, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+        if (score_host) CUDA_TRY(cudaMemcpyAsync(score_host, dsc, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+    }
+    cudaFreeAsync(dp, st); cudaFreeAsync(dout, st); cudaFreeAsync(dlen, st); cudaFreeAsync(dsc, st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return rc;
+}
+int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, int beam_width, int merge_repeated,
+                       int32_t* out_host, int32_t* out_len_host, float* logprob_host, void* stream) {
+    return decode_host(true, probs_host, B, T, V, eps, beam_width, merge_repeated, out_host, out_len_host, logprob_host, stream);
+}
+int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps, int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream) {
+    return decode_host(false, probs_host, B, T, V, eps, 0, 1, out_host, out_len_host, score_host, stream);
+}
+
+int crnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+              const float* a_scale, const float* a_shift, const float* bias, int relu, int split_k, void* stream) {
+    GemmArgs g; g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.transA = transA; g.transB = transB; g.a_scale = a_scale; g.a_shift = a_shift; g.bias = bias; g.relu = relu; g.split_k = split_k;
+    return launch_gemm_simt(g, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

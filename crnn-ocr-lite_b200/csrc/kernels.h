@@ -1,0 +1,85 @@
+// kernels.h -- internal launcher prototypes (host side) for the CRNN hot-path kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+struct GemmArgs {
+    const float* A = nullptr; const float* B = nullptr; float* C = nullptr;
+    int M = 0, N = 0, K = 0;
+    int lda = 0, ldb = 0, ldc = 0;
+    int transA = 0, transB = 0;
+    const float* a_scale = nullptr; const float* a_shift = nullptr;  // A <- relu6(A*scale[ch]+shift[ch])
+    const float* bias = nullptr;
+    int relu = 0;
+    int accumulate = 0;   // C += result (non split-K)
+    int split_k = 1;      // >1: atomicAdd into pre-zeroed C
+};
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
+
+// ---- ctc.cu ----
+int launch_ctc_loss_grad(const float* probs, int t_off, const int* labels, int maxL, const int* label_len,
+                         const int* input_len, int B, int T, int V, float eps, float* loss, float* grad_u,
+                         float* grad_logits, float scale, int* status, cudaStream_t st);
+int launch_ctc_greedy(const float* probs, const int* seq_len, int B, int T, int V, float eps,
+                      int* out, int* out_len, float* score, cudaStream_t st);
+int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V, float eps, int W, int merge_repeated,
+                    int* out, int* out_len, float* logprob, cudaStream_t st);
+
+// ---- conv.cu (depthwise conv, BN statistics, activation/pool, elementwise) ----
+int launch_dwconv_fwd(const float* x, const float* k33c, float* y, int B, int H, int W, int C, cudaStream_t st);
+int launch_dwconv_bwd_data(const float* dy, const float* k33c, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st);
+int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
+// per-channel sum / sum of squares over rows of y[M][C] -> stats[0..C) , stats[C..2C) (double, pre-zeroed)
+int launch_colstats(const float* y, long long M, int C, double* stats, cudaStream_t st);
+// training: batch stats -> scale/shift (+ saved mean / inv-std, moving-stat update); inference: moving stats
+int launch_bn_finalize(const double* stats, long long M, int C, const float* gamma, const float* beta,
+                       float* moving_mean, float* moving_var, float eps, float momentum, int training,
+                       float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);
+// a = dropout(pool(relu6(y*scale+shift)))  ; pool (ph,pw) in {(1,1),(2,2),(1,2)}
+int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C,
+                        int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+// dz = unpool(da * dropmask) * 1[0 <= z <= 6] with z = y*scale+shift ; also accumulates sum(dz), sum(dz*xhat) (double[2C], pre-zeroed)
+int launch_act_pool_bwd(const float* da, const float* y, const float* scale, const float* shift,
+                        const float* save_mean, const float* save_invstd, float* dz, double* red,
+                        int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+// dz = da * 1[0<=z<=6] (no pool/dropout), z = y*scale+shift, + reductions  (the BN after the depthwise conv)
+int launch_relu6_bwd(const float* da, const float* y, const float* scale, const float* shift,
+                     const float* save_mean, const float* save_invstd, float* dz, double* red, long long M, int C, cudaStream_t st);
+// BN training backward: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) in place; dgamma = sum(dz*xhat), dbeta = sum(dz)
+int launch_bn_bwd_apply(float* dz_inout, const float* y, const double* red, const float* gamma, const float* save_mean,
+                        const float* save_invstd, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
+// misc elementwise
+int launch_colsum(const float* y, long long M, int C, int ldy, float* out, cudaStream_t st);            // out[c] = sum_m y[m][c]
+int launch_relu_dropout_bwd(float* g_inout, const float* act, long long n, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+int launch_dropout_fwd(float* x_inout, long long n, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+int launch_sum_dirs(const float* hs, float* out, long long rows, int U, cudaStream_t st);               // out[r][u] = hs[r][0][u]+hs[r][1][u]
+int launch_dup_dirs(const float* g, float* out, long long rows, int U, cudaStream_t st);                // out[r][d][u] = g[r][u]
+int launch_softmax_rows(const float* z, float* p, long long rows, int V, cudaStream_t st);
+int launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);                       // out[C][R] = in[R][C]^T
+
+// ---- stn.cu ----
+struct StnDims { int H, W, H1, W1, P1h, P1w, C1h, C1w, P2h, P2w, C2h, C2w, F; };
+StnDims stn_dims(int H, int W);
+// locnet conv trunk: x (B,H,W) -> p1 (B,P1h,P1w) , p2 (B,P2h,P2w,20) [+argmax idx], flat (B,F)
+int launch_stn_trunk_fwd(const float* x, const float* k1, const float* b1, const float* k2, const float* b2,
+                         float* p1, float* p2, int* p2arg, float* flat, int B, int H, int W, cudaStream_t st);
+int launch_stn_trunk_bwd(const float* dflat, const float* p1, const float* p2, const int* p2arg, const float* k2,
+                         float* dk1, float* db1, float* dk2, float* db2, float* scratch_dc1, int B, int H, int W, cudaStream_t st);
+// sampler: x (B,H,W), theta (B,6) -> padded out (B,H+2*pad,W+2*pad) (border zeroed)
+int launch_stn_sample_fwd(const float* x, const float* theta, float* out, int B, int H, int W, int pad, cudaStream_t st);
+int launch_stn_sample_bwd(const float* x, const float* theta, const float* dout_padded, float* dtheta, int B, int H, int W, int pad, cudaStream_t st);
+
+// ---- rnn.cu ----
+// xp (B,T,2,G*U) input projections (+bias), U0/U1 (U,G*U) recurrent kernels of the two directions; hs (B,T,2,U) outputs; gates (B,T,2,GS*U) saved for BPTT (may be null)
+int launch_rnn_fwd(int cell, const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, int U, cudaStream_t st);
+// dout (B,T,2,U) gradient wrt hs; UcatT (2,G*U,U) transposed recurrent kernels; outputs dxp (B,T,2,G*U), hprev (B,T,2,U), rh (B,T,2,U) (GRU only)
+int launch_rnn_bwd(int cell, const float* dout, const float* hs, const float* gates, const float* UcatT,
+                   float* dxp, float* hprev, float* rh, int B, int T, int U, cudaStream_t st);
+
+// ---- optim.cu ----
+int launch_sumsq(const float* g, long long n, double* out /*pre-zeroed*/, cudaStream_t st);
+int launch_adam(float* w, const float* g, float* m, float* v, long long n, const double* sumsq, float clipnorm,
+                float lr_t, float b1, float b2, float eps, float gscale, cudaStream_t st);
+int launch_sgd_nesterov(float* w, const float* g, float* vel, long long n, const double* sumsq, float clipnorm,
+                        float lr_i, float momentum, float gscale, cudaStream_t st);

@@ -1,0 +1,111 @@
+"""CTC stage of the reference behind its own names (gasparian/CRNN-OCR-lite utils.py:98-103, 314-321, 331-357):
+ctc_batch_cost / ctc_decode on the B200 kernels (csrc/ctc.cu) + DecodeCTCPred / labels_to_text."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+K_EPS = 1e-7   # keras.backend.epsilon()
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def ctc_batch_cost_device(probs, labels, label_len, input_len, t_off=0, want_grad_u=False, want_grad_logits=False, scale=1.0):
+    """K.ctc_batch_cost on probs[:, t_off:, :] (utils.py:102-103).  probs (B,T,V) CUDA f32; labels (B,maxL) i32."""
+    lib = _lib.load()
+    B, T, V = probs.shape
+    assert probs.is_cuda and probs.dtype == torch.float32 and probs.is_contiguous()
+    labels = labels.to(torch.int32).contiguous(); label_len = label_len.to(torch.int32).contiguous().view(-1)
+    input_len = input_len.to(torch.int32).contiguous().view(-1)
+    dev = probs.device
+    loss = torch.empty(B, dtype=torch.float32, device=dev)
+    gu = torch.empty(B, T - t_off, V, dtype=torch.float32, device=dev) if want_grad_u else None
+    gz = torch.empty(B, T, V, dtype=torch.float32, device=dev) if want_grad_logits else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(lib.crnn_ctc_loss_grad(_ptr(probs), B, T, V, t_off, _ptr(labels), labels.shape[1], _ptr(label_len), _ptr(input_len),
+                                      K_EPS, _ptr(loss), _ptr(gu), _ptr(gz), float(scale), _ptr(status), _stream(dev)))
+    st = int(status.item())
+    if st != 0:
+        raise ValueError(f"Not enough time for target transition sequence (batch element {-st - 1})")
+    if want_grad_u or want_grad_logits:
+        return loss, gu, gz
+    return loss
+
+
+def ctc_decode_device(probs, seq_len=None, greedy=True, beam_width=100, merge_repeated=True):
+    """K.ctc_decode(y_pred, input_length, greedy, beam_width, top_paths=1): returns (dense (B,T) padded -1, lengths, score)."""
+    lib = _lib.load()
+    B, T, V = probs.shape
+    assert probs.is_cuda and probs.dtype == torch.float32 and probs.is_contiguous()
+    dev = probs.device
+    out = torch.empty(B, T, dtype=torch.int32, device=dev)
+    n = torch.empty(B, dtype=torch.int32, device=dev)
+    score = torch.empty(B, dtype=torch.float32, device=dev)
+    sl = seq_len.to(torch.int32).contiguous() if seq_len is not None else None
+    if greedy:
+        _lib.check(lib.crnn_ctc_greedy(_ptr(probs), _ptr(sl), B, T, V, K_EPS, _ptr(out), _ptr(n), _ptr(score), _stream(dev)))
+    else:
+        _lib.check(lib.crnn_ctc_beam(_ptr(probs), _ptr(sl), B, T, V, K_EPS, int(beam_width), int(bool(merge_repeated)),
+                                     _ptr(out), _ptr(n), _ptr(score), _stream(dev)))
+    return out, n, score
+
+
+def ctc_decode_host(probs, greedy=False, beam_width=10, merge_repeated=True):
+    """Host numpy (N,T,V) softmax -> host numpy labels: H2D + decode + D2H inside the C ABI call."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.CrnnError("ctc_decode needs a CUDA device: no CPU fallback on this path")
+    probs = np.ascontiguousarray(probs, np.float32)
+    B, T, V = probs.shape
+    out = np.empty((B, T), np.int32); n = np.empty(B, np.int32); score = np.empty(B, np.float32)
+    st = _stream(torch.device("cuda", torch.cuda.current_device()))
+    if greedy:
+        _lib.check(lib.crnn_ctc_greedy_host(probs.ctypes.data, B, T, V, K_EPS, out.ctypes.data, n.ctypes.data, score.ctypes.data, st))
+    else:
+        _lib.check(lib.crnn_ctc_beam_host(probs.ctypes.data, B, T, V, K_EPS, int(beam_width), int(bool(merge_repeated)),
+                                          out.ctypes.data, n.ctypes.data, score.ctypes.data, st))
+    return out, n, score
+
+
+def labels_to_text(labels, inverse_classes=None):
+    """utils.py:314-321."""
+    ret = []
+    for c in labels:
+        if c == len(inverse_classes) or c == -1:
+            ret.append("")
+        else:
+            ret.append(str(inverse_classes[c]))
+    return "".join(ret)
+
+
+class DecodeCTCPred:
+    """utils.py:331-357: same constructor / decode(result) contract (top-1 strings), one batched GPU beam search
+    instead of one TF graph + CPU op per sample.  `greedy=True` is an added switch (BASELINE configs[0,1])."""
+
+    def __init__(self, top_paths=1, beam_width=5, inverse_classes=None, greedy=False):
+        self.top_paths = top_paths
+        self.beam_width = beam_width
+        self.inverse_classes = inverse_classes
+        self.greedy = greedy
+
+    def labels_to_text(self, labels):
+        return labels_to_text(labels, self.inverse_classes)
+
+    def decode(self, result):
+        if self.top_paths != 1:
+            raise NotImplementedError("only top_paths=1 (what predict.py:111 uses)")
+        if self.beam_width < self.top_paths:
+            self.beam_width = self.top_paths
+        result = np.asarray(result, np.float32)
+        if result.ndim == 2:
+            result = result[None]
+        labels, n, _ = ctc_decode_host(result, greedy=self.greedy, beam_width=self.beam_width, merge_repeated=True)
+        return [self.labels_to_text(labels[i, :n[i]]) for i in range(labels.shape[0])]

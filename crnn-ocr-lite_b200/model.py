@@ -1,0 +1,390 @@
+"""Host-side mirror of the reference's model surface (gasparian/CRNN-OCR-lite utils.py:32-96, 300-329) over the
+B200 C ABI (include/crnn_b200.h).  PyTorch is used only as the device allocator / stream provider / NCCL plumbing.
+
+    CRNN(num_classes, max_string_len, shape, time_dense_size, GRU, n_units).get_model() -> CRNNModel
+    CRNNModel: load_weights / save_weights / get_weights / set_weights / to_json / summary / compile /
+               predict_on_batch / predict_generator / train_on_batch / fit_generator / save
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import hdf5_lite
+
+BLOCK_PLAN = [(1, 64, None), (64, 128, None), (128, 256, (2, 2)), (256, 256, None), (256, 512, (1, 2)), (512, 512, None), (512, 512, None)]
+
+
+def _cell_name(gru):
+    return "gru" if gru else "lstm"
+
+
+def weight_shapes(imgh, imgw, num_classes, cell, n_units=256, time_dense=128):
+    """Keras `layer_names`/`weight_names` order and shapes of models/<name>/final_weights.h5."""
+    s = OrderedDict()
+    p1h, p1w = imgh // 2, imgw // 2
+    c2h, c2w = (p1h - 4) // 2 - 4, (p1w - 4) // 2 - 4
+    s["conv2d_1/kernel"] = (5, 5, 1, 20); s["conv2d_1/bias"] = (20,)
+    s["conv2d_2/kernel"] = (5, 5, 20, 20); s["conv2d_2/bias"] = (20,)
+    s["dense_1/kernel"] = (c2h * c2w * 20, 50); s["dense_1/bias"] = (50,)
+    s["dense_2/kernel"] = (50, 6); s["dense_2/bias"] = (6,)
+    for i, (cin, cout, _) in enumerate(BLOCK_PLAN, 1):
+        s[f"depthwise_conv2d_{i}/depthwise_kernel"] = (3, 3, cin, 1)
+        for nm in ("gamma", "beta", "moving_mean", "moving_variance"):
+            s[f"batch_normalization_{2 * i - 1}/{nm}"] = (cin,)
+        s[f"conv2d_{i + 2}/kernel"] = (1, 1, cin, cout)
+        for nm in ("gamma", "beta", "moving_mean", "moving_variance"):
+            s[f"batch_normalization_{2 * i}/{nm}"] = (cout,)
+    feat = ((imgw + 4) // 4) * 512
+    s["dense1/kernel"] = (feat, time_dense); s["dense1/bias"] = (time_dense,)
+    g = 3 if cell == "gru" else 4
+    for layer, cin in ((1, time_dense), (2, n_units)):
+        for d in ("forward", "backward"):
+            base = f"bidirectional_{layer}/{d}_{cell}_{layer}"
+            s[base + "/kernel"] = (cin, g * n_units); s[base + "/recurrent_kernel"] = (n_units, g * n_units); s[base + "/bias"] = (g * n_units,)
+    s["dense2/kernel"] = (2 * n_units, num_classes); s["dense2/bias"] = (num_classes,)
+    return s
+
+
+def keras_initial_weights(shapes, cell, n_units=256, seed=None):
+    """Keras default initialisers for a freshly built model (train.py:168 before load_weights)."""
+    rng = np.random.default_rng(seed)
+    w = OrderedDict()
+    for name, shp in shapes.items():
+        leaf = name.split("/")[-1]
+        if leaf in ("bias", "beta", "moving_mean"):
+            a = np.zeros(shp, np.float32)
+            if leaf == "bias" and "lstm" in name:
+                a[n_units:2 * n_units] = 1.0  # unit_forget_bias
+        elif leaf in ("gamma", "moving_variance"):
+            a = np.ones(shp, np.float32)
+        elif leaf == "recurrent_kernel":
+            blocks = []
+            for _ in range(shp[1] // shp[0]):
+                q, r = np.linalg.qr(rng.standard_normal((shp[0], shp[0])))
+                blocks.append(q * np.sign(np.diag(r)))
+            a = np.concatenate(blocks, 1).astype(np.float32)
+        else:
+            if leaf == "depthwise_kernel":
+                fan_in, fan_out = 9 * shp[2], 9
+            elif len(shp) == 4:
+                fan_in, fan_out = shp[0] * shp[1] * shp[2], shp[0] * shp[1] * shp[3]
+            else:
+                fan_in, fan_out = shp
+            if name.startswith("bidirectional") or name.startswith("dense2"):   # he_normal (utils.py:78-85)
+                a = np.clip(rng.standard_normal(shp), -2, 2) * (math.sqrt(2.0 / fan_in) / 0.87962566103423978)
+            else:                                                                 # glorot_uniform
+                lim = math.sqrt(6.0 / (fan_in + fan_out))
+                a = rng.uniform(-lim, lim, shp)
+            a = a.astype(np.float32)
+        w[name] = a
+    w["dense_2/kernel"][:] = 0                                                    # get_initial_weights, utils.py:239-245
+    w["dense_2/bias"][:] = np.array([1, 0, 0, 0, 1, 0], np.float32)
+    return w
+
+
+class Adam:
+    """keras.optimizers.Adam subset used by train.py:188."""
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, clipnorm=0.0, **_):
+        self.kind, self.lr, self.beta_1, self.beta_2, self.epsilon, self.clipnorm = "adam", lr, beta_1, beta_2, epsilon, clipnorm
+
+
+class SGD:
+    """keras.optimizers.SGD subset used by train.py:190."""
+    def __init__(self, lr=0.01, decay=0.0, momentum=0.0, nesterov=False, clipnorm=0.0, **_):
+        if not nesterov:
+            raise NotImplementedError("only the reference's nesterov=True SGD is implemented")
+        self.kind, self.lr, self.decay, self.momentum, self.clipnorm = "sgd", lr, decay, momentum, clipnorm
+
+
+class _History:
+    def __init__(self):
+        self.history = {"loss": []}
+
+
+class CRNNModel:
+    def __init__(self, num_classes, max_string_len, shape, time_dense_size, gru, n_units, max_batch=64, device=None, seed=None):
+        if not torch.cuda.is_available():
+            raise _lib.CrnnError("CRNNModel needs a CUDA device: this path has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.imgh, self.imgw = int(shape[0]), int(shape[1])
+        self.num_classes, self.max_len = int(num_classes), int(max_string_len)
+        self.cell = _cell_name(gru)
+        self.n_units, self.time_dense = int(n_units), int(time_dense_size)
+        self.max_batch = int(max_batch)
+        self.T = (self.imgh + 4) // 2
+        self.cfg = _lib.CrnnConfig(self.imgh, self.imgw, self.num_classes, _lib.CRNN_CELL_GRU if gru else _lib.CRNN_CELL_LSTM,
+                                   self.n_units, self.time_dense, self.max_len, self.max_batch)
+        nbytes = ctypes.c_size_t()
+        _lib.check(self.lib.crnn_workspace_bytes(ctypes.byref(self.cfg), ctypes.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self.workspace = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        self.handle = ctypes.c_void_p()
+        _lib.check(self.lib.crnn_create(ctypes.byref(self.cfg), self.workspace.data_ptr(), nbytes.value, ctypes.byref(self.handle)))
+        self.shapes = weight_shapes(self.imgh, self.imgw, self.num_classes, self.cell, self.n_units, self.time_dense)
+        self.optimizer = None
+        self.stop_training = False
+        self.dropout = True
+        self._step_seed = np.random.SeedSequence(seed).generate_state(1, np.uint64)[0] | 1
+        self._pinned = {}
+        self.set_weights(keras_initial_weights(self.shapes, self.cell, self.n_units, seed))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.crnn_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ tensors
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def tensor(self, name) -> torch.Tensor:
+        """Torch view (no copy) of a named tensor of the workspace: weights, 'grad/<w>', 'act/<x>', 'arena/<a>'."""
+        info = _lib.TensorInfo()
+        _lib.check(self.lib.crnn_tensor_lookup(self.handle, name.encode(), ctypes.byref(info)))
+        raw = self.workspace[info.offset: info.offset + info.numel * 4]
+        return raw.view(torch.int32 if info.is_int else torch.float32)
+
+    def tensor_names(self):
+        return [self.lib.crnn_tensor_name(self.handle, i).decode() for i in range(self.lib.crnn_num_tensors(self.handle))]
+
+    def set_weights(self, weights):
+        for name, shp in self.shapes.items():
+            if name not in weights:
+                raise KeyError(f"missing weight {name}")
+            a = np.ascontiguousarray(weights[name], np.float32)
+            if tuple(a.shape) != tuple(shp):
+                raise ValueError(f"{name}: shape {a.shape} != {shp}")
+            self.tensor(name).copy_(torch.from_numpy(a.reshape(-1)))
+
+    def get_weights(self):
+        return OrderedDict((n, self.tensor(n).cpu().numpy().reshape(s).copy()) for n, s in self.shapes.items())
+
+    def get_grads(self):
+        return OrderedDict((n, self.tensor("grad/" + n).cpu().numpy().reshape(s).copy()) for n, s in self.shapes.items()
+                           if not n.endswith(("moving_mean", "moving_variance")))
+
+    def activation(self, name, B=None):
+        return self.tensor("act/" + name).cpu().numpy()
+
+    # ------------------------------------------------------------------ Keras-compatible weight I/O
+    def load_weights(self, path):
+        """model.load_weights(path) of the reference (utils.py:305,328; train.py:171): Keras-2.2.2 HDF5 layout."""
+        self.set_weights(hdf5_lite.load_keras_weights(path))
+
+    def _keras_layers(self):
+        layers = OrderedDict()
+        w = self.get_weights()
+        for name, arr in w.items():
+            layer, leaf = name.split("/", 1)
+            layers.setdefault(layer, OrderedDict())[f"{layer}/{leaf}:0"] = arr
+        return layers
+
+    def save_weights(self, path):
+        """model.save_weights (train.py:215), readable by Keras 2.2.2 / h5py and by load_weights above."""
+        hdf5_lite.save_keras_weights(path, self._keras_layers())
+
+    def save(self, path):
+        """model.save (train.py:216): weights + optimizer moments + training_config in one file."""
+        extra = {"training_config": json.dumps(self._training_config()), "model_config": self.to_json()}
+        layers = self._keras_layers()
+        if self.optimizer is not None and self.optimizer.kind == "adam":
+            opt = OrderedDict()
+            opt["Adam/iterations:0"] = np.array([self.iterations()], np.float32)
+            for n, s in self.shapes.items():
+                if n.endswith(("moving_mean", "moving_variance")):
+                    continue
+                opt[f"training/Adam/m/{n}:0"] = self.tensor("adam_m/" + n).cpu().numpy().reshape(s)
+                opt[f"training/Adam/v/{n}:0"] = self.tensor("adam_v/" + n).cpu().numpy().reshape(s)
+            layers["optimizer_weights"] = opt
+        hdf5_lite.save_keras_weights(path, layers, extra_root_attrs=extra)
+
+    def _training_config(self):
+        o = self.optimizer
+        if o is None:
+            return {}
+        cfgd = {k: v for k, v in vars(o).items() if k != "kind"}
+        return {"optimizer_config": {"class_name": "Adam" if o.kind == "adam" else "SGD", "config": cfgd}, "loss": {"ctc": "lambda"}}
+
+    def to_json(self):
+        return json.dumps({"class_name": "Model", "keras_version": "2.2.2", "backend": "crnn_b200",
+                           "config": {"name": "crnn_b200", "num_classes": self.num_classes, "max_string_len": self.max_len,
+                                      "shape": [self.imgh, self.imgw, 1], "time_dense_size": self.time_dense,
+                                      "GRU": self.cell == "gru", "n_units": self.n_units}})
+
+    def summary(self, print_fn=print):
+        tot = sum(int(np.prod(s)) for s in self.shapes.values())
+        nt = sum(int(np.prod(s)) for n, s in self.shapes.items() if n.endswith(("moving_mean", "moving_variance")))
+        print_fn("_" * 65)
+        for n, s in self.shapes.items():
+            print_fn(f"{n:<58}{str(tuple(s)):>20}")
+        print_fn("=" * 65)
+        print_fn(f"Total params: {tot:,}\nTrainable params: {tot - nt:,}\nNon-trainable params: {nt:,}")
+
+    # ------------------------------------------------------------------ inference (predict.py:166)
+    def forward_device(self, x_dev: torch.Tensor) -> torch.Tensor:
+        """x_dev (B,imgh,imgw,1) float32 CUDA tensor -> view of the softmax (B,T,V) inside the workspace."""
+        B = int(x_dev.shape[0])
+        assert x_dev.is_cuda and x_dev.dtype == torch.float32 and x_dev.is_contiguous()
+        _lib.check(self.lib.crnn_forward(self.handle, x_dev.data_ptr(), B, None, self._stream()))
+        return self.tensor("act/softmax")[: B * self.T * self.num_classes].view(B, self.T, self.num_classes)
+
+    def predict_on_batch(self, x) -> np.ndarray:
+        """Host numpy (B,imgh,imgw,1) -> host numpy softmax (B,T,V): H2D + forward + D2H through the C ABI."""
+        x = np.ascontiguousarray(x, np.float32)
+        out = []
+        for s in range(0, x.shape[0], self.max_batch):
+            xb = x[s:s + self.max_batch]
+            o = np.empty((xb.shape[0], self.T, self.num_classes), np.float32)
+            _lib.check(self.lib.crnn_forward_host(self.handle, xb.ctypes.data, xb.shape[0], o.ctypes.data, self._stream()))
+            out.append(o)
+        return np.concatenate(out, 0)
+
+    predict = predict_on_batch
+
+    def predict_generator(self, generator, steps, **_):
+        outs = []
+        for _i in range(steps):
+            inputs, _t = next(generator)
+            outs.append(self.predict_on_batch(inputs["the_input"] if isinstance(inputs, dict) else inputs))
+        return np.concatenate(outs, 0)
+
+    # ------------------------------------------------------------------ training (train.py:187-209)
+    def compile(self, loss=None, optimizer=None, **_):
+        self.optimizer = optimizer
+
+    def iterations(self):
+        it = ctypes.c_int64()
+        _lib.check(self.lib.crnn_get_iterations(self.handle, ctypes.byref(it)))
+        return it.value
+
+    def train_fwd_bwd_device(self, x_dev, labels_dev, label_len_dev, input_len_dev, dropout_seed=0):
+        """Forward (training mode) + CTC + backward on device tensors; returns a view of the per-sample losses."""
+        B = int(x_dev.shape[0])
+        loss = self.tensor("act/loss")[:B]
+        _lib.check(self.lib.crnn_train_fwd_bwd(self.handle, x_dev.data_ptr(), labels_dev.data_ptr(), label_len_dev.data_ptr(),
+                                               input_len_dev.data_ptr(), B, loss.data_ptr(), ctypes.c_uint64(int(dropout_seed)), self._stream()))
+        return loss
+
+    def optimizer_step(self, grad_scale=1.0):
+        o = self.optimizer
+        if o is None:
+            raise RuntimeError("compile(optimizer=...) first")
+        if o.kind == "adam":
+            _lib.check(self.lib.crnn_adam_step(self.handle, o.lr, o.beta_1, o.beta_2, o.epsilon, o.clipnorm or 0.0, grad_scale, self._stream()))
+        else:
+            _lib.check(self.lib.crnn_sgd_step(self.handle, o.lr, o.decay, o.momentum, o.clipnorm or 0.0, grad_scale, self._stream()))
+
+    def allreduce_grads(self):
+        """Data-parallel exchange (NEW capability): one NCCL sum all-reduce of the flat gradient arena."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.tensor("arena/grads"), op=dist.ReduceOp.SUM)
+            return 1.0 / dist.get_world_size()
+        return 1.0
+
+    def _stage(self, key, arr, dtype):
+        """host numpy -> pinned staging -> device (async on the current stream)."""
+        arr = np.ascontiguousarray(arr)
+        t = self._pinned.get(key)
+        if t is None or t[0].numel() < arr.size or t[0].dtype != dtype:
+            pin = torch.empty(max(arr.size, 1), dtype=dtype).pin_memory()
+            dev = torch.empty(max(arr.size, 1), dtype=dtype, device=self.device)
+            self._pinned[key] = t = (pin, dev)
+        pin, dev = t
+        pin[:arr.size].copy_(torch.from_numpy(arr.reshape(-1)).to(dtype))
+        dev[:arr.size].copy_(pin[:arr.size], non_blocking=True)
+        return dev[:arr.size]
+
+    def train_on_batch(self, inputs, outputs=None):
+        """Keras train_on_batch on the generator's dict (utils.py:495-502): host buffers in, scalar mean loss out."""
+        x = np.asarray(inputs["the_input"], np.float32)
+        B = x.shape[0]
+        xd = self._stage("x", x, torch.float32).view(B, self.imgh, self.imgw, 1)
+        lab = self._stage("labels", np.asarray(inputs["the_labels"]).astype(np.int32), torch.int32)
+        ll = self._stage("label_len", np.asarray(inputs["label_length"]).reshape(-1).astype(np.int32), torch.int32)
+        il = self._stage("input_len", np.asarray(inputs["input_length"]).reshape(-1).astype(np.int32), torch.int32)
+        self._step_seed = (int(self._step_seed) * 6364136223846793005 + 1442695040888963407) % (1 << 64) | 1
+        loss = self.train_fwd_bwd_device(xd, lab, ll, il, dropout_seed=self._step_seed if self.dropout else 0)
+        scale = self.allreduce_grads()
+        self.optimizer_step(scale)
+        val = float(loss.mean().item())          # D2H of the step's result
+        st = ctypes.c_int32()
+        _lib.check(self.lib.crnn_ctc_status(self.handle, ctypes.byref(st), self._stream()))
+        if st.value != 0:
+            raise ValueError(f"Not enough time for target transition sequence (batch element {-st.value - 1})")
+        return val
+
+    def test_on_batch(self, inputs, outputs=None):
+        """Validation loss: inference-mode forward + CTC loss (no gradient)."""
+        x = np.asarray(inputs["the_input"], np.float32)
+        B = x.shape[0]
+        xd = self._stage("x", x, torch.float32).view(B, self.imgh, self.imgw, 1)
+        sm = self.forward_device(xd)
+        lab = self._stage("labels", np.asarray(inputs["the_labels"]).astype(np.int32), torch.int32)
+        ll = self._stage("label_len", np.asarray(inputs["label_length"]).reshape(-1).astype(np.int32), torch.int32)
+        il = self._stage("input_len", np.asarray(inputs["input_length"]).reshape(-1).astype(np.int32), torch.int32)
+        from .ctc import ctc_batch_cost_device
+        return float(ctc_batch_cost_device(sm, lab.view(B, -1), ll, il, t_off=2).mean().item())
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, validation_data=None, validation_steps=None,
+                      shuffle=False, verbose=1, callbacks=None, **_):
+        """Subset of Keras fit_generator that train.py:201-209 relies on."""
+        hist = _History()
+        callbacks = callbacks or []
+        for cb in callbacks:
+            cb.model = self
+            getattr(cb, "on_train_begin", lambda logs=None: None)({})
+        self.stop_training = False
+        for epoch in range(epochs):
+            run = 0.0
+            for step in range(steps_per_epoch):
+                inputs, targets = next(generator)
+                loss = self.train_on_batch(inputs, targets)
+                run += loss
+                for cb in callbacks:
+                    getattr(cb, "on_batch_end", lambda b, logs=None: None)(step, {"loss": loss})
+                if verbose and (step % 50 == 0 or step == steps_per_epoch - 1):
+                    print(f"Epoch {epoch + 1}/{epochs} step {step + 1}/{steps_per_epoch} - loss: {run / (step + 1):.4f}", flush=True)
+                if self.stop_training:
+                    break
+            logs = {"loss": run / max(1, step + 1)}
+            hist.history["loss"].append(logs["loss"])
+            if validation_data is not None and validation_steps and not self.stop_training:
+                v = sum(self.test_on_batch(*next(validation_data)) for _ in range(validation_steps)) / validation_steps
+                logs["val_loss"] = v
+                hist.history.setdefault("val_loss", []).append(v)
+            for cb in callbacks:
+                getattr(cb, "on_epoch_end", lambda e, logs=None: None)(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            getattr(cb, "on_train_end", lambda logs=None: None)({})
+        return hist
+
+
+class CRNN:
+    """CRNN(num_classes=97, max_string_len=23, shape=(40,40,1), time_dense_size=128, GRU=False, n_units=256)
+    -- same constructor as the reference (utils.py:34-41); get_model() returns the B200 engine."""
+
+    def __init__(self, num_classes=97, max_string_len=23, shape=(40, 40, 1), time_dense_size=128, GRU=False, n_units=256,
+                 max_batch=64, seed=None):
+        self.num_classes, self.shape, self.max_string_len = num_classes, shape, max_string_len
+        self.n_units, self.GRU, self.time_dense_size = n_units, GRU, time_dense_size
+        self.max_batch, self.seed = max_batch, seed
+
+    def get_model(self):
+        self.pooling_counter_h, self.pooling_counter_w = 1, 2      # utils.py:52-55 for the fixed block plan
+        return CRNNModel(self.num_classes, self.max_string_len, self.shape, self.time_dense_size, bool(self.GRU), self.n_units,
+                         max_batch=self.max_batch, seed=self.seed)

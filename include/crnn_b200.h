@@ -1,0 +1,124 @@
+/*
+ * crnn_b200.h -- C ABI of the B200-native CRNN-OCR hot path (libcrnn_b200.so).
+ *
+ * The reference (gasparian/CRNN-OCR-lite) has NO FFI / plugin interface for this path: its hot path is the
+ * Python surface of utils.py driving Keras 2.2.2 / TensorFlow 1.8.  Each entry point below
+ * therefore cites the reference *call site* it replaces; the Python mirror of that surface lives in
+ * crnn-ocr-lite_b200/ (utils-compatible names) and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 (CRNN_OK) or a negative status; crnn_last_error() gives the message
+ *     (thread-local); nothing throws across the ABI.
+ *   - device pointers are BORROWED: the caller (PyTorch is only the allocator / stream provider) owns all
+ *     memory, including the handle's workspace.  `stream` is a cudaStream_t passed as void*; every call is
+ *     asynchronous on it, no hidden synchronisation, except the *_host convenience entry points which copy
+ *     host<->device and synchronise the stream before returning.
+ *   - one handle per GPU; a handle is not thread-safe, different handles are independent.
+ *   - tensors are fp32, NHWC; axis 1 of the image is the text-line width (time), as in the reference
+ *     (utils.py:370 flips+transposes the image).  Class V-1 is the CTC blank.
+ */
+#ifndef CRNN_B200_H
+#define CRNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRNN_OK 0
+#define CRNN_ERR_INVALID (-1)
+#define CRNN_ERR_CUDA (-2)
+#define CRNN_ERR_NOMEM (-3)
+#define CRNN_ERR_UNKNOWN_NAME (-4)
+#define CRNN_ERR_INFEASIBLE (-5)   /* "Not enough time for target transition sequence" (TF CTCLoss) */
+
+#define CRNN_CELL_GRU 0            /* what the reference CLI actually builds */
+#define CRNN_CELL_LSTM 1           /* utils.py:78-79 */
+
+typedef struct crnn_handle crnn_handle;
+
+/* CRNN(num_classes, max_string_len, shape, time_dense_size, GRU, n_units) -- utils.py:34-41 */
+typedef struct {
+    int32_t imgh;          /* shape[0]: text-line width / time axis (train.py:105, default 100) */
+    int32_t imgw;          /* shape[1]: line height (train.py:106, 32) */
+    int32_t num_classes;   /* len(lexicon)+1 (train.py:165) */
+    int32_t cell;          /* CRNN_CELL_* */
+    int32_t n_units;       /* 256 */
+    int32_t time_dense;    /* 128 */
+    int32_t max_len;       /* max_string_len (23) */
+    int32_t max_batch;     /* largest batch the workspace is sized for */
+} crnn_config;
+
+typedef struct {
+    int64_t offset;        /* in bytes from the workspace base */
+    int64_t numel;
+    int32_t is_int;        /* 1: int32 tensor, 0: float32 */
+} crnn_tensor_info;
+
+const char* crnn_last_error(void);
+const char* crnn_version(void);
+
+/* ---------------------------------------------------------------- model handle (CRNN.get_model, utils.py:58-96) */
+int crnn_workspace_bytes(const crnn_config* cfg, size_t* bytes);
+/* `workspace` = device memory of >= crnn_workspace_bytes, 256-byte aligned, zero-filled by the caller */
+int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes, crnn_handle** out);
+int crnn_destroy(crnn_handle* h);
+/* named tensors inside the workspace: weights ("conv2d_3/kernel", ... the names of models/<name>/final_weights.h5,
+ * utils.py:328 load_weights), their gradients ("grad/<name>"), Adam state ("adam_m/<name>", "adam_v/<name>"),
+ * activations ("act/<name>").  Flat arenas: "arena/params", "arena/grads", "arena/opt_m", "arena/opt_v". */
+int crnn_num_tensors(const crnn_handle* h);
+const char* crnn_tensor_name(const crnn_handle* h, int index);
+int crnn_tensor_lookup(const crnn_handle* h, const char* name, crnn_tensor_info* out);
+
+/* predictor = Model(the_input -> softmax).predict (utils.py:308-312, predict.py:166): x (B,imgh,imgw,1) ->
+ * softmax (B,T,V).  BN uses moving statistics, no dropout. */
+int crnn_forward(crnn_handle* h, const float* x_dev, int B, float* softmax_dev, void* stream);
+/* same with host buffers (H2D + forward + D2H, synchronises) */
+int crnn_forward_host(crnn_handle* h, const float* x_host, int B, float* softmax_host, void* stream);
+
+/* one training forward/backward: model.train_on_batch up to the gradients (train.py:187-209):
+ * STN+conv+BiRNN forward in training mode, ctc_lambda_func (utils.py:98-103), full backward.  Gradients of the
+ * MEAN-over-batch loss land in "arena/grads"; per-sample losses in loss_dev (B).  dropout_seed==0 disables
+ * dropout (parity mode); otherwise masks are a stateless hash of (seed, layer, element). */
+int crnn_train_fwd_bwd(crnn_handle* h, const float* x_dev, const int32_t* labels_dev, const int32_t* label_len_dev,
+                       const int32_t* input_len_dev, int B, float* loss_dev, uint64_t dropout_seed, void* stream);
+/* optimizers.Adam(lr, beta_1=.5, beta_2=.999, clipnorm=5) / SGD(nesterov) step over the arenas (train.py:188-190);
+ * grad_scale folds 1/world_size after a sum all-reduce of "arena/grads". */
+int crnn_adam_step(crnn_handle* h, float lr, float beta1, float beta2, float eps, float clipnorm, float grad_scale, void* stream);
+int crnn_sgd_step(crnn_handle* h, float lr, float decay, float momentum, float clipnorm, float grad_scale, void* stream);
+int crnn_get_iterations(const crnn_handle* h, int64_t* it);
+int crnn_set_iterations(crnn_handle* h, int64_t it);
+/* status of the last CTC loss launch (read after a stream sync): 0 or -(b+1) for the first infeasible sample */
+int crnn_ctc_status(crnn_handle* h, int32_t* status_host, void* stream);
+
+/* ---------------------------------------------------------------- stand-alone CTC ops on device buffers */
+/* K.ctc_batch_cost (utils.py:103) on probs[:, t_off:, :]; grad_u / grad_logits may be NULL.
+ * status_dev: one int32, 0 or -(b+1). */
+int crnn_ctc_loss_grad(const float* probs_dev, int B, int T, int V, int t_off, const int32_t* labels_dev, int max_len,
+                       const int32_t* label_len_dev, const int32_t* input_len_dev, float eps,
+                       float* loss_dev, float* grad_u_dev, float* grad_logits_dev, float scale,
+                       int32_t* status_dev, void* stream);
+/* K.ctc_decode(greedy=True): out (B,T) padded with -1 */
+int crnn_ctc_greedy(const float* probs_dev, const int32_t* seq_len_dev, int B, int T, int V, float eps,
+                    int32_t* out_dev, int32_t* out_len_dev, float* score_dev, void* stream);
+/* K.ctc_decode(greedy=False, beam_width, top_paths=1) as used by DecodeCTCPred.decode (utils.py:347-357) */
+int crnn_ctc_beam(const float* probs_dev, const int32_t* seq_len_dev, int B, int T, int V, float eps, int beam_width,
+                  int merge_repeated, int32_t* out_dev, int32_t* out_len_dev, float* logprob_dev, void* stream);
+/* host-buffer variant: copies probs H2D, decodes, copies labels D2H, synchronises */
+int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, int beam_width, int merge_repeated,
+                       int32_t* out_host, int32_t* out_len_host, float* logprob_host, void* stream);
+int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps,
+                         int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream);
+
+/* ---------------------------------------------------------------- building blocks exposed for parity tests */
+/* C[M,N] = op(A) op(B) (+bias, relu); see csrc/gemm_simt.cu */
+int crnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+              int transA, int transB, const float* a_scale, const float* a_shift, const float* bias, int relu,
+              int split_k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

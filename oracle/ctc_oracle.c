@@ -146,27 +146,36 @@ void ctc_oracle_greedy(const float* probs, int B, int T, int V, const int* seq_l
  * ("new"), a TopN of `beam_width` leaves ordered by new.total, sequential insert / evict.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
-    int parent, label, first_child, next_sib;
+    int parent, label;
+    int children;      /* index into Tree.kids of this entry's (V-1) child ids, -1 until populated (TF PopulateChildren) */
     float ob, ol, ot;  /* oldp: blank, label, total */
     float nb, nl, nt;  /* newp */
 } Entry;
 
 typedef struct {
     Entry* e; int n, cap;
+    int* kids; int nk, capk;   /* pool of children-id arrays, (V-1) ints each */
+    int nc;                    /* V-1 */
 } Tree;
 
 static int tree_new(Tree* tr, int parent, int label) {
     if (tr->n == tr->cap) { tr->cap *= 2; tr->e = (Entry*)realloc(tr->e, sizeof(Entry) * tr->cap); }
     Entry* x = &tr->e[tr->n];
-    x->parent = parent; x->label = label; x->first_child = -1; x->next_sib = -1;
+    x->parent = parent; x->label = label; x->children = -1;
     x->ob = x->ol = x->ot = x->nb = x->nl = x->nt = LOGZERO;
-    if (parent >= 0) { x->next_sib = tr->e[parent].first_child; tr->e[parent].first_child = tr->n; }
     return tr->n++;
 }
+/* BeamEntry::GetChild: children are created lazily with oldp=newp=-inf */
 static int tree_child(Tree* tr, int parent, int label) {
-    for (int c = tr->e[parent].first_child; c >= 0; c = tr->e[c].next_sib)
-        if (tr->e[c].label == label) return c;
-    return tree_new(tr, parent, label);
+    if (tr->e[parent].children < 0) {
+        if (tr->nk + tr->nc > tr->capk) { while (tr->nk + tr->nc > tr->capk) tr->capk *= 2; tr->kids = (int*)realloc(tr->kids, sizeof(int) * tr->capk); }
+        tr->e[parent].children = tr->nk;
+        for (int k = 0; k < tr->nc; ++k) tr->kids[tr->nk + k] = -1;
+        tr->nk += tr->nc;
+    }
+    int* slot = &tr->kids[tr->e[parent].children + label];
+    if (*slot < 0) { int id = tree_new(tr, parent, label); slot = &tr->kids[tr->e[parent].children + label]; *slot = id; }
+    return *slot;
 }
 
 /* leaves: unordered array of <= W entry ids; "bottom" = smallest new.total */
@@ -186,9 +195,10 @@ void ctc_oracle_beam(const float* probs, int B, int T, int V, const int* seq_len
     int* leaves = (int*)malloc(sizeof(int) * (W + 1));
     int* branches = (int*)malloc(sizeof(int) * (W + 1));
     Tree tr; tr.cap = 1024; tr.e = (Entry*)malloc(sizeof(Entry) * tr.cap);
+    tr.capk = 4096; tr.kids = (int*)malloc(sizeof(int) * tr.capk); tr.nc = V - 1;
 
     for (int b = 0; b < B; ++b) {
-        tr.n = 0;
+        tr.n = 0; tr.nk = 0;
         int root = tree_new(&tr, -1, -1);
         tr.e[root].nt = 0.f; tr.e[root].nb = 0.f; tr.e[root].nl = LOGZERO;
         int nleaves = 1; leaves[0] = root;
@@ -279,5 +289,5 @@ void ctc_oracle_beam(const float* probs, int B, int T, int V, const int* seq_len
         out_len[b] = n;
         if (log_prob) log_prob[b] = tr.e[leaves[best]].nt;
     }
-    free(in); free(leaves); free(branches); free(tr.e);
+    free(in); free(leaves); free(branches); free(tr.e); free(tr.kids);
 }

@@ -1,0 +1,285 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (libcrnn_b200.so), against the CPU oracle
+on identical seeded inputs.  Integer outputs (decode indices) must be bit-exact; floating point within the stated
+fp32 tolerances.  Run with `pytest -m gpu` on a B200 (gpurun)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn_oracle as N
+from oracle import ctc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import crnn_b200
+    return crnn_b200
+
+
+def _rand_probs(rng, B, T, V, scale=3.0):
+    z = rng.standard_normal((B, T, V)).astype(np.float32) * scale
+    z -= z.max(-1, keepdims=True)
+    p = np.exp(z)
+    return (p / p.sum(-1, keepdims=True)).astype(np.float32)
+
+
+def _labels(rng, B, V, maxL, T):
+    lens = rng.integers(1, min(maxL, T // 2) + 1, B).astype(np.int32)
+    lab = np.full((B, maxL), V - 1, np.int32)
+    for b in range(B):
+        l = rng.integers(0, V - 1, lens[b])
+        if b % 3 == 0 and lens[b] >= 2:
+            l[1] = l[0]
+        lab[b, :lens[b]] = l
+    return lab, lens
+
+
+# ------------------------------------------------------------------------------------------- CTC loss / grad
+@pytest.mark.parametrize("T,V,maxL,t_off", [(52, 38, 23, 2), (66, 38, 23, 2), (25, 96, 12, 0), (9, 5, 3, 0)])
+def test_ctc_loss_grad(cb, T, V, maxL, t_off):
+    rng = np.random.default_rng(T * 100 + V)
+    B = 16
+    probs = _rand_probs(rng, B, T, V)
+    lab, lens = _labels(rng, B, V, maxL, T - t_off)
+    in_len = np.full(B, T - t_off, np.int32)
+    in_len[1] = T - t_off - 3
+    loss_o, gu_o = O.ctc_loss_grad(probs[:, t_off:], lab, lens, in_len)
+    d = "cuda"
+    loss, gu, gz = cb.ctc_batch_cost_device(torch.tensor(probs, device=d), torch.tensor(lab, device=d), torch.tensor(lens, device=d),
+                                            torch.tensor(in_len, device=d), t_off=t_off, want_grad_u=True, want_grad_logits=True, scale=1.0 / B)
+    # fp32 log-space arithmetic at |log p| ~ 100-200: tolerance 2e-4 absolute on the gradient, 1e-4 relative on the loss
+    np.testing.assert_allclose(loss.cpu().numpy(), loss_o, rtol=1e-5, atol=2e-4)
+    np.testing.assert_allclose(gu.cpu().numpy(), gu_o, rtol=0, atol=2e-4)
+    # chained gradient wrt the dense2 logits vs autograd through u=log(p+eps), p=softmax(z)
+    z = torch.log(torch.tensor(probs, dtype=torch.float64)).requires_grad_(True)
+    p = torch.softmax(z, -1)
+    u = torch.log(p[:, t_off:] + 1e-7)
+    (u * torch.tensor(gu_o, dtype=torch.float64)).sum().backward()
+    np.testing.assert_allclose(gz.cpu().numpy(), z.grad.numpy() / B, rtol=0, atol=2e-5)
+    assert np.all(gz.cpu().numpy()[:, :t_off] == 0)
+
+
+def test_ctc_loss_infeasible(cb):
+    probs = torch.tensor(_rand_probs(np.random.default_rng(0), 2, 4, 5), device="cuda")
+    lab = torch.tensor([[1, 2, 4], [1, 1, 2]], dtype=torch.int32, device="cuda")
+    with pytest.raises(ValueError, match="Not enough time"):
+        cb.ctc_batch_cost_device(probs, lab, torch.tensor([2, 3], device="cuda"), torch.tensor([4, 3], device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------- decoders (index-exact)
+@pytest.mark.parametrize("B,T,V,scale", [(64, 25, 96, 3.0), (32, 52, 38, 6.0), (8, 66, 38, 1.0), (5, 3, 4, 2.0)])
+def test_greedy_exact(cb, B, T, V, scale):
+    probs = _rand_probs(np.random.default_rng(B + T), B, T, V, scale)
+    o, n, s = O.greedy(probs)
+    out, cnt, score = cb.ctc_decode_device(torch.tensor(probs, device="cuda"), greedy=True)
+    np.testing.assert_array_equal(out.cpu().numpy(), o)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), n)
+    np.testing.assert_allclose(score.cpu().numpy(), s, rtol=1e-5)
+
+
+def _beam_compare(cb, probs, W=10, merge=True, seq_len=None):
+    o, n, lp = O.beam(probs, seq_len=seq_len, beam_width=W, merge_repeated=merge)
+    sl = torch.tensor(seq_len, device="cuda") if seq_len is not None else None
+    out, cnt, score = cb.ctc_decode_device(torch.tensor(probs, device="cuda"), seq_len=sl, greedy=False, beam_width=W, merge_repeated=merge)
+    out, cnt, score = out.cpu().numpy(), cnt.cpu().numpy(), score.cpu().numpy()
+    bad = [b for b in range(probs.shape[0]) if cnt[b] != n[b] or not np.array_equal(out[b], o[b])]
+    return bad, (o, n, lp), (out, cnt, score)
+
+
+@pytest.mark.parametrize("B,T,V,scale,W", [(64, 25, 96, 3.0, 10), (32, 52, 38, 6.0, 10), (16, 66, 38, 1.0, 10), (16, 25, 96, 3.0, 3),
+                                           (9, 12, 7, 1.0, 32), (4, 1, 5, 1.0, 10)])
+def test_beam_exact(cb, B, T, V, scale, W):
+    probs = _rand_probs(np.random.default_rng(B * 7 + T), B, T, V, scale)
+    bad, (o, n, lp), (out, cnt, score) = _beam_compare(cb, probs, W)
+    assert not bad, (bad, o[bad[0]], out[bad[0]])
+    np.testing.assert_allclose(score, lp, rtol=1e-4, atol=1e-4)
+
+
+def test_beam_merge_off_and_ragged(cb):
+    rng = np.random.default_rng(5)
+    probs = _rand_probs(rng, 24, 30, 20, 2.0)
+    sl = rng.integers(1, 31, 24).astype(np.int32)
+    for merge in (True, False):
+        bad, _, _ = _beam_compare(cb, probs, 10, merge, sl)
+        assert not bad
+
+
+def test_beam_full_config3(cb):
+    """BASELINE configs[3]: (4096,25,96) logits ~ N(0,1)*3, beam 10.  Index-exact vs the oracle; a mismatch is only
+    tolerated when the oracle's own top-2 beam totals are within fp32 rounding (near-tie)."""
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((4096, 25, 96)).astype(np.float32) * 3
+    probs = torch.softmax(torch.tensor(z), -1).numpy()
+    bad, (o, n, lp), (out, cnt, score) = _beam_compare(cb, probs, 10)
+    assert len(bad) <= 2, f"{len(bad)} mismatching sequences"
+    for b in bad:   # both outputs must be (near-)equally probable labellings
+        assert abs(score[b] - lp[b]) < 1e-3
+    # size-independent property: decode of a one-hot path equals its collapse
+    paths = rng.integers(0, 96, (4096, 25))
+    oh = np.full((4096, 25, 96), 1e-5, np.float32)
+    np.put_along_axis(oh, paths[..., None], 1.0, -1)
+    out, cnt, _ = cb.ctc_decode_device(torch.tensor(oh, device="cuda"), greedy=False, beam_width=10, merge_repeated=False)
+    out, cnt = out.cpu().numpy(), cnt.cpu().numpy()
+    for b in range(0, 4096, 37):
+        ref, prev = [], -1
+        for k in paths[b]:
+            if k != 95 and k != prev:
+                ref.append(k)
+            prev = k
+        assert list(out[b, :cnt[b]]) == ref
+
+
+def test_decode_host_api(cb):
+    """DecodeCTCPred.decode (utils.py:347-357) through host buffers."""
+    lex = [c for c in "0123456789abcdefghijklmnopqrstuvwxyz-"]
+    probs = _rand_probs(np.random.default_rng(9), 40, 52, 38, 5.0)
+    dec = cb.DecodeCTCPred(top_paths=1, beam_width=10, inverse_classes=lex)
+    got = dec.decode(probs)
+    o, n, _ = O.beam(probs, beam_width=10, merge_repeated=True)
+    want = ["".join(lex[k] for k in o[i, :n[i]]) for i in range(40)]
+    assert got == want
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,tA,tB", [(300, 64, 1, 0, 0), (1000, 128, 64, 0, 0), (513, 38, 512, 0, 0), (70, 50, 760, 0, 0),
+                                         (64, 130, 1000, 1, 0), (1, 64, 5000, 1, 0), (777, 64, 128, 0, 1), (300, 1, 64, 0, 1),
+                                         (4608, 128, 300, 1, 0)])
+def test_gemm(cb, M, N, K, tA, tB):
+    lib = cb._lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if tA else (M, K), generator=g)
+    Bm = torch.randn((N, K) if tB else (K, N), generator=g)
+    sc = torch.rand(A.shape[1], generator=g) + 0.5
+    sh = torch.randn(A.shape[1], generator=g)
+    bias = torch.randn(N, generator=g)
+    for prologue, split in ((False, 1), (True, 1), (False, 4)):
+        Ae = torch.clamp(A * sc + sh, 0, 6) if prologue else A
+        ref = (Ae.T if tA else Ae).double() @ (Bm.T if tB else Bm).double()
+        if split == 1:
+            ref = torch.relu(ref + bias.double())
+        C = torch.zeros(M, N, device="cuda")
+        Ad, Bd, scd, shd, bd = A.cuda(), Bm.cuda(), sc.cuda(), sh.cuda(), bias.cuda()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        cb._lib.check(lib.crnn_gemm(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, A.shape[1], Bm.shape[1], N, tA, tB,
+                                    scd.data_ptr() if prologue else None, shd.data_ptr() if prologue else None,
+                                    bd.data_ptr() if split == 1 else None, 1 if split == 1 else 0, split, st))
+        tol = 1e-5 * K ** 0.5 * 8
+        np.testing.assert_allclose(C.cpu().numpy(), ref.float().numpy(), rtol=1e-4, atol=tol)
+
+
+# ------------------------------------------------------------------------------------------- whole network
+def _make(cb, cfg, B, seed):
+    w = N.randomize_for_test(N.init_weights(cfg, seed), seed)
+    m = cb.CRNN(cfg.num_classes, cfg.max_len, (cfg.imgh, cfg.imgw, 1), cfg.time_dense, cfg.cell == "gru", cfg.n_units, max_batch=B).get_model()
+    m.set_weights(w)
+    return w, m
+
+
+def _cmp(name, got, want, atol, rtol=1e-4):
+    got, want = np.asarray(got, np.float32).reshape(-1), np.asarray(want, np.float32).reshape(-1)
+    err = np.abs(got - want)
+    lim = atol + rtol * np.abs(want)
+    assert np.all(err <= lim), f"{name}: max err {err.max():.3e} at {err.argmax()} (want {want[err.argmax()]:.5f}, got {got[err.argmax()]:.5f}), tol {atol}"
+
+
+@pytest.mark.parametrize("imgh,cell,V", [(100, "gru", 38), (128, "gru", 38), (128, "lstm", 38), (100, "lstm", 97)])
+def test_forward_inference_parity(cb, imgh, cell, V):
+    cfg = N.Cfg(imgh=imgh, cell=cell, num_classes=V)
+    B = 4
+    w, m = _make(cb, cfg, B, 1)
+    x, _, _, _ = N.synth_batch(cfg, B, 11)
+    keep = N.forward(N.to_torch(w), torch.tensor(x), cfg, training=False)
+    sm = m.predict_on_batch(x)
+    T = cfg.T
+    # stated fp32 tolerance: 2e-4 absolute on O(1) activations (different summation order, fp32 accumulate)
+    _cmp("theta", m.activation("theta")[:B * 6], keep["theta"].numpy(), 2e-5)
+    a0 = m.activation("a0")[:B * (imgh + 4) * 36].reshape(B, imgh + 4, 36)
+    _cmp("stn", a0[:, 2:-2, 2:-2], keep["stn"].numpy()[..., 0], 2e-4)
+    assert np.all(a0[:, :2] == 0) and np.all(a0[:, -2:] == 0) and np.all(a0[:, :, :2] == 0) and np.all(a0[:, :, -2:] == 0)
+    for i in range(1, 8):
+        k = keep[f"block{i}"].numpy()
+        _cmp(f"block{i}", m.activation(f"block{i}")[:k.size], k, 5e-4)
+    _cmp("dense1", m.activation("dense1")[:B * T * 128], keep["dense1"].numpy(), 5e-4)
+    _cmp("rnn1", m.activation("rnn1")[:B * T * 256], keep["rnn1"].numpy(), 5e-4)
+    _cmp("rnn2", m.activation("hs2")[:B * T * 512], keep["rnn2"].numpy(), 5e-4)
+    _cmp("softmax", sm, keep["softmax"].numpy(), 2e-4)
+    # decode indices of the two softmaxes agree (greedy + beam)
+    g1 = O.greedy(sm)[0]; g2 = O.greedy(keep["softmax"].numpy())[0]
+    np.testing.assert_array_equal(g1, g2)
+
+
+def test_sampler_bitexact_given_theta(cb):
+    """With the oracle's theta injected, the sampler output is bit-identical (same fp32 op order, no FMA contraction)."""
+    cfg = N.Cfg(imgh=100)
+    B = 4
+    w, m = _make(cb, cfg, B, 2)
+    rng = np.random.default_rng(0)
+    w["dense_2/kernel"][:] = 0
+    m.set_weights(w)
+    for trial in range(3):
+        th = (np.array([1, 0, 0, 0, 1, 0], np.float32) + rng.standard_normal((6,)).astype(np.float32) * (0.0 if trial == 0 else 0.3)).astype(np.float32)
+        w["dense_2/bias"][:] = th
+        m.set_weights(w)
+        x, _, _, _ = N.synth_batch(cfg, B, 20 + trial)
+        m.predict_on_batch(x)
+        want = N.bilinear_sampler(torch.tensor(x), torch.tensor(np.tile(th, (B, 1)))).numpy()[..., 0]
+        a0 = m.activation("a0")[:B * 104 * 36].reshape(B, 104, 36)[:, 2:-2, 2:-2]
+        np.testing.assert_array_equal(a0, want)
+        if trial == 0:   # closed-form invariants of the identity transform
+            assert np.all(a0[:, -1] == 0) and np.abs(a0[:, :, -1]).max() < 1e-6 and np.all(a0[:, 0, 0] == x[:, 0, 0, 0])
+
+
+@pytest.mark.parametrize("imgh,cell", [(100, "gru"), (128, "lstm")])
+def test_train_step_parity(cb, imgh, cell):
+    """Full training forward/backward (BN batch statistics, CTC, BPTT, STN) + Adam vs torch autograd on the oracle.
+    Dropout disabled on both sides (RNG streams cannot match TF)."""
+    cfg = N.Cfg(imgh=imgh, cell=cell)
+    B = 6
+    w, m = _make(cb, cfg, B, 3)
+    x, lab, L, il = N.synth_batch(cfg, B, 33)
+    loss_o, per_o, g_o, stats_o, keep = N.loss_and_grads(w, x, lab, L, il, cfg)
+    d = "cuda"
+    per = m.train_fwd_bwd_device(torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d), dropout_seed=0)
+    np.testing.assert_allclose(per.cpu().numpy(), per_o, rtol=2e-4, atol=2e-3)
+    g = m.get_grads()
+    # gradient tolerance: relative to the largest entry of each tensor (fp32 accumulation over up to 4e5 rows)
+    for k, want in g_o.items():
+        got = g[k]
+        scale = max(np.abs(want).max(), 1e-6)
+        err = np.abs(got - want).max() / scale
+        assert err < 3e-3, f"grad {k}: rel-to-max err {err:.2e} (max |g| {scale:.3e})"
+    neww = m.get_weights()
+    for k, want in stats_o.items():
+        np.testing.assert_allclose(neww[k], want, rtol=1e-4, atol=1e-5, err_msg=k)
+    # Adam(lr 1e-4, b1 .5, b2 .999, eps 1e-7, clipnorm 5) step (train.py:188)
+    m.compile(optimizer=cb.Adam(lr=1e-4, beta_1=0.5, beta_2=0.999, epsilon=1e-7, clipnorm=5.0))
+    m.optimizer_step()
+    state = {}
+    w2, norm = N.adam_step(w, g_o, state, lr=1e-4, b1=0.5, b2=0.999, eps=1e-7, clipnorm=5.0)
+    got = m.get_weights()
+    for k in g_o:
+        # Adam's first step moves every weight by ~lr*sign(g): compare the update, tolerance 2% of lr
+        np.testing.assert_allclose(got[k] - w[k], w2[k] - w[k], rtol=0, atol=2e-6 + 0.02e-4, err_msg=k)
+
+
+def test_dropout_statistics(cb):
+    cfg = N.Cfg(imgh=100)
+    B = 4
+    w, m = _make(cb, cfg, B, 4)
+    x, lab, L, il = N.synth_batch(cfg, B, 44)
+    d = "cuda"
+    args = (torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d))
+    m.train_fwd_bwd_device(*args, dropout_seed=0)
+    a_off = m.activation("block4").copy()
+    m.train_fwd_bwd_device(*args, dropout_seed=12345)
+    a_on = m.activation("block4")
+    nz = a_off != 0
+    kept = a_on[nz] != 0
+    assert abs(kept.mean() - 0.9) < 0.01                     # Dropout(0.1), utils.py:56
+    np.testing.assert_allclose(a_on[nz][kept], a_off[nz][kept] / 0.9, rtol=2e-3, atol=1e-3)
+    g1 = m.get_grads()["dense2/kernel"].copy()
+    m.train_fwd_bwd_device(*args, dropout_seed=12345)      # stateless masks: same seed -> same step
+    np.testing.assert_allclose(m.get_grads()["dense2/kernel"], g1, rtol=1e-4, atol=1e-6)
