@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- measurement contract of the CRNN-OCR hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU (oracle port)
+
+A "step" = one full training step of BASELINE.json configs[2]: STN + conv stack + BiRNN forward/backward +
+ctc_batch_cost gradient + clipnorm/Adam on one batch of 64 synthetic 128x32 text-line images per GPU (fp32, random-init
+weights, dropout on).  N>1: data parallel, batch 64 per GPU (weak scaling), one NCCL all-reduce of the flat gradient
+arena per step.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "text-line images/sec (fwd+bwd+CTC) per GPU; CTC beam-10 decode lines/sec"
+BATCH = 64
+IMGH, IMGW, V, MAXLEN = 128, 32, 38, 23
+
+
+def synth_batch(B, seed):
+    """SURVEY 8d configs[2]: normalised U{0..255} pixels, L~U{3..23} labels padded with the blank, input_length = T-2."""
+    rng = np.random.default_rng(seed)
+    x = ((rng.integers(0, 256, (B, IMGH, IMGW, 1)).astype(np.float32) - np.float32(118.24236953981779)) / np.float32(36.72835353999682))
+    L = rng.integers(3, MAXLEN + 1, B).astype(np.int32)
+    lab = np.full((B, MAXLEN), V - 1, np.int32)
+    for b in range(B):
+        lab[b, :L[b]] = rng.integers(0, V - 1, L[b])
+    il = np.full(B, (IMGH + 4) // 2 - 2, np.int32)
+    return x.astype(np.float32), lab, L, il
+
+
+def workload_config(args, world):
+    return {"workload": "configs[2]: full train step (STN+dw-separable conv stack+Bi%s fwd/bwd + ctc_batch_cost grad + clipnorm5/Adam), "
+                        "batch 64 per GPU, 128x32 gray, V=38, fp32, random-init, dropout on" % args.cell.upper(),
+            "global_batch": BATCH * world, "per_gpu_batch": BATCH, "imgh": IMGH, "imgw": IMGW, "num_classes": V, "cell": args.cell,
+            "parallelism": "dp%d" % world,
+            "l2": "per-step working set (~2.5 GB of activations/gradients rewritten every step) >> 126 MB L2; no explicit flush"}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[5 + i].strip().lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def oracle_train_step_fn(cell, sample_batch, threads):
+    import torch
+    from oracle import crnn_oracle as N
+    torch.set_num_threads(threads)
+    cfg = N.Cfg(imgh=IMGH, imgw=IMGW, num_classes=V, cell=cell, max_len=MAXLEN)
+    w = N.init_weights(cfg, 0)
+    x, lab, L, il = synth_batch(sample_batch, 2)
+    state = {}
+
+    def step():
+        nonlocal w
+        loss, per, g, stats, _ = N.loss_and_grads(w, x, lab, L, il, cfg)
+        w, _ = N.adam_step(w, g, state, lr=1e-4, b1=0.5, b2=0.999, eps=1e-7, clipnorm=5.0)
+        w.update(stats)
+        return loss
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    cores = os.cpu_count() or 1
+    sample = 16
+    step = oracle_train_step_fn(args.cell, sample, cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    desc = "oracle port (PyTorch-CPU fp32 restatement of the Keras graph + C restatement of TF CTCLoss + Keras Adam), one train step on %d of the 64 images per step" % sample
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this path has no CPU fallback"}), flush=True)
+        return 2
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import crnn_b200 as cb
+    lib = cb._lib.load()
+
+    model = cb.CRNN(V, MAXLEN, (IMGH, IMGW, 1), 128, args.cell == "gru", 256, max_batch=BATCH, seed=1234).get_model()
+    model.compile(optimizer=cb.Adam(lr=1e-4, beta_1=0.5, beta_2=0.999, epsilon=1e-7, clipnorm=5.0))
+    if world > 1:   # identical replicas
+        dist.broadcast(model.tensor("arena/params"), src=0)
+    x, lab, L, il = synth_batch(BATCH, 2 + rank)
+    xd, labd, Ld, ild = (torch.tensor(a, device=dev) for a in (x, lab, L, il))
+    seed_base = 0x5EED0000 + rank
+
+    step_no = [0]
+
+    def step_device():
+        step_no[0] += 1
+        model.train_fwd_bwd_device(xd, labd, Ld, ild, dropout_seed=seed_base + step_no[0])
+        model.optimizer_step(model.allreduce_grads())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.crnn_launch_count()
+    ms = timed(step_device, args.steps)
+    launches = lib.crnn_launch_count() - l0
+    value = BATCH * world * args.steps / (ms / 1e3)
+
+    # ---- e2e: host numpy in -> train_on_batch (pinned staging + H2D, step, D2H of the loss) every step
+    host_inputs = {"the_input": x, "the_labels": lab, "input_length": il.reshape(-1, 1), "label_length": L.reshape(-1, 1)}
+    for _ in range(2):
+        model.train_on_batch(host_inputs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.train_on_batch(host_inputs)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = BATCH * world * args.steps / float(e2e_s.item())
+    clocks = sampler.stop() if sampler else None
+    h2d = x.nbytes + lab.nbytes + L.nbytes + il.nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- per-stage CUDA-event profile of the same step (rank 0), dominant kernel -> roofline
+    import ctypes
+    ns = lib.crnn_profile_num_stages()
+    cb._lib.check(lib.crnn_profile_enable(model.handle, 1))
+    nprof = 3
+    if world == 1:
+        for _ in range(nprof):
+            step_device()
+    else:   # keep the collective pattern of the other ranks untouched: profile forward/backward only
+        for _ in range(nprof):
+            model.train_fwd_bwd_device(xd, labd, Ld, ild, dropout_seed=seed_base)
+    msv = (ctypes.c_double * ns)(); wk = (ctypes.c_double * ns)(); ln = (ctypes.c_longlong * ns)()
+    cb._lib.check(lib.crnn_profile_report(model.handle, msv, wk, ln))
+    cb._lib.check(lib.crnn_profile_enable(model.handle, 0))
+    stages = []
+    for i in range(ns):
+        nm = lib.crnn_profile_stage_name(i).decode()
+        stages.append({"stage": nm, "ms_per_step": msv[i] / nprof, "launches_per_step": ln[i] / nprof, "work_per_step": wk[i] / nprof})
+    tot = sum(s["ms_per_step"] for s in stages) or 1.0
+    for s in stages:
+        s["share"] = s["ms_per_step"] / tot
+    stages.sort(key=lambda s: -s["ms_per_step"])
+    pk = peaks()
+    top = stages[0]
+    is_gemm = top["stage"].startswith("gemm")
+    if is_gemm:
+        ach = top["work_per_step"] / (top["ms_per_step"] / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"]}
+    else:
+        ach = top["work_per_step"] / (top["ms_per_step"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+    roof.update({"traffic": None, "kernel": "stage '%s' (%d launches/step, %.3f ms/step, %.1f%% of the step)" %
+                 (top["stage"], round(top["launches_per_step"]), top["ms_per_step"], 100 * top["share"]),
+                 "peak_source": "%s (MEASURED_PEAKS.json: %s)" % (pk["src"], "bf16_tflops_sustained, kernel timed inside the step" if is_gemm else "hbm_gbs"),
+                 "note": "fp32 SIMT GEMM measured against the bf16 tensor-core peak" if is_gemm else ""})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump({"stages": stages, "ms_per_step_events": tot}, open(os.path.join(ROOT, "gpurun_out", "bench_stages.json"), "w"), indent=1)
+    print("[bench] per-stage (CUDA events, rank 0): " + "; ".join("%s %.2fms" % (s["stage"], s["ms_per_step"]) for s in stages[:10]), file=sys.stderr)
+
+    # ---- secondary numbers: configs[1] forward+greedy, configs[3] beam-10 decode
+    extra = {}
+    try:
+        def fwd_greedy():
+            sm = model.forward_device(xd)
+            cb.ctc_decode_device(sm, greedy=True)
+        for _ in range(3):
+            fwd_greedy()
+        extra["fwd_greedy_images_per_s"] = BATCH * args.steps / (timed(fwd_greedy, args.steps) / 1e3) if world == 1 else None
+    except Exception as e:  # pragma: no cover
+        extra["fwd_greedy_error"] = repr(e)
+    beam = None
+    if world == 1:
+        rng = np.random.default_rng(3)
+        z = (rng.standard_normal((4096, 25, 96)).astype(np.float32) * 3)
+        pd_ = torch.softmax(torch.tensor(z, device=dev), -1).contiguous()
+        ph = pd_.cpu().numpy()
+        for _ in range(3):
+            cb.ctc_decode_device(pd_, greedy=False, beam_width=10)
+        bms = timed(lambda: cb.ctc_decode_device(pd_, greedy=False, beam_width=10), 20) / 20
+        cb.ctc_decode_host(ph, greedy=False, beam_width=10)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            cb.ctc_decode_host(ph, greedy=False, beam_width=10)
+        bh = (time.perf_counter() - t0) / 5
+        from oracle import ctc_oracle as O
+        sub = ph[:1024]
+        t0 = time.perf_counter(); O.beam(sub, beam_width=10); c1 = 1024 / (time.perf_counter() - t0)
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter(); O.beam_threaded(ph, cores, beam_width=10); cN = 4096 / (time.perf_counter() - t0)
+        beam = {"workload": "configs[3]: beam-10 decode, (4096,25,96) softmax of N(0,1)*3 logits, merge_repeated",
+                "lines_per_s_device": 4096 / (bms / 1e3), "lines_per_s_e2e_host_buffers": 4096 / bh, "ms_per_call": bms,
+                "cpu_oracle_1thread_lines_per_s": c1, "cpu_oracle_all_threads_lines_per_s": cN, "cpu_threads": cores,
+                "speedup_e2e_vs_cpu_1thread": (4096 / bh) / c1, "speedup_device_vs_cpu_1thread": (4096 / (bms / 1e3)) / c1,
+                "hbm_frac": (4096 * 25 * 96 * 4 / (bms / 1e3) / 1e9) / pk["hbm"]}
+    # ---- CPU baseline: the oracle port, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = 32
+        st = oracle_train_step_fn(args.cell, sample, cores)
+        oracle_train_step_fn(args.cell, 2, cores)()   # page in the CPU kernels
+        t0 = time.perf_counter(); st(); dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "one oracle train step (PyTorch-CPU fp32 restatement + C CTC + Adam) on 32 of the 64 images, %.1f s" % dt}
+
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "api": "CRNNModel.train_on_batch(host numpy dict) == Keras train_on_batch (train.py:201-209)"},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "roofline": roof, "cpu_baseline": cpu, "beam_decode": beam, "extra": extra,
+            "stages_top": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.items()} for s in stages[:8]]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cell", default="gru", choices=["gru", "lstm"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -25,7 +25,8 @@ void crnn_set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
-#define LAUNCH_CHECK() CUDA_TRY(cudaGetLastError())
+extern long long g_crnn_launches;   // kernels launched by this library (engine.cu)
+#define LAUNCH_CHECK() do { ++g_crnn_launches; CUDA_TRY(cudaGetLastError()); } while (0)
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

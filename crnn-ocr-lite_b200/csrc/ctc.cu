@@ -191,14 +191,24 @@ __global__ void ctc_greedy_kernel(const float* __restrict__ probs, const int* __
 }
 
 // =================================================================================================
-// Beam search: one warp per sequence, prefix trie + beam state in shared memory.
+// Beam search: one warp per sequence, prefix trie + beam state in shared memory, the sorted list of leaves
+// distributed over the lanes (lane i holds the i-th best leaf).
 //
-// Equivalent (absent exact ties) to TF's sequential insert/evict over a TopN of `W` leaves: every step
-// scores the survivors (standard prefix-beam recursion using the parent's t-1 probabilities iff the parent
-// is still in the beam) and all W*(V-1) children that are not already in the beam, then keeps the global
-// top-W by total log-prob.  The trie gives every prefix one node id for its whole life, so a prefix that
-// leaves the beam and later re-enters as a child re-links to children of it that stayed -- exactly what
-// TF's persistent BeamEntry tree does.
+// This reproduces TF 1.8's CTCBeamSearchDecoder::Step *including its sequential side effects* -- it is NOT a plain
+// "score all W*(V-1) children, keep the global top-W":
+//   phase 1  every survivor gets the standard prefix-beam update (parent's t-1 probabilities iff the parent is in
+//            the beam);
+//   phase 2  parents are visited best-first (beam order).  A parent is skipped if its t-1 total does not beat the
+//            current bottom leaf, or if it was BLOCKED: TF resets the t-1 probabilities ("Deactivate child") of a
+//            survivor that has already been evicted from the leaves when its own parent reaches its label in the
+//            children loop, so that survivor never expands children in this step.  For each parent the children
+//            that are not already survivors are inserted into the leaves iff they beat the bottom (strictly, when the
+//            list is full); insertion order does not matter for the resulting set, only for the blocking test, which
+//            is evaluated in closed form: survivor c (child k_c of parent b) is blocked iff
+//            rank(c in leaves) + #{eligible children of b with label < k_c and total > total(c)} >= W.
+// The trie gives every prefix one node id for its whole life, so a prefix that leaves the beam and re-enters later as
+// a child re-links to children of it that stayed -- what TF's persistent BeamEntry tree does.
+// (oracle/beam_reference_py.py states the same formulation in Python; tests check both against the literal restatement.)
 // =================================================================================================
 struct TrieNode { short parent, label, first_child, next_sib; };
 
@@ -216,20 +226,18 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
     const unsigned FULL = 0xffffffffu;
     const int blank = V - 1, NC = V - 1;
     const int Tb = seq_len ? seq_len[b] : T;
+    const int NOID = 0x7fffffff;
 
     unsigned char* base = smraw + (size_t)wib * smem_per_warp_bytes;
-    float* in_ = (float*)base;                                   // V (padded to even)
-    float* cand = in_ + ((V + 3) & ~3);                          // W*NC
-    TrieNode* nodes = (TrieNode*)(cand + (((size_t)W * NC + 3) & ~3));   // 1 + W*T
+    float* in_ = (float*)base;                                           // V (padded)
+    TrieNode* nodes = (TrieNode*)(in_ + ((V + 3) & ~3));                 // 1 + W*T
     int* bnode = (int*)(nodes + (((size_t)1 + (size_t)W * T + 1) & ~1)); // [2][32]
-    float* bpb = (float*)(bnode + 64);                           // [2][32] blank
-    float* bpl = bpb + 64;                                       // [2][32] label
-    float* bpt = bpl + 64;                                       // [2][32] total
-    int* excl = (int*)(bpt + 64);                                // [32]
-    int* selid = excl + 32;                                      // [32]
+    float* bpb = (float*)(bnode + 64);                                   // [2][32] blank
+    float* bpl = bpb + 64;                                               // [2][32] label
+    float* bpt = bpl + 64;                                               // [2][32] total
 
-    int nn = 1;        // nodes in the trie (uniform across lanes)
-    int nb = 1;        // beam entries
+    int nn = 1;        // nodes in the trie (uniform)
+    int nb = 1;        // beam entries (uniform); slots are in descending-total order
     int cur = 0;
     if (lane == 0) {
         nodes[0].parent = -1; nodes[0].label = -1; nodes[0].first_child = -1; nodes[0].next_sib = -1;
@@ -248,121 +256,134 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
         __syncwarp();
 
         const int* on = bnode + cur * 32; const float* opb = bpb + cur * 32; const float* opl = bpl + cur * 32; const float* opt = bpt + cur * 32;
-        // (b) survivors: lane e < nb
+        // ---- phase 1: survivors (lane e < nb)
         float s_nb = NEG_INF, s_nl = NEG_INF, s_nt = NEG_INF;
-        int s_node = -1;
+        int s_node = -1, s_q = -1, s_k = -1;
         if (lane < nb) {
             s_node = on[lane];
             const TrieNode nd = nodes[s_node];
             float nl = opl[lane];
-            int ex = -1;
             if (nd.parent >= 0) {
-                int q = -1;
-                for (int i = 0; i < nb; ++i) if (on[i] == nd.parent) q = i;
-                if (q >= 0) {
-                    float prev = (nd.label == nodes[nd.parent].label) ? opb[q] : opt[q];
+                for (int i = 0; i < nb; ++i) if (on[i] == nd.parent) s_q = i;
+                if (s_q >= 0) {
+                    float prev = (nd.label == nodes[nd.parent].label) ? opb[s_q] : opt[s_q];
                     nl = lse2(nl, prev);
-                    ex = q * NC + nd.label;
                 }
                 nl += in_[nd.label];
+                s_k = nd.label;
             }
             s_nl = nl;
             s_nb = opt[lane] + in_[blank];
             s_nt = lse2(s_nb, nl);
-            excl[lane] = ex;
         }
-        // (c) children of every beam entry
-        const int ncand = nb * NC;
-        for (int c = lane; c < ncand; c += 32) {
-            int q = c / NC, k = c - q * NC;
-            float prev = (k == nodes[on[q]].label) ? opb[q] : opt[q];
-            cand[c] = in_[k] + prev;
-        }
-        __syncwarp();
-        if (lane < nb && excl[lane] >= 0) cand[excl[lane]] = NEG_INF;   // child already in the beam: handled in (b)
-        __syncwarp();
+        // ---- leaves list L over the lanes: (Lv, Lid); id<0: survivor -1-e, id>=0: child q*NC+k
+        float Lv = NEG_INF; int Lid = NOID; int nL = 0;
+        auto insert = [&](float v, int id) {     // warp-uniform call; keeps L sorted (descending), capacity W
+            int pos = __popc(__ballot_sync(FULL, Lv > v));
+            float upv = __shfl_up_sync(FULL, Lv, 1); int upi = __shfl_up_sync(FULL, Lid, 1);
+            if (lane > pos) { Lv = upv; Lid = upi; } else if (lane == pos) { Lv = v; Lid = id; }
+            if (lane >= W) { Lv = NEG_INF; Lid = NOID; }
+            if (nL < W) ++nL;
+        };
+        for (int e = 0; e < nb; ++e) insert(__shfl_sync(FULL, s_nt, e), -1 - e);
 
-        // (d) global top-W of survivors U children
-        float lv = s_nt; int lid = (lane < nb) ? -1 - lane : 0x7fffffff;   // local best (value, id)
-        if (!(lane < nb)) lv = NEG_INF;
-        for (int c = lane; c < ncand; c += 32) { float v = cand[c]; if (v > lv) { lv = v; lid = c; } }
-        bool surv_used = false;
-        int nsel = 0;
-        float my_sel_v = NEG_INF; int my_sel_id = 0;   // lane r keeps selection r
-        for (int r = 0; r < W; ++r) {
-            float bv = lv; int bl = lane;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                float ov = __shfl_xor_sync(FULL, bv, o); int ol = __shfl_xor_sync(FULL, bl, o);
-                if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+        // ---- phase 2: parents in beam order
+        bool blocked = false;     // lane e: survivor e lost its t-1 probabilities (cannot expand children)
+        for (int r = 0; r < nb; ++r) {
+            const bool r_blocked = __shfl_sync(FULL, (int)blocked, r) != 0;
+            const float ot = opt[r], ob = opb[r];
+            float bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
+            if (r_blocked || !(ot > bottom)) continue;     // is_candidate(b->oldp)
+            const int lab_r = nodes[on[r]].label;
+            const unsigned km = __ballot_sync(FULL, lane < nb && s_q == r);   // survivors that are children of r
+            // blocking test for every such survivor
+            for (unsigned m = km; m; m &= m - 1) {
+                const int c = __ffs(m) - 1;
+                const int k_c = __shfl_sync(FULL, s_k, c);
+                const float s_c = __shfl_sync(FULL, s_nt, c);
+                const unsigned pm = __ballot_sync(FULL, Lid == -1 - c);
+                bool blk;
+                if (pm == 0) blk = true;                     // already evicted from the leaves
+                else {
+                    int cnt = __ffs(pm) - 1;                 // rank of c in L
+                    for (int k0 = 0; k0 < k_c; k0 += 32) {
+                        const int k = k0 + lane;
+                        bool ok = k < k_c;
+                        for (unsigned m2 = km; m2; m2 &= m2 - 1) { const int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (k == kk) ok = false; }
+                        float x = ok ? in_[k] + ((k == lab_r) ? ob : ot) : NEG_INF;
+                        cnt += __popc(__ballot_sync(FULL, x > s_c));
+                    }
+                    blk = cnt >= W;
+                }
+                if (blk && lane == c) blocked = true;
             }
-            if (!(bv > NEG_INF)) break;
-            int wid = __shfl_sync(FULL, lid, bl);
-            if (lane == r) { my_sel_v = bv; my_sel_id = wid; }
-            ++nsel;
-            if (lane == bl) {   // consume and rescan
-                if (wid < 0) surv_used = true; else cand[wid] = NEG_INF;
-                lv = NEG_INF; lid = 0x7fffffff;
-                if (lane < nb && !surv_used) { lv = s_nt; lid = -1 - lane; }
-                for (int c = lane; c < ncand; c += 32) { float v = cand[c]; if (v > lv) { lv = v; lid = c; } }
+            // insert the eligible children of r
+            for (int k0 = 0; k0 < NC; k0 += 32) {
+                const int k = k0 + lane;
+                float x = (k < NC) ? in_[k] + ((k == lab_r) ? ob : ot) : NEG_INF;
+                for (unsigned m2 = km; m2; m2 &= m2 - 1) { int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (k == kk) x = NEG_INF; }
+                bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
+                for (unsigned m = __ballot_sync(FULL, x > bottom); m; m &= m - 1) {
+                    const int src = __ffs(m) - 1;
+                    const float v = __shfl_sync(FULL, x, src);
+                    bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
+                    if (v > bottom) insert(v, r * NC + k0 + src);
+                }
             }
         }
-        // (e) build the new beam in the other buffer
+
+        // ---- build the new beam (slot i = i-th best leaf) in the other buffer
         const int nxt = cur ^ 1;
         int* nnode = bnode + nxt * 32; float* npb = bpb + nxt * 32; float* npl = bpl + nxt * 32; float* npt = bpt + nxt * 32;
-        // survivors move their (node, blank, label, total) to the selecting lane's slot
-        for (int r = 0; r < nsel; ++r) {
-            int id = __shfl_sync(FULL, my_sel_id, r);
-            float v = __shfl_sync(FULL, my_sel_v, r);
-            if (id < 0) {
-                int e = -1 - id;
-                if (lane == e) { nnode[r] = s_node; npb[r] = s_nb; npl[r] = s_nl; npt[r] = s_nt; }
-            } else if (lane == 0) {
-                int q = id / NC, k = id - q * NC;
-                int par = on[q];
+        const int esrc = (Lid < 0) ? (-1 - Lid) : 0;
+        const int g_node = __shfl_sync(FULL, s_node, esrc);
+        const float g_nb = __shfl_sync(FULL, s_nb, esrc), g_nl = __shfl_sync(FULL, s_nl, esrc), g_nt = __shfl_sync(FULL, s_nt, esrc);
+        if (lane < nL) {
+            if (Lid < 0) { nnode[lane] = g_node; npb[lane] = g_nb; npl[lane] = g_nl; npt[lane] = g_nt; }
+            else { npb[lane] = NEG_INF; npl[lane] = Lv; npt[lane] = Lv; }
+        }
+        for (int i = 0; i < nL; ++i) {     // trie find-or-create for the new children (lane 0, sequential)
+            const int id = __shfl_sync(FULL, Lid, i);
+            if (id >= 0 && lane == 0) {
+                const int q = id / NC, k = id - q * NC;
+                const int par = on[q];
                 int c = nodes[par].first_child;
                 while (c >= 0 && nodes[c].label != k) c = nodes[c].next_sib;
                 if (c < 0) {
-                    c = nn + 0;   // allocate (lane 0 tracks the count, broadcast below)
+                    c = nn;
                     nodes[c].parent = (short)par; nodes[c].label = (short)k;
                     nodes[c].first_child = -1; nodes[c].next_sib = nodes[par].first_child;
                     nodes[par].first_child = (short)c;
                     ++nn;
                 }
-                nnode[r] = c; npb[r] = NEG_INF; npl[r] = v; npt[r] = v;
+                nnode[i] = c;
             }
         }
         nn = __shfl_sync(FULL, nn, 0);
-        nb = nsel;
+        nb = nL;
         cur = nxt;
         __syncwarp();
     }
 
-    // top path = best total
+    // top path = best total = slot 0 (slots are sorted); before the first step it is the root
     const float* fpt = bpt + cur * 32; const int* fn = bnode + cur * 32;
-    float bv = (lane < nb) ? fpt[lane] : NEG_INF; int bl = lane;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        float ov = __shfl_xor_sync(FULL, bv, o); int ol = __shfl_xor_sync(FULL, bl, o);
-        if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
-    }
     int n = 0;
     if (lane == 0) {
         // TF BeamEntry::LabelSeq: walk leaf -> root, drop a label equal to the previously visited one
         int prev = -1;
-        for (int c = fn[bl]; nodes[c].parent >= 0; c = nodes[c].parent) {
+        for (int c = fn[0]; nodes[c].parent >= 0; c = nodes[c].parent) {
             int l = nodes[c].label;
             if (!merge_repeated || l != prev) ++n;
             prev = l;
         }
         int i = n; prev = -1;
-        for (int c = fn[bl]; nodes[c].parent >= 0; c = nodes[c].parent) {
+        for (int c = fn[0]; nodes[c].parent >= 0; c = nodes[c].parent) {
             int l = nodes[c].label;
             if (!merge_repeated || l != prev) out[(size_t)b * T + (--i)] = l;
             prev = l;
         }
         out_len[b] = n;
-        if (logprob) logprob[b] = bv;
+        if (logprob) logprob[b] = fpt[0];
     }
     n = __shfl_sync(FULL, n, 0);
     for (int t = n + lane; t < T; t += 32) out[(size_t)b * T + t] = -1;
@@ -412,11 +433,10 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
     if (B <= 0) return CRNN_OK;
     if (W < 1 || W > BEAM_MAX_W) { crnn_set_error("ctc_beam: beam width %d not in [1,%d]", W, BEAM_MAX_W); return CRNN_ERR_INVALID; }
     if ((size_t)1 + (size_t)W * T > 32000) { crnn_set_error("ctc_beam: W*T too large"); return CRNN_ERR_INVALID; }
-    size_t per = sizeof(float) * ((V + 3) & ~3) + sizeof(float) * (((size_t)W * (V - 1) + 3) & ~3)
-               + sizeof(TrieNode) * (((size_t)1 + (size_t)W * T + 1) & ~1)
-               + sizeof(int) * 64 + sizeof(float) * 64 * 3 + sizeof(int) * 64;
+    size_t per = sizeof(float) * ((V + 3) & ~3) + sizeof(TrieNode) * (((size_t)1 + (size_t)W * T + 1) & ~1)
+               + sizeof(int) * 64 + sizeof(float) * 64 * 3;
     per = (per + 15) & ~(size_t)15;
-    int warps = 4;
+    int warps = 8;
     while (warps > 1 && per * warps > 200 * 1024) warps >>= 1;
     size_t smem = per * warps;
     if (smem > 227 * 1024) { crnn_set_error("ctc_beam: per-sequence state %zu B exceeds shared memory", per); return CRNN_ERR_INVALID; }

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+long long g_crnn_launches = 0;
 static thread_local char g_err[512] = "";
 void crnn_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -26,6 +27,25 @@ constexpr float kBnEps = 1e-3f, kBnMomentum = 0.99f, kKerasEps = 1e-7f;
 constexpr float kDropBlock = 0.1f, kDropDense1 = 0.4f, kDropRnn = 0.2f;
 
 struct Tensor { std::string name; int64_t offset; int64_t numel; int is_int; };
+
+// ---- per-stage profiler: CUDA-event pairs around every stage of the step, on the launching stream ----
+enum Stage { ST_STN = 0, ST_DWCONV, ST_BN_STATS, ST_GEMM_PW_FWD, ST_ACT_POOL, ST_GEMM_HEAD_FWD, ST_RNN_FWD, ST_SOFTMAX, ST_CTC,
+             ST_GEMM_HEAD_BWD, ST_RNN_BWD, ST_ACT_BWD, ST_BN_BWD, ST_GEMM_PW_DW, ST_GEMM_PW_DX, ST_DWCONV_BWD, ST_STN_BWD,
+             ST_OPTIM, ST_MISC, ST_COUNT };
+const char* kStageNames[ST_COUNT] = {"stn_fwd", "dwconv_fwd", "bn_stats", "gemm_pw_fwd", "act_pool_fwd", "gemm_head_fwd", "rnn_fwd", "softmax",
+                                     "ctc_loss_grad", "gemm_head_bwd", "rnn_bwd", "act_pool_bwd", "bn_bwd", "gemm_pw_dw", "gemm_pw_dx",
+                                     "dwconv_bwd", "stn_bwd", "optimizer", "misc"};
+struct Prof {
+    bool on = false;
+    struct Rec { int stage; cudaEvent_t a, b; double work; long long launches; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    cudaEvent_t ev() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+};
 
 struct Layout {
     std::vector<Tensor> tensors;
@@ -58,6 +78,7 @@ struct crnn_handle {
     int64_t iterations = 0;
     std::vector<std::pair<std::string, int64_t>> weights;   // trainable, Keras order
     std::vector<std::pair<std::string, int64_t>> stats;     // BN moving statistics
+    Prof prof;
 
     float* f(const std::string& name) const {
         auto it = L.index.find(name);
@@ -75,6 +96,19 @@ struct crnn_handle {
 };
 
 namespace {
+
+struct Scope {   // records a [start, stop] event pair around a stage when profiling is enabled
+    crnn_handle* h; cudaStream_t st; int idx = -1; long long l0;
+    Scope(crnn_handle* h_, cudaStream_t st_, int stage, double work) : h(h_), st(st_) {
+        if (!h->prof.on) return;
+        Prof::Rec r; r.stage = stage; r.a = h->prof.ev(); r.b = h->prof.ev(); r.work = work; r.launches = 0;
+        l0 = g_crnn_launches;
+        cudaEventRecord(r.a, st);
+        idx = (int)h->prof.recs.size(); h->prof.recs.push_back(r);
+    }
+    ~Scope() { if (idx >= 0) { cudaEventRecord(h->prof.recs[idx].b, st); h->prof.recs[idx].launches = g_crnn_launches - l0; } }
+};
+#define ST(stage, work, call) do { Scope _s(h, st, stage, (double)(work)); int _r = (call); if (_r != CRNN_OK) return _r; } while (0)
 
 int validate(const crnn_config* c) {
     if (!c) { crnn_set_error("null config"); return CRNN_ERR_INVALID; }
@@ -196,23 +230,26 @@ int pick_split(int M, int N, int K) {
 }
 
 // C = A(MxK) @ B(KxN) + bias (, relu)
-int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias, int relu,
+int gemm_nn(crnn_handle* h, int stage, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias, int relu,
             const float* sc, const float* sh, cudaStream_t st) {
     GemmArgs g; g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
     g.bias = bias; g.relu = relu; g.a_scale = sc; g.a_shift = sh;
+    Scope _s(h, st, stage, 2.0 * M * N * K);
     return launch_gemm_simt(g, st);
 }
 // dW(KinxN) += X(MxKin)^T @ dY(MxN)   (reduction over rows M; split-K atomics into pre-zeroed dW)
-int gemm_tn(const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, int Kin, int N, int M, const float* sc, const float* sh, cudaStream_t st) {
+int gemm_tn(crnn_handle* h, int stage, const float* X, int ldx, const float* dY, int ldy, float* dW, int ldw, int Kin, int N, int M, const float* sc, const float* sh, cudaStream_t st) {
     GemmArgs g; g.A = X; g.B = dY; g.C = dW; g.M = Kin; g.N = N; g.K = M; g.lda = ldx; g.ldb = ldy; g.ldc = ldw;
     g.transA = 1; g.a_scale = sc; g.a_shift = sh; g.split_k = pick_split(Kin, N, M);
     if (g.split_k == 1) g.accumulate = 1;   // grads arena is pre-zeroed; keep += semantics either way
+    Scope _s(h, st, stage, 2.0 * Kin * N * M);
     return launch_gemm_simt(g, st);
 }
 // dX(MxKin) (+)= dY(MxN) @ W(KinxN)^T
-int gemm_nt(const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int Kin, int N, int accumulate, cudaStream_t st) {
+int gemm_nt(crnn_handle* h, int stage, const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int Kin, int N, int accumulate, cudaStream_t st) {
     GemmArgs g; g.A = dY; g.B = Wt; g.C = dX; g.M = M; g.N = Kin; g.K = N; g.lda = ldy; g.ldb = ldw; g.ldc = ldx;
     g.transB = 1; g.accumulate = accumulate;
+    Scope _s(h, st, stage, 2.0 * M * Kin * N);
     return launch_gemm_simt(g, st);
 }
 
@@ -224,7 +261,7 @@ int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool 
     double* stats = reinterpret_cast<double*>(h->a("stats"));
     if (training) {
         CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-        TRY(launch_colstats(y, M, C, stats, st));
+        ST(ST_BN_STATS, 4.0 * M * C, launch_colstats(y, M, C, stats, st));
     }
     return launch_bn_finalize(stats, M, C, h->w(bnname(bn, "gamma")), h->w(bnname(bn, "beta")), h->w(bnname(bn, "moving_mean")),
                               h->w(bnname(bn, "moving_variance")), kBnEps, kBnMomentum, training ? 1 : 0,
@@ -236,11 +273,11 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
     const bool drop = training && seed != 0;
     const int H = h->H, W = h->W, U = h->U, G = h->G, T = h->T, V = h->V;
     // ---- STN (utils.py:247-258)
-    TRY(launch_stn_trunk_fwd(x, h->w("conv2d_1/kernel"), h->w("conv2d_1/bias"), h->w("conv2d_2/kernel"), h->w("conv2d_2/bias"),
+    ST(ST_STN, 0, launch_stn_trunk_fwd(x, h->w("conv2d_1/kernel"), h->w("conv2d_1/bias"), h->w("conv2d_2/kernel"), h->w("conv2d_2/bias"),
                              h->a("p1"), h->a("p2"), reinterpret_cast<int*>(h->a("p2arg")), h->a("flat"), B, H, W, st));
-    TRY(gemm_nn(h->a("flat"), h->sd.F, h->w("dense_1/kernel"), 50, h->a("loc_d1"), 50, B, 50, h->sd.F, h->w("dense_1/bias"), 1, nullptr, nullptr, st));
-    TRY(gemm_nn(h->a("loc_d1"), 50, h->w("dense_2/kernel"), 6, h->a("theta"), 6, B, 6, 50, h->w("dense_2/bias"), 0, nullptr, nullptr, st));
-    TRY(launch_stn_sample_fwd(x, h->a("theta"), h->a("a0"), B, H, W, 2, st));
+    TRY(gemm_nn(h, ST_STN, h->a("flat"), h->sd.F, h->w("dense_1/kernel"), 50, h->a("loc_d1"), 50, B, 50, h->sd.F, h->w("dense_1/bias"), 1, nullptr, nullptr, st));
+    TRY(gemm_nn(h, ST_STN, h->a("loc_d1"), 50, h->w("dense_2/kernel"), 6, h->a("theta"), 6, B, 6, 50, h->w("dense_2/bias"), 0, nullptr, nullptr, st));
+    ST(ST_STN, 0, launch_stn_sample_fwd(x, h->a("theta"), h->a("a0"), B, H, W, 2, st));
     // ---- depthwise-separable stack (utils.py:43-56, 64-70)
     const float* in = h->a("a0");
     int hh = h->Hp, ww = h->Wp;
@@ -248,39 +285,39 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         const BlockPlan& b = kBlocks[i - 1];
         const long long M = (long long)B * hh * ww;
         float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
-        TRY(launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st));
+        ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st));
         TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st));
-        TRY(gemm_nn(dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
+        TRY(gemm_nn(h, ST_GEMM_PW_FWD, dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
                     h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), st));
         TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st));
-        TRY(launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
+        ST(ST_ACT_POOL, 4.0 * M * b.cout * (1.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
                                 drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
         hh /= b.ph; ww /= b.pw; in = out;
     }
     // ---- dense1 (utils.py:72-75): (B,T,9,512) is already (B*T, 4608) with feature = w*512+c
     const int M = B * T;
-    TRY(gemm_nn(in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
-    if (drop) TRY(launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st));
+    TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
+    if (drop) ST(ST_MISC, 0, launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st));
     // ---- two bidirectional recurrent layers (utils.py:77-82)
     const float* rin = h->a("dense1"); int kin = h->TD;
     for (int layer = 1; layer <= 2; ++layer) {
         float* xp = h->a(nm("xp%d", layer)); float* hs = h->a(nm("hs%d", layer));
         for (int d = 0; d < 2; ++d)
-            TRY(gemm_nn(rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
+            TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
                         h->w(h->rnn(layer, d) + "/bias"), 0, nullptr, nullptr, st));
-        TRY(launch_rnn_fwd(h->cfg.cell, xp, h->w(h->rnn(layer, 0) + "/recurrent_kernel"), h->w(h->rnn(layer, 1) + "/recurrent_kernel"),
+        ST(ST_RNN_FWD, 0, launch_rnn_fwd(h->cfg.cell, xp, h->w(h->rnn(layer, 0) + "/recurrent_kernel"), h->w(h->rnn(layer, 1) + "/recurrent_kernel"),
                            hs, training ? h->a(nm("gates%d", layer)) : nullptr, B, T, U, st));
-        if (layer == 1) { TRY(launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
+        if (layer == 1) { ST(ST_MISC, 0, launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
     }
     const float* head_in = h->a("hs2");                                                                      // merge_mode='concat'
     if (drop) {
         CUDA_TRY(cudaMemcpyAsync(h->a("rnn2drop"), h->a("hs2"), sizeof(float) * (size_t)M * 2 * U, cudaMemcpyDeviceToDevice, st));
-        TRY(launch_dropout_fwd(h->a("rnn2drop"), (long long)M * 2 * U, kDropRnn, seed, 9, st));
+        ST(ST_MISC, 0, launch_dropout_fwd(h->a("rnn2drop"), (long long)M * 2 * U, kDropRnn, seed, 9, st));
         head_in = h->a("rnn2drop");
     }
     // ---- dense2 + softmax (utils.py:85-86)
-    TRY(gemm_nn(head_in, 2 * U, h->w("dense2/kernel"), V, h->a("logits"), V, M, V, 2 * U, h->w("dense2/bias"), 0, nullptr, nullptr, st));
-    TRY(launch_softmax_rows(h->a("logits"), h->a("softmax"), M, V, st));
+    TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, head_in, 2 * U, h->w("dense2/kernel"), V, h->a("logits"), V, M, V, 2 * U, h->w("dense2/bias"), 0, nullptr, nullptr, st));
+    ST(ST_SOFTMAX, 0, launch_softmax_rows(h->a("logits"), h->a("softmax"), M, V, st));
     return CRNN_OK;
 }
 
@@ -288,21 +325,21 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
     const int U = h->U, G = h->G, T = h->T, M = B * T;
     float* UT = h->a("UT"); float* dxp = h->a("dxp"); float* hprev = h->a("hprev"); float* rh = h->a("rh");
     for (int d = 0; d < 2; ++d)
-        TRY(launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
-    TRY(launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
+        ST(ST_MISC, 0, launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
+    ST(ST_RNN_BWD, 0, launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
     for (int d = 0; d < 2; ++d) {
         const std::string base = h->rnn(layer, d);
         const float* dxd = dxp + d * G * U;
         float* gU = h->g(base + "/recurrent_kernel");
         if (h->cfg.cell == CRNN_CELL_GRU) {
-            TRY(gemm_tn(hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, 2 * U, M, nullptr, nullptr, st));
-            TRY(gemm_tn(rh + d * U, 2 * U, dxd + 2 * U, 2 * G * U, gU + 2 * U, G * U, U, U, M, nullptr, nullptr, st));
+            TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, 2 * U, M, nullptr, nullptr, st));
+            TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, rh + d * U, 2 * U, dxd + 2 * U, 2 * G * U, gU + 2 * U, G * U, U, U, M, nullptr, nullptr, st));
         } else {
-            TRY(gemm_tn(hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, G * U, M, nullptr, nullptr, st));
+            TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, G * U, M, nullptr, nullptr, st));
         }
-        TRY(gemm_tn(rin, kin, dxd, 2 * G * U, h->g(base + "/kernel"), G * U, kin, G * U, M, nullptr, nullptr, st));
-        TRY(launch_colsum(dxd, M, G * U, 2 * G * U, h->g(base + "/bias"), st));
-        TRY(gemm_nt(dxd, 2 * G * U, h->w(base + "/kernel"), G * U, dx, kin, M, kin, G * U, d, st));
+        TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, rin, kin, dxd, 2 * G * U, h->g(base + "/kernel"), G * U, kin, G * U, M, nullptr, nullptr, st));
+        ST(ST_MISC, 0, launch_colsum(dxd, M, G * U, 2 * G * U, h->g(base + "/bias"), st));
+        TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, dxd, 2 * G * U, h->w(base + "/kernel"), G * U, dx, kin, M, kin, G * U, d, st));
     }
     return CRNN_OK;
 }
@@ -313,24 +350,24 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     const int U = h->U, T = h->T, V = h->V, M = B * T;
     CUDA_TRY(cudaMemsetAsync(h->f("arena/grads"), 0, sizeof(float) * (size_t)h->n_params, st));
     // ---- CTC (utils.py:98-103); mean over the batch (identity Keras loss, train.py:192) => scale 1/B
-    TRY(launch_ctc_loss_grad(h->a("softmax"), 2, labels, h->cfg.max_len, label_len, input_len, B, T, V, kKerasEps, loss, nullptr,
+    ST(ST_CTC, 0, launch_ctc_loss_grad(h->a("softmax"), 2, labels, h->cfg.max_len, label_len, input_len, B, T, V, kKerasEps, loss, nullptr,
                              h->a("dlogits"), 1.f / (float)B, reinterpret_cast<int*>(h->a("status")), st));
     float* gA = h->a("gA"); float* gB = h->a("gB");
     // ---- dense2
     const float* head_in = drop ? h->a("rnn2drop") : h->a("hs2");
-    TRY(gemm_tn(head_in, 2 * U, h->a("dlogits"), V, h->g("dense2/kernel"), V, 2 * U, V, M, nullptr, nullptr, st));
-    TRY(launch_colsum(h->a("dlogits"), M, V, V, h->g("dense2/bias"), st));
-    TRY(gemm_nt(h->a("dlogits"), V, h->w("dense2/kernel"), V, gA, 2 * U, M, 2 * U, V, 0, st));
-    if (drop) TRY(launch_dropout_fwd(gA, (long long)M * 2 * U, kDropRnn, seed, 9, st));
+    TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, head_in, 2 * U, h->a("dlogits"), V, h->g("dense2/kernel"), V, 2 * U, V, M, nullptr, nullptr, st));
+    ST(ST_MISC, 0, launch_colsum(h->a("dlogits"), M, V, V, h->g("dense2/bias"), st));
+    TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, h->a("dlogits"), V, h->w("dense2/kernel"), V, gA, 2 * U, M, 2 * U, V, 0, st));
+    if (drop) ST(ST_MISC, 0, launch_dropout_fwd(gA, (long long)M * 2 * U, kDropRnn, seed, 9, st));
     // ---- recurrent layers
     TRY(rnn_backward(h, 2, gA, h->a("rnn1"), U, gB, B, st));            // gB = d rnn1 (M,U)
-    TRY(launch_dup_dirs(gB, gA, M, U, st));                              // 'sum' merge: same gradient to both directions
+    ST(ST_MISC, 0, launch_dup_dirs(gB, gA, M, U, st));                              // 'sum' merge: same gradient to both directions
     TRY(rnn_backward(h, 1, gA, h->a("dense1"), h->TD, gB, B, st));      // gB = d dense1 (M,TD)
     // ---- dense1
-    TRY(launch_relu_dropout_bwd(gB, h->a("dense1"), (long long)M * h->TD, drop ? kDropDense1 : 0.f, seed, 8, st));
-    TRY(gemm_tn(h->a("block7"), h->FEAT, gB, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, st));
-    TRY(launch_colsum(gB, M, h->TD, h->TD, h->g("dense1/bias"), st));
-    TRY(gemm_nt(gB, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
+    ST(ST_MISC, 0, launch_relu_dropout_bwd(gB, h->a("dense1"), (long long)M * h->TD, drop ? kDropDense1 : 0.f, seed, 8, st));
+    TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, h->a("block7"), h->FEAT, gB, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, st));
+    ST(ST_MISC, 0, launch_colsum(gB, M, h->TD, h->TD, h->g("dense1/bias"), st));
+    TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, gB, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
     // ---- conv stack, reverse
     float* cur = gA; float* other = gB;
     int dims_h[8], dims_w[8];
@@ -344,34 +381,34 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
         const float* dw = h->a(nm("dw%d", i)); const float* pw = h->a(nm("pw%d", i));
         const int bn1 = 2 * i - 1, bn2 = 2 * i;
         CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cout, st));
-        TRY(launch_act_pool_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
+        ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (2.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
                                 other, red, B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
-        TRY(launch_bn_bwd_apply(other, pw, red, h->w(bnname(bn2, "gamma")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
+        ST(ST_BN_BWD, 12.0 * Mi * b.cout, launch_bn_bwd_apply(other, pw, red, h->w(bnname(bn2, "gamma")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
                                 h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")), Mi, b.cout, st));
-        TRY(gemm_tn(dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
+        TRY(gemm_tn(h, ST_GEMM_PW_DW, dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
                     h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
-        TRY(gemm_nt(other, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, cur, b.cin, (int)Mi, b.cin, b.cout, 0, st));
+        TRY(gemm_nt(h, ST_GEMM_PW_DX, other, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, cur, b.cin, (int)Mi, b.cin, b.cout, 0, st));
         CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cin, st));
-        TRY(launch_relu6_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+        ST(ST_ACT_BWD, 12.0 * Mi * b.cin, launch_relu6_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
                              cur, red, Mi, b.cin, st));
-        TRY(launch_bn_bwd_apply(cur, dw, red, h->w(bnname(bn1, "gamma")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+        ST(ST_BN_BWD, 12.0 * Mi * b.cin, launch_bn_bwd_apply(cur, dw, red, h->w(bnname(bn1, "gamma")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
                                 h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
         const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
-        TRY(launch_dwconv_bwd_weight(bin, cur, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, st));
-        TRY(launch_dwconv_bwd_data(cur, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
+        ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, cur, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, st));
+        ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(cur, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
         float* t = cur; cur = other; other = t;
     }
     // ---- STN: sampler -> theta -> localisation net
     CUDA_TRY(cudaMemsetAsync(h->a("dtheta"), 0, sizeof(float) * 6 * B, st));
-    TRY(launch_stn_sample_bwd(x, h->a("theta"), cur, h->a("dtheta"), B, h->H, h->W, 2, st));
-    TRY(gemm_tn(h->a("loc_d1"), 50, h->a("dtheta"), 6, h->g("dense_2/kernel"), 6, 50, 6, B, nullptr, nullptr, st));
-    TRY(launch_colsum(h->a("dtheta"), B, 6, 6, h->g("dense_2/bias"), st));
-    TRY(gemm_nt(h->a("dtheta"), 6, h->w("dense_2/kernel"), 6, h->a("dd1"), 50, B, 50, 6, 0, st));
-    TRY(launch_relu_dropout_bwd(h->a("dd1"), h->a("loc_d1"), (long long)B * 50, 0.f, 0, 0, st));
-    TRY(gemm_tn(h->a("flat"), h->sd.F, h->a("dd1"), 50, h->g("dense_1/kernel"), 50, h->sd.F, 50, B, nullptr, nullptr, st));
-    TRY(launch_colsum(h->a("dd1"), B, 50, 50, h->g("dense_1/bias"), st));
-    TRY(gemm_nt(h->a("dd1"), 50, h->w("dense_1/kernel"), 50, h->a("dflat"), h->sd.F, B, h->sd.F, 50, 0, st));
-    TRY(launch_stn_trunk_bwd(h->a("dflat"), h->a("p1"), h->a("p2"), reinterpret_cast<const int*>(h->a("p2arg")), h->w("conv2d_2/kernel"),
+    ST(ST_STN_BWD, 0, launch_stn_sample_bwd(x, h->a("theta"), cur, h->a("dtheta"), B, h->H, h->W, 2, st));
+    TRY(gemm_tn(h, ST_STN_BWD, h->a("loc_d1"), 50, h->a("dtheta"), 6, h->g("dense_2/kernel"), 6, 50, 6, B, nullptr, nullptr, st));
+    ST(ST_STN_BWD, 0, launch_colsum(h->a("dtheta"), B, 6, 6, h->g("dense_2/bias"), st));
+    TRY(gemm_nt(h, ST_STN_BWD, h->a("dtheta"), 6, h->w("dense_2/kernel"), 6, h->a("dd1"), 50, B, 50, 6, 0, st));
+    ST(ST_STN_BWD, 0, launch_relu_dropout_bwd(h->a("dd1"), h->a("loc_d1"), (long long)B * 50, 0.f, 0, 0, st));
+    TRY(gemm_tn(h, ST_STN_BWD, h->a("flat"), h->sd.F, h->a("dd1"), 50, h->g("dense_1/kernel"), 50, h->sd.F, 50, B, nullptr, nullptr, st));
+    ST(ST_STN_BWD, 0, launch_colsum(h->a("dd1"), B, 50, 50, h->g("dense_1/bias"), st));
+    TRY(gemm_nt(h, ST_STN_BWD, h->a("dd1"), 50, h->w("dense_1/kernel"), 50, h->a("dflat"), h->sd.F, B, h->sd.F, 50, 0, st));
+    ST(ST_STN_BWD, 0, launch_stn_trunk_bwd(h->a("dflat"), h->a("p1"), h->a("p2"), reinterpret_cast<const int*>(h->a("p2arg")), h->w("conv2d_2/kernel"),
                              h->g("conv2d_1/kernel"), h->g("conv2d_1/bias"), h->g("conv2d_2/kernel"), h->g("conv2d_2/bias"), nullptr, B, h->H, h->W, st));
     return CRNN_OK;
 }
@@ -444,10 +481,10 @@ int crnn_adam_step(crnn_handle* h, float lr, float b1, float b2, float eps, floa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* ss = reinterpret_cast<double*>(h->a("sumsq"));
     CUDA_TRY(cudaMemsetAsync(ss, 0, sizeof(double), st));
-    TRY(launch_sumsq(h->f("arena/grads"), h->n_params, ss, st));
+    ST(ST_OPTIM, 4.0 * h->n_params * 1, launch_sumsq(h->f("arena/grads"), h->n_params, ss, st));
     const double t = (double)(h->iterations + 1);
     const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
-    TRY(launch_adam(h->f("arena/params"), h->f("arena/grads"), h->f("arena/opt_m"), h->f("arena/opt_v"), h->n_params, ss, clipnorm, lr_t, b1, b2, eps, grad_scale, st));
+    ST(ST_OPTIM, 4.0 * h->n_params * 7, launch_adam(h->f("arena/params"), h->f("arena/grads"), h->f("arena/opt_m"), h->f("arena/opt_v"), h->n_params, ss, clipnorm, lr_t, b1, b2, eps, grad_scale, st));
     h->iterations += 1;
     return CRNN_OK;
 }
@@ -456,9 +493,9 @@ int crnn_sgd_step(crnn_handle* h, float lr, float decay, float momentum, float c
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* ss = reinterpret_cast<double*>(h->a("sumsq"));
     CUDA_TRY(cudaMemsetAsync(ss, 0, sizeof(double), st));
-    TRY(launch_sumsq(h->f("arena/grads"), h->n_params, ss, st));
+    ST(ST_OPTIM, 4.0 * h->n_params * 1, launch_sumsq(h->f("arena/grads"), h->n_params, ss, st));
     const float lr_i = (float)((double)lr * (1.0 / (1.0 + (double)decay * (double)h->iterations)));
-    TRY(launch_sgd_nesterov(h->f("arena/params"), h->f("arena/grads"), h->f("arena/opt_m"), h->n_params, ss, clipnorm, lr_i, momentum, grad_scale, st));
+    ST(ST_OPTIM, 4.0 * h->n_params * 5, launch_sgd_nesterov(h->f("arena/params"), h->f("arena/grads"), h->f("arena/opt_m"), h->n_params, ss, clipnorm, lr_i, momentum, grad_scale, st));
     h->iterations += 1;
     return CRNN_OK;
 }
@@ -519,6 +556,29 @@ int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, 
 }
 int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps, int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream) {
     return decode_host(false, probs_host, B, T, V, eps, 0, 1, out_host, out_len_host, score_host, stream);
+}
+
+long long crnn_launch_count(void) { return g_crnn_launches; }
+
+int crnn_profile_enable(crnn_handle* h, int on) {
+    if (!h) return CRNN_ERR_INVALID;
+    h->prof.on = on != 0; h->prof.recs.clear(); h->prof.used = 0;
+    return CRNN_OK;
+}
+int crnn_profile_num_stages(void) { return ST_COUNT; }
+const char* crnn_profile_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : nullptr; }
+// synchronises the device, aggregates the event pairs recorded since the last enable/report, then clears them
+int crnn_profile_report(crnn_handle* h, double* ms, double* work, long long* launches) {
+    if (!h || !ms || !work || !launches) return CRNN_ERR_INVALID;
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < ST_COUNT; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+    for (auto& r : h->prof.recs) {
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.stage] += t; work[r.stage] += r.work; launches[r.stage] += r.launches;
+    }
+    h->prof.recs.clear(); h->prof.used = 0;
+    return CRNN_OK;
 }
 
 int crnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,

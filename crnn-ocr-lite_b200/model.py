@@ -288,10 +288,9 @@ class CRNNModel:
 
     def allreduce_grads(self):
         """Data-parallel exchange (NEW capability): one NCCL sum all-reduce of the flat gradient arena."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.tensor("arena/grads"), op=dist.ReduceOp.SUM)
-            return 1.0 / dist.get_world_size()
+        from . import parallel
+        if parallel.world_size() > 1:
+            return parallel.allreduce_sum_(self.tensor("arena/grads"))
         return 1.0
 
     def _stage(self, key, arr, dtype):

@@ -1,0 +1,52 @@
+"""Data-parallel plumbing (NEW capability; the reference is single-device, train.py:111,116 -- SURVEY 0.8 / 8e).
+
+One process per GPU; the only exchange of the training step is ONE sum all-reduce of the flat fp32 gradient arena
+(NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests).  Averaging (1/world) is folded into the optimiser kernel as
+`grad_scale`; clip-by-global-norm and Adam run AFTER the reduce, identically on every rank; BatchNorm statistics stay
+per replica."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None, device=None):
+    """Initialise torch.distributed from the torchrun environment (RANK / WORLD_SIZE / MASTER_*); no-op for 1 process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or dist.is_initialized():
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+    dist.init_process_group(backend, **kw)
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def allreduce_sum_(flat: torch.Tensor) -> float:
+    """In-place sum all-reduce of the flat gradient arena; returns the scale (1/world) the optimiser must apply."""
+    w = world_size()
+    if w > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return 1.0 / w
+
+
+def broadcast_(flat: torch.Tensor, src=0):
+    """Make every replica start from rank `src`'s parameters."""
+    if world_size() > 1:
+        dist.broadcast(flat, src=src)
+
+
+def shard_batch(n_items: int, r=None, w=None):
+    """Contiguous shard [lo, hi) of a global batch for this rank (text lines are independent: no data-path collective)."""
+    r = rank() if r is None else r
+    w = world_size() if w is None else w
+    per, rem = divmod(n_items, w)
+    lo = r * per + min(r, rem)
+    return lo, lo + per + (1 if r < rem else 0)

@@ -118,6 +118,15 @@ int crnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int
               int transA, int transB, const float* a_scale, const float* a_shift, const float* bias, int relu,
               int split_k, void* stream);
 
+/* ---------------------------------------------------------------- measurement hooks (bench.py) */
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+long long crnn_launch_count(void);
+/* per-stage CUDA-event timing of the step, recorded on the launching stream while enabled */
+int crnn_profile_enable(crnn_handle* h, int on);
+int crnn_profile_num_stages(void);
+const char* crnn_profile_stage_name(int stage);
+int crnn_profile_report(crnn_handle* h, double* ms, double* work, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

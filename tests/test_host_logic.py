@@ -1,0 +1,167 @@
+"""CPU-only tests (no GPU): weight-file I/O, the C-ABI surface, the workspace layout planner, data-parallel plumbing."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_W = "/root/reference/models/OCR_mjsynth_FULL_2/final_weights.h5"
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import __graft_entry__ as g
+    g.build()
+    import crnn_b200
+    return crnn_b200
+
+
+def test_header_symbols_exported(cb):
+    """libcrnn_b200.so loads and exports every function include/crnn_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "crnn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(crnn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    lib = cb._lib.load()
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert names == set(cb._lib.SYMBOLS)
+    assert b"sm_100a" in lib.crnn_version()
+
+
+@pytest.mark.parametrize("imgh,cell,V", [(100, "gru", 38), (128, "lstm", 97)])
+def test_workspace_layout(cb, imgh, cell, V):
+    """The planner is pure host code: every Keras weight has a slot of the right size (+grad/Adam mirrors)."""
+    lib = cb._lib.load()
+    cfg = cb._lib.CrnnConfig(imgh, 32, V, 0 if cell == "gru" else 1, 256, 128, 23, 64)
+    n = ctypes.c_size_t()
+    cb._lib.check(lib.crnn_workspace_bytes(ctypes.byref(cfg), ctypes.byref(n)))
+    assert 1 << 30 < n.value < 16 << 30
+    h = ctypes.c_void_p()
+    cb._lib.check(lib.crnn_create(ctypes.byref(cfg), ctypes.c_void_p(1 << 20), n.value, ctypes.byref(h)))   # fake, never dereferenced
+    shapes = cb.weight_shapes(imgh, 32, V, cell)
+    total = 0
+    for name, shp in shapes.items():
+        info = cb._lib.TensorInfo()
+        cb._lib.check(lib.crnn_tensor_lookup(h, name.encode(), ctypes.byref(info)))
+        assert info.numel == int(np.prod(shp)), name
+        assert info.offset % 16 == 0
+        total += info.numel
+        if not name.endswith(("moving_mean", "moving_variance")):
+            for pre in ("grad/", "adam_m/", "adam_v/"):
+                i2 = cb._lib.TensorInfo()
+                cb._lib.check(lib.crnn_tensor_lookup(h, (pre + name).encode(), ctypes.byref(i2)))
+                assert i2.numel == info.numel
+    if (imgh, cell, V) == (100, "gru", 38):
+        assert total == 2831027     # models/*/model_summary.txt:156
+    info = cb._lib.TensorInfo()
+    assert lib.crnn_tensor_lookup(h, b"no/such", ctypes.byref(info)) == -4
+    assert b"no/such" in lib.crnn_last_error()
+    lib.crnn_destroy(h)
+    bad = cb._lib.CrnnConfig(101, 32, V, 0, 256, 128, 23, 64)
+    assert lib.crnn_workspace_bytes(ctypes.byref(bad), ctypes.byref(n)) == -1
+
+
+def test_no_cpu_fallback(cb):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cb._lib.CrnnError):
+        cb.CRNN(38, 23, (100, 32, 1), 128, True, 256).get_model()
+    with pytest.raises(cb._lib.CrnnError):
+        cb.DecodeCTCPred(beam_width=10, inverse_classes=list("ab")).decode(np.ones((1, 3, 3), np.float32) / 3)
+
+
+def test_hdf5_roundtrip(cb, tmp_path):
+    from collections import OrderedDict
+    rng = np.random.default_rng(0)
+    layers = OrderedDict()
+    layers["the_input"] = OrderedDict()
+    layers["conv2d_1"] = OrderedDict([("conv2d_1/kernel:0", rng.standard_normal((5, 5, 1, 20)).astype(np.float32)),
+                                      ("conv2d_1/bias:0", rng.standard_normal(20).astype(np.float32))])
+    layers["bidirectional_1"] = OrderedDict([("bidirectional_1/forward_gru_1/kernel:0", rng.standard_normal((128, 768)).astype(np.float32)),
+                                             ("bidirectional_1/backward_gru_1/bias:0", rng.standard_normal(768).astype(np.float32))])
+    for i in range(30):   # > 8 entries: several SNOD leaves
+        layers[f"batch_normalization_{i}"] = OrderedDict([(f"batch_normalization_{i}/gamma:0", rng.standard_normal(7).astype(np.float32))])
+    p = str(tmp_path / "w.h5")
+    cb.hdf5_lite.save_keras_weights(p, layers)
+    root = cb.hdf5_lite.read_h5(p)
+    assert root.attrs["layer_names"] == list(layers.keys())
+    assert root.attrs["keras_version"] == "2.2.2" and root.attrs["backend"] == "tensorflow"
+    got = cb.hdf5_lite.load_keras_weights(p)
+    flat = {f"{l}/{k[len(l) + 1:-2]}": v for l, ws in layers.items() for k, v in ws.items()}
+    assert list(got.keys()) == list(flat.keys())
+    for k in flat:
+        np.testing.assert_array_equal(got[k], flat[k])
+
+
+@pytest.mark.skipif(not os.path.exists(REF_W), reason="reference artefacts not mounted")
+def test_read_shipped_weights(cb):
+    w = cb.hdf5_lite.load_keras_weights(REF_W)
+    shapes = cb.weight_shapes(100, 32, 38, "gru")
+    assert list(w.keys()) == list(shapes.keys())          # Keras layer_names/weight_names order
+    assert all(tuple(w[k].shape) == tuple(shapes[k]) for k in shapes)
+    assert sum(v.size for v in w.values()) == 2831027
+    full = cb.hdf5_lite.read_h5(REF_W.replace("final_weights", "final_model"))
+    assert "model_weights" in full.children and "optimizer_weights" in full.children
+    assert '"beta_1": 0.5' in full.attrs["training_config"] and '"clipnorm": 5' in full.attrs["training_config"]
+
+
+def test_shard_batch(cb):
+    par = cb.parallel
+    for n, w in ((512, 8), (10, 4), (3, 4)):
+        cover = []
+        for r in range(w):
+            lo, hi = par.shard_batch(n, r, w)
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
+
+
+_DP_SCRIPT = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, %(root)r)
+import crnn_b200 as cb
+from oracle import crnn_oracle as N
+par = cb.parallel
+par.init_distributed("gloo")
+r, w = par.rank(), par.world_size()
+assert w == 2
+rng = np.random.default_rng(100 + r)
+g_local = {"a": rng.standard_normal(1000).astype(np.float32) * 3, "b": rng.standard_normal((7, 9)).astype(np.float32)}
+flat = torch.tensor(np.concatenate([v.reshape(-1) for v in g_local.values()]))
+params = torch.full((5,), float(r))
+par.broadcast_(params)
+assert torch.all(params == 0)
+scale = par.allreduce_sum_(flat)
+assert scale == 0.5
+# what a single process would compute on the concatenated batch: mean of the two per-replica gradients
+both = [np.random.default_rng(100 + k) for k in range(2)]
+ga = [{"a": q.standard_normal(1000).astype(np.float32) * 3, "b": q.standard_normal((7, 9)).astype(np.float32)} for q in both]
+mean = {k: (ga[0][k] + ga[1][k]) / 2 for k in ga[0]}
+got = (flat * scale).numpy()
+np.testing.assert_allclose(got, np.concatenate([v.reshape(-1) for v in mean.values()]), rtol=1e-6)
+# clip-by-global-norm AFTER the reduce, then Adam, identically on every rank (oracle optimiser as the stand-in)
+w0 = {k: np.zeros_like(v) for k, v in mean.items()}
+neww, norm = N.adam_step(w0, {"a": got[:1000], "b": got[1000:].reshape(7, 9)}, {}, clipnorm=5.0)
+ref, norm_ref = N.adam_step(w0, mean, {}, clipnorm=5.0)
+assert abs(norm - norm_ref) < 1e-3 and norm > 5.0
+for k in ref: np.testing.assert_allclose(neww[k], ref[k], rtol=1e-5, atol=1e-9)
+lo, hi = par.shard_batch(64)
+assert (lo, hi) == (32 * r, 32 * r + 32)
+print("rank", r, "ok")
+'''
+
+
+def test_dp_world2_gloo(tmp_path):
+    """world_size-2 gloo run of the data-parallel host logic (sum all-reduce, 1/world scale, clip after reduce)."""
+    script = tmp_path / "dp.py"
+    script.write_text(_DP_SCRIPT % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

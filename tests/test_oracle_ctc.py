@@ -127,19 +127,18 @@ def test_beam_onehot_equals_collapse_and_greedy():
         assert np.all(g[b, gn[b]:] == -1)
 
 
-def test_beam_sequential_vs_global_topk_spec():
-    """The TF sequential insert/evict equals a 'score everything then take the global top-W' formulation
-    (the GPU design) on tie-free random input -- checked with an independent numpy implementation."""
-    from oracle.beam_reference_py import beam_global_topk
-    rng = np.random.default_rng(11)
-    probs = _rand_probs(rng, 24, 25, 96)
-    out, n, _ = O.beam(probs, beam_width=10, merge_repeated=True)
-    for b in range(probs.shape[0]):
-        assert beam_global_topk(probs[b], 10, True) == list(out[b, :n[b]])
-    probs = _rand_probs(rng, 12, 52, 38, scale=6.0)
-    out, n, _ = O.beam(probs, beam_width=10, merge_repeated=True)
-    for b in range(probs.shape[0]):
-        assert beam_global_topk(probs[b], 10, True) == list(out[b, :n[b]])
+def test_beam_parent_sequential_formulation():
+    """The formulation the CUDA kernel uses (parents visited best-first, closed-form 'blocked survivor' test, top-W
+    merge per parent; oracle/beam_reference_py.py) equals the literal TF sequential insert/evict restatement --
+    including on near-uniform inputs, where TF's "Deactivate child" side effect changes the result and a naive
+    global top-W would NOT match (found on the first GPU run)."""
+    from oracle.beam_reference_py import beam_parent_sequential
+    for (B, T, V, sc, W, seed) in [(12, 25, 96, 3.0, 10, 11), (8, 52, 38, 6.0, 10, 12), (16, 66, 38, 1.0, 10, 178),
+                                   (12, 40, 38, 0.5, 10, 2), (12, 30, 20, 1.5, 5, 3), (8, 30, 12, 1.0, 32, 6), (8, 20, 8, 0.7, 4, 7)]:
+        probs = _rand_probs(np.random.default_rng(seed), B, T, V, sc)
+        out, n, _ = O.beam(probs, beam_width=W, merge_repeated=True)
+        for b in range(B):
+            assert beam_parent_sequential(probs[b], W, True) == list(out[b, :n[b]]), (B, T, V, sc, W, seed, b)
 
 
 def test_threaded_driver_matches():
