@@ -305,7 +305,7 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         for (int d = 0; d < 2; ++d)
             TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
                         h->w(h->rnn(layer, d) + "/bias"), 0, nullptr, nullptr, st));
-        ST(ST_RNN_FWD, 0, launch_rnn_fwd(h->cfg.cell, xp, h->w(h->rnn(layer, 0) + "/recurrent_kernel"), h->w(h->rnn(layer, 1) + "/recurrent_kernel"),
+        ST(ST_RNN_FWD, 4.0 * B * T * 2 * (G * U + U + (training ? h->GS * U : 0)), launch_rnn_fwd(h->cfg.cell, xp, h->w(h->rnn(layer, 0) + "/recurrent_kernel"), h->w(h->rnn(layer, 1) + "/recurrent_kernel"),
                            hs, training ? h->a(nm("gates%d", layer)) : nullptr, B, T, U, st));
         if (layer == 1) { ST(ST_MISC, 0, launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
     }
@@ -326,7 +326,7 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
     float* UT = h->a("UT"); float* dxp = h->a("dxp"); float* hprev = h->a("hprev"); float* rh = h->a("rh");
     for (int d = 0; d < 2; ++d)
         ST(ST_MISC, 0, launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
-    ST(ST_RNN_BWD, 0, launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
+    ST(ST_RNN_BWD, 4.0 * B * T * 2 * (2 * U + h->GS * U + G * U + 2 * U), launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
     for (int d = 0; d < 2; ++d) {
         const std::string base = h->rnn(layer, d);
         const float* dxd = dxp + d * G * U;

@@ -379,8 +379,8 @@ def loss_and_grads(w_np, x, labels, label_len, input_len, cfg, masks=None, dtype
     loss = per.mean()
     names = [k for k in w if is_trainable(k)]
     grads = torch.autograd.grad(loss, [w[k] for k in names], allow_unused=True)
-    g = OrderedDict((k, (gi if gi is not None else torch.zeros_like(w[k])).detach().numpy()) for k, gi in zip(names, grads))
-    return float(loss), per.detach().numpy(), g, OrderedDict((k, v.numpy()) for k, v in new_stats.items()), keep
+    g = OrderedDict((k, (gi if gi is not None else torch.zeros_like(w[k])).detach().to(torch.float32).numpy()) for k, gi in zip(names, grads))
+    return float(loss.detach()), per.detach().numpy(), g, OrderedDict((k, v.to(torch.float32).numpy()) for k, v in new_stats.items()), keep
 
 
 def clip_by_global_norm(grads, clipnorm=5.0):

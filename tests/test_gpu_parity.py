@@ -236,34 +236,42 @@ def test_sampler_bitexact_given_theta(cb):
 @pytest.mark.parametrize("imgh,cell", [(100, "gru"), (128, "lstm")])
 def test_train_step_parity(cb, imgh, cell):
     """Full training forward/backward (BN batch statistics, CTC, BPTT, STN) + Adam vs torch autograd on the oracle.
-    Dropout disabled on both sides (RNG streams cannot match TF)."""
+    Dropout disabled on both sides (RNG streams cannot match TF).
+    Reference = the oracle run in float64; the fp32 oracle (what Keras/TF computes in) gives the yardstick: the CUDA
+    gradient of every tensor must be within max(3e-3, 4 x fp32-oracle error) of the fp64 truth, relative to the
+    tensor's max-abs entry (these sums cancel heavily: 1e5..4e5 terms of random sign)."""
     cfg = N.Cfg(imgh=imgh, cell=cell)
     B = 6
     w, m = _make(cb, cfg, B, 3)
     x, lab, L, il = N.synth_batch(cfg, B, 33)
-    loss_o, per_o, g_o, stats_o, keep = N.loss_and_grads(w, x, lab, L, il, cfg)
+    loss_o, per_o, g32, stats_o, keep = N.loss_and_grads(w, x, lab, L, il, cfg)
+    loss64, per64, g64, _, _ = N.loss_and_grads(w, x, lab, L, il, cfg, dtype=torch.float64)
     d = "cuda"
     per = m.train_fwd_bwd_device(torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d), dropout_seed=0)
-    np.testing.assert_allclose(per.cpu().numpy(), per_o, rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(per.cpu().numpy(), per64, rtol=2e-4, atol=2e-3)
     g = m.get_grads()
-    # gradient tolerance: relative to the largest entry of each tensor (fp32 accumulation over up to 4e5 rows)
-    for k, want in g_o.items():
-        got = g[k]
-        scale = max(np.abs(want).max(), 1e-6)
-        err = np.abs(got - want).max() / scale
-        assert err < 3e-3, f"grad {k}: rel-to-max err {err:.2e} (max |g| {scale:.3e})"
+    rows, bad = [], []
+    for k, want in g64.items():
+        scale = max(np.abs(want).max(), 1e-9)
+        e_gpu = np.abs(g[k] - want).max() / scale
+        e_ref = np.abs(g32[k] - want).max() / scale
+        rows.append((e_gpu, e_ref, scale, k))
+        if e_gpu > max(3e-3, 4 * e_ref):
+            bad.append(k)
+    report = "\n".join("%-55s gpu %.2e  fp32-oracle %.2e  max|g| %.3e" % (k, a, r, sc) for a, r, sc, k in sorted(rows, reverse=True))
+    print(report)
+    assert not bad, "gradients out of tolerance: %s\n%s" % (bad, report)
     neww = m.get_weights()
     for k, want in stats_o.items():
         np.testing.assert_allclose(neww[k], want, rtol=1e-4, atol=1e-5, err_msg=k)
-    # Adam(lr 1e-4, b1 .5, b2 .999, eps 1e-7, clipnorm 5) step (train.py:188)
+    # Adam(lr 1e-4, b1 .5, b2 .999, eps 1e-7, clipnorm 5) step (train.py:188) on the CUDA gradients themselves
     m.compile(optimizer=cb.Adam(lr=1e-4, beta_1=0.5, beta_2=0.999, epsilon=1e-7, clipnorm=5.0))
     m.optimizer_step()
-    state = {}
-    w2, norm = N.adam_step(w, g_o, state, lr=1e-4, b1=0.5, b2=0.999, eps=1e-7, clipnorm=5.0)
+    w2, norm = N.adam_step(w, g, {}, lr=1e-4, b1=0.5, b2=0.999, eps=1e-7, clipnorm=5.0)
     got = m.get_weights()
-    for k in g_o:
-        # Adam's first step moves every weight by ~lr*sign(g): compare the update, tolerance 2% of lr
-        np.testing.assert_allclose(got[k] - w[k], w2[k] - w[k], rtol=0, atol=2e-6 + 0.02e-4, err_msg=k)
+    for k in g:
+        np.testing.assert_allclose(got[k] - w[k], w2[k] - w[k], rtol=0, atol=1e-7, err_msg=k)
+    assert m.iterations() == 1
 
 
 def test_dropout_statistics(cb):
@@ -274,12 +282,12 @@ def test_dropout_statistics(cb):
     d = "cuda"
     args = (torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d))
     m.train_fwd_bwd_device(*args, dropout_seed=0)
-    a_off = m.activation("block4").copy()
+    a_off = m.activation("block1").copy()          # first dropout: its input does not depend on any mask
     m.train_fwd_bwd_device(*args, dropout_seed=12345)
-    a_on = m.activation("block4")
+    a_on = m.activation("block1")
     nz = a_off != 0
     kept = a_on[nz] != 0
-    assert abs(kept.mean() - 0.9) < 0.01                     # Dropout(0.1), utils.py:56
+    assert abs(kept.mean() - 0.9) < 0.005                    # Dropout(0.1), utils.py:56
     np.testing.assert_allclose(a_on[nz][kept], a_off[nz][kept] / 0.9, rtol=2e-3, atol=1e-3)
     g1 = m.get_grads()["dense2/kernel"].copy()
     m.train_fwd_bwd_device(*args, dropout_seed=12345)      # stateless masks: same seed -> same step
