@@ -3,6 +3,7 @@
 // separable blocks -> dense1 -> 2 x Bidirectional GRU/LSTM -> dense2 -> softmax -> CTC (utils.py:98-103), the full
 // backward of that graph and the Keras optimiser step (train.py:187-192).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -79,6 +80,7 @@ struct crnn_handle {
     std::vector<std::pair<std::string, int64_t>> weights;   // trainable, Keras order
     std::vector<std::pair<std::string, int64_t>> stats;     // BN moving statistics
     Prof prof;
+    bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
 
     float* f(const std::string& name) const {
         auto it = L.index.find(name);
@@ -305,8 +307,13 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         for (int d = 0; d < 2; ++d)
             TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
                         h->w(h->rnn(layer, d) + "/bias"), 0, nullptr, nullptr, st));
-        ST(ST_RNN_FWD, 4.0 * B * T * 2 * (G * U + U + (training ? h->GS * U : 0)), launch_rnn_fwd(h->cfg.cell, xp, h->w(h->rnn(layer, 0) + "/recurrent_kernel"), h->w(h->rnn(layer, 1) + "/recurrent_kernel"),
-                           hs, training ? h->a(nm("gates%d", layer)) : nullptr, B, T, U, st));
+        {
+            const float* U0 = h->w(h->rnn(layer, 0) + "/recurrent_kernel"); const float* U1 = h->w(h->rnn(layer, 1) + "/recurrent_kernel");
+            float* gsave = training ? h->a(nm("gates%d", layer)) : nullptr;
+            const double work = 4.0 * B * T * 2 * (G * U + U + (training ? h->GS * U : 0));
+            if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) ST(ST_RNN_FWD, work, launch_gru_fwd_cluster(xp, U0, U1, hs, gsave, B, T, st));
+            else ST(ST_RNN_FWD, work, launch_rnn_fwd(h->cfg.cell, xp, U0, U1, hs, gsave, B, T, U, st));
+        }
         if (layer == 1) { ST(ST_MISC, 0, launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
     }
     const float* head_in = h->a("hs2");                                                                      // merge_mode='concat'
@@ -324,9 +331,15 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
 int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const float* rin, int kin, float* dx /*(M,kin)*/, int B, cudaStream_t st) {
     const int U = h->U, G = h->G, T = h->T, M = B * T;
     float* UT = h->a("UT"); float* dxp = h->a("dxp"); float* hprev = h->a("hprev"); float* rh = h->a("rh");
-    for (int d = 0; d < 2; ++d)
-        ST(ST_MISC, 0, launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
-    ST(ST_RNN_BWD, 4.0 * B * T * 2 * (2 * U + h->GS * U + G * U + 2 * U), launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
+    const double bwork = 4.0 * B * T * 2 * (2 * U + h->GS * U + G * U + 2 * U);
+    if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) {
+        ST(ST_RNN_BWD, bwork, launch_gru_bwd_cluster(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
+                                                     h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, rh, B, T, st));
+    } else {
+        for (int d = 0; d < 2; ++d)
+            ST(ST_MISC, 0, launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
+        ST(ST_RNN_BWD, bwork, launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
+    }
     for (int d = 0; d < 2; ++d) {
         const std::string base = h->rnn(layer, d);
         const float* dxd = dxp + d * G * U;
@@ -434,6 +447,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     crnn_handle* h = new crnn_handle(); h->cfg = *cfg; plan(h);
     if ((size_t)h->L.cursor > workspace_bytes) { crnn_set_error("workspace too small: need %lld bytes", (long long)h->L.cursor); delete h; return CRNN_ERR_NOMEM; }
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
+    { const char* e = getenv("CRNN_RNN_V1"); h->rnn_v1 = e && e[0] == '1'; }
     *out = h;
     return CRNN_OK;
 }

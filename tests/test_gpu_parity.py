@@ -259,8 +259,15 @@ def test_train_step_parity(cb, imgh, cell):
         if e_gpu > max(3e-3, 4 * e_ref):
             bad.append(k)
     report = "\n".join("%-55s gpu %.2e  fp32-oracle %.2e  max|g| %.3e" % (k, a, r, sc) for a, r, sc, k in sorted(rows, reverse=True))
-    print(report)
-    assert not bad, "gradients out of tolerance: %s\n%s" % (bad, report)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    open("gpurun_out/grad_parity_%d_%s.txt" % (imgh, cell), "w").write(report + "\n")
+    assert not bad, "gradients out of tolerance: %s\n%s" % (bad, report[:3000])
+    # the recurrent head is well conditioned (no BN/ReLU6/max-pool switching downstream of it): tight bound
+    for a, r, sc, k in rows:
+        if k.startswith(("dense2", "bidirectional")):
+            assert a < 2e-3, (k, a)
+        assert a < 0.15, (k, a)
     neww = m.get_weights()
     for k, want in stats_o.items():
         np.testing.assert_allclose(neww[k], want, rtol=1e-4, atol=1e-5, err_msg=k)
