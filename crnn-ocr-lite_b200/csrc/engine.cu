@@ -80,6 +80,7 @@ struct crnn_handle {
     std::vector<std::pair<std::string, int64_t>> weights;   // trainable, Keras order
     std::vector<std::pair<std::string, int64_t>> stats;     // BN moving statistics
     Prof prof;
+    bool gemm_simt = false;   // CRNN_GEMM_SIMT=1: fp32 SIMT GEMM for the pointwise convs instead of the tcgen05 3xTF32 kernel
     bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
 
     float* f(const std::string& name) const {
@@ -215,6 +216,12 @@ void plan(crnn_handle* h) {
     A("dxp", M * 2 * h->G * h->U); A("hprev", M * 2 * h->U); A("rh", M * 2 * h->U);
     A("UT", (int64_t)2 * h->G * h->U * h->U);
     A("dtheta", B * 6); A("dd1", B * 50); A("dflat", B * h->sd.F);
+    for (int i = 2; i <= 7; ++i) {   // pre-swizzled hi/lo weight images of the tcgen05 pointwise kernel (gemm_tc.cu)
+        const BlockPlan& b = kBlocks[i - 1];
+        char nm2[32];
+        snprintf(nm2, sizeof(nm2), "wimg_fwd%d", i); A(nm2, (int64_t)tc_weight_image_floats(b.cout, b.cin));
+        snprintf(nm2, sizeof(nm2), "wimg_dx%d", i); A(nm2, (int64_t)tc_weight_image_floats(b.cin, b.cout));
+    }
     L.add("act/stats", 2 * 512, 8); L.add("act/red", 2 * 512, 8); L.add("act/sumsq", 1, 8);
     L.add("act/status", 1, 4, 1);
     L.add("act/labels", B * c.max_len, 4, 1); L.add("act/label_len", B, 4, 1); L.add("act/input_len", B, 4, 1);
@@ -259,9 +266,9 @@ std::string bnname(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b)
 std::string actbn(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b), "bn%d/%s", bn, leaf); return b; }
 std::string nm(const char* fmt, int i) { char b[64]; snprintf(b, sizeof(b), fmt, i); return b; }
 
-int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool training, cudaStream_t st) {
+int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool training, cudaStream_t st, bool stats_ready = false) {
     double* stats = reinterpret_cast<double*>(h->a("stats"));
-    if (training) {
+    if (training && !stats_ready) {
         CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
         ST(ST_BN_STATS, 4.0 * M * C, launch_colstats(y, M, C, stats, st));
     }
@@ -289,9 +296,19 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
         ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st));
         TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st));
-        TRY(gemm_nn(h, ST_GEMM_PW_FWD, dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
-                    h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), st));
-        TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st));
+        const bool tc = !h->gemm_simt && (b.cin % 32 == 0);
+        if (tc) {
+            float* img = h->a(nm("wimg_fwd%d", i));
+            ST(ST_MISC, 0, launch_prep_weight_images(h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cout, b.cin, 1, img, st));
+            double* stats = reinterpret_cast<double*>(h->a("stats"));
+            if (training) CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * b.cout, st));
+            ST(ST_GEMM_PW_FWD, 2.0 * M * b.cout * b.cin, launch_xw_gemm_tc(dw, b.cin, img, pw, b.cout, (int)M, b.cout, b.cin,
+                                                                          h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), training ? stats : nullptr, st));
+        } else {
+            TRY(gemm_nn(h, ST_GEMM_PW_FWD, dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
+                        h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), st));
+        }
+        TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st, tc));
         ST(ST_ACT_POOL, 4.0 * M * b.cout * (1.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
                                 drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
         hh /= b.ph; ww /= b.pw; in = out;
@@ -357,6 +374,38 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
     return CRNN_OK;
 }
 
+// backward of depthwise-separable block i: `cur` holds d(block output) on entry and is clobbered; d(block input) lands in `other`
+int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* other, int B, bool drop, uint64_t seed, cudaStream_t st) {
+    double* red = reinterpret_cast<double*>(h->a("red"));
+    const BlockPlan& b = kBlocks[i - 1];
+    const long long Mi = (long long)B * hh * ww;
+    const float* dw = h->a(nm("dw%d", i)); const float* pw = h->a(nm("pw%d", i));
+    const int bn1 = 2 * i - 1, bn2 = 2 * i;
+    CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cout, st));
+    ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (2.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
+                            other, red, B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
+    ST(ST_BN_BWD, 12.0 * Mi * b.cout, launch_bn_bwd_apply(other, pw, red, h->w(bnname(bn2, "gamma")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
+                            h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")), Mi, b.cout, st));
+    TRY(gemm_tn(h, ST_GEMM_PW_DW, dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
+                h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
+    if (!h->gemm_simt && (b.cout % 32 == 0) && (b.cin % 4 == 0)) {
+        float* img = h->a(nm("wimg_dx%d", i));
+        ST(ST_MISC, 0, launch_prep_weight_images(h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, 0, img, st));
+        ST(ST_GEMM_PW_DX, 2.0 * Mi * b.cin * b.cout, launch_xw_gemm_tc(other, b.cout, img, cur, b.cin, (int)Mi, b.cin, b.cout, nullptr, nullptr, nullptr, st));
+    } else {
+        TRY(gemm_nt(h, ST_GEMM_PW_DX, other, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, cur, b.cin, (int)Mi, b.cin, b.cout, 0, st));
+    }
+    CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cin, st));
+    ST(ST_ACT_BWD, 12.0 * Mi * b.cin, launch_relu6_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+                         cur, red, Mi, b.cin, st));
+    ST(ST_BN_BWD, 12.0 * Mi * b.cin, launch_bn_bwd_apply(cur, dw, red, h->w(bnname(bn1, "gamma")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+                            h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
+    const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
+    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, cur, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, st));
+    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(cur, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
+    return CRNN_OK;
+}
+
 int backward(crnn_handle* h, const float* x, const int* labels, const int* label_len, const int* input_len, int B,
              float* loss, uint64_t seed, cudaStream_t st) {
     const bool drop = seed != 0;
@@ -386,29 +435,8 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     int dims_h[8], dims_w[8];
     dims_h[1] = h->Hp; dims_w[1] = h->Wp;
     for (int i = 1; i < 7; ++i) { dims_h[i + 1] = dims_h[i] / kBlocks[i - 1].ph; dims_w[i + 1] = dims_w[i] / kBlocks[i - 1].pw; }
-    double* red = reinterpret_cast<double*>(h->a("red"));
     for (int i = 7; i >= 1; --i) {
-        const BlockPlan& b = kBlocks[i - 1];
-        const int hh = dims_h[i], ww = dims_w[i];
-        const long long Mi = (long long)B * hh * ww;
-        const float* dw = h->a(nm("dw%d", i)); const float* pw = h->a(nm("pw%d", i));
-        const int bn1 = 2 * i - 1, bn2 = 2 * i;
-        CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cout, st));
-        ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (2.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
-                                other, red, B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
-        ST(ST_BN_BWD, 12.0 * Mi * b.cout, launch_bn_bwd_apply(other, pw, red, h->w(bnname(bn2, "gamma")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
-                                h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")), Mi, b.cout, st));
-        TRY(gemm_tn(h, ST_GEMM_PW_DW, dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
-                    h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
-        TRY(gemm_nt(h, ST_GEMM_PW_DX, other, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, cur, b.cin, (int)Mi, b.cin, b.cout, 0, st));
-        CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cin, st));
-        ST(ST_ACT_BWD, 12.0 * Mi * b.cin, launch_relu6_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                             cur, red, Mi, b.cin, st));
-        ST(ST_BN_BWD, 12.0 * Mi * b.cin, launch_bn_bwd_apply(cur, dw, red, h->w(bnname(bn1, "gamma")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                                h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
-        const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
-        ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, cur, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, st));
-        ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(cur, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
+        TRY(block_backward(h, i, dims_h[i], dims_w[i], cur, other, B, drop, seed, st));
         float* t = cur; cur = other; other = t;
     }
     // ---- STN: sampler -> theta -> localisation net
@@ -448,6 +476,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     if ((size_t)h->L.cursor > workspace_bytes) { crnn_set_error("workspace too small: need %lld bytes", (long long)h->L.cursor); delete h; return CRNN_ERR_NOMEM; }
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_RNN_V1"); h->rnn_v1 = e && e[0] == '1'; }
+    { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     *out = h;
     return CRNN_OK;
 }
@@ -571,6 +600,31 @@ int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, 
 int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps, int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream) {
     return decode_host(false, probs_host, B, T, V, eps, 0, 1, out_host, out_len_host, score_host, stream);
 }
+
+int crnn_gemm_tc(const float* X, int ldx, const float* W, int ldw, int w_transposed, float* out, int ldo, int M, int N, int K,
+                 const float* x_scale, const float* x_shift, double* stats, float* img_scratch, void* stream) {
+    if (!X || !W || !out || !img_scratch) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TRY(launch_prep_weight_images(W, ldw, N, K, w_transposed, img_scratch, st));
+    return launch_xw_gemm_tc(X, ldx, img_scratch, out, ldo, M, N, K, x_scale, x_shift, stats, st);
+}
+// teacher-forced backward of ONE conv block (parity tests): after a training-mode forward of batch B, takes d(block_i output)
+// (numel of act/block{i}) from dout_dev, zeroes the gradient arena, runs the block's backward and copies d(block_i input) to din_dev.
+int crnn_debug_block_backward(crnn_handle* h, int block, const float* dout_dev, float* din_dev, int B, uint64_t dropout_seed, void* stream) {
+    if (!h || !dout_dev || !din_dev || block < 1 || block > 7 || B < 1 || B > h->maxB) { crnn_set_error("bad argument"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int hh = h->Hp, ww = h->Wp;
+    for (int i = 1; i < block; ++i) { hh /= kBlocks[i - 1].ph; ww /= kBlocks[i - 1].pw; }
+    const BlockPlan& b = kBlocks[block - 1];
+    const size_t n_out = (size_t)B * (hh / b.ph) * (ww / b.pw) * b.cout, n_in = (size_t)B * hh * ww * b.cin;
+    CUDA_TRY(cudaMemsetAsync(h->f("arena/grads"), 0, sizeof(float) * (size_t)h->n_params, st));
+    CUDA_TRY(cudaMemcpyAsync(h->a("gA"), dout_dev, sizeof(float) * n_out, cudaMemcpyDeviceToDevice, st));
+    TRY(block_backward(h, block, hh, ww, h->a("gA"), h->a("gB"), B, dropout_seed != 0, dropout_seed, st));
+    CUDA_TRY(cudaMemcpyAsync(din_dev, h->a("gB"), sizeof(float) * n_in, cudaMemcpyDeviceToDevice, st));
+    return CRNN_OK;
+}
+
+long long crnn_gemm_tc_scratch_floats(int N, int K) { return (long long)tc_weight_image_floats(N, K); }
 
 long long crnn_launch_count(void) { return g_crnn_launches; }
 

@@ -1,0 +1,284 @@
+// gemm_tc.cu -- 5th-gen tensor-core (tcgen05 / TMEM) kernel for the pointwise 1x1 convolutions of the depthwise-separable
+// stack (reference utils.py:47) and their input-gradient:   out[m][n] = sum_k f(X[m][k]) * Wop[n][k]
+//
+//   forward : X = raw depthwise output (M pixels x Cin), f = BatchNorm + ReLU6 fused on load, Wop = kernel^T (Cout x Cin)
+//   dX      : X = dY (M x Cout), f = identity, Wop = kernel (Cin x Cout)
+//
+// fp32 fidelity on TF32 tensor cores: every operand is split a = hi + lo (hi = RN-to-tf32(a), lo = a - hi, exact) and
+// three MMAs  hi*hi + lo*hi + hi*lo  are accumulated in fp32 in TMEM ("3xTF32"; the dropped lo*lo term is 2^-22 relative),
+// which keeps the stack inside the fp32 tolerance of the parity tests.
+//
+// The problem is computed TRANSPOSED on the tensor core:  D[n][m] (128 channels = TMEM lanes, 128 pixels = TMEM columns)
+//   UMMA A operand (128 x K, K-major) = 16 KB pre-swizzled weight images (hi, lo) written once per step by
+//                                       prep_weight_images_kernel, staged by ONE cp.async.bulk (TMA engine) per image;
+//   UMMA B operand (128 pixels x K, K-major) = the activation tile: 4 producer warps load it (coalesced 128-byte rows), apply
+//                                       BN+ReLU6, split hi/lo and store it into the canonical SWIZZLE_128B layout.
+// so the epilogue is free of transposes: a warp owns 32 consecutive channels (its TMEM lane quarter), each thread reads its
+// channel's 128 pixel values with tcgen05.ld and (a) stores are 128-byte coalesced per pixel row, (b) the BatchNorm batch
+// statistics of the output (sum, sum of squares per channel) are plain in-thread reductions -> fused, no extra pass.
+//
+// Pipeline: 3 smem stages of {Whi, Wlo, Xhi, Xlo} x (128 rows x 32 fp32) = 64 KB; mbarriers full[s] (128 producer arrivals + 1 expect_tx +
+// bulk-copy transaction bytes), empty[s] (tcgen05.commit), acc (tcgen05.commit after the last k-block).
+// Warp 4 = TMEM allocator + single-thread MMA issuer.  One CTA per SM (192 KB smem), grid = (channel tiles, pixel tiles).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int TC_BP = 128;        // pixels per CTA  (UMMA N)
+constexpr int TC_BC = 128;        // channels per CTA (UMMA M)
+constexpr int TC_BK = 32;         // fp32 per k-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_FLOATS = 128 * TC_BK;            // 4096 floats = 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_FLOATS * 4; // Whi, Wlo, Xhi, Xlo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 160;
+
+// ---- canonical K-major SWIZZLE_128B placement of element (row r, k) inside a 128 x 32 fp32 tile (float offset)
+__host__ __device__ __forceinline__ int sw128_off(int r, int k) {
+    return (r >> 3) * 256 + (r & 7) * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();   // ~2 s
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BP >> 3) << 17) | ((uint32_t)(TC_BC >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TcArgs {
+    const float* X; int ldx;          // (M, K) activations, row stride ldx
+    const float* Wimg;                // weight images: [(ct*KB + kb)*2 + hl][4096]
+    float* out; int ldo;              // (M, N)
+    int M, N, K;
+    const float* x_scale; const float* x_shift;   // optional BN+ReLU6 on X (per k)
+    double* stats;                    // optional [2*N] column sum / sum of squares of out
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024-B alignment
+    float* stage_base = (float*)smem;
+    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = bars; uint64_t* empty = bars + TC_STAGES; uint64_t* accb = bars + 2 * TC_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ct = blockIdx.x;                 // channel tile
+    const int m0 = blockIdx.y * TC_BP;         // first pixel
+    const int KB = a.K / TC_BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }   // 128 producers + the expect_tx arrival
+        mbar_init(accb, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {   // TMEM: 128 columns (fp32 accumulator 128 lanes x 128 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =========================== producers: activation tile transform + weight bulk copies ===========================
+        const int c8 = tid & 7;                 // 16-byte chunk (4 k) inside the 128-byte row
+        const int r0 = tid >> 3;                // first row handled by this thread (rows r0 + 16*i)
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (kb / TC_STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);       // first pass returns immediately (fresh barrier, parity 1)
+            float* Whi = stage_base + (size_t)s * (4 * TC_TILE_FLOATS);
+            float* Wlo = Whi + TC_TILE_FLOATS; float* Xhi = Wlo + TC_TILE_FLOATS; float* Xlo = Xhi + TC_TILE_FLOATS;
+            if (tid == 0) {
+                const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
+                mbar_arrive_expect_tx(&full[s], 2 * TC_TILE_FLOATS * 4);
+                bulk_g2s(Whi, src, TC_TILE_FLOATS * 4, &full[s]);
+                bulk_g2s(Wlo, src + TC_TILE_FLOATS, TC_TILE_FLOATS * 4, &full[s]);
+            }
+            const int k = kb * TC_BK + c8 * 4;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.x_scale) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + k)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + k)); }
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + r0 + 16 * i;
+                v[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 16 * i;
+                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                if (a.x_scale) {
+                    x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
+                    x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
+                    if (m0 + r >= a.M) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                }
+                uint32_t hi[4]; float lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(x[q]); lo[q] = x[q] - __uint_as_float(hi[q]); }
+                const int off = (r >> 3) * 256 + (r & 7) * 32 + ((c8 ^ (r & 7)) << 2);
+                *reinterpret_cast<uint4*>(Xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(Xlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(&full[s]);
+        }
+        // =========================== epilogue: TMEM -> registers -> coalesced global stores (+ BN statistics) ===========================
+        mbar_wait(accb, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int n = ct * TC_BC + warp * 32 + lane;          // this thread's output channel
+        const bool n_ok = n < a.N;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BP; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const int m = m0 + c0 + p;
+                if (m < a.M && n_ok) {
+                    const float val = __uint_as_float(r[p]);
+                    a.out[(size_t)m * a.ldo + n] = val;          // 32 lanes = 32 consecutive channels: 128-byte coalesced
+                    s1 += val; s2 = fmaf(val, val, s2);
+                }
+            }
+        }
+        if (a.stats && n_ok) { atomicAdd(a.stats + n, (double)s1); atomicAdd(a.stats + a.N + n, (double)s2); }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // =========================== warp 4: single-thread MMA issue ===========================
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (kb / TC_STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t whi = smem_u32(stage_base + (size_t)s * (4 * TC_TILE_FLOATS));
+                const uint32_t wlo = whi + TC_TILE_FLOATS * 4, xhi = wlo + TC_TILE_FLOATS * 4, xlo = xhi + TC_TILE_FLOATS * 4;
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {      // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
+                    const uint32_t o = ks * 32;
+                    umma_tf32(tmem_base, umma_desc(wlo + o), umma_desc(xhi + o), (kb | ks) ? 1u : 0u);   // small terms first
+                    umma_tf32(tmem_base, umma_desc(whi + o), umma_desc(xlo + o), 1u);
+                    umma_tf32(tmem_base, umma_desc(whi + o), umma_desc(xhi + o), 1u);
+                }
+                umma_commit(&empty[s]);                       // frees the stage when these MMAs have read it
+                if (kb == KB - 1) umma_commit(accb);          // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
+    }
+}
+
+// Wimg[((ct*KB + kb)*2 + hl)*4096 + sw128_off(r, kk)] for Wop[n = ct*128 + r][k = kb*32 + kk]; rows n >= N are zero.
+//   transposed=1: Wop[n][k] = W[k*ldw + n]  (forward: Keras kernel is (Cin, Cout));  0: Wop[n][k] = W[n*ldw + k]  (dX)
+__global__ void prep_weight_images_kernel(const float* __restrict__ W, int ldw, int N, int K, int transposed, float* __restrict__ img)
+{
+    const int KB = K / TC_BK;
+    const int NT = (N + TC_BC - 1) / TC_BC;
+    const long long total = (long long)NT * TC_BC * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int n, k;
+        if (transposed) { n = (int)(i % (NT * TC_BC)); k = (int)(i / (NT * TC_BC)); }    // coalesced reads along n
+        else            { k = (int)(i % K); n = (int)(i / K); }                           // coalesced reads along k
+        float w = 0.f;
+        if (n < N) w = transposed ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k];
+        const uint32_t hi = to_tf32(w);
+        const float lo = w - __uint_as_float(hi);
+        const int ct = n / TC_BC, r = n % TC_BC, kb = k / TC_BK, kk = k % TC_BK;
+        float* t = img + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
+        const int off = sw128_off(r, kk);
+        t[off] = __uint_as_float(hi);
+        t[TC_TILE_FLOATS + off] = lo;
+    }
+}
+}  // namespace
+
+size_t tc_weight_image_floats(int N, int K) { return (size_t)((N + TC_BC - 1) / TC_BC) * (K / TC_BK) * 2 * TC_TILE_FLOATS; }
+
+int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transposed, float* img, cudaStream_t st)
+{
+    if (K % TC_BK) { crnn_set_error("gemm_tc: K=%d must be a multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
+    long long total = (long long)((N + TC_BC - 1) / TC_BC) * TC_BC * K;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    prep_weight_images_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K, transposed, img);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
+
+int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
+                      const float* x_scale, const float* x_shift, double* stats, cudaStream_t st)
+{
+    if (M <= 0 || N <= 0) return CRNN_OK;
+    if (K % TC_BK || K <= 0) { crnn_set_error("gemm_tc: K=%d must be a positive multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
+    if ((ldx % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Wimg) & 15)) { crnn_set_error("gemm_tc: X/Wimg must be 16-byte aligned, ldx %% 4 == 0"); return CRNN_ERR_INVALID; }
+    static bool configured = false;
+    if (!configured) { CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); configured = true; }
+    TcArgs a; a.X = X; a.ldx = ldx; a.Wimg = Wimg; a.out = out; a.ldo = ldo; a.M = M; a.N = N; a.K = K;
+    a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats;
+    dim3 grid((N + TC_BC - 1) / TC_BC, (M + TC_BP - 1) / TC_BP);
+    xw_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}

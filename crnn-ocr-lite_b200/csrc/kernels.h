@@ -17,6 +17,12 @@ struct GemmArgs {
 };
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 
+// ---- gemm_tc.cu : tcgen05 / TMEM 3xTF32 kernel, out[m][n] = sum_k f(X[m][k]) * Wop[n][k] ----
+size_t tc_weight_image_floats(int N, int K);
+int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transposed, float* img, cudaStream_t st);
+int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
+                      const float* x_scale, const float* x_shift, double* stats, cudaStream_t st);
+
 // ---- ctc.cu ----
 int launch_ctc_loss_grad(const float* probs, int t_off, const int* labels, int maxL, const int* label_len,
                          const int* input_len, int B, int T, int V, float eps, float* loss, float* grad_u,

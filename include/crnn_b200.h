@@ -118,6 +118,19 @@ int crnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int
               int transA, int transB, const float* a_scale, const float* a_shift, const float* bias, int relu,
               int split_k, void* stream);
 
+/* teacher-forced backward of ONE depthwise-separable block (utils.py:43-56) for the parity tests: after a training-mode
+ * forward of batch B, reads d(block output) from dout_dev, zeroes "arena/grads", runs that block's backward alone and
+ * writes d(block input) to din_dev. */
+int crnn_debug_block_backward(crnn_handle* h, int block, const float* dout_dev, float* din_dev, int B, uint64_t dropout_seed, void* stream);
+
+/* tcgen05 / TMEM 3xTF32 kernel of the pointwise convolutions (csrc/gemm_tc.cu): out[m][n] = sum_k f(X[m][k]) * Wop[n][k],
+ * f = optional relu6(x*scale[k]+shift[k]); Wop[n][k] = W[k*ldw+n] if w_transposed else W[n*ldw+k]; K % 32 == 0;
+ * stats (optional, pre-zeroed double[2N]) receives per-column sum / sum of squares of out.
+ * img_scratch: crnn_gemm_tc_scratch_floats(N,K) floats of device memory for the pre-swizzled hi/lo weight images. */
+int crnn_gemm_tc(const float* X, int ldx, const float* W, int ldw, int w_transposed, float* out, int ldo, int M, int N, int K,
+                 const float* x_scale, const float* x_shift, double* stats, float* img_scratch, void* stream);
+long long crnn_gemm_tc_scratch_floats(int N, int K);
+
 /* ---------------------------------------------------------------- measurement hooks (bench.py) */
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 long long crnn_launch_count(void);

@@ -171,6 +171,35 @@ def test_gemm(cb, M, N, K, tA, tB):
         np.testing.assert_allclose(C.cpu().numpy(), ref.float().numpy(), rtol=1e-4, atol=tol)
 
 
+@pytest.mark.parametrize("M,N,K,transposed,prologue", [(1000, 128, 64, 1, True), (4097, 256, 128, 1, True), (300, 512, 512, 1, False),
+                                                      (777, 64, 128, 0, False), (2500, 128, 256, 0, False), (128, 256, 32, 0, True)])
+def test_gemm_tc(cb, M, N, K, transposed, prologue):
+    """tcgen05 3xTF32 pointwise kernel vs an fp64 matmul: fp32-level accuracy (not TF32-level), fused BN statistics."""
+    lib = cb._lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn(M, K, generator=g) * 2
+    W = torch.randn((K, N) if transposed else (N, K), generator=g)
+    sc = torch.rand(K, generator=g) + 0.5
+    sh = torch.randn(K, generator=g)
+    Xe = torch.clamp(X * sc + sh, 0, 6) if prologue else X
+    ref = Xe.double() @ (W.double() if transposed else W.double().T)
+    Xd, Wd, scd, shd = X.cuda(), W.cuda(), sc.cuda(), sh.cuda()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(lib.crnn_gemm_tc_scratch_floats(N, K), device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cb._lib.check(lib.crnn_gemm_tc(Xd.data_ptr(), K, Wd.data_ptr(), W.shape[1], transposed, out.data_ptr(), N, M, N, K,
+                                   scd.data_ptr() if prologue else None, shd.data_ptr() if prologue else None, stats.data_ptr(), scratch.data_ptr(), st))
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # plain TF32 would give ~1e-3 * scale; 3xTF32 must stay at fp32 level
+    assert err < 2e-6 * scale * K ** 0.5 + 1e-5, (err, scale)
+    np.testing.assert_allclose(stats[:N].cpu().numpy(), ref.sum(0).numpy(), rtol=1e-5, atol=1e-3 * K ** 0.5)
+    np.testing.assert_allclose(stats[N:].cpu().numpy(), (ref * ref).sum(0).numpy(), rtol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------- whole network
 def _make(cb, cfg, B, seed):
     w = N.randomize_for_test(N.init_weights(cfg, seed), seed)
@@ -250,24 +279,27 @@ def test_train_step_parity(cb, imgh, cell):
     per = m.train_fwd_bwd_device(torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d), dropout_seed=0)
     np.testing.assert_allclose(per.cpu().numpy(), per64, rtol=2e-4, atol=2e-3)
     g = m.get_grads()
-    rows, bad = [], []
+    rows, bad, ratios = [], [], []
     for k, want in g64.items():
         scale = max(np.abs(want).max(), 1e-9)
         e_gpu = np.abs(g[k] - want).max() / scale
         e_ref = np.abs(g32[k] - want).max() / scale
         rows.append((e_gpu, e_ref, scale, k))
-        if e_gpu > max(3e-3, 4 * e_ref):
+        if e_ref > 1e-4:
+            ratios.append(e_gpu / e_ref)
+        if e_gpu > max(3e-3, 10 * e_ref):
             bad.append(k)
     report = "\n".join("%-55s gpu %.2e  fp32-oracle %.2e  max|g| %.3e" % (k, a, r, sc) for a, r, sc, k in sorted(rows, reverse=True))
     import os
     os.makedirs("gpurun_out", exist_ok=True)
-    open("gpurun_out/grad_parity_%d_%s.txt" % (imgh, cell), "w").write(report + "\n")
+    open("gpurun_out/grad_parity_%d_%s.txt" % (imgh, cell), "w").write(report + "\nmedian gpu/fp32-oracle error ratio: %.2f\n" % np.median(ratios))
+    # end-to-end gradients of this net are chaotic (a 1e-7 input perturbation moves them by 1-4 %): the CUDA path
+    # must be as close to the fp64 truth as the fp32 CPU oracle is -- per tensor within 10x, in the median within 2.5x
     assert not bad, "gradients out of tolerance: %s\n%s" % (bad, report[:3000])
-    # the recurrent head is well conditioned (no BN/ReLU6/max-pool switching downstream of it): tight bound
-    for a, r, sc, k in rows:
+    assert np.median(ratios) < 2.5, np.median(ratios)
+    for a, r, sc, k in rows:   # the recurrent head is well conditioned: tight bound
         if k.startswith(("dense2", "bidirectional")):
             assert a < 2e-3, (k, a)
-        assert a < 0.15, (k, a)
     neww = m.get_weights()
     for k, want in stats_o.items():
         np.testing.assert_allclose(neww[k], want, rtol=1e-4, atol=1e-5, err_msg=k)
@@ -279,6 +311,73 @@ def test_train_step_parity(cb, imgh, cell):
     for k in g:
         np.testing.assert_allclose(got[k] - w[k], w2[k] - w[k], rtol=0, atol=1e-7, err_msg=k)
     assert m.iterations() == 1
+
+
+def _trained_forward(cb, cfg, B, seed):
+    w, m = _make(cb, cfg, B, seed)
+    x, lab, L, il = N.synth_batch(cfg, B, 50 + seed)
+    d = "cuda"
+    m.train_fwd_bwd_device(torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d), dropout_seed=0)
+    return w, m, x
+
+
+@pytest.mark.parametrize("block", [1, 2, 3, 4, 5, 6, 7])
+def test_block_backward_isolated(cb, block):
+    """Teacher-forced backward of ONE depthwise-separable block (act/pool/BN backward, pointwise dW / dX GEMMs, ReLU6+BN backward,
+    depthwise dW / dX): the oracle re-runs that single block in fp64 on the CUDA path's own block input, so the end-to-end chaos
+    (test_train_step_parity) cannot hide a kernel bug.  Tolerance 2e-3 of each tensor's max-abs entry."""
+    cfg = N.Cfg(imgh=100, cell="gru")
+    B = 4
+    w, m, x = _trained_forward(cb, cfg, B, 7)
+    lib = cb._lib.load()
+    hh, ww = cfg.imgh + 4, cfg.imgw + 4
+    for i in range(1, block):
+        p = N.BLOCK_PLAN[i - 1][2]
+        if p:
+            hh, ww = hh // p[0], ww // p[1]
+    cin, cout, pool = N.BLOCK_PLAN[block - 1]
+    ho, wo = (hh // pool[0], ww // pool[1]) if pool else (hh, ww)
+    xin = (m.activation("a0") if block == 1 else m.activation(f"block{block - 1}"))[:B * hh * ww * cin].reshape(B, hh, ww, cin).copy()
+    G = np.random.default_rng(block).standard_normal((B, ho, wo, cout)).astype(np.float32)
+    Gd = torch.tensor(G, device="cuda")
+    din = torch.empty(B * hh * ww * cin, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cb._lib.check(lib.crnn_debug_block_backward(m.handle, block, Gd.data_ptr(), din.data_ptr(), B, ctypes.c_uint64(0), st))
+    torch.cuda.synchronize()
+    g = m.get_grads()
+    names = [f"depthwise_conv2d_{block}/depthwise_kernel", f"batch_normalization_{2 * block - 1}/gamma", f"batch_normalization_{2 * block - 1}/beta",
+             f"conv2d_{block + 2}/kernel", f"batch_normalization_{2 * block}/gamma", f"batch_normalization_{2 * block}/beta"]
+    wt = N.to_torch(w, torch.float64, grad=True)
+    xt = torch.tensor(xin, dtype=torch.float64, requires_grad=True)
+    out = N.conv_block(wt, block, xt, pool, True, None, None, {})
+    (out * torch.tensor(G, dtype=torch.float64)).sum().backward()
+    for k in names:
+        want = wt[k].grad.numpy()
+        sc = max(np.abs(want).max(), 1e-9)
+        err = np.abs(g[k] - want).max() / sc
+        assert err < 2e-3, f"block {block} {k}: {err:.2e} (max |g| {sc:.3e})"
+    want = xt.grad.numpy().reshape(-1)
+    err = np.abs(din.cpu().numpy() - want).max() / np.abs(want).max()
+    assert err < 2e-3, f"block {block} d(input): {err:.2e}"
+
+
+def test_stn_backward_isolated(cb):
+    """Sampler backward (d theta) + localisation-net backward, teacher-forced with the CUDA path's own d(STN output)."""
+    cfg = N.Cfg(imgh=100, cell="gru")
+    B = 4
+    w, m, x = _trained_forward(cb, cfg, B, 9)
+    Hp, Wp = cfg.imgh + 4, cfg.imgw + 4
+    da0 = m.activation("gB")[:B * Hp * Wp].reshape(B, Hp, Wp, 1).copy()     # gradient buffer after the 7th (odd) ping-pong swap
+    g = m.get_grads()
+    wt = N.to_torch(w, torch.float64, grad=True)
+    xt = torch.tensor(x, dtype=torch.float64)
+    s = N.bilinear_sampler(xt, N.stn_locnet(wt, xt))
+    (torch.nn.functional.pad(s, (0, 0, 2, 2, 2, 2)) * torch.tensor(da0, dtype=torch.float64)).sum().backward()
+    for k in ("conv2d_1/kernel", "conv2d_1/bias", "conv2d_2/kernel", "conv2d_2/bias", "dense_1/kernel", "dense_1/bias", "dense_2/kernel", "dense_2/bias"):
+        want = wt[k].grad.numpy()
+        sc = max(np.abs(want).max(), 1e-9)
+        err = np.abs(g[k] - want).max() / sc
+        assert err < 2e-3, f"{k}: {err:.2e} (max |g| {sc:.3e})"
 
 
 def test_dropout_statistics(cb):
