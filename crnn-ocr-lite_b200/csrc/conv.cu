@@ -64,7 +64,47 @@ __global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restric
 }
 
 // ------------------------------------------------------------------ depthwise 3x3 backward-weight
-// dk[i][j][c] = sum_{b,h,w} x[b,h+i-1,w+j-1,c] * dy[b,h,w,c].  blockDim = (CT channels, PY pixel lanes)
+// dk[i][j][c] = sum_{b,h,w} x[b,h+i-1,w+j-1,c] * dy[b,h,w,c].  blockDim = (CQ channel-quads | CT channels, PY pixel lanes)
+__global__ void dwconv3x3_bwd_weight_vec4(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
+                                          int B, int H, int W, int C4, long long npix)
+{
+    extern __shared__ float red[];   // [PY][36][CQ]
+    const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    float4 acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < C4) {
+        for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < npix; p += (long long)gridDim.y * PY) {
+            int w = (int)(p % W); long long r = p / W;
+            int h = (int)(r % H); int b = (int)(r / H);
+            const float4 g = ldg4(dy + (size_t)p * C + c4 * 4);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                int hh = h + i - 1;
+                if (hh < 0 || hh >= H) continue;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    int ww = w + j - 1;
+                    if (ww < 0 || ww >= W) continue;
+                    fma4(acc[i * 3 + j], ldg4(x + (((size_t)b * H + hh) * W + ww) * C + c4 * 4), g);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        red[((threadIdx.y * 36) + q * 4 + 0) * CQ + threadIdx.x] = acc[q].x; red[((threadIdx.y * 36) + q * 4 + 1) * CQ + threadIdx.x] = acc[q].y;
+        red[((threadIdx.y * 36) + q * 4 + 2) * CQ + threadIdx.x] = acc[q].z; red[((threadIdx.y * 36) + q * 4 + 3) * CQ + threadIdx.x] = acc[q].w;
+    }
+    __syncthreads();
+    if (c4 < C4)
+        for (int e = threadIdx.y; e < 36; e += PY) {
+            float sum = 0.f;
+            for (int yy = 0; yy < PY; ++yy) sum += red[(yy * 36 + e) * CQ + threadIdx.x];
+            atomicAdd(dk + (size_t)(e >> 2) * C + c4 * 4 + (e & 3), sum);
+        }
+}
 __global__ void dwconv3x3_bwd_weight(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
                                      int B, int H, int W, int C, long long npix)
 {
@@ -181,65 +221,75 @@ __global__ void act_pool_fwd_kernel(const float* __restrict__ y, const float* __
     }
 }
 
-// backward of the above (thread per pooled output x 4 channels); writes dz for the whole window and
-// accumulates sum(dz), sum(dz*xhat) per channel (smem float atomics -> global double atomics).
+// backward of the above.  blockDim = (CQ channel-quads, PY pixel lanes): a thread owns 4 fixed channels and strides over the
+// pooled pixels, so sum(dz), sum(dz*xhat) accumulate in registers (one smem reduction + one double atomic per channel per CTA).
 __global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     float* __restrict__ dz, double* __restrict__ red, int B, int H, int W, int C4, int ph, int pw,
-                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long total)
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix)
 {
-    extern __shared__ float sred[];   // [2][C]
+    extern __shared__ float sred[];   // [PY][8][CQ]
+    const int CQ = blockDim.x, PY = blockDim.y;
     const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
-    __syncthreads();
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        int c4 = (int)(idx % C4); long long r = idx / C4;
-        int wo = (int)(r % Wo); r /= Wo;
-        int ho = (int)(r % Ho); int b = (int)(r / Ho);
-        float sc[4], sh[4], mu[4], is[4], g[4];
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    if (c4 < C4) {
+        float sc[4], sh[4], mu[4], is[4];
         { float4 t = ldg4(scale + c4 * 4); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
         { float4 t = ldg4(shift + c4 * 4); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
         { float4 t = ldg4(mean + c4 * 4); mu[0] = t.x; mu[1] = t.y; mu[2] = t.z; mu[3] = t.w; }
         { float4 t = ldg4(invstd + c4 * 4); is[0] = t.x; is[1] = t.y; is[2] = t.z; is[3] = t.w; }
-        { float4 t = ldg4(da + (size_t)idx * 4); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
-        if (rate > 0.f)
+        for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < npix; p += (long long)gridDim.y * PY) {
+            int wo = (int)(p % Wo); long long r = p / Wo;
+            int ho = (int)(r % Ho); int b = (int)(r / Ho);
+            const long long oidx = p * C4 + c4;
+            float g[4];
+            { float4 t = ldg4(da + (size_t)oidx * 4); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+            if (rate > 0.f)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) g[q] *= crnn_dropout_mask(seed, layer, idx * 4 + q, rate, inv_keep);
-        float yv[4][4], best[4]; int arg[4];   // window <= 4 elements
+                for (int q = 0; q < 4; ++q) g[q] *= crnn_dropout_mask(seed, layer, oidx * 4 + q, rate, inv_keep);
+            float yv[4][4], best[4]; int arg[4];   // window <= 4 elements
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { best[q] = -INFINITY; arg[q] = 0; }
-        int n = 0;
-        for (int i = 0; i < ph; ++i)
-            for (int j = 0; j < pw; ++j, ++n) {
-                float4 t = ldg4(y + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4);
-                yv[n][0] = t.x; yv[n][1] = t.y; yv[n][2] = t.z; yv[n][3] = t.w;
+            for (int q = 0; q < 4; ++q) { best[q] = -INFINITY; arg[q] = 0; }
+            int n = 0;
+            for (int i = 0; i < ph; ++i)
+                for (int j = 0; j < pw; ++j, ++n) {
+                    float4 t = ldg4(y + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4);
+                    yv[n][0] = t.x; yv[n][1] = t.y; yv[n][2] = t.z; yv[n][3] = t.w;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float aq = relu6f(fmaf(yv[n][q], sc[q], sh[q]));
-                    if (aq > best[q]) { best[q] = aq; arg[q] = n; }   // first max wins (TF / torch max-pool grad)
+                    for (int q = 0; q < 4; ++q) {
+                        float aq = relu6f(fmaf(yv[n][q], sc[q], sh[q]));
+                        if (aq > best[q]) { best[q] = aq; arg[q] = n; }   // first max wins (TF / torch max-pool grad)
+                    }
                 }
-            }
-        float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-        n = 0;
-        for (int i = 0; i < ph; ++i)
-            for (int j = 0; j < pw; ++j, ++n) {
-                float o[4];
+            n = 0;
+            for (int i = 0; i < ph; ++i)
+                for (int j = 0; j < pw; ++j, ++n) {
+                    float o[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float z = fmaf(yv[n][q], sc[q], sh[q]);
-                    float d = (arg[q] == n && z >= 0.f && z <= 6.f) ? g[q] : 0.f;
-                    o[q] = d; s1[q] += d; s2[q] = fmaf(d, (yv[n][q] - mu[q]) * is[q], s2[q]);
+                    for (int q = 0; q < 4; ++q) {
+                        float z = fmaf(yv[n][q], sc[q], sh[q]);
+                        float d = (arg[q] == n && z >= 0.f && z <= 6.f) ? g[q] : 0.f;
+                        o[q] = d; s1[q] += d; s2[q] = fmaf(d, (yv[n][q] - mu[q]) * is[q], s2[q]);
+                    }
+                    *reinterpret_cast<float4*>(dz + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
                 }
-                *reinterpret_cast<float4*>(dz + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (s1[q] != 0.f) atomicAdd(&sred[c4 * 4 + q], s1[q]);
-            if (s2[q] != 0.f) atomicAdd(&sred[C + c4 * 4 + q], s2[q]);
         }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sred[(threadIdx.y * 8 + q) * CQ + threadIdx.x] = s1[q];
+        sred[(threadIdx.y * 8 + 4 + q) * CQ + threadIdx.x] = s2[q];
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) if (sred[i] != 0.f) atomicAdd(red + i, (double)sred[i]);
+    if (threadIdx.y == 0 && c4 < C4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double t1 = 0.0, t2 = 0.0;
+            for (int i = 0; i < PY; ++i) { t1 += sred[(i * 8 + q) * CQ + threadIdx.x]; t2 += sred[(i * 8 + 4 + q) * CQ + threadIdx.x]; }
+            atomicAdd(red + c4 * 4 + q, t1); atomicAdd(red + C + c4 * 4 + q, t2);
+        }
+    }
 }
 
 // relu6 backward only (BN after the depthwise conv): y,da,dz [M][C]
@@ -392,9 +442,13 @@ int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, in
 }
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk, int B, int H, int W, int C, cudaStream_t st) {
     dim3 grid, block; long long npix = (long long)B * H * W;
-    chan_block(C, npix, grid, block);
-    size_t smem = sizeof(float) * block.y * 9 * block.x;
-    dwconv3x3_bwd_weight<<<grid, block, smem, st>>>(x, dy, dk, B, H, W, C, npix);
+    if (C % 4 == 0) {
+        chan_block(C / 4, npix, grid, block);
+        dwconv3x3_bwd_weight_vec4<<<grid, block, sizeof(float) * 36 * 256, st>>>(x, dy, dk, B, H, W, C / 4, npix);
+    } else {
+        chan_block(C, npix, grid, block);
+        dwconv3x3_bwd_weight<<<grid, block, sizeof(float) * block.y * 9 * block.x, st>>>(x, dy, dk, B, H, W, C, npix);
+    }
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_colstats(const float* y, long long M, int C, double* stats, cudaStream_t st) {
@@ -417,9 +471,10 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
 int launch_act_pool_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                         float* dz, double* red, int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
-    long long total = (long long)B * (H / ph) * (W / pw) * (C / 4);
-    act_pool_bwd_kernel<<<grid1d(total, 256, 148 * 4), 256, sizeof(float) * 2 * C, st>>>(da, y, scale, shift, mean, invstd, dz, red, B, H, W, C / 4, ph, pw,
-                                                                                         rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, total);
+    const long long npix = (long long)B * (H / ph) * (W / pw);
+    dim3 grid, block; chan_block(C / 4, npix, grid, block);
+    act_pool_bwd_kernel<<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, dz, red, B, H, W, C / 4, ph, pw,
+                                                                      rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, npix);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_relu6_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,

@@ -309,7 +309,7 @@ def test_train_step_parity(cb, imgh, cell):
     w2, norm = N.adam_step(w, g, {}, lr=1e-4, b1=0.5, b2=0.999, eps=1e-7, clipnorm=5.0)
     got = m.get_weights()
     for k in g:
-        np.testing.assert_allclose(got[k] - w[k], w2[k] - w[k], rtol=0, atol=1e-7, err_msg=k)
+        np.testing.assert_allclose(got[k] - w[k], w2[k] - w[k], rtol=0, atol=3e-7, err_msg=k)   # 1-2 ulp of the O(1) weights
     assert m.iterations() == 1
 
 
@@ -325,7 +325,9 @@ def _trained_forward(cb, cfg, B, seed):
 def test_block_backward_isolated(cb, block):
     """Teacher-forced backward of ONE depthwise-separable block (act/pool/BN backward, pointwise dW / dX GEMMs, ReLU6+BN backward,
     depthwise dW / dX): the oracle re-runs that single block in fp64 on the CUDA path's own block input, so the end-to-end chaos
-    (test_train_step_parity) cannot hide a kernel bug.  Tolerance 2e-3 of each tensor's max-abs entry."""
+    (test_train_step_parity) cannot hide a kernel bug.  Tolerance 1e-2 of each tensor's max-abs entry: a single ReLU6 / max-pool
+    decision that flips between the fp32 CUDA forward and the fp64 oracle forward moves an entry by ~3e-3 (one term of a sum of a few
+    thousand random-sign terms); a wrong kernel shows up as O(0.1 .. 1)."""
     cfg = N.Cfg(imgh=100, cell="gru")
     B = 4
     w, m, x = _trained_forward(cb, cfg, B, 7)
@@ -355,10 +357,10 @@ def test_block_backward_isolated(cb, block):
         want = wt[k].grad.numpy()
         sc = max(np.abs(want).max(), 1e-9)
         err = np.abs(g[k] - want).max() / sc
-        assert err < 2e-3, f"block {block} {k}: {err:.2e} (max |g| {sc:.3e})"
+        assert err < 1e-2, f"block {block} {k}: {err:.2e} (max |g| {sc:.3e})"
     want = xt.grad.numpy().reshape(-1)
     err = np.abs(din.cpu().numpy() - want).max() / np.abs(want).max()
-    assert err < 2e-3, f"block {block} d(input): {err:.2e}"
+    assert err < 1e-2, f"block {block} d(input): {err:.2e}"
 
 
 def test_stn_backward_isolated(cb):
