@@ -386,8 +386,13 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
                             other, red, B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
     ST(ST_BN_BWD, 12.0 * Mi * b.cout, launch_bn_bwd_apply(other, pw, red, h->w(bnname(bn2, "gamma")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
                             h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")), Mi, b.cout, st));
-    TRY(gemm_tn(h, ST_GEMM_PW_DW, dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
-                h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
+    if (!h->gemm_simt && (b.cin % 4 == 0)) {
+        ST(ST_GEMM_PW_DW, 2.0 * Mi * b.cin * b.cout, launch_xty_gemm_tc(dw, b.cin, b.cin, other, b.cout, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, (int)Mi,
+                                                                       h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
+    } else {
+        TRY(gemm_tn(h, ST_GEMM_PW_DW, dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
+                    h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
+    }
     if (!h->gemm_simt && (b.cout % 32 == 0) && (b.cin % 4 == 0)) {
         float* img = h->a(nm("wimg_dx%d", i));
         ST(ST_MISC, 0, launch_prep_weight_images(h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, 0, img, st));
@@ -624,6 +629,11 @@ int crnn_debug_block_backward(crnn_handle* h, int block, const float* dout_dev, 
     return CRNN_OK;
 }
 
+int crnn_gemm_tc_dw(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
+                    const float* x_scale, const float* x_shift, void* stream) {
+    if (!X || !dY || !dW) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    return launch_xty_gemm_tc(X, ldx, Cin, dY, ldy, Cout, dW, ldw, M, x_scale, x_shift, static_cast<cudaStream_t>(stream));
+}
 long long crnn_gemm_tc_scratch_floats(int N, int K) { return (long long)tc_weight_image_floats(N, K); }
 
 long long crnn_launch_count(void) { return g_crnn_launches; }

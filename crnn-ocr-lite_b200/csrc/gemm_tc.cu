@@ -231,6 +231,197 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
     }
 }
 
+// =====================================================================================================================
+// Weight gradient of the pointwise conv:  dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]     (contraction over PIXELS)
+// Both operands are "MN-major" for the tensor core (channels contiguous per pixel row), so the producers keep the natural
+// 128-byte channel rows: tile = [mn-block of 32 channels][k-group of 8 pixels][8 pixel rows x 128 B], SWIZZLE_128B
+// (16-byte chunk index XOR pixel-row index), LBO = mn-block stride (4096 B), SBO = k-group stride (1024 B); one
+// tcgen05.mma (K = 8 tf32) consumes one k-group.  D[128 ci lanes][NB co columns] accumulates in TMEM over the CTA's pixel
+// range (split-K over pixels across CTAs), epilogue = fp32 atomicAdd into the pre-zeroed gradient.
+// =====================================================================================================================
+template <int NB> struct DwCfg {
+    static constexpr int STAGES = NB == 256 ? 2 : 3;
+    static constexpr int A_FLOATS = 128 * 32;            // X tile (hi or lo): 32 pixels x 128 ci
+    static constexpr int B_FLOATS = NB * 32;             // dY tile (hi or lo): 32 pixels x NB co
+    static constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4 + 1024 + 256;
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {   // MN-major SWIZZLE_128B: LBO = 4096 B, SBO = 1024 B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (256ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+template <uint32_t IDESC>
+__device__ __forceinline__ void umma_tf32_i(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+
+struct DwArgs {
+    const float* X; int ldx; int Cin;       // (M, Cin) raw activations (+ optional BN/ReLU6 per ci)
+    const float* dY; int ldy; int Cout;     // (M, Cout)
+    float* dW; int ldw;                     // (Cin, Cout), pre-zeroed / accumulated with atomics
+    int M; int px_per_cta;                  // pixel range per CTA (multiple of 32)
+    const float* x_scale; const float* x_shift;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
+{
+    using C = DwCfg<NB>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* stage_base = (float*)smem;
+    uint64_t* bars = (uint64_t*)(smem + C::STAGES * C::STAGE_FLOATS * 4);
+    uint64_t* full = bars; uint64_t* empty = bars + C::STAGES; uint64_t* accb = bars + 2 * C::STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * C::STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ci0 = blockIdx.x * 128, co0 = blockIdx.y * NB;
+    const int p_begin = blockIdx.z * a.px_per_cta;
+    int p_end = p_begin + a.px_per_cta; if (p_end > a.M) p_end = a.M;
+    const int KB = (p_end - p_begin + 31) / 32;
+    if (KB <= 0) return;                       // uniform for the whole CTA
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(accb, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NB) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------ producers
+        const int q = tid & 31;                 // channel quad inside a 128-channel group
+        const int pr0 = tid >> 5;               // pixel rows pr0 + 4*i
+        const int ci = ci0 + q * 4;
+        const bool ci_ok = ci < a.Cin;          // Cin is a multiple of 4
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.x_scale && ci_ok) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + ci)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + ci)); }
+        const int mb = q >> 3, chunk = q & 7;   // mn-block (32 channels) and 16-byte chunk of this quad
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % C::STAGES;
+            const uint32_t ph = (kb / C::STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            float* Ahi = stage_base + (size_t)s * C::STAGE_FLOATS;
+            float* Alo = Ahi + C::A_FLOATS; float* Bhi = Alo + C::A_FLOATS; float* Blo = Bhi + C::B_FLOATS;
+            const int pbase = p_begin + kb * 32;
+            // X tile: 32 pixels x 128 ci
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int p = pbase + pr0 + 4 * i;
+                v[i] = (p < p_end && ci_ok) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)p * a.ldx + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int pl = pr0 + 4 * i;                       // pixel row inside the k-block
+                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                if (a.x_scale) {
+                    x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
+                    x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
+                    if (!(pbase + pl < p_end && ci_ok)) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                }
+                uint32_t hi[4]; float lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(x[e]); lo[e] = x[e] - __uint_as_float(hi[e]); }
+                const int kr = pl & 7, g = pl >> 3;
+                const int off = mb * 1024 + g * 256 + kr * 32 + ((chunk ^ kr) << 2);     // floats
+                *reinterpret_cast<uint4*>(Ahi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            // dY tile: 32 pixels x NB co  (NB/128 groups of 128 channels)
+#pragma unroll
+            for (int gq = 0; gq < NB / 128; ++gq) {
+                const int co = co0 + gq * 128 + q * 4;
+                const bool co_ok = co < a.Cout;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int p = pbase + pr0 + 4 * i;
+                    v[i] = (p < p_end && co_ok) ? __ldg(reinterpret_cast<const float4*>(a.dY + (size_t)p * a.ldy + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int pl = pr0 + 4 * i;
+                    const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                    uint32_t hi[4]; float lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(x[e]); lo[e] = x[e] - __uint_as_float(hi[e]); }
+                    const int kr = pl & 7, g = pl >> 3;
+                    const int off = (gq * 4 + mb) * 1024 + g * 256 + kr * 32 + ((chunk ^ kr) << 2);
+                    *reinterpret_cast<uint4*>(Bhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(Blo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full[s]);
+        }
+        // ------------------------------------------------ epilogue: TMEM -> atomicAdd into dW
+        mbar_wait(accb, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = ci0 + warp * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < a.Cin) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = co0 + c0 + j;
+                    if (co < a.Cout) atomicAdd(a.dW + (size_t)row * a.ldw + co, __uint_as_float(r[j]));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ------------------------------------------------ warp 4: MMA issue
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % C::STAGES;
+            const uint32_t ph = (kb / C::STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t ahi = smem_u32(stage_base + (size_t)s * C::STAGE_FLOATS);
+                const uint32_t alo = ahi + C::A_FLOATS * 4, bhi = alo + C::A_FLOATS * 4, blo = bhi + C::B_FLOATS * 4;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {                  // one k-group (8 pixels) per MMA
+                    const uint32_t o = g * 1024;
+                    umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(alo + o), umma_desc_mn(bhi + o), (kb | g) ? 1u : 0u);
+                    umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(ahi + o), umma_desc_mn(blo + o), 1u);
+                    umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(ahi + o), umma_desc_mn(bhi + o), 1u);
+                }
+                umma_commit(&empty[s]);
+                if (kb == KB - 1) umma_commit(accb);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NB) : "memory");
+    }
+}
+
 // Wimg[((ct*KB + kb)*2 + hl)*4096 + sw128_off(r, kk)] for Wop[n = ct*128 + r][k = kb*32 + kk]; rows n >= N are zero.
 //   transposed=1: Wop[n][k] = W[k*ldw + n]  (forward: Keras kernel is (Cin, Cout));  0: Wop[n][k] = W[n*ldw + k]  (dX)
 __global__ void prep_weight_images_kernel(const float* __restrict__ W, int ldw, int N, int K, int transposed, float* __restrict__ img)
@@ -279,6 +470,34 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats;
     dim3 grid((N + TC_BC - 1) / TC_BC, (M + TC_BP - 1) / TC_BP);
     xw_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
+
+int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
+                       const float* x_scale, const float* x_shift, cudaStream_t st)
+{
+    if (M <= 0 || Cin <= 0 || Cout <= 0) return CRNN_OK;
+    if ((Cin % 4) || (Cout % 4) || (ldx % 4) || (ldy % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(dY) & 15)) {
+        crnn_set_error("gemm_tc dW: channels / leading dims must be multiples of 4 and pointers 16-byte aligned"); return CRNN_ERR_INVALID;
+    }
+    const int NB = Cout > 128 ? 256 : 128;
+    const int tiles = ((Cin + 127) / 128) * ((Cout + NB - 1) / NB);
+    int splits = (148 + tiles - 1) / tiles;
+    int per = ((M + splits - 1) / splits + 31) / 32 * 32;
+    if (per < 32) per = 32;
+    splits = (M + per - 1) / per;
+    DwArgs a; a.X = X; a.ldx = ldx; a.Cin = Cin; a.dY = dY; a.ldy = ldy; a.Cout = Cout; a.dW = dW; a.ldw = ldw; a.M = M; a.px_per_cta = per;
+    a.x_scale = x_scale; a.x_shift = x_shift;
+    dim3 grid((Cin + 127) / 128, (Cout + NB - 1) / NB, splits);
+    static bool c128 = false, c256 = false;
+    if (NB == 256) {
+        if (!c256) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<256>::SMEM_BYTES)); c256 = true; }
+        xty_gemm_tc_kernel<256><<<grid, TC_THREADS, DwCfg<256>::SMEM_BYTES, st>>>(a);
+    } else {
+        if (!c128) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<128>::SMEM_BYTES)); c128 = true; }
+        xty_gemm_tc_kernel<128><<<grid, TC_THREADS, DwCfg<128>::SMEM_BYTES, st>>>(a);
+    }
     LAUNCH_CHECK();
     return CRNN_OK;
 }

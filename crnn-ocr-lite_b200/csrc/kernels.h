@@ -23,6 +23,10 @@ int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transpo
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st);
 
+// dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]  (tcgen05, MN-major operands, split-K over pixels, atomics into pre-zeroed dW)
+int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
+                       const float* x_scale, const float* x_shift, cudaStream_t st);
+
 // ---- ctc.cu ----
 int launch_ctc_loss_grad(const float* probs, int t_off, const int* labels, int maxL, const int* label_len,
                          const int* input_len, int B, int T, int V, float eps, float* loss, float* grad_u,

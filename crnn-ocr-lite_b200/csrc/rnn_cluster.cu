@@ -83,6 +83,12 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         const int t = dir ? T - 1 - s : s;
         const float* hcur = hT + cur * (U * RB);
         float* hnxt = hT + (cur ^ 1) * (U * RB);
+        float nxz = 0.f, nxr = 0.f, nxh = 0.f;             // next step's projections: issued now, consumed one step later
+        if (s + 1 < T) {
+            const int tn = dir ? T - 2 - s : s + 1;
+            const float* x = xp + (((size_t)bb * T + tn) * 2 + dir) * (3 * U);
+            nxz = __ldg(x + j); nxr = __ldg(x + U + j); nxh = __ldg(x + 2 * U + j);
+        }
         // ---- phase A: z,r pre-activations of the own 32 units: part[ks][col 0..63][row 0..7]
         {
             float acc[4][4] = {};
@@ -131,11 +137,7 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         }
 #pragma unroll
         for (int c = 0; c < NCTA; ++c) cluster.map_shared_rank(hnxt, c)[j * RB + er] = hn;
-        if (s + 1 < T) {
-            const int tn = dir ? T - 2 - s : s + 1;
-            const float* x = xp + (((size_t)bb * T + tn) * 2 + dir) * (3 * U);
-            xz = x[j]; xr = x[U + j]; xh = x[2 * U + j];
-        }
+        xz = nxz; xr = nxr; xh = nxh;
         cluster.sync();
         cur ^= 1;
     }
@@ -198,14 +200,24 @@ gru_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__
     const int uh = tid >> 7, rg = (tid >> 6) & 1, kq = tid & 63;
 
     float dh = 0.f;
-    for (int s = T - 1; s >= 0; --s) {
+    // software pipeline: the loads of step s-1 are issued at the top of step s
+    auto load_step = [&](int s, float& z, float& r, float& hh, float& hp, float& dov) {
         const int t = dir ? T - 1 - s : s;
         const int tp = dir ? t + 1 : t - 1;
         const size_t o = ((size_t)bb * T + t) * 2 + dir;
         const float* g = gates + o * (3 * U);
-        const float z = g[j], r = g[U + j], hh = g[2 * U + j];
-        const float hp = (s > 0) ? hs[(((size_t)bb * T + tp) * 2 + dir) * U + j] : 0.f;
-        const float dht = (valid ? dout[o * U + j] : 0.f) + dh;
+        z = __ldg(g + j); r = __ldg(g + U + j); hh = __ldg(g + 2 * U + j);
+        hp = (s > 0) ? __ldg(hs + (((size_t)bb * T + tp) * 2 + dir) * U + j) : 0.f;
+        dov = valid ? __ldg(dout + o * U + j) : 0.f;
+    };
+    float nz, nr, nhh, nhp, ndo;
+    load_step(T - 1, nz, nr, nhh, nhp, ndo);
+    for (int s = T - 1; s >= 0; --s) {
+        const int t = dir ? T - 1 - s : s;
+        const size_t o = ((size_t)bb * T + t) * 2 + dir;
+        const float z = nz, r = nr, hh = nhh, hp = nhp;
+        const float dht = ndo + dh;
+        if (s > 0) load_step(s - 1, nz, nr, nhh, nhp, ndo);
         const float dz = dht * (hp - hh);
         float dhn = dht * z;
         const float da_h = dht * (1.f - z) * (1.f - hh * hh);

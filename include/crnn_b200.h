@@ -130,6 +130,9 @@ int crnn_debug_block_backward(crnn_handle* h, int block, const float* dout_dev, 
 int crnn_gemm_tc(const float* X, int ldx, const float* W, int ldw, int w_transposed, float* out, int ldo, int M, int N, int K,
                  const float* x_scale, const float* x_shift, double* stats, float* img_scratch, void* stream);
 long long crnn_gemm_tc_scratch_floats(int N, int K);
+/* weight gradient on the tensor cores: dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]; dW must be pre-zeroed (atomics) */
+int crnn_gemm_tc_dw(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
+                    const float* x_scale, const float* x_shift, void* stream);
 
 /* ---------------------------------------------------------------- measurement hooks (bench.py) */
 /* kernels launched by this library since load (bench.py's gpu_launches) */

@@ -196,8 +196,30 @@ def test_gemm_tc(cb, M, N, K, transposed, prologue):
     scale = ref.abs().max().item()
     # plain TF32 would give ~1e-3 * scale; 3xTF32 must stay at fp32 level
     assert err < 2e-6 * scale * K ** 0.5 + 1e-5, (err, scale)
-    np.testing.assert_allclose(stats[:N].cpu().numpy(), ref.sum(0).numpy(), rtol=1e-5, atol=1e-3 * K ** 0.5)
+    np.testing.assert_allclose(stats[:N].cpu().numpy(), ref.sum(0).numpy(), rtol=1e-5, atol=2e-6 * ref.abs().sum(0).max().item())   # cancelling sums
     np.testing.assert_allclose(stats[N:].cpu().numpy(), (ref * ref).sum(0).numpy(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,Cin,Cout,prologue", [(3000, 64, 128, True), (5000, 128, 256, True), (777, 256, 512, False), (33, 512, 512, True), (40000, 64, 128, False)])
+def test_gemm_tc_dw(cb, M, Cin, Cout, prologue):
+    """tcgen05 3xTF32 weight-gradient kernel (MN-major operands, split-K over pixels) vs fp64."""
+    lib = cb._lib.load()
+    g = torch.Generator().manual_seed(M + Cin)
+    X = torch.randn(M, Cin, generator=g) * 2
+    dY = torch.randn(M, Cout, generator=g)
+    sc = torch.rand(Cin, generator=g) + 0.5
+    sh = torch.randn(Cin, generator=g)
+    Xe = torch.clamp(X * sc + sh, 0, 6) if prologue else X
+    ref = Xe.double().T @ dY.double()
+    Xd, Yd, scd, shd = X.cuda(), dY.cuda(), sc.cuda(), sh.cuda()
+    dW = torch.zeros(Cin, Cout, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cb._lib.check(lib.crnn_gemm_tc_dw(Xd.data_ptr(), Cin, Cin, Yd.data_ptr(), Cout, Cout, dW.data_ptr(), Cout, M,
+                                      scd.data_ptr() if prologue else None, shd.data_ptr() if prologue else None, st))
+    torch.cuda.synchronize()
+    err = (dW.cpu().double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err < 3e-6 * scale * max(1.0, (M / 1000.0) ** 0.5) + 1e-4, (err, scale)
 
 
 # ------------------------------------------------------------------------------------------- whole network
@@ -325,9 +347,8 @@ def _trained_forward(cb, cfg, B, seed):
 def test_block_backward_isolated(cb, block):
     """Teacher-forced backward of ONE depthwise-separable block (act/pool/BN backward, pointwise dW / dX GEMMs, ReLU6+BN backward,
     depthwise dW / dX): the oracle re-runs that single block in fp64 on the CUDA path's own block input, so the end-to-end chaos
-    (test_train_step_parity) cannot hide a kernel bug.  Tolerance 1e-2 of each tensor's max-abs entry: a single ReLU6 / max-pool
-    decision that flips between the fp32 CUDA forward and the fp64 oracle forward moves an entry by ~3e-3 (one term of a sum of a few
-    thousand random-sign terms); a wrong kernel shows up as O(0.1 .. 1)."""
+    (test_train_step_parity) cannot hide a kernel bug.  Tolerance 3e-3 of each tensor's max-abs entry, with the upstream gradient
+    zeroed at the (few) elements whose ReLU6 / max-pool decision is numerically ambiguous."""
     cfg = N.Cfg(imgh=100, cell="gru")
     B = 4
     w, m, x = _trained_forward(cb, cfg, B, 7)
@@ -341,6 +362,26 @@ def test_block_backward_isolated(cb, block):
     ho, wo = (hh // pool[0], ww // pool[1]) if pool else (hh, ww)
     xin = (m.activation("a0") if block == 1 else m.activation(f"block{block - 1}"))[:B * hh * ww * cin].reshape(B, hh, ww, cin).copy()
     G = np.random.default_rng(block).standard_normal((B, ho, wo, cout)).astype(np.float32)
+    # Zero the upstream gradient where the block's LAST ReLU6 / max-pool decision is within 1e-3 of switching: the fp32 CUDA forward
+    # and the fp64 oracle forward may legitimately decide differently there (a few of ~1e6 elements), and each such flip moves a
+    # weight-gradient entry by ~1e-2 of its max -- that is conditioning, not a kernel property.
+    with torch.no_grad():
+        w64 = N.to_torch(w, torch.float64)
+        kp = {}
+        N.conv_block(w64, block, torch.tensor(xin, dtype=torch.float64), None, True, None, None, kp)
+        z2 = N.batchnorm(w64, 2 * block, kp[f"pw{block}"], True, None)
+        near = (z2.abs() < 1e-3) | ((z2 - 6).abs() < 1e-3)
+        a2 = N.relu6(z2)
+        if pool:
+            nearp = torch.nn.functional.max_pool2d(near.permute(0, 3, 1, 2).double(), pool).permute(0, 2, 3, 1) > 0
+            win = torch.nn.functional.unfold(a2.permute(0, 3, 1, 2).reshape(B * cout, 1, hh, ww), pool, stride=pool)   # (B*C, ph*pw, L)
+            top2 = win.topk(2, dim=1).values
+            tie = ((top2[:, 0] - top2[:, 1]) < 1e-3) & (top2[:, 0] > 0) & (top2[:, 0] < 6)
+            tie = tie.reshape(B, cout, ho, wo).permute(0, 2, 3, 1)
+            keepmask = ~(nearp | tie)
+        else:
+            keepmask = ~near
+    G = (G * keepmask.numpy()).astype(np.float32)
     Gd = torch.tensor(G, device="cuda")
     din = torch.empty(B * hh * ww * cin, device="cuda")
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -357,10 +398,10 @@ def test_block_backward_isolated(cb, block):
         want = wt[k].grad.numpy()
         sc = max(np.abs(want).max(), 1e-9)
         err = np.abs(g[k] - want).max() / sc
-        assert err < 1e-2, f"block {block} {k}: {err:.2e} (max |g| {sc:.3e})"
+        assert err < 3e-3, f"block {block} {k}: {err:.2e} (max |g| {sc:.3e})"
     want = xt.grad.numpy().reshape(-1)
     err = np.abs(din.cpu().numpy() - want).max() / np.abs(want).max()
-    assert err < 1e-2, f"block {block} d(input): {err:.2e}"
+    assert err < 3e-3, f"block {block} d(input): {err:.2e}"
 
 
 def test_stn_backward_isolated(cb):
