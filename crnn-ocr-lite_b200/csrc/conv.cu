@@ -221,11 +221,15 @@ __global__ void act_pool_fwd_kernel(const float* __restrict__ y, const float* __
     }
 }
 
-// backward of the above.  blockDim = (CQ channel-quads, PY pixel lanes): a thread owns 4 fixed channels and strides over the
-// pooled pixels, so sum(dz), sum(dz*xhat) accumulate in registers (one smem reduction + one double atomic per channel per CTA).
+// backward of the above, two passes over (da, y) with blockDim = (CQ channel-quads, PY pixel lanes):
+//   APPLY=false: only the reductions sum(dz), sum(dz*xhat) per channel (registers -> smem -> one double atomic per channel per CTA)
+//   APPLY=true : recomputes dz and writes the BatchNorm-backward result dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))
+// so the intermediate dz never touches HBM.  dz = unpool(da * dropmask) * 1[0 <= z <= 6], z = y*scale+shift.
+template <bool APPLY>
 __global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    float* __restrict__ dz, double* __restrict__ red, int B, int H, int W, int C4, int ph, int pw,
+                                    const float* __restrict__ gamma, float* __restrict__ dy, double* __restrict__ red,
+                                    int B, int H, int W, int C4, int ph, int pw, double invM,
                                     float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix)
 {
     extern __shared__ float sred[];   // [PY][8][CQ]
@@ -234,11 +238,18 @@ __global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* _
     const int c4 = blockIdx.x * CQ + threadIdx.x;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     if (c4 < C4) {
-        float sc[4], sh[4], mu[4], is[4];
+        float sc[4], sh[4], mu[4], is[4], gs[4] = {0, 0, 0, 0}, m1[4] = {0, 0, 0, 0}, m2[4] = {0, 0, 0, 0};
         { float4 t = ldg4(scale + c4 * 4); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
         { float4 t = ldg4(shift + c4 * 4); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
         { float4 t = ldg4(mean + c4 * 4); mu[0] = t.x; mu[1] = t.y; mu[2] = t.z; mu[3] = t.w; }
         { float4 t = ldg4(invstd + c4 * 4); is[0] = t.x; is[1] = t.y; is[2] = t.z; is[3] = t.w; }
+        if (APPLY) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                gs[q] = gamma[c4 * 4 + q] * is[q];
+                m1[q] = (float)(red[c4 * 4 + q] * invM); m2[q] = (float)(red[C + c4 * 4 + q] * invM);
+            }
+        }
         for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < npix; p += (long long)gridDim.y * PY) {
             int wo = (int)(p % Wo); long long r = p / Wo;
             int ho = (int)(r % Ho); int b = (int)(r / Ho);
@@ -268,14 +279,17 @@ __global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* _
                     float o[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float z = fmaf(yv[n][q], sc[q], sh[q]);
-                        float d = (arg[q] == n && z >= 0.f && z <= 6.f) ? g[q] : 0.f;
-                        o[q] = d; s1[q] += d; s2[q] = fmaf(d, (yv[n][q] - mu[q]) * is[q], s2[q]);
+                        const float z = fmaf(yv[n][q], sc[q], sh[q]);
+                        const float d = (arg[q] == n && z >= 0.f && z <= 6.f) ? g[q] : 0.f;
+                        const float xh = (yv[n][q] - mu[q]) * is[q];
+                        if (APPLY) o[q] = gs[q] * (d - m1[q] - xh * m2[q]);
+                        else { s1[q] += d; s2[q] = fmaf(d, xh, s2[q]); }
                     }
-                    *reinterpret_cast<float4*>(dz + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (APPLY) *reinterpret_cast<float4*>(dy + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
                 }
         }
     }
+    if (APPLY) return;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         sred[(threadIdx.y * 8 + q) * CQ + threadIdx.x] = s1[q];
@@ -292,10 +306,19 @@ __global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* _
     }
 }
 
-// relu6 backward only (BN after the depthwise conv): y,da,dz [M][C]
-__global__ void relu6_bwd_kernel(const float* da /* may alias dz */, const float* __restrict__ y, const float* __restrict__ scale,
+// dgamma += sum(dz*xhat), dbeta += sum(dz) from the reduction buffer
+__global__ void bn_param_grads_kernel(const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta, int C)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) { dbeta[c] += (float)red[c]; dgamma[c] += (float)red[C + c]; }
+}
+
+// ReLU6 + BatchNorm backward of the BN that follows the depthwise conv (no pool / dropout): y, da, dy are [M][C].
+//   APPLY=false: reductions only;  APPLY=true: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dy may alias da.
+template <bool APPLY>
+__global__ void relu6_bwd_kernel(const float* da /* may alias dy */, const float* __restrict__ y, const float* __restrict__ scale,
                                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                 float* dz, double* __restrict__ red, long long M, int C)
+                                 const float* __restrict__ gamma, float* dy, double* __restrict__ red, long long M, int C, double invM)
 {
     extern __shared__ float sred[];   // [PY][2][CT]
     const int CT = blockDim.x, PY = blockDim.y;
@@ -303,14 +326,18 @@ __global__ void relu6_bwd_kernel(const float* da /* may alias dz */, const float
     float s1 = 0.f, s2 = 0.f;
     if (c < C) {
         const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+        float gs = 0.f, m1 = 0.f, m2 = 0.f;
+        if (APPLY) { gs = gamma[c] * is; m1 = (float)(red[c] * invM); m2 = (float)(red[C + c] * invM); }
         for (long long m = blockIdx.y * (long long)PY + threadIdx.y; m < M; m += (long long)gridDim.y * PY) {
-            float yv = __ldg(y + (size_t)m * C + c);
-            float z = fmaf(yv, sc, sh);
-            float d = (z >= 0.f && z <= 6.f) ? da[(size_t)m * C + c] : 0.f;
-            dz[(size_t)m * C + c] = d;
-            s1 += d; s2 = fmaf(d, (yv - mu) * is, s2);
+            const float yv = __ldg(y + (size_t)m * C + c);
+            const float z = fmaf(yv, sc, sh);
+            const float d = (z >= 0.f && z <= 6.f) ? da[(size_t)m * C + c] : 0.f;
+            const float xh = (yv - mu) * is;
+            if (APPLY) dy[(size_t)m * C + c] = gs * (d - m1 - xh * m2);
+            else { s1 += d; s2 = fmaf(d, xh, s2); }
         }
     }
+    if (APPLY) return;
     sred[(threadIdx.y * 2 + 0) * CT + threadIdx.x] = s1;
     sred[(threadIdx.y * 2 + 1) * CT + threadIdx.x] = s2;
     __syncthreads();
@@ -468,19 +495,31 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
     act_pool_fwd_kernel<<<grid1d(total, 256), 256, 0, st>>>(y, scale, shift, a, B, H, W, C / 4, ph, pw, rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, total);
     LAUNCH_CHECK(); return CRNN_OK;
 }
-int launch_act_pool_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
-                        float* dz, double* red, int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
+// two launches: reductions, then apply (+ a tiny launch for dgamma/dbeta); `red` (double[2C]) must be pre-zeroed
+int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                           const float* gamma, float* dy, double* red, float* dgamma, float* dbeta,
+                           int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
+    const double invM = 1.0 / ((double)B * H * W);
+    const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
-    act_pool_bwd_kernel<<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, dz, red, B, H, W, C / 4, ph, pw,
-                                                                      rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, npix);
+    act_pool_bwd_kernel<false><<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, ph, pw, invM, rate, ik, seed, layer, npix);
+    LAUNCH_CHECK();
+    act_pool_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, ph, pw, invM, rate, ik, seed, layer, npix);
+    LAUNCH_CHECK();
+    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
 }
-int launch_relu6_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
-                     float* dz, double* red, long long M, int C, cudaStream_t st) {
+int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st) {
     dim3 grid, block; chan_block(C, M, grid, block);
-    relu6_bwd_kernel<<<grid, block, sizeof(float) * 2 * 256, st>>>(da, y, scale, shift, mean, invstd, dz, red, M, C);
+    const double invM = 1.0 / (double)M;
+    relu6_bwd_kernel<false><<<grid, block, sizeof(float) * 2 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
+    LAUNCH_CHECK();
+    relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
+    LAUNCH_CHECK();
+    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_bn_bwd_apply(float* dz, const float* y, const double* red, const float* gamma, const float* mean, const float* invstd,

@@ -216,6 +216,7 @@ void plan(crnn_handle* h) {
     A("dxp", M * 2 * h->G * h->U); A("hprev", M * 2 * h->U); A("rh", M * 2 * h->U);
     A("UT", (int64_t)2 * h->G * h->U * h->U);
     A("dtheta", B * 6); A("dd1", B * 50); A("dflat", B * h->sd.F);
+    A("wimg_head", (int64_t)tc_weight_image_floats(h->FEAT, h->TD > 1024 ? h->TD : 1024));   // head GEMMs reuse one image buffer
     for (int i = 2; i <= 7; ++i) {   // pre-swizzled hi/lo weight images of the tcgen05 pointwise kernel (gemm_tc.cu)
         const BlockPlan& b = kBlocks[i - 1];
         char nm2[32];
@@ -261,6 +262,16 @@ int gemm_nt(crnn_handle* h, int stage, const float* dY, int ldy, const float* Wt
     Scope _s(h, st, stage, 2.0 * M * Kin * N);
     return launch_gemm_simt(g, st);
 }
+
+// out[M][N] = [out +] relu?(X[M][K] @ Wop^T + bias) on the tensor cores; Wop[n][k] = W[k*ldw+n] (transposed) or W[n*ldw+k]
+int tc_xw(crnn_handle* h, int stage, const float* X, int ldx, const float* W, int ldw, int transposed, float* out, int ldo, int M, int N, int K,
+          const float* bias, int relu, int accumulate, cudaStream_t st) {
+    float* img = h->a("wimg_head");
+    ST(ST_MISC, 0, launch_prep_weight_images(W, ldw, N, K, transposed, img, st));
+    ST(stage, 2.0 * M * N * K, launch_xw_gemm_tc(X, ldx, img, out, ldo, M, N, K, nullptr, nullptr, nullptr, st, bias, relu, accumulate));
+    return CRNN_OK;
+}
+bool tc_ok(const crnn_handle* h, int N, int K) { return !h->gemm_simt && (K % 32 == 0) && (N % 4 == 0) && N >= 64; }
 
 std::string bnname(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b), "batch_normalization_%d/%s", bn, leaf); return b; }
 std::string actbn(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b), "bn%d/%s", bn, leaf); return b; }
@@ -315,15 +326,19 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
     }
     // ---- dense1 (utils.py:72-75): (B,T,9,512) is already (B*T, 4608) with feature = w*512+c
     const int M = B * T;
-    TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
+    if (tc_ok(h, h->TD, h->FEAT)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, 1, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, 0, st));
+    else TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
     if (drop) ST(ST_MISC, 0, launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st));
     // ---- two bidirectional recurrent layers (utils.py:77-82)
     const float* rin = h->a("dense1"); int kin = h->TD;
     for (int layer = 1; layer <= 2; ++layer) {
         float* xp = h->a(nm("xp%d", layer)); float* hs = h->a(nm("hs%d", layer));
-        for (int d = 0; d < 2; ++d)
-            TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
-                        h->w(h->rnn(layer, d) + "/bias"), 0, nullptr, nullptr, st));
+        for (int d = 0; d < 2; ++d) {
+            if (tc_ok(h, G * U, kin)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, 1, xp + d * G * U, 2 * G * U, M, G * U, kin,
+                                                h->w(h->rnn(layer, d) + "/bias"), 0, 0, st));
+            else TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
+                             h->w(h->rnn(layer, d) + "/bias"), 0, nullptr, nullptr, st));
+        }
         {
             const float* U0 = h->w(h->rnn(layer, 0) + "/recurrent_kernel"); const float* U1 = h->w(h->rnn(layer, 1) + "/recurrent_kernel");
             float* gsave = training ? h->a(nm("gates%d", layer)) : nullptr;
@@ -361,15 +376,21 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
         const std::string base = h->rnn(layer, d);
         const float* dxd = dxp + d * G * U;
         float* gU = h->g(base + "/recurrent_kernel");
+        const bool tc = !h->gemm_simt;
+        auto dwgemm = [&](const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw) -> int {
+            if (tc) { ST(ST_GEMM_HEAD_BWD, 2.0 * M * Cin * Cout, launch_xty_gemm_tc(X, ldx, Cin, dY, ldy, Cout, dW, ldw, M, nullptr, nullptr, st)); return CRNN_OK; }
+            return gemm_tn(h, ST_GEMM_HEAD_BWD, X, ldx, dY, ldy, dW, ldw, Cin, Cout, M, nullptr, nullptr, st);
+        };
         if (h->cfg.cell == CRNN_CELL_GRU) {
-            TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, 2 * U, M, nullptr, nullptr, st));
-            TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, rh + d * U, 2 * U, dxd + 2 * U, 2 * G * U, gU + 2 * U, G * U, U, U, M, nullptr, nullptr, st));
+            TRY(dwgemm(hprev + d * U, 2 * U, U, dxd, 2 * G * U, 2 * U, gU, G * U));
+            TRY(dwgemm(rh + d * U, 2 * U, U, dxd + 2 * U, 2 * G * U, U, gU + 2 * U, G * U));
         } else {
-            TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, hprev + d * U, 2 * U, dxd, 2 * G * U, gU, G * U, U, G * U, M, nullptr, nullptr, st));
+            TRY(dwgemm(hprev + d * U, 2 * U, U, dxd, 2 * G * U, G * U, gU, G * U));
         }
-        TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, rin, kin, dxd, 2 * G * U, h->g(base + "/kernel"), G * U, kin, G * U, M, nullptr, nullptr, st));
+        TRY(dwgemm(rin, kin, kin, dxd, 2 * G * U, G * U, h->g(base + "/kernel"), G * U));
         ST(ST_MISC, 0, launch_colsum(dxd, M, G * U, 2 * G * U, h->g(base + "/bias"), st));
-        TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, dxd, 2 * G * U, h->w(base + "/kernel"), G * U, dx, kin, M, kin, G * U, d, st));
+        if (tc_ok(h, kin, G * U)) TRY(tc_xw(h, ST_GEMM_HEAD_BWD, dxd, 2 * G * U, h->w(base + "/kernel"), G * U, 0, dx, kin, M, kin, G * U, nullptr, 0, d, st));
+        else TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, dxd, 2 * G * U, h->w(base + "/kernel"), G * U, dx, kin, M, kin, G * U, d, st));
     }
     return CRNN_OK;
 }
@@ -382,10 +403,10 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
     const float* dw = h->a(nm("dw%d", i)); const float* pw = h->a(nm("pw%d", i));
     const int bn1 = 2 * i - 1, bn2 = 2 * i;
     CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cout, st));
-    ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (2.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
-                            other, red, B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
-    ST(ST_BN_BWD, 12.0 * Mi * b.cout, launch_bn_bwd_apply(other, pw, red, h->w(bnname(bn2, "gamma")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
-                            h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")), Mi, b.cout, st));
+    ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (3.0 + 2.0 / (b.ph * b.pw)),
+       launch_act_pool_bn_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
+                              h->w(bnname(bn2, "gamma")), other, red, h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")),
+                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
     if (!h->gemm_simt && (b.cin % 4 == 0)) {
         ST(ST_GEMM_PW_DW, 2.0 * Mi * b.cin * b.cout, launch_xty_gemm_tc(dw, b.cin, b.cin, other, b.cout, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, (int)Mi,
                                                                        h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
@@ -401,10 +422,9 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
         TRY(gemm_nt(h, ST_GEMM_PW_DX, other, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, cur, b.cin, (int)Mi, b.cin, b.cout, 0, st));
     }
     CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cin, st));
-    ST(ST_ACT_BWD, 12.0 * Mi * b.cin, launch_relu6_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                         cur, red, Mi, b.cin, st));
-    ST(ST_BN_BWD, 12.0 * Mi * b.cin, launch_bn_bwd_apply(cur, dw, red, h->w(bnname(bn1, "gamma")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                            h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
+    ST(ST_BN_BWD, 20.0 * Mi * b.cin,
+       launch_relu6_bn_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+                           h->w(bnname(bn1, "gamma")), cur, red, h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
     const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
     ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, cur, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, st));
     ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(cur, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
@@ -432,9 +452,11 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     TRY(rnn_backward(h, 1, gA, h->a("dense1"), h->TD, gB, B, st));      // gB = d dense1 (M,TD)
     // ---- dense1
     ST(ST_MISC, 0, launch_relu_dropout_bwd(gB, h->a("dense1"), (long long)M * h->TD, drop ? kDropDense1 : 0.f, seed, 8, st));
-    TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, h->a("block7"), h->FEAT, gB, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, st));
+    if (!h->gemm_simt) ST(ST_GEMM_HEAD_BWD, 2.0 * M * h->FEAT * h->TD, launch_xty_gemm_tc(h->a("block7"), h->FEAT, h->FEAT, gB, h->TD, h->TD, h->g("dense1/kernel"), h->TD, M, nullptr, nullptr, st));
+    else TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, h->a("block7"), h->FEAT, gB, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, st));
     ST(ST_MISC, 0, launch_colsum(gB, M, h->TD, h->TD, h->g("dense1/bias"), st));
-    TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, gB, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
+    if (tc_ok(h, h->FEAT, h->TD)) TRY(tc_xw(h, ST_GEMM_HEAD_BWD, gB, h->TD, h->w("dense1/kernel"), h->TD, 0, gA, h->FEAT, M, h->FEAT, h->TD, nullptr, 0, 0, st));
+    else TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, gB, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
     // ---- conv stack, reverse
     float* cur = gA; float* other = gB;
     int dims_h[8], dims_w[8];

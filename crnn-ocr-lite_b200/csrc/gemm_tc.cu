@@ -95,6 +95,7 @@ struct TcArgs {
     int M, N, K;
     const float* x_scale; const float* x_shift;   // optional BN+ReLU6 on X (per k)
     double* stats;                    // optional [2*N] column sum / sum of squares of out
+    const float* bias; int relu; int accumulate;   // epilogue: out = [out +] relu?(acc + bias[n])
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int n = ct * TC_BC + warp * 32 + lane;          // this thread's output channel
         const bool n_ok = n < a.N;
+        const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < TC_BP; c0 += 32) {
@@ -193,8 +195,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
             for (int p = 0; p < 32; ++p) {
                 const int m = m0 + c0 + p;
                 if (m < a.M && n_ok) {
-                    const float val = __uint_as_float(r[p]);
-                    a.out[(size_t)m * a.ldo + n] = val;          // 32 lanes = 32 consecutive channels: 128-byte coalesced
+                    float val = __uint_as_float(r[p]) + bias;
+                    if (a.relu) val = fmaxf(val, 0.f);
+                    float* dst = a.out + (size_t)m * a.ldo + n;   // 32 lanes = 32 consecutive channels: 128-byte coalesced
+                    if (a.accumulate) val += *dst;
+                    *dst = val;
                     s1 += val; s2 = fmaf(val, val, s2);
                 }
             }
@@ -234,9 +239,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
 // =====================================================================================================================
 // Weight gradient of the pointwise conv:  dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]     (contraction over PIXELS)
 // Both operands are "MN-major" for the tensor core (channels contiguous per pixel row), so the producers keep the natural
-// 128-byte channel rows: tile = [mn-block of 32 channels][k-group of 8 pixels][8 pixel rows x 128 B], SWIZZLE_128B
-// (16-byte chunk index XOR pixel-row index), LBO = mn-block stride (4096 B), SBO = k-group stride (1024 B); one
-// tcgen05.mma (K = 8 tf32) consumes one k-group.  D[128 ci lanes][NB co columns] accumulates in TMEM over the CTA's pixel
+// 128-byte channel rows.  MN-major TF32 only exists with LayoutType SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom,
+// Swizzle<2,5,2>): atom = 4 pixel rows x 128 B, the 32-byte chunk index is XORed with the row index.  Tile =
+// [mn-block of 32 channels][k-group of 4 pixels][4 rows x 128 B]; LBO = mn-block stride (4096 B), SBO = k-group stride
+// (512 B); one tcgen05.mma (K = 8 tf32) consumes two k-groups (start address advances by 1024 B).  D[128 ci lanes][NB co columns] accumulates in TMEM over the CTA's pixel
 // range (split-K over pixels across CTAs), epilogue = fp32 atomicAdd into the pre-zeroed gradient.
 // =====================================================================================================================
 template <int NB> struct DwCfg {
@@ -247,8 +253,13 @@ template <int NB> struct DwCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4 + 1024 + 256;
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {   // MN-major SWIZZLE_128B: LBO = 4096 B, SBO = 1024 B
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (256ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {   // MN-major SWIZZLE_128B_BASE32B: LBO = 4096 B, SBO = 512 B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+// float offset of (pixel row pl in 0..31, 16-byte chunk c16 in 0..7) inside one 32-channel mn-block of an MN-major tile
+__device__ __forceinline__ int mn_off(int pl, int c16) {
+    const int kr = pl & 3, kg = pl >> 2;
+    return kg * 128 + kr * 32 + ((((c16 >> 1) ^ kr) << 3) | ((c16 & 1) << 2));
 }
 template <uint32_t IDESC>
 __device__ __forceinline__ void umma_tf32_i(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -334,8 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 uint32_t hi[4]; float lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(x[e]); lo[e] = x[e] - __uint_as_float(hi[e]); }
-                const int kr = pl & 7, g = pl >> 3;
-                const int off = mb * 1024 + g * 256 + kr * 32 + ((chunk ^ kr) << 2);     // floats
+                const int off = mb * 1024 + mn_off(pl, chunk);     // floats
                 *reinterpret_cast<uint4*>(Ahi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -356,8 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                     uint32_t hi[4]; float lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(x[e]); lo[e] = x[e] - __uint_as_float(hi[e]); }
-                    const int kr = pl & 7, g = pl >> 3;
-                    const int off = (gq * 4 + mb) * 1024 + g * 256 + kr * 32 + ((chunk ^ kr) << 2);
+                    const int off = (gq * 4 + mb) * 1024 + mn_off(pl, chunk);
                     *reinterpret_cast<uint4*>(Bhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<float4*>(Blo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 const uint32_t ahi = smem_u32(stage_base + (size_t)s * C::STAGE_FLOATS);
                 const uint32_t alo = ahi + C::A_FLOATS * 4, bhi = alo + C::A_FLOATS * 4, blo = bhi + C::B_FLOATS * 4;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {                  // one k-group (8 pixels) per MMA
+                for (int g = 0; g < 4; ++g) {                  // 8 pixels (two 4-row atoms, 1024 B) per MMA
                     const uint32_t o = g * 1024;
                     umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(alo + o), umma_desc_mn(bhi + o), (kb | g) ? 1u : 0u);
                     umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(ahi + o), umma_desc_mn(blo + o), 1u);
@@ -459,7 +468,8 @@ int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transpo
 }
 
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
-                      const float* x_scale, const float* x_shift, double* stats, cudaStream_t st)
+                      const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
+                      const float* bias, int relu, int accumulate)
 {
     if (M <= 0 || N <= 0) return CRNN_OK;
     if (K % TC_BK || K <= 0) { crnn_set_error("gemm_tc: K=%d must be a positive multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
@@ -467,7 +477,7 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     static bool configured = false;
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); configured = true; }
     TcArgs a; a.X = X; a.ldx = ldx; a.Wimg = Wimg; a.out = out; a.ldo = ldo; a.M = M; a.N = N; a.K = K;
-    a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats;
+    a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats; a.bias = bias; a.relu = relu; a.accumulate = accumulate;
     dim3 grid((N + TC_BC - 1) / TC_BC, (M + TC_BP - 1) / TC_BP);
     xw_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
     LAUNCH_CHECK();

@@ -21,7 +21,8 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 size_t tc_weight_image_floats(int N, int K);
 int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transposed, float* img, cudaStream_t st);
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
-                      const float* x_scale, const float* x_shift, double* stats, cudaStream_t st);
+                      const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
+                      const float* bias = nullptr, int relu = 0, int accumulate = 0);
 
 // dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]  (tcgen05, MN-major operands, split-K over pixels, atomics into pre-zeroed dW)
 int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
@@ -49,13 +50,14 @@ int launch_bn_finalize(const double* stats, long long M, int C, const float* gam
 // a = dropout(pool(relu6(y*scale+shift)))  ; pool (ph,pw) in {(1,1),(2,2),(1,2)}
 int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C,
                         int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
-// dz = unpool(da * dropmask) * 1[0 <= z <= 6] with z = y*scale+shift ; also accumulates sum(dz), sum(dz*xhat) (double[2C], pre-zeroed)
-int launch_act_pool_bwd(const float* da, const float* y, const float* scale, const float* shift,
-                        const float* save_mean, const float* save_invstd, float* dz, double* red,
-                        int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
-// dz = da * 1[0<=z<=6] (no pool/dropout), z = y*scale+shift, + reductions  (the BN after the depthwise conv)
-int launch_relu6_bwd(const float* da, const float* y, const float* scale, const float* shift,
-                     const float* save_mean, const float* save_invstd, float* dz, double* red, long long M, int C, cudaStream_t st);
+// fused (ReLU6 + MaxPool + Dropout) backward + BatchNorm-train backward, two passes over (da, y), no dz round trip:
+//   dz = unpool(da*dropmask) * 1[0<=z<=6];  dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dgamma += sum(dz*xhat), dbeta += sum(dz)
+int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                           const float* gamma, float* dy, double* red /*pre-zeroed [2C]*/, float* dgamma, float* dbeta,
+                           int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+// same for the BN after the depthwise conv (no pool / dropout); dy may alias da
+int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
 // BN training backward: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) in place; dgamma = sum(dz*xhat), dbeta = sum(dz)
 int launch_bn_bwd_apply(float* dz_inout, const float* y, const double* red, const float* gamma, const float* save_mean,
                         const float* save_invstd, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
