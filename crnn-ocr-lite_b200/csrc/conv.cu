@@ -225,15 +225,16 @@ __global__ void act_pool_fwd_kernel(const float* __restrict__ y, const float* __
 //   APPLY=false: only the reductions sum(dz), sum(dz*xhat) per channel (registers -> smem -> one double atomic per channel per CTA)
 //   APPLY=true : recomputes dz and writes the BatchNorm-backward result dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))
 // so the intermediate dz never touches HBM.  dz = unpool(da * dropmask) * 1[0 <= z <= 6], z = y*scale+shift.
-template <bool APPLY>
-__global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ scale,
+template <bool APPLY, int PH, int PW>
+__global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, float* __restrict__ dy, double* __restrict__ red,
-                                    int B, int H, int W, int C4, int ph, int pw, double invM,
+                                    int B, int H, int W, int C4, double invM,
                                     float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix)
 {
     extern __shared__ float sred[];   // [PY][8][CQ]
     const int CQ = blockDim.x, PY = blockDim.y;
+    constexpr int ph = PH, pw = PW;
     const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
@@ -259,12 +260,14 @@ __global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* _
             if (rate > 0.f)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) g[q] *= crnn_dropout_mask(seed, layer, oidx * 4 + q, rate, inv_keep);
-            float yv[4][4], best[4]; int arg[4];   // window <= 4 elements
+            float yv[PH * PW][4], best[4]; int arg[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) { best[q] = -INFINITY; arg[q] = 0; }
-            int n = 0;
+#pragma unroll
             for (int i = 0; i < ph; ++i)
-                for (int j = 0; j < pw; ++j, ++n) {
+#pragma unroll
+                for (int j = 0; j < pw; ++j) {
+                    const int n = i * pw + j;
                     float4 t = ldg4(y + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4);
                     yv[n][0] = t.x; yv[n][1] = t.y; yv[n][2] = t.z; yv[n][3] = t.w;
 #pragma unroll
@@ -273,9 +276,11 @@ __global__ void act_pool_bwd_kernel(const float* __restrict__ da, const float* _
                         if (aq > best[q]) { best[q] = aq; arg[q] = n; }   // first max wins (TF / torch max-pool grad)
                     }
                 }
-            n = 0;
+#pragma unroll
             for (int i = 0; i < ph; ++i)
-                for (int j = 0; j < pw; ++j, ++n) {
+#pragma unroll
+                for (int j = 0; j < pw; ++j) {
+                    const int n = i * pw + j;
                     float o[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -504,9 +509,13 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
     const double invM = 1.0 / ((double)B * H * W);
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
-    act_pool_bwd_kernel<false><<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, ph, pw, invM, rate, ik, seed, layer, npix);
-    LAUNCH_CHECK();
-    act_pool_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, ph, pw, invM, rate, ik, seed, layer, npix);
+#define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix)
+    const size_t sm = sizeof(float) * 8 * 256;
+    if (ph == 1 && pw == 1) { APB(false, 1, 1, sm); LAUNCH_CHECK(); APB(true, 1, 1, 0); }
+    else if (ph == 2 && pw == 2) { APB(false, 2, 2, sm); LAUNCH_CHECK(); APB(true, 2, 2, 0); }
+    else if (ph == 1 && pw == 2) { APB(false, 1, 2, sm); LAUNCH_CHECK(); APB(true, 1, 2, 0); }
+    else { crnn_set_error("act_pool: unsupported pool %dx%d", ph, pw); return CRNN_ERR_INVALID; }
+#undef APB
     LAUNCH_CHECK();
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
