@@ -40,6 +40,44 @@ __global__ void dwconv3x3_vec4(const float* __restrict__ x, const float* __restr
         *reinterpret_cast<float4*>(y + (size_t)idx * 4) = acc;
     }
 }
+// 4 consecutive w positions per thread: 18 input + 9 weight float4 loads for 4 outputs (sliding window in registers)
+template <bool FLIP>
+__global__ void __launch_bounds__(256) dwconv3x3_vec4_w4(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
+                                                         int B, int H, int W, int C4, int WG, long long total)
+{
+    const int C = C4 * 4;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(idx % C4); long long r = idx / C4;
+        int wg = (int)(r % WG); r /= WG;
+        int h = (int)(r % H); int b = (int)(r / H);
+        const int w0 = wg * 4;
+        float4 kv[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) kv[q] = ldg4(k + (size_t)q * C + c4 * 4);
+        float4 acc[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int hh = FLIP ? h - i + 1 : h + i - 1;
+            if (hh < 0 || hh >= H) continue;
+            const float* row = x + (((size_t)b * H + hh) * W) * C + c4 * 4;
+            float4 xv[6];
+#pragma unroll
+            for (int t = 0; t < 6; ++t) {
+                const int col = w0 - 1 + t;
+                xv[t] = (col >= 0 && col < W) ? ldg4(row + (size_t)col * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) fma4(acc[o], xv[FLIP ? (o - j + 2) : (o + j)], kv[i * 3 + j]);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (w0 + o < W) *reinterpret_cast<float4*>(y + ((((size_t)b * H + h) * W + w0 + o) * C4 + c4) * 4) = acc[o];
+    }
+}
 template <bool FLIP>
 __global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                              int B, int H, int W, long long total)
@@ -65,8 +103,8 @@ __global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restric
 
 // ------------------------------------------------------------------ depthwise 3x3 backward-weight
 // dk[i][j][c] = sum_{b,h,w} x[b,h+i-1,w+j-1,c] * dy[b,h,w,c].  blockDim = (CQ channel-quads | CT channels, PY pixel lanes)
-__global__ void dwconv3x3_bwd_weight_vec4(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
-                                          int B, int H, int W, int C4, long long npix)
+__global__ void __launch_bounds__(256) dwconv3x3_bwd_weight_vec4(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
+                                          int B, int H, int W, int C4, int WG, long long ngroups)
 {
     extern __shared__ float red[];   // [PY][36][CQ]
     const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
@@ -75,20 +113,30 @@ __global__ void dwconv3x3_bwd_weight_vec4(const float* __restrict__ x, const flo
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c4 < C4) {
-        for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < npix; p += (long long)gridDim.y * PY) {
-            int w = (int)(p % W); long long r = p / W;
+        // one iteration = 4 consecutive pixels of a row: 18 x loads + 4 dy loads feed 36 float4 FMAs
+        for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < ngroups; p += (long long)gridDim.y * PY) {
+            int wg = (int)(p % WG); long long r = p / WG;
             int h = (int)(r % H); int b = (int)(r / H);
-            const float4 g = ldg4(dy + (size_t)p * C + c4 * 4);
+            const int w0 = wg * 4;
+            float4 g[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                g[o] = (w0 + o < W) ? ldg4(dy + ((((size_t)b * H + h) * W + w0 + o) * C4 + c4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                int hh = h + i - 1;
+                const int hh = h + i - 1;
                 if (hh < 0 || hh >= H) continue;
+                const float* row = x + (((size_t)b * H + hh) * W) * C + c4 * 4;
+                float4 xv[6];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    int ww = w + j - 1;
-                    if (ww < 0 || ww >= W) continue;
-                    fma4(acc[i * 3 + j], ldg4(x + (((size_t)b * H + hh) * W + ww) * C + c4 * 4), g);
+                for (int t = 0; t < 6; ++t) {
+                    const int col = w0 - 1 + t;
+                    xv[t] = (col >= 0 && col < W) ? ldg4(row + (size_t)col * C) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) fma4(acc[i * 3 + j], xv[o + j], g[o]);
             }
         }
     }
@@ -251,6 +299,7 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
                 m1[q] = (float)(red[c4 * 4 + q] * invM); m2[q] = (float)(red[C + c4 * 4 + q] * invM);
             }
         }
+#pragma unroll 2
         for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < npix; p += (long long)gridDim.y * PY) {
             int wo = (int)(p % Wo); long long r = p / Wo;
             int ho = (int)(r % Ho); int b = (int)(r / Ho);
@@ -321,7 +370,7 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ red, float* __r
 // ReLU6 + BatchNorm backward of the BN that follows the depthwise conv (no pool / dropout): y, da, dy are [M][C].
 //   APPLY=false: reductions only;  APPLY=true: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dy may alias da.
 template <bool APPLY>
-__global__ void relu6_bwd_kernel(const float* da /* may alias dy */, const float* __restrict__ y, const float* __restrict__ scale,
+__global__ void relu6_bwd_scalar_kernel(const float* da /* may alias dy */, const float* __restrict__ y, const float* __restrict__ scale,
                                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                  const float* __restrict__ gamma, float* dy, double* __restrict__ red, long long M, int C, double invM)
 {
@@ -350,6 +399,68 @@ __global__ void relu6_bwd_kernel(const float* da /* may alias dy */, const float
         double t1 = 0.0, t2 = 0.0;
         for (int i = 0; i < PY; ++i) { t1 += sred[(i * 2) * CT + threadIdx.x]; t2 += sred[(i * 2 + 1) * CT + threadIdx.x]; }
         atomicAdd(red + c, t1); atomicAdd(red + C + c, t2);
+    }
+}
+
+// float4 version (C % 4 == 0): blockDim = (CQ channel quads, PY row lanes), two rows per iteration for memory-level parallelism
+template <bool APPLY>
+__global__ void __launch_bounds__(256) relu6_bwd_kernel(const float* da /* may alias dy */, const float* __restrict__ y, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                 const float* __restrict__ gamma, float* dy, double* __restrict__ red, long long M, int C4, double invM)
+{
+    extern __shared__ float sred[];   // [PY][8][CQ]
+    const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    if (c4 < C4) {
+        float sc[4], sh[4], mu[4], is[4], gs[4] = {0, 0, 0, 0}, m1[4] = {0, 0, 0, 0}, m2[4] = {0, 0, 0, 0};
+        { float4 t = ldg4(scale + c4 * 4); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
+        { float4 t = ldg4(shift + c4 * 4); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
+        { float4 t = ldg4(mean + c4 * 4); mu[0] = t.x; mu[1] = t.y; mu[2] = t.z; mu[3] = t.w; }
+        { float4 t = ldg4(invstd + c4 * 4); is[0] = t.x; is[1] = t.y; is[2] = t.z; is[3] = t.w; }
+        if (APPLY) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { gs[q] = gamma[c4 * 4 + q] * is[q]; m1[q] = (float)(red[c4 * 4 + q] * invM); m2[q] = (float)(red[C + c4 * 4 + q] * invM); }
+        }
+        const long long stride = (long long)gridDim.y * PY;
+        for (long long m = blockIdx.y * (long long)PY + threadIdx.y; m < M; m += 2 * stride) {
+            const long long m2r = m + stride;
+            const bool two = m2r < M;
+            const size_t o0 = ((size_t)m * C4 + c4) * 4, o1 = ((size_t)(two ? m2r : m) * C4 + c4) * 4;
+            const float4 y0 = ldg4(y + o0), y1 = ldg4(y + o1);
+            const float4 d0 = *reinterpret_cast<const float4*>(da + o0), d1 = *reinterpret_cast<const float4*>(da + o1);
+            const float yv[2][4] = {{y0.x, y0.y, y0.z, y0.w}, {y1.x, y1.y, y1.z, y1.w}};
+            const float dv[2][4] = {{d0.x, d0.y, d0.z, d0.w}, {d1.x, d1.y, d1.z, d1.w}};
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (rr == 1 && !two) break;
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float z = fmaf(yv[rr][q], sc[q], sh[q]);
+                    const float d = (z >= 0.f && z <= 6.f) ? dv[rr][q] : 0.f;
+                    const float xh = (yv[rr][q] - mu[q]) * is[q];
+                    if (APPLY) o[q] = gs[q] * (d - m1[q] - xh * m2[q]);
+                    else { s1[q] += d; s2[q] = fmaf(d, xh, s2[q]); }
+                }
+                if (APPLY) *reinterpret_cast<float4*>(dy + (rr ? o1 : o0)) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    if (APPLY) return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sred[(threadIdx.y * 8 + q) * CQ + threadIdx.x] = s1[q];
+        sred[(threadIdx.y * 8 + 4 + q) * CQ + threadIdx.x] = s2[q];
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && c4 < C4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double t1 = 0.0, t2 = 0.0;
+            for (int i = 0; i < PY; ++i) { t1 += sred[(i * 8 + q) * CQ + threadIdx.x]; t2 += sred[(i * 8 + 4 + q) * CQ + threadIdx.x]; }
+            atomicAdd(red + c4 * 4 + q, t1); atomicAdd(red + C + c4 * 4 + q, t2);
+        }
     }
 }
 
@@ -460,14 +571,14 @@ inline void chan_block(int C, long long M, dim3& grid, dim3& block) {
 }  // namespace
 
 int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st) {
-    if (C % 4 == 0) { long long total = (long long)B * H * W * (C / 4); dwconv3x3_vec4<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, C / 4, total); }
+    if (C % 4 == 0) { const int WG = (W + 3) / 4; long long total = (long long)B * H * WG * (C / 4); dwconv3x3_vec4_w4<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, C / 4, WG, total); }
     else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
     if (accumulate) { crnn_set_error("dwconv_bwd_data: accumulate unsupported"); return CRNN_ERR_INVALID; }
-    if (C % 4 == 0) { long long total = (long long)B * H * W * (C / 4); dwconv3x3_vec4<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, C / 4, total); }
+    if (C % 4 == 0) { const int WG = (W + 3) / 4; long long total = (long long)B * H * WG * (C / 4); dwconv3x3_vec4_w4<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, C / 4, WG, total); }
     else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;
@@ -475,8 +586,9 @@ int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, in
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk, int B, int H, int W, int C, cudaStream_t st) {
     dim3 grid, block; long long npix = (long long)B * H * W;
     if (C % 4 == 0) {
-        chan_block(C / 4, npix, grid, block);
-        dwconv3x3_bwd_weight_vec4<<<grid, block, sizeof(float) * 36 * 256, st>>>(x, dy, dk, B, H, W, C / 4, npix);
+        const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
+        chan_block(C / 4, ngroups, grid, block);
+        dwconv3x3_bwd_weight_vec4<<<grid, block, sizeof(float) * 36 * 256, st>>>(x, dy, dk, B, H, W, C / 4, WG, ngroups);
     } else {
         chan_block(C, npix, grid, block);
         dwconv3x3_bwd_weight<<<grid, block, sizeof(float) * block.y * 9 * block.x, st>>>(x, dy, dk, B, H, W, C, npix);
@@ -522,11 +634,19 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
 }
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                         const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st) {
-    dim3 grid, block; chan_block(C, M, grid, block);
+    dim3 grid, block;
     const double invM = 1.0 / (double)M;
-    relu6_bwd_kernel<false><<<grid, block, sizeof(float) * 2 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
-    LAUNCH_CHECK();
-    relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
+    if (C % 4 == 0) {
+        chan_block(C / 4, (M + 1) / 2, grid, block);
+        relu6_bwd_kernel<false><<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM);
+        LAUNCH_CHECK();
+        relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM);
+    } else {
+        chan_block(C, M, grid, block);
+        relu6_bwd_scalar_kernel<false><<<grid, block, sizeof(float) * 2 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
+        LAUNCH_CHECK();
+        relu6_bwd_scalar_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
+    }
     LAUNCH_CHECK();
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
