@@ -20,6 +20,8 @@
 // Pipeline: 3 smem stages of {Whi, Wlo, Xhi, Xlo} x (128 rows x 32 fp32) = 64 KB; mbarriers full[s] (128 producer arrivals + 1 expect_tx +
 // bulk-copy transaction bytes), empty[s] (tcgen05.commit), acc (tcgen05.commit after the last k-block).
 // Warp 4 = TMEM allocator + single-thread MMA issuer.  One CTA per SM (192 KB smem), grid = (channel tiles, pixel tiles).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -278,10 +280,13 @@ struct DwArgs {
     const float* x_scale; const float* x_shift;
 };
 
+constexpr int DW_THREADS = 288;     // 8 producer warps + 1 MMA warp
+
 template <int NB>
-__global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
+__global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
 {
     using C = DwCfg<NB>;
+    constexpr int NG = NB / 128;            // 128-channel groups of the dY tile
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* stage_base = (float*)smem;
@@ -297,11 +302,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
     if (KB <= 0) return;                       // uniform for the whole CTA
 
     if (tid == 0) {
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 256); mbar_init(&empty[s], 1); }
         mbar_init(accb, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NB) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -310,33 +315,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ------------------------------------------------ producers
+    if (warp < 8) {
+        // ------------------------------------------------ producers (next k-block's loads stay in flight in registers)
         const int q = tid & 31;                 // channel quad inside a 128-channel group
-        const int pr0 = tid >> 5;               // pixel rows pr0 + 4*i
+        const int pr0 = tid >> 5;               // pixel rows pr0 + 8*i
         const int ci = ci0 + q * 4;
-        const bool ci_ok = ci < a.Cin;          // Cin is a multiple of 4
+        const bool ci_ok = ci < a.Cin;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.x_scale && ci_ok) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + ci)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + ci)); }
-        const int mb = q >> 3, chunk = q & 7;   // mn-block (32 channels) and 16-byte chunk of this quad
+        const int mb = q >> 3, chunk = q & 7;
+        float4 xv[4], yv[NG][4], xn[4], yn[NG][4];
+        auto prefetch = [&](int kb, float4 (&xd)[4], float4 (&yd)[NG][4]) {
+            const int pbase = p_begin + kb * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int p = pbase + pr0 + 8 * i;
+                xd[i] = (p < p_end && ci_ok) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)p * a.ldx + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const int co = co0 + g * 128 + q * 4;
+                    yd[g][i] = (p < p_end && co < a.Cout) ? __ldg(reinterpret_cast<const float4*>(a.dY + (size_t)p * a.ldy + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        prefetch(0, xv, yv);
         for (int kb = 0; kb < KB; ++kb) {
+            if (kb + 1 < KB) prefetch(kb + 1, xn, yn);
             const int s = kb % C::STAGES;
             const uint32_t ph = (kb / C::STAGES) & 1;
             mbar_wait(&empty[s], ph ^ 1);
             float* Ahi = stage_base + (size_t)s * C::STAGE_FLOATS;
             float* Alo = Ahi + C::A_FLOATS; float* Bhi = Alo + C::A_FLOATS; float* Blo = Bhi + C::B_FLOATS;
             const int pbase = p_begin + kb * 32;
-            // X tile: 32 pixels x 128 ci
-            float4 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int p = pbase + pr0 + 4 * i;
-                v[i] = (p < p_end && ci_ok) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)p * a.ldx + ci)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int pl = pr0 + 4 * i;                       // pixel row inside the k-block
-                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            for (int i = 0; i < 4; ++i) {
+                const int pl = pr0 + 8 * i;
+                float x[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
                 if (a.x_scale) {
                     x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
                     x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
@@ -345,43 +359,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 uint32_t hi[4]; float lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(x[e]); lo[e] = x[e] - __uint_as_float(hi[e]); }
-                const int off = mb * 1024 + mn_off(pl, chunk);     // floats
+                const int off = mb * 1024 + mn_off(pl, chunk);
                 *reinterpret_cast<uint4*>(Ahi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            // dY tile: 32 pixels x NB co  (NB/128 groups of 128 channels)
 #pragma unroll
-            for (int gq = 0; gq < NB / 128; ++gq) {
-                const int co = co0 + gq * 128 + q * 4;
-                const bool co_ok = co < a.Cout;
+                for (int g = 0; g < NG; ++g) {
+                    const float y[4] = {yv[g][i].x, yv[g][i].y, yv[g][i].z, yv[g][i].w};
+                    uint32_t yh[4]; float yl[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int p = pbase + pr0 + 4 * i;
-                    v[i] = (p < p_end && co_ok) ? __ldg(reinterpret_cast<const float4*>(a.dY + (size_t)p * a.ldy + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int pl = pr0 + 4 * i;
-                    const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                    uint32_t hi[4]; float lo[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(x[e]); lo[e] = x[e] - __uint_as_float(hi[e]); }
-                    const int off = (gq * 4 + mb) * 1024 + mn_off(pl, chunk);
-                    *reinterpret_cast<uint4*>(Bhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(Blo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    for (int e = 0; e < 4; ++e) { yh[e] = to_tf32(y[e]); yl[e] = y[e] - __uint_as_float(yh[e]); }
+                    const int offb = (g * 4 + mb) * 1024 + mn_off(pl, chunk);
+                    *reinterpret_cast<uint4*>(Bhi + offb) = make_uint4(yh[0], yh[1], yh[2], yh[3]);
+                    *reinterpret_cast<float4*>(Blo + offb) = make_float4(yl[0], yl[1], yl[2], yl[3]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full[s]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xv[i] = xn[i];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) yv[g][i] = yn[g][i];
+            }
         }
-        // ------------------------------------------------ epilogue: TMEM -> atomicAdd into dW
+        // ------------------------------------------------ epilogue: TMEM -> atomicAdd into dW (warps w and w+4 split the columns)
         mbar_wait(accb, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = ci0 + warp * 32 + lane;
+        const int lq = warp & 3;
+        const int row = ci0 + lq * 32 + lane;
+        const int cbeg = (warp >> 2) * (NB / 2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < NB; c0 += 32) {
+        for (int c0 = cbeg; c0 < cbeg + NB / 2; c0 += 32) {
             uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
-        // ------------------------------------------------ warp 4: MMA issue
+        // ------------------------------------------------ warp 8: MMA issue
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % C::STAGES;
             const uint32_t ph = (kb / C::STAGES) & 1;
@@ -425,9 +435,187 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NB) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// v2 of the kernel above: PERSISTENT CTAs (one per SM) walking a static tile schedule (channel tile fastest, so the CTAs
+// that run concurrently share the activation tile in L2), with
+//   * producers (warps 0-3) that keep the NEXT k-block's global loads in flight in registers while they transform and store
+//     the current one (the ncu capture of v1 showed 1.7 long-scoreboard stalls per issue and 8 % resident warps);
+//   * two TMEM accumulator buffers (2 x 128 columns) and dedicated epilogue warps (5-8), so the TMEM->HBM epilogue of tile i
+//     overlaps the MMAs of tile i+1;  barriers: full/empty per smem stage, tmem_full/tmem_empty per accumulator buffer.
+// =====================================================================================================================
+constexpr int TC2_THREADS = 288;
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NT, int MT)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* stage_base = (float*)smem;
+    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = bars; uint64_t* empty = bars + TC_STAGES;
+    uint64_t* tfull = bars + 2 * TC_STAGES; uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KB = a.K / TC_BK;
+    const int total = NT * MT;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =========================== producers ===========================
+        const int c8 = tid & 7, r0 = tid >> 3;
+        int t = blockIdx.x, kb = 0;
+        float4 v[8], vn[8];
+        auto prefetch = [&](int tt, int kk, float4 (&dst)[8]) {
+            const int m0 = (tt / NT) * TC_BP;
+            const int k = kk * TC_BK + c8 * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + r0 + 16 * i;
+                dst[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (t < total) prefetch(t, 0, v);
+        uint32_t it = 0;
+        while (t < total) {
+            int tn = t, kn = kb + 1;
+            if (kn == KB) { kn = 0; tn = t + gridDim.x; }
+            if (tn < total) prefetch(tn, kn, vn);
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            float* Whi = stage_base + (size_t)s * (4 * TC_TILE_FLOATS);
+            float* Wlo = Whi + TC_TILE_FLOATS; float* Xhi = Wlo + TC_TILE_FLOATS; float* Xlo = Xhi + TC_TILE_FLOATS;
+            const int ct = t % NT, m0 = (t / NT) * TC_BP;
+            if (tid == 0) {
+                const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
+                mbar_arrive_expect_tx(&full[s], 2 * TC_TILE_FLOATS * 4);
+                bulk_g2s(Whi, src, TC_TILE_FLOATS * 4, &full[s]);
+                bulk_g2s(Wlo, src + TC_TILE_FLOATS, TC_TILE_FLOATS * 4, &full[s]);
+            }
+            const int k = kb * TC_BK + c8 * 4;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.x_scale) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + k)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + k)); }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 16 * i;
+                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                if (a.x_scale) {
+                    x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
+                    x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
+                    if (m0 + r >= a.M) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                }
+                uint32_t hi[4]; float lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(x[q]); lo[q] = x[q] - __uint_as_float(hi[q]); }
+                const int off = (r >> 3) * 256 + (r & 7) * 32 + ((c8 ^ (r & 7)) << 2);
+                *reinterpret_cast<uint4*>(Xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(Xlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full[s]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = vn[i];
+            t = tn; kb = kn; ++it;
+        }
+    } else if (warp == 4) {
+        // =========================== MMA issuer ===========================
+        uint32_t it = 0;
+        int j = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+            const int buf = j & 1;
+            mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * TC_BP);
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t whi = smem_u32(stage_base + (size_t)s * (4 * TC_TILE_FLOATS));
+                    const uint32_t wlo = whi + TC_TILE_FLOATS * 4, xhi = wlo + TC_TILE_FLOATS * 4, xlo = xhi + TC_TILE_FLOATS * 4;
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        const uint32_t o = ks * 32;
+                        umma_tf32(tacc, umma_desc(wlo + o), umma_desc(xhi + o), (kb | ks) ? 1u : 0u);
+                        umma_tf32(tacc, umma_desc(whi + o), umma_desc(xlo + o), 1u);
+                        umma_tf32(tacc, umma_desc(whi + o), umma_desc(xhi + o), 1u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == KB - 1) umma_commit(&tfull[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =========================== epilogue warps 5..8 ===========================
+        const int q = warp & 3;                                     // TMEM lane quarter this warp may access
+        int j = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+            const int buf = j & 1;
+            const int ct = t % NT, m0 = (t / NT) * TC_BP;
+            mbar_wait(&tfull[buf], (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int n = ct * TC_BC + q * 32 + lane;
+            const bool n_ok = n < a.N;
+            const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_BP; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BP + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int p = 0; p < 32; ++p) {
+                    const int m = m0 + c0 + p;
+                    if (m < a.M && n_ok) {
+                        float val = __uint_as_float(r[p]) + bias;
+                        if (a.relu) val = fmaxf(val, 0.f);
+                        float* dst = a.out + (size_t)m * a.ldo + n;
+                        if (a.accumulate) val += *dst;
+                        *dst = val;
+                        s1 += val; s2 = fmaf(val, val, s2);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&tempty[buf]);                               // accumulator buffer may be overwritten
+            if (a.stats && n_ok) { atomicAdd(a.stats + n, (double)s1); atomicAdd(a.stats + a.N + n, (double)s2); }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
     }
 }
 
@@ -474,12 +662,27 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     if (M <= 0 || N <= 0) return CRNN_OK;
     if (K % TC_BK || K <= 0) { crnn_set_error("gemm_tc: K=%d must be a positive multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
     if ((ldx % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Wimg) & 15)) { crnn_set_error("gemm_tc: X/Wimg must be 16-byte aligned, ldx %% 4 == 0"); return CRNN_ERR_INVALID; }
-    static bool configured = false;
-    if (!configured) { CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); configured = true; }
     TcArgs a; a.X = X; a.ldx = ldx; a.Wimg = Wimg; a.out = out; a.ldo = ldo; a.M = M; a.N = N; a.K = K;
     a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats; a.bias = bias; a.relu = relu; a.accumulate = accumulate;
-    dim3 grid((N + TC_BC - 1) / TC_BC, (M + TC_BP - 1) / TC_BP);
-    xw_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    static int use_v1 = -1;
+    if (use_v1 < 0) { const char* e = getenv("CRNN_GEMM_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+    const int NT = (N + TC_BC - 1) / TC_BC, MT = (M + TC_BP - 1) / TC_BP;
+    if (use_v1) {
+        static bool configured = false;
+        if (!configured) { CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); configured = true; }
+        xw_gemm_tc_kernel<<<dim3(NT, MT), TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    } else {
+        static bool configured2 = false;
+        static int num_sms = 148;
+        if (!configured2) {
+            CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            configured2 = true;
+        }
+        const long long total = (long long)NT * MT;
+        const int grid = (int)(total < num_sms ? total : num_sms);
+        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC_SMEM_BYTES, st>>>(a, NT, MT);
+    }
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -503,10 +706,10 @@ int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ld
     static bool c128 = false, c256 = false;
     if (NB == 256) {
         if (!c256) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<256>::SMEM_BYTES)); c256 = true; }
-        xty_gemm_tc_kernel<256><<<grid, TC_THREADS, DwCfg<256>::SMEM_BYTES, st>>>(a);
+        xty_gemm_tc_kernel<256><<<grid, DW_THREADS, DwCfg<256>::SMEM_BYTES, st>>>(a);
     } else {
         if (!c128) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<128>::SMEM_BYTES)); c128 = true; }
-        xty_gemm_tc_kernel<128><<<grid, TC_THREADS, DwCfg<128>::SMEM_BYTES, st>>>(a);
+        xty_gemm_tc_kernel<128><<<grid, DW_THREADS, DwCfg<128>::SMEM_BYTES, st>>>(a);
     }
     LAUNCH_CHECK();
     return CRNN_OK;
