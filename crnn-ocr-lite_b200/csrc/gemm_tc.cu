@@ -444,21 +444,32 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
 // =====================================================================================================================
 // v2 of the kernel above: PERSISTENT CTAs (one per SM) walking a static tile schedule (channel tile fastest, so the CTAs
 // that run concurrently share the activation tile in L2), with
-//   * producers (warps 0-3) that keep the NEXT k-block's global loads in flight in registers while they transform and store
-//     the current one (the ncu capture of v1 showed 1.7 long-scoreboard stalls per issue and 8 % resident warps);
+//   * producers (warps 0-3) that stream the raw fp32 activations into a 4-deep shared-memory ring with cp.async (LDGSTS: 48 KB
+//     in flight per SM, no registers) and transform ring entries into the hi/lo SWIZZLE_128B tiles (the ncu capture of v1 showed
+//     1.7 long-scoreboard stalls per issue, 8 % resident warps and 12 % DRAM throughput: far too few bytes in flight);
 //   * two TMEM accumulator buffers (2 x 128 columns) and dedicated epilogue warps (5-8), so the TMEM->HBM epilogue of tile i
 //     overlaps the MMAs of tile i+1;  barriers: full/empty per smem stage, tmem_full/tmem_empty per accumulator buffer.
 // =====================================================================================================================
 constexpr int TC2_THREADS = 288;
+constexpr int TC2_STAGES = 2;                 // {Whi, Wlo, Xhi, Xlo} compute stages
+constexpr int TC2_RAW = 4;                    // raw fp32 activation ring filled by cp.async (48 KB in flight per SM)
+constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC_STAGE_BYTES + TC2_RAW * TC_TILE_FLOATS * 4 + 1024 + 256;
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {   // src_bytes = 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NT, int MT)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* stage_base = (float*)smem;
-    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* full = bars; uint64_t* empty = bars + TC_STAGES;
-    uint64_t* tfull = bars + 2 * TC_STAGES; uint64_t* tempty = tfull + 2;
+    float* raw_base = stage_base + (size_t)TC2_STAGES * 4 * TC_TILE_FLOATS;
+    uint64_t* bars = (uint64_t*)(raw_base + (size_t)TC2_RAW * TC_TILE_FLOATS);
+    uint64_t* full = bars; uint64_t* empty = bars + TC2_STAGES;
+    uint64_t* tfull = bars + 2 * TC2_STAGES; uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     const int total = NT * MT;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -481,61 +492,73 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 
     if (warp < 4) {
         // =========================== producers ===========================
+        // Each thread owns the same 8 (row, 16-byte chunk) slots in every ring entry, so it only ever waits for ITS OWN cp.async
+        // groups: no cross-thread synchronisation between the asynchronous fill and the transform.
         const int c8 = tid & 7, r0 = tid >> 3;
-        int t = blockIdx.x, kb = 0;
-        float4 v[8], vn[8];
-        auto prefetch = [&](int tt, int kk, float4 (&dst)[8]) {
+        auto issue = [&](int tt, int kk, int slot) {     // raw[slot][r][c8*4..] <- X[m0+r][kk*32 + c8*4 ..]   (rows >= M zero-filled)
+            float* raw = raw_base + (size_t)slot * TC_TILE_FLOATS;
             const int m0 = (tt / NT) * TC_BP;
             const int k = kk * TC_BK + c8 * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int m = m0 + r0 + 16 * i;
-                dst[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int r = r0 + 16 * i, m = m0 + r;
+                const bool ok = m < a.M;
+                cp_async16(raw + r * TC_BK + c8 * 4, a.X + (size_t)(ok ? m : 0) * a.ldx + k, ok ? 16u : 0u);
             }
         };
-        if (t < total) prefetch(t, 0, v);
-        uint32_t it = 0;
-        while (t < total) {
-            int tn = t, kn = kb + 1;
-            if (kn == KB) { kn = 0; tn = t + gridDim.x; }
-            if (tn < total) prefetch(tn, kn, vn);
-            const int s = it % TC_STAGES;
-            const uint32_t ph = (it / TC_STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            float* Whi = stage_base + (size_t)s * (4 * TC_TILE_FLOATS);
-            float* Wlo = Whi + TC_TILE_FLOATS; float* Xhi = Wlo + TC_TILE_FLOATS; float* Xlo = Xhi + TC_TILE_FLOATS;
-            const int ct = t % NT, m0 = (t / NT) * TC_BP;
-            if (tid == 0) {
-                const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
-                mbar_arrive_expect_tx(&full[s], 2 * TC_TILE_FLOATS * 4);
-                bulk_g2s(Whi, src, TC_TILE_FLOATS * 4, &full[s]);
-                bulk_g2s(Wlo, src + TC_TILE_FLOATS, TC_TILE_FLOATS * 4, &full[s]);
-            }
-            const int k = kb * TC_BK + c8 * 4;
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.x_scale) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + k)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + k)); }
+        // fill the ring
+        int ft = blockIdx.x, fk = 0;                      // next (tile, k-block) to FETCH
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 16 * i;
-                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                if (a.x_scale) {
-                    x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
-                    x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
-                    if (m0 + r >= a.M) { x[0] = x[1] = x[2] = x[3] = 0.f; }
-                }
-                uint32_t hi[4]; float lo[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(x[q]); lo[q] = x[q] - __uint_as_float(hi[q]); }
-                const int off = (r >> 3) * 256 + (r & 7) * 32 + ((c8 ^ (r & 7)) << 2);
-                *reinterpret_cast<uint4*>(Xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(Xlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full[s]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = vn[i];
-            t = tn; kb = kn; ++it;
+        for (int d = 0; d < TC2_RAW; ++d) {
+            if (ft < total) { issue(ft, fk, d); if (++fk == KB) { fk = 0; ft += gridDim.x; } }
+            cp_async_commit();                            // (possibly empty) group keeps the group count uniform
         }
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int ct = t % NT, m0 = (t / NT) * TC_BP;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % TC2_STAGES;
+                const uint32_t ph = (it / TC2_STAGES) & 1;
+                const int slot = it % TC2_RAW;
+                cp_async_wait<TC2_RAW - 1>();             // this thread's chunks of ring entry `slot` have landed
+                mbar_wait(&empty[s], ph ^ 1);
+                float* Whi = stage_base + (size_t)s * (4 * TC_TILE_FLOATS);
+                float* Wlo = Whi + TC_TILE_FLOATS; float* Xhi = Wlo + TC_TILE_FLOATS; float* Xlo = Xhi + TC_TILE_FLOATS;
+                if (tid == 0) {
+                    const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
+                    mbar_arrive_expect_tx(&full[s], 2 * TC_TILE_FLOATS * 4);
+                    bulk_g2s(Whi, src, TC_TILE_FLOATS * 4, &full[s]);
+                    bulk_g2s(Wlo, src + TC_TILE_FLOATS, TC_TILE_FLOATS * 4, &full[s]);
+                }
+                const float* raw = raw_base + (size_t)slot * TC_TILE_FLOATS;
+                const int k = kb * TC_BK + c8 * 4;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.x_scale) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + k)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + k)); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + 16 * i;
+                    const float4 v = *reinterpret_cast<const float4*>(raw + r * TC_BK + c8 * 4);
+                    float x[4] = {v.x, v.y, v.z, v.w};
+                    if (a.x_scale) {
+                        x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
+                        x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
+                        if (m0 + r >= a.M) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                    }
+                    uint32_t hi[4]; float lo[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(x[q]); lo[q] = x[q] - __uint_as_float(hi[q]); }
+                    const int off = (r >> 3) * 256 + (r & 7) * 32 + ((c8 ^ (r & 7)) << 2);
+                    *reinterpret_cast<uint4*>(Xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(Xlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full[s]);
+                // refill the ring entry just consumed
+                if (ft < total) { issue(ft, fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; } }
+                cp_async_commit();
+            }
+        }
+        cp_async_wait<0>();
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         uint32_t it = 0;
@@ -546,8 +569,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(buf * TC_BP);
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (it / TC_STAGES) & 1;
+                const int s = it % TC2_STAGES;
+                const uint32_t ph = (it / TC2_STAGES) & 1;
                 mbar_wait(&full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
@@ -675,13 +698,13 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
         static bool configured2 = false;
         static int num_sms = 148;
         if (!configured2) {
-            CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
             int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
             configured2 = true;
         }
         const long long total = (long long)NT * MT;
         const int grid = (int)(total < num_sms ? total : num_sms);
-        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC_SMEM_BYTES, st>>>(a, NT, MT);
+        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, NT, MT);
     }
     LAUNCH_CHECK();
     return CRNN_OK;

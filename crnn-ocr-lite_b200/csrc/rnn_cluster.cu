@@ -130,15 +130,17 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         for (int ks = 0; ks < 16; ++ks) ah += part[(ks * 32 + eu) * RB + er];
         const float hh = tanhf(xh + ah);
         const float hn = z * hown + (1.f - z) * hh;
+#pragma unroll
+        for (int c = 0; c < NCTA; ++c) cluster.map_shared_rank(hnxt, c)[j * RB + er] = hn;
+        xz = nxz; xr = nxr; xh = nxh;
+        cluster.sync();
+        // global stores AFTER the barrier: barrier.cluster.arrive.release fences all earlier memory operations, so stores issued
+        // just before it put a full HBM round trip on the critical path of every step (ncu: 1.7 membar stalls per issue)
         if (valid) {
             const size_t o = ((size_t)b * T + t) * 2 + dir;
             hs[o * U + j] = hn;
             if (gates) { float* g = gates + o * (3 * U); g[j] = z; g[U + j] = r; g[2 * U + j] = hh; }
         }
-#pragma unroll
-        for (int c = 0; c < NCTA; ++c) cluster.map_shared_rank(hnxt, c)[j * RB + er] = hn;
-        xz = nxz; xr = nxr; xh = nxh;
-        cluster.sync();
         cur ^= 1;
     }
 }
@@ -264,13 +266,13 @@ gru_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__
                 push_tile(acc, half, dst, rg, kq, u0);
             }
         }
-        if (valid) {
+        cluster.sync();
+        if (valid) {   // after the barrier (see the forward kernel): keeps the HBM stores off the release fence
             float* d = dxp + o * (3 * U);
             d[j] = da_z; d[U + j] = da_r; d[2 * U + j] = da_h;
             hprev_out[o * U + j] = hp;
             rh_out[o * U + j] = r * hp;
         }
-        cluster.sync();
 #pragma unroll
         for (int c = 0; c < NCTA; ++c) dhn += recvB[(c * UPC + eu) * RB + er];
         dh = dhn;
