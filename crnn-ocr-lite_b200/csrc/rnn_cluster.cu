@@ -34,6 +34,18 @@ __device__ __forceinline__ void fma44(float (&acc)[4][4], const float4 a, const 
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
 }
 
+// Broadcast one value per (unit, row) to the same offset of `buf` in all 8 CTAs.  Rows are the fastest index (er = lane & 7), so the
+// lanes with er % 4 == 0 gather their 4-row group with shuffles and issue ONE 16-byte st.shared::cluster per destination
+// (512 instead of 2048 remote stores per exchange and CTA).
+__device__ __forceinline__ void push4(cg::cluster_group& cluster, float* buf, int off, float v, int er) {
+    const float v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2), v3 = __shfl_down_sync(0xffffffffu, v, 3);
+    if ((er & 3) == 0) {
+        const float4 q = make_float4(v, v1, v2, v3);
+#pragma unroll
+        for (int c = 0; c < NCTA; ++c) *reinterpret_cast<float4*>(cluster.map_shared_rank(buf, c) + off) = q;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------- forward
 // smem: Us[256][96] | hT[2][256][8] | rhT[256][8] | part[4096]
 constexpr int FWD_SMEM_FLOATS = U * GC + 2 * U * RB + U * RB + 4096;
@@ -109,8 +121,7 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         const float z = hard_sigmoid(xz + az);
         const float r = hard_sigmoid(xr + ar);
         const float rh = r * hown;
-#pragma unroll
-        for (int c = 0; c < NCTA; ++c) cluster.map_shared_rank(rhT, c)[j * RB + er] = rh;
+        push4(cluster, rhT, j * RB + er, rh, er);
         cluster.sync();
         // ---- phase B: candidate pre-activation: part[ks][col 0..31][row]
         {
@@ -130,8 +141,7 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         for (int ks = 0; ks < 16; ++ks) ah += part[(ks * 32 + eu) * RB + er];
         const float hh = tanhf(xh + ah);
         const float hn = z * hown + (1.f - z) * hh;
-#pragma unroll
-        for (int c = 0; c < NCTA; ++c) cluster.map_shared_rank(hnxt, c)[j * RB + er] = hn;
+        push4(cluster, hnxt, j * RB + er, hn, er);
         xz = nxz; xr = nxr; xh = nxh;
         cluster.sync();
         // global stores AFTER the barrier: barrier.cluster.arrive.release fences all earlier memory operations, so stores issued
