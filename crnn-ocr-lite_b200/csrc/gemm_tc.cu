@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
 //   * two TMEM accumulator buffers (2 x 128 columns) and dedicated epilogue warps (5-8), so the TMEM->HBM epilogue of tile i
 //     overlaps the MMAs of tile i+1;  barriers: full/empty per smem stage, tmem_full/tmem_empty per accumulator buffer.
 // =====================================================================================================================
-constexpr int TC2_THREADS = 288;
+constexpr int TC2_THREADS = 416;                // 4 producer warps + 1 MMA warp + 8 epilogue warps
 constexpr int TC2_STAGES = 2;                 // {Whi, Wlo, Xhi, Xlo} compute stages
 constexpr int TC2_RAW = 4;                    // raw fp32 activation ring filled by cp.async (48 KB in flight per SM)
 constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC_STAGE_BYTES + TC2_RAW * TC_TILE_FLOATS * 4 + 1024 + 256;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 
     if (tid == 0) {
         for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -590,8 +590,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             }
         }
     } else {
-        // =========================== epilogue warps 5..8 ===========================
+        // =========================== epilogue warps 5..12 ===========================
+        // Two warps per TMEM lane quarter, each draining half of the 128 pixel columns.  (ncu on the 4-warp version: ~47 % of all
+        // stall samples in this loop and the MMA warp waiting on tmem_empty -> the epilogue, not the tensor core, paced the tile.)
         const int q = warp & 3;                                     // TMEM lane quarter this warp may access
+        const int half = (warp - 5) >> 2;                           // 0: columns 0..63, 1: columns 64..127
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
             const int buf = j & 1;
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_BP; c0 += 32) {
+            for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BP + c0);
                 asm volatile(
@@ -616,16 +619,26 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float* dst = a.out + (size_t)(m0 + c0) * a.ldo + n;     // 32 lanes = 32 consecutive channels: 128-byte coalesced rows
+                if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast path: full 32-pixel chunk, no per-element predicate
 #pragma unroll
-                for (int p = 0; p < 32; ++p) {
-                    const int m = m0 + c0 + p;
-                    if (m < a.M && n_ok) {
+                    for (int p = 0; p < 32; ++p) {
                         float val = __uint_as_float(r[p]) + bias;
                         if (a.relu) val = fmaxf(val, 0.f);
-                        float* dst = a.out + (size_t)m * a.ldo + n;
-                        if (a.accumulate) val += *dst;
-                        *dst = val;
+                        *dst = val; dst += a.ldo;
                         s1 += val; s2 = fmaf(val, val, s2);
+                    }
+                } else if (n_ok) {
+#pragma unroll
+                    for (int p = 0; p < 32; ++p) {
+                        if (m0 + c0 + p < a.M) {
+                            float val = __uint_as_float(r[p]) + bias;
+                            if (a.relu) val = fmaxf(val, 0.f);
+                            if (a.accumulate) val += *dst;
+                            *dst = val;
+                            s1 += val; s2 = fmaf(val, val, s2);
+                        }
+                        dst += a.ldo;
                     }
                 }
             }
