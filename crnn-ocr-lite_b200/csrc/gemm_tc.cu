@@ -450,10 +450,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
 //   * two TMEM accumulator buffers (2 x 128 columns) and dedicated epilogue warps (5-8), so the TMEM->HBM epilogue of tile i
 //     overlaps the MMAs of tile i+1;  barriers: full/empty per smem stage, tmem_full/tmem_empty per accumulator buffer.
 // =====================================================================================================================
-constexpr int TC2_THREADS = 416;                // 4 producer warps + 1 MMA warp + 8 epilogue warps
-constexpr int TC2_STAGES = 2;                 // {Whi, Wlo, Xhi, Xlo} compute stages
-constexpr int TC2_RAW = 4;                    // raw fp32 activation ring filled by cp.async (48 KB in flight per SM)
-constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC_STAGE_BYTES + TC2_RAW * TC_TILE_FLOATS * 4 + 1024 + 256;
+constexpr int TC2_THREADS = 448;                // 4 activation-producer warps + MMA warp + 8 epilogue warps + weight-loader warp
+constexpr int TC2_XSTAGES = 2;                  // {Xhi, Xlo} tiles consumed by the tensor core
+constexpr int TC2_WRING = 3;                    // {Whi, Wlo} weight tiles, streamed by the loader warp ahead of the MMA
+constexpr int TC2_RAW = 3;                      // raw fp32 activation ring filled by cp.async
+constexpr int TC2_SMEM_BYTES = (TC2_WRING * 2 + TC2_XSTAGES * 2 + TC2_RAW) * TC_TILE_FLOATS * 4 + 1024 + 256;
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {   // src_bytes = 0 -> zero fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
@@ -465,11 +466,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float* stage_base = (float*)smem;
-    float* raw_base = stage_base + (size_t)TC2_STAGES * 4 * TC_TILE_FLOATS;
+    float* w_base = (float*)smem;                                               // [WRING][Whi | Wlo]
+    float* x_base = w_base + (size_t)TC2_WRING * 2 * TC_TILE_FLOATS;            // [XSTAGES][Xhi | Xlo]
+    float* raw_base = x_base + (size_t)TC2_XSTAGES * 2 * TC_TILE_FLOATS;        // [RAW][128 x 32 fp32]
     uint64_t* bars = (uint64_t*)(raw_base + (size_t)TC2_RAW * TC_TILE_FLOATS);
-    uint64_t* full = bars; uint64_t* empty = bars + TC2_STAGES;
-    uint64_t* tfull = bars + 2 * TC2_STAGES; uint64_t* tempty = tfull + 2;
+    uint64_t* wfull = bars; uint64_t* wempty = wfull + TC2_WRING;
+    uint64_t* xfull = wempty + TC2_WRING; uint64_t* xempty = xfull + TC2_XSTAGES;
+    uint64_t* tfull = xempty + TC2_XSTAGES; uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -477,7 +480,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     const int total = NT * MT;
 
     if (tid == 0) {
-        for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TC2_WRING; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < TC2_XSTAGES; ++s) { mbar_init(&xfull[s], 128); mbar_init(&xempty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -491,7 +495,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // =========================== producers ===========================
+        // =========================== activation producers ===========================
         // Each thread owns the same 8 (row, 16-byte chunk) slots in every ring entry, so it only ever waits for ITS OWN cp.async
         // groups: no cross-thread synchronisation between the asynchronous fill and the transform.
         const int c8 = tid & 7, r0 = tid >> 3;
@@ -506,7 +510,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 cp_async16(raw + r * TC_BK + c8 * 4, a.X + (size_t)(ok ? m : 0) * a.ldx + k, ok ? 16u : 0u);
             }
         };
-        // fill the ring
         int ft = blockIdx.x, fk = 0;                      // next (tile, k-block) to FETCH
 #pragma unroll
         for (int d = 0; d < TC2_RAW; ++d) {
@@ -515,21 +518,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         }
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int ct = t % NT, m0 = (t / NT) * TC_BP;
+            const int m0 = (t / NT) * TC_BP;
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it % TC2_STAGES;
-                const uint32_t ph = (it / TC2_STAGES) & 1;
+                const int s = it % TC2_XSTAGES;
+                const uint32_t ph = (it / TC2_XSTAGES) & 1;
                 const int slot = it % TC2_RAW;
                 cp_async_wait<TC2_RAW - 1>();             // this thread's chunks of ring entry `slot` have landed
-                mbar_wait(&empty[s], ph ^ 1);
-                float* Whi = stage_base + (size_t)s * (4 * TC_TILE_FLOATS);
-                float* Wlo = Whi + TC_TILE_FLOATS; float* Xhi = Wlo + TC_TILE_FLOATS; float* Xlo = Xhi + TC_TILE_FLOATS;
-                if (tid == 0) {
-                    const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
-                    mbar_arrive_expect_tx(&full[s], 2 * TC_TILE_FLOATS * 4);
-                    bulk_g2s(Whi, src, TC_TILE_FLOATS * 4, &full[s]);
-                    bulk_g2s(Wlo, src + TC_TILE_FLOATS, TC_TILE_FLOATS * 4, &full[s]);
-                }
+                mbar_wait(&xempty[s], ph ^ 1);
+                float* Xhi = x_base + (size_t)s * (2 * TC_TILE_FLOATS);
+                float* Xlo = Xhi + TC_TILE_FLOATS;
                 const float* raw = raw_base + (size_t)slot * TC_TILE_FLOATS;
                 const int k = kb * TC_BK + c8 * 4;
                 float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -552,13 +549,28 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     *reinterpret_cast<float4*>(Xlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&full[s]);
-                // refill the ring entry just consumed
-                if (ft < total) { issue(ft, fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; } }
+                mbar_arrive(&xfull[s]);
+                if (ft < total) { issue(ft, fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; } }   // refill the ring entry just consumed
                 cp_async_commit();
             }
         }
         cp_async_wait<0>();
+    } else if (warp == 13) {
+        // =========================== weight loader: one thread streams the pre-swizzled hi/lo images (TMA bulk copies) ===========================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int ct = t % NT;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int ws = it % TC2_WRING;
+                    mbar_wait(&wempty[ws], ((it / TC2_WRING) & 1) ^ 1);
+                    float* Whi = w_base + (size_t)ws * (2 * TC_TILE_FLOATS);
+                    const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
+                    mbar_arrive_expect_tx(&wfull[ws], 2 * TC_TILE_FLOATS * 4);
+                    bulk_g2s(Whi, src, 2 * TC_TILE_FLOATS * 4, &wfull[ws]);      // hi and lo images are contiguous: one 32 KB copy
+                }
+            }
+        }
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         uint32_t it = 0;
@@ -569,13 +581,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(buf * TC_BP);
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it % TC2_STAGES;
-                const uint32_t ph = (it / TC2_STAGES) & 1;
-                mbar_wait(&full[s], ph);
+                const int xs = it % TC2_XSTAGES, ws = it % TC2_WRING;
+                mbar_wait(&wfull[ws], (it / TC2_WRING) & 1);
+                mbar_wait(&xfull[xs], (it / TC2_XSTAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t whi = smem_u32(stage_base + (size_t)s * (4 * TC_TILE_FLOATS));
-                    const uint32_t wlo = whi + TC_TILE_FLOATS * 4, xhi = wlo + TC_TILE_FLOATS * 4, xlo = xhi + TC_TILE_FLOATS * 4;
+                    const uint32_t whi = smem_u32(w_base + (size_t)ws * (2 * TC_TILE_FLOATS)), wlo = whi + TC_TILE_FLOATS * 4;
+                    const uint32_t xhi = smem_u32(x_base + (size_t)xs * (2 * TC_TILE_FLOATS)), xlo = xhi + TC_TILE_FLOATS * 4;
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
                         const uint32_t o = ks * 32;
@@ -583,7 +595,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                         umma_tf32(tacc, umma_desc(whi + o), umma_desc(xlo + o), 1u);
                         umma_tf32(tacc, umma_desc(whi + o), umma_desc(xhi + o), 1u);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&xempty[xs]);
+                    umma_commit(&wempty[ws]);
                     if (kb == KB - 1) umma_commit(&tfull[buf]);
                 }
                 __syncwarp();

@@ -34,6 +34,42 @@ __device__ __forceinline__ void fma44(float (&acc)[4][4], const float4 a, const 
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+// 16-byte remote store that also signals the DESTINATION CTA's mbarrier (complete_tx of 16 bytes): data + flag in one operation,
+// so the per-step exchange needs no cluster-wide barrier / release fence (ncu: ERRBAR + UCGABAR were ~25 % of the stall samples).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count)); }
+__device__ __forceinline__ void bar_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {   // bounded: a protocol bug traps instead of hanging the GPU
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+constexpr uint32_t XCHG_BYTES = NCTA * UPC * RB * 4;   // bytes every CTA receives per exchange (8 KB)
+
+// Broadcast one value per (unit, row) to the same offset of `buf` in all 8 CTAs, signalling each destination's barrier.
+__device__ __forceinline__ void push4_async(float* buf, uint64_t* bar, int off, float v, int er) {
+    const float v1 = __shfl_down_sync(0xffffffffu, v, 1), v2 = __shfl_down_sync(0xffffffffu, v, 2), v3 = __shfl_down_sync(0xffffffffu, v, 3);
+    if ((er & 3) == 0) {
+        const float4 q = make_float4(v, v1, v2, v3);
+        const uint32_t a = smem_addr(buf + off), b = smem_addr(bar);
+#pragma unroll
+        for (int c = 0; c < NCTA; ++c) st_async_v4(map_rank(a, c), q, map_rank(b, c));
+    }
+}
+
 // Broadcast one value per (unit, row) to the same offset of `buf` in all 8 CTAs.  Rows are the fastest index (er = lane & 7), so the
 // lanes with er % 4 == 0 gather their 4-row group with shuffles and issue ONE 16-byte st.shared::cluster per destination
 // (512 instead of 2048 remote stores per exchange and CTA).
@@ -48,7 +84,7 @@ __device__ __forceinline__ void push4(cg::cluster_group& cluster, float* buf, in
 
 // ------------------------------------------------------------------------------------------------- forward
 // smem: Us[256][96] | hT[2][256][8] | rhT[256][8] | part[4096]
-constexpr int FWD_SMEM_FLOATS = U * GC + 2 * U * RB + U * RB + 4096;
+constexpr int FWD_SMEM_FLOATS = U * GC + 2 * U * RB + 2 * U * RB + 4096 + 16;   // + 4 mbarriers
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(256, 1)
 gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U0, const float* __restrict__ U1,
@@ -57,8 +93,10 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
     extern __shared__ __align__(16) float sm[];
     float* Us = sm;
     float* hT = Us + U * GC;
-    float* rhT = hT + 2 * U * RB;
-    float* part = rhT + U * RB;
+    float* rhT = hT + 2 * U * RB;                  // [2][256][8]
+    float* part = rhT + 2 * U * RB;
+    uint64_t* barR = reinterpret_cast<uint64_t*>(part + 4096);   // [2] r*h exchange of step s -> barR[s&1]
+    uint64_t* barH = barR + 2;                                    // [2] h   exchange of step s -> barH[s&1]
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int dir = blockIdx.y, b0 = (blockIdx.x / NCTA) * RB;
@@ -70,8 +108,12 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         Us[i] = __ldg(Um + (size_t)k * (3 * U) + g * U + crank * UPC + u);
     }
     for (int i = tid; i < 2 * U * RB; i += 256) hT[i] = 0.f;
+    if (tid == 0) {
+        bar_init(&barR[0], 1); bar_init(&barR[1], 1); bar_init(&barH[0], 1); bar_init(&barH[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    cluster.sync();
+    cluster.sync();                                  // every CTA's barriers and buffers exist before the first remote store
 
     // epilogue identity: row er (fastest) x unit eu  -> consecutive threads write consecutive floats of hT[unit][row]
     const int er = tid & 7, eu = tid >> 3;
@@ -84,23 +126,29 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
     const int a_rt = lane >> 4, a_ct = lane & 15;            // phase A: warp = k-slice (32 k), 2 row-tiles x 16 col-tiles
     const int b_ks = tid >> 4, b_rt = (tid >> 3) & 1, b_ct = tid & 7;   // phase B: 16 k-slices (16 k), 2 x 8 tiles
 
-    int cur = 0;
     float xz, xr, xh;
     {
         const int t0 = dir ? T - 1 : 0;
         const float* x = xp + (((size_t)bb * T + t0) * 2 + dir) * (3 * U);
         xz = x[j]; xr = x[U + j]; xh = x[2 * U + j];
     }
+    // Per step: h_{t-1} lives in hT[s&1]; r*h goes through rhT[s&1]; h_t is written into hT[(s+1)&1] of every CTA.
+    // Exchanges are st.async (data + complete_tx on the destination's mbarrier); the double buffers are protected by the data
+    // dependencies themselves (a CTA can only run one exchange ahead of the slowest CTA of its cluster).
     for (int s = 0; s < T; ++s) {
         const int t = dir ? T - 1 - s : s;
+        const int cur = s & 1;
+        const uint32_t ph = (s >> 1) & 1;
         const float* hcur = hT + cur * (U * RB);
         float* hnxt = hT + (cur ^ 1) * (U * RB);
+        float* rhc = rhT + cur * (U * RB);
         float nxz = 0.f, nxr = 0.f, nxh = 0.f;             // next step's projections: issued now, consumed one step later
         if (s + 1 < T) {
             const int tn = dir ? T - 2 - s : s + 1;
             const float* x = xp + (((size_t)bb * T + tn) * 2 + dir) * (3 * U);
             nxz = __ldg(x + j); nxr = __ldg(x + U + j); nxh = __ldg(x + 2 * U + j);
         }
+        if (s > 0) bar_wait(&barH[(s - 1) & 1], ((s - 1) >> 1) & 1);      // h_{t-1} of all 256 units has landed
         // ---- phase A: z,r pre-activations of the own 32 units: part[ks][col 0..63][row 0..7]
         {
             float acc[4][4] = {};
@@ -120,13 +168,14 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         const float hown = hcur[j * RB + er];
         const float z = hard_sigmoid(xz + az);
         const float r = hard_sigmoid(xr + ar);
-        const float rh = r * hown;
-        push4(cluster, rhT, j * RB + er, rh, er);
-        cluster.sync();
+        if (tid == 0) bar_expect(&barR[cur], XCHG_BYTES);
+        push4_async(rhc, &barR[cur], j * RB + er, r * hown, er);
+        bar_wait(&barR[cur], ph);
+        __syncthreads();                                    // everybody is done with `part` (phase A partials)
         // ---- phase B: candidate pre-activation: part[ks][col 0..31][row]
         {
             float acc[4][4] = {};
-            const float* hp = rhT + (b_ks * 16) * RB + b_rt * 4;
+            const float* hp = rhc + (b_ks * 16) * RB + b_rt * 4;
             const float* up = Us + (b_ks * 16) * GC + 2 * UPC + b_ct * 4;
 #pragma unroll 8
             for (int kk = 0; kk < 16; ++kk)
@@ -141,18 +190,18 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
         for (int ks = 0; ks < 16; ++ks) ah += part[(ks * 32 + eu) * RB + er];
         const float hh = tanhf(xh + ah);
         const float hn = z * hown + (1.f - z) * hh;
-        push4(cluster, hnxt, j * RB + er, hn, er);
-        xz = nxz; xr = nxr; xh = nxh;
-        cluster.sync();
-        // global stores AFTER the barrier: barrier.cluster.arrive.release fences all earlier memory operations, so stores issued
-        // just before it put a full HBM round trip on the critical path of every step (ncu: 1.7 membar stalls per issue)
+        if (tid == 0) bar_expect(&barH[cur], XCHG_BYTES);
+        push4_async(hnxt, &barH[cur], j * RB + er, hn, er);
         if (valid) {
             const size_t o = ((size_t)b * T + t) * 2 + dir;
             hs[o * U + j] = hn;
             if (gates) { float* g = gates + o * (3 * U); g[j] = z; g[U + j] = r; g[2 * U + j] = hh; }
         }
-        cur ^= 1;
+        xz = nxz; xr = nxr; xh = nxh;
+        __syncthreads();                                    // `part` (phase B partials) free for the next step
     }
+    bar_wait(&barH[(T - 1) & 1], ((T - 1) >> 1) & 1);       // drain: all stores targeting this CTA have landed
+    cluster.sync();                                         // nobody exits while a peer may still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------- backward (BPTT)
