@@ -46,10 +46,11 @@ __global__ void __launch_bounds__(256) dwconv3x3_vec4_w4(const float* __restrict
                                                          int B, int H, int W, int C4, int WG, long long total)
 {
     const int C = C4 * 4;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        int c4 = (int)(idx % C4); long long r = idx / C4;
-        int wg = (int)(r % WG); r /= WG;
-        int h = (int)(r % H); int b = (int)(r / H);
+    const int total32 = (int)total;                 // < 2^31 (checked by the launcher)
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += gridDim.x * blockDim.x) {
+        const int c4 = idx % C4; int r = idx / C4;
+        const int wg = r % WG; r /= WG;
+        const int h = r % H; const int b = r / H;
         const int w0 = wg * 4;
         float4 kv[9];
 #pragma unroll
@@ -114,9 +115,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_weight_vec4(const float* __
     for (int q = 0; q < 9; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c4 < C4) {
         // one iteration = 4 consecutive pixels of a row: 18 x loads + 4 dy loads feed 36 float4 FMAs
-        for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < ngroups; p += (long long)gridDim.y * PY) {
-            int wg = (int)(p % WG); long long r = p / WG;
-            int h = (int)(r % H); int b = (int)(r / H);
+        const int ng32 = (int)ngroups, pstride = gridDim.y * PY;
+        for (int p = blockIdx.y * PY + threadIdx.y; p < ng32; p += pstride) {
+            const int wg = p % WG; const int r = p / WG;
+            const int h = r % H; const int b = r / H;
             const int w0 = wg * 4;
             float4 g[4];
 #pragma unroll
@@ -249,10 +251,11 @@ __global__ void act_pool_fwd_kernel(const float* __restrict__ y, const float* __
                                     float rate, float inv_keep, uint64_t seed, uint32_t layer, long long total)
 {
     const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        int c4 = (int)(idx % C4); long long r = idx / C4;
-        int wo = (int)(r % Wo); r /= Wo;
-        int ho = (int)(r % Ho); int b = (int)(r / Ho);
+    const int total32 = (int)total;                 // < 2^31 (checked by the launcher)
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += gridDim.x * blockDim.x) {
+        const int c4 = idx % C4; int r = idx / C4;
+        const int wo = r % Wo; r /= Wo;
+        const int ho = r % Ho; const int b = r / Ho;
         float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         for (int i = 0; i < ph; ++i)
@@ -262,8 +265,8 @@ __global__ void act_pool_fwd_kernel(const float* __restrict__ y, const float* __
                 m.z = fmaxf(m.z, relu6f(fmaf(v.z, sc.z, sh.z))); m.w = fmaxf(m.w, relu6f(fmaf(v.w, sc.w, sh.w)));
             }
         if (rate > 0.f) {
-            m.x *= crnn_dropout_mask(seed, layer, idx * 4 + 0, rate, inv_keep); m.y *= crnn_dropout_mask(seed, layer, idx * 4 + 1, rate, inv_keep);
-            m.z *= crnn_dropout_mask(seed, layer, idx * 4 + 2, rate, inv_keep); m.w *= crnn_dropout_mask(seed, layer, idx * 4 + 3, rate, inv_keep);
+            m.x *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 0, rate, inv_keep); m.y *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 1, rate, inv_keep);
+            m.z *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 2, rate, inv_keep); m.w *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 3, rate, inv_keep);
         }
         *reinterpret_cast<float4*>(a + (size_t)idx * 4) = m;
     }
@@ -278,12 +281,13 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
                                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, float* __restrict__ dy, double* __restrict__ red,
                                     int B, int H, int W, int C4, double invM,
-                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix)
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix_ll)
 {
     extern __shared__ float sred[];   // [PY][8][CQ]
+    constexpr int ph = PH, pw = PW, NW = PH * PW;
     const int CQ = blockDim.x, PY = blockDim.y;
-    constexpr int ph = PH, pw = PW;
     const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
+    const int npix = (int)npix_ll;                  // < 2^31 (checked by the launcher): 32-bit index arithmetic
     const int c4 = blockIdx.x * CQ + threadIdx.x;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     if (c4 < C4) {
@@ -299,48 +303,60 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
                 m1[q] = (float)(red[c4 * 4 + q] * invM); m2[q] = (float)(red[C + c4 * 4 + q] * invM);
             }
         }
+        const int pstride = gridDim.y * PY;
 #pragma unroll 2
-        for (long long p = blockIdx.y * (long long)PY + threadIdx.y; p < npix; p += (long long)gridDim.y * PY) {
-            int wo = (int)(p % Wo); long long r = p / Wo;
-            int ho = (int)(r % Ho); int b = (int)(r / Ho);
-            const long long oidx = p * C4 + c4;
+        for (int p = blockIdx.y * PY + threadIdx.y; p < npix; p += pstride) {
+            const int wo = p % Wo; const int r = p / Wo;
+            const int ho = r % Ho; const int b = r / Ho;
+            const size_t oidx = (size_t)p * C4 + c4;
             float g[4];
-            { float4 t = ldg4(da + (size_t)oidx * 4); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+            { float4 t = ldg4(da + oidx * 4); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
             if (rate > 0.f)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) g[q] *= crnn_dropout_mask(seed, layer, oidx * 4 + q, rate, inv_keep);
-            float yv[PH * PW][4], best[4]; int arg[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { best[q] = -INFINITY; arg[q] = 0; }
-#pragma unroll
-            for (int i = 0; i < ph; ++i)
-#pragma unroll
-                for (int j = 0; j < pw; ++j) {
-                    const int n = i * pw + j;
-                    float4 t = ldg4(y + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4);
-                    yv[n][0] = t.x; yv[n][1] = t.y; yv[n][2] = t.z; yv[n][3] = t.w;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float aq = relu6f(fmaf(yv[n][q], sc[q], sh[q]));
-                        if (aq > best[q]) { best[q] = aq; arg[q] = n; }   // first max wins (TF / torch max-pool grad)
-                    }
-                }
+            const size_t base = (((size_t)b * H + ho * ph) * W + wo * pw) * C + c4 * 4;
+            float yv[NW][4];
 #pragma unroll
             for (int i = 0; i < ph; ++i)
 #pragma unroll
                 for (int j = 0; j < pw; ++j) {
-                    const int n = i * pw + j;
-                    float o[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float z = fmaf(yv[n][q], sc[q], sh[q]);
-                        const float d = (arg[q] == n && z >= 0.f && z <= 6.f) ? g[q] : 0.f;
-                        const float xh = (yv[n][q] - mu[q]) * is[q];
-                        if (APPLY) o[q] = gs[q] * (d - m1[q] - xh * m2[q]);
-                        else { s1[q] += d; s2[q] = fmaf(d, xh, s2[q]); }
-                    }
-                    if (APPLY) *reinterpret_cast<float4*>(dy + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    const float4 t = ldg4(y + base + ((size_t)i * W + j) * C);
+                    yv[i * pw + j][0] = t.x; yv[i * pw + j][1] = t.y; yv[i * pw + j][2] = t.z; yv[i * pw + j][3] = t.w;
                 }
+            // arg-max of relu6(z) over the window (first max wins, like TF / torch max-pool grad); only that element gets gradient
+            float dq[4], xq[4]; int arg[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float best = -INFINITY, zb = 0.f, yb = 0.f; int ab = 0;
+#pragma unroll
+                for (int n = 0; n < NW; ++n) {
+                    const float z = fmaf(yv[n][q], sc[q], sh[q]);
+                    const float aq = relu6f(z);
+                    if (aq > best) { best = aq; zb = z; yb = yv[n][q]; ab = n; }
+                }
+                arg[q] = ab;
+                dq[q] = (zb >= 0.f && zb <= 6.f) ? g[q] : 0.f;
+                xq[q] = (yb - mu[q]) * is[q];
+            }
+            if (!APPLY) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { s1[q] += dq[q]; s2[q] = fmaf(dq[q], xq[q], s2[q]); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < ph; ++i)
+#pragma unroll
+                    for (int j = 0; j < pw; ++j) {
+                        const int n = i * pw + j;
+                        float o[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float xh = (yv[n][q] - mu[q]) * is[q];
+                            const float d = (arg[q] == n) ? dq[q] : 0.f;
+                            o[q] = gs[q] * (d - m1[q] - xh * m2[q]);
+                        }
+                        *reinterpret_cast<float4*>(dy + base + ((size_t)i * W + j) * C) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+            }
         }
     }
     if (APPLY) return;
@@ -550,6 +566,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
     for (int i = threadIdx.y; i < 32; i += blockDim.y) { int cc = c0 + i; if (r < R && cc < C) out[(size_t)cc * R + r] = tile[threadIdx.x][i]; }
 }
 
+inline bool too_big(long long n) { if (n >= (1ll << 31)) { crnn_set_error("tensor too large for 32-bit indexing (%lld elements)", n); return true; } return false; }
 inline int grid1d(long long total, int threads, int max_blocks = 148 * 16) {
     long long b = (total + threads - 1) / threads;
     if (b > max_blocks) b = max_blocks;
@@ -571,6 +588,7 @@ inline void chan_block(int C, long long M, dim3& grid, dim3& block) {
 }  // namespace
 
 int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st) {
+    if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     if (C % 4 == 0) { const int WG = (W + 3) / 4; long long total = (long long)B * H * WG * (C / 4); dwconv3x3_vec4_w4<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, C / 4, WG, total); }
     else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
@@ -578,6 +596,7 @@ int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, in
 }
 int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
     if (accumulate) { crnn_set_error("dwconv_bwd_data: accumulate unsupported"); return CRNN_ERR_INVALID; }
+    if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     if (C % 4 == 0) { const int WG = (W + 3) / 4; long long total = (long long)B * H * WG * (C / 4); dwconv3x3_vec4_w4<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, C / 4, WG, total); }
     else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
@@ -609,6 +628,7 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
                         float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     long long total = (long long)B * (H / ph) * (W / pw) * (C / 4);
+    if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     act_pool_fwd_kernel<<<grid1d(total, 256), 256, 0, st>>>(y, scale, shift, a, B, H, W, C / 4, ph, pw, rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, total);
     LAUNCH_CHECK(); return CRNN_OK;
 }
@@ -618,6 +638,7 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
                            int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
+    if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     const double invM = 1.0 / ((double)B * H * W);
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
