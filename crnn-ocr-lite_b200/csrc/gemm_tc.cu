@@ -444,23 +444,39 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
 // =====================================================================================================================
 // v2 of the kernel above: PERSISTENT CTAs (one per SM) walking a static tile schedule (channel tile fastest, so the CTAs
 // that run concurrently share the activation tile in L2), with
-//   * producers (warps 0-3) that stream the raw fp32 activations into a 4-deep shared-memory ring with cp.async (LDGSTS: 48 KB
+//   * producers (warps 0-7) that stream the raw fp32 activations into a 3-deep shared-memory ring with cp.async (LDGSTS: 48 KB
 //     in flight per SM, no registers) and transform ring entries into the hi/lo SWIZZLE_128B tiles (the ncu capture of v1 showed
 //     1.7 long-scoreboard stalls per issue, 8 % resident warps and 12 % DRAM throughput: far too few bytes in flight);
-//   * two TMEM accumulator buffers (2 x 128 columns) and dedicated epilogue warps (5-8), so the TMEM->HBM epilogue of tile i
+//   * two TMEM accumulator buffers (2 x 128 columns) and dedicated epilogue warps (9-16), so the TMEM->HBM epilogue of tile i
 //     overlaps the MMAs of tile i+1;  barriers: full/empty per smem stage, tmem_full/tmem_empty per accumulator buffer.
 // =====================================================================================================================
-constexpr int TC2_THREADS = 448;                // 4 activation-producer warps + MMA warp + 8 epilogue warps + weight-loader warp
+constexpr int TC2_PROD_WARPS = 8;                // activation-producer warps 0..7
+constexpr int TC2_MMA_WARP = TC2_PROD_WARPS;     // warp 8 issues the MMAs (and owns the TMEM allocation)
+constexpr int TC2_EPI_WARP0 = TC2_MMA_WARP + 1;  // epilogue warps 9..16 (two per TMEM lane quarter)
+constexpr int TC2_LOAD_WARP = TC2_EPI_WARP0 + 8; // warp 17 streams the weight images
+constexpr int TC2_THREADS = (TC2_LOAD_WARP + 1) * 32;
 constexpr int TC2_XSTAGES = 2;                  // {Xhi, Xlo} tiles consumed by the tensor core
 constexpr int TC2_WRING = 3;                    // {Whi, Wlo} weight tiles, streamed by the loader warp ahead of the MMA
 constexpr int TC2_RAW = 3;                      // raw fp32 activation ring filled by cp.async
 constexpr int TC2_SMEM_BYTES = (TC2_WRING * 2 + TC2_XSTAGES * 2 + TC2_RAW) * TC_TILE_FLOATS * 4 + 1024 + 256;
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {   // src_bytes = 0 -> zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src, uint32_t src_bytes) {   // src_bytes = 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// x = hi + lo with hi = x rounded to TF32 (nearest, ties away: the value cvt.rna.tf32.f32 returns for finite x) and lo exact in fp32.
+// Two integer ops instead of the four-instruction sequence ptxas emits for the cvt (which also handles Inf/NaN; activations are finite).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
+}
 
 __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NT, int MT)
 {
@@ -481,11 +497,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 
     if (tid == 0) {
         for (int s = 0; s < TC2_WRING; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < TC2_XSTAGES; ++s) { mbar_init(&xfull[s], 128); mbar_init(&xempty[s], 1); }
+        for (int s = 0; s < TC2_XSTAGES; ++s) { mbar_init(&xfull[s], TC2_PROD_WARPS); mbar_init(&xempty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC2_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -494,20 +510,26 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < TC2_PROD_WARPS) {
         // =========================== activation producers ===========================
-        // Each thread owns the same 8 (row, 16-byte chunk) slots in every ring entry, so it only ever waits for ITS OWN cp.async
-        // groups: no cross-thread synchronisation between the asynchronous fill and the transform.
-        const int c8 = tid & 7, r0 = tid >> 3;
+        // Each thread owns the same 4 (row, 16-byte chunk) slots in every ring entry, so it only ever waits for ITS OWN cp.async
+        // groups: no cross-thread synchronisation between the asynchronous fill and the transform.  (ncu source view of the 4-warp
+        // version: the MMA warp spun on x_full 45x more than on w_full, i.e. this transform paced the kernel - each k-block waited a
+        // full L2 round trip for the BN scale/shift, and the generic-address ST->LD ordering serialised the chunks.  Hence: 8 warps,
+        // scale/shift prefetched one k-block ahead, all raw chunks loaded before the first store, shared-space 32-bit addressing.)
+        const int c8 = tid & 7, r0 = tid >> 3;                                   // r0 in 0..31; rows r0 + 32 i
+        const uint32_t raw_u32 = smem_u32(raw_base) + (uint32_t)(r0 * TC_BK + c8 * 4) * 4u;
+        const uint32_t x_u32 = smem_u32(x_base) + (uint32_t)((r0 >> 3) * 256 + (r0 & 7) * 32 + ((c8 ^ (r0 & 7)) << 2)) * 4u;
+        const bool bn = a.x_scale != nullptr;
         auto issue = [&](int tt, int kk, int slot) {     // raw[slot][r][c8*4..] <- X[m0+r][kk*32 + c8*4 ..]   (rows >= M zero-filled)
-            float* raw = raw_base + (size_t)slot * TC_TILE_FLOATS;
             const int m0 = (tt / NT) * TC_BP;
-            const int k = kk * TC_BK + c8 * 4;
+            const float* src = a.X + (size_t)(kk * TC_BK + c8 * 4);
+            const uint32_t dst = raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 16 * i, m = m0 + r;
+            for (int i = 0; i < 4; ++i) {
+                const int m = m0 + r0 + 32 * i;
                 const bool ok = m < a.M;
-                cp_async16(raw + r * TC_BK + c8 * 4, a.X + (size_t)(ok ? m : 0) * a.ldx + k, ok ? 16u : 0u);
+                cp_async16_s(dst + (uint32_t)i * (32u * TC_BK * 4u), src + (size_t)(ok ? m : 0) * a.ldx, ok ? 16u : 0u);
             }
         };
         int ft = blockIdx.x, fk = 0;                      // next (tile, k-block) to FETCH
@@ -516,46 +538,52 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             if (ft < total) { issue(ft, fk, d); if (++fk == KB) { fk = 0; ft += gridDim.x; } }
             cp_async_commit();                            // (possibly empty) group keeps the group count uniform
         }
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bn) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + c8 * 4)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + c8 * 4)); }
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int m0 = (t / NT) * TC_BP;
+            const bool tail = m0 + TC_BP > a.M;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = it % TC2_XSTAGES;
                 const uint32_t ph = (it / TC2_XSTAGES) & 1;
                 const int slot = it % TC2_RAW;
+                float4 scn = sc, shn = sh;                // next k-block's scale/shift: in flight during this block's transform
+                if (bn) {
+                    const int kn = (kb + 1 == KB ? 0 : kb + 1) * TC_BK + c8 * 4;
+                    scn = __ldg(reinterpret_cast<const float4*>(a.x_scale + kn)); shn = __ldg(reinterpret_cast<const float4*>(a.x_shift + kn));
+                }
                 cp_async_wait<TC2_RAW - 1>();             // this thread's chunks of ring entry `slot` have landed
-                mbar_wait(&xempty[s], ph ^ 1);
-                float* Xhi = x_base + (size_t)s * (2 * TC_TILE_FLOATS);
-                float* Xlo = Xhi + TC_TILE_FLOATS;
-                const float* raw = raw_base + (size_t)slot * TC_TILE_FLOATS;
-                const int k = kb * TC_BK + c8 * 4;
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a.x_scale) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + k)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + k)); }
+                float4 v[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + 16 * i;
-                    const float4 v = *reinterpret_cast<const float4*>(raw + r * TC_BK + c8 * 4);
-                    float x[4] = {v.x, v.y, v.z, v.w};
-                    if (a.x_scale) {
-                        x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
-                        x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
-                        if (m0 + r >= a.M) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                for (int i = 0; i < 4; ++i) v[i] = lds128(raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u) + (uint32_t)i * (32u * TC_BK * 4u));
+                if (bn) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i].x = relu6f(fmaf(v[i].x, sc.x, sh.x)); v[i].y = relu6f(fmaf(v[i].y, sc.y, sh.y));
+                        v[i].z = relu6f(fmaf(v[i].z, sc.z, sh.z)); v[i].w = relu6f(fmaf(v[i].w, sc.w, sh.w));
+                        if (tail && m0 + r0 + 32 * i >= a.M) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    uint32_t hi[4]; float lo[4];
+                }
+                mbar_wait(&xempty[s], ph ^ 1);
+                const uint32_t xhi = x_u32 + (uint32_t)s * (2u * TC_TILE_FLOATS * 4u), xlo = xhi + TC_TILE_FLOATS * 4u;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(x[q]); lo[q] = x[q] - __uint_as_float(hi[q]); }
-                    const int off = (r >> 3) * 256 + (r & 7) * 32 + ((c8 ^ (r & 7)) << 2);
-                    *reinterpret_cast<uint4*>(Xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(Xlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                for (int i = 0; i < 4; ++i) {
+                    float h0, h1, h2, h3, l0, l1, l2, l3;
+                    split_tf32(v[i].x, h0, l0); split_tf32(v[i].y, h1, l1); split_tf32(v[i].z, h2, l2); split_tf32(v[i].w, h3, l3);
+                    sts128(xhi + (uint32_t)i * 4096u, h0, h1, h2, h3);       // row r0 + 32 i: 4 eight-row groups = 4 x 1024 B further
+                    sts128(xlo + (uint32_t)i * 4096u, l0, l1, l2, l3);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&xfull[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xfull[s]);
                 if (ft < total) { issue(ft, fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; } }   // refill the ring entry just consumed
                 cp_async_commit();
+                sc = scn; sh = shn;
             }
         }
         cp_async_wait<0>();
-    } else if (warp == 13) {
+    } else if (warp == TC2_LOAD_WARP) {
         // =========================== weight loader: one thread streams the pre-swizzled hi/lo images (TMA bulk copies) ===========================
         if (lane == 0) {
             uint32_t it = 0;
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == TC2_MMA_WARP) {
         // =========================== MMA issuer ===========================
         uint32_t it = 0;
         int j = 0;
@@ -603,11 +631,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             }
         }
     } else {
-        // =========================== epilogue warps 5..12 ===========================
+        // =========================== epilogue warps 9..16 ===========================
         // Two warps per TMEM lane quarter, each draining half of the 128 pixel columns.  (ncu on the 4-warp version: ~47 % of all
         // stall samples in this loop and the MMA warp waiting on tmem_empty -> the epilogue, not the tensor core, paced the tile.)
         const int q = warp & 3;                                     // TMEM lane quarter this warp may access
-        const int half = (warp - 5) >> 2;                           // 0: columns 0..63, 1: columns 64..127
+        const int half = (warp - TC2_EPI_WARP0) >> 2;                           // 0: columns 0..63, 1: columns 64..127
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
             const int buf = j & 1;
@@ -662,7 +690,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC2_MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
     }

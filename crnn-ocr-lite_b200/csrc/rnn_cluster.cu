@@ -206,7 +206,7 @@ gru_fwd_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ U
 
 // ------------------------------------------------------------------------------------------------- backward (BPTT)
 // smem: UT[96][256] | da[3][32][8] | recvA[8][32][8] | recvB[8][32][8] | half[2048]
-constexpr int BWD_SMEM_FLOATS = GC * U + 3 * UPC * RB + 2 * NCTA * UPC * RB + 2048;
+constexpr int BWD_SMEM_FLOATS = GC * U + 3 * UPC * RB + 2 * NCTA * UPC * RB + 2048 + 8;   // + 2 mbarriers
 
 // partial[r][k] = sum_{u in [u0,u1)} da[gsel][u][r] * UT[col0+u][k]   for this thread's 4 rows x 4 k, accumulated into acc
 __device__ __forceinline__ void bwd_dot(float (&acc)[4][4], const float* __restrict__ da_g, const float* __restrict__ UTg, int u0, int u1, int rg, int kq)
@@ -216,17 +216,21 @@ __device__ __forceinline__ void bwd_dot(float (&acc)[4][4], const float* __restr
         fma44(acc, *reinterpret_cast<const float4*>(da_g + u * RB + rg * 4), *reinterpret_cast<const float4*>(UTg + (size_t)u * U + kq * 4));
 }
 
-// add the other u-half's partial and push the 4(row) x 4(k) tile as four 16-byte row vectors into the owner's buffer
-__device__ __forceinline__ void push_tile(float (&acc)[4][4], const float* __restrict__ half, float* dst, int rg, int kq, int u0)
+// add the other u-half's partial and push the 4(row) x 4(k) tile as four 16-byte st.async row vectors into the owner CTA's receive
+// buffer (slot of this source CTA), each signalling 16 bytes on the owner's mbarrier
+__device__ __forceinline__ void push_tile_async(float (&acc)[4][4], const float* __restrict__ half, float* recv_local, uint64_t* bar_local,
+                                                int owner, int crank, int rg, int kq, int u0)
 {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float4 hv = *reinterpret_cast<const float4*>(half + (rg * 4 + i) * U + kq * 4);
         acc[i][0] += hv.x; acc[i][1] += hv.y; acc[i][2] += hv.z; acc[i][3] += hv.w;
     }
+    const uint32_t rbar = map_rank(smem_addr(bar_local), owner);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(dst + (u0 + q) * RB + rg * 4) = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
+        st_async_v4(map_rank(smem_addr(recv_local + crank * (UPC * RB) + (u0 + q) * RB + rg * 4), owner),
+                    make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]), rbar);
 }
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(256, 1)
@@ -240,6 +244,8 @@ gru_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__
     float* recvA = da + 3 * UPC * RB;               // [8 src][32][8]
     float* recvB = recvA + NCTA * UPC * RB;
     float* half = recvB + NCTA * UPC * RB;          // [8 rows][256 k] second u-half partial
+    uint64_t* barA = reinterpret_cast<uint64_t*>(half + 2048);   // d(r*h) reduce-scatter
+    uint64_t* barB = barA + 1;                                    // dh_{t-1} reduce-scatter
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int dir = blockIdx.y, b0 = (blockIdx.x / NCTA) * RB;
@@ -248,6 +254,10 @@ gru_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__
     for (int i = tid; i < GC * U; i += 256) {
         int k = i / GC, c = i - k * GC, g = c / UPC, u = c - g * UPC;     // coalesced-ish global read, transposed smem write
         UT[(size_t)c * U + k] = __ldg(Um + (size_t)k * (3 * U) + g * U + crank * UPC + u);
+    }
+    if (tid == 0) {
+        bar_init(barA, 1); bar_init(barB, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     cluster.sync();
@@ -275,6 +285,7 @@ gru_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__
     load_step(T - 1, nz, nr, nhh, nhp, ndo);
     for (int s = T - 1; s >= 0; --s) {
         const int t = dir ? T - 1 - s : s;
+        const uint32_t xph = (uint32_t)((T - 1 - s) & 1);       // phase parity of this step's two exchanges
         const size_t o = ((size_t)bb * T + t) * 2 + dir;
         const float z = nz, r = nr, hh = nhh, hp = nhp;
         const float dht = ndo + dh;
@@ -295,11 +306,11 @@ gru_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__
             __syncthreads();
             if (uh == 0) {
                 const int owner = (kq * 4) / UPC, u0 = (kq * 4) % UPC;
-                float* dst = cluster.map_shared_rank(recvA, owner) + crank * (UPC * RB);
-                push_tile(acc, half, dst, rg, kq, u0);
+                push_tile_async(acc, half, recvA, barA, owner, crank, rg, kq, u0);
             }
         }
-        cluster.sync();
+        if (tid == 0) bar_expect(barA, XCHG_BYTES);
+        bar_wait(barA, xph);
         float drh = 0.f;
 #pragma unroll
         for (int c = 0; c < NCTA; ++c) drh += recvA[(c * UPC + eu) * RB + er];
@@ -321,21 +332,23 @@ gru_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__
             __syncthreads();
             if (uh == 0) {
                 const int owner = (kq * 4) / UPC, u0 = (kq * 4) % UPC;
-                float* dst = cluster.map_shared_rank(recvB, owner) + crank * (UPC * RB);
-                push_tile(acc, half, dst, rg, kq, u0);
+                push_tile_async(acc, half, recvB, barB, owner, crank, rg, kq, u0);
             }
         }
-        cluster.sync();
-        if (valid) {   // after the barrier (see the forward kernel): keeps the HBM stores off the release fence
+        if (tid == 0) bar_expect(barB, XCHG_BYTES);
+        if (valid) {
             float* d = dxp + o * (3 * U);
             d[j] = da_z; d[U + j] = da_r; d[2 * U + j] = da_h;
             hprev_out[o * U + j] = hp;
             rh_out[o * U + j] = r * hp;
         }
+        bar_wait(barB, xph);
 #pragma unroll
         for (int c = 0; c < NCTA; ++c) dhn += recvB[(c * UPC + eu) * RB + er];
         dh = dhn;
+        __syncthreads();          // recvA/recvB/half/da of this step fully consumed before the next step's local writes
     }
+    cluster.sync();               // nobody exits while a peer may still address its shared memory
 }
 }  // namespace
 
