@@ -5,9 +5,12 @@ CPU restatement (PyTorch-CPU tensors, fp32 by default, fp64 optional) of the ref
 Keras 2.2.2 / TF 1.8 semantics summarised in SURVEY.md Appendix A.  Backward = torch.autograd over this
 restated forward (CTC gradient = the TF CTCLoss op gradient from oracle/ctc_oracle.c).
 
-PARITY UNPINNED: Keras/TF cannot run in this image and the reference has no tests; the restatement is
-pinned by structure (parameter counts / shapes of the shipped weight files, model_summary.txt), by
-closed-form invariants of the sampler (tests/test_oracle_net.py) and by torch cross-checks only.
+PARITY: Keras/TF cannot run in this image and the reference has no tests.  forward() + beam decode are PINNED
+against the reference's own example predictions (7 figure-extracted inputs through the shipped weights give the labels
+the reference printed, e.g. "cellist" -> "celist"; tests/test_golden.py, tests/golden/make_reference_examples.py).
+The training half (CTC gradient, backward, Adam) is PARITY UNPINNED: pinned by structure (parameter counts /
+shapes of the shipped weight files, model_summary.txt), closed-form sampler invariants (tests/test_oracle_net.py) and
+torch cross-checks only.
 
 Tensor layout follows the reference: NHWC, axis 1 ("H") = text-line width = time, axis 2 ("W") = 32.
 Weight names are "<keras layer>/<weight>" exactly as stored in models/<name>/final_weights.h5.

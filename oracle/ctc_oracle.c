@@ -12,10 +12,11 @@
  * (TF core/util/ctc/ctc_loss_calculator.{h,cc}, ctc_beam_search.h, ctc_beam_entry.h, lib/gtl/top_n.h;
  * Keras backend/tensorflow_backend.py ctc_batch_cost / ctc_decode, epsilon()=1e-7).
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors for this path and its own
- * implementation cannot run in this image; the restatement is pinned only by independent cross-checks
+ * PARITY UNPINNED for the loss/gradient: the reference ships no tests / golden vectors for this path and its
+ * own implementation cannot run in this image; the restatement is pinned only by independent cross-checks
  * (torch.nn.functional.ctc_loss in fp64, brute-force most-probable-labelling enumeration) -- see
- * tests/test_oracle_ctc.py.
+ * tests/test_oracle_ctc.py.  The beam decoder is additionally exercised by the reference's own example
+ * predictions (tests/test_golden.py: shipped weights + README-figure inputs -> the labels the reference printed).
  *
  * All arithmetic is float32 in log space, exactly like the TF CPU kernels.
  */
