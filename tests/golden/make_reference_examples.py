@@ -19,6 +19,9 @@ from PIL import Image
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/imgs/STN_examples/mjsynth_%d.png"
+SRC_IAM = "/root/reference/imgs/STN_examples/IAM_%d.png"            # same figure layout, produced with models/OCR_IAM_ver1
+TRUE_IAM = ["expressed", "mr.", "to", "intelligence", "surfaces", "effected"]
+PRED_IAM = ["expresed", "mr-", "to", "inteligence", "surfaces", "efected"]
 TRUE = ["cellist", "conduction", "gropes", "breeziest", "alisha", "mapmakers", "trojan"]
 PRED = ["celist", "conduction", "cropes", "breziest", "alisha", "mapmakers", "trojan"]     # "Pred. label" titles
 
@@ -55,9 +58,20 @@ def main():
     for i in range(1, 8):
         a, b = panels(SRC % i)
         inp.append(a); stn.append(b)
+    inp2, stn2 = [], []
+    for i in range(1, 7):
+        a, b = panels(SRC_IAM % i)
+        inp2.append(a); stn2.append(b)
     np.savez_compressed(os.path.join(HERE, "reference_examples.npz"), input_panel=np.stack(inp), stn_panel=np.stack(stn),
-                        true_label=np.array(TRUE), ref_pred=np.array(PRED))
-    print("written reference_examples.npz", np.stack(inp).shape)
+                        true_label=np.array(TRUE), ref_pred=np.array(PRED),
+                        iam_input_panel=np.stack(inp2), iam_stn_panel=np.stack(stn2), iam_true_label=np.array(TRUE_IAM), iam_ref_pred=np.array(PRED_IAM))
+    # the IAM examples need the IAM-finetuned weights (models/OCR_IAM_ver1/final_weights.h5), read with our own HDF5 reader
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import crnn_b200 as cb
+    w = cb.hdf5_lite.load_keras_weights("/root/reference/models/OCR_IAM_ver1/final_weights.h5")
+    np.savez_compressed(os.path.join(HERE, "shipped_iam_weights.npz"), **{k.replace("/", "__"): v for k, v in w.items()})
+    print("written reference_examples.npz", np.stack(inp).shape, np.stack(inp2).shape, "+ shipped_iam_weights.npz")
 
 
 if __name__ == "__main__":
