@@ -70,6 +70,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// x = hi + lo with hi = x rounded to TF32 (nearest, ties away: the value cvt.rna.tf32.f32 returns for finite x) and lo exact in fp32.
+// Two integer ops instead of the four-instruction sequence ptxas emits for the cvt (which also handles Inf/NaN; activations are finite).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
+}
+
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2
@@ -98,6 +111,7 @@ struct TcArgs {
     const float* x_scale; const float* x_shift;   // optional BN+ReLU6 on X (per k)
     double* stats;                    // optional [2*N] column sum / sum of squares of out
     const float* bias; int relu; int accumulate;   // epilogue: out = [out +] relu?(acc + bias[n])
+    int diag;                         // CRNN_GEMM_DIAG (timing experiments only, results are garbage): 1 no epilogue stores, 2 no transform, 4 no MMA, 8 no activation fetch
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
@@ -344,9 +358,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
             const int s = kb % C::STAGES;
             const uint32_t ph = (kb / C::STAGES) & 1;
             mbar_wait(&empty[s], ph ^ 1);
-            float* Ahi = stage_base + (size_t)s * C::STAGE_FLOATS;
-            float* Alo = Ahi + C::A_FLOATS; float* Bhi = Alo + C::A_FLOATS; float* Blo = Bhi + C::B_FLOATS;
+            const uint32_t ahi = smem_u32(stage_base + (size_t)s * C::STAGE_FLOATS);
+            const uint32_t alo = ahi + C::A_FLOATS * 4, bhi = alo + C::A_FLOATS * 4, blo = bhi + C::B_FLOATS * 4;
             const int pbase = p_begin + kb * 32;
+            const bool tail = pbase + 32 > p_end;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int pl = pr0 + 8 * i;
@@ -354,23 +369,23 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 if (a.x_scale) {
                     x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
                     x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
-                    if (!(pbase + pl < p_end && ci_ok)) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                    if ((tail && pbase + pl >= p_end) || !ci_ok) { x[0] = x[1] = x[2] = x[3] = 0.f; }
                 }
-                uint32_t hi[4]; float lo[4];
+                float hi[4], lo[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(x[e]); lo[e] = x[e] - __uint_as_float(hi[e]); }
-                const int off = mb * 1024 + mn_off(pl, chunk);
-                *reinterpret_cast<uint4*>(Ahi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(Alo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[e], lo[e]);
+                const uint32_t off = (uint32_t)(mb * 1024 + mn_off(pl, chunk)) * 4u;
+                sts128(ahi + off, hi[0], hi[1], hi[2], hi[3]);
+                sts128(alo + off, lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const float y[4] = {yv[g][i].x, yv[g][i].y, yv[g][i].z, yv[g][i].w};
-                    uint32_t yh[4]; float yl[4];
+                    float yh[4], yl[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { yh[e] = to_tf32(y[e]); yl[e] = y[e] - __uint_as_float(yh[e]); }
-                    const int offb = (g * 4 + mb) * 1024 + mn_off(pl, chunk);
-                    *reinterpret_cast<uint4*>(Bhi + offb) = make_uint4(yh[0], yh[1], yh[2], yh[3]);
-                    *reinterpret_cast<float4*>(Blo + offb) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+                    for (int e = 0; e < 4; ++e) split_tf32(y[e], yh[e], yl[e]);
+                    const uint32_t offb = off + (uint32_t)(g * 4) * 4096u;
+                    sts128(bhi + offb, yh[0], yh[1], yh[2], yh[3]);
+                    sts128(blo + offb, yl[0], yl[1], yl[2], yl[3]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -382,11 +397,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 for (int g = 0; g < NG; ++g) yv[g][i] = yn[g][i];
             }
         }
-        // ------------------------------------------------ epilogue: TMEM -> atomicAdd into dW (warps w and w+4 split the columns)
+        // ------------------------------------------------ epilogue: TMEM -> smem transpose -> coalesced red.global.add.v4.f32 into dW.
+        // (ncu r1d: scalar REDs straight from the TMEM layout -- lane = dW row, 1 KB apart -- were 32 sectors per instruction and ~1/3
+        // of the kernel; the split-K head GEMMs were pure epilogue.)  The pipeline stages are idle once acc_full fires and hold the tile.
         mbar_wait(accb, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr int SROW = NB + 4;                      // padded row: 16-byte aligned, conflict-free STS.128 / LDS.128
+        const uint32_t S = smem_u32(stage_base);
         const int lq = warp & 3;
-        const int row = ci0 + lq * 32 + lane;
         const int cbeg = (warp >> 2) * (NB / 2);
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + NB / 2; c0 += 32) {
@@ -402,11 +420,22 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < a.Cin) {
+            const uint32_t dst = S + (uint32_t)((lq * 32 + lane) * SROW + c0) * 4u;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int co = co0 + c0 + j;
-                    if (co < a.Cout) atomicAdd(a.dW + (size_t)row * a.ldw + co, __uint_as_float(r[j]));
+            for (int j = 0; j < 8; ++j)
+                sts128(dst + j * 16, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");    // the 8 producer/epilogue warps only (the MMA warp is not part of it)
+#pragma unroll 1
+        for (int i = 0; i < 16; ++i) {
+            const int row = warp + 8 * i, grow = ci0 + row;
+            if (grow >= a.Cin) continue;
+#pragma unroll
+            for (int h = 0; h < NG; ++h) {
+                const int col = h * 128 + lane * 4, co = co0 + col;
+                if (co < a.Cout) {
+                    const float4 v = lds128(S + (uint32_t)(row * SROW + col) * 4u);
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dW + (size_t)grow * a.ldw + co), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
                 }
             }
         }
@@ -465,20 +494,7 @@ __device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src,
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// x = hi + lo with hi = x rounded to TF32 (nearest, ties away: the value cvt.rna.tf32.f32 returns for finite x) and lo exact in fp32.
-// Two integer ops instead of the four-instruction sequence ptxas emits for the cvt (which also handles Inf/NaN; activations are finite).
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-    lo = x - hi;
-}
-
-__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NT, int MT)
+__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NTP, int MT, int NSUB)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -493,7 +509,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KB = a.K / TC_BK;
-    const int total = NT * MT;
+    const int total = NTP * MT;        // CTA tile = 128 pixels x (NSUB x 128) channels: the transformed X stage feeds NSUB accumulators
 
     if (tid == 0) {
         for (int s = 0; s < TC2_WRING; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
@@ -502,7 +518,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC2_MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -521,28 +537,27 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         const uint32_t raw_u32 = smem_u32(raw_base) + (uint32_t)(r0 * TC_BK + c8 * 4) * 4u;
         const uint32_t x_u32 = smem_u32(x_base) + (uint32_t)((r0 >> 3) * 256 + (r0 & 7) * 32 + ((c8 ^ (r0 & 7)) << 2)) * 4u;
         const bool bn = a.x_scale != nullptr;
-        auto issue = [&](int tt, int kk, int slot) {     // raw[slot][r][c8*4..] <- X[m0+r][kk*32 + c8*4 ..]   (rows >= M zero-filled)
-            const int m0 = (tt / NT) * TC_BP;
+        auto issue = [&](int m0, int kk, int slot) {     // raw[slot][r][c8*4..] <- X[m0+r][kk*32 + c8*4 ..]   (rows >= M zero-filled)
             const float* src = a.X + (size_t)(kk * TC_BK + c8 * 4);
             const uint32_t dst = raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = m0 + r0 + 32 * i;
                 const bool ok = m < a.M;
-                cp_async16_s(dst + (uint32_t)i * (32u * TC_BK * 4u), src + (size_t)(ok ? m : 0) * a.ldx, ok ? 16u : 0u);
+                if (!(a.diag & 8)) cp_async16_s(dst + (uint32_t)i * (32u * TC_BK * 4u), src + (size_t)(ok ? m : 0) * a.ldx, ok ? 16u : 0u);
             }
         };
-        int ft = blockIdx.x, fk = 0;                      // next (tile, k-block) to FETCH
+        int ft = blockIdx.x, fk = 0, fm0 = (ft / NTP) * TC_BP;     // next (tile, k-block) to FETCH
 #pragma unroll
         for (int d = 0; d < TC2_RAW; ++d) {
-            if (ft < total) { issue(ft, fk, d); if (++fk == KB) { fk = 0; ft += gridDim.x; } }
+            if (ft < total) { issue(fm0, fk, d); if (++fk == KB) { fk = 0; ft += gridDim.x; fm0 = (ft / NTP) * TC_BP; } }
             cp_async_commit();                            // (possibly empty) group keeps the group count uniform
         }
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bn) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + c8 * 4)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + c8 * 4)); }
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int m0 = (t / NT) * TC_BP;
+            const int m0 = (t / NTP) * TC_BP;
             const bool tail = m0 + TC_BP > a.M;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = it % TC2_XSTAGES;
@@ -554,6 +569,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     scn = __ldg(reinterpret_cast<const float4*>(a.x_scale + kn)); shn = __ldg(reinterpret_cast<const float4*>(a.x_shift + kn));
                 }
                 cp_async_wait<TC2_RAW - 1>();             // this thread's chunks of ring entry `slot` have landed
+                if (a.diag & 2) { mbar_wait(&xempty[s], ph ^ 1); __syncwarp(); if (lane == 0) mbar_arrive(&xfull[s]); }
+                else {
                 float4 v[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[i] = lds128(raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u) + (uint32_t)i * (32u * TC_BK * 4u));
@@ -577,7 +594,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xfull[s]);
-                if (ft < total) { issue(ft, fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; } }   // refill the ring entry just consumed
+                }
+                if (ft < total) { issue(fm0, fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; fm0 = (ft / NTP) * TC_BP; } }   // refill the ring entry just consumed
                 cp_async_commit();
                 sc = scn; sh = shn;
             }
@@ -588,46 +606,54 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int ct = t % NT;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int ws = it % TC2_WRING;
-                    mbar_wait(&wempty[ws], ((it / TC2_WRING) & 1) ^ 1);
-                    float* Whi = w_base + (size_t)ws * (2 * TC_TILE_FLOATS);
-                    const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
-                    mbar_arrive_expect_tx(&wfull[ws], 2 * TC_TILE_FLOATS * 4);
-                    bulk_g2s(Whi, src, 2 * TC_TILE_FLOATS * 4, &wfull[ws]);      // hi and lo images are contiguous: one 32 KB copy
+                const int ct0 = (t % NTP) * NSUB;
+                for (int kb = 0; kb < KB; ++kb) {
+                    for (int h = 0; h < NSUB; ++h, ++it) {
+                        const int ws = it % TC2_WRING;
+                        mbar_wait(&wempty[ws], ((it / TC2_WRING) & 1) ^ 1);
+                        float* Whi = w_base + (size_t)ws * (2 * TC_TILE_FLOATS);
+                        const float* src = a.Wimg + ((size_t)((ct0 + h) * KB + kb) * 2) * TC_TILE_FLOATS;
+                        mbar_arrive_expect_tx(&wfull[ws], 2 * TC_TILE_FLOATS * 4);
+                        bulk_g2s(Whi, src, 2 * TC_TILE_FLOATS * 4, &wfull[ws]);      // hi and lo images are contiguous: one 32 KB copy
+                    }
                 }
             }
         }
     } else if (warp == TC2_MMA_WARP) {
         // =========================== MMA issuer ===========================
-        uint32_t it = 0;
+        uint32_t it = 0, wit = 0;
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
             const int buf = j & 1;
             mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tacc = tmem_base + (uint32_t)(buf * TC_BP);
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int xs = it % TC2_XSTAGES, ws = it % TC2_WRING;
-                mbar_wait(&wfull[ws], (it / TC2_WRING) & 1);
+                const int xs = it % TC2_XSTAGES;
                 mbar_wait(&xfull[xs], (it / TC2_XSTAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t whi = smem_u32(w_base + (size_t)ws * (2 * TC_TILE_FLOATS)), wlo = whi + TC_TILE_FLOATS * 4;
-                    const uint32_t xhi = smem_u32(x_base + (size_t)xs * (2 * TC_TILE_FLOATS)), xlo = xhi + TC_TILE_FLOATS * 4;
+                for (int h = 0; h < NSUB; ++h, ++wit) {
+                    const int ws = wit % TC2_WRING;
+                    const uint32_t tacc = tmem_base + (uint32_t)(buf * 256 + h * TC_BP);
+                    mbar_wait(&wfull[ws], (wit / TC2_WRING) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t whi = smem_u32(w_base + (size_t)ws * (2 * TC_TILE_FLOATS)), wlo = whi + TC_TILE_FLOATS * 4;
+                        const uint32_t xhi = smem_u32(x_base + (size_t)xs * (2 * TC_TILE_FLOATS)), xlo = xhi + TC_TILE_FLOATS * 4;
 #pragma unroll
-                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                        const uint32_t o = ks * 32;
-                        umma_tf32(tacc, umma_desc(wlo + o), umma_desc(xhi + o), (kb | ks) ? 1u : 0u);
-                        umma_tf32(tacc, umma_desc(whi + o), umma_desc(xlo + o), 1u);
-                        umma_tf32(tacc, umma_desc(whi + o), umma_desc(xhi + o), 1u);
+                        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                            if (a.diag & 4) break;
+                            const uint32_t o = ks * 32;
+                            umma_tf32(tacc, umma_desc(wlo + o), umma_desc(xhi + o), (kb | ks) ? 1u : 0u);
+                            umma_tf32(tacc, umma_desc(whi + o), umma_desc(xlo + o), 1u);
+                            umma_tf32(tacc, umma_desc(whi + o), umma_desc(xhi + o), 1u);
+                        }
+                        umma_commit(&wempty[ws]);
+                        if (h == NSUB - 1) {
+                            umma_commit(&xempty[xs]);
+                            if (kb == KB - 1) umma_commit(&tfull[buf]);
+                        }
                     }
-                    umma_commit(&xempty[xs]);
-                    umma_commit(&wempty[ws]);
-                    if (kb == KB - 1) umma_commit(&tfull[buf]);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -636,20 +662,36 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         // stall samples in this loop and the MMA warp waiting on tmem_empty -> the epilogue, not the tensor core, paced the tile.)
         const int q = warp & 3;                                     // TMEM lane quarter this warp may access
         const int half = (warp - TC2_EPI_WARP0) >> 2;                           // 0: columns 0..63, 1: columns 64..127
+        // BN statistics: per-thread fp64 running sums over all tiles of the same channel group, flushed with two atomics per channel
+        // when the group changes / at the end (per-tile atomics = ~5 k same-address fp64 atomics per channel in block 2/3: ~50 us of
+        // pure L2 atomic serialisation in the DIAG=15 skeleton run)
+        double S1[2] = {0.0, 0.0}, S2[2] = {0.0, 0.0};
+        int cur_ct0 = -1;
+        auto flush_stats = [&]() {
+            if (!a.stats || cur_ct0 < 0) return;
+            for (int h = 0; h < NSUB; ++h) {
+                const int n = (cur_ct0 + h) * TC_BC + q * 32 + lane;
+                if (n < a.N) { atomicAdd(a.stats + n, S1[h]); atomicAdd(a.stats + a.N + n, S2[h]); }
+                S1[h] = S2[h] = 0.0;
+            }
+        };
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
             const int buf = j & 1;
-            const int ct = t % NT, m0 = (t / NT) * TC_BP;
+            const int ct0 = (t % NTP) * NSUB, m0 = (t / NTP) * TC_BP;
+            if (ct0 != cur_ct0) { flush_stats(); cur_ct0 = ct0; }
             mbar_wait(&tfull[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int n = ct * TC_BC + q * 32 + lane;
+#pragma unroll 1
+          for (int h = 0; h < NSUB; ++h) {
+            const int n = (ct0 + h) * TC_BC + q * 32 + lane;
             const bool n_ok = n < a.N;
             const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
             for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BP + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + h * TC_BP + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -661,7 +703,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float* dst = a.out + (size_t)(m0 + c0) * a.ldo + n;     // 32 lanes = 32 consecutive channels: 128-byte coalesced rows
-                if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast path: full 32-pixel chunk, no per-element predicate
+                if (a.diag & 1) {
+                } else if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast path: full 32-pixel chunk, no per-element predicate
 #pragma unroll
                     for (int p = 0; p < 32; ++p) {
                         float val = __uint_as_float(r[p]) + bias;
@@ -683,16 +726,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     }
                 }
             }
+            if (h == 0) { S1[0] += (double)s1; S2[0] += (double)s2; } else { S1[1] += (double)s1; S2[1] += (double)s2; }
+          }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty[buf]);                               // accumulator buffer may be overwritten
-            if (a.stats && n_ok) { atomicAdd(a.stats + n, (double)s1); atomicAdd(a.stats + a.N + n, (double)s2); }
         }
+        flush_stats();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == TC2_MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }
 
@@ -741,6 +786,9 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     if ((ldx % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Wimg) & 15)) { crnn_set_error("gemm_tc: X/Wimg must be 16-byte aligned, ldx %% 4 == 0"); return CRNN_ERR_INVALID; }
     TcArgs a; a.X = X; a.ldx = ldx; a.Wimg = Wimg; a.out = out; a.ldo = ldo; a.M = M; a.N = N; a.K = K;
     a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats; a.bias = bias; a.relu = relu; a.accumulate = accumulate;
+    static int diag = -1, nsub_env = -1;
+    if (diag < 0) { const char* e = getenv("CRNN_GEMM_DIAG"); diag = e ? atoi(e) : 0; const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; }
+    a.diag = diag;
     static int use_v1 = -1;
     if (use_v1 < 0) { const char* e = getenv("CRNN_GEMM_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
     const int NT = (N + TC_BC - 1) / TC_BC, MT = (M + TC_BP - 1) / TC_BP;
@@ -756,9 +804,13 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
             int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
             configured2 = true;
         }
-        const long long total = (long long)NT * MT;
+        // two channel tiles per CTA tile when there are enough tiles to fill the SMs anyway: the BN/ReLU6 + hi/lo transform of the
+        // activation tile (the instruction-issue bottleneck, ncu r1d) is then shared by 2 x 128 output channels
+        const int NSUB = (NT % 2 == 0 && (long long)(NT / 2) * MT >= num_sms && nsub_env != 1) ? 2 : 1;
+        const int NTP = NT / NSUB;
+        const long long total = (long long)NTP * MT;
         const int grid = (int)(total < num_sms ? total : num_sms);
-        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, NT, MT);
+        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, NTP, MT, NSUB);
     }
     LAUNCH_CHECK();
     return CRNN_OK;
@@ -770,6 +822,9 @@ int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ld
     if (M <= 0 || Cin <= 0 || Cout <= 0) return CRNN_OK;
     if ((Cin % 4) || (Cout % 4) || (ldx % 4) || (ldy % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(dY) & 15)) {
         crnn_set_error("gemm_tc dW: channels / leading dims must be multiples of 4 and pointers 16-byte aligned"); return CRNN_ERR_INVALID;
+    }
+    if ((ldw % 4) || (reinterpret_cast<uintptr_t>(dW) & 15)) {
+        crnn_set_error("gemm_tc dW: dW must be 16-byte aligned with ldw %% 4 == 0 (vector reductions)"); return CRNN_ERR_INVALID;
     }
     const int NB = Cout > 128 ? 256 : 128;
     const int tiles = ((Cin + 127) / 128) * ((Cout + NB - 1) / NB);
