@@ -494,6 +494,16 @@ __device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src,
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int LDO, bool STATS>
+__device__ __forceinline__ void epi_store(float* dst, const uint32_t (&r)[32], int ldo_rt, float& s1, float& s2) {
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const float val = __uint_as_float(r[p]);
+        if (LDO > 0) dst[p * LDO] = val; else dst[(size_t)p * ldo_rt] = val;
+        if (STATS) { s1 += val; s2 = fmaf(val, val, s2); }
+    }
+}
+
 __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NTP, int MT, int NSUB)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -537,20 +547,28 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         const uint32_t raw_u32 = smem_u32(raw_base) + (uint32_t)(r0 * TC_BK + c8 * 4) * 4u;
         const uint32_t x_u32 = smem_u32(x_base) + (uint32_t)((r0 >> 3) * 256 + (r0 & 7) * 32 + ((c8 ^ (r0 & 7)) << 2)) * 4u;
         const bool bn = a.x_scale != nullptr;
-        auto issue = [&](int m0, int kk, int slot) {     // raw[slot][r][c8*4..] <- X[m0+r][kk*32 + c8*4 ..]   (rows >= M zero-filled)
-            const float* src = a.X + (size_t)(kk * TC_BK + c8 * 4);
-            const uint32_t dst = raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u);
+        // fetch state: the 4 row pointers of the tile being fetched are computed once per tile, a k-block fetch is 4 x (64-bit add + LDGSTS)
+        const float* frp[4]; uint32_t fsz[4];
+        auto set_fetch_tile = [&](int tt) {
+            const int m0 = (tt / NTP) * TC_BP;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = m0 + r0 + 32 * i;
                 const bool ok = m < a.M;
-                if (!(a.diag & 8)) cp_async16_s(dst + (uint32_t)i * (32u * TC_BK * 4u), src + (size_t)(ok ? m : 0) * a.ldx, ok ? 16u : 0u);
+                frp[i] = a.X + (size_t)(ok ? m : 0) * a.ldx + c8 * 4;
+                fsz[i] = (ok && !(a.diag & 8)) ? 16u : 0u;                      // 0 -> zero fill (rows >= M)
             }
         };
-        int ft = blockIdx.x, fk = 0, fm0 = (ft / NTP) * TC_BP;     // next (tile, k-block) to FETCH
+        auto issue = [&](int kk, int slot) {             // raw[slot][r][c8*4..] <- X[m0+r][kk*32 + c8*4 ..]
+            const uint32_t dst = raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async16_s(dst + (uint32_t)i * (32u * TC_BK * 4u), frp[i] + kk * TC_BK, fsz[i]);
+        };
+        int ft = blockIdx.x, fk = 0;                      // next (tile, k-block) to FETCH
+        if (ft < total) set_fetch_tile(ft);
 #pragma unroll
         for (int d = 0; d < TC2_RAW; ++d) {
-            if (ft < total) { issue(fm0, fk, d); if (++fk == KB) { fk = 0; ft += gridDim.x; fm0 = (ft / NTP) * TC_BP; } }
+            if (ft < total) { issue(fk, d); if (++fk == KB) { fk = 0; ft += gridDim.x; if (ft < total) set_fetch_tile(ft); } }
             cp_async_commit();                            // (possibly empty) group keeps the group count uniform
         }
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -579,7 +597,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     for (int i = 0; i < 4; ++i) {
                         v[i].x = relu6f(fmaf(v[i].x, sc.x, sh.x)); v[i].y = relu6f(fmaf(v[i].y, sc.y, sh.y));
                         v[i].z = relu6f(fmaf(v[i].z, sc.z, sh.z)); v[i].w = relu6f(fmaf(v[i].w, sc.w, sh.w));
-                        if (tail && m0 + r0 + 32 * i >= a.M) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (tail) {                           // last pixel tile only: rows >= M must stay zero after the shift
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (m0 + r0 + 32 * i >= a.M) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
                 mbar_wait(&xempty[s], ph ^ 1);
@@ -595,7 +616,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xfull[s]);
                 }
-                if (ft < total) { issue(fm0, fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; fm0 = (ft / NTP) * TC_BP; } }   // refill the ring entry just consumed
+                if (ft < total) { issue(fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; if (ft < total) set_fetch_tile(ft); } }   // refill the ring entry just consumed
                 cp_async_commit();
                 sc = scn; sh = shn;
             }
@@ -704,13 +725,31 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float* dst = a.out + (size_t)(m0 + c0) * a.ldo + n;     // 32 lanes = 32 consecutive channels: 128-byte coalesced rows
                 if (a.diag & 1) {
-                } else if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast path: full 32-pixel chunk, no per-element predicate
+                } else if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast paths: full 32-pixel chunk, no per-element predicate
+                    // row stride known at compile time for the conv-stack widths -> the 32 stores use immediate offsets (the generic
+                    // loop costs a 64-bit add per store; the epilogue warps share the issue slots with the activation producers)
+                    if (a.stats) {                                              // conv forward: store + BN statistics
+                        switch (a.ldo) {
+                            case 128: epi_store<128, true>(dst, r, 0, s1, s2); break;
+                            case 256: epi_store<256, true>(dst, r, 0, s1, s2); break;
+                            case 512: epi_store<512, true>(dst, r, 0, s1, s2); break;
+                            default: epi_store<0, true>(dst, r, a.ldo, s1, s2);
+                        }
+                    } else if (a.bias || a.relu) {                              // head: bias (+ ReLU)
 #pragma unroll
-                    for (int p = 0; p < 32; ++p) {
-                        float val = __uint_as_float(r[p]) + bias;
-                        if (a.relu) val = fmaxf(val, 0.f);
-                        *dst = val; dst += a.ldo;
-                        s1 += val; s2 = fmaf(val, val, s2);
+                        for (int p = 0; p < 32; ++p) {
+                            float val = __uint_as_float(r[p]) + bias;
+                            if (a.relu) val = fmaxf(val, 0.f);
+                            dst[(size_t)p * a.ldo] = val;
+                        }
+                    } else {                                                    // dX: plain store
+                        switch (a.ldo) {
+                            case 64: epi_store<64, false>(dst, r, 0, s1, s2); break;
+                            case 128: epi_store<128, false>(dst, r, 0, s1, s2); break;
+                            case 256: epi_store<256, false>(dst, r, 0, s1, s2); break;
+                            case 512: epi_store<512, false>(dst, r, 0, s1, s2); break;
+                            default: epi_store<0, false>(dst, r, a.ldo, s1, s2);
+                        }
                     }
                 } else if (n_ok) {
 #pragma unroll
@@ -828,7 +867,11 @@ int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ld
     }
     const int NB = Cout > 128 ? 256 : 128;
     const int tiles = ((Cin + 127) / 128) * ((Cout + NB - 1) / NB);
-    int splits = (148 + tiles - 1) / tiles;
+    // split-K over pixels so that tiles x splits fills the SMs in ONE wave (the kernel runs one CTA per SM: 152 CTAs on 148 SMs
+    // doubled blocks 6/7's time)
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    int splits = sms / tiles; if (splits < 1) splits = 1;
     int per = ((M + splits - 1) / splits + 31) / 32 * 32;
     if (per < 32) per = 32;
     splits = (M + per - 1) / per;

@@ -24,8 +24,8 @@ StnDims stn_dims(int H, int W) {
 namespace {
 constexpr int NC = 20;   // locnet conv channels
 
-// one CTA per image
-__global__ void __launch_bounds__(256)
+// one CTA per image (1024 threads: every loop is a latency-bound dependent FMA chain per output, so warps are what hides it)
+__global__ void __launch_bounds__(1024)
 stn_trunk_fwd_kernel(const float* __restrict__ x, const float* __restrict__ k1, const float* __restrict__ b1,
                      const float* __restrict__ k2, const float* __restrict__ b2,
                      float* __restrict__ p1g, float* __restrict__ p2g, int* __restrict__ p2arg, float* __restrict__ flat, StnDims d)
@@ -80,7 +80,7 @@ stn_trunk_fwd_kernel(const float* __restrict__ x, const float* __restrict__ k1, 
 }
 
 // backward of the trunk for one image: weight/bias grads (atomics into the shared grad buffers)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 stn_trunk_bwd_kernel(const float* __restrict__ dflat, const float* __restrict__ p1g, const float* __restrict__ p2g,
                      const int* __restrict__ p2arg, const float* __restrict__ k2,
                      float* __restrict__ dk1, float* __restrict__ db1, float* __restrict__ dk2, float* __restrict__ db2, StnDims d)
@@ -91,10 +91,12 @@ stn_trunk_bwd_kernel(const float* __restrict__ dflat, const float* __restrict__ 
     float* p2 = p1 + d.P1h * d.P1w;       // n2
     float* dc2 = p2 + n2;                 // F
     float* dp2 = dc2 + d.F;               // n2
+    float* sk2 = dp2 + n2;                // 25*NC*NC conv2 kernel (read 500x per dp2 output)
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < d.P1h * d.P1w; i += blockDim.x) p1[i] = p1g[(size_t)b * d.P1h * d.P1w + i];
     for (int i = tid; i < n2; i += blockDim.x) p2[i] = p2g[(size_t)b * n2 + i];
     for (int i = tid; i < d.F; i += blockDim.x) dc2[i] = dflat[(size_t)b * d.F + i];
+    for (int i = tid; i < 25 * NC * NC; i += blockDim.x) sk2[i] = k2[i];
     __syncthreads();
     // db2, dk2
     for (int co = tid; co < NC; co += blockDim.x) {
@@ -118,9 +120,9 @@ stn_trunk_bwd_kernel(const float* __restrict__ dflat, const float* __restrict__ 
             for (int jj = 0; jj < 5; ++jj) {
                 int ww = w - jj; if (ww < 0 || ww >= d.C2w) continue;
                 const float* g = dc2 + (hh * d.C2w + ww) * NC;
-                const float* kk = k2 + ((ii * 5 + jj) * NC + ci) * NC;
+                const float* kk = sk2 + ((ii * 5 + jj) * NC + ci) * NC;
 #pragma unroll
-                for (int co = 0; co < NC; ++co) s = fmaf(g[co], __ldg(kk + co), s);
+                for (int co = 0; co < NC; ++co) s = fmaf(g[co], kk[co], s);
             }
         }
         dp2[i] = s;
@@ -231,7 +233,7 @@ int launch_stn_trunk_fwd(const float* x, const float* k1, const float* b1, const
     size_t smem = sizeof(float) * ((size_t)d.P1h * d.P1w + 25 * NC + (size_t)d.P2h * d.P2w * NC);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) { CUDA_TRY(cudaFuncSetAttribute(stn_trunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-    stn_trunk_fwd_kernel<<<B, 256, smem, st>>>(x, k1, b1, k2, b2, p1, p2, p2arg, flat, d);
+    stn_trunk_fwd_kernel<<<B, 1024, smem, st>>>(x, k1, b1, k2, b2, p1, p2, p2arg, flat, d);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_stn_trunk_bwd(const float* dflat, const float* p1, const float* p2, const int* p2arg, const float* k2,
@@ -239,10 +241,10 @@ int launch_stn_trunk_bwd(const float* dflat, const float* p1, const float* p2, c
 {
     StnDims d = stn_dims(H, W);
     size_t n2 = (size_t)d.P2h * d.P2w * NC;
-    size_t smem = sizeof(float) * ((size_t)d.P1h * d.P1w + 2 * n2 + d.F);
+    size_t smem = sizeof(float) * ((size_t)d.P1h * d.P1w + 2 * n2 + d.F + 25 * NC * NC);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) { CUDA_TRY(cudaFuncSetAttribute(stn_trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-    stn_trunk_bwd_kernel<<<B, 256, smem, st>>>(dflat, p1, p2, p2arg, k2, dk1, db1, dk2, db2, d);
+    stn_trunk_bwd_kernel<<<B, 1024, smem, st>>>(dflat, p1, p2, p2arg, k2, dk1, db1, dk2, db2, d);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_stn_sample_fwd(const float* x, const float* theta, float* out, int B, int H, int W, int pad, cudaStream_t st)
