@@ -58,9 +58,33 @@ __host__ __device__ __forceinline__ uint32_t crnn_hash(uint64_t seed, uint32_t l
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
     return (uint32_t)(x >> 32);
 }
-// returns 0 or 1/(1-rate)
+// Stateless dropout masks.  Element i belongs to the 4-element group i >> 2; one 2 x 32-bit mix of (seed, layer, group) yields four
+// 16-bit uniform fields, element i keeps its value iff field[i & 3] >= rate * 65536 (effective rate quantised to 1/65536).  One mix per
+// float4 instead of one 64-bit hash per element: the elementwise kernels were instruction-bound on the old per-element hash
+// (ncu r1e: 382 warp instructions per float4 in act_pool_fwd).
+__host__ __device__ __forceinline__ uint32_t crnn_mix32(uint32_t x) {          // "lowbias32" finaliser
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ void crnn_dropout_bits(uint64_t seed, uint32_t layer, uint64_t group, uint32_t& lo, uint32_t& hi) {
+    const uint32_t k = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ ((layer + 1u) * 0x85EBCA6Bu);
+    const uint32_t g = (uint32_t)group ^ ((uint32_t)(group >> 32) * 0xC2B2AE35u);
+    lo = crnn_mix32(g ^ k);
+    hi = crnn_mix32((g + 0x9E3779B9u) ^ (k * 0x27D4EB2Fu + 0x165667B1u));
+}
+__host__ __device__ __forceinline__ uint32_t crnn_dropout_thr16(float rate) { return (uint32_t)((double)rate * 65536.0); }
+// masks (0 or inv_keep) of elements 4*group .. 4*group+3
+__host__ __device__ __forceinline__ void crnn_dropout_mask4(uint64_t seed, uint32_t layer, uint64_t group, float rate, float inv_keep, float (&m)[4]) {
+    uint32_t lo, hi; crnn_dropout_bits(seed, layer, group, lo, hi);
+    const uint32_t thr = crnn_dropout_thr16(rate);
+    m[0] = (lo & 0xffffu) >= thr ? inv_keep : 0.f; m[1] = (lo >> 16) >= thr ? inv_keep : 0.f;
+    m[2] = (hi & 0xffffu) >= thr ? inv_keep : 0.f; m[3] = (hi >> 16) >= thr ? inv_keep : 0.f;
+}
+// returns 0 or 1/(1-rate) for element idx (same mask as crnn_dropout_mask4 gives that element)
 __host__ __device__ __forceinline__ float crnn_dropout_mask(uint64_t seed, uint32_t layer, uint64_t idx, float rate, float inv_keep) {
-    uint32_t thr = (uint32_t)((double)rate * 4294967296.0);
-    return crnn_hash(seed, layer, idx) >= thr ? inv_keep : 0.f;
+    uint32_t lo, hi; crnn_dropout_bits(seed, layer, idx >> 2, lo, hi);
+    const uint32_t w = (idx & 2) ? hi : lo;
+    const uint32_t f = (idx & 1) ? (w >> 16) : (w & 0xffffu);
+    return f >= crnn_dropout_thr16(rate) ? inv_keep : 0.f;
 }
 #endif

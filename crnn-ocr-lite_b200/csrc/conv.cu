@@ -2,6 +2,8 @@
 // DepthwiseConv2D 3x3 'same' (fwd, bwd-data, bwd-weight), BatchNormalization statistics / finalize / backward,
 // ReLU6 + MaxPooling + Dropout (fwd / bwd), and the small element-wise glue of the recurrent head.
 // All tensors NHWC fp32; channel counts are 1 or multiples of 4 (float4 path).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -246,29 +248,41 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double M, i
 }
 
 // ------------------------------------------------------------------ BN + ReLU6 + MaxPool + Dropout forward
-__global__ void act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                                    float* __restrict__ a, int B, int H, int W, int C4, int ph, int pw,
-                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long total)
+// blockDim = (CQ channel quads, PY pixel lanes): a thread keeps its 4 channels' scale/shift in registers and walks output pixels
+// (one integer division per pixel; two pixels' window loads in flight).  ncu r1e on the 1-D version: 382 warp instructions per float4
+// (per-element 64-bit dropout hash + 4 div/mod) and 48 % issue-active at 3.3 TB/s, i.e. instruction-bound, not HBM-bound.
+template <int PH, int PW>
+__global__ void __launch_bounds__(256) act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    float* __restrict__ a, int W, int C4, int Wo, int npix,
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer)
 {
-    const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
-    const int total32 = (int)total;                 // < 2^31 (checked by the launcher)
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += gridDim.x * blockDim.x) {
-        const int c4 = idx % C4; int r = idx / C4;
-        const int wo = r % Wo; r /= Wo;
-        const int ho = r % Ho; const int b = r / Ho;
-        float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
+    const int CQ = blockDim.x, PY = blockDim.y;
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    if (c4 >= C4) return;
+    const int C = C4 * 4;
+    const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
+    const int pstride = gridDim.y * PY;
+#pragma unroll 2
+    for (int p = blockIdx.y * PY + threadIdx.y; p < npix; p += pstride) {
+        const int row = p / Wo, wo = p - row * Wo;                       // row = b*Ho + ho; input row = row*PH because H = Ho*PH
+        const float* src = y + ((size_t)(row * PH) * W + wo * PW) * C + c4 * 4;
+        float4 v[PH * PW];
+#pragma unroll
+        for (int i = 0; i < PH; ++i)
+#pragma unroll
+            for (int j = 0; j < PW; ++j) v[i * PW + j] = ldg4(src + ((size_t)i * W + j) * C);
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        for (int i = 0; i < ph; ++i)
-            for (int j = 0; j < pw; ++j) {
-                float4 v = ldg4(y + (((size_t)b * H + ho * ph + i) * W + wo * pw + j) * C + c4 * 4);
-                m.x = fmaxf(m.x, relu6f(fmaf(v.x, sc.x, sh.x))); m.y = fmaxf(m.y, relu6f(fmaf(v.y, sc.y, sh.y)));
-                m.z = fmaxf(m.z, relu6f(fmaf(v.z, sc.z, sh.z))); m.w = fmaxf(m.w, relu6f(fmaf(v.w, sc.w, sh.w)));
-            }
-        if (rate > 0.f) {
-            m.x *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 0, rate, inv_keep); m.y *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 1, rate, inv_keep);
-            m.z *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 2, rate, inv_keep); m.w *= crnn_dropout_mask(seed, layer, (uint64_t)idx * 4 + 3, rate, inv_keep);
+#pragma unroll
+        for (int n = 0; n < PH * PW; ++n) {
+            m.x = fmaxf(m.x, relu6f(fmaf(v[n].x, sc.x, sh.x))); m.y = fmaxf(m.y, relu6f(fmaf(v[n].y, sc.y, sh.y)));
+            m.z = fmaxf(m.z, relu6f(fmaf(v[n].z, sc.z, sh.z))); m.w = fmaxf(m.w, relu6f(fmaf(v[n].w, sc.w, sh.w)));
         }
-        *reinterpret_cast<float4*>(a + (size_t)idx * 4) = m;
+        const size_t oidx = (size_t)p * C4 + c4;
+        if (rate > 0.f) {
+            float dm[4]; crnn_dropout_mask4(seed, layer, (uint64_t)oidx, rate, inv_keep, dm);
+            m.x *= dm[0]; m.y *= dm[1]; m.z *= dm[2]; m.w *= dm[3];
+        }
+        *reinterpret_cast<float4*>(a + oidx * 4) = m;
     }
 }
 
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
     extern __shared__ float sred[];   // [PY][8][CQ]
     constexpr int ph = PH, pw = PW, NW = PH * PW;
     const int CQ = blockDim.x, PY = blockDim.y;
-    const int Ho = H / ph, Wo = W / pw, C = C4 * 4;
+    const int Wo = W / pw, C = C4 * 4;
     const int npix = (int)npix_ll;                  // < 2^31 (checked by the launcher): 32-bit index arithmetic
     const int c4 = blockIdx.x * CQ + threadIdx.x;
     float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
@@ -306,15 +320,16 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
         const int pstride = gridDim.y * PY;
 #pragma unroll 2
         for (int p = blockIdx.y * PY + threadIdx.y; p < npix; p += pstride) {
-            const int wo = p % Wo; const int r = p / Wo;
-            const int ho = r % Ho; const int b = r / Ho;
+            const int row = p / Wo, wo = p - row * Wo;       // row = b*Ho + ho; input row = row*ph because H = Ho*ph
             const size_t oidx = (size_t)p * C4 + c4;
             float g[4];
             { float4 t = ldg4(da + oidx * 4); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
-            if (rate > 0.f)
+            if (rate > 0.f) {
+                float dm[4]; crnn_dropout_mask4(seed, layer, (uint64_t)oidx, rate, inv_keep, dm);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) g[q] *= crnn_dropout_mask(seed, layer, oidx * 4 + q, rate, inv_keep);
-            const size_t base = (((size_t)b * H + ho * ph) * W + wo * pw) * C + c4 * 4;
+                for (int q = 0; q < 4; ++q) g[q] *= dm[q];
+            }
+            const size_t base = ((size_t)(row * ph) * W + wo * pw) * C + c4 * 4;
             float yv[NW][4];
 #pragma unroll
             for (int i = 0; i < ph; ++i)
@@ -627,9 +642,17 @@ int launch_bn_finalize(const double* stats, long long M, int C, const float* gam
 int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C, int ph, int pw,
                         float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
-    long long total = (long long)B * (H / ph) * (W / pw) * (C / 4);
+    const long long npix = (long long)B * (H / ph) * (W / pw);
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
-    act_pool_fwd_kernel<<<grid1d(total, 256), 256, 0, st>>>(y, scale, shift, a, B, H, W, C / 4, ph, pw, rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, total);
+    const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+    dim3 grid, block; chan_block(C / 4, npix, grid, block);
+    grid.y = (unsigned)std::min<long long>((npix + block.y - 1) / block.y, (long long)grid.y * 2);     // ~8 CTAs per SM: short dependent chains, many loads in flight
+#define APF(PH_, PW_) act_pool_fwd_kernel<PH_, PW_><<<grid, block, 0, st>>>(y, scale, shift, a, W, C / 4, W / pw, (int)npix, rate, ik, seed, layer)
+    if (ph == 1 && pw == 1) APF(1, 1);
+    else if (ph == 2 && pw == 2) APF(2, 2);
+    else if (ph == 1 && pw == 2) APF(1, 2);
+    else { crnn_set_error("act_pool: unsupported pool %dx%d", ph, pw); return CRNN_ERR_INVALID; }
+#undef APF
     LAUNCH_CHECK(); return CRNN_OK;
 }
 // two launches: reductions, then apply (+ a tiny launch for dgamma/dbeta); `red` (double[2C]) must be pre-zeroed
