@@ -81,6 +81,81 @@ __global__ void __launch_bounds__(256) dwconv3x3_vec4_w4(const float* __restrict
             if (w0 + o < W) *reinterpret_cast<float4*>(y + ((((size_t)b * H + h) * W + w0 + o) * C4 + c4) * 4) = acc[o];
     }
 }
+// Channel-block variant of the kernel above (blockDim = (CQ channel quads, PY lanes)): a thread keeps the nine taps of its 4 channels
+// in registers and walks (image row, 4-column group) work items, so the per-item weight loads and two of the three integer divisions
+// disappear; with STATS it also accumulates the BatchNorm statistics of its outputs (fp32 per item, fp64 across items, smem across the
+// PY lanes, one fp64 atomic pair per channel and CTA) -- the separate colstats pass over the depthwise output is gone.
+template <bool FLIP, bool STATS>
+__global__ void __launch_bounds__(256) dwconv3x3_cb_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
+                                                           int H, int W, int C4, int WG, int ngroups, double* __restrict__ stats)
+{
+    extern __shared__ double dsm[];   // STATS: [PY][8][CQ]
+    const int CQ = blockDim.x, PY = blockDim.y;
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    const int C = C4 * 4;
+    double S[4] = {0.0, 0.0, 0.0, 0.0}, Q[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c4 < C4) {
+        float4 kv[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) kv[q] = ldg4(k + (size_t)q * C + c4 * 4);
+        const int gstride = gridDim.y * PY;
+        for (int g = blockIdx.y * PY + threadIdx.y; g < ngroups; g += gstride) {
+            const int rowi = g / WG, wg = g - rowi * WG;         // rowi = b*H + h
+            const int h = rowi % H;
+            const int w0 = wg * 4;
+            float4 acc[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int dh = FLIP ? 1 - i : i - 1;
+                if (h + dh < 0 || h + dh >= H) continue;
+                const float* row = x + ((size_t)(rowi + dh) * W) * C + c4 * 4;
+                float4 xv[6];
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const int col = w0 - 1 + t;
+                    xv[t] = (col >= 0 && col < W) ? ldg4(row + (size_t)col * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) fma4(acc[o], xv[FLIP ? (o - j + 2) : (o + j)], kv[i * 3 + j]);
+            }
+            float* dst = y + ((size_t)rowi * W + w0) * C + c4 * 4;
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (w0 + o < W) {
+                    *reinterpret_cast<float4*>(dst + (size_t)o * C) = acc[o];
+                    if (STATS) {
+                        s[0] += acc[o].x; s[1] += acc[o].y; s[2] += acc[o].z; s[3] += acc[o].w;
+                        q[0] = fmaf(acc[o].x, acc[o].x, q[0]); q[1] = fmaf(acc[o].y, acc[o].y, q[1]);
+                        q[2] = fmaf(acc[o].z, acc[o].z, q[2]); q[3] = fmaf(acc[o].w, acc[o].w, q[3]);
+                    }
+                }
+            if (STATS) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { S[e] += (double)s[e]; Q[e] += (double)q[e]; }
+            }
+        }
+    }
+    if (!STATS) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        dsm[(threadIdx.y * 8 + e) * CQ + threadIdx.x] = S[e];
+        dsm[(threadIdx.y * 8 + 4 + e) * CQ + threadIdx.x] = Q[e];
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && c4 < C4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            double t1 = 0.0, t2 = 0.0;
+            for (int i = 0; i < PY; ++i) { t1 += dsm[(i * 8 + e) * CQ + threadIdx.x]; t2 += dsm[(i * 8 + 4 + e) * CQ + threadIdx.x]; }
+            atomicAdd(stats + c4 * 4 + e, t1); atomicAdd(stats + C + c4 * 4 + e, t2);
+        }
+    }
+}
 template <bool FLIP>
 __global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                              int B, int H, int W, long long total)
@@ -602,17 +677,26 @@ inline void chan_block(int C, long long M, dim3& grid, dim3& block) {
 
 }  // namespace
 
-int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st) {
+int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats) {
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
-    if (C % 4 == 0) { const int WG = (W + 3) / 4; long long total = (long long)B * H * WG * (C / 4); dwconv3x3_vec4_w4<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, C / 4, WG, total); }
-    else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, total); }
-    else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
+    if (C % 4 == 0) {
+        const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
+        dim3 grid, block; chan_block(C / 4, ngroups, grid, block);
+        if (stats) dwconv3x3_cb_kernel<false, true><<<grid, block, sizeof(double) * 8 * 256, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, stats);
+        else dwconv3x3_cb_kernel<false, false><<<grid, block, 0, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, nullptr);
+    }
+    else if (C == 1 && !stats) { long long total = (long long)B * H * W; dwconv3x3_c1<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, total); }
+    else { crnn_set_error("dwconv: C must be 1 or a multiple of 4 (fused statistics need C %% 4 == 0)"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
     if (accumulate) { crnn_set_error("dwconv_bwd_data: accumulate unsupported"); return CRNN_ERR_INVALID; }
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
-    if (C % 4 == 0) { const int WG = (W + 3) / 4; long long total = (long long)B * H * WG * (C / 4); dwconv3x3_vec4_w4<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, C / 4, WG, total); }
+    if (C % 4 == 0) {
+        const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
+        dim3 grid, block; chan_block(C / 4, ngroups, grid, block);
+        dwconv3x3_cb_kernel<true, false><<<grid, block, 0, st>>>(dy, k, dx, H, W, C / 4, WG, (int)ngroups, nullptr);
+    }
     else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;

@@ -305,8 +305,11 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         const BlockPlan& b = kBlocks[i - 1];
         const long long M = (long long)B * hh * ww;
         float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
-        ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st));
-        TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st));
+        const bool dw_stats = training && (b.cin % 4 == 0);       // BN statistics of the depthwise output fused into the conv kernel
+        double* dstats = reinterpret_cast<double*>(h->a("stats"));
+        if (dw_stats) CUDA_TRY(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * b.cin, st));
+        ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st, dw_stats ? dstats : nullptr));
+        TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st, dw_stats));
         const bool tc = !h->gemm_simt && (b.cin % 32 == 0);
         if (tc) {
             float* img = h->a(nm("wimg_fwd%d", i));

@@ -38,7 +38,7 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
                     int* out, int* out_len, float* logprob, cudaStream_t st);
 
 // ---- conv.cu (depthwise conv, BN statistics, activation/pool, elementwise) ----
-int launch_dwconv_fwd(const float* x, const float* k33c, float* y, int B, int H, int W, int C, cudaStream_t st);
+int launch_dwconv_fwd(const float* x, const float* k33c, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats = nullptr);
 int launch_dwconv_bwd_data(const float* dy, const float* k33c, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st);
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
 // per-channel sum / sum of squares over rows of y[M][C] -> stats[0..C) , stats[C..2C) (double, pre-zeroed)
