@@ -329,11 +329,12 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double M, i
 template <int PH, int PW>
 __global__ void __launch_bounds__(256) act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                     float* __restrict__ a, int W, int C4, int Wo, int npix,
-                                    float rate, float inv_keep, uint64_t seed, uint32_t layer)
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr)
 {
     const int CQ = blockDim.x, PY = blockDim.y;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
     if (c4 >= C4) return;
+    if (seed_ptr) seed = *seed_ptr;                 // graph replay: the step's seed lives in device memory
     const int C = C4 * 4;
     const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
     const int pstride = gridDim.y * PY;
@@ -370,9 +371,10 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
                                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, float* __restrict__ dy, double* __restrict__ red,
                                     int B, int H, int W, int C4, double invM,
-                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix_ll)
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix_ll, const uint64_t* __restrict__ seed_ptr)
 {
     extern __shared__ float sred[];   // [PY][8][CQ]
+    if (seed_ptr) seed = *seed_ptr;
     constexpr int ph = PH, pw = PW, NW = PH * PW;
     const int CQ = blockDim.x, PY = blockDim.y;
     const int Wo = W / pw, C = C4 * 4;
@@ -609,11 +611,74 @@ __global__ void relu_dropout_bwd_kernel(float* __restrict__ g, const float* __re
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         g[i] = act[i] > 0.f ? g[i] * inv_keep : 0.f;
 }
-__global__ void dropout_kernel(float* __restrict__ x, long long n, float rate, float inv_keep, uint64_t seed, uint32_t layer)
+__global__ void dropout_kernel(const float* in, float* x, long long n, float rate, float inv_keep, uint64_t seed, uint32_t layer,
+                               const uint64_t* __restrict__ seed_ptr)
 {
+    if (seed_ptr) seed = *seed_ptr;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        x[i] *= crnn_dropout_mask(seed, layer, (uint64_t)i, rate, inv_keep);
+        x[i] = in[i] * crnn_dropout_mask(seed, layer, (uint64_t)i, rate, inv_keep);
 }
+// ------------------------------------------------------------------ block 1 (Cin = 1): pointwise conv = outer product
+// blockDim = 256 = 16 pixel lanes x 16 channel quads (Cout = 64); a warp covers 2 pixels x 64 channels = 2 x 256 B contiguous.
+// BN statistics of the output in closed form: sum_m f_m w_c = w_c * S1, sum_m (f_m w_c)^2 = w_c^2 * S2 (S1, S2 accumulated in double per CTA).
+__global__ void __launch_bounds__(256) pw1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      const float* __restrict__ w, float* __restrict__ out, int M, int C4, double* __restrict__ stats)
+{
+    __shared__ float s1s[8], s2s[8];
+    const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, PL = blockDim.x / C4;
+    const float sc = __ldg(scale), sh = __ldg(shift);
+    const float4 wq = ldg4(w + c4 * 4);
+    float s1 = 0.f, s2 = 0.f;
+    for (int m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL) {
+        const float f = relu6f(fmaf(__ldg(x + m), sc, sh));
+        *reinterpret_cast<float4*>(out + ((size_t)m * C4 + c4) * 4) = make_float4(f * wq.x, f * wq.y, f * wq.z, f * wq.w);
+        if (c4 == 0) { s1 += f; s2 = fmaf(f, f, s2); }
+    }
+    if (!stats) return;
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { s1s[threadIdx.x >> 5] = s1; s2s[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    const int C = C4 * 4;
+    if (threadIdx.x < C) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += (double)s1s[i]; b += (double)s2s[i]; }
+        const double wc = (double)__ldg(w + threadIdx.x);
+        atomicAdd(stats + threadIdx.x, wc * a);
+        atomicAdd(stats + C + threadIdx.x, wc * wc * b);
+    }
+}
+// backward in one pass over dY: dX[m] = sum_c dY[m][c] w[c] (16-lane shuffle reduce), dW[c] += sum_m f(x[m]) dY[m][c]
+__global__ void __launch_bounds__(256) pw1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      const float* __restrict__ dY, const float* __restrict__ w, float* __restrict__ dX,
+                                                      float* __restrict__ dW, int M)
+{
+    __shared__ float4 sacc[256];
+    const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
+    const float sc = __ldg(scale), sh = __ldg(shift);
+    const float4 wq = ldg4(w + c4 * 4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int mstep = gridDim.x * 16;
+    // every lane of a warp runs the same number of iterations (M is padded to the stride by the bound check inside)
+    for (int m0 = blockIdx.x * 16; m0 < M; m0 += mstep) {
+        const int m = m0 + pl;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f); float f = 0.f;
+        if (m < M) { g = ldg4(dY + ((size_t)m * 16 + c4) * 4); f = relu6f(fmaf(__ldg(x + m), sc, sh)); }
+        float d = g.x * wq.x + g.y * wq.y + g.z * wq.z + g.w * wq.w;
+#pragma unroll
+        for (int o = 8; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (c4 == 0 && m < M) dX[m] = d;
+        acc.x = fmaf(f, g.x, acc.x); acc.y = fmaf(f, g.y, acc.y); acc.z = fmaf(f, g.z, acc.z); acc.w = fmaf(f, g.w, acc.w);
+    }
+    sacc[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 16; ++i) { const float4 v = sacc[i * 16 + threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        atomicAdd(dW + threadIdx.x * 4 + 0, t.x); atomicAdd(dW + threadIdx.x * 4 + 1, t.y);
+        atomicAdd(dW + threadIdx.x * 4 + 2, t.z); atomicAdd(dW + threadIdx.x * 4 + 3, t.w);
+    }
+}
+__global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }
 __global__ void sum_dirs_kernel(const float* __restrict__ hs, float* __restrict__ out, long long rows, int U)
 {
     long long n = rows * U;
@@ -724,14 +789,14 @@ int launch_bn_finalize(const double* stats, long long M, int C, const float* gam
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C, int ph, int pw,
-                        float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
+                        float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
     grid.y = (unsigned)std::min<long long>((npix + block.y - 1) / block.y, (long long)grid.y * 2);     // ~8 CTAs per SM: short dependent chains, many loads in flight
-#define APF(PH_, PW_) act_pool_fwd_kernel<PH_, PW_><<<grid, block, 0, st>>>(y, scale, shift, a, W, C / 4, W / pw, (int)npix, rate, ik, seed, layer)
+#define APF(PH_, PW_) act_pool_fwd_kernel<PH_, PW_><<<grid, block, 0, st>>>(y, scale, shift, a, W, C / 4, W / pw, (int)npix, rate, ik, seed, layer, seed_ptr)
     if (ph == 1 && pw == 1) APF(1, 1);
     else if (ph == 2 && pw == 2) APF(2, 2);
     else if (ph == 1 && pw == 2) APF(1, 2);
@@ -742,14 +807,14 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
 // two launches: reductions, then apply (+ a tiny launch for dgamma/dbeta); `red` (double[2C]) must be pre-zeroed
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red, float* dgamma, float* dbeta,
-                           int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
+                           int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     const double invM = 1.0 / ((double)B * H * W);
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
-#define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix)
+#define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix, seed_ptr)
     const size_t sm = sizeof(float) * 8 * 256;
     if (ph == 1 && pw == 1) { APB(false, 1, 1, sm); LAUNCH_CHECK(); APB(true, 1, 1, 0); }
     else if (ph == 2 && pw == 2) { APB(false, 2, 2, sm); LAUNCH_CHECK(); APB(true, 2, 2, 0); }
@@ -794,9 +859,29 @@ int launch_relu_dropout_bwd(float* g, const float* act, long long n, float rate,
     relu_dropout_bwd_kernel<<<grid1d(n, 256), 256, 0, st>>>(g, act, n, rate > 0.f ? 1.f / (1.f - rate) : 1.f);
     LAUNCH_CHECK(); return CRNN_OK;
 }
-int launch_dropout_fwd(float* x, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st) {
+int launch_dropout_fwd(float* x, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
     if (rate <= 0.f) return CRNN_OK;
-    dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(x, n, rate, 1.f / (1.f - rate), seed, layer);
+    dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(x, x, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_dropout_copy(const float* in, float* out, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
+    dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(in, out, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_pw1_fwd(const float* x, const float* scale, const float* shift, const float* w, float* out, long long M, int Cout, double* stats, cudaStream_t st) {
+    if (Cout != 64 || too_big(M * Cout)) { crnn_set_error("pw1_fwd: Cout must be 64"); return CRNN_ERR_INVALID; }
+    const int grid = (int)std::min<long long>((M + 15) / 16, 148 * 8);
+    pw1_fwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, w, out, (int)M, Cout / 4, stats);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const float* dY, const float* w, float* dX, float* dW, long long M, int Cout, cudaStream_t st) {
+    if (Cout != 64 || too_big(M * Cout)) { crnn_set_error("pw1_bwd: Cout must be 64"); return CRNN_ERR_INVALID; }
+    const int grid = (int)std::min<long long>((M + 15) / 16, 148 * 8);
+    pw1_bwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, dY, w, dX, dW, (int)M);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_set_u64(uint64_t* p, uint64_t v, cudaStream_t st) {
+    set_u64_kernel<<<1, 1, 0, st>>>(p, v);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_sum_dirs(const float* hs, float* out, long long rows, int U, cudaStream_t st) {

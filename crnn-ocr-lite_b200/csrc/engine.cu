@@ -82,6 +82,20 @@ struct crnn_handle {
     Prof prof;
     bool gemm_simt = false;   // CRNN_GEMM_SIMT=1: fp32 SIMT GEMM for the pointwise convs instead of the tcgen05 3xTF32 kernel
     bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
+    // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
+    // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
+    // stream = a parallel branch of the graph.  CRNN_GRAPH=0 / CRNN_OVERLAP=0 switch either off; profiling runs eager + serial.
+    bool use_graph = true, overlap = true;
+    cudaStream_t side = nullptr, cap = nullptr;
+    std::vector<cudaEvent_t> evs; size_t ev_used = 0;
+    const uint64_t* seed_ptr = nullptr;   // non-null while capturing: dropout kernels read the seed from device memory
+    struct StepGraph { int kind, B; const void* p[6]; int drop; int calls; cudaGraphExec_t exec; long long launches; };
+    std::vector<StepGraph> graphs;
+    int bn_off[16];   // offset (in doubles) of BN n's [sum | sumsq] slots inside act/stats and act/red
+    cudaEvent_t ev() {
+        if (ev_used == evs.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); }
+        return evs[ev_used++];
+    }
 
     float* f(const std::string& name) const {
         auto it = L.index.find(name);
@@ -112,6 +126,21 @@ struct Scope {   // records a [start, stop] event pair around a stage when profi
     ~Scope() { if (idx >= 0) { cudaEventRecord(h->prof.recs[idx].b, st); h->prof.recs[idx].launches = g_crnn_launches - l0; } }
 };
 #define ST(stage, work, call) do { Scope _s(h, st, stage, (double)(work)); int _r = (call); if (_r != CRNN_OK) return _r; } while (0)
+
+// Side branch of the step: returns the stream for work that is off the critical path, ordered after everything issued on `st` so far.
+// Under stream capture the event pair becomes a graph edge; eagerly it is a real cross-stream dependency.
+cudaStream_t side_after(crnn_handle* h, cudaStream_t st) {
+    if (!h->overlap || h->prof.on || !h->side) return st;
+    cudaEvent_t e = h->ev();
+    cudaEventRecord(e, st); cudaStreamWaitEvent(h->side, e, 0);
+    return h->side;
+}
+// everything issued on the side branch so far completes before what follows on `st`
+void side_join(crnn_handle* h, cudaStream_t st) {
+    if (!h->overlap || h->prof.on || !h->side) return;
+    cudaEvent_t e = h->ev();
+    cudaEventRecord(e, h->side); cudaStreamWaitEvent(st, e, 0);
+}
 
 int validate(const crnn_config* c) {
     if (!c) { crnn_set_error("null config"); return CRNN_ERR_INVALID; }
@@ -212,18 +241,48 @@ void plan(crnn_handle* h) {
     A("rnn1", M * h->U); A("rnn2drop", M * 2 * h->U);
     A("logits", M * h->V); A("softmax", M * h->V); A("dlogits", M * h->V); A("loss", B);
     // backward scratch
+    // d(block output) ping-pongs between gA/gB; the pointwise-output and depthwise-output gradients of every block get their own
+    // buffers so that the weight-gradient branch of the step graph can read them without write-after-read hazards
     A("gA", max_act); A("gB", max_act);
-    A("dxp", M * 2 * h->G * h->U); A("hprev", M * 2 * h->U); A("rh", M * 2 * h->U);
+    hh = h->Hp; ww = h->Wp;
+    for (int i = 1; i <= 7; ++i) {
+        const BlockPlan& b = kBlocks[i - 1];
+        char nm2[32];
+        snprintf(nm2, sizeof(nm2), "dpw%d", i); A(nm2, B * hh * ww * b.cout);
+        snprintf(nm2, sizeof(nm2), "ddw%d", i); A(nm2, B * hh * ww * b.cin);
+        hh /= b.ph; ww /= b.pw;
+    }
+    for (int layer = 1; layer <= 2; ++layer) {
+        char nm2[32];
+        snprintf(nm2, sizeof(nm2), "dxp%d", layer); A(nm2, M * 2 * h->G * h->U);
+        snprintf(nm2, sizeof(nm2), "hprev%d", layer); A(nm2, M * 2 * h->U);
+        snprintf(nm2, sizeof(nm2), "rh%d", layer); A(nm2, M * 2 * h->U);
+    }
     A("UT", (int64_t)2 * h->G * h->U * h->U);
-    A("dtheta", B * 6); A("dd1", B * 50); A("dflat", B * h->sd.F);
-    A("wimg_head", (int64_t)tc_weight_image_floats(h->FEAT, h->TD > 1024 ? h->TD : 1024));   // head GEMMs reuse one image buffer
-    for (int i = 2; i <= 7; ++i) {   // pre-swizzled hi/lo weight images of the tcgen05 pointwise kernel (gemm_tc.cu)
+    A("dtheta", B * 6); A("dd1", B * 50); A("dflat", B * h->sd.F); A("ddense1", M * h->TD);
+    // pre-swizzled hi/lo weight images of the tcgen05 kernels (gemm_tc.cu), one per GEMM: prepared once per step on the side branch
+    A("wimg_d1f", (int64_t)tc_weight_image_floats(h->TD, h->FEAT)); A("wimg_d1b", (int64_t)tc_weight_image_floats(h->FEAT, h->TD));
+    for (int layer = 1; layer <= 2; ++layer)
+        for (int d = 0; d < 2; ++d) {
+            const int kin = layer == 1 ? h->TD : h->U;
+            char nm2[32];
+            snprintf(nm2, sizeof(nm2), "wimg_r%d%df", layer, d); A(nm2, (int64_t)tc_weight_image_floats(h->G * h->U, kin));
+            snprintf(nm2, sizeof(nm2), "wimg_r%d%db", layer, d); A(nm2, (int64_t)tc_weight_image_floats(kin, h->G * h->U));
+        }
+    for (int i = 2; i <= 7; ++i) {
         const BlockPlan& b = kBlocks[i - 1];
         char nm2[32];
         snprintf(nm2, sizeof(nm2), "wimg_fwd%d", i); A(nm2, (int64_t)tc_weight_image_floats(b.cout, b.cin));
         snprintf(nm2, sizeof(nm2), "wimg_dx%d", i); A(nm2, (int64_t)tc_weight_image_floats(b.cin, b.cout));
     }
-    L.add("act/stats", 2 * 512, 8); L.add("act/red", 2 * 512, 8); L.add("act/sumsq", 1, 8);
+    {   // per-BN [sum | sumsq] slots (forward statistics / backward reductions): one memset per pass instead of one per layer
+        int off = 0;
+        for (int i = 1; i <= 7; ++i)
+            for (int k = 0; k < 2; ++k) { h->bn_off[2 * i - 1 + k] = off; off += 2 * (k ? kBlocks[i - 1].cout : kBlocks[i - 1].cin); }
+        h->bn_off[15] = off;
+        L.add("act/stats", off, 8); L.add("act/red", off, 8);
+    }
+    L.add("act/sumsq", 1, 8); L.add("act/seed", 1, 8);
     L.add("act/status", 1, 4, 1);
     L.add("act/labels", B * c.max_len, 4, 1); L.add("act/label_len", B, 4, 1); L.add("act/input_len", B, 4, 1);
     L.cursor = (L.cursor + 255) & ~(int64_t)255;
@@ -263,11 +322,9 @@ int gemm_nt(crnn_handle* h, int stage, const float* dY, int ldy, const float* Wt
     return launch_gemm_simt(g, st);
 }
 
-// out[M][N] = [out +] relu?(X[M][K] @ Wop^T + bias) on the tensor cores; Wop[n][k] = W[k*ldw+n] (transposed) or W[n*ldw+k]
-int tc_xw(crnn_handle* h, int stage, const float* X, int ldx, const float* W, int ldw, int transposed, float* out, int ldo, int M, int N, int K,
+// out[M][N] = [out +] relu?(X[M][K] @ Wop^T + bias) on the tensor cores; `img` = weight image prepared by prep_images()
+int tc_xw(crnn_handle* h, int stage, const float* X, int ldx, const float* img, float* out, int ldo, int M, int N, int K,
           const float* bias, int relu, int accumulate, cudaStream_t st) {
-    float* img = h->a("wimg_head");
-    ST(ST_MISC, 0, launch_prep_weight_images(W, ldw, N, K, transposed, img, st));
     ST(stage, 2.0 * M * N * K, launch_xw_gemm_tc(X, ldx, img, out, ldo, M, N, K, nullptr, nullptr, nullptr, st, bias, relu, accumulate));
     return CRNN_OK;
 }
@@ -277,26 +334,55 @@ std::string bnname(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b)
 std::string actbn(int bn, const char* leaf) { char b[64]; snprintf(b, sizeof(b), "bn%d/%s", bn, leaf); return b; }
 std::string nm(const char* fmt, int i) { char b[64]; snprintf(b, sizeof(b), fmt, i); return b; }
 
+double* bn_stats(crnn_handle* h, int bn) { return reinterpret_cast<double*>(h->a("stats")) + h->bn_off[bn]; }
+double* bn_red(crnn_handle* h, int bn) { return reinterpret_cast<double*>(h->a("red")) + h->bn_off[bn]; }
+
+// act/stats is zeroed once at the start of a training forward; stats_ready = the producer kernel already accumulated into the slot
 int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool training, cudaStream_t st, bool stats_ready = false) {
-    double* stats = reinterpret_cast<double*>(h->a("stats"));
-    if (training && !stats_ready) {
-        CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-        ST(ST_BN_STATS, 4.0 * M * C, launch_colstats(y, M, C, stats, st));
-    }
+    double* stats = bn_stats(h, bn);
+    if (training && !stats_ready) ST(ST_BN_STATS, 4.0 * M * C, launch_colstats(y, M, C, stats, st));
     return launch_bn_finalize(stats, M, C, h->w(bnname(bn, "gamma")), h->w(bnname(bn, "beta")), h->w(bnname(bn, "moving_mean")),
                               h->w(bnname(bn, "moving_variance")), kBnEps, kBnMomentum, training ? 1 : 0,
                               h->a(actbn(bn, "scale")), h->a(actbn(bn, "shift")), h->a(actbn(bn, "mean")), h->a(actbn(bn, "invstd")), st);
+}
+
+// hi/lo weight images of every tcgen05 GEMM of the step (forward ones; plus the dX ones when training), issued on `ss`
+int prep_images(crnn_handle* h, bool training, cudaStream_t ss) {
+    cudaStream_t st = ss;
+    if (h->gemm_simt) return CRNN_OK;
+    const int U = h->U, G = h->G;
+    for (int i = 2; i <= 7; ++i) {
+        const BlockPlan& b = kBlocks[i - 1];
+        const float* W = h->w(nm("conv2d_%d/kernel", i + 2));
+        ST(ST_MISC, 0, launch_prep_weight_images(W, b.cout, b.cout, b.cin, 1, h->a(nm("wimg_fwd%d", i)), ss));
+        if (training) ST(ST_MISC, 0, launch_prep_weight_images(W, b.cout, b.cin, b.cout, 0, h->a(nm("wimg_dx%d", i)), ss));
+    }
+    if (tc_ok(h, h->TD, h->FEAT)) ST(ST_MISC, 0, launch_prep_weight_images(h->w("dense1/kernel"), h->TD, h->TD, h->FEAT, 1, h->a("wimg_d1f"), ss));
+    if (training && tc_ok(h, h->FEAT, h->TD)) ST(ST_MISC, 0, launch_prep_weight_images(h->w("dense1/kernel"), h->TD, h->FEAT, h->TD, 0, h->a("wimg_d1b"), ss));
+    for (int layer = 1; layer <= 2; ++layer)
+        for (int d = 0; d < 2; ++d) {
+            const int kin = layer == 1 ? h->TD : U;
+            const float* W = h->w(h->rnn(layer, d) + "/kernel");
+            char nf[32], nb[32]; snprintf(nf, sizeof(nf), "wimg_r%d%df", layer, d); snprintf(nb, sizeof(nb), "wimg_r%d%db", layer, d);
+            if (tc_ok(h, G * U, kin)) ST(ST_MISC, 0, launch_prep_weight_images(W, G * U, G * U, kin, 1, h->a(nf), ss));
+            if (training && tc_ok(h, kin, G * U)) ST(ST_MISC, 0, launch_prep_weight_images(W, G * U, kin, G * U, 0, h->a(nb), ss));
+        }
+    return CRNN_OK;
 }
 
 int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed, cudaStream_t st) {
     if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
     const bool drop = training && seed != 0;
     const int H = h->H, W = h->W, U = h->U, G = h->G, T = h->T, V = h->V;
+    h->ev_used = 0;
+    // ---- side branch: weight images of all tensor-core GEMMs of this step (weights only change in the optimiser)
+    TRY(prep_images(h, training, side_after(h, st)));
+    if (training) CUDA_TRY(cudaMemsetAsync(h->a("stats"), 0, sizeof(double) * h->bn_off[15], st));
     // ---- STN (utils.py:247-258)
     ST(ST_STN, 0, launch_stn_trunk_fwd(x, h->w("conv2d_1/kernel"), h->w("conv2d_1/bias"), h->w("conv2d_2/kernel"), h->w("conv2d_2/bias"),
                              h->a("p1"), h->a("p2"), reinterpret_cast<int*>(h->a("p2arg")), h->a("flat"), B, H, W, st));
-    TRY(gemm_nn(h, ST_STN, h->a("flat"), h->sd.F, h->w("dense_1/kernel"), 50, h->a("loc_d1"), 50, B, 50, h->sd.F, h->w("dense_1/bias"), 1, nullptr, nullptr, st));
-    TRY(gemm_nn(h, ST_STN, h->a("loc_d1"), 50, h->w("dense_2/kernel"), 6, h->a("theta"), 6, B, 6, 50, h->w("dense_2/bias"), 0, nullptr, nullptr, st));
+    ST(ST_STN, 0, launch_stn_head_fwd(h->a("flat"), h->w("dense_1/kernel"), h->w("dense_1/bias"), h->w("dense_2/kernel"), h->w("dense_2/bias"),
+                                      h->a("loc_d1"), h->a("theta"), B, h->sd.F, st));
     ST(ST_STN, 0, launch_stn_sample_fwd(x, h->a("theta"), h->a("a0"), B, H, W, 2, st));
     // ---- depthwise-separable stack (utils.py:43-56, 64-70)
     const float* in = h->a("a0");
@@ -306,38 +392,43 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         const long long M = (long long)B * hh * ww;
         float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
         const bool dw_stats = training && (b.cin % 4 == 0);       // BN statistics of the depthwise output fused into the conv kernel
-        double* dstats = reinterpret_cast<double*>(h->a("stats"));
-        if (dw_stats) CUDA_TRY(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * b.cin, st));
-        ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st, dw_stats ? dstats : nullptr));
+        ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st,
+                                                         dw_stats ? bn_stats(h, 2 * i - 1) : nullptr));
         TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st, dw_stats));
         const bool tc = !h->gemm_simt && (b.cin % 32 == 0);
+        bool pw_stats = false;
         if (tc) {
-            float* img = h->a(nm("wimg_fwd%d", i));
-            ST(ST_MISC, 0, launch_prep_weight_images(h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cout, b.cin, 1, img, st));
-            double* stats = reinterpret_cast<double*>(h->a("stats"));
-            if (training) CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * b.cout, st));
-            ST(ST_GEMM_PW_FWD, 2.0 * M * b.cout * b.cin, launch_xw_gemm_tc(dw, b.cin, img, pw, b.cout, (int)M, b.cout, b.cin,
-                                                                          h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), training ? stats : nullptr, st));
+            if (i == 2) side_join(h, st);                          // the weight images are ready
+            ST(ST_GEMM_PW_FWD, 2.0 * M * b.cout * b.cin, launch_xw_gemm_tc(dw, b.cin, h->a(nm("wimg_fwd%d", i)), pw, b.cout, (int)M, b.cout, b.cin,
+                                                                          h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")),
+                                                                          training ? bn_stats(h, 2 * i) : nullptr, st));
+            pw_stats = true;
+        } else if (b.cin == 1) {                                   // block 1: the "GEMM" is an outer product
+            ST(ST_GEMM_PW_FWD, 2.0 * M * b.cout, launch_pw1_fwd(dw, h->a(actbn(1, "scale")), h->a(actbn(1, "shift")), h->w(nm("conv2d_%d/kernel", i + 2)), pw, M, b.cout,
+                                                                training ? bn_stats(h, 2 * i) : nullptr, st));
+            pw_stats = true;
         } else {
             TRY(gemm_nn(h, ST_GEMM_PW_FWD, dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
                         h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), st));
         }
-        TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st, tc));
+        TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st, pw_stats));
         ST(ST_ACT_POOL, 4.0 * M * b.cout * (1.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
-                                drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
+                                drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr));
         hh /= b.ph; ww /= b.pw; in = out;
     }
+    if (h->gemm_simt) side_join(h, st);
     // ---- dense1 (utils.py:72-75): (B,T,9,512) is already (B*T, 4608) with feature = w*512+c
     const int M = B * T;
-    if (tc_ok(h, h->TD, h->FEAT)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, 1, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, 0, st));
+    if (tc_ok(h, h->TD, h->FEAT)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->a("wimg_d1f"), h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, 0, st));
     else TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
-    if (drop) ST(ST_MISC, 0, launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st));
+    if (drop) ST(ST_MISC, 0, launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st, h->seed_ptr));
     // ---- two bidirectional recurrent layers (utils.py:77-82)
     const float* rin = h->a("dense1"); int kin = h->TD;
     for (int layer = 1; layer <= 2; ++layer) {
         float* xp = h->a(nm("xp%d", layer)); float* hs = h->a(nm("hs%d", layer));
         for (int d = 0; d < 2; ++d) {
-            if (tc_ok(h, G * U, kin)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, 1, xp + d * G * U, 2 * G * U, M, G * U, kin,
+            char nf[32]; snprintf(nf, sizeof(nf), "wimg_r%d%df", layer, d);
+            if (tc_ok(h, G * U, kin)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, rin, kin, h->a(nf), xp + d * G * U, 2 * G * U, M, G * U, kin,
                                                 h->w(h->rnn(layer, d) + "/bias"), 0, 0, st));
             else TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, rin, kin, h->w(h->rnn(layer, d) + "/kernel"), G * U, xp + d * G * U, 2 * G * U, M, G * U, kin,
                              h->w(h->rnn(layer, d) + "/bias"), 0, nullptr, nullptr, st));
@@ -353,8 +444,7 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
     }
     const float* head_in = h->a("hs2");                                                                      // merge_mode='concat'
     if (drop) {
-        CUDA_TRY(cudaMemcpyAsync(h->a("rnn2drop"), h->a("hs2"), sizeof(float) * (size_t)M * 2 * U, cudaMemcpyDeviceToDevice, st));
-        ST(ST_MISC, 0, launch_dropout_fwd(h->a("rnn2drop"), (long long)M * 2 * U, kDropRnn, seed, 9, st));
+        ST(ST_MISC, 0, launch_dropout_copy(h->a("hs2"), h->a("rnn2drop"), (long long)M * 2 * U, kDropRnn, seed, 9, st, h->seed_ptr));
         head_in = h->a("rnn2drop");
     }
     // ---- dense2 + softmax (utils.py:85-86)
@@ -363,9 +453,11 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
     return CRNN_OK;
 }
 
+// Recurrent layer backward.  Critical path (on st): BPTT kernel -> dX of the input projections.  Side branch: the three weight
+// gradients per direction + the bias column sums.
 int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const float* rin, int kin, float* dx /*(M,kin)*/, int B, cudaStream_t st) {
     const int U = h->U, G = h->G, T = h->T, M = B * T;
-    float* UT = h->a("UT"); float* dxp = h->a("dxp"); float* hprev = h->a("hprev"); float* rh = h->a("rh");
+    float* UT = h->a("UT"); float* dxp = h->a(nm("dxp%d", layer)); float* hprev = h->a(nm("hprev%d", layer)); float* rh = h->a(nm("rh%d", layer));
     const double bwork = 4.0 * B * T * 2 * (2 * U + h->GS * U + G * U + 2 * U);
     if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) {
         ST(ST_RNN_BWD, bwork, launch_gru_bwd_cluster(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
@@ -375,14 +467,15 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
             ST(ST_MISC, 0, launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
         ST(ST_RNN_BWD, bwork, launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
     }
+    cudaStream_t ss = side_after(h, st);
     for (int d = 0; d < 2; ++d) {
         const std::string base = h->rnn(layer, d);
         const float* dxd = dxp + d * G * U;
         float* gU = h->g(base + "/recurrent_kernel");
         const bool tc = !h->gemm_simt;
         auto dwgemm = [&](const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw) -> int {
-            if (tc) { ST(ST_GEMM_HEAD_BWD, 2.0 * M * Cin * Cout, launch_xty_gemm_tc(X, ldx, Cin, dY, ldy, Cout, dW, ldw, M, nullptr, nullptr, st)); return CRNN_OK; }
-            return gemm_tn(h, ST_GEMM_HEAD_BWD, X, ldx, dY, ldy, dW, ldw, Cin, Cout, M, nullptr, nullptr, st);
+            if (tc) { ST(ST_GEMM_HEAD_BWD, 2.0 * M * Cin * Cout, launch_xty_gemm_tc(X, ldx, Cin, dY, ldy, Cout, dW, ldw, M, nullptr, nullptr, ss)); return CRNN_OK; }
+            return gemm_tn(h, ST_GEMM_HEAD_BWD, X, ldx, dY, ldy, dW, ldw, Cin, Cout, M, nullptr, nullptr, ss);
         };
         if (h->cfg.cell == CRNN_CELL_GRU) {
             TRY(dwgemm(hprev + d * U, 2 * U, U, dxd, 2 * G * U, 2 * U, gU, G * U));
@@ -391,46 +484,59 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
             TRY(dwgemm(hprev + d * U, 2 * U, U, dxd, 2 * G * U, G * U, gU, G * U));
         }
         TRY(dwgemm(rin, kin, kin, dxd, 2 * G * U, G * U, h->g(base + "/kernel"), G * U));
-        ST(ST_MISC, 0, launch_colsum(dxd, M, G * U, 2 * G * U, h->g(base + "/bias"), st));
-        if (tc_ok(h, kin, G * U)) TRY(tc_xw(h, ST_GEMM_HEAD_BWD, dxd, 2 * G * U, h->w(base + "/kernel"), G * U, 0, dx, kin, M, kin, G * U, nullptr, 0, d, st));
+        ST(ST_MISC, 0, launch_colsum(dxd, M, G * U, 2 * G * U, h->g(base + "/bias"), ss));
+    }
+    for (int d = 0; d < 2; ++d) {
+        const std::string base = h->rnn(layer, d);
+        const float* dxd = dxp + d * G * U;
+        char nb[32]; snprintf(nb, sizeof(nb), "wimg_r%d%db", layer, d);
+        if (tc_ok(h, kin, G * U)) TRY(tc_xw(h, ST_GEMM_HEAD_BWD, dxd, 2 * G * U, h->a(nb), dx, kin, M, kin, G * U, nullptr, 0, d, st));
         else TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, dxd, 2 * G * U, h->w(base + "/kernel"), G * U, dx, kin, M, kin, G * U, d, st));
     }
     return CRNN_OK;
 }
 
-// backward of depthwise-separable block i: `cur` holds d(block output) on entry and is clobbered; d(block input) lands in `other`
+// Backward of depthwise-separable block i: `cur` holds d(block output) on entry, d(block input) lands in `other`.
+// Critical path (st): BN/ReLU6/pool backward -> dX GEMM -> BN/ReLU6 backward -> depthwise conv backward-data.
+// Side branch: pointwise dW GEMM and depthwise dW (they read the block's own dpw/ddw buffers, which nobody overwrites this step).
 int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* other, int B, bool drop, uint64_t seed, cudaStream_t st) {
-    double* red = reinterpret_cast<double*>(h->a("red"));
     const BlockPlan& b = kBlocks[i - 1];
     const long long Mi = (long long)B * hh * ww;
     const float* dw = h->a(nm("dw%d", i)); const float* pw = h->a(nm("pw%d", i));
+    float* dpw = h->a(nm("dpw%d", i)); float* ddw = h->a(nm("ddw%d", i));
     const int bn1 = 2 * i - 1, bn2 = 2 * i;
-    CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cout, st));
     ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (3.0 + 2.0 / (b.ph * b.pw)),
        launch_act_pool_bn_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
-                              h->w(bnname(bn2, "gamma")), other, red, h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")),
-                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st));
-    if (!h->gemm_simt && (b.cin % 4 == 0)) {
-        ST(ST_GEMM_PW_DW, 2.0 * Mi * b.cin * b.cout, launch_xty_gemm_tc(dw, b.cin, b.cin, other, b.cout, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, (int)Mi,
-                                                                       h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
+                              h->w(bnname(bn2, "gamma")), dpw, bn_red(h, bn2), h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")),
+                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr));
+    if (b.cin == 1) {
+        // block 1: dW[co] = sum_m f(x[m]) dY[m][co] and dX[m] = sum_co dY[m][co] W[co] in ONE pass over dY
+        ST(ST_GEMM_PW_DX, 4.0 * Mi * b.cout, launch_pw1_bwd(dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), dpw, h->w(nm("conv2d_%d/kernel", i + 2)),
+                                                            ddw, h->g(nm("conv2d_%d/kernel", i + 2)), Mi, b.cout, st));
     } else {
-        TRY(gemm_tn(h, ST_GEMM_PW_DW, dw, b.cin, other, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
-                    h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), st));
+        cudaStream_t ss = side_after(h, st);
+        if (!h->gemm_simt && (b.cin % 4 == 0)) {
+            ST(ST_GEMM_PW_DW, 2.0 * Mi * b.cin * b.cout, launch_xty_gemm_tc(dw, b.cin, b.cin, dpw, b.cout, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, (int)Mi,
+                                                                           h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), ss));
+        } else {
+            TRY(gemm_tn(h, ST_GEMM_PW_DW, dw, b.cin, dpw, b.cout, h->g(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, (int)Mi,
+                        h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), ss));
+        }
+        if (!h->gemm_simt && (b.cout % 32 == 0) && (b.cin % 4 == 0)) {
+            ST(ST_GEMM_PW_DX, 2.0 * Mi * b.cin * b.cout, launch_xw_gemm_tc(dpw, b.cout, h->a(nm("wimg_dx%d", i)), ddw, b.cin, (int)Mi, b.cin, b.cout, nullptr, nullptr, nullptr, st));
+        } else {
+            TRY(gemm_nt(h, ST_GEMM_PW_DX, dpw, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, ddw, b.cin, (int)Mi, b.cin, b.cout, 0, st));
+        }
     }
-    if (!h->gemm_simt && (b.cout % 32 == 0) && (b.cin % 4 == 0)) {
-        float* img = h->a(nm("wimg_dx%d", i));
-        ST(ST_MISC, 0, launch_prep_weight_images(h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, b.cin, b.cout, 0, img, st));
-        ST(ST_GEMM_PW_DX, 2.0 * Mi * b.cin * b.cout, launch_xw_gemm_tc(other, b.cout, img, cur, b.cin, (int)Mi, b.cin, b.cout, nullptr, nullptr, nullptr, st));
-    } else {
-        TRY(gemm_nt(h, ST_GEMM_PW_DX, other, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, cur, b.cin, (int)Mi, b.cin, b.cout, 0, st));
-    }
-    CUDA_TRY(cudaMemsetAsync(red, 0, sizeof(double) * 2 * b.cin, st));
     ST(ST_BN_BWD, 20.0 * Mi * b.cin,
-       launch_relu6_bn_bwd(cur, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                           h->w(bnname(bn1, "gamma")), cur, red, h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
+       launch_relu6_bn_bwd(ddw, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
     const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
-    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, cur, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, st));
-    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(cur, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
+    {
+        cudaStream_t ss = side_after(h, st);
+        ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, ddw, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, ss));
+    }
+    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
     return CRNN_OK;
 }
 
@@ -439,27 +545,35 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     const bool drop = seed != 0;
     const int U = h->U, T = h->T, V = h->V, M = B * T;
     CUDA_TRY(cudaMemsetAsync(h->f("arena/grads"), 0, sizeof(float) * (size_t)h->n_params, st));
+    CUDA_TRY(cudaMemsetAsync(h->a("red"), 0, sizeof(double) * h->bn_off[15], st));
     // ---- CTC (utils.py:98-103); mean over the batch (identity Keras loss, train.py:192) => scale 1/B
     ST(ST_CTC, 0, launch_ctc_loss_grad(h->a("softmax"), 2, labels, h->cfg.max_len, label_len, input_len, B, T, V, kKerasEps, loss, nullptr,
                              h->a("dlogits"), 1.f / (float)B, reinterpret_cast<int*>(h->a("status")), st));
     float* gA = h->a("gA"); float* gB = h->a("gB");
     // ---- dense2
     const float* head_in = drop ? h->a("rnn2drop") : h->a("hs2");
-    TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, head_in, 2 * U, h->a("dlogits"), V, h->g("dense2/kernel"), V, 2 * U, V, M, nullptr, nullptr, st));
-    ST(ST_MISC, 0, launch_colsum(h->a("dlogits"), M, V, V, h->g("dense2/bias"), st));
+    {
+        cudaStream_t ss = side_after(h, st);
+        TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, head_in, 2 * U, h->a("dlogits"), V, h->g("dense2/kernel"), V, 2 * U, V, M, nullptr, nullptr, ss));
+        ST(ST_MISC, 0, launch_colsum(h->a("dlogits"), M, V, V, h->g("dense2/bias"), ss));
+    }
     TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, h->a("dlogits"), V, h->w("dense2/kernel"), V, gA, 2 * U, M, 2 * U, V, 0, st));
-    if (drop) ST(ST_MISC, 0, launch_dropout_fwd(gA, (long long)M * 2 * U, kDropRnn, seed, 9, st));
+    if (drop) ST(ST_MISC, 0, launch_dropout_fwd(gA, (long long)M * 2 * U, kDropRnn, seed, 9, st, h->seed_ptr));
     // ---- recurrent layers
     TRY(rnn_backward(h, 2, gA, h->a("rnn1"), U, gB, B, st));            // gB = d rnn1 (M,U)
     ST(ST_MISC, 0, launch_dup_dirs(gB, gA, M, U, st));                              // 'sum' merge: same gradient to both directions
-    TRY(rnn_backward(h, 1, gA, h->a("dense1"), h->TD, gB, B, st));      // gB = d dense1 (M,TD)
+    float* dd = h->a("ddense1");                                         // own buffer: the side branch reads it while gB is recycled
+    TRY(rnn_backward(h, 1, gA, h->a("dense1"), h->TD, dd, B, st));       // dd = d dense1 (M,TD)
     // ---- dense1
-    ST(ST_MISC, 0, launch_relu_dropout_bwd(gB, h->a("dense1"), (long long)M * h->TD, drop ? kDropDense1 : 0.f, seed, 8, st));
-    if (!h->gemm_simt) ST(ST_GEMM_HEAD_BWD, 2.0 * M * h->FEAT * h->TD, launch_xty_gemm_tc(h->a("block7"), h->FEAT, h->FEAT, gB, h->TD, h->TD, h->g("dense1/kernel"), h->TD, M, nullptr, nullptr, st));
-    else TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, h->a("block7"), h->FEAT, gB, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, st));
-    ST(ST_MISC, 0, launch_colsum(gB, M, h->TD, h->TD, h->g("dense1/bias"), st));
-    if (tc_ok(h, h->FEAT, h->TD)) TRY(tc_xw(h, ST_GEMM_HEAD_BWD, gB, h->TD, h->w("dense1/kernel"), h->TD, 0, gA, h->FEAT, M, h->FEAT, h->TD, nullptr, 0, 0, st));
-    else TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, gB, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
+    ST(ST_MISC, 0, launch_relu_dropout_bwd(dd, h->a("dense1"), (long long)M * h->TD, drop ? kDropDense1 : 0.f, seed, 8, st));
+    {
+        cudaStream_t ss = side_after(h, st);
+        if (!h->gemm_simt) ST(ST_GEMM_HEAD_BWD, 2.0 * M * h->FEAT * h->TD, launch_xty_gemm_tc(h->a("block7"), h->FEAT, h->FEAT, dd, h->TD, h->TD, h->g("dense1/kernel"), h->TD, M, nullptr, nullptr, ss));
+        else TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, h->a("block7"), h->FEAT, dd, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, ss));
+        ST(ST_MISC, 0, launch_colsum(dd, M, h->TD, h->TD, h->g("dense1/bias"), ss));
+    }
+    if (tc_ok(h, h->FEAT, h->TD)) TRY(tc_xw(h, ST_GEMM_HEAD_BWD, dd, h->TD, h->a("wimg_d1b"), gA, h->FEAT, M, h->FEAT, h->TD, nullptr, 0, 0, st));
+    else TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, dd, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
     // ---- conv stack, reverse
     float* cur = gA; float* other = gB;
     int dims_h[8], dims_w[8];
@@ -472,15 +586,63 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     // ---- STN: sampler -> theta -> localisation net
     CUDA_TRY(cudaMemsetAsync(h->a("dtheta"), 0, sizeof(float) * 6 * B, st));
     ST(ST_STN_BWD, 0, launch_stn_sample_bwd(x, h->a("theta"), cur, h->a("dtheta"), B, h->H, h->W, 2, st));
-    TRY(gemm_tn(h, ST_STN_BWD, h->a("loc_d1"), 50, h->a("dtheta"), 6, h->g("dense_2/kernel"), 6, 50, 6, B, nullptr, nullptr, st));
-    ST(ST_STN_BWD, 0, launch_colsum(h->a("dtheta"), B, 6, 6, h->g("dense_2/bias"), st));
-    TRY(gemm_nt(h, ST_STN_BWD, h->a("dtheta"), 6, h->w("dense_2/kernel"), 6, h->a("dd1"), 50, B, 50, 6, 0, st));
-    ST(ST_STN_BWD, 0, launch_relu_dropout_bwd(h->a("dd1"), h->a("loc_d1"), (long long)B * 50, 0.f, 0, 0, st));
-    TRY(gemm_tn(h, ST_STN_BWD, h->a("flat"), h->sd.F, h->a("dd1"), 50, h->g("dense_1/kernel"), 50, h->sd.F, 50, B, nullptr, nullptr, st));
-    ST(ST_STN_BWD, 0, launch_colsum(h->a("dd1"), B, 50, 50, h->g("dense_1/bias"), st));
-    TRY(gemm_nt(h, ST_STN_BWD, h->a("dd1"), 50, h->w("dense_1/kernel"), 50, h->a("dflat"), h->sd.F, B, h->sd.F, 50, 0, st));
+    // critical path: dd1 = relu'(loc_d1) * (dtheta @ W2^T), dflat = dd1 @ W1^T in one kernel; parameter gradients on the side branch
+    ST(ST_STN_BWD, 0, launch_stn_head_bwd(h->a("dtheta"), h->a("loc_d1"), h->w("dense_1/kernel"), h->w("dense_2/kernel"), h->a("dd1"), h->a("dflat"), B, h->sd.F, st));
+    {
+        cudaStream_t ss = side_after(h, st);
+        TRY(gemm_tn(h, ST_STN_BWD, h->a("loc_d1"), 50, h->a("dtheta"), 6, h->g("dense_2/kernel"), 6, 50, 6, B, nullptr, nullptr, ss));
+        ST(ST_STN_BWD, 0, launch_colsum(h->a("dtheta"), B, 6, 6, h->g("dense_2/bias"), ss));
+        TRY(gemm_tn(h, ST_STN_BWD, h->a("flat"), h->sd.F, h->a("dd1"), 50, h->g("dense_1/kernel"), 50, h->sd.F, 50, B, nullptr, nullptr, ss));
+        ST(ST_STN_BWD, 0, launch_colsum(h->a("dd1"), B, 50, 50, h->g("dense_1/bias"), ss));
+    }
     ST(ST_STN_BWD, 0, launch_stn_trunk_bwd(h->a("dflat"), h->a("p1"), h->a("p2"), reinterpret_cast<const int*>(h->a("p2arg")), h->w("conv2d_2/kernel"),
                              h->g("conv2d_1/kernel"), h->g("conv2d_1/bias"), h->g("conv2d_2/kernel"), h->g("conv2d_2/bias"), nullptr, B, h->H, h->W, st));
+    side_join(h, st);
+    return CRNN_OK;
+}
+
+// Runs `body(stream)` -- a fixed launch sequence over workspace buffers -- through a CUDA graph: the first call with a given
+// (kind, batch, buffer pointers, dropout on/off) runs eagerly (lazy kernel attributes get configured), the second is captured on
+// the handle's private capture stream and instantiated, every later one is a single cudaGraphLaunch on the caller's stream.
+// The only per-step scalar, the dropout seed, lives in device memory ("act/seed") and is refreshed before each launch.
+template <class F>
+int run_graphed(crnn_handle* h, int kind, int B, const void* const (&ptrs)[6], int drop, uint64_t seed, cudaStream_t st, F&& body) {
+    if (!h->use_graph || h->prof.on || !h->cap) { h->seed_ptr = nullptr; return body(st); }
+    crnn_handle::StepGraph* g = nullptr;
+    for (auto& e : h->graphs)
+        if (e.kind == kind && e.B == B && e.drop == drop && !memcmp(e.p, ptrs, sizeof(e.p))) { g = &e; break; }
+    if (!g) {
+        if (h->graphs.size() >= 16) {   // callers that pass fresh buffers every step would otherwise re-capture forever
+            for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+            h->graphs.clear();
+        }
+        crnn_handle::StepGraph e; e.kind = kind; e.B = B; e.drop = drop; e.calls = 0; e.exec = nullptr; e.launches = 0;
+        memcpy(e.p, ptrs, sizeof(e.p));
+        h->graphs.push_back(e); g = &h->graphs.back();
+    }
+    uint64_t* seed_dev = reinterpret_cast<uint64_t*>(h->a("seed"));
+    if (!g->exec) {
+        if (g->calls <= 0) { if (g->calls == 0) g->calls = 1; h->seed_ptr = nullptr; return body(st); }   // first call (or capture disabled: -1)
+        const long long l0 = g_crnn_launches;
+        CUDA_TRY(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
+        h->seed_ptr = seed_dev;
+        const int rc = body(h->cap);
+        h->seed_ptr = nullptr;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
+        g->launches = g_crnn_launches - l0; g_crnn_launches = l0;
+        cudaError_t ie = cudaSuccess;
+        if (rc == CRNN_OK && ce == cudaSuccess && graph) ie = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != CRNN_OK) { g->calls = -1; cudaGetLastError(); return rc; }
+        if (ce != cudaSuccess || ie != cudaSuccess || !g->exec) {   // could not capture: stay eager for this key
+            g->calls = -1; g->exec = nullptr; cudaGetLastError();
+            return body(st);
+        }
+    }
+    if (drop) TRY(launch_set_u64(seed_dev, seed, st));
+    CUDA_TRY(cudaGraphLaunch(g->exec, st));
+    g_crnn_launches += g->launches;
     return CRNN_OK;
 }
 }  // namespace
@@ -507,10 +669,23 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_RNN_V1"); h->rnn_v1 = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
+    { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
+    { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
+    if (cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking) != cudaSuccess) { h->cap = nullptr; cudaGetLastError(); }
     *out = h;
     return CRNN_OK;
 }
-int crnn_destroy(crnn_handle* h) { delete h; return CRNN_OK; }
+int crnn_destroy(crnn_handle* h) {
+    if (!h) return CRNN_OK;
+    for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+    for (auto e : h->evs) cudaEventDestroy(e);
+    for (auto e : h->prof.pool) cudaEventDestroy(e);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->cap) cudaStreamDestroy(h->cap);
+    delete h;
+    return CRNN_OK;
+}
 int crnn_num_tensors(const crnn_handle* h) { return h ? (int)h->L.tensors.size() : 0; }
 const char* crnn_tensor_name(const crnn_handle* h, int i) { return (h && i >= 0 && i < (int)h->L.tensors.size()) ? h->L.tensors[i].name.c_str() : nullptr; }
 int crnn_tensor_lookup(const crnn_handle* h, const char* name, crnn_tensor_info* out) {
@@ -522,20 +697,26 @@ int crnn_tensor_lookup(const crnn_handle* h, const char* name, crnn_tensor_info*
     return CRNN_OK;
 }
 
+static int forward_graphed(crnn_handle* h, const float* x_dev, int B, float* softmax_dev, cudaStream_t st) {
+    if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
+    const void* const key[6] = {x_dev, softmax_dev, nullptr, nullptr, nullptr, nullptr};
+    return run_graphed(h, 0, B, key, 0, 0, st, [&](cudaStream_t s) -> int {
+        TRY(forward(h, x_dev, B, false, 0, s));
+        if (softmax_dev && softmax_dev != h->a("softmax"))
+            CUDA_TRY(cudaMemcpyAsync(softmax_dev, h->a("softmax"), sizeof(float) * (size_t)B * h->T * h->V, cudaMemcpyDeviceToDevice, s));
+        return CRNN_OK;
+    });
+}
 int crnn_forward(crnn_handle* h, const float* x_dev, int B, float* softmax_dev, void* stream) {
     if (!h || !x_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TRY(forward(h, x_dev, B, false, 0, st));
-    if (softmax_dev && softmax_dev != h->a("softmax"))
-        CUDA_TRY(cudaMemcpyAsync(softmax_dev, h->a("softmax"), sizeof(float) * (size_t)B * h->T * h->V, cudaMemcpyDeviceToDevice, st));
-    return CRNN_OK;
+    return forward_graphed(h, x_dev, B, softmax_dev, static_cast<cudaStream_t>(stream));
 }
 int crnn_forward_host(crnn_handle* h, const float* x_host, int B, float* softmax_host, void* stream) {
     if (!h || !x_host || !softmax_host) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
     if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaMemcpyAsync(h->a("x"), x_host, sizeof(float) * (size_t)B * h->H * h->W, cudaMemcpyHostToDevice, st));
-    TRY(forward(h, h->a("x"), B, false, 0, st));
+    TRY(forward_graphed(h, h->a("x"), B, nullptr, st));
     CUDA_TRY(cudaMemcpyAsync(softmax_host, h->a("softmax"), sizeof(float) * (size_t)B * h->T * h->V, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return CRNN_OK;
@@ -544,9 +725,14 @@ int crnn_forward_host(crnn_handle* h, const float* x_host, int B, float* softmax
 int crnn_train_fwd_bwd(crnn_handle* h, const float* x_dev, const int32_t* labels_dev, const int32_t* label_len_dev,
                        const int32_t* input_len_dev, int B, float* loss_dev, uint64_t dropout_seed, void* stream) {
     if (!h || !x_dev || !labels_dev || !label_len_dev || !input_len_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TRY(forward(h, x_dev, B, true, dropout_seed, st));
-    return backward(h, x_dev, labels_dev, label_len_dev, input_len_dev, B, loss_dev ? loss_dev : h->a("loss"), dropout_seed, st);
+    float* loss = loss_dev ? loss_dev : h->a("loss");
+    const void* const key[6] = {x_dev, labels_dev, label_len_dev, input_len_dev, loss, nullptr};
+    return run_graphed(h, 1, B, key, dropout_seed != 0, dropout_seed, st, [&](cudaStream_t s) -> int {
+        TRY(forward(h, x_dev, B, true, dropout_seed, s));
+        return backward(h, x_dev, labels_dev, label_len_dev, input_len_dev, B, loss, dropout_seed, s);
+    });
 }
 
 int crnn_adam_step(crnn_handle* h, float lr, float b1, float b2, float eps, float clipnorm, float grad_scale, void* stream) {
@@ -648,8 +834,11 @@ int crnn_debug_block_backward(crnn_handle* h, int block, const float* dout_dev, 
     const BlockPlan& b = kBlocks[block - 1];
     const size_t n_out = (size_t)B * (hh / b.ph) * (ww / b.pw) * b.cout, n_in = (size_t)B * hh * ww * b.cin;
     CUDA_TRY(cudaMemsetAsync(h->f("arena/grads"), 0, sizeof(float) * (size_t)h->n_params, st));
+    CUDA_TRY(cudaMemsetAsync(h->a("red"), 0, sizeof(double) * h->bn_off[15], st));
     CUDA_TRY(cudaMemcpyAsync(h->a("gA"), dout_dev, sizeof(float) * n_out, cudaMemcpyDeviceToDevice, st));
+    h->ev_used = 0;
     TRY(block_backward(h, block, hh, ww, h->a("gA"), h->a("gB"), B, dropout_seed != 0, dropout_seed, st));
+    side_join(h, st);
     CUDA_TRY(cudaMemcpyAsync(din_dev, h->a("gB"), sizeof(float) * n_in, cudaMemcpyDeviceToDevice, st));
     return CRNN_OK;
 }

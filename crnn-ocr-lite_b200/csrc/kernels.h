@@ -49,12 +49,13 @@ int launch_bn_finalize(const double* stats, long long M, int C, const float* gam
                        float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);
 // a = dropout(pool(relu6(y*scale+shift)))  ; pool (ph,pw) in {(1,1),(2,2),(1,2)}
 int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C,
-                        int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+                        int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr = nullptr);
 // fused (ReLU6 + MaxPool + Dropout) backward + BatchNorm-train backward, two passes over (da, y), no dz round trip:
 //   dz = unpool(da*dropmask) * 1[0<=z<=6];  dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dgamma += sum(dz*xhat), dbeta += sum(dz)
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red /*pre-zeroed [2C]*/, float* dgamma, float* dbeta,
-                           int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+                           int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st,
+                           const uint64_t* seed_ptr = nullptr);
 // same for the BN after the depthwise conv (no pool / dropout); dy may alias da
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                         const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
@@ -64,7 +65,15 @@ int launch_bn_bwd_apply(float* dz_inout, const float* y, const double* red, cons
 // misc elementwise
 int launch_colsum(const float* y, long long M, int C, int ldy, float* out, cudaStream_t st);            // out[c] = sum_m y[m][c]
 int launch_relu_dropout_bwd(float* g_inout, const float* act, long long n, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
-int launch_dropout_fwd(float* x_inout, long long n, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st);
+// seed_ptr (optional): device location of the step's dropout seed (CUDA-graph replay); overrides `seed` when non-null
+int launch_dropout_fwd(float* x_inout, long long n, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr = nullptr);
+int launch_dropout_copy(const float* in, float* out, long long n, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr = nullptr);
+int launch_set_u64(uint64_t* p, uint64_t v, cudaStream_t st);
+// block 1 of the conv stack (Cin = 1): the pointwise conv is an outer product out[m][co] = f(x[m]) * w[co], f = relu6(x*scale+shift).
+// stats (optional, pre-zeroed double[2*Cout]) receives the per-channel sum / sum of squares of out.
+int launch_pw1_fwd(const float* x, const float* scale, const float* shift, const float* w, float* out, long long M, int Cout, double* stats, cudaStream_t st);
+// its backward in one pass over dY: dX[m] = sum_co dY[m][co] w[co];  dW[co] += sum_m f(x[m]) dY[m][co]
+int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const float* dY, const float* w, float* dX, float* dW, long long M, int Cout, cudaStream_t st);
 int launch_sum_dirs(const float* hs, float* out, long long rows, int U, cudaStream_t st);               // out[r][u] = hs[r][0][u]+hs[r][1][u]
 int launch_dup_dirs(const float* g, float* out, long long rows, int U, cudaStream_t st);                // out[r][d][u] = g[r][u]
 int launch_softmax_rows(const float* z, float* p, long long rows, int V, cudaStream_t st);
@@ -78,6 +87,10 @@ int launch_stn_trunk_fwd(const float* x, const float* k1, const float* b1, const
                          float* p1, float* p2, int* p2arg, float* flat, int B, int H, int W, cudaStream_t st);
 int launch_stn_trunk_bwd(const float* dflat, const float* p1, const float* p2, const int* p2arg, const float* k2,
                          float* dk1, float* db1, float* dk2, float* db2, float* scratch_dc1, int B, int H, int W, cudaStream_t st);
+// localisation head: loc_d1 = relu(flat @ W1 + b1) (B,50); theta = loc_d1 @ W2 + b2 (B,6)      (utils.py:253-256)
+int launch_stn_head_fwd(const float* flat, const float* W1, const float* b1, const float* W2, const float* b2, float* loc_d1, float* theta, int B, int F, cudaStream_t st);
+// its data gradient: dd1 = 1[loc_d1 > 0] * (dtheta @ W2^T) (B,50); dflat = dd1 @ W1^T (B,F)
+int launch_stn_head_bwd(const float* dtheta, const float* loc_d1, const float* W1, const float* W2, float* dd1, float* dflat, int B, int F, cudaStream_t st);
 // sampler: x (B,H,W), theta (B,6) -> padded out (B,H+2*pad,W+2*pad) (border zeroed)
 int launch_stn_sample_fwd(const float* x, const float* theta, float* out, int B, int H, int W, int pad, cudaStream_t st);
 int launch_stn_sample_bwd(const float* x, const float* theta, const float* dout_padded, float* dtheta, int B, int H, int W, int pad, cudaStream_t st);

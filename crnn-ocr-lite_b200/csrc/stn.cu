@@ -223,6 +223,66 @@ __global__ void stn_sample_bwd_kernel(const float* __restrict__ x, const float* 
         atomicAdd(dtheta + (size_t)b * 6 + threadIdx.x, s);
     }
 }
+// ---- localisation head (utils.py:253-256): Dense(50) -> relu -> Dense(6).  One CTA per image, 512 threads = 8 k-slices x 64 unit
+// lanes (50 active); the 6-wide second layer runs on the relu'd row while it is still in shared memory.
+constexpr int ND1 = 50, NTH = 6;
+__global__ void __launch_bounds__(512)
+stn_head_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                    const float* __restrict__ b2, float* __restrict__ loc_d1, float* __restrict__ theta, int F)
+{
+    extern __shared__ float hsm[];            // flat row [F] | partial [8][64] | d1 [64]
+    float* row = hsm; float* part = row + F; float* d1 = part + 8 * 64;
+    const int b = blockIdx.x, tid = threadIdx.x, n = tid & 63, ks = tid >> 6;
+    for (int k = tid; k < F; k += 512) row[k] = __ldg(flat + (size_t)b * F + k);
+    __syncthreads();
+    float acc = 0.f;
+    if (n < ND1) {
+        const int per = (F + 7) / 8, k0 = ks * per, k1 = min(F, k0 + per);
+#pragma unroll 4
+        for (int k = k0; k < k1; ++k) acc = fmaf(row[k], __ldg(W1 + (size_t)k * ND1 + n), acc);
+    }
+    part[ks * 64 + n] = acc;
+    __syncthreads();
+    if (tid < 64) {
+        float v = 0.f;
+        if (tid < ND1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v += part[i * 64 + tid];
+            v = fmaxf(v + __ldg(b1 + tid), 0.f);
+            loc_d1[(size_t)b * ND1 + tid] = v;
+        }
+        d1[tid] = v;
+    }
+    __syncthreads();
+    if (tid < NTH) {
+        float v = __ldg(b2 + tid);
+        for (int i = 0; i < ND1; ++i) v = fmaf(d1[i], __ldg(W2 + i * NTH + tid), v);
+        theta[(size_t)b * NTH + tid] = v;
+    }
+}
+// data gradient of the head: dd1 = 1[loc_d1 > 0] * (dtheta @ W2^T); dflat = dd1 @ W1^T (one CTA per image)
+__global__ void __launch_bounds__(256)
+stn_head_bwd_kernel(const float* __restrict__ dtheta, const float* __restrict__ loc_d1, const float* __restrict__ W1, const float* __restrict__ W2,
+                    float* __restrict__ dd1, float* __restrict__ dflat, int F)
+{
+    __shared__ float g[ND1];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid < ND1) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < NTH; ++j) v = fmaf(__ldg(dtheta + (size_t)b * NTH + j), __ldg(W2 + tid * NTH + j), v);
+        v = __ldg(loc_d1 + (size_t)b * ND1 + tid) > 0.f ? v : 0.f;
+        g[tid] = v; dd1[(size_t)b * ND1 + tid] = v;
+    }
+    __syncthreads();
+    for (int k = tid; k < F; k += 256) {
+        const float* wr = W1 + (size_t)k * ND1;
+        float v = 0.f;
+#pragma unroll 10
+        for (int i = 0; i < ND1; ++i) v = fmaf(g[i], __ldg(wr + i), v);
+        dflat[(size_t)b * F + k] = v;
+    }
+}
 }  // namespace
 
 int launch_stn_trunk_fwd(const float* x, const float* k1, const float* b1, const float* k2, const float* b2,
@@ -259,4 +319,21 @@ int launch_stn_sample_bwd(const float* x, const float* theta, const float* dout,
     dim3 grid(ceil_div((long long)H * W, 256 * 4), B);
     stn_sample_bwd_kernel<<<grid, 256, 0, st>>>(x, theta, dout, dtheta, H, W, pad);
     LAUNCH_CHECK(); return CRNN_OK;
+}
+
+int launch_stn_head_fwd(const float* flat, const float* W1, const float* b1, const float* W2, const float* b2, float* loc_d1, float* theta, int B, int F, cudaStream_t st)
+{
+    if (B <= 0) return CRNN_OK;
+    const size_t smem = sizeof(float) * ((size_t)F + 8 * 64 + 64);
+    if (smem > 48 * 1024) { crnn_set_error("stn_head: flatten size %d too large", F); return CRNN_ERR_INVALID; }
+    stn_head_fwd_kernel<<<B, 512, smem, st>>>(flat, W1, b1, W2, b2, loc_d1, theta, F);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
+int launch_stn_head_bwd(const float* dtheta, const float* loc_d1, const float* W1, const float* W2, float* dd1, float* dflat, int B, int F, cudaStream_t st)
+{
+    if (B <= 0) return CRNN_OK;
+    stn_head_bwd_kernel<<<B, 256, 0, st>>>(dtheta, loc_d1, W1, W2, dd1, dflat, F);
+    LAUNCH_CHECK();
+    return CRNN_OK;
 }

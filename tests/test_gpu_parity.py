@@ -441,3 +441,48 @@ def test_dropout_statistics(cb):
     g1 = m.get_grads()["dense2/kernel"].copy()
     m.train_fwd_bwd_device(*args, dropout_seed=12345)      # stateless masks: same seed -> same step
     np.testing.assert_allclose(m.get_grads()["dense2/kernel"], g1, rtol=1e-4, atol=1e-6)
+
+
+def test_graph_replay_matches_eager(cb):
+    """The train step / predictor forward are replayed from a CUDA graph from the third call with the same buffers on
+    (csrc/engine.cu run_graphed); the replay must reproduce the eager launch sequence, including the per-step dropout seed
+    that the graph reads from device memory."""
+    cfg = N.Cfg(imgh=100)
+    B = 4
+    w, m = _make(cb, cfg, B, 5)
+    x, lab, L, il = N.synth_batch(cfg, B, 55)
+    d = "cuda"
+    args = (torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d))
+
+    def step(seed):
+        per = m.train_fwd_bwd_device(*args, dropout_seed=seed).cpu().numpy().copy()
+        g = m.get_grads()
+        return per, {k: g[k].copy() for k in ("dense2/kernel", "conv2d_5/kernel", "depthwise_conv2d_2/depthwise_kernel", "conv2d_1/kernel",
+                                              "bidirectional_1/forward_gru_1/recurrent_kernel", "batch_normalization_3/gamma", "dense_1/kernel")}, m.activation("block1").copy()
+
+    def close(a, b):
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-5, atol=1e-5)
+        for k in a[1]:
+            sc = np.abs(a[1][k]).max() + 1e-12
+            assert np.abs(a[1][k] - b[1][k]).max() / sc < 2e-3, k      # atomics: run-to-run summation order
+    for seeds in ((0, 0, 0, 0), (111, 222, 111, 222)):
+        r = [step(s) for s in seeds]     # call 1 eager, call 2 captured + launched, calls 3.. replayed
+        close(r[0], r[2])
+        close(r[1], r[3])
+        if seeds[0]:
+            np.testing.assert_array_equal(r[0][2], r[2][2])          # same seed -> same masks (eager vs replay)
+            np.testing.assert_array_equal(r[1][2], r[3][2])
+            assert (r[0][2] != r[1][2]).mean() > 0.01                  # different seed -> different masks under replay
+        else:
+            close(r[0], r[1])
+    # the optimiser step between replays changes the weights the graph reads (same buffers): losses must move
+    m.compile(optimizer=cb.Adam(lr=1e-2, beta_1=0.5, beta_2=0.999, epsilon=1e-7, clipnorm=5.0))
+    l0 = step(0)[0]
+    m.optimizer_step()
+    l1 = step(0)[0]
+    assert np.abs(l1 - l0).max() > 1e-4
+    sm = [m.predict_on_batch(x) for _ in range(4)]
+    for s in sm[1:]:
+        np.testing.assert_array_equal(s, sm[0])
+    ref = N.forward(N.to_torch(m.get_weights()), torch.tensor(x), cfg, training=False)["softmax"].numpy()
+    _cmp("softmax(graph)", sm[3], ref, 3e-4)
