@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_vec4_w4(const float* __restrict
 // PY lanes, one fp64 atomic pair per channel and CTA) -- the separate colstats pass over the depthwise output is gone.
 template <bool FLIP, bool STATS>
 __global__ void __launch_bounds__(256) dwconv3x3_cb_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
-                                                           int H, int W, int C4, int WG, int ngroups, double* __restrict__ stats)
+                                                           int H, int W, int C4, int WG, int ngroups, double* __restrict__ stats, int rev)
 {
     extern __shared__ double dsm[];   // STATS: [PY][8][CQ]
     const int CQ = blockDim.x, PY = blockDim.y;
@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) dwconv3x3_cb_kernel(const float* __restri
 #pragma unroll
         for (int q = 0; q < 9; ++q) kv[q] = ldg4(k + (size_t)q * C + c4 * 4);
         const int gstride = gridDim.y * PY;
-        for (int g = blockIdx.y * PY + threadIdx.y; g < ngroups; g += gstride) {
+        for (int g0 = blockIdx.y * PY + threadIdx.y; g0 < ngroups; g0 += gstride) {
+            const int g = rev ? ngroups - 1 - g0 : g0;
             const int rowi = g / WG, wg = g - rowi * WG;         // rowi = b*H + h
             const int h = rowi % H;
             const int w0 = wg * 4;
@@ -329,7 +330,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double M, i
 template <int PH, int PW>
 __global__ void __launch_bounds__(256) act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                     float* __restrict__ a, int W, int C4, int Wo, int npix,
-                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr)
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr, int rev)
 {
     const int CQ = blockDim.x, PY = blockDim.y;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
@@ -339,7 +340,8 @@ __global__ void __launch_bounds__(256) act_pool_fwd_kernel(const float* __restri
     const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
     const int pstride = gridDim.y * PY;
 #pragma unroll 2
-    for (int p = blockIdx.y * PY + threadIdx.y; p < npix; p += pstride) {
+    for (int p0 = blockIdx.y * PY + threadIdx.y; p0 < npix; p0 += pstride) {
+        const int p = rev ? npix - 1 - p0 : p0;                          // serpentine traversal (see engine.cu): start where the producer ended
         const int row = p / Wo, wo = p - row * Wo;                       // row = b*Ho + ho; input row = row*PH because H = Ho*PH
         const float* src = y + ((size_t)(row * PH) * W + wo * PW) * C + c4 * 4;
         float4 v[PH * PW];
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
                                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, float* __restrict__ dy, double* __restrict__ red,
                                     int B, int H, int W, int C4, double invM,
-                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix_ll, const uint64_t* __restrict__ seed_ptr)
+                                    float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix_ll, const uint64_t* __restrict__ seed_ptr, int rev)
 {
     extern __shared__ float sred[];   // [PY][8][CQ]
     if (seed_ptr) seed = *seed_ptr;
@@ -396,7 +398,8 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
         }
         const int pstride = gridDim.y * PY;
 #pragma unroll 2
-        for (int p = blockIdx.y * PY + threadIdx.y; p < npix; p += pstride) {
+        for (int p0 = blockIdx.y * PY + threadIdx.y; p0 < npix; p0 += pstride) {
+            const int p = rev ? npix - 1 - p0 : p0;
             const int row = p / Wo, wo = p - row * Wo;       // row = b*Ho + ho; input row = row*ph because H = Ho*ph
             const size_t oidx = (size_t)p * C4 + c4;
             float g[4];
@@ -514,7 +517,7 @@ __global__ void relu6_bwd_scalar_kernel(const float* da /* may alias dy */, cons
 template <bool APPLY>
 __global__ void __launch_bounds__(256) relu6_bwd_kernel(const float* da /* may alias dy */, const float* __restrict__ y, const float* __restrict__ scale,
                                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                 const float* __restrict__ gamma, float* dy, double* __restrict__ red, long long M, int C4, double invM)
+                                 const float* __restrict__ gamma, float* dy, double* __restrict__ red, long long M, int C4, double invM, int rev)
 {
     extern __shared__ float sred[];   // [PY][8][CQ]
     const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
@@ -534,7 +537,8 @@ __global__ void __launch_bounds__(256) relu6_bwd_kernel(const float* da /* may a
         for (long long m = blockIdx.y * (long long)PY + threadIdx.y; m < M; m += 2 * stride) {
             const long long m2r = m + stride;
             const bool two = m2r < M;
-            const size_t o0 = ((size_t)m * C4 + c4) * 4, o1 = ((size_t)(two ? m2r : m) * C4 + c4) * 4;
+            const long long ma = rev ? M - 1 - m : m, mb = two ? (rev ? M - 1 - m2r : m2r) : ma;
+            const size_t o0 = ((size_t)ma * C4 + c4) * 4, o1 = ((size_t)mb * C4 + c4) * 4;
             const float4 y0 = ldg4(y + o0), y1 = ldg4(y + o1);
             const float4 d0 = *reinterpret_cast<const float4*>(da + o0), d1 = *reinterpret_cast<const float4*>(da + o1);
             const float yv[2][4] = {{y0.x, y0.y, y0.z, y0.w}, {y1.x, y1.y, y1.z, y1.w}};
@@ -622,14 +626,15 @@ __global__ void dropout_kernel(const float* in, float* x, long long n, float rat
 // blockDim = 256 = 16 pixel lanes x 16 channel quads (Cout = 64); a warp covers 2 pixels x 64 channels = 2 x 256 B contiguous.
 // BN statistics of the output in closed form: sum_m f_m w_c = w_c * S1, sum_m (f_m w_c)^2 = w_c^2 * S2 (S1, S2 accumulated in double per CTA).
 __global__ void __launch_bounds__(256) pw1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                                                      const float* __restrict__ w, float* __restrict__ out, int M, int C4, double* __restrict__ stats)
+                                                      const float* __restrict__ w, float* __restrict__ out, int M, int C4, double* __restrict__ stats, int rev)
 {
     __shared__ float s1s[8], s2s[8];
     const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, PL = blockDim.x / C4;
     const float sc = __ldg(scale), sh = __ldg(shift);
     const float4 wq = ldg4(w + c4 * 4);
     float s1 = 0.f, s2 = 0.f;
-    for (int m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL) {
+    for (int m0 = blockIdx.x * PL + pl; m0 < M; m0 += gridDim.x * PL) {
+        const int m = rev ? M - 1 - m0 : m0;
         const float f = relu6f(fmaf(__ldg(x + m), sc, sh));
         *reinterpret_cast<float4*>(out + ((size_t)m * C4 + c4) * 4) = make_float4(f * wq.x, f * wq.y, f * wq.z, f * wq.w);
         if (c4 == 0) { s1 += f; s2 = fmaf(f, f, s2); }
@@ -650,7 +655,7 @@ __global__ void __launch_bounds__(256) pw1_fwd_kernel(const float* __restrict__ 
 // backward in one pass over dY: dX[m] = sum_c dY[m][c] w[c] (16-lane shuffle reduce), dW[c] += sum_m f(x[m]) dY[m][c]
 __global__ void __launch_bounds__(256) pw1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                                       const float* __restrict__ dY, const float* __restrict__ w, float* __restrict__ dX,
-                                                      float* __restrict__ dW, int M)
+                                                      float* __restrict__ dW, int M, int rev)
 {
     __shared__ float4 sacc[256];
     const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
@@ -660,13 +665,13 @@ __global__ void __launch_bounds__(256) pw1_bwd_kernel(const float* __restrict__ 
     const int mstep = gridDim.x * 16;
     // every lane of a warp runs the same number of iterations (M is padded to the stride by the bound check inside)
     for (int m0 = blockIdx.x * 16; m0 < M; m0 += mstep) {
-        const int m = m0 + pl;
+        const int mf = m0 + pl, m = rev ? M - 1 - mf : mf;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f); float f = 0.f;
-        if (m < M) { g = ldg4(dY + ((size_t)m * 16 + c4) * 4); f = relu6f(fmaf(__ldg(x + m), sc, sh)); }
+        if (mf < M) { g = ldg4(dY + ((size_t)m * 16 + c4) * 4); f = relu6f(fmaf(__ldg(x + m), sc, sh)); }
         float d = g.x * wq.x + g.y * wq.y + g.z * wq.z + g.w * wq.w;
 #pragma unroll
         for (int o = 8; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (c4 == 0 && m < M) dX[m] = d;
+        if (c4 == 0 && mf < M) dX[m] = d;
         acc.x = fmaf(f, g.x, acc.x); acc.y = fmaf(f, g.y, acc.y); acc.z = fmaf(f, g.z, acc.z); acc.w = fmaf(f, g.w, acc.w);
     }
     sacc[threadIdx.x] = acc;
@@ -742,25 +747,25 @@ inline void chan_block(int C, long long M, dim3& grid, dim3& block) {
 
 }  // namespace
 
-int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats) {
+int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats, int rev) {
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
         dim3 grid, block; chan_block(C / 4, ngroups, grid, block);
-        if (stats) dwconv3x3_cb_kernel<false, true><<<grid, block, sizeof(double) * 8 * 256, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, stats);
-        else dwconv3x3_cb_kernel<false, false><<<grid, block, 0, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, nullptr);
+        if (stats) dwconv3x3_cb_kernel<false, true><<<grid, block, sizeof(double) * 8 * 256, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, stats, rev);
+        else dwconv3x3_cb_kernel<false, false><<<grid, block, 0, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, nullptr, rev);
     }
     else if (C == 1 && !stats) { long long total = (long long)B * H * W; dwconv3x3_c1<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4 (fused statistics need C %% 4 == 0)"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;
 }
-int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
+int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev) {
     if (accumulate) { crnn_set_error("dwconv_bwd_data: accumulate unsupported"); return CRNN_ERR_INVALID; }
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
         dim3 grid, block; chan_block(C / 4, ngroups, grid, block);
-        dwconv3x3_cb_kernel<true, false><<<grid, block, 0, st>>>(dy, k, dx, H, W, C / 4, WG, (int)ngroups, nullptr);
+        dwconv3x3_cb_kernel<true, false><<<grid, block, 0, st>>>(dy, k, dx, H, W, C / 4, WG, (int)ngroups, nullptr, rev);
     }
     else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
@@ -789,14 +794,14 @@ int launch_bn_finalize(const double* stats, long long M, int C, const float* gam
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C, int ph, int pw,
-                        float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
+                        float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr, int rev) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
     grid.y = (unsigned)std::min<long long>((npix + block.y - 1) / block.y, (long long)grid.y * 2);     // ~8 CTAs per SM: short dependent chains, many loads in flight
-#define APF(PH_, PW_) act_pool_fwd_kernel<PH_, PW_><<<grid, block, 0, st>>>(y, scale, shift, a, W, C / 4, W / pw, (int)npix, rate, ik, seed, layer, seed_ptr)
+#define APF(PH_, PW_) act_pool_fwd_kernel<PH_, PW_><<<grid, block, 0, st>>>(y, scale, shift, a, W, C / 4, W / pw, (int)npix, rate, ik, seed, layer, seed_ptr, rev)
     if (ph == 1 && pw == 1) APF(1, 1);
     else if (ph == 2 && pw == 2) APF(2, 2);
     else if (ph == 1 && pw == 2) APF(1, 2);
@@ -807,14 +812,14 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
 // two launches: reductions, then apply (+ a tiny launch for dgamma/dbeta); `red` (double[2C]) must be pre-zeroed
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red, float* dgamma, float* dbeta,
-                           int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
+                           int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr, int rev) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
     const double invM = 1.0 / ((double)B * H * W);
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
-#define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix, seed_ptr)
+#define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix, seed_ptr, (A_) ? !rev : rev)
     const size_t sm = sizeof(float) * 8 * 256;
     if (ph == 1 && pw == 1) { APB(false, 1, 1, sm); LAUNCH_CHECK(); APB(true, 1, 1, 0); }
     else if (ph == 2 && pw == 2) { APB(false, 2, 2, sm); LAUNCH_CHECK(); APB(true, 2, 2, 0); }
@@ -826,14 +831,14 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
-                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st) {
+                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev) {
     dim3 grid, block;
     const double invM = 1.0 / (double)M;
     if (C % 4 == 0) {
         chan_block(C / 4, (M + 1) / 2, grid, block);
-        relu6_bwd_kernel<false><<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM);
+        relu6_bwd_kernel<false><<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM, rev);
         LAUNCH_CHECK();
-        relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM);
+        relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM, !rev);
     } else {
         chan_block(C, M, grid, block);
         relu6_bwd_scalar_kernel<false><<<grid, block, sizeof(float) * 2 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
@@ -868,16 +873,16 @@ int launch_dropout_copy(const float* in, float* out, long long n, float rate, ui
     dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(in, out, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
     LAUNCH_CHECK(); return CRNN_OK;
 }
-int launch_pw1_fwd(const float* x, const float* scale, const float* shift, const float* w, float* out, long long M, int Cout, double* stats, cudaStream_t st) {
+int launch_pw1_fwd(const float* x, const float* scale, const float* shift, const float* w, float* out, long long M, int Cout, double* stats, cudaStream_t st, int rev) {
     if (Cout != 64 || too_big(M * Cout)) { crnn_set_error("pw1_fwd: Cout must be 64"); return CRNN_ERR_INVALID; }
     const int grid = (int)std::min<long long>((M + 15) / 16, 148 * 8);
-    pw1_fwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, w, out, (int)M, Cout / 4, stats);
+    pw1_fwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, w, out, (int)M, Cout / 4, stats, rev);
     LAUNCH_CHECK(); return CRNN_OK;
 }
-int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const float* dY, const float* w, float* dX, float* dW, long long M, int Cout, cudaStream_t st) {
+int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const float* dY, const float* w, float* dX, float* dW, long long M, int Cout, cudaStream_t st, int rev) {
     if (Cout != 64 || too_big(M * Cout)) { crnn_set_error("pw1_bwd: Cout must be 64"); return CRNN_ERR_INVALID; }
     const int grid = (int)std::min<long long>((M + 15) / 16, 148 * 8);
-    pw1_bwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, dY, w, dX, dW, (int)M);
+    pw1_bwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, dY, w, dX, dW, (int)M, rev);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_set_u64(uint64_t* p, uint64_t v, cudaStream_t st) {

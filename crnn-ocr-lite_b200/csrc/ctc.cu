@@ -9,16 +9,31 @@
 #include "common.cuh"
 
 // =================================================================================================
-// CTC loss + gradient.  One CTA (128 threads) per sequence:
-//   phase 0  all threads : u=log(p+eps), re-softmax (TF does), log y          -> smem logy[T'][V]
-//   phase 1  warp 0      : alpha sweep (lanes over the 2L+1 extended-label states) -> smem alpha[T'][S]
-//            warp 1      : beta sweep  (independent of alpha)                     -> smem beta[T'][S]
-//   phase 2  all threads : per (t,k) gradient  y - exp(LSE_{s:l'_s=k}(alpha+beta) - log p)
-//                          optionally chained through u=log(p+eps) and the dense2 softmax to d/d logits.
+// CTC loss + gradient.  One CTA (128 threads = 4 warps) per sequence, everything in shared memory:
+//   phase 0  warp per frame : u=log(p+eps), re-softmax (TF does), log y (lanes over classes)        -> smem logy[T'][V]
+//   phase 1  warp 0         : alpha sweep, warp 1: beta sweep (independent).  A lane OWNS the extended-label states s = lane + 32 j
+//                             in registers; neighbours s-1, s-2 (s+1, s+2) arrive by shuffles, so a time step is one dependent
+//                             chain of two LogSumExp per lane with no shared-memory round trip.              -> smem alpha/beta[T'][S]
+//   phase 2  warp per frame : per-class LSE_{s: l'_s = k}(alpha+beta): states grouped by label with __match_any (lanes over label
+//                             positions, the blank states by a warp max/sum reduction), then lanes over classes form
+//                             y - exp(acc - log p) and chain it through u=log(p+eps) and the dense2 softmax to d/d logits.
+// (ncu r1f on the previous version -- thread per (t,k) looping over all states: 188 us per launch, the 1/38 of the items that were
+//  blanks serialised 24 LogSumExp each and the divergence made every warp iteration that slow.)
 // =================================================================================================
 #define CTC_MAX_NS 8   // states per lane  -> S <= 256, L <= 127
+#define CTC_WARPS 8
 
-__global__ void __launch_bounds__(128)
+// LogSumExp on the sequential alpha/beta chains: max + log(1 + exp(min - max)) with the hardware ex2/lg2 approximations
+// (|error| <= ~3e-7 per call; the chain is 2 calls per time step, so <= ~4e-5 on log p(l|x) ~ 1e2 -- inside the stated 1e-5 relative
+// tolerance).  The accurate expf/log1pf pair is ~6x longer and this chain is pure latency (one warp, ncu r1g: 11 cycles / instruction).
+__device__ __forceinline__ float lse2_fast(float a, float b) {
+    const float mx = fmaxf(a, b), mn = fminf(a, b);
+    if (mx == NEG_INF) return NEG_INF;
+    return mx + __logf(1.f + __expf(mn - mx));
+}
+
+template <int NS>
+__global__ void __launch_bounds__(CTC_WARPS * 32)
 ctc_loss_grad_kernel(const float* __restrict__ probs,   // (B, T, V) softmax output, full T
                      int t_off,                          // frames dropped at the front (reference: 2)
                      const int* __restrict__ labels, int maxL,
@@ -30,6 +45,7 @@ ctc_loss_grad_kernel(const float* __restrict__ probs,   // (B, T, V) softmax out
                      float scale, int* __restrict__ status)
 {
     extern __shared__ float sm[];
+    constexpr unsigned FULL = 0xffffffffu;
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Tp = T - t_off;
@@ -41,7 +57,8 @@ ctc_loss_grad_kernel(const float* __restrict__ probs,   // (B, T, V) softmax out
     float* logy = sm;                      // Tp*V
     float* alpha = logy + (size_t)Tp * V;  // Tp*Smax
     float* beta = alpha + (size_t)Tp * Smax;
-    int* lp = (int*)(beta + (size_t)Tp * Smax);  // Smax
+    float* acc = beta + (size_t)Tp * Smax; // CTC_WARPS x V
+    int* lp = (int*)(acc + CTC_WARPS * (size_t)V); // Smax
     __shared__ float s_logp;
     __shared__ int s_bad;
 
@@ -61,100 +78,181 @@ ctc_loss_grad_kernel(const float* __restrict__ probs,   // (B, T, V) softmax out
         return;
     }
 
-    // ---- phase 0: log y (thread per frame, serial over classes: same summation order as the oracle) ----
-    for (int t = tid; t < Tb; t += blockDim.x) {
+    // ---- phase 0: log y, warp per frame, lanes over classes ----
+    for (int t = warp; t < Tb; t += CTC_WARPS) {
         const float* p = pb + (size_t)t * V;
         float* ly = logy + (size_t)t * V;
         float mx = -INFINITY;
-        for (int k = 0; k < V; ++k) { float u = logf(p[k] + eps); ly[k] = u; mx = fmaxf(mx, u); }
+        for (int k = lane; k < V; k += 32) { const float u = logf(__ldg(p + k) + eps); ly[k] = u; mx = fmaxf(mx, u); }
+        mx = warp_max(mx);
         float sum = 0.f;
-        for (int k = 0; k < V; ++k) sum += expf(ly[k] - mx);
-        for (int k = 0; k < V; ++k) ly[k] = logf(expf(ly[k] - mx) / sum);
-    }
-    for (int i = tid; i < Tb * S; i += blockDim.x) {
-        int t = i / S, s = i - t * S;
-        alpha[t * Smax + s] = NEG_INF; beta[t * Smax + s] = NEG_INF;
+        for (int k = lane; k < V; k += 32) sum += expf(ly[k] - mx);
+        sum = warp_sum(sum);
+        const float lsum = logf(sum);
+        for (int k = lane; k < V; k += 32) ly[k] = (ly[k] - mx) - lsum;      // = log(exp(u - mx) / sum)
     }
     __syncthreads();
 
-    // ---- phase 1: alpha (warp 0) and beta (warp 1) ----
+    // ---- phase 1: alpha (warp 0) and beta (warp 1), states in registers ----
+    const int nj = (S + 31) >> 5;
     if (warp == 0) {
-        if (lane == 0) { alpha[0] = logy[blank]; if (S > 1) alpha[1] = logy[lp[1]]; }
-        __syncwarp();
+        float a[NS]; int lab[NS]; bool skip[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            const int s = lane + 32 * j;
+            const bool ok = s < S;
+            lab[j] = ok ? lp[s] : blank;
+            skip[j] = ok && s > 1 && lab[j] != blank && lab[j] != lp[s - 2];
+            a[j] = NEG_INF;
+        }
+        if (lane == 0) a[0] = logy[blank];
+        if (lane == 1 && S > 1) a[0] = logy[lab[0]];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { const int s = lane + 32 * j; if (j < nj && s < S) alpha[s] = a[j]; }
         for (int t = 1; t < Tb; ++t) {
             int lo = S - 2 * (Tb - t); if (lo < 0) lo = 0;
             int hi = 2 * (t + 1); if (hi > S) hi = S;
-            const float* ap = alpha + (size_t)(t - 1) * Smax;
-            float* an = alpha + (size_t)t * Smax;
             const float* ly = logy + (size_t)t * V;
-            for (int s = lo + lane; s < hi; s += 32) {
-                float a = ap[s];
-                if (s > 0) a = lse2(a, ap[s - 1]);
-                int l = lp[s];
-                if (s > 1 && l != blank && l != lp[s - 2]) a = lse2(a, ap[s - 2]);
-                an[s] = ly[l] + a;
+            float* an = alpha + (size_t)t * Smax;
+            float c31 = NEG_INF, c30 = NEG_INF;          // previous 32-state block's (old) values at lanes 31 / 30
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                if (j < nj) {
+                    const int s = lane + 32 * j;
+                    const float cur = a[j];
+                    float up1 = __shfl_up_sync(FULL, cur, 1), up2 = __shfl_up_sync(FULL, cur, 2);
+                    if (lane == 0) { up1 = c31; up2 = c30; } else if (lane == 1) up2 = c31;
+                    c31 = __shfl_sync(FULL, cur, 31); c30 = __shfl_sync(FULL, cur, 30);
+                    float v = cur;
+                    if (s > 0) v = lse2_fast(v, up1);
+                    if (skip[j]) v = lse2_fast(v, up2);
+                    v = (s >= lo && s < hi) ? ly[lab[j]] + v : NEG_INF;
+                    a[j] = v;
+                    if (s < S) an[s] = v;
+                }
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) { beta[(size_t)(Tb - 1) * Smax + S - 1] = 0.f; if (S > 1) beta[(size_t)(Tb - 1) * Smax + S - 2] = 0.f; }
-        __syncwarp();
+        float bt[NS]; int lab[NS]; bool skip2[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            const int s = lane + 32 * j;
+            const bool ok = s < S;
+            lab[j] = ok ? lp[s] : blank;
+            skip2[j] = (s + 2 < S) && lp[s + 2] != blank && lp[s + 2] != lab[j];
+            bt[j] = (ok && s >= S - 2) ? 0.f : NEG_INF;     // beta[Tb-1][S-1] = beta[Tb-1][S-2] = 0
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { const int s = lane + 32 * j; if (j < nj && s < S) beta[(size_t)(Tb - 1) * Smax + s] = bt[j]; }
         for (int t = Tb - 2; t >= 0; --t) {
             int lo = S - 2 * (Tb - t); if (lo < 0) lo = 0;
             int hi = 2 * (t + 1); if (hi > S) hi = S;
-            const float* bn = beta + (size_t)(t + 1) * Smax;
-            float* bc = beta + (size_t)t * Smax;
             const float* ly = logy + (size_t)(t + 1) * V;
-            for (int s = lo + lane; s < hi; s += 32) {
-                int l = lp[s];
-                float v = bn[s] + ly[l];
-                if (s + 1 < S) v = lse2(v, bn[s + 1] + ly[lp[s + 1]]);
-                if (s + 2 < S) { int l2 = lp[s + 2]; if (l2 != blank && l2 != l) v = lse2(v, bn[s + 2] + ly[l2]); }
-                bc[s] = v;
+            float* bc = beta + (size_t)t * Smax;
+            float c[NS + 1];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { const int s = lane + 32 * j; c[j] = (j < nj && s < S) ? bt[j] + ly[lab[j]] : NEG_INF; }
+            c[NS] = NEG_INF;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                if (j < nj) {
+                    const int s = lane + 32 * j;
+                    float dn1 = __shfl_down_sync(FULL, c[j], 1), dn2 = __shfl_down_sync(FULL, c[j], 2);
+                    const float n0 = __shfl_sync(FULL, c[j + 1], 0), n1 = __shfl_sync(FULL, c[j + 1], 1);
+                    if (lane == 31) { dn1 = n0; dn2 = n1; } else if (lane == 30) dn2 = n0;
+                    float v = c[j];
+                    if (s + 1 < S) v = lse2_fast(v, dn1);
+                    if (skip2[j]) v = lse2_fast(v, dn2);
+                    v = (s >= lo && s < hi) ? v : NEG_INF;
+                    bt[j] = v;
+                    if (s < S) bc[s] = v;
+                }
             }
-            __syncwarp();
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        float lpv = NEG_INF;
-        for (int s = 0; s < S; ++s) lpv = lse2(lpv, alpha[s] + beta[s]);
-        s_logp = lpv;
-        loss[b] = -lpv;
+    if (warp == 0) {   // log p(l|x) = LSE_s(alpha_0(s) + beta_0(s))
+        float m = NEG_INF;
+        for (int s = lane; s < S; s += 32) m = fmaxf(m, alpha[s] + beta[s]);
+        m = warp_max(m);
+        float sum = 0.f;
+        if (m != NEG_INF) for (int s = lane; s < S; s += 32) sum += expf(alpha[s] + beta[s] - m);
+        sum = warp_sum(sum);
+        if (lane == 0) { const float lpv = (m == NEG_INF) ? NEG_INF : m + logf(sum); s_logp = lpv; loss[b] = -lpv; }
     }
+    if (grad_logits) for (int i = tid; i < t_off * V; i += blockDim.x) grad_logits[(size_t)b * T * V + i] = 0.f;   // frames 0,1: no gradient (utils.py:102)
     __syncthreads();
     const float logp = s_logp;
 
-    // ---- phase 2a: g_u[t][k] overwrites logy[t][k]  (thread per (t,k)) ----
-    for (int i = tid; i < Tb * V; i += blockDim.x) {
-        int t = i / V, k = i - t * V;
-        float acc = NEG_INF;
+    // ---- phase 2: warp per frame ----
+    float* accw = acc + (size_t)warp * V;
+    for (int t = warp; t < Tp; t += CTC_WARPS) {
+        float* gu = grad_u ? grad_u + ((size_t)b * Tp + t) * V : nullptr;
+        float* gz = grad_logits ? grad_logits + ((size_t)b * T + t + t_off) * V : nullptr;
+        if (t >= Tb) {
+            for (int k = lane; k < V; k += 32) { if (gu) gu[k] = 0.f; if (gz) gz[k] = 0.f; }
+            continue;
+        }
         const float* a = alpha + (size_t)t * Smax;
         const float* be = beta + (size_t)t * Smax;
-        if (k == blank) { for (int s = 0; s < S; s += 2) acc = lse2(acc, a[s] + be[s]); }
-        else            { for (int s = 1; s < S; s += 2) if (lp[s] == k) acc = lse2(acc, a[s] + be[s]); }
-        float y = expf(logy[i]);
-        float g = (acc == NEG_INF || logp == NEG_INF) ? y : y - expf(acc - logp);
-        logy[i] = g;
-    }
-    __syncthreads();
-    if (grad_u) {
-        float* g = grad_u + (size_t)b * Tp * V;
-        for (int i = tid; i < Tp * V; i += blockDim.x) g[i] = (i < Tb * V) ? logy[i] : 0.f;
-    }
-    // ---- phase 2b: chain to the dense2 logits: u=log(p+eps), p=softmax(z)  (thread per frame) ----
-    if (grad_logits) {
-        float* gz = grad_logits + (size_t)b * T * V;
-        for (int i = tid; i < t_off * V; i += blockDim.x) gz[i] = 0.f;          // frames 0,1: no gradient (utils.py:102)
-        for (int t = tid; t < Tp; t += blockDim.x) {
-            float* o = gz + (size_t)(t + t_off) * V;
-            if (t >= Tb) { for (int k = 0; k < V; ++k) o[k] = 0.f; continue; }
-            const float* p = pb + (size_t)t * V;
-            const float* g = logy + (size_t)t * V;
-            float dot = 0.f;
-            for (int k = 0; k < V; ++k) dot += (g[k] / (p[k] + eps)) * p[k];
-            for (int k = 0; k < V; ++k) o[k] = scale * p[k] * (g[k] / (p[k] + eps) - dot);
+        for (int k = lane; k < V; k += 32) accw[k] = NEG_INF;
+        // blank states s = 2i, i = 0..L
+        float mB = NEG_INF;
+        for (int i = lane; i <= L; i += 32) mB = fmaxf(mB, a[2 * i] + be[2 * i]);
+        mB = warp_max(mB);
+        float sB = 0.f;
+        if (mB != NEG_INF) for (int i = lane; i <= L; i += 32) sB += expf(a[2 * i] + be[2 * i] - mB);
+        sB = warp_sum(sB);
+        __syncwarp();
+        // label states s = 2i+1 in chunks of 32 positions; equal labels inside a chunk are combined with shuffles, across chunks via accw
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            const bool on = i < L;
+            const int l = on ? lp[2 * i + 1] : -1 - lane;                 // inactive lanes form singleton groups
+            const float v = on ? a[2 * i + 1] + be[2 * i + 1] : NEG_INF;
+            const unsigned grp = __match_any_sync(FULL, l);
+            float m = v;
+            unsigned rem = grp & ~(1u << lane);
+            while (__any_sync(FULL, rem != 0)) {
+                const int src = rem ? __ffs(rem) - 1 : lane;
+                const float o = __shfl_sync(FULL, v, src);
+                if (rem) { m = fmaxf(m, o); rem &= rem - 1; }
+            }
+            float sum = (m == NEG_INF) ? 0.f : expf(v - m);
+            rem = grp & ~(1u << lane);
+            while (__any_sync(FULL, rem != 0)) {
+                const int src = rem ? __ffs(rem) - 1 : lane;
+                const float o = __shfl_sync(FULL, v, src);
+                if (rem) { if (m != NEG_INF) sum += expf(o - m); rem &= rem - 1; }
+            }
+            if (on && (__ffs(grp) - 1) == lane && l >= 0 && l < V) {
+                const float r = (m == NEG_INF) ? NEG_INF : m + logf(sum);
+                accw[l] = lse2(accw[l], r);
+            }
+            __syncwarp();
         }
+        if (lane == 0) accw[blank] = lse2(accw[blank], (mB == NEG_INF) ? NEG_INF : mB + logf(sB));
+        __syncwarp();
+        // gradient wrt u (overwrites logy[t]) and the chain to the dense2 logits: u=log(p+eps), p=softmax(z)
+        const float* p = pb + (size_t)t * V;
+        float* ly = logy + (size_t)t * V;
+        float dot = 0.f;
+        for (int k = lane; k < V; k += 32) {
+            const float y = expf(ly[k]);
+            const float ac = accw[k];
+            const float g = (ac == NEG_INF || logp == NEG_INF) ? y : y - expf(ac - logp);
+            ly[k] = g;
+            if (gu) gu[k] = g;
+            const float pk = __ldg(p + k);
+            dot += __fdividef(g, pk + eps) * pk;
+        }
+        dot = warp_sum(dot);
+        if (gz)
+            for (int k = lane; k < V; k += 32) {
+                const float pk = __ldg(p + k);
+                gz[k] = scale * pk * (__fdividef(ly[k], pk + eps) - dot);
+            }
+        __syncwarp();
     }
 }
 
@@ -394,7 +492,7 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
 // =================================================================================================
 size_t ctc_loss_smem_bytes(int T, int t_off, int V, int maxL) {
     int Tp = T - t_off, Smax = 2 * maxL + 1;
-    return sizeof(float) * ((size_t)Tp * V + 2 * (size_t)Tp * Smax) + sizeof(int) * Smax;
+    return sizeof(float) * ((size_t)Tp * V + 2 * (size_t)Tp * Smax + CTC_WARPS * (size_t)V) + sizeof(int) * Smax;
 }
 
 int launch_ctc_loss_grad(const float* probs, int t_off, const int* labels, int maxL, const int* label_len,
@@ -403,16 +501,23 @@ int launch_ctc_loss_grad(const float* probs, int t_off, const int* labels, int m
 {
     if (B <= 0) return CRNN_OK;
     if (T - t_off <= 0 || V < 2 || maxL < 0) { crnn_set_error("ctc_loss: bad shape"); return CRNN_ERR_INVALID; }
+    if (2 * maxL + 1 > 32 * CTC_MAX_NS) { crnn_set_error("ctc_loss: max label length %d exceeds %d", maxL, (32 * CTC_MAX_NS - 1) / 2); return CRNN_ERR_INVALID; }
     size_t smem = ctc_loss_smem_bytes(T, t_off, V, maxL);
     if (smem > 227 * 1024) { crnn_set_error("ctc_loss: T'*(V+2S) too large for shared memory (%zu B)", smem); return CRNN_ERR_INVALID; }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(ctc_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    const int ns = (2 * maxL + 1 + 31) / 32;
     CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
-    ctc_loss_grad_kernel<<<B, 128, smem, st>>>(probs, t_off, labels, maxL, label_len, input_len, B, T, V, eps,
-                                               loss, grad_u, grad_logits, scale, status);
+#define CTC_LAUNCH(NS_)                                                                                                                   \
+    do {                                                                                                                                  \
+        static size_t configured = 0;                                                                                                     \
+        if (smem > 48 * 1024 && smem > configured) {                                                                                      \
+            CUDA_TRY(cudaFuncSetAttribute(ctc_loss_grad_kernel<NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+            configured = smem;                                                                                                            \
+        }                                                                                                                                 \
+        ctc_loss_grad_kernel<NS_><<<B, CTC_WARPS * 32, smem, st>>>(probs, t_off, labels, maxL, label_len, input_len, B, T, V, eps,        \
+                                                                   loss, grad_u, grad_logits, scale, status);                             \
+    } while (0)
+    if (ns <= 1) CTC_LAUNCH(1); else if (ns <= 2) CTC_LAUNCH(2); else if (ns <= 4) CTC_LAUNCH(4); else CTC_LAUNCH(8);
+#undef CTC_LAUNCH
     LAUNCH_CHECK();
     return CRNN_OK;
 }

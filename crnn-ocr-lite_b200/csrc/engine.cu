@@ -85,7 +85,10 @@ struct crnn_handle {
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
     // stream = a parallel branch of the graph.  CRNN_GRAPH=0 / CRNN_OVERLAP=0 switch either off; profiling runs eager + serial.
-    bool use_graph = true, overlap = true;
+    bool use_graph = true, overlap = true, serp = true;
+    int flip = 0;   // serpentine traversal: consecutive kernels of the conv-stack chain walk their tensors in alternating directions, so each
+                    // one starts on the bytes its producer touched last (still in the 126 MB L2) -- CRNN_SERPENTINE=0 disables
+    int rv() { const int r = serp ? flip : 0; flip ^= 1; return r; }
     cudaStream_t side = nullptr, cap = nullptr;
     std::vector<cudaEvent_t> evs; size_t ev_used = 0;
     const uint64_t* seed_ptr = nullptr;   // non-null while capturing: dropout kernels read the seed from device memory
@@ -374,7 +377,7 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
     if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
     const bool drop = training && seed != 0;
     const int H = h->H, W = h->W, U = h->U, G = h->G, T = h->T, V = h->V;
-    h->ev_used = 0;
+    h->ev_used = 0; h->flip = 0;
     // ---- side branch: weight images of all tensor-core GEMMs of this step (weights only change in the optimiser)
     TRY(prep_images(h, training, side_after(h, st)));
     if (training) CUDA_TRY(cudaMemsetAsync(h->a("stats"), 0, sizeof(double) * h->bn_off[15], st));
@@ -393,7 +396,7 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
         const bool dw_stats = training && (b.cin % 4 == 0);       // BN statistics of the depthwise output fused into the conv kernel
         ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st,
-                                                         dw_stats ? bn_stats(h, 2 * i - 1) : nullptr));
+                                                         dw_stats ? bn_stats(h, 2 * i - 1) : nullptr, h->rv()));
         TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st, dw_stats));
         const bool tc = !h->gemm_simt && (b.cin % 32 == 0);
         bool pw_stats = false;
@@ -401,11 +404,11 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
             if (i == 2) side_join(h, st);                          // the weight images are ready
             ST(ST_GEMM_PW_FWD, 2.0 * M * b.cout * b.cin, launch_xw_gemm_tc(dw, b.cin, h->a(nm("wimg_fwd%d", i)), pw, b.cout, (int)M, b.cout, b.cin,
                                                                           h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")),
-                                                                          training ? bn_stats(h, 2 * i) : nullptr, st));
+                                                                          training ? bn_stats(h, 2 * i) : nullptr, st, nullptr, 0, 0, h->rv()));
             pw_stats = true;
         } else if (b.cin == 1) {                                   // block 1: the "GEMM" is an outer product
             ST(ST_GEMM_PW_FWD, 2.0 * M * b.cout, launch_pw1_fwd(dw, h->a(actbn(1, "scale")), h->a(actbn(1, "shift")), h->w(nm("conv2d_%d/kernel", i + 2)), pw, M, b.cout,
-                                                                training ? bn_stats(h, 2 * i) : nullptr, st));
+                                                                training ? bn_stats(h, 2 * i) : nullptr, st, h->rv()));
             pw_stats = true;
         } else {
             TRY(gemm_nn(h, ST_GEMM_PW_FWD, dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
@@ -413,7 +416,7 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         }
         TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st, pw_stats));
         ST(ST_ACT_POOL, 4.0 * M * b.cout * (1.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
-                                drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr));
+                                drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv()));
         hh /= b.ph; ww /= b.pw; in = out;
     }
     if (h->gemm_simt) side_join(h, st);
@@ -508,11 +511,12 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
     ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (3.0 + 2.0 / (b.ph * b.pw)),
        launch_act_pool_bn_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
                               h->w(bnname(bn2, "gamma")), dpw, bn_red(h, bn2), h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")),
-                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr));
+                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv()));
+    h->rv();   // two kernels (reduce, apply): two direction flips
     if (b.cin == 1) {
         // block 1: dW[co] = sum_m f(x[m]) dY[m][co] and dX[m] = sum_co dY[m][co] W[co] in ONE pass over dY
         ST(ST_GEMM_PW_DX, 4.0 * Mi * b.cout, launch_pw1_bwd(dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), dpw, h->w(nm("conv2d_%d/kernel", i + 2)),
-                                                            ddw, h->g(nm("conv2d_%d/kernel", i + 2)), Mi, b.cout, st));
+                                                            ddw, h->g(nm("conv2d_%d/kernel", i + 2)), Mi, b.cout, st, h->rv()));
     } else {
         cudaStream_t ss = side_after(h, st);
         if (!h->gemm_simt && (b.cin % 4 == 0)) {
@@ -523,20 +527,21 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
                         h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), ss));
         }
         if (!h->gemm_simt && (b.cout % 32 == 0) && (b.cin % 4 == 0)) {
-            ST(ST_GEMM_PW_DX, 2.0 * Mi * b.cin * b.cout, launch_xw_gemm_tc(dpw, b.cout, h->a(nm("wimg_dx%d", i)), ddw, b.cin, (int)Mi, b.cin, b.cout, nullptr, nullptr, nullptr, st));
+            ST(ST_GEMM_PW_DX, 2.0 * Mi * b.cin * b.cout, launch_xw_gemm_tc(dpw, b.cout, h->a(nm("wimg_dx%d", i)), ddw, b.cin, (int)Mi, b.cin, b.cout, nullptr, nullptr, nullptr, st, nullptr, 0, 0, h->rv()));
         } else {
             TRY(gemm_nt(h, ST_GEMM_PW_DX, dpw, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, ddw, b.cin, (int)Mi, b.cin, b.cout, 0, st));
         }
     }
     ST(ST_BN_BWD, 20.0 * Mi * b.cin,
        launch_relu6_bn_bwd(ddw, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st));
+                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st, h->rv()));
+    h->rv();
     const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
     {
         cudaStream_t ss = side_after(h, st);
         ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, ddw, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, ss));
     }
-    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st));
+    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st, h->rv()));
     return CRNN_OK;
 }
 
@@ -671,6 +676,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }
+    { const char* e = getenv("CRNN_SERPENTINE"); h->serp = !(e && e[0] == '0'); }
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
     if (cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking) != cudaSuccess) { h->cap = nullptr; cudaGetLastError(); }
     *out = h;
@@ -786,26 +792,52 @@ int crnn_ctc_beam(const float* probs_dev, const int32_t* seq_len_dev, int B, int
     return launch_ctc_beam(probs_dev, seq_len_dev, B, T, V, eps, beam_width, merge_repeated, out_dev, out_len_dev, logprob_dev, static_cast<cudaStream_t>(stream));
 }
 
+// Host-buffer decode (DecodeCTCPred.decode, utils.py:347-357, takes host softmax rows): grow-only device scratch owned by the
+// library (cudaMallocAsync's default pool hands its memory back at every synchronise: 39 MB re-allocated per call cost ~10 ms),
+// and the batch is cut into chunks whose H2D copies (copy stream) overlap the decode of the previous chunk (caller's stream).
+namespace {
+struct DecodeScratch { void* p = nullptr; size_t cap = 0; cudaStream_t copy = nullptr; cudaEvent_t ev[8] = {}; int dev = -1; };
+DecodeScratch g_dec;
+}
 static int decode_host(bool beam, const float* probs_host, int B, int T, int V, float eps, int beam_width, int merge_repeated,
                        int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream) {
     if (!probs_host || !out_host || !out_len_host) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
     if (B <= 0) return CRNN_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
     const size_t np = (size_t)B * T * V, no = (size_t)B * T;
-    float* dp = nullptr; int32_t* dout = nullptr; int32_t* dlen = nullptr; float* dsc = nullptr;
-    CUDA_TRY(cudaMallocAsync(&dp, sizeof(float) * np, st));
-    CUDA_TRY(cudaMallocAsync(&dout, sizeof(int32_t) * no, st));
-    CUDA_TRY(cudaMallocAsync(&dlen, sizeof(int32_t) * B, st));
-    CUDA_TRY(cudaMallocAsync(&dsc, sizeof(float) * B, st));
-    CUDA_TRY(cudaMemcpyAsync(dp, probs_host, sizeof(float) * np, cudaMemcpyHostToDevice, st));
-    int rc = beam ? launch_ctc_beam(dp, nullptr, B, T, V, eps, beam_width, merge_repeated, dout, dlen, dsc, st)
-                  : launch_ctc_greedy(dp, nullptr, B, T, V, eps, dout, dlen, dsc, st);
+    const size_t off_out = (sizeof(float) * np + 255) & ~(size_t)255, off_len = off_out + ((sizeof(int32_t) * no + 255) & ~(size_t)255);
+    const size_t off_sc = off_len + ((sizeof(int32_t) * B + 255) & ~(size_t)255), need = off_sc + sizeof(float) * B;
+    DecodeScratch& D = g_dec;
+    if (D.dev != dev || D.cap < need) {
+        if (D.p) { cudaDeviceSynchronize(); cudaFree(D.p); D.p = nullptr; D.cap = 0; }
+        CUDA_TRY(cudaMalloc(&D.p, need)); D.cap = need; D.dev = dev;
+        if (!D.copy) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&D.copy, cudaStreamNonBlocking));
+            for (auto& e : D.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+    }
+    char* base = static_cast<char*>(D.p);
+    float* dp = reinterpret_cast<float*>(base); int32_t* dout = reinterpret_cast<int32_t*>(base + off_out);
+    int32_t* dlen = reinterpret_cast<int32_t*>(base + off_len); float* dsc = reinterpret_cast<float*>(base + off_sc);
+    const int nchunk = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+    const int per = (B + nchunk - 1) / nchunk;
+    // the copy stream must not overwrite the scratch while an earlier call on `st` still reads it
+    CUDA_TRY(cudaEventRecord(D.ev[7], st)); CUDA_TRY(cudaStreamWaitEvent(D.copy, D.ev[7], 0));
+    int rc = CRNN_OK;
+    for (int c = 0; c < nchunk && rc == CRNN_OK; ++c) {
+        const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
+        if (nb <= 0) break;
+        CUDA_TRY(cudaMemcpyAsync(dp + (size_t)b0 * T * V, probs_host + (size_t)b0 * T * V, sizeof(float) * (size_t)nb * T * V, cudaMemcpyHostToDevice, D.copy));
+        CUDA_TRY(cudaEventRecord(D.ev[c], D.copy)); CUDA_TRY(cudaStreamWaitEvent(st, D.ev[c], 0));
+        rc = beam ? launch_ctc_beam(dp + (size_t)b0 * T * V, nullptr, nb, T, V, eps, beam_width, merge_repeated, dout + (size_t)b0 * T, dlen + b0, dsc + b0, st)
+                  : launch_ctc_greedy(dp + (size_t)b0 * T * V, nullptr, nb, T, V, eps, dout + (size_t)b0 * T, dlen + b0, dsc + b0, st);
+    }
     if (rc == CRNN_OK) {
         CUDA_TRY(cudaMemcpyAsync(out_host, dout, sizeof(int32_t) * no, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(out_len_host, dlen, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
         if (score_host) CUDA_TRY(cudaMemcpyAsync(score_host, dsc, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
     }
-    cudaFreeAsync(dp, st); cudaFreeAsync(dout, st); cudaFreeAsync(dlen, st); cudaFreeAsync(dsc, st);
     CUDA_TRY(cudaStreamSynchronize(st));
     return rc;
 }

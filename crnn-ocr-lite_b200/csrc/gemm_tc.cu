@@ -111,6 +111,7 @@ struct TcArgs {
     const float* x_scale; const float* x_shift;   // optional BN+ReLU6 on X (per k)
     double* stats;                    // optional [2*N] column sum / sum of squares of out
     const float* bias; int relu; int accumulate;   // epilogue: out = [out +] relu?(acc + bias[n])
+    int rev;                          // v2: walk the pixel tiles from the end of the tensor (serpentine traversal)
     int diag;                         // CRNN_GEMM_DIAG (timing experiments only, results are garbage): 1 no epilogue stores, 2 no transform, 4 no MMA, 8 no activation fetch
 };
 
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         // fetch state: the 4 row pointers of the tile being fetched are computed once per tile, a k-block fetch is 4 x (64-bit add + LDGSTS)
         const float* frp[4]; uint32_t fsz[4];
         auto set_fetch_tile = [&](int tt) {
-            const int m0 = (tt / NTP) * TC_BP;
+            const int m0 = (a.rev ? MT - 1 - tt / NTP : tt / NTP) * TC_BP;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = m0 + r0 + 32 * i;
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         if (bn) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + c8 * 4)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + c8 * 4)); }
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int m0 = (t / NTP) * TC_BP;
+            const int m0 = (a.rev ? MT - 1 - t / NTP : t / NTP) * TC_BP;
             const bool tail = m0 + TC_BP > a.M;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = it % TC2_XSTAGES;
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
             const int buf = j & 1;
-            const int ct0 = (t % NTP) * NSUB, m0 = (t / NTP) * TC_BP;
+            const int ct0 = (t % NTP) * NSUB, m0 = (a.rev ? MT - 1 - t / NTP : t / NTP) * TC_BP;
             if (ct0 != cur_ct0) { flush_stats(); cur_ct0 = ct0; }
             mbar_wait(&tfull[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -818,13 +819,13 @@ int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transpo
 
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
-                      const float* bias, int relu, int accumulate)
+                      const float* bias, int relu, int accumulate, int rev)
 {
     if (M <= 0 || N <= 0) return CRNN_OK;
     if (K % TC_BK || K <= 0) { crnn_set_error("gemm_tc: K=%d must be a positive multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
     if ((ldx % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Wimg) & 15)) { crnn_set_error("gemm_tc: X/Wimg must be 16-byte aligned, ldx %% 4 == 0"); return CRNN_ERR_INVALID; }
     TcArgs a; a.X = X; a.ldx = ldx; a.Wimg = Wimg; a.out = out; a.ldo = ldo; a.M = M; a.N = N; a.K = K;
-    a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats; a.bias = bias; a.relu = relu; a.accumulate = accumulate;
+    a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats; a.bias = bias; a.relu = relu; a.accumulate = accumulate; a.rev = rev;
     static int diag = -1, nsub_env = -1;
     if (diag < 0) { const char* e = getenv("CRNN_GEMM_DIAG"); diag = e ? atoi(e) : 0; const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; }
     a.diag = diag;

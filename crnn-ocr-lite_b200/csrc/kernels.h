@@ -22,7 +22,7 @@ size_t tc_weight_image_floats(int N, int K);
 int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transposed, float* img, cudaStream_t st);
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
-                      const float* bias = nullptr, int relu = 0, int accumulate = 0);
+                      const float* bias = nullptr, int relu = 0, int accumulate = 0, int rev = 0);
 
 // dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]  (tcgen05, MN-major operands, split-K over pixels, atomics into pre-zeroed dW)
 int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
@@ -38,8 +38,9 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
                     int* out, int* out_len, float* logprob, cudaStream_t st);
 
 // ---- conv.cu (depthwise conv, BN statistics, activation/pool, elementwise) ----
-int launch_dwconv_fwd(const float* x, const float* k33c, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats = nullptr);
-int launch_dwconv_bwd_data(const float* dy, const float* k33c, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st);
+// rev (here and below): walk the tensor from its end (serpentine traversal: a kernel starts where its producer finished, in L2)
+int launch_dwconv_fwd(const float* x, const float* k33c, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats = nullptr, int rev = 0);
+int launch_dwconv_bwd_data(const float* dy, const float* k33c, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev = 0);
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
 // per-channel sum / sum of squares over rows of y[M][C] -> stats[0..C) , stats[C..2C) (double, pre-zeroed)
 int launch_colstats(const float* y, long long M, int C, double* stats, cudaStream_t st);
@@ -49,16 +50,16 @@ int launch_bn_finalize(const double* stats, long long M, int C, const float* gam
                        float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);
 // a = dropout(pool(relu6(y*scale+shift)))  ; pool (ph,pw) in {(1,1),(2,2),(1,2)}
 int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C,
-                        int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr = nullptr);
+                        int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr = nullptr, int rev = 0);
 // fused (ReLU6 + MaxPool + Dropout) backward + BatchNorm-train backward, two passes over (da, y), no dz round trip:
 //   dz = unpool(da*dropmask) * 1[0<=z<=6];  dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dgamma += sum(dz*xhat), dbeta += sum(dz)
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red /*pre-zeroed [2C]*/, float* dgamma, float* dbeta,
                            int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st,
-                           const uint64_t* seed_ptr = nullptr);
+                           const uint64_t* seed_ptr = nullptr, int rev = 0);   // reduce pass walks `rev`, apply pass the opposite way
 // same for the BN after the depthwise conv (no pool / dropout); dy may alias da
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
-                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
+                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev = 0);
 // BN training backward: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) in place; dgamma = sum(dz*xhat), dbeta = sum(dz)
 int launch_bn_bwd_apply(float* dz_inout, const float* y, const double* red, const float* gamma, const float* save_mean,
                         const float* save_invstd, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
@@ -71,9 +72,9 @@ int launch_dropout_copy(const float* in, float* out, long long n, float drop_rat
 int launch_set_u64(uint64_t* p, uint64_t v, cudaStream_t st);
 // block 1 of the conv stack (Cin = 1): the pointwise conv is an outer product out[m][co] = f(x[m]) * w[co], f = relu6(x*scale+shift).
 // stats (optional, pre-zeroed double[2*Cout]) receives the per-channel sum / sum of squares of out.
-int launch_pw1_fwd(const float* x, const float* scale, const float* shift, const float* w, float* out, long long M, int Cout, double* stats, cudaStream_t st);
+int launch_pw1_fwd(const float* x, const float* scale, const float* shift, const float* w, float* out, long long M, int Cout, double* stats, cudaStream_t st, int rev = 0);
 // its backward in one pass over dY: dX[m] = sum_co dY[m][co] w[co];  dW[co] += sum_m f(x[m]) dY[m][co]
-int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const float* dY, const float* w, float* dX, float* dW, long long M, int Cout, cudaStream_t st);
+int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const float* dY, const float* w, float* dX, float* dW, long long M, int Cout, cudaStream_t st, int rev = 0);
 int launch_sum_dirs(const float* hs, float* out, long long rows, int U, cudaStream_t st);               // out[r][u] = hs[r][0][u]+hs[r][1][u]
 int launch_dup_dirs(const float* g, float* out, long long rows, int U, cudaStream_t st);                // out[r][d][u] = g[r][u]
 int launch_softmax_rows(const float* z, float* p, long long rows, int V, cudaStream_t st);
