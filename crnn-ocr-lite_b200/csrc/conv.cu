@@ -3,6 +3,7 @@
 // ReLU6 + MaxPooling + Dropout (fwd / bwd), and the small element-wise glue of the recurrent head.
 // All tensors NHWC fp32; channel counts are 1 or multiples of 4 (float4 path).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -10,6 +11,9 @@
 namespace {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+#ifndef DWCONV_MIN_CTAS
+#define DWCONV_MIN_CTAS 1   // (a cap of 3 CTAs = 80 registers spills 56-112 B of the window and ran 15-25 % slower)
+#endif
 __device__ __forceinline__ void fma4(float4& a, const float4 x, const float4 k) {
     a.x = fmaf(x.x, k.x, a.x); a.y = fmaf(x.y, k.y, a.y); a.z = fmaf(x.z, k.z, a.z); a.w = fmaf(x.w, k.w, a.w);
 }
@@ -85,8 +89,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_vec4_w4(const float* __restrict
 // in registers and walks (image row, 4-column group) work items, so the per-item weight loads and two of the three integer divisions
 // disappear; with STATS it also accumulates the BatchNorm statistics of its outputs (fp32 per item, fp64 across items, smem across the
 // PY lanes, one fp64 atomic pair per channel and CTA) -- the separate colstats pass over the depthwise output is gone.
+// (tried: prefetch.global.L1 of the next item's 3x6 window -- 15 % slower, the extra 18 instructions cost more than the hidden latency)
 template <bool FLIP, bool STATS>
-__global__ void __launch_bounds__(256) dwconv3x3_cb_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
+__global__ void __launch_bounds__(256, DWCONV_MIN_CTAS) dwconv3x3_cb_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                                                            int H, int W, int C4, int WG, int ngroups, double* __restrict__ stats, int rev)
 {
     extern __shared__ double dsm[];   // STATS: [PY][8][CQ]
@@ -182,7 +187,7 @@ __global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restric
 
 // ------------------------------------------------------------------ depthwise 3x3 backward-weight
 // dk[i][j][c] = sum_{b,h,w} x[b,h+i-1,w+j-1,c] * dy[b,h,w,c].  blockDim = (CQ channel-quads | CT channels, PY pixel lanes)
-__global__ void __launch_bounds__(256) dwconv3x3_bwd_weight_vec4(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
+__global__ void __launch_bounds__(256, DWCONV_MIN_CTAS) dwconv3x3_bwd_weight_vec4(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
                                           int B, int H, int W, int C4, int WG, long long ngroups)
 {
     extern __shared__ float red[];   // [PY][36][CQ]
@@ -576,6 +581,73 @@ __global__ void __launch_bounds__(256) relu6_bwd_kernel(const float* da /* may a
     }
 }
 
+// Reduction pass of the BatchNorm(+ReLU6[+Dropout]) backward on a non-pooled [M][C] tensor: red[c] += sum_m dz, red[C+c] += sum_m dz*xhat with
+// dz = da * dropmask * 1[0 <= z <= 6].  Dedicated kernel (instead of the APPLY=false instances of the two kernels above): 4 rows = 8 float4
+// loads in flight per thread and ~64 registers, because this pass is pure HBM latency (ncu r1h: 2.8-4.0 TB/s, long-scoreboard 15-18 per issue).
+template <bool DROP>
+__global__ void __launch_bounds__(256, 3) bn_relu6_reduce_kernel(const float* __restrict__ da, const float* __restrict__ y, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                 double* __restrict__ red, int M, int C4, int rev,
+                                 float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr)
+{
+    extern __shared__ float sred[];   // [PY][8][CQ]
+    const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    if (DROP && seed_ptr) seed = *seed_ptr;
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    if (c4 < C4) {
+        const float4 sc = ldg4(scale + c4 * 4), sh = ldg4(shift + c4 * 4);
+        float4 xa = ldg4(invstd + c4 * 4), xb = ldg4(mean + c4 * 4);            // xhat = y*xa + xb
+        xb.x = -xb.x * xa.x; xb.y = -xb.y * xa.y; xb.z = -xb.z * xa.z; xb.w = -xb.w * xa.w;
+        const int stride = gridDim.y * PY;
+        for (int m0 = blockIdx.y * PY + threadIdx.y; m0 < M; m0 += 4 * stride) {
+            float4 yv[4], dv[4]; size_t o[4]; bool ok[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int mm = m0 + r * stride;
+                ok[r] = mm < M;
+                const int m = ok[r] ? (rev ? M - 1 - mm : mm) : (rev ? M - 1 - m0 : m0);
+                o[r] = (size_t)m * C4 + c4;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { yv[r] = ldg4(y + o[r] * 4); dv[r] = ldg4(da + o[r] * 4); }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (!ok[r]) continue;
+                float d[4] = {dv[r].x, dv[r].y, dv[r].z, dv[r].w};
+                const float yy[4] = {yv[r].x, yv[r].y, yv[r].z, yv[r].w};
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+                if (DROP) {
+                    float dm[4]; crnn_dropout_mask4(seed, layer, (uint64_t)o[r], rate, inv_keep, dm);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) d[q] *= dm[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float z = fmaf(yy[q], scv[q], shv[q]);
+                    const float dz = (z >= 0.f && z <= 6.f) ? d[q] : 0.f;
+                    s1[q] += dz; s2[q] = fmaf(dz, fmaf(yy[q], xav[q], xbv[q]), s2[q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sred[(threadIdx.y * 8 + q) * CQ + threadIdx.x] = s1[q];
+        sred[(threadIdx.y * 8 + 4 + q) * CQ + threadIdx.x] = s2[q];
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && c4 < C4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double t1 = 0.0, t2 = 0.0;
+            for (int i = 0; i < PY; ++i) { t1 += sred[(i * 8 + q) * CQ + threadIdx.x]; t2 += sred[(i * 8 + 4 + q) * CQ + threadIdx.x]; }
+            atomicAdd(red + c4 * 4 + q, t1); atomicAdd(red + C + c4 * 4 + q, t2);
+        }
+    }
+}
+
 // dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))  (in place);  block 0 also emits dgamma/dbeta
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restrict__ y, const double* __restrict__ red,
                                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -809,6 +881,21 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
 #undef APF
     LAUNCH_CHECK(); return CRNN_OK;
 }
+static int launch_bn_relu6_reduce(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
+                                  double* red, long long M, int C, int rev, float rate, uint64_t seed, uint32_t layer, const uint64_t* seed_ptr, cudaStream_t st) {
+    const int C4 = C / 4;
+    const int CQ = C4 >= 64 ? 64 : (C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1)))));
+    const int PY = 256 / CQ, gx = (C4 + CQ - 1) / CQ;
+    long long gy = (148 * 3 + gx - 1) / gx;                         // 3 resident CTAs per SM (launch bounds), one wave
+    const long long maxy = (M + 4LL * PY - 1) / (4LL * PY);
+    if (gy > maxy) gy = maxy;
+    if (gy < 1) gy = 1;
+    const dim3 grid(gx, (unsigned)gy), block(CQ, PY);
+    const size_t sm = sizeof(float) * 8 * 256;
+    if (rate > 0.f) bn_relu6_reduce_kernel<true><<<grid, block, sm, st>>>(da, y, scale, shift, mean, invstd, red, (int)M, C4, rev, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
+    else bn_relu6_reduce_kernel<false><<<grid, block, sm, st>>>(da, y, scale, shift, mean, invstd, red, (int)M, C4, rev, 0.f, 1.f, 0, 0, nullptr);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
 // two launches: reductions, then apply (+ a tiny launch for dgamma/dbeta); `red` (double[2C]) must be pre-zeroed
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red, float* dgamma, float* dbeta,
@@ -821,7 +908,11 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
 #define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix, seed_ptr, (A_) ? !rev : rev)
     const size_t sm = sizeof(float) * 8 * 256;
-    if (ph == 1 && pw == 1) { APB(false, 1, 1, sm); LAUNCH_CHECK(); APB(true, 1, 1, 0); }
+    if (ph == 1 && pw == 1) {
+        const int rc = launch_bn_relu6_reduce(da, y, scale, shift, mean, invstd, red, (long long)B * H * W, C, rev, rate, seed, layer, seed_ptr, st);
+        if (rc != CRNN_OK) return rc;
+        APB(true, 1, 1, 0);
+    }
     else if (ph == 2 && pw == 2) { APB(false, 2, 2, sm); LAUNCH_CHECK(); APB(true, 2, 2, 0); }
     else if (ph == 1 && pw == 2) { APB(false, 1, 2, sm); LAUNCH_CHECK(); APB(true, 1, 2, 0); }
     else { crnn_set_error("act_pool: unsupported pool %dx%d", ph, pw); return CRNN_ERR_INVALID; }
@@ -836,8 +927,8 @@ int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, con
     const double invM = 1.0 / (double)M;
     if (C % 4 == 0) {
         chan_block(C / 4, (M + 1) / 2, grid, block);
-        relu6_bwd_kernel<false><<<grid, block, sizeof(float) * 8 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM, rev);
-        LAUNCH_CHECK();
+        if (too_big(M * C)) return CRNN_ERR_INVALID;
+        { const int rc = launch_bn_relu6_reduce(da, y, scale, shift, mean, invstd, red, M, C, rev, 0.f, 0, 0, nullptr, st); if (rc != CRNN_OK) return rc; }
         relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM, !rev);
     } else {
         chan_block(C, M, grid, block);
