@@ -82,6 +82,7 @@ struct crnn_handle {
     Prof prof;
     bool gemm_simt = false;   // CRNN_GEMM_SIMT=1: fp32 SIMT GEMM for the pointwise convs instead of the tcgen05 3xTF32 kernel
     bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
+    bool rnn_simt_cluster = false;   // CRNN_RNN_SIMT_CLUSTER=1: cluster kernels with U in shared memory + FFMA (rnn_cluster.cu) instead of rnn_mma.cu
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
     // stream = a parallel branch of the graph.  CRNN_GRAPH=0 / CRNN_OVERLAP=0 switch either off; profiling runs eager + serial.
@@ -440,7 +441,8 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
             const float* U0 = h->w(h->rnn(layer, 0) + "/recurrent_kernel"); const float* U1 = h->w(h->rnn(layer, 1) + "/recurrent_kernel");
             float* gsave = training ? h->a(nm("gates%d", layer)) : nullptr;
             const double work = 4.0 * B * T * 2 * (G * U + U + (training ? h->GS * U : 0));
-            if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) ST(ST_RNN_FWD, work, launch_gru_fwd_cluster(xp, U0, U1, hs, gsave, B, T, st));
+            if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1 && h->rnn_simt_cluster) ST(ST_RNN_FWD, work, launch_gru_fwd_cluster(xp, U0, U1, hs, gsave, B, T, st));
+            else if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) ST(ST_RNN_FWD, work, launch_gru_fwd_mma(xp, U0, U1, hs, gsave, B, T, st));
             else ST(ST_RNN_FWD, work, launch_rnn_fwd(h->cfg.cell, xp, U0, U1, hs, gsave, B, T, U, st));
         }
         if (layer == 1) { ST(ST_MISC, 0, launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
@@ -462,7 +464,10 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
     const int U = h->U, G = h->G, T = h->T, M = B * T;
     float* UT = h->a("UT"); float* dxp = h->a(nm("dxp%d", layer)); float* hprev = h->a(nm("hprev%d", layer)); float* rh = h->a(nm("rh%d", layer));
     const double bwork = 4.0 * B * T * 2 * (2 * U + h->GS * U + G * U + 2 * U);
-    if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) {
+    if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1 && !h->rnn_simt_cluster) {
+        ST(ST_RNN_BWD, bwork, launch_gru_bwd_mma(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
+                                                 h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, rh, B, T, st));
+    } else if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) {
         ST(ST_RNN_BWD, bwork, launch_gru_bwd_cluster(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
                                                      h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, rh, B, T, st));
     } else {
@@ -673,6 +678,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     if ((size_t)h->L.cursor > workspace_bytes) { crnn_set_error("workspace too small: need %lld bytes", (long long)h->L.cursor); delete h; return CRNN_ERR_NOMEM; }
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_RNN_V1"); h->rnn_v1 = e && e[0] == '1'; }
+    { const char* e = getenv("CRNN_RNN_SIMT_CLUSTER"); h->rnn_simt_cluster = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }

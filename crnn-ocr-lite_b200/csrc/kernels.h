@@ -103,6 +103,10 @@ int launch_rnn_fwd(int cell, const float* xp, const float* U0, const float* U1, 
 int launch_rnn_bwd(int cell, const float* dout, const float* hs, const float* gates, const float* UcatT,
                    float* dxp, float* hprev, float* rh, int B, int T, int U, cudaStream_t st);
 
+// ---- rnn_mma.cu : cluster-resident GRU with U held in registers as mma.sync tf32 fragments (3xTF32), state via DSMEM ----
+int launch_gru_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
+int launch_gru_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
+                       float* dxp, float* hprev, float* rh, int B, int T, cudaStream_t st);
 // ---- rnn_cluster.cu : cluster-resident GRU (U column-sharded over 8 CTAs' shared memory, state via DSMEM) ----
 int launch_gru_fwd_cluster(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
 int launch_gru_bwd_cluster(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
