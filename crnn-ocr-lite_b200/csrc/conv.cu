@@ -821,6 +821,7 @@ inline void chan_block(int C, long long M, dim3& grid, dim3& block) {
 
 int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats, int rev) {
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
+    { const int rc = launch_dwconv_rows(x, k, y, B, H, W, C, 0, stats, rev, st); if (rc <= 0) return rc; }   // row-marching kernel (dwconv_rows.cu) when the shape allows
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
         dim3 grid, block; chan_block(C / 4, ngroups, grid, block);
@@ -834,6 +835,7 @@ int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, in
 int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev) {
     if (accumulate) { crnn_set_error("dwconv_bwd_data: accumulate unsupported"); return CRNN_ERR_INVALID; }
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
+    { const int rc = launch_dwconv_rows(dy, k, dx, B, H, W, C, 1, nullptr, rev, st); if (rc <= 0) return rc; }
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
         dim3 grid, block; chan_block(C / 4, ngroups, grid, block);

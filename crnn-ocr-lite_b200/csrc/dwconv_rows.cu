@@ -1,0 +1,176 @@
+// dwconv_rows.cu -- row-marching DepthwiseConv2D 3x3 'same' kernels (forward, backward-data, backward-weight) for sm_100a.
+// Reference op: utils.py:44-46 (DepthwiseConv2D(3x3, same, stride 1, depth_multiplier 1, no bias)), NHWC fp32.
+//
+// The channel-block kernel in conv.cu gives every thread one (row, 4-column group) item: 18 input loads for 4 outputs, i.e. every
+// input element is fetched 4.5 times (L1/L2 absorb it, but the LSU does not) and ~210 instructions are issued per output float4;
+// ncu r1h shows it at 20-26 % of HBM peak, 52 % of its stalls on the long scoreboard, 2 CTAs per SM.  An HBM-bound op should not be
+// instruction/latency bound, so here a thread owns 4 channels x 3 adjacent columns and MARCHES DOWN a strip of image rows:
+//   * input row r (5 float4: the 3 columns + 1 halo column each side) is loaded once and scattered into THREE output-row
+//     accumulators (rows r-1, r, r+1), so vertical reuse lives in registers: 5 loads per 3 outputs (1.67x instead of 4.5x);
+//   * the next row's loads are issued before the current row's 108 FFMAs (register double buffer) -> 10 independent 16-byte
+//     loads in flight per thread, no shared-memory staging, no barriers;
+//   * the nine taps are read from shared memory (conflict-free LDS.128) instead of occupying 36 registers;
+//   * ~45 issued instructions per output float4.
+// Strips are RS rows of one image (halo re-read (RS+2)/RS, mostly L2 hits because neighbouring strips run concurrently); RS is
+// chosen by the launcher so the grid fills whole waves of 148 SMs x resident CTAs.
+#include <algorithm>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, const float4 x, const float4 k) {
+    a.x = fmaf(x.x, k.x, a.x); a.y = fmaf(x.y, k.y, a.y); a.z = fmaf(x.z, k.z, a.z); a.w = fmaf(x.w, k.w, a.w);
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+constexpr int SEG = 3;          // output columns per thread
+constexpr int NTHR = 256;
+
+// Work item = (image b, strip, column segment); blockDim = (CQ channel quads, PY items).
+// y[r][w] = sum_{i,j} x[r+i-1][w+j-1] * kk[i][j], kk = k (forward) or k rotated by 180 degrees (FLIP: backward-data).
+template <bool FLIP, bool STATS>
+__global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
+                                                                 int H, int W, int C4, int nseg, int nstrips, int RS, int nitems,
+                                                                 double* __restrict__ stats, int rev)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float4* ks = reinterpret_cast<float4*>(smraw);              // [9][CQ] taps of this CTA's channel quads
+    const int CQ = blockDim.x, PY = blockDim.y;
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    const int C = C4 * 4;
+    const bool cok = c4 < C4;
+    if (cok)
+        for (int q = threadIdx.y; q < 9; q += PY) ks[q * CQ + threadIdx.x] = ldg4(k + (size_t)(FLIP ? 8 - q : q) * C + c4 * 4);
+    __syncthreads();
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    int item = blockIdx.y * PY + threadIdx.y;
+    if (cok && item < nitems) {
+        if (rev) item = nitems - 1 - item;
+        const int seg = item % nseg; const int t1 = item / nseg;
+        const int strip = t1 % nstrips; const int b = t1 / nstrips;
+        const int w0 = seg * SEG;
+        const int hs = strip * RS, he = min(H, hs + RS);
+        const bool lok = w0 > 0, rok = w0 + SEG < W;                 // halo columns inside the image?
+        const float4* kq = ks + threadIdx.x;
+        // pointer to column w0-1 of virtual row hs-1
+        const float* xrow = x + (((size_t)b * H + hs - 1) * W + (w0 - 1)) * C + c4 * 4;
+        float* yrow = y + (((size_t)b * H + hs) * W + w0) * C + c4 * 4;
+        const size_t rstride = (size_t)W * C;
+        float4 acc[3][SEG];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int o = 0; o < SEG; ++o) acc[a][o] = zero4();
+        float4 xb[2][SEG + 2];
+        auto load_row = [&](float4 (&d)[SEG + 2], int r, const float* p) {
+            const bool v = r >= 0 && r < H;
+            d[0] = (v && lok) ? ldg4(p) : zero4();
+#pragma unroll
+            for (int t = 1; t <= SEG; ++t) d[t] = v ? ldg4(p + (size_t)t * C) : zero4();
+            d[SEG + 1] = (v && rok) ? ldg4(p + (size_t)(SEG + 1) * C) : zero4();
+        };
+        const int nsteps = he - hs + 2;                              // virtual input rows hs-1 .. he
+        load_row(xb[0], hs - 1, xrow);
+        for (int base = 0; base < nsteps; base += 6) {
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int q = base + u;
+                if (q < nsteps) {
+                    const int r = hs - 1 + q;
+                    if (q + 1 < nsteps) load_row(xb[(u + 1) & 1], r + 1, xrow + (size_t)(q + 1) * rstride);
+                    float4 (&xc)[SEG + 2] = xb[u & 1];
+                    float4 (&A)[SEG] = acc[u % 3];               // output row r-1 (gets tap row 2)
+                    float4 (&Bm)[SEG] = acc[(u + 1) % 3];        // output row r   (tap row 1)
+                    float4 (&Cn)[SEG] = acc[(u + 2) % 3];        // output row r+1 (tap row 0)
+                    if (r >= 0 && r < H) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const float4 k0 = kq[(0 * 3 + j) * CQ], k1 = kq[(1 * 3 + j) * CQ], k2 = kq[(2 * 3 + j) * CQ];
+#pragma unroll
+                            for (int o = 0; o < SEG; ++o) { fma4(A[o], xc[o + j], k2); fma4(Bm[o], xc[o + j], k1); fma4(Cn[o], xc[o + j], k0); }
+                        }
+                    }
+                    if (q >= 2) {                                    // output row r-1 = hs + q - 2 is complete
+                        float* dst = yrow + (size_t)(q - 2) * rstride;
+#pragma unroll
+                        for (int o = 0; o < SEG; ++o) {
+                            *reinterpret_cast<float4*>(dst + (size_t)o * C) = A[o];
+                            if (STATS) {
+                                s[0] += A[o].x; s[1] += A[o].y; s[2] += A[o].z; s[3] += A[o].w;
+                                sq[0] = fmaf(A[o].x, A[o].x, sq[0]); sq[1] = fmaf(A[o].y, A[o].y, sq[1]);
+                                sq[2] = fmaf(A[o].z, A[o].z, sq[2]); sq[3] = fmaf(A[o].w, A[o].w, sq[3]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < SEG; ++o) A[o] = zero4();    // becomes the "row r+2" accumulator of the next step
+                }
+            }
+        }
+    }
+    if (!STATS) return;
+    // BatchNorm statistics of the outputs (fp32 per thread over <= RS x 3 values, fp64 across threads): one atomic pair per channel and CTA
+    __syncthreads();                                                 // taps no longer needed: reuse the buffer
+    double* dsm = reinterpret_cast<double*>(smraw);                  // [PY][8][CQ]
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        dsm[(threadIdx.y * 8 + e) * CQ + threadIdx.x] = (double)s[e];
+        dsm[(threadIdx.y * 8 + 4 + e) * CQ + threadIdx.x] = (double)sq[e];
+    }
+    __syncthreads();
+    for (int e = threadIdx.y; e < 8; e += PY) {
+        if (!cok) break;
+        double t = 0.0;
+        for (int i = 0; i < PY; ++i) t += dsm[(i * 8 + e) * CQ + threadIdx.x];
+        atomicAdd(stats + (e >> 2) * C + c4 * 4 + (e & 3), t);
+    }
+}
+
+bool g_rows_disabled = false, g_rows_env_read = false;
+bool rows_enabled() {
+    if (!g_rows_env_read) { const char* e = getenv("CRNN_DWCONV_V1"); g_rows_disabled = e && e[0] == '1'; g_rows_env_read = true; }
+    return !g_rows_disabled;
+}
+
+// strips per image: RS = ceil(H / n) rows (at least 6), n chosen to maximise (fill of the last wave of 148 SMs x `occ` resident CTAs)
+// x (useful rows per loaded row) x (balance of the short last strip); ties -> longer strips
+void plan_rows(int B, int H, int W, int C4, int occ, dim3& grid, dim3& block, int& nseg, int& nstrips, int& RS, int& nitems) {
+    const int CQ = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
+    const int PY = NTHR / CQ, gx = (C4 + CQ - 1) / CQ;
+    nseg = W / SEG;
+    double best = -1.0; int bestd = 1;
+    for (int n = 1; n <= H; ++n) {
+        const int rs = (H + n - 1) / n;
+        if (rs < 6 && n > 1) break;
+        const int d = (H + rs - 1) / rs;                         // strips actually needed with this strip length
+        const long long items = (long long)B * d * nseg;
+        const long long ctas = (long long)gx * ((items + PY - 1) / PY);
+        const long long cap = 148LL * occ;
+        const double eff = (double)ctas / (double)(((ctas + cap - 1) / cap) * cap) * ((double)rs / (rs + 2)) * ((double)H / ((double)d * rs));
+        if (eff > best + 1e-9) { best = eff; bestd = d; }
+    }
+    nstrips = bestd; RS = (H + bestd - 1) / bestd;
+    nstrips = (H + RS - 1) / RS;
+    nitems = B * nstrips * nseg;
+    grid = dim3(gx, (unsigned)((nitems + PY - 1) / PY)); block = dim3(CQ, PY);
+}
+
+}  // namespace
+
+// returns CRNN_OK when the row-marching kernel ran, 1 when the shape is not covered (caller falls back to the channel-block kernel)
+int launch_dwconv_rows(const float* x, const float* k, float* y, int B, int H, int W, int C, int flip, double* stats, int rev, cudaStream_t st)
+{
+    if (!rows_enabled() || C % 4 || W % SEG || W < SEG || (flip && stats)) return 1;
+    dim3 grid, block; int nseg, nstrips, RS, nitems;
+    plan_rows(B, H, W, C / 4, 2, grid, block, nseg, nstrips, RS, nitems);
+    const size_t sm = std::max(sizeof(float4) * 9 * block.x, stats ? sizeof(double) * 8 * NTHR : (size_t)0);
+    if (flip) dwconv3x3_rows_kernel<true, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev);
+    else if (stats) dwconv3x3_rows_kernel<false, true><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev);
+    else dwconv3x3_rows_kernel<false, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
