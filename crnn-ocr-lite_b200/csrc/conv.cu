@@ -846,6 +846,7 @@ int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, in
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk, int B, int H, int W, int C, cudaStream_t st) {
+    { const int rc = launch_dwconv_rows_bwd_weight(x, dy, dk, B, H, W, C, st); if (rc <= 0) return rc; }
     dim3 grid, block; long long npix = (long long)B * H * W;
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;

@@ -130,6 +130,93 @@ __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __
     }
 }
 
+// Backward-weight: dk[i][j][c] = sum_{b,r,w} x[r+i-1][w+j-1][c] * dy[r][w][c].  Same marching scheme with 2 output columns per thread:
+// input row r of x (4 float4 incl. halo) meets the three dy rows r+1, r, r-1 (tap rows 0, 1, 2) that live in a 4-slot register ring
+// (the slot of row r-3 is refilled with row r+2 one step ahead); the nine tap accumulators (36 registers) stay put for the whole strip
+// and are reduced across the CTA through shared memory, then one fp32 atomic per tap/channel and CTA.
+constexpr int SEGW = 2;
+__global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
+                                                                            int H, int W, int C4, int nseg, int nstrips, int RS, int nitems)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* red = reinterpret_cast<float*>(smraw);               // [PY][36][CQ]
+    const int CQ = blockDim.x, PY = blockDim.y;
+    const int c4 = blockIdx.x * CQ + threadIdx.x;
+    const int C = C4 * 4;
+    const bool cok = c4 < C4;
+    float4 acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = zero4();
+    const int item = blockIdx.y * PY + threadIdx.y;
+    if (cok && item < nitems) {
+        const int seg = item % nseg; const int t1 = item / nseg;
+        const int strip = t1 % nstrips; const int b = t1 / nstrips;
+        const int w0 = seg * SEGW;
+        const int hs = strip * RS, he = min(H, hs + RS);
+        bool xok[SEGW + 2], dok[SEGW];
+#pragma unroll
+        for (int t = 0; t < SEGW + 2; ++t) xok[t] = (w0 - 1 + t) >= 0 && (w0 - 1 + t) < W;
+#pragma unroll
+        for (int o = 0; o < SEGW; ++o) dok[o] = (w0 + o) < W;
+        const size_t rstride = (size_t)W * C;
+        const float* xrow = x + (((size_t)b * H + hs - 1) * W + (w0 - 1)) * C + c4 * 4;   // column w0-1 of virtual row hs-1
+        const float* drow = dy + (((size_t)b * H + hs) * W + w0) * C + c4 * 4;            // column w0 of row hs
+        float4 xb[2][SEGW + 2], dr[4][SEGW];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int o = 0; o < SEGW; ++o) dr[a][o] = zero4();
+        auto load_x = [&](float4 (&d)[SEGW + 2], int r, const float* p) {
+            const bool v = r >= 0 && r < H;
+#pragma unroll
+            for (int t = 0; t < SEGW + 2; ++t) d[t] = (v && xok[t]) ? ldg4(p + (size_t)t * C) : zero4();
+        };
+        auto load_dy = [&](float4 (&d)[SEGW], int rho, const float* p) {
+            const bool v = rho >= hs && rho < he;
+#pragma unroll
+            for (int o = 0; o < SEGW; ++o) d[o] = (v && dok[o]) ? ldg4(p + (size_t)o * C) : zero4();
+        };
+        const int nsteps = he - hs + 2;                              // virtual x rows hs-1 .. he
+        load_x(xb[0], hs - 1, xrow);
+        load_dy(dr[0], hs, drow);
+        for (int base = 0; base < nsteps; base += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = base + u;
+                if (q < nsteps) {
+                    const int r = hs - 1 + q;
+                    if (q + 1 < nsteps) {
+                        load_x(xb[(u + 1) & 1], r + 1, xrow + (size_t)(q + 1) * rstride);
+                        load_dy(dr[(u + 1) & 3], hs + q + 1, drow + (size_t)(q + 1) * rstride);
+                    }
+                    if (r >= 0 && r < H) {
+                        float4 (&xc)[SEGW + 2] = xb[u & 1];
+                        float4 (&d0)[SEGW] = dr[u & 3];              // dy row r+1 -> tap row 0
+                        float4 (&d1)[SEGW] = dr[(u + 3) & 3];        // dy row r   -> tap row 1
+                        float4 (&d2)[SEGW] = dr[(u + 2) & 3];        // dy row r-1 -> tap row 2
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+#pragma unroll
+                            for (int o = 0; o < SEGW; ++o) { fma4(acc[0 + j], xc[o + j], d0[o]); fma4(acc[3 + j], xc[o + j], d1[o]); fma4(acc[6 + j], xc[o + j], d2[o]); }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        red[((threadIdx.y * 36) + q * 4 + 0) * CQ + threadIdx.x] = acc[q].x; red[((threadIdx.y * 36) + q * 4 + 1) * CQ + threadIdx.x] = acc[q].y;
+        red[((threadIdx.y * 36) + q * 4 + 2) * CQ + threadIdx.x] = acc[q].z; red[((threadIdx.y * 36) + q * 4 + 3) * CQ + threadIdx.x] = acc[q].w;
+    }
+    __syncthreads();
+    if (cok)
+        for (int e = threadIdx.y; e < 36; e += PY) {
+            float sum = 0.f;
+            for (int yy = 0; yy < PY; ++yy) sum += red[(yy * 36 + e) * CQ + threadIdx.x];
+            atomicAdd(dk + (size_t)(e >> 2) * C + c4 * 4 + (e & 3), sum);
+        }
+}
+
 bool g_rows_disabled = false, g_rows_env_read = false;
 bool rows_enabled() {
     if (!g_rows_env_read) { const char* e = getenv("CRNN_DWCONV_V1"); g_rows_disabled = e && e[0] == '1'; g_rows_env_read = true; }
@@ -138,10 +225,10 @@ bool rows_enabled() {
 
 // strips per image: RS = ceil(H / n) rows (at least 6), n chosen to maximise (fill of the last wave of 148 SMs x `occ` resident CTAs)
 // x (useful rows per loaded row) x (balance of the short last strip); ties -> longer strips
-void plan_rows(int B, int H, int W, int C4, int occ, dim3& grid, dim3& block, int& nseg, int& nstrips, int& RS, int& nitems) {
+void plan_rows(int B, int H, int W, int C4, int occ, int segw, dim3& grid, dim3& block, int& nseg, int& nstrips, int& RS, int& nitems) {
     const int CQ = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
     const int PY = NTHR / CQ, gx = (C4 + CQ - 1) / CQ;
-    nseg = W / SEG;
+    nseg = (W + segw - 1) / segw;
     double best = -1.0; int bestd = 1;
     for (int n = 1; n <= H; ++n) {
         const int rs = (H + n - 1) / n;
@@ -166,11 +253,21 @@ int launch_dwconv_rows(const float* x, const float* k, float* y, int B, int H, i
 {
     if (!rows_enabled() || C % 4 || W % SEG || W < SEG || (flip && stats)) return 1;
     dim3 grid, block; int nseg, nstrips, RS, nitems;
-    plan_rows(B, H, W, C / 4, 2, grid, block, nseg, nstrips, RS, nitems);
+    plan_rows(B, H, W, C / 4, 2, SEG, grid, block, nseg, nstrips, RS, nitems);
     const size_t sm = std::max(sizeof(float4) * 9 * block.x, stats ? sizeof(double) * 8 * NTHR : (size_t)0);
     if (flip) dwconv3x3_rows_kernel<true, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev);
     else if (stats) dwconv3x3_rows_kernel<false, true><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev);
     else dwconv3x3_rows_kernel<false, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
+
+int launch_dwconv_rows_bwd_weight(const float* x, const float* dy, float* dk, int B, int H, int W, int C, cudaStream_t st)
+{
+    if (!rows_enabled() || C % 4) return 1;
+    dim3 grid, block; int nseg, nstrips, RS, nitems;
+    plan_rows(B, H, W, C / 4, 2, SEGW, grid, block, nseg, nstrips, RS, nitems);
+    dwconv3x3_rows_bwd_weight_kernel<<<grid, block, sizeof(float) * 36 * NTHR, st>>>(x, dy, dk, H, W, C / 4, nseg, nstrips, RS, nitems);
     LAUNCH_CHECK();
     return CRNN_OK;
 }

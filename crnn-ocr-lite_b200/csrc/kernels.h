@@ -42,6 +42,7 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
 int launch_dwconv_fwd(const float* x, const float* k33c, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats = nullptr, int rev = 0);
 int launch_dwconv_bwd_data(const float* dy, const float* k33c, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev = 0);
 // dwconv_rows.cu: row-marching variants; return 1 (not an error) when the shape is not covered and the caller must fall back
+int launch_dwconv_rows_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
 int launch_dwconv_rows(const float* x, const float* k33c, float* y, int B, int H, int W, int C, int flip, double* stats, int rev, cudaStream_t st);
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
 // per-channel sum / sum of squares over rows of y[M][C] -> stats[0..C) , stats[C..2C) (double, pre-zeroed)
