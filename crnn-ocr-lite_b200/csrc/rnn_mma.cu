@@ -9,14 +9,13 @@
 //     forward : out^T (96 gate columns x 8 rows) = Ushard^T (96 x 256) . h^T (256 x 8)
 //     backward: dh^T  (256 units x 8 rows)       = Ushard   (256 x 96) . da^T (96 x 8)
 // U never changes during the sequence, so every warp loads its A fragments ONCE: the tf32 "hi" part as 48 registers per thread and
-// the residual "lo" part (scaled by 2^11) as 24 registers of packed fp16 -- 72 of the 128 registers of a 512-thread CTA, 144 KB of
-// the SM's register file.  Per step a warp only reads the tiny h / da operand from shared memory (conflict-free B fragments) and
-// issues 12-36 MMAs.  fp32 fidelity: a.b = a_hi.b_hi + a_hi.b_lo + a_lo.b_hi ("3xTF32", the dropped a_lo.b_lo term is 2^-22 relative).
+// the residual "lo" part as 24 registers of packed bf16 -- 72 of the 128 registers of a 512-thread CTA, 144 KB of the SM's register
+// file.  Per step a warp only reads the tiny h / da operand from shared memory (conflict-free B fragments) and issues 8-24 MMAs.
+// fp32 fidelity: a.b = a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (the dropped a_lo.b_lo term is 2^-22 relative), see mma2() below.
 // tcgen05 is not used here on purpose: with M = 8 batch rows per step the problem is latency-, not throughput-bound, and the
 // smem-descriptor / commit / tcgen05.ld round trip of one UMMA is longer than this whole register-resident mma.sync chain.
 // Same math as rnn.cu / the oracle (Keras 2.2.2 GRUCell reset_after=False, hard_sigmoid).
 #include <cooperative_groups.h>
-#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -29,7 +28,6 @@ constexpr int NCTA = 8;       // CTAs per cluster
 constexpr int UPC = U / NCTA; // units per CTA (32)
 constexpr int RB = 8;         // batch rows per cluster (= N of the MMA)
 constexpr int NT = 512;       // threads per CTA (16 warps)
-constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t map_rank(uint32_t saddr, uint32_t rank) {
@@ -73,29 +71,44 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// One A fragment (16 x 8 slice of the stationary matrix), split for 3xTF32: hi = tf32(a); lo = fp16((a - hi) * 2^11), two per register.
-struct AFrag { uint32_t hi[4]; __half2 lo[2]; };
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// fp32-faithful product on the legacy tensor path in TWO instructions per 16x8x8 block instead of the three of "3xTF32":
+//   a.b = a_hi.b_hi  (tf32 m16n8k8)  +  [ a_hi.b_lo + a_lo.b_hi ]  (ONE bf16 m16n8k16)
+// The two cross terms are 2^-11 smaller than the main term, so bf16 operands (8 bits) are enough for them (error <= ~2^-19 of the
+// product); they share one k16 MMA by interleaving along k: slot 2t <- (a_hi', b_lo), slot 2t+1 <- (a_lo, b_hi').  The element
+// (row, k) -> register mapping of the bf16 A/B fragments is then exactly that of the tf32 fragments, so a_hi' is just the upper half
+// of the tf32 register (one PRMT) and the residuals are stored as packed bf16 pairs.  (HMMA.1688.F32.TF32 issues once per ~13 cycles
+// per SM sub-partition on B200 -- ncu r1j: the tensor pipe was the floor of every step.)
+struct AFrag { uint32_t hi[4]; uint32_t lo[2]; };   // hi: tf32 bit patterns; lo: bf16(a - hi) of elements (0,1) and (2,3)
+__device__ __forceinline__ uint32_t pack_bf16(float lo_half, float hi_half) {   // result = {hi_half -> bits 31:16, lo_half -> bits 15:0}
+    uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half)); return r;
+}
 __device__ __forceinline__ void afrag_set(AFrag& f, float a0, float a1, float a2, float a3) {
     const float a[4] = {a0, a1, a2, a3};
     float l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { f.hi[i] = to_tf32(a[i]); l[i] = (a[i] - __uint_as_float(f.hi[i])) * LO_SCALE; }
-    f.lo[0] = __floats2half2_rn(l[0], l[1]); f.lo[1] = __floats2half2_rn(l[2], l[3]);
+    for (int i = 0; i < 4; ++i) { f.hi[i] = to_tf32(a[i]); l[i] = a[i] - __uint_as_float(f.hi[i]); }
+    f.lo[0] = pack_bf16(l[0], l[1]); f.lo[1] = pack_bf16(l[2], l[3]);
 }
-// acc_m += A_hi.b_hi, acc_x += A_hi.b_lo, acc_l += (2^11 A_lo).b_hi   (three independent accumulators: dependent chains stay short)
-__device__ __forceinline__ void mma3(float (&am)[4], float (&ax)[4], float (&al)[4], const AFrag& f, uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-    const float2 l01 = __half22float2(f.lo[0]), l23 = __half22float2(f.lo[1]);
-    const uint32_t lo[4] = {__float_as_uint(l01.x), __float_as_uint(l01.y), __float_as_uint(l23.x), __float_as_uint(l23.y)};   // fp16 values are exact tf32
-    mma_tf32(am, f.hi, bh0, bh1);
-    mma_tf32(ax, f.hi, bl0, bl1);
-    mma_tf32(al, lo, bh0, bh1);
-}
-// B fragment (k8 x n8) of a [k][row] (row fastest, 8 floats per k) shared-memory operand, split hi/lo
-__device__ __forceinline__ void bfrag(const float* __restrict__ p, int k0, int gid, int tig, uint32_t& bh0, uint32_t& bh1, uint32_t& bl0, uint32_t& bl1) {
+// B fragment (k8 x n8) of a [k][row] (row fastest, 8 floats per k) shared-memory operand: tf32 hi parts + packed {b_lo, b_hi'} pairs
+struct BFrag { uint32_t h0, h1, x0, x1; };
+__device__ __forceinline__ BFrag bfrag(const float* __restrict__ p, int k0, int gid, int tig) {
     const float b0 = p[(k0 + tig) * RB + gid], b1 = p[(k0 + tig + 4) * RB + gid];
-    bh0 = to_tf32(b0); bh1 = to_tf32(b1);
-    bl0 = __float_as_uint(b0 - __uint_as_float(bh0)); bl1 = __float_as_uint(b1 - __uint_as_float(bh1));   // the MMA truncates to tf32
+    BFrag f;
+    f.h0 = to_tf32(b0); f.h1 = to_tf32(b1);
+    const float h0 = __uint_as_float(f.h0), h1 = __uint_as_float(f.h1);
+    f.x0 = pack_bf16(b0 - h0, h0); f.x1 = pack_bf16(b1 - h1, h1);        // slot 2t: b_lo, slot 2t+1: b_hi'
+    return f;
 }
+// acc_m += A_hi.B_hi ; acc_x += cross terms   (two accumulators: the dependent MMA chains stay short)
+__device__ __forceinline__ void mma2(float (&am)[4], float (&ax)[4], const uint32_t (&hi)[4], uint32_t lo01, uint32_t lo23, const BFrag& b) {
+    mma_tf32(am, hi, b.h0, b.h1);
+    mma_bf16(ax, __byte_perm(hi[0], lo01, 0x5432), __byte_perm(hi[1], lo01, 0x7632), __byte_perm(hi[2], lo23, 0x5432), __byte_perm(hi[3], lo23, 0x7632), b.x0, b.x1);
+}
+__device__ __forceinline__ void mma2(float (&am)[4], float (&ax)[4], const AFrag& f, const BFrag& b) { mma2(am, ax, f.hi, f.lo[0], f.lo[1], b); }
 
 // Broadcast one value per (unit, row) to the same offset of `buf` in all 8 CTAs, signalling each destination's barrier.  Rows are the
 // fastest index (er = lane & 7): the lanes with er % 4 == 0 gather their 4-row group with shuffles -> one 16-byte st.async per destination.
@@ -186,19 +199,18 @@ gru_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, c
         if (s > 0) bar_wait(&barH[(s - 1) & 1], ((s - 1) >> 1) & 1);      // h_{t-1} of all 256 units has landed
         // ---- phase A: z / r pre-activation partials of the k-slice
         {
-            float am[2][4] = {}, al[2][4] = {};            // (hi.hi + hi.lo) and lo.hi chains; 2 m-tiles interleave
+            float am[2][4] = {}, ax[2][4] = {};            // main and cross-term chains; 2 m-tiles interleave
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                uint32_t bh0, bh1, bl0, bl1;
-                bfrag(hcur, 32 * ks + 8 * kk, gid, tig, bh0, bh1, bl0, bl1);
+                const BFrag bf = bfrag(hcur, 32 * ks + 8 * kk, gid, tig);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) mma3(am[mt], am[mt], al[mt], fa[mt][kk], bh0, bh1, bl0, bl1);
+                for (int mt = 0; mt < 2; ++mt) mma2(am[mt], ax[mt], fa[mt][kk], bf);
             }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 float* p = partA + ((ks * 64 + mp * 32 + 16 * mt + gid) * RB + 2 * tig);
-                *reinterpret_cast<float2*>(p) = make_float2(fmaf(al[mt][0], LO_UNSCALE, am[mt][0]), fmaf(al[mt][1], LO_UNSCALE, am[mt][1]));
-                *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(fmaf(al[mt][2], LO_UNSCALE, am[mt][2]), fmaf(al[mt][3], LO_UNSCALE, am[mt][3]));
+                *reinterpret_cast<float2*>(p) = make_float2(am[mt][0] + ax[mt][0], am[mt][1] + ax[mt][1]);
+                *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[mt][2] + ax[mt][2], am[mt][3] + ax[mt][3]);
             }
         }
         const float hown = hcur[j * RB + er];
@@ -217,16 +229,12 @@ gru_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, c
         bar_wait(&barR[cur], ph);
         // ---- phase B: candidate pre-activation partials
         {
-            float am[4] = {}, ax[4] = {}, al[4] = {};
+            float am[4] = {}, ax[4] = {};
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                uint32_t bh0, bh1, bl0, bl1;
-                bfrag(rhc, 32 * ks + 8 * kk, gid, tig, bh0, bh1, bl0, bl1);
-                mma3(am, ax, al, fb[kk], bh0, bh1, bl0, bl1);
-            }
+            for (int kk = 0; kk < 4; ++kk) mma2(am, ax, fb[kk], bfrag(rhc, 32 * ks + 8 * kk, gid, tig));
             float* p = partB + ((ks * 32 + 16 * mp + gid) * RB + 2 * tig);
-            *reinterpret_cast<float2*>(p) = make_float2(am[0] + ax[0] + al[0] * LO_UNSCALE, am[1] + ax[1] + al[1] * LO_UNSCALE);
-            *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[2] + ax[2] + al[2] * LO_UNSCALE, am[3] + ax[3] + al[3] * LO_UNSCALE);
+            *reinterpret_cast<float2*>(p) = make_float2(am[0] + ax[0], am[1] + ax[1]);
+            *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[2] + ax[2], am[3] + ax[3]);
         }
         __syncthreads();
         if (tid == 0) bar_expect(&barH[cur], XCHG_BYTES);
@@ -345,14 +353,10 @@ gru_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs,
         __syncthreads();
         // ---- d(r*h) partial of the warp's 16 units from the own 32 candidate-gate columns; reduce-scatter into recvA
         {
-            float am[4] = {}, ax[4] = {}, al[4] = {};
+            float am[4] = {}, ax[4] = {};
 #pragma unroll
-            for (int kk = 8; kk < 12; ++kk) {
-                uint32_t bh0, bh1, bl0, bl1;
-                bfrag(da, 8 * kk, gid, tig, bh0, bh1, bl0, bl1);
-                mma3(am, ax, al, fu[kk], bh0, bh1, bl0, bl1);
-            }
-            const float c[4] = {am[0] + ax[0] + al[0] * LO_UNSCALE, am[1] + ax[1] + al[1] * LO_UNSCALE, am[2] + ax[2] + al[2] * LO_UNSCALE, am[3] + ax[3] + al[3] * LO_UNSCALE};
+            for (int kk = 8; kk < 12; ++kk) mma2(am, ax, fu[kk], bfrag(da, 8 * kk, gid, tig));
+            const float c[4] = {am[0] + ax[0], am[1] + ax[1], am[2] + ax[2], am[3] + ax[3]};
             push_tile(c, recvA, barA, owner, crank, ubase, gid, tig);
         }
         if (tid == 0) bar_expect(barA, XCHG_BYTES);
@@ -373,14 +377,10 @@ gru_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs,
         __syncthreads();
         // ---- dh_{t-1} partial from the z and r gates (64 own columns); reduce-scatter into recvB
         {
-            float am[4] = {}, ax[4] = {}, al[4] = {};
+            float am[4] = {}, ax[4] = {};
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                uint32_t bh0, bh1, bl0, bl1;
-                bfrag(da, 8 * kk, gid, tig, bh0, bh1, bl0, bl1);
-                mma3(am, ax, al, fu[kk], bh0, bh1, bl0, bl1);
-            }
-            const float c[4] = {am[0] + ax[0] + al[0] * LO_UNSCALE, am[1] + ax[1] + al[1] * LO_UNSCALE, am[2] + ax[2] + al[2] * LO_UNSCALE, am[3] + ax[3] + al[3] * LO_UNSCALE};
+            for (int kk = 0; kk < 8; ++kk) mma2(am, ax, fu[kk], bfrag(da, 8 * kk, gid, tig));
+            const float c[4] = {am[0] + ax[0], am[1] + ax[1], am[2] + ax[2], am[3] + ax[3]};
             push_tile(c, recvB, barB, owner, crank, ubase, gid, tig);
         }
         if (tid == 0) bar_expect(barB, XCHG_BYTES);
