@@ -443,6 +443,7 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
             const double work = 4.0 * B * T * 2 * (G * U + U + (training ? h->GS * U : 0));
             if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1 && h->rnn_simt_cluster) ST(ST_RNN_FWD, work, launch_gru_fwd_cluster(xp, U0, U1, hs, gsave, B, T, st));
             else if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) ST(ST_RNN_FWD, work, launch_gru_fwd_mma(xp, U0, U1, hs, gsave, B, T, st));
+            else if (h->cfg.cell == CRNN_CELL_LSTM && !h->rnn_v1 && U == 256) ST(ST_RNN_FWD, work, launch_lstm_fwd_mma(xp, U0, U1, hs, gsave, B, T, st));
             else ST(ST_RNN_FWD, work, launch_rnn_fwd(h->cfg.cell, xp, U0, U1, hs, gsave, B, T, U, st));
         }
         if (layer == 1) { ST(ST_MISC, 0, launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
@@ -467,6 +468,9 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
     if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1 && !h->rnn_simt_cluster) {
         ST(ST_RNN_BWD, bwork, launch_gru_bwd_mma(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
                                                  h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, rh, B, T, st));
+    } else if (h->cfg.cell == CRNN_CELL_LSTM && !h->rnn_v1 && U == 256) {
+        ST(ST_RNN_BWD, bwork, launch_lstm_bwd_mma(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
+                                                  h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, B, T, st));
     } else if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) {
         ST(ST_RNN_BWD, bwork, launch_gru_bwd_cluster(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
                                                      h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, rh, B, T, st));

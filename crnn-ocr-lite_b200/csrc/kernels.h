@@ -110,6 +110,9 @@ int launch_rnn_bwd(int cell, const float* dout, const float* hs, const float* ga
 int launch_gru_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
 int launch_gru_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
                        float* dxp, float* hprev, float* rh, int B, int T, cudaStream_t st);
+int launch_lstm_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
+int launch_lstm_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
+                        float* dxp, float* hprev, int B, int T, cudaStream_t st);
 // ---- rnn_cluster.cu : cluster-resident GRU (U column-sharded over 8 CTAs' shared memory, state via DSMEM) ----
 int launch_gru_fwd_cluster(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
 int launch_gru_bwd_cluster(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,

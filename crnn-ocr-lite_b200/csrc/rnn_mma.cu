@@ -401,6 +401,261 @@ gru_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs,
     }
     cluster.sync();               // nobody exits while a peer may still address its shared memory
 }
+
+// ================================================================================================= LSTM
+// Keras 2.2.2 LSTMCell: kernel columns [i, f, c, o], i/f/o = hard_sigmoid, c' = f*c + i*tanh(.), h' = o*tanh(c').
+// One exchange per step (no r*h dependency): every CTA owns 32 units x 4 gates = 128 columns of U (256 x 1024).  The tf32 hi parts of
+// its 16 A fragments take 64 registers per thread; the bf16 residual pairs do not fit beside them and live in shared memory in
+// fragment order (one conflict-free LDS.64 per fragment and step).
+constexpr int LG = 4;                 // gates
+constexpr int LC = LG * UPC;          // gate columns per CTA (128)
+constexpr int LFR = 16;               // A fragments per warp
+
+// ---- forward.  warp = (k-quarter kq: 64 k = 8 k-steps, gate g: 2 m-tiles of 16 units)
+// smem: hT[2][256][8] | part[4][128][8] | lo[16][512] uint2 | xring[RING][4][256] | 2 mbarriers
+constexpr int LF_SMEM_BYTES = 4 * (2 * U * RB + 4 * LC * RB + RING * 4 * (UPC * RB)) + 8 * LFR * NT + 32;
+
+__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
+lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, const float* __restrict__ U1,
+                    float* __restrict__ hs, float* __restrict__ gates, int B, int T)
+{
+    extern __shared__ __align__(16) float sm[];
+    float* hT = sm;                                 // [2][256][8]
+    float* part = hT + 2 * U * RB;                  // [4 k-quarters][128 cols (gate-major)][8 rows]
+    uint2* los = reinterpret_cast<uint2*>(part + 4 * LC * RB);     // [16 frags][512 threads]
+    float* xring = reinterpret_cast<float*>(los + LFR * NT);       // [RING][4 gates][256]
+    uint64_t* barH = reinterpret_cast<uint64_t*>(xring + RING * 4 * (UPC * RB));   // [2]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int dir = blockIdx.y, b0 = (blockIdx.x / NCTA) * RB;
+    const float* Um = dir ? U1 : U0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int kq = warp & 3, g = warp >> 2;
+
+    uint32_t fh[2][8][4];                           // tf32 hi parts of the A fragments (m-tile, k-step)
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const float* r0 = Um + (size_t)(64 * kq + 8 * kk + tig) * (LG * U);
+        const float* r1 = r0 + (size_t)4 * (LG * U);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int c = g * U + crank * UPC + 16 * mt + gid;
+            AFrag f; afrag_set(f, __ldg(r0 + c), __ldg(r0 + c + 8), __ldg(r1 + c), __ldg(r1 + c + 8));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fh[mt][kk][i] = f.hi[i];
+            los[(mt * 8 + kk) * NT + tid] = make_uint2(f.lo[0], f.lo[1]);
+        }
+    }
+    for (int i = tid; i < 2 * U * RB; i += NT) hT[i] = 0.f;
+    if (tid == 0) {
+        bar_init(&barH[0], 1); bar_init(&barH[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster.sync();
+
+    const bool ew = tid < UPC * RB;                 // element-wise threads: unit eu x row er
+    const int er = tid & 7, eu = (tid >> 3) & 31;
+    const int j = crank * UPC + eu;
+    const int b = b0 + er;
+    const bool valid = b < B;
+    const int bb = valid ? b : B - 1;
+    constexpr int EW = UPC * RB;
+    const float* xbase = xp + ((size_t)bb * T * 2 + dir) * (LG * U) + j;
+    auto prefetch = [&](int sp) {
+        if (ew && sp < T) {
+            const float* x = xbase + (size_t)(dir ? T - 1 - sp : sp) * (2 * LG * U);
+            float* d = xring + (sp % RING) * (4 * EW) + tid;
+#pragma unroll
+            for (int q = 0; q < LG; ++q) cp_async4(d + q * EW, x + q * U);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int sp = 0; sp < PF; ++sp) prefetch(sp);
+    float cst = 0.f;                                // cell state of (unit eu, row er)
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? T - 1 - s : s;
+        const int cur = s & 1;
+        const float* hcur = hT + cur * (U * RB);
+        float* hnxt = hT + (cur ^ 1) * (U * RB);
+        prefetch(s + PF);
+        if (s > 0) bar_wait(&barH[(s - 1) & 1], ((s - 1) >> 1) & 1);      // h_{t-1} of all 256 units has landed
+        {
+            float am[2][4] = {}, ax[2][4] = {};
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const BFrag bf = bfrag(hcur, 64 * kq + 8 * kk, gid, tig);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint2 lo = los[(mt * 8 + kk) * NT + tid];
+                    mma2(am[mt], ax[mt], fh[mt][kk], lo.x, lo.y, bf);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                float* p = part + ((kq * LC + g * UPC + 16 * mt + gid) * RB + 2 * tig);
+                *reinterpret_cast<float2*>(p) = make_float2(am[mt][0] + ax[mt][0], am[mt][1] + ax[mt][1]);
+                *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[mt][2] + ax[mt][2], am[mt][3] + ax[mt][3]);
+            }
+        }
+        cp_async_wait_pf();
+        __syncthreads();
+        if (tid == 0) bar_expect(&barH[cur], XCHG_BYTES);
+        if (ew) {                                   // warps 0..7, warp-uniform
+            float a[LG];
+#pragma unroll
+            for (int q = 0; q < LG; ++q) {
+                float v = xring[(s % RING) * (4 * EW) + q * EW + tid];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) v += part[k4 * (LC * RB) + q * EW + tid];
+                a[q] = v;
+            }
+            const float ig = hard_sigmoid(a[0]), fg = hard_sigmoid(a[1]), gg = tanhf(a[2]), og = hard_sigmoid(a[3]);
+            cst = fg * cst + ig * gg;
+            const float hn = og * tanhf(cst);
+            push4_async(hnxt, &barH[cur], j * RB + er, hn, er);
+            if (valid) {
+                const size_t o = ((size_t)b * T + t) * 2 + dir;
+                hs[o * U + j] = hn;
+                if (gates) { float* gp = gates + o * (5 * U); gp[j] = ig; gp[U + j] = fg; gp[2 * U + j] = gg; gp[3 * U + j] = og; gp[4 * U + j] = cst; }
+            }
+        }
+        // no second barrier: `part` is rewritten only after the next barH wait, which completes only after every element-wise
+        // thread of this CTA has pushed (i.e. has finished reading `part`)
+    }
+    bar_wait(&barH[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    cluster.sync();
+}
+
+// ---- backward.  warp w owns hidden units [16 w, 16 w + 16) for all 128 shard columns (16 k-steps, gate-major)
+// smem: da[2][4][32][8] | recv[2][8][32][8] | lo[16][512] uint2 | gring[RING][8][256] | 2 mbarriers
+constexpr int LB_SMEM_BYTES = 4 * (2 * LC * RB + 2 * NCTA * UPC * RB + RING * 8 * (UPC * RB)) + 8 * LFR * NT + 32;
+
+__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
+lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs, const float* __restrict__ gates,
+                    const float* __restrict__ U0, const float* __restrict__ U1,
+                    float* __restrict__ dxp, float* __restrict__ hprev_out, int B, int T)
+{
+    extern __shared__ __align__(16) float sm[];
+    float* da = sm;                                 // [2][4 gates i,f,g,o][32 units][8 rows]
+    float* recv = da + 2 * LC * RB;                 // [2][8 src][32][8]
+    uint2* los = reinterpret_cast<uint2*>(recv + 2 * NCTA * UPC * RB);
+    float* gring = reinterpret_cast<float*>(los + LFR * NT);       // [RING][8: i, f, g, o, c, c_prev, h_prev, dout][256]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gring + RING * 8 * (UPC * RB));   // [2]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int dir = blockIdx.y, b0 = (blockIdx.x / NCTA) * RB;
+    const float* Um = dir ? U1 : U0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+
+    uint32_t fh[LFR][4];
+    {
+        const float* r0 = Um + (size_t)(16 * warp + gid) * (LG * U);
+        const float* r1 = r0 + (size_t)8 * (LG * U);
+#pragma unroll
+        for (int kk = 0; kk < LFR; ++kk) {
+            const int c = 8 * kk + tig;
+            const int cg0 = (c >> 5) * U + crank * UPC + (c & 31), cg1 = ((c + 4) >> 5) * U + crank * UPC + ((c + 4) & 31);
+            AFrag f; afrag_set(f, __ldg(r0 + cg0), __ldg(r1 + cg0), __ldg(r0 + cg1), __ldg(r1 + cg1));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fh[kk][i] = f.hi[i];
+            los[kk * NT + tid] = make_uint2(f.lo[0], f.lo[1]);
+        }
+    }
+    if (tid == 0) {
+        bar_init(&bar[0], 1); bar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster.sync();
+
+    const bool ew = tid < UPC * RB;
+    const int er = tid & 7, eu = (tid >> 3) & 31;
+    const int j = crank * UPC + eu;
+    const int b = b0 + er;
+    const bool valid = b < B;
+    const int bb = valid ? b : B - 1;
+    const int owner = warp >> 1, ubase = 16 * (warp & 1);
+    constexpr int EW = UPC * RB;
+    auto prefetch = [&](int s) {                    // s counts down; s < 0 -> empty group
+        if (ew && s >= 0) {
+            const int t = dir ? T - 1 - s : s;
+            const int tp = dir ? t + 1 : t - 1;
+            const size_t o = ((size_t)bb * T + t) * 2 + dir;
+            const float* gp = gates + o * (5 * U) + j;
+            float* d = gring + (s % RING) * (8 * EW) + tid;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) cp_async4(d + q * EW, gp + q * U);
+            if (s > 0) {
+                const size_t op = ((size_t)bb * T + tp) * 2 + dir;
+                cp_async4(d + 5 * EW, gates + op * (5 * U) + 4 * U + j);
+                cp_async4(d + 6 * EW, hs + op * U + j);
+            }
+            cp_async4(d + 7 * EW, dout + o * U + j);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int q = 0; q < PF; ++q) prefetch(T - 1 - q);
+    float dh = 0.f, dc = 0.f;
+    for (int s = T - 1; s >= 0; --s) {
+        const int n = T - 1 - s;                    // step counter
+        const int buf = n & 1;
+        const uint32_t ph = (uint32_t)((n >> 1) & 1);
+        const int t = dir ? T - 1 - s : s;
+        float* dab = da + buf * (LC * RB);
+        float* rcv = recv + buf * (NCTA * UPC * RB);
+        prefetch(s - PF);
+        cp_async_wait_pf();
+        float sa[LG] = {0.f, 0.f, 0.f, 0.f}, hp = 0.f;
+        if (ew) {
+            const float* d = gring + (s % RING) * (8 * EW) + tid;
+            const float ig = d[0], fg = d[EW], gg = d[2 * EW], og = d[3 * EW], cc = d[4 * EW];
+            const float cp = (s > 0) ? d[5 * EW] : 0.f;
+            hp = (s > 0) ? d[6 * EW] : 0.f;
+            const float dht = (valid ? d[7 * EW] : 0.f) + dh;
+            const float tc = tanhf(cc);
+            const float dog = dht * tc;
+            const float dct = dc + dht * og * (1.f - tc * tc);
+            sa[0] = (ig > 0.f && ig < 1.f) ? 0.2f * dct * gg : 0.f;
+            sa[1] = (fg > 0.f && fg < 1.f) ? 0.2f * dct * cp : 0.f;
+            sa[2] = dct * ig * (1.f - gg * gg);
+            sa[3] = (og > 0.f && og < 1.f) ? 0.2f * dog : 0.f;
+            dc = dct * fg;
+#pragma unroll
+            for (int q = 0; q < LG; ++q) dab[(q * UPC + eu) * RB + er] = sa[q];
+        }
+        __syncthreads();
+        {
+            float am[4] = {}, ax[4] = {};
+#pragma unroll
+            for (int kk = 0; kk < LFR; ++kk) {
+                const uint2 lo = los[kk * NT + tid];
+                mma2(am, ax, fh[kk], lo.x, lo.y, bfrag(dab, 8 * kk, gid, tig));
+            }
+            const float c[4] = {am[0] + ax[0], am[1] + ax[1], am[2] + ax[2], am[3] + ax[3]};
+            push_tile(c, rcv, &bar[buf], owner, crank, ubase, gid, tig);
+        }
+        if (tid == 0) bar_expect(&bar[buf], XCHG_BYTES);
+        if (ew) {
+            if (valid) {
+                const size_t o = ((size_t)b * T + t) * 2 + dir;
+                float* d = dxp + o * (LG * U);
+#pragma unroll
+                for (int q = 0; q < LG; ++q) d[q * U + j] = sa[q];
+                hprev_out[o * U + j] = hp;
+            }
+            bar_wait(&bar[buf], ph);
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCTA; ++c) acc += rcv[(c * UPC + eu) * RB + er];
+            dh = acc;
+        }
+        // da / recv are double-buffered: the buffers of this step are rewritten two steps later, after the barrier of the next step
+    }
+    cluster.sync();
+}
 }  // namespace
 
 int launch_gru_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st)
@@ -424,6 +679,29 @@ int launch_gru_bwd_mma(const float* dout, const float* hs, const float* gates, c
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(gru_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     dim3 grid(NCTA * ceil_div(B, RB), 2);
     gru_bwd_mma_kernel<<<grid, NT, smem, st>>>(dout, hs, gates, U0, U1, dxp, hprev, rh, B, T);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
+
+int launch_lstm_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st)
+{
+    if (B <= 0) return CRNN_OK;
+    static bool configured = false;
+    if (!configured) { CUDA_TRY(cudaFuncSetAttribute(lstm_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES)); configured = true; }
+    dim3 grid(NCTA * ceil_div(B, RB), 2);
+    lstm_fwd_mma_kernel<<<grid, NT, LF_SMEM_BYTES, st>>>(xp, U0, U1, hs, gates, B, T);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
+
+int launch_lstm_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
+                        float* dxp, float* hprev, int B, int T, cudaStream_t st)
+{
+    if (B <= 0) return CRNN_OK;
+    static bool configured = false;
+    if (!configured) { CUDA_TRY(cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM_BYTES)); configured = true; }
+    dim3 grid(NCTA * ceil_div(B, RB), 2);
+    lstm_bwd_mma_kernel<<<grid, NT, LB_SMEM_BYTES, st>>>(dout, hs, gates, U0, U1, dxp, hprev, B, T);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
