@@ -56,6 +56,23 @@ def peaks():
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
 
 
+def profiled_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the stage's dominant kernel, from the committed ncu --set full
+    summary (profiles/r01_ncu_full_summary.json); None when the stage has no capture."""
+    kern = {"act_pool_bwd": ("actbwd", "act_pool_bwd_kernel<1"), "bn_bwd": ("relu6bwd", "relu6_bwd_kernel<1"),
+            "rnn_fwd": ("gru_fwd_mma", "gru_fwd_mma_kernel"), "rnn_bwd": ("gru_bwd_mma", "gru_bwd_mma_kernel"),
+            "dwconv_fwd": ("dwrows_fwd", "dwconv3x3_rows_kernel"), "dwconv_bwd": ("dwrows_bwd", "dwconv3x3_rows_kernel"),
+            "gemm_pw_fwd": ("xw2_fwd_b6", "xw_gemm_tc_v2_kernel"), "gemm_pw_dx": ("xw2_dx_b6", "xw_gemm_tc_v2_kernel")}.get(stage)
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    if kern is None or not os.path.exists(p):
+        return None
+    for r in json.load(open(p)):
+        if r.get("capture") == kern[0] and kern[1] in r.get("kernel", ""):
+            return {"bytes_per_launch": (r["dram_read_MB"] + r["dram_write_MB"]) * 1e6, "launch": "%s (%s), %.1f us under ncu" % (r["kernel"].strip(), kern[0], r["time_us"]),
+                    "source": "profiles/r01_ncu_full_summary.json"}
+    return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -256,7 +273,7 @@ def run_ours(args):
     else:
         ach = top["work_per_step"] / (top["ms_per_step"] / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-    roof.update({"traffic": None, "kernel": "stage '%s' (%d launches/step, %.3f ms/step, %.1f%% of the step)" %
+    roof.update({"traffic": profiled_traffic(top["stage"]), "kernel": "stage '%s' (%d launches/step, %.3f ms/step, %.1f%% of the step)" %
                  (top["stage"], round(top["launches_per_step"]), top["ms_per_step"], 100 * top["share"]),
                  "peak_source": "%s (MEASURED_PEAKS.json: %s)" % (pk["src"], "bf16_tflops_sustained, kernel timed inside the step" if is_gemm else "hbm_gbs"),
                  "note": "fp32-faithful 3xTF32 tcgen05 GEMM (3 tensor-core products per mathematical MAC; achieved counts 2*M*N*K once) measured against the bf16 tensor-core peak" if is_gemm else ""})
@@ -275,6 +292,24 @@ def run_ours(args):
         extra["fwd_greedy_images_per_s"] = BATCH * args.steps / (timed(fwd_greedy, args.steps) / 1e3) if world == 1 else None
     except Exception as e:  # pragma: no cover
         extra["fwd_greedy_error"] = repr(e)
+    # ---- the other recurrent cell of the reference (utils.py:77-82: GRU flag off -> LSTM), same workload, device-timed
+    if world == 1:
+        try:
+            other = "lstm" if args.cell == "gru" else "gru"
+            m2 = cb.CRNN(V, MAXLEN, (IMGH, IMGW, 1), 128, other == "gru", 256, max_batch=BATCH, seed=1234).get_model()
+            m2.compile(optimizer=cb.Adam(lr=1e-4, beta_1=0.5, beta_2=0.999, epsilon=1e-7, clipnorm=5.0))
+
+            def step_other():
+                step_no[0] += 1
+                m2.train_fwd_bwd_device(xd, labd, Ld, ild, dropout_seed=seed_base + step_no[0])
+                m2.optimizer_step()
+            for _ in range(5):
+                step_other()
+            n2 = max(5, args.steps // 2)
+            extra["train_step_%s_images_per_s" % other] = BATCH * n2 / (timed(step_other, n2) / 1e3)
+            del m2
+        except Exception as e:  # pragma: no cover
+            extra["other_cell_error"] = repr(e)
     beam = None
     if world == 1:
         rng = np.random.default_rng(3)
@@ -312,11 +347,15 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = pick_cpu_threads(args.cell)
-        sample = 16
+        sample, nrep = BATCH, 3
         st = oracle_train_step_fn(args.cell, sample, cores)
-        t0 = time.perf_counter(); st(); dt = time.perf_counter() - t0
-        cpu = {"value": sample / dt, "unit": "images/s", "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
-               "sample": "one oracle train step (PyTorch-CPU fp32 restatement + C CTC + Adam) on 16 of the 64 images, %.1f s, best of 8/16/32 threads" % dt}
+        st()                                                    # warm-up (allocator, oneDNN primitive caches)
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            st()
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample * nrep / dt, "unit": "images/s", "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
+               "sample": "%d oracle train steps (PyTorch-CPU fp32 restatement + C CTC + Adam) on the full batch of %d images, %.1f s of CPU work, best of 8/16/32 threads" % (nrep, sample, dt)}
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

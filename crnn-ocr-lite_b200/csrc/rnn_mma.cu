@@ -482,21 +482,21 @@ lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, 
         prefetch(s + PF);
         if (s > 0) bar_wait(&barH[(s - 1) & 1], ((s - 1) >> 1) & 1);      // h_{t-1} of all 256 units has landed
         {
-            float am[2][4] = {}, ax[2][4] = {};
+            float am[2][4] = {};                           // one chain per m-tile: 4 warps per scheduler keep the tensor pipe busy
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const BFrag bf = bfrag(hcur, 64 * kq + 8 * kk, gid, tig);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint2 lo = los[(mt * 8 + kk) * NT + tid];
-                    mma2(am[mt], ax[mt], fh[mt][kk], lo.x, lo.y, bf);
+                    mma2(am[mt], am[mt], fh[mt][kk], lo.x, lo.y, bf);
                 }
             }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 float* p = part + ((kq * LC + g * UPC + 16 * mt + gid) * RB + 2 * tig);
-                *reinterpret_cast<float2*>(p) = make_float2(am[mt][0] + ax[mt][0], am[mt][1] + ax[mt][1]);
-                *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[mt][2] + ax[mt][2], am[mt][3] + ax[mt][3]);
+                *reinterpret_cast<float2*>(p) = make_float2(am[mt][0], am[mt][1]);
+                *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[mt][2], am[mt][3]);
             }
         }
         cp_async_wait_pf();
