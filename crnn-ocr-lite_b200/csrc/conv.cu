@@ -694,6 +694,21 @@ __global__ void dropout_kernel(const float* in, float* x, long long n, float rat
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         x[i] = in[i] * crnn_dropout_mask(seed, layer, (uint64_t)i, rate, inv_keep);
 }
+// Fixed-order sum of the S split-K copies of a GEMM output, fused with bias, ReLU and (training) the inverted-dropout mask of the layer.
+__global__ void sum_partials_kernel(const float* __restrict__ part, int S, long long stride, int N4, long long total4, const float* __restrict__ bias, int relu,
+                                    float* __restrict__ out, int ldo, float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr)
+{
+    if (seed_ptr) seed = *seed_ptr;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / N4; const int n4 = (int)(i - m * N4);
+        float4 v = ldg4(part + i * 4);
+        for (int s2 = 1; s2 < S; ++s2) { const float4 w = ldg4(part + (size_t)s2 * stride + i * 4); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+        if (bias) { const float4 b = ldg4(bias + n4 * 4); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (rate > 0.f) { float mk[4]; crnn_dropout_mask4(seed, layer, (uint64_t)i, rate, inv_keep, mk); v.x *= mk[0]; v.y *= mk[1]; v.z *= mk[2]; v.w *= mk[3]; }
+        *reinterpret_cast<float4*>(out + (size_t)m * ldo + n4 * 4) = v;
+    }
+}
 // ------------------------------------------------------------------ block 1 (Cin = 1): pointwise conv = outer product
 // blockDim = 256 = 16 pixel lanes x 16 channel quads (Cout = 64); a warp covers 2 pixels x 64 channels = 2 x 256 B contiguous.
 // BN statistics of the output in closed form: sum_m f_m w_c = w_c * S1, sum_m (f_m w_c)^2 = w_c^2 * S2 (S1, S2 accumulated in double per CTA).
@@ -961,6 +976,13 @@ int launch_relu_dropout_bwd(float* g, const float* act, long long n, float rate,
 int launch_dropout_fwd(float* x, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
     if (rate <= 0.f) return CRNN_OK;
     dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(x, x, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_sum_partials(const float* part, int S, long long stride, long long M, int N, const float* bias, int relu, float* out, int ldo,
+                        float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
+    if ((N % 4) || (ldo % 4) || (stride % 4) || S < 1) { crnn_set_error("sum_partials: N, ldo and stride must be multiples of 4"); return CRNN_ERR_INVALID; }
+    const long long total4 = M * (N / 4);
+    sum_partials_kernel<<<grid1d(total4, 256), 256, 0, st>>>(part, S, stride, N / 4, total4, bias, relu, out, ldo, rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, seed_ptr);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_dropout_copy(const float* in, float* out, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {

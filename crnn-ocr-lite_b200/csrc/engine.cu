@@ -248,6 +248,7 @@ void plan(crnn_handle* h) {
     // d(block output) ping-pongs between gA/gB; the pointwise-output and depthwise-output gradients of every block get their own
     // buffers so that the weight-gradient branch of the step graph can read them without write-after-read hazards
     A("gA", max_act); A("gB", max_act);
+    A("gemm_part", (int64_t)8 * h->maxB * h->T * std::max(h->TD, h->U));      // split-K copies of the small head GEMMs (<= 8 copies)
     hh = h->Hp; ww = h->Wp;
     for (int i = 1; i <= 7; ++i) {
         const BlockPlan& b = kBlocks[i - 1];
@@ -423,9 +424,19 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
     if (h->gemm_simt) side_join(h, st);
     // ---- dense1 (utils.py:72-75): (B,T,9,512) is already (B*T, 4608) with feature = w*512+c
     const int M = B * T;
-    if (tc_ok(h, h->TD, h->FEAT)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->a("wimg_d1f"), h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, 0, st));
-    else TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
-    if (drop) ST(ST_MISC, 0, launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st, h->seed_ptr));
+    const int ks1 = tc_ok(h, h->TD, h->FEAT) ? std::min(8, xw_gemm_tc_pick_ksplit(M, h->TD, h->FEAT)) : 1;
+    if (ks1 > 1) {
+        // 33 output tiles for 148 SMs: split K = 4608 over `ks1` CTAs per tile, then one pass sums the copies + bias + ReLU + dropout
+        float* part = h->a("gemm_part");
+        ST(ST_GEMM_HEAD_FWD, 2.0 * M * h->TD * h->FEAT, launch_xw_gemm_tc(in, h->FEAT, h->a("wimg_d1f"), part, h->TD, M, h->TD, h->FEAT, nullptr, nullptr, nullptr, st,
+                                                                           nullptr, 0, 0, 0, ks1, (long long)M * h->TD));
+        ST(ST_MISC, 0, launch_sum_partials(part, ks1, (long long)M * h->TD, M, h->TD, h->w("dense1/bias"), 1, h->a("dense1"), h->TD,
+                                           drop ? kDropDense1 : 0.f, seed, 8, st, h->seed_ptr));
+    } else {
+        if (tc_ok(h, h->TD, h->FEAT)) TRY(tc_xw(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->a("wimg_d1f"), h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, 0, st));
+        else TRY(gemm_nn(h, ST_GEMM_HEAD_FWD, in, h->FEAT, h->w("dense1/kernel"), h->TD, h->a("dense1"), h->TD, M, h->TD, h->FEAT, h->w("dense1/bias"), 1, nullptr, nullptr, st));
+        if (drop) ST(ST_MISC, 0, launch_dropout_fwd(h->a("dense1"), (long long)M * h->TD, kDropDense1, seed, 8, st, h->seed_ptr));
+    }
     // ---- two bidirectional recurrent layers (utils.py:77-82)
     const float* rin = h->a("dense1"); int kin = h->TD;
     for (int layer = 1; layer <= 2; ++layer) {
@@ -497,6 +508,19 @@ int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const
         }
         TRY(dwgemm(rin, kin, kin, dxd, 2 * G * U, G * U, h->g(base + "/kernel"), G * U));
         ST(ST_MISC, 0, launch_colsum(dxd, M, G * U, 2 * G * U, h->g(base + "/bias"), ss));
+    }
+    const int ksx = tc_ok(h, kin, G * U) ? std::min(4, xw_gemm_tc_pick_ksplit(M, kin, G * U)) : 1;
+    if (ksx > 1) {
+        // 33-66 output tiles: both directions x `ksx` k-slices write disjoint copies, one pass adds them up (fixed order)
+        float* part = h->a("gemm_part");
+        const long long stride = (long long)M * kin;
+        for (int d = 0; d < 2; ++d) {
+            char nb[32]; snprintf(nb, sizeof(nb), "wimg_r%d%db", layer, d);
+            ST(ST_GEMM_HEAD_BWD, 2.0 * M * kin * G * U, launch_xw_gemm_tc(dxp + d * G * U, 2 * G * U, h->a(nb), part + (size_t)d * ksx * stride, kin, M, kin, G * U,
+                                                                          nullptr, nullptr, nullptr, st, nullptr, 0, 0, 0, ksx, stride));
+        }
+        ST(ST_MISC, 0, launch_sum_partials(part, 2 * ksx, stride, M, kin, nullptr, 0, dx, kin, 0.f, 0, 0, st, nullptr));
+        return CRNN_OK;
     }
     for (int d = 0; d < 2; ++d) {
         const std::string base = h->rnn(layer, d);

@@ -505,7 +505,10 @@ __device__ __forceinline__ void epi_store(float* dst, const uint32_t (&r)[32], i
     }
 }
 
-__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NTP, int MT, int NSUB)
+// KS > 1: split-K.  Work item t = (CTA tile t / KS, k-slice t % KS); every slice contracts KBS k-blocks and stores its partial tile
+// into its own copy of the output (out + slice * split_stride) -- the caller sums the copies in a fixed order (deterministic, no atomics).
+// Used for the head GEMMs whose 128-pixel x 128-channel tiling yields only 33-66 tiles for 148 SMs (dense1: M=4224, N=128, K=4608).
+__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NTP, int MT, int NSUB, int KS, long long split_stride)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -520,7 +523,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KB = a.K / TC_BK;
-    const int total = NTP * MT;        // CTA tile = 128 pixels x (NSUB x 128) channels: the transformed X stage feeds NSUB accumulators
+    const int KBS = (KB + KS - 1) / KS;                 // k-blocks per slice
+    const int total = NTP * MT * KS;   // CTA tile = 128 pixels x (NSUB x 128) channels: the transformed X stage feeds NSUB accumulators
+    auto kb_lo = [&](int t) { return (t % KS) * KBS; };
+    auto kb_hi = [&](int t) { const int e = (t % KS) * KBS + KBS; return e < KB ? e : KB; };
 
     if (tid == 0) {
         for (int s = 0; s < TC2_WRING; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
@@ -551,7 +557,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         // fetch state: the 4 row pointers of the tile being fetched are computed once per tile, a k-block fetch is 4 x (64-bit add + LDGSTS)
         const float* frp[4]; uint32_t fsz[4];
         auto set_fetch_tile = [&](int tt) {
-            const int m0 = (a.rev ? MT - 1 - tt / NTP : tt / NTP) * TC_BP;
+            const int m0 = (a.rev ? MT - 1 - (tt / KS) / NTP : (tt / KS) / NTP) * TC_BP;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = m0 + r0 + 32 * i;
@@ -565,20 +571,22 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 #pragma unroll
             for (int i = 0; i < 4; ++i) cp_async16_s(dst + (uint32_t)i * (32u * TC_BK * 4u), frp[i] + kk * TC_BK, fsz[i]);
         };
-        int ft = blockIdx.x, fk = 0;                      // next (tile, k-block) to FETCH
-        if (ft < total) set_fetch_tile(ft);
+        int ft = blockIdx.x, fk = 0, fke = 0;             // next (tile, k-block) to FETCH, end of that tile's k range
+        if (ft < total) { set_fetch_tile(ft); fk = kb_lo(ft); fke = kb_hi(ft); }
+        auto fetch_advance = [&]() { if (++fk == fke) { ft += gridDim.x; if (ft < total) { set_fetch_tile(ft); fk = kb_lo(ft); fke = kb_hi(ft); } } };
 #pragma unroll
         for (int d = 0; d < TC2_RAW; ++d) {
-            if (ft < total) { issue(fk, d); if (++fk == KB) { fk = 0; ft += gridDim.x; if (ft < total) set_fetch_tile(ft); } }
+            if (ft < total) { issue(fk, d); fetch_advance(); }
             cp_async_commit();                            // (possibly empty) group keeps the group count uniform
         }
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bn) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + c8 * 4)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + c8 * 4)); }
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int m0 = (a.rev ? MT - 1 - t / NTP : t / NTP) * TC_BP;
+            const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
             const bool tail = m0 + TC_BP > a.M;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int kb0 = kb_lo(t), kb1 = kb_hi(t);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % TC2_XSTAGES;
                 const uint32_t ph = (it / TC2_XSTAGES) & 1;
                 const int slot = it % TC2_RAW;
@@ -617,7 +625,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xfull[s]);
                 }
-                if (ft < total) { issue(fk, slot); if (++fk == KB) { fk = 0; ft += gridDim.x; if (ft < total) set_fetch_tile(ft); } }   // refill the ring entry just consumed
+                if (ft < total) { issue(fk, slot); fetch_advance(); }   // refill the ring entry just consumed
                 cp_async_commit();
                 sc = scn; sh = shn;
             }
@@ -628,8 +636,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int ct0 = (t % NTP) * NSUB;
-                for (int kb = 0; kb < KB; ++kb) {
+                const int ct0 = ((t / KS) % NTP) * NSUB;
+                const int kb0 = kb_lo(t), kb1 = kb_hi(t);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     for (int h = 0; h < NSUB; ++h, ++it) {
                         const int ws = it % TC2_WRING;
                         mbar_wait(&wempty[ws], ((it / TC2_WRING) & 1) ^ 1);
@@ -649,7 +658,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             const int buf = j & 1;
             mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int kb0 = kb_lo(t), kb1 = kb_hi(t);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int xs = it % TC2_XSTAGES;
                 mbar_wait(&xfull[xs], (it / TC2_XSTAGES) & 1);
                 for (int h = 0; h < NSUB; ++h, ++wit) {
@@ -664,14 +674,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                         for (int ks = 0; ks < TC_BK / 8; ++ks) {
                             if (a.diag & 4) break;
                             const uint32_t o = ks * 32;
-                            umma_tf32(tacc, umma_desc(wlo + o), umma_desc(xhi + o), (kb | ks) ? 1u : 0u);
+                            umma_tf32(tacc, umma_desc(wlo + o), umma_desc(xhi + o), ((kb - kb0) | ks) ? 1u : 0u);
                             umma_tf32(tacc, umma_desc(whi + o), umma_desc(xlo + o), 1u);
                             umma_tf32(tacc, umma_desc(whi + o), umma_desc(xhi + o), 1u);
                         }
                         umma_commit(&wempty[ws]);
                         if (h == NSUB - 1) {
                             umma_commit(&xempty[xs]);
-                            if (kb == KB - 1) umma_commit(&tfull[buf]);
+                            if (kb == kb1 - 1) umma_commit(&tfull[buf]);
                         }
                     }
                     __syncwarp();
@@ -700,7 +710,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
             const int buf = j & 1;
-            const int ct0 = (t % NTP) * NSUB, m0 = (a.rev ? MT - 1 - t / NTP : t / NTP) * TC_BP;
+            const int ct0 = ((t / KS) % NTP) * NSUB, m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
+            float* const outp = a.out + (size_t)(t % KS) * (size_t)split_stride;      // this k-slice's copy of the output
             if (ct0 != cur_ct0) { flush_stats(); cur_ct0 = ct0; }
             mbar_wait(&tfull[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -724,7 +735,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float* dst = a.out + (size_t)(m0 + c0) * a.ldo + n;     // 32 lanes = 32 consecutive channels: 128-byte coalesced rows
+                float* dst = outp + (size_t)(m0 + c0) * a.ldo + n;      // 32 lanes = 32 consecutive channels: 128-byte coalesced rows
                 if (a.diag & 1) {
                 } else if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast paths: full 32-pixel chunk, no per-element predicate
                     // row stride known at compile time for the conv-stack widths -> the 32 stores use immediate offsets (the generic
@@ -817,9 +828,24 @@ int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transpo
     return CRNN_OK;
 }
 
+int xw_gemm_tc_pick_ksplit(int M, int N, int K)
+{
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int NT = (N + TC_BC - 1) / TC_BC, MT = (M + TC_BP - 1) / TC_BP, KB = K / TC_BK;
+    const int NSUB = (NT % 2 == 0 && (long long)(NT / 2) * MT >= sms) ? 2 : 1;
+    const long long tiles = (long long)(NT / NSUB) * MT;
+    if (tiles * 2 > sms || KB < 8) return 1;
+    int ks = (int)(sms / tiles);
+    if (ks > KB / 4) ks = KB / 4;
+    if (ks < 1) ks = 1;
+    const int kbs = (KB + ks - 1) / ks;
+    return (KB + kbs - 1) / kbs;                      // no empty slices
+}
+
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
-                      const float* bias, int relu, int accumulate, int rev)
+                      const float* bias, int relu, int accumulate, int rev, int ksplit, long long split_stride)
 {
     if (M <= 0 || N <= 0) return CRNN_OK;
     if (K % TC_BK || K <= 0) { crnn_set_error("gemm_tc: K=%d must be a positive multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
@@ -832,6 +858,11 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     static int use_v1 = -1;
     if (use_v1 < 0) { const char* e = getenv("CRNN_GEMM_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
     const int NT = (N + TC_BC - 1) / TC_BC, MT = (M + TC_BP - 1) / TC_BP;
+    if (ksplit > 1 && (use_v1 || x_scale || stats || bias || relu || accumulate || split_stride < (long long)M * ldo - (ldo - N) || ksplit > K / TC_BK)) {
+        crnn_set_error("gemm_tc: split-K needs the plain-store epilogue (no BN prologue / statistics / bias / relu / accumulate) and disjoint output copies");
+        return CRNN_ERR_INVALID;
+    }
+    if (ksplit < 1) ksplit = 1;
     if (use_v1) {
         static bool configured = false;
         if (!configured) { CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); configured = true; }
@@ -848,9 +879,9 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
         // activation tile (the instruction-issue bottleneck, ncu r1d) is then shared by 2 x 128 output channels
         const int NSUB = (NT % 2 == 0 && (long long)(NT / 2) * MT >= num_sms && nsub_env != 1) ? 2 : 1;
         const int NTP = NT / NSUB;
-        const long long total = (long long)NTP * MT;
+        const long long total = (long long)NTP * MT * ksplit;
         const int grid = (int)(total < num_sms ? total : num_sms);
-        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, NTP, MT, NSUB);
+        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, NTP, MT, NSUB, ksplit, split_stride);
     }
     LAUNCH_CHECK();
     return CRNN_OK;

@@ -22,7 +22,13 @@ size_t tc_weight_image_floats(int N, int K);
 int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transposed, float* img, cudaStream_t st);
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
-                      const float* bias = nullptr, int relu = 0, int accumulate = 0, int rev = 0);
+                      const float* bias = nullptr, int relu = 0, int accumulate = 0, int rev = 0, int ksplit = 1, long long split_stride = 0);
+// split-K for GEMMs with too few 128 x 128 output tiles to fill the SMs: slices the caller should request (1 = none); every slice
+// writes its own copy of the output (split_stride floats apart), summed in a fixed order by launch_sum_partials
+int xw_gemm_tc_pick_ksplit(int M, int N, int K);
+// out[m*ldo + n] = mask(m*N + n) * act(sum_{s<S} part[s*stride + m*N + n] + bias[n]);  act = ReLU if relu; mask = inverted dropout if rate > 0
+int launch_sum_partials(const float* part, int S, long long stride, long long M, int N, const float* bias, int relu, float* out, int ldo,
+                        float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr);
 
 // dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]  (tcgen05, MN-major operands, split-K over pixels, atomics into pre-zeroed dW)
 int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
