@@ -79,7 +79,10 @@ stn_trunk_fwd_kernel(const float* __restrict__ x, const float* __restrict__ k1, 
     }
 }
 
-// backward of the trunk for one image: weight/bias grads (atomics into the shared grad buffers)
+// backward of the trunk for one image: weight/bias grads (atomics into the shared grad buffers).  Two CTAs per image run the two
+// independent halves concurrently (ncu r1m: one 1024-thread CTA per image took 133 us at the tail of the step's critical path):
+//   blockIdx.y == 0: db2, dk2 (conv2 weight gradient: 10 000 outputs x 52 positions)
+//   blockIdx.y == 1: dp2 (conv2 input gradient) -> through pool2's argmax -> db1, dk1 (two threads per dk1 output)
 __global__ void __launch_bounds__(1024)
 stn_trunk_bwd_kernel(const float* __restrict__ dflat, const float* __restrict__ p1g, const float* __restrict__ p2g,
                      const int* __restrict__ p2arg, const float* __restrict__ k2,
@@ -92,25 +95,30 @@ stn_trunk_bwd_kernel(const float* __restrict__ dflat, const float* __restrict__ 
     float* dc2 = p2 + n2;                 // F
     float* dp2 = dc2 + d.F;               // n2
     float* sk2 = dp2 + n2;                // 25*NC*NC conv2 kernel (read 500x per dp2 output)
+    unsigned char* arg = reinterpret_cast<unsigned char*>(sk2 + 25 * NC * NC);   // n2 pool2 argmax codes (0..3)
     const int b = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < d.P1h * d.P1w; i += blockDim.x) p1[i] = p1g[(size_t)b * d.P1h * d.P1w + i];
-    for (int i = tid; i < n2; i += blockDim.x) p2[i] = p2g[(size_t)b * n2 + i];
     for (int i = tid; i < d.F; i += blockDim.x) dc2[i] = dflat[(size_t)b * d.F + i];
+    if (blockIdx.y == 0) {
+        for (int i = tid; i < n2; i += blockDim.x) p2[i] = p2g[(size_t)b * n2 + i];
+        __syncthreads();
+        for (int co = tid; co < NC; co += blockDim.x) {
+            float s = 0.f;
+            for (int r = 0; r < d.C2h * d.C2w; ++r) s += dc2[r * NC + co];
+            atomicAdd(db2 + co, s);
+        }
+        for (int i = tid; i < 25 * NC * NC; i += blockDim.x) {
+            int co = i % NC; int r = i / NC; int ci = r % NC; int q = r / NC; int ii = q / 5, jj = q % 5;
+            float s = 0.f;
+            for (int h = 0; h < d.C2h; ++h)
+                for (int w = 0; w < d.C2w; ++w) s = fmaf(p2[((h + ii) * d.P2w + w + jj) * NC + ci], dc2[(h * d.C2w + w) * NC + co], s);
+            atomicAdd(dk2 + i, s);
+        }
+        return;
+    }
+    for (int i = tid; i < d.P1h * d.P1w; i += blockDim.x) p1[i] = p1g[(size_t)b * d.P1h * d.P1w + i];
     for (int i = tid; i < 25 * NC * NC; i += blockDim.x) sk2[i] = k2[i];
+    for (int i = tid; i < n2; i += blockDim.x) arg[i] = (unsigned char)p2arg[(size_t)b * n2 + i];
     __syncthreads();
-    // db2, dk2
-    for (int co = tid; co < NC; co += blockDim.x) {
-        float s = 0.f;
-        for (int r = 0; r < d.C2h * d.C2w; ++r) s += dc2[r * NC + co];
-        atomicAdd(db2 + co, s);
-    }
-    for (int i = tid; i < 25 * NC * NC; i += blockDim.x) {
-        int co = i % NC; int r = i / NC; int ci = r % NC; int q = r / NC; int ii = q / 5, jj = q % 5;
-        float s = 0.f;
-        for (int h = 0; h < d.C2h; ++h)
-            for (int w = 0; w < d.C2w; ++w) s = fmaf(p2[((h + ii) * d.P2w + w + jj) * NC + ci], dc2[(h * d.C2w + w) * NC + co], s);
-        atomicAdd(dk2 + i, s);
-    }
     // dp2[h'][w'][ci] = sum_{ii,jj,co} dc2[h'-ii][w'-jj][co] * k2[ii][jj][ci][co]
     for (int i = tid; i < n2; i += blockDim.x) {
         int ci = i % NC; int r = i / NC; int w = r % d.P2w, h = r / d.P2w;
@@ -134,16 +142,19 @@ stn_trunk_bwd_kernel(const float* __restrict__ dflat, const float* __restrict__ 
         for (int r = 0; r < d.P2h * d.P2w; ++r) s += dp2[r * NC + co];
         atomicAdd(db1 + co, s);
     }
-    for (int i = tid; i < 25 * NC; i += blockDim.x) {
+    const int npos = d.P2h * d.P2w, hpos = (npos + 1) / 2;
+    for (int i2 = tid; i2 < 2 * 25 * NC; i2 += blockDim.x) {
+        const int i = i2 % (25 * NC), part = i2 / (25 * NC);
         int co = i % NC; int q = i / NC; int ii = q / 5, jj = q % 5;
         float s = 0.f;
-        for (int h2 = 0; h2 < d.P2h; ++h2)
-            for (int w2 = 0; w2 < d.P2w; ++w2) {
-                int e = (h2 * d.P2w + w2) * NC + co;
-                int a = p2arg[(size_t)b * n2 + e];
-                int h = 2 * h2 + (a >> 1), w = 2 * w2 + (a & 1);
-                s = fmaf(p1[(h + ii) * d.P1w + w + jj], dp2[e], s);
-            }
+        const int r1 = min(npos, (part + 1) * hpos);
+        for (int r = part * hpos; r < r1; ++r) {
+            const int h2 = r / d.P2w, w2 = r - h2 * d.P2w;
+            const int e = r * NC + co;
+            const int a = arg[e];
+            const int h = 2 * h2 + (a >> 1), w = 2 * w2 + (a & 1);
+            s = fmaf(p1[(h + ii) * d.P1w + w + jj], dp2[e], s);
+        }
         atomicAdd(dk1 + i, s);
     }
 }
@@ -304,10 +315,10 @@ int launch_stn_trunk_bwd(const float* dflat, const float* p1, const float* p2, c
 {
     StnDims d = stn_dims(H, W);
     size_t n2 = (size_t)d.P2h * d.P2w * NC;
-    size_t smem = sizeof(float) * ((size_t)d.P1h * d.P1w + 2 * n2 + d.F + 25 * NC * NC);
+    size_t smem = sizeof(float) * ((size_t)d.P1h * d.P1w + 2 * n2 + d.F + 25 * NC * NC) + ((n2 + 15) / 16) * 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) { CUDA_TRY(cudaFuncSetAttribute(stn_trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-    stn_trunk_bwd_kernel<<<B, 1024, smem, st>>>(dflat, p1, p2, p2arg, k2, dk1, db1, dk2, db2, d);
+    stn_trunk_bwd_kernel<<<dim3(B, 2), 1024, smem, st>>>(dflat, p1, p2, p2arg, k2, dk1, db1, dk2, db2, d);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_stn_sample_fwd(const float* x, const float* theta, float* out, int B, int H, int W, int pad, cudaStream_t st)
