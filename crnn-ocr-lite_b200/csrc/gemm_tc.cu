@@ -99,6 +99,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
 }
+// fp32-faithful product in TWO UMMAs per 8-wide k group instead of the three of 3xTF32 (the kernel is paced by the tensor pipe and by
+// its shared-memory operand reads, ncu r1f: l1tex data_pipe_tc wavefronts 41 % with 3 UMMAs):
+//   w.x = w_hi.x_hi (kind::tf32, K = 8)  +  [ w_hi'.x_lo + w_lo.x_hi' ] (ONE kind::f16 bf16 UMMA, K = 16)
+// The cross terms are 2^-11 of the main term, so bf16 operands suffice for them (error <= ~2^-19 of a product).  They share one UMMA by
+// interleaving along K: the "x" tiles hold, per (row, k), one 32-bit word {bf16 slot 2k, bf16 slot 2k+1} = {w_hi', w_lo} for the weights
+// and {x_lo, x_hi'} for the activations -- same bytes per row, same SWIZZLE_128B geometry and the same 32-byte K advance as the tf32 tile.
+constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BP >> 3) << 17) | ((uint32_t)(TC_BC >> 4) << 24);
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC_BF16), "r"(accumulate) : "memory");
+}
+// {slot0 -> bits 15:0, slot1 -> bits 31:16}, round to nearest
+__device__ __forceinline__ float pack_bf16x2(float slot0, float slot1) {
+    uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(slot1), "f"(slot0)); return __uint_as_float(r);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -182,7 +200,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
                 for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(x[q]); lo[q] = x[q] - __uint_as_float(hi[q]); }
                 const int off = (r >> 3) * 256 + (r & 7) * 32 + ((c8 ^ (r & 7)) << 2);
                 *reinterpret_cast<uint4*>(Xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(Xlo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(Xlo + off) = make_float4(pack_bf16x2(lo[0], __uint_as_float(hi[0])), pack_bf16x2(lo[1], __uint_as_float(hi[1])),
+                                                                    pack_bf16x2(lo[2], __uint_as_float(hi[2])), pack_bf16x2(lo[3], __uint_as_float(hi[3])));   // {x_lo, x_hi'}
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
             mbar_arrive(&full[s]);
@@ -236,8 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
 #pragma unroll
                 for (int ks = 0; ks < TC_BK / 8; ++ks) {      // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
                     const uint32_t o = ks * 32;
-                    umma_tf32(tmem_base, umma_desc(wlo + o), umma_desc(xhi + o), (kb | ks) ? 1u : 0u);   // small terms first
-                    umma_tf32(tmem_base, umma_desc(whi + o), umma_desc(xlo + o), 1u);
+                    umma_bf16(tmem_base, umma_desc(wlo + o), umma_desc(xlo + o), (kb | ks) ? 1u : 0u);   // cross terms first
                     umma_tf32(tmem_base, umma_desc(whi + o), umma_desc(xhi + o), 1u);
                 }
                 umma_commit(&empty[s]);                       // frees the stage when these MMAs have read it
@@ -619,7 +637,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     float h0, h1, h2, h3, l0, l1, l2, l3;
                     split_tf32(v[i].x, h0, l0); split_tf32(v[i].y, h1, l1); split_tf32(v[i].z, h2, l2); split_tf32(v[i].w, h3, l3);
                     sts128(xhi + (uint32_t)i * 4096u, h0, h1, h2, h3);       // row r0 + 32 i: 4 eight-row groups = 4 x 1024 B further
-                    sts128(xlo + (uint32_t)i * 4096u, l0, l1, l2, l3);
+                    sts128(xlo + (uint32_t)i * 4096u, pack_bf16x2(l0, h0), pack_bf16x2(l1, h1), pack_bf16x2(l2, h2), pack_bf16x2(l3, h3));   // {x_lo, x_hi'}
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -674,8 +692,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                         for (int ks = 0; ks < TC_BK / 8; ++ks) {
                             if (a.diag & 4) break;
                             const uint32_t o = ks * 32;
-                            umma_tf32(tacc, umma_desc(wlo + o), umma_desc(xhi + o), ((kb - kb0) | ks) ? 1u : 0u);
-                            umma_tf32(tacc, umma_desc(whi + o), umma_desc(xlo + o), 1u);
+                            umma_bf16(tacc, umma_desc(wlo + o), umma_desc(xlo + o), ((kb - kb0) | ks) ? 1u : 0u);   // cross terms first
                             umma_tf32(tacc, umma_desc(whi + o), umma_desc(xhi + o), 1u);
                         }
                         umma_commit(&wempty[ws]);
@@ -811,7 +828,7 @@ __global__ void prep_weight_images_kernel(const float* __restrict__ W, int ldw, 
         float* t = img + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
         const int off = sw128_off(r, kk);
         t[off] = __uint_as_float(hi);
-        t[TC_TILE_FLOATS + off] = lo;
+        t[TC_TILE_FLOATS + off] = pack_bf16x2(__uint_as_float(hi), lo);          // {w_hi', w_lo}
     }
 }
 }  // namespace
