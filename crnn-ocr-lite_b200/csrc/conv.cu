@@ -940,13 +940,14 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
-                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev) {
+                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev, int reduce_done) {
     dim3 grid, block;
     const double invM = 1.0 / (double)M;
+    if (reduce_done && (C % 4)) { crnn_set_error("relu6_bn_bwd: fused reduction needs C %% 4 == 0"); return CRNN_ERR_INVALID; }
     if (C % 4 == 0) {
         chan_block(C / 4, (M + 1) / 2, grid, block);
         if (too_big(M * C)) return CRNN_ERR_INVALID;
-        { const int rc = launch_bn_relu6_reduce(da, y, scale, shift, mean, invstd, red, M, C, rev, 0.f, 0, 0, nullptr, st); if (rc != CRNN_OK) return rc; }
+        if (!reduce_done) { const int rc = launch_bn_relu6_reduce(da, y, scale, shift, mean, invstd, red, M, C, rev, 0.f, 0, 0, nullptr, st); if (rc != CRNN_OK) return rc; }
         relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM, !rev);
     } else {
         chan_block(C, M, grid, block);

@@ -82,6 +82,7 @@ struct crnn_handle {
     Prof prof;
     bool gemm_simt = false;   // CRNN_GEMM_SIMT=1: fp32 SIMT GEMM for the pointwise convs instead of the tcgen05 3xTF32 kernel
     bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
+    bool fuse_bn_red = true;   // CRNN_FUSE_BN_RED=0: separate reduction pass for the ReLU6+BN backward after the depthwise conv
     bool rnn_simt_cluster = false;   // CRNN_RNN_SIMT_CLUSTER=1: cluster kernels with U in shared memory + FFMA (rnn_cluster.cu) instead of rnn_mma.cu
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
@@ -541,6 +542,7 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
     const float* dw = h->a(nm("dw%d", i)); const float* pw = h->a(nm("pw%d", i));
     float* dpw = h->a(nm("dpw%d", i)); float* ddw = h->a(nm("ddw%d", i));
     const int bn1 = 2 * i - 1, bn2 = 2 * i;
+    bool fused_red = false;            // reduction pass of the BN1 backward done by the dX GEMM epilogue
     ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (3.0 + 2.0 / (b.ph * b.pw)),
        launch_act_pool_bn_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
                               h->w(bnname(bn2, "gamma")), dpw, bn_red(h, bn2), h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")),
@@ -560,14 +562,18 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
                         h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), ss));
         }
         if (!h->gemm_simt && (b.cout % 32 == 0) && (b.cin % 4 == 0)) {
-            ST(ST_GEMM_PW_DX, 2.0 * Mi * b.cin * b.cout, launch_xw_gemm_tc(dpw, b.cout, h->a(nm("wimg_dx%d", i)), ddw, b.cin, (int)Mi, b.cin, b.cout, nullptr, nullptr, nullptr, st, nullptr, 0, 0, h->rv()));
+            // the epilogue also accumulates the reduction pass of the ReLU6+BN backward below (sum dz, sum dz*xhat per channel)
+            const TcBnRed rr = {dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd"))};
+            fused_red = h->fuse_bn_red;
+            ST(ST_GEMM_PW_DX, 2.0 * Mi * b.cin * b.cout, launch_xw_gemm_tc(dpw, b.cout, h->a(nm("wimg_dx%d", i)), ddw, b.cin, (int)Mi, b.cin, b.cout, nullptr, nullptr,
+                                                                          fused_red ? bn_red(h, bn1) : nullptr, st, nullptr, 0, 0, h->rv(), 1, 0, fused_red ? &rr : nullptr));
         } else {
             TRY(gemm_nt(h, ST_GEMM_PW_DX, dpw, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, ddw, b.cin, (int)Mi, b.cin, b.cout, 0, st));
         }
     }
     ST(ST_BN_BWD, 20.0 * Mi * b.cin,
        launch_relu6_bn_bwd(ddw, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st, h->rv()));
+                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st, h->rv(), fused_red ? 1 : 0));
     h->rv();
     const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
     {
@@ -707,6 +713,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_RNN_V1"); h->rnn_v1 = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_RNN_SIMT_CLUSTER"); h->rnn_simt_cluster = e && e[0] == '1'; }
+    { const char* e = getenv("CRNN_FUSE_BN_RED"); h->fuse_bn_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }

@@ -130,6 +130,9 @@ struct TcArgs {
     double* stats;                    // optional [2*N] column sum / sum of squares of out
     const float* bias; int relu; int accumulate;   // epilogue: out = [out +] relu?(acc + bias[n])
     int rev;                          // v2: walk the pixel tiles from the end of the tensor (serpentine traversal)
+    // v2, optional: fused reduction pass of the BatchNorm+ReLU6 backward that consumes `out` (= dL/d relu6(bn(y))): with y = red_y[m][n]
+    // (same shape / row stride as out) the epilogue accumulates stats[n] += dz, stats[N + n] += dz * xhat, dz = out * 1[0 <= y*sc+sh <= 6]
+    const float* red_y; const float* red_scale; const float* red_shift; const float* red_mean; const float* red_invstd;
     int diag;                         // CRNN_GEMM_DIAG (timing experiments only, results are garbage): 1 no epilogue stores, 2 no transform, 4 no MMA, 8 no activation fetch
 };
 
@@ -513,6 +516,22 @@ __device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src,
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// store + BN-backward reduction: dz = val * 1[0 <= y*sc+sh <= 6]; s1 += dz; s2 += dz * (y*xa + xb)
+template <int LDO>
+__device__ __forceinline__ void epi_store_red(float* dst, const float* __restrict__ ysrc, const uint32_t (&r)[32], int ldo_rt,
+                                              float sc, float sh, float xa, float xb, float& s1, float& s2) {
+    float y[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) y[p] = __ldg(LDO > 0 ? ysrc + p * LDO : ysrc + (size_t)p * ldo_rt);
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+        const float val = __uint_as_float(r[p]);
+        if (LDO > 0) dst[p * LDO] = val; else dst[(size_t)p * ldo_rt] = val;
+        const float z = fmaf(y[p], sc, sh);
+        const float dz = (z >= 0.f && z <= 6.f) ? val : 0.f;
+        s1 += dz; s2 = fmaf(dz, fmaf(y[p], xa, xb), s2);
+    }
+}
 template <int LDO, bool STATS>
 __device__ __forceinline__ void epi_store(float* dst, const uint32_t (&r)[32], int ldo_rt, float& s1, float& s2) {
 #pragma unroll
@@ -737,6 +756,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             const int n = (ct0 + h) * TC_BC + q * 32 + lane;
             const bool n_ok = n < a.N;
             const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
+            float rsc = 0.f, rsh = 0.f, rxa = 0.f, rxb = 0.f;                    // fused BN-backward reduction: per-channel constants
+            if (a.red_y && n_ok) { rsc = __ldg(a.red_scale + n); rsh = __ldg(a.red_shift + n); rxa = __ldg(a.red_invstd + n); rxb = -__ldg(a.red_mean + n) * rxa; }
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
             for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
@@ -757,7 +778,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 } else if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast paths: full 32-pixel chunk, no per-element predicate
                     // row stride known at compile time for the conv-stack widths -> the 32 stores use immediate offsets (the generic
                     // loop costs a 64-bit add per store; the epilogue warps share the issue slots with the activation producers)
-                    if (a.stats) {                                              // conv forward: store + BN statistics
+                    if (a.red_y) {                                              // dX + reduction pass of the following BN/ReLU6 backward
+                        const float* ysrc = a.red_y + (size_t)(m0 + c0) * a.ldo + n;
+                        switch (a.ldo) {
+                            case 64: epi_store_red<64>(dst, ysrc, r, 0, rsc, rsh, rxa, rxb, s1, s2); break;
+                            case 128: epi_store_red<128>(dst, ysrc, r, 0, rsc, rsh, rxa, rxb, s1, s2); break;
+                            case 256: epi_store_red<256>(dst, ysrc, r, 0, rsc, rsh, rxa, rxb, s1, s2); break;
+                            case 512: epi_store_red<512>(dst, ysrc, r, 0, rsc, rsh, rxa, rxb, s1, s2); break;
+                            default: epi_store_red<0>(dst, ysrc, r, a.ldo, rsc, rsh, rxa, rxb, s1, s2);
+                        }
+                    } else if (a.stats) {                                       // conv forward: store + BN statistics
                         switch (a.ldo) {
                             case 128: epi_store<128, true>(dst, r, 0, s1, s2); break;
                             case 256: epi_store<256, true>(dst, r, 0, s1, s2); break;
@@ -788,7 +818,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                             if (a.relu) val = fmaxf(val, 0.f);
                             if (a.accumulate) val += *dst;
                             *dst = val;
-                            s1 += val; s2 = fmaf(val, val, s2);
+                            if (a.red_y) {
+                                const float y = __ldg(a.red_y + (size_t)(m0 + c0 + p) * a.ldo + n);
+                                const float z = fmaf(y, rsc, rsh);
+                                const float dz = (z >= 0.f && z <= 6.f) ? val : 0.f;
+                                s1 += dz; s2 = fmaf(dz, fmaf(y, rxa, rxb), s2);
+                            } else { s1 += val; s2 = fmaf(val, val, s2); }
                         }
                         dst += a.ldo;
                     }
@@ -862,13 +897,18 @@ int xw_gemm_tc_pick_ksplit(int M, int N, int K)
 
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
-                      const float* bias, int relu, int accumulate, int rev, int ksplit, long long split_stride)
+                      const float* bias, int relu, int accumulate, int rev, int ksplit, long long split_stride, const TcBnRed* red)
 {
     if (M <= 0 || N <= 0) return CRNN_OK;
     if (K % TC_BK || K <= 0) { crnn_set_error("gemm_tc: K=%d must be a positive multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
     if ((ldx % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Wimg) & 15)) { crnn_set_error("gemm_tc: X/Wimg must be 16-byte aligned, ldx %% 4 == 0"); return CRNN_ERR_INVALID; }
     TcArgs a; a.X = X; a.ldx = ldx; a.Wimg = Wimg; a.out = out; a.ldo = ldo; a.M = M; a.N = N; a.K = K;
     a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats; a.bias = bias; a.relu = relu; a.accumulate = accumulate; a.rev = rev;
+    a.red_y = nullptr; a.red_scale = a.red_shift = a.red_mean = a.red_invstd = nullptr;
+    if (red) {
+        if (!stats || bias || relu || accumulate || ksplit > 1) { crnn_set_error("gemm_tc: the fused BN-backward reduction needs stats and the plain-store epilogue"); return CRNN_ERR_INVALID; }
+        a.red_y = red->y; a.red_scale = red->scale; a.red_shift = red->shift; a.red_mean = red->mean; a.red_invstd = red->invstd;
+    }
     static int diag = -1, nsub_env = -1;
     if (diag < 0) { const char* e = getenv("CRNN_GEMM_DIAG"); diag = e ? atoi(e) : 0; const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; }
     a.diag = diag;

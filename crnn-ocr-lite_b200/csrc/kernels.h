@@ -20,9 +20,12 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 // ---- gemm_tc.cu : tcgen05 / TMEM 3xTF32 kernel, out[m][n] = sum_k f(X[m][k]) * Wop[n][k] ----
 size_t tc_weight_image_floats(int N, int K);
 int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transposed, float* img, cudaStream_t st);
+// fused reduction pass of the BatchNorm+ReLU6 backward consuming the GEMM output (see TcArgs::red_y); y has the output's shape / stride
+struct TcBnRed { const float* y; const float* scale; const float* shift; const float* mean; const float* invstd; };
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
-                      const float* bias = nullptr, int relu = 0, int accumulate = 0, int rev = 0, int ksplit = 1, long long split_stride = 0);
+                      const float* bias = nullptr, int relu = 0, int accumulate = 0, int rev = 0, int ksplit = 1, long long split_stride = 0,
+                      const TcBnRed* red = nullptr);
 // split-K for GEMMs with too few 128 x 128 output tiles to fill the SMs: slices the caller should request (1 = none); every slice
 // writes its own copy of the output (split_stride floats apart), summed in a fixed order by launch_sum_partials
 int xw_gemm_tc_pick_ksplit(int M, int N, int K);
@@ -67,8 +70,10 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
                            int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st,
                            const uint64_t* seed_ptr = nullptr, int rev = 0);   // reduce pass walks `rev`, apply pass the opposite way
 // same for the BN after the depthwise conv (no pool / dropout); dy may alias da
+// reduce_done != 0: `red` was already accumulated by the producer of `da` (fused into the dX GEMM epilogue), only the apply pass runs
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
-                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev = 0);
+                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev = 0,
+                        int reduce_done = 0);
 // BN training backward: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) in place; dgamma = sum(dz*xhat), dbeta = sum(dz)
 int launch_bn_bwd_apply(float* dz_inout, const float* y, const double* red, const float* gamma, const float* save_mean,
                         const float* save_invstd, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
