@@ -749,6 +749,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             const int ct0 = ((t / KS) % NTP) * NSUB, m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
             float* const outp = a.out + (size_t)(t % KS) * (size_t)split_stride;      // this k-slice's copy of the output
             if (ct0 != cur_ct0) { flush_stats(); cur_ct0 = ct0; }
+            if (a.red_y) {
+                // the fused reduction reads y = red_y at the tile's positions: pull this warp's 64 pixel rows x 128 B (per channel tile) into
+                // L2 while the tensor core is still working on the tile (the loads sit on the epilogue's critical path otherwise)
+                for (int h = 0; h < NSUB; ++h) {
+                    const int nb = (ct0 + h) * TC_BC + q * 32;
+#pragma unroll
+                    for (int pp = 0; pp < 64; pp += 32) {
+                        const int m = m0 + half * 64 + pp + lane;
+                        if (m < a.M && nb < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.red_y + (size_t)m * a.ldo + nb));
+                    }
+                }
+            }
             mbar_wait(&tfull[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
