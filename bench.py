@@ -176,6 +176,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO prints to stdout)
         dist.init_process_group("nccl", device_id=dev)
     import crnn_b200 as cb
     lib = cb._lib.load()
