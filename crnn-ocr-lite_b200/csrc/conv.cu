@@ -482,6 +482,11 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ red, float* __r
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) { dbeta[c] += (float)red[c]; dgamma[c] += (float)red[C + c]; }
 }
+__global__ void bn_param_grads_all_kernel(BnGradTable t)       // blockIdx.y = layer
+{
+    const int l = blockIdx.y, C = t.C[l];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) { t.dbeta[l][c] += (float)t.red[l][c]; t.dgamma[l][c] += (float)t.red[l][C + c]; }
+}
 
 // ReLU6 + BatchNorm backward of the BN that follows the depthwise conv (no pool / dropout): y, da, dy are [M][C].
 //   APPLY=false: reductions only;  APPLY=true: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dy may alias da.
@@ -917,7 +922,8 @@ static int launch_bn_relu6_reduce(const float* da, const float* y, const float* 
 // two launches: reductions, then apply (+ a tiny launch for dgamma/dbeta); `red` (double[2C]) must be pre-zeroed
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red, float* dgamma, float* dbeta,
-                           int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr, int rev) {
+                           int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr, int rev,
+                           int emit_param_grads) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
@@ -936,11 +942,12 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
     else { crnn_set_error("act_pool: unsupported pool %dx%d", ph, pw); return CRNN_ERR_INVALID; }
 #undef APB
     LAUNCH_CHECK();
+    if (!emit_param_grads) return CRNN_OK;
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
-                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev, int reduce_done) {
+                        const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev, int reduce_done, int emit_param_grads) {
     dim3 grid, block;
     const double invM = 1.0 / (double)M;
     if (reduce_done && (C % 4)) { crnn_set_error("relu6_bn_bwd: fused reduction needs C %% 4 == 0"); return CRNN_ERR_INVALID; }
@@ -956,7 +963,13 @@ int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, con
         relu6_bwd_scalar_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
     }
     LAUNCH_CHECK();
+    if (!emit_param_grads) return CRNN_OK;
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
+int launch_bn_param_grads_all(const BnGradTable& t, cudaStream_t st) {
+    if (t.n <= 0) return CRNN_OK;
+    bn_param_grads_all_kernel<<<dim3(2, t.n), 256, 0, st>>>(t);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_bn_bwd_apply(float* dz, const float* y, const double* red, const float* gamma, const float* mean, const float* invstd,

@@ -82,6 +82,7 @@ struct crnn_handle {
     Prof prof;
     bool gemm_simt = false;   // CRNN_GEMM_SIMT=1: fp32 SIMT GEMM for the pointwise convs instead of the tcgen05 3xTF32 kernel
     bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
+    bool defer_bn_grads = false;   // full backward: dgamma/dbeta of all 14 BN layers in one launch at the end instead of 14 tiny ones
     bool fuse_bn_red = true;   // CRNN_FUSE_BN_RED=0: separate reduction pass for the ReLU6+BN backward after the depthwise conv
     bool rnn_simt_cluster = false;   // CRNN_RNN_SIMT_CLUSTER=1: cluster kernels with U in shared memory + FFMA (rnn_cluster.cu) instead of rnn_mma.cu
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
@@ -546,7 +547,7 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
     ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (3.0 + 2.0 / (b.ph * b.pw)),
        launch_act_pool_bn_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
                               h->w(bnname(bn2, "gamma")), dpw, bn_red(h, bn2), h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")),
-                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv()));
+                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv(), h->defer_bn_grads ? 0 : 1));
     h->rv();   // two kernels (reduce, apply): two direction flips
     if (b.cin == 1) {
         // block 1: dW[co] = sum_m f(x[m]) dY[m][co] and dX[m] = sum_co dY[m][co] W[co] in ONE pass over dY
@@ -573,7 +574,7 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
     }
     ST(ST_BN_BWD, 20.0 * Mi * b.cin,
        launch_relu6_bn_bwd(ddw, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st, h->rv(), fused_red ? 1 : 0));
+                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st, h->rv(), fused_red ? 1 : 0, h->defer_bn_grads ? 0 : 1));
     h->rv();
     const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
     {
@@ -623,9 +624,20 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     int dims_h[8], dims_w[8];
     dims_h[1] = h->Hp; dims_w[1] = h->Wp;
     for (int i = 1; i < 7; ++i) { dims_h[i + 1] = dims_h[i] / kBlocks[i - 1].ph; dims_w[i + 1] = dims_w[i] / kBlocks[i - 1].pw; }
+    h->defer_bn_grads = true;
     for (int i = 7; i >= 1; --i) {
-        TRY(block_backward(h, i, dims_h[i], dims_w[i], cur, other, B, drop, seed, st));
+        const int rc = block_backward(h, i, dims_h[i], dims_w[i], cur, other, B, drop, seed, st);
+        if (rc != CRNN_OK) { h->defer_bn_grads = false; return rc; }
         float* t = cur; cur = other; other = t;
+    }
+    h->defer_bn_grads = false;
+    {
+        BnGradTable tb; tb.n = 14;
+        for (int bn = 1; bn <= 14; ++bn) {
+            tb.red[bn - 1] = bn_red(h, bn); tb.dgamma[bn - 1] = h->g(bnname(bn, "gamma")); tb.dbeta[bn - 1] = h->g(bnname(bn, "beta"));
+            tb.C[bn - 1] = (bn & 1) ? kBlocks[(bn - 1) / 2].cin : kBlocks[(bn - 1) / 2].cout;
+        }
+        ST(ST_BN_BWD, 0, launch_bn_param_grads_all(tb, side_after(h, st)));
     }
     // ---- STN: sampler -> theta -> localisation net
     CUDA_TRY(cudaMemsetAsync(h->a("dtheta"), 0, sizeof(float) * 6 * B, st));

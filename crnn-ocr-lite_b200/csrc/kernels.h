@@ -68,12 +68,15 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red /*pre-zeroed [2C]*/, float* dgamma, float* dbeta,
                            int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st,
-                           const uint64_t* seed_ptr = nullptr, int rev = 0);   // reduce pass walks `rev`, apply pass the opposite way
+                           const uint64_t* seed_ptr = nullptr, int rev = 0, int emit_param_grads = 1);   // reduce pass walks `rev`, apply pass the opposite way
 // same for the BN after the depthwise conv (no pool / dropout); dy may alias da
 // reduce_done != 0: `red` was already accumulated by the producer of `da` (fused into the dX GEMM epilogue), only the apply pass runs
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                         const float* gamma, float* dy, double* red, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st, int rev = 0,
-                        int reduce_done = 0);
+                        int reduce_done = 0, int emit_param_grads = 1);
+// dgamma / dbeta of up to 16 BatchNorm layers from their reduction buffers in ONE launch (instead of one tiny launch per layer on the critical path)
+struct BnGradTable { const double* red[16]; float* dgamma[16]; float* dbeta[16]; int C[16]; int n; };
+int launch_bn_param_grads_all(const BnGradTable& t, cudaStream_t st);
 // BN training backward: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) in place; dgamma = sum(dz*xhat), dbeta = sum(dz)
 int launch_bn_bwd_apply(float* dz_inout, const float* y, const double* red, const float* gamma, const float* save_mean,
                         const float* save_invstd, float* dgamma, float* dbeta, long long M, int C, cudaStream_t st);
