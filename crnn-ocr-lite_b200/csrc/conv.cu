@@ -852,9 +852,16 @@ int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, in
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4 (fused statistics need C %% 4 == 0)"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;
 }
-int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev) {
+int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev,
+                           const DwRowsRed* red, double* red_buf, int* red_done) {
     if (accumulate) { crnn_set_error("dwconv_bwd_data: accumulate unsupported"); return CRNN_ERR_INVALID; }
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
+    if (red_done) *red_done = 0;
+    if (red && red_buf) {
+        const int rc = launch_dwconv_rows(dy, k, dx, B, H, W, C, 1, red_buf, rev, st, red);
+        if (rc < 0) return rc;
+        if (rc == 0) { if (red_done) *red_done = 1; return rc; }
+    }
     { const int rc = launch_dwconv_rows(dy, k, dx, B, H, W, C, 1, nullptr, rev, st); if (rc <= 0) return rc; }
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
@@ -923,7 +930,7 @@ static int launch_bn_relu6_reduce(const float* da, const float* y, const float* 
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red, float* dgamma, float* dbeta,
                            int B, int H, int W, int C, int ph, int pw, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr, int rev,
-                           int emit_param_grads) {
+                           int emit_param_grads, int reduce_done) {
     if (C % 4 || H % ph || W % pw || ph * pw > 4) { crnn_set_error("act_pool: unsupported shape"); return CRNN_ERR_INVALID; }
     const long long npix = (long long)B * (H / ph) * (W / pw);
     if (too_big((long long)B * H * W * C)) return CRNN_ERR_INVALID;
@@ -932,9 +939,12 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
 #define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix, seed_ptr, (A_) ? !rev : rev)
     const size_t sm = sizeof(float) * 8 * 256;
+    if (reduce_done && (ph != 1 || pw != 1)) { crnn_set_error("act_pool_bn_bwd: a fused reduction only exists for the non-pooled blocks"); return CRNN_ERR_INVALID; }
     if (ph == 1 && pw == 1) {
-        const int rc = launch_bn_relu6_reduce(da, y, scale, shift, mean, invstd, red, (long long)B * H * W, C, rev, rate, seed, layer, seed_ptr, st);
-        if (rc != CRNN_OK) return rc;
+        if (!reduce_done) {
+            const int rc = launch_bn_relu6_reduce(da, y, scale, shift, mean, invstd, red, (long long)B * H * W, C, rev, rate, seed, layer, seed_ptr, st);
+            if (rc != CRNN_OK) return rc;
+        }
         APB(true, 1, 1, 0);
     }
     else if (ph == 2 && pw == 2) { APB(false, 2, 2, sm); LAUNCH_CHECK(); APB(true, 2, 2, 0); }

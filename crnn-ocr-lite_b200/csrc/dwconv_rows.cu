@@ -32,19 +32,32 @@ constexpr int NTHR = 256;
 
 // Work item = (image b, strip, column segment); blockDim = (CQ channel quads, PY items).
 // y[r][w] = sum_{i,j} x[r+i-1][w+j-1] * kk[i][j], kk = k (forward) or k rotated by 180 degrees (FLIP: backward-data).
-template <bool FLIP, bool STATS>
+// RED (backward-data only): the output is d(block output) of the block below, whose BatchNorm+ReLU6(+Dropout) backward starts with a
+// reduction pass over exactly this tensor -- it is accumulated here while the values are still in registers (red[c] += dz,
+// red[C+c] += dz*xhat, dz = out * dropmask * 1[0 <= bn(y) <= 6], y = that block's raw pointwise output), saving one read of out and a launch.
+struct RowsRed { const float* y; const float* scale; const float* shift; const float* mean; const float* invstd;
+                 float rate, inv_keep; uint64_t seed; uint32_t layer; const uint64_t* seed_ptr; };
+template <bool FLIP, bool STATS, bool RED>
 __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                                                                  int H, int W, int C4, int nseg, int nstrips, int RS, int nitems,
-                                                                 double* __restrict__ stats, int rev)
+                                                                 double* __restrict__ stats, int rev, RowsRed rr)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    float4* ks = reinterpret_cast<float4*>(smraw);              // [9][CQ] taps of this CTA's channel quads
+    float4* ks = reinterpret_cast<float4*>(smraw);              // [9][CQ] taps of this CTA's channel quads (+ [4][CQ] BN constants with RED)
     const int CQ = blockDim.x, PY = blockDim.y;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
     const int C = C4 * 4;
     const bool cok = c4 < C4;
     if (cok)
         for (int q = threadIdx.y; q < 9; q += PY) ks[q * CQ + threadIdx.x] = ldg4(k + (size_t)(FLIP ? 8 - q : q) * C + c4 * 4);
+    if (RED && cok && threadIdx.y == 0) {
+        const float4 xa = ldg4(rr.invstd + c4 * 4), mu = ldg4(rr.mean + c4 * 4);
+        ks[9 * CQ + threadIdx.x] = ldg4(rr.scale + c4 * 4);
+        ks[10 * CQ + threadIdx.x] = ldg4(rr.shift + c4 * 4);
+        ks[11 * CQ + threadIdx.x] = xa;                                                   // xhat = y*xa + xb
+        ks[12 * CQ + threadIdx.x] = make_float4(-mu.x * xa.x, -mu.y * xa.y, -mu.z * xa.z, -mu.w * xa.w);
+    }
+    const uint64_t rseed = (RED && rr.seed_ptr) ? *rr.seed_ptr : rr.seed;
     __syncthreads();
     float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
     int item = blockIdx.y * PY + threadIdx.y;
@@ -82,6 +95,12 @@ __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __
                 if (q < nsteps) {
                     const int r = hs - 1 + q;
                     if (q + 1 < nsteps) load_row(xb[(u + 1) & 1], r + 1, xrow + (size_t)(q + 1) * rstride);
+                    float4 yv[SEG];                                  // RED: raw activations at the positions stored at the end of this step
+                    if (RED && q >= 2) {
+                        const float* yp = rr.y + (yrow - y) + (size_t)(q - 2) * rstride;
+#pragma unroll
+                        for (int o = 0; o < SEG; ++o) yv[o] = ldg4(yp + (size_t)o * C);
+                    }
                     float4 (&xc)[SEG + 2] = xb[u & 1];
                     float4 (&A)[SEG] = acc[u % 3];               // output row r-1 (gets tap row 2)
                     float4 (&Bm)[SEG] = acc[(u + 1) % 3];        // output row r   (tap row 1)
@@ -104,6 +123,25 @@ __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __
                                 sq[0] = fmaf(A[o].x, A[o].x, sq[0]); sq[1] = fmaf(A[o].y, A[o].y, sq[1]);
                                 sq[2] = fmaf(A[o].z, A[o].z, sq[2]); sq[3] = fmaf(A[o].w, A[o].w, sq[3]);
                             }
+                            if (RED) {
+                                const float4 sc = kq[9 * CQ], sh = kq[10 * CQ], xa = kq[11 * CQ], xbn = kq[12 * CQ];
+                                float d[4] = {A[o].x, A[o].y, A[o].z, A[o].w};
+                                if (rr.rate > 0.f) {
+                                    float dm[4];
+                                    crnn_dropout_mask4(rseed, rr.layer, (uint64_t)(((dst - y) + (size_t)o * C) >> 2), rr.rate, rr.inv_keep, dm);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) d[e] *= dm[e];
+                                }
+                                const float yy[4] = {yv[o].x, yv[o].y, yv[o].z, yv[o].w};
+                                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                                const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xbn.x, xbn.y, xbn.z, xbn.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float z = fmaf(yy[e], scv[e], shv[e]);
+                                    const float dz = (z >= 0.f && z <= 6.f) ? d[e] : 0.f;
+                                    s[e] += dz; sq[e] = fmaf(dz, fmaf(yy[e], xav[e], xbv[e]), sq[e]);
+                                }
+                            }
                         }
                     }
 #pragma unroll
@@ -112,8 +150,8 @@ __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __
             }
         }
     }
-    if (!STATS) return;
-    // BatchNorm statistics of the outputs (fp32 per thread over <= RS x 3 values, fp64 across threads): one atomic pair per channel and CTA
+    if (!STATS && !RED) return;
+    // BatchNorm statistics of the outputs (STATS) / reduction pass of the next BatchNorm backward (RED) (fp32 per thread over <= RS x 3 values, fp64 across threads): one atomic pair per channel and CTA
     __syncthreads();                                                 // taps no longer needed: reuse the buffer
     double* dsm = reinterpret_cast<double*>(smraw);                  // [PY][8][CQ]
 #pragma unroll
@@ -249,15 +287,20 @@ void plan_rows(int B, int H, int W, int C4, int occ, int segw, dim3& grid, dim3&
 }  // namespace
 
 // returns CRNN_OK when the row-marching kernel ran, 1 when the shape is not covered (caller falls back to the channel-block kernel)
-int launch_dwconv_rows(const float* x, const float* k, float* y, int B, int H, int W, int C, int flip, double* stats, int rev, cudaStream_t st)
+int launch_dwconv_rows(const float* x, const float* k, float* y, int B, int H, int W, int C, int flip, double* stats, int rev, cudaStream_t st,
+                       const DwRowsRed* red)
 {
-    if (!rows_enabled() || C % 4 || W % SEG || W < SEG || (flip && stats)) return 1;
+    if (!rows_enabled() || C % 4 || W % SEG || W < SEG || (flip && stats && !red) || (red && (!flip || !stats))) return 1;
     dim3 grid, block; int nseg, nstrips, RS, nitems;
     plan_rows(B, H, W, C / 4, 2, SEG, grid, block, nseg, nstrips, RS, nitems);
-    const size_t sm = std::max(sizeof(float4) * 9 * block.x, stats ? sizeof(double) * 8 * NTHR : (size_t)0);
-    if (flip) dwconv3x3_rows_kernel<true, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev);
-    else if (stats) dwconv3x3_rows_kernel<false, true><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev);
-    else dwconv3x3_rows_kernel<false, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev);
+    const size_t sm = std::max(sizeof(float4) * 13 * block.x, (stats ? sizeof(double) * 8 * NTHR : (size_t)0));
+    RowsRed rr = {};
+    if (red) { rr.y = red->y; rr.scale = red->scale; rr.shift = red->shift; rr.mean = red->mean; rr.invstd = red->invstd; rr.rate = red->rate;
+               rr.inv_keep = red->rate > 0.f ? 1.f / (1.f - red->rate) : 1.f; rr.seed = red->seed; rr.layer = red->layer; rr.seed_ptr = red->seed_ptr; }
+    if (red) dwconv3x3_rows_kernel<true, false, true><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev, rr);
+    else if (flip) dwconv3x3_rows_kernel<true, false, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev, rr);
+    else if (stats) dwconv3x3_rows_kernel<false, true, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev, rr);
+    else dwconv3x3_rows_kernel<false, false, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev, rr);
     LAUNCH_CHECK();
     return CRNN_OK;
 }

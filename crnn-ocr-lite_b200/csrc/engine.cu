@@ -82,6 +82,7 @@ struct crnn_handle {
     Prof prof;
     bool gemm_simt = false;   // CRNN_GEMM_SIMT=1: fp32 SIMT GEMM for the pointwise convs instead of the tcgen05 3xTF32 kernel
     bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
+    int bn2_red_done[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [block]: reduction pass of the block's BN2 backward already accumulated by the producer of its dy
     bool defer_bn_grads = false;   // full backward: dgamma/dbeta of all 14 BN layers in one launch at the end instead of 14 tiny ones
     bool fuse_bn_red = true;   // CRNN_FUSE_BN_RED=0: separate reduction pass for the ReLU6+BN backward after the depthwise conv
     bool rnn_simt_cluster = false;   // CRNN_RNN_SIMT_CLUSTER=1: cluster kernels with U in shared memory + FFMA (rnn_cluster.cu) instead of rnn_mma.cu
@@ -547,7 +548,8 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
     ST(ST_ACT_BWD, 4.0 * Mi * b.cout * (3.0 + 2.0 / (b.ph * b.pw)),
        launch_act_pool_bn_bwd(cur, pw, h->a(actbn(bn2, "scale")), h->a(actbn(bn2, "shift")), h->a(actbn(bn2, "mean")), h->a(actbn(bn2, "invstd")),
                               h->w(bnname(bn2, "gamma")), dpw, bn_red(h, bn2), h->g(bnname(bn2, "gamma")), h->g(bnname(bn2, "beta")),
-                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv(), h->defer_bn_grads ? 0 : 1));
+                              B, hh, ww, b.cout, b.ph, b.pw, drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv(), h->defer_bn_grads ? 0 : 1, h->bn2_red_done[i]));
+    h->bn2_red_done[i] = 0;
     h->rv();   // two kernels (reduce, apply): two direction flips
     if (b.cin == 1) {
         // block 1: dW[co] = sum_m f(x[m]) dY[m][co] and dX[m] = sum_co dY[m][co] W[co] in ONE pass over dY
@@ -581,7 +583,17 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
         cudaStream_t ss = side_after(h, st);
         ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, ddw, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, ss));
     }
-    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st, h->rv()));
+    // `other` becomes d(output of block i-1): when that block is not pooled, its BN2-backward reduction pass is accumulated by this kernel
+    DwRowsRed rr; const DwRowsRed* rrp = nullptr; double* rbuf = nullptr;
+    if (i >= 2 && h->fuse_bn_red && h->defer_bn_grads && kBlocks[i - 2].ph == 1 && kBlocks[i - 2].pw == 1) {
+        const int pbn = 2 * (i - 1);
+        rr.y = h->a(nm("pw%d", i - 1)); rr.scale = h->a(actbn(pbn, "scale")); rr.shift = h->a(actbn(pbn, "shift")); rr.mean = h->a(actbn(pbn, "mean"));
+        rr.invstd = h->a(actbn(pbn, "invstd")); rr.rate = drop ? kDropBlock : 0.f; rr.seed = seed; rr.layer = (uint32_t)(i - 1); rr.seed_ptr = h->seed_ptr;
+        rrp = &rr; rbuf = bn_red(h, pbn);
+    }
+    int done = 0;
+    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st, h->rv(), rrp, rbuf, &done));
+    if (i >= 2) h->bn2_red_done[i - 1] = done;
     return CRNN_OK;
 }
 

@@ -49,10 +49,17 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
 // ---- conv.cu (depthwise conv, BN statistics, activation/pool, elementwise) ----
 // rev (here and below): walk the tensor from its end (serpentine traversal: a kernel starts where its producer finished, in L2)
 int launch_dwconv_fwd(const float* x, const float* k33c, float* y, int B, int H, int W, int C, cudaStream_t st, double* stats = nullptr, int rev = 0);
-int launch_dwconv_bwd_data(const float* dy, const float* k33c, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev = 0);
+// `red` (backward-data only, needs `stats` = the reduction buffer): fused reduction pass of the BatchNorm+ReLU6(+Dropout) backward that
+// consumes the output (see dwconv_rows.cu); y = raw pre-BN activation with the output's shape
+struct DwRowsRed { const float* y; const float* scale; const float* shift; const float* mean; const float* invstd;
+                   float rate; uint64_t seed; uint32_t layer; const uint64_t* seed_ptr; };
+// red_done (optional out): set to 1 when the fused reduction described by `red` / `red_buf` was performed by the kernel that ran
+int launch_dwconv_bwd_data(const float* dy, const float* k33c, float* dx, int B, int H, int W, int C, int accumulate, cudaStream_t st, int rev = 0,
+                           const DwRowsRed* red = nullptr, double* red_buf = nullptr, int* red_done = nullptr);
 // dwconv_rows.cu: row-marching variants; return 1 (not an error) when the shape is not covered and the caller must fall back
 int launch_dwconv_rows_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
-int launch_dwconv_rows(const float* x, const float* k33c, float* y, int B, int H, int W, int C, int flip, double* stats, int rev, cudaStream_t st);
+int launch_dwconv_rows(const float* x, const float* k33c, float* y, int B, int H, int W, int C, int flip, double* stats, int rev, cudaStream_t st,
+                       const DwRowsRed* red = nullptr);
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
 // per-channel sum / sum of squares over rows of y[M][C] -> stats[0..C) , stats[C..2C) (double, pre-zeroed)
 int launch_colstats(const float* y, long long M, int C, double* stats, cudaStream_t st);
@@ -68,7 +75,8 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
 int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
                            const float* gamma, float* dy, double* red /*pre-zeroed [2C]*/, float* dgamma, float* dbeta,
                            int B, int H, int W, int C, int ph, int pw, float drop_rate, uint64_t seed, uint32_t layer, cudaStream_t st,
-                           const uint64_t* seed_ptr = nullptr, int rev = 0, int emit_param_grads = 1);   // reduce pass walks `rev`, apply pass the opposite way
+                           const uint64_t* seed_ptr = nullptr, int rev = 0, int emit_param_grads = 1,
+                           int reduce_done = 0);   // reduce pass walks `rev`, apply pass the opposite way; reduce_done: `red` already accumulated by the producer of da
 // same for the BN after the depthwise conv (no pool / dropout); dy may alias da
 // reduce_done != 0: `red` was already accumulated by the producer of `da` (fused into the dX GEMM epilogue), only the apply pass runs
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
