@@ -413,7 +413,9 @@ constexpr int LFR = 16;               // A fragments per warp
 
 // ---- forward.  warp = (k-quarter kq: 64 k = 8 k-steps, gate g: 2 m-tiles of 16 units)
 // smem: hT[2][256][8] | part[4][128][8] | lo[16][512] uint2 | xring[RING][4][256] | 2 mbarriers
-constexpr int LF_SMEM_BYTES = 4 * (2 * U * RB + 4 * LC * RB + RING * 4 * (UPC * RB)) + 8 * LFR * NT + 32;
+constexpr int LHS = 4;                // of the 16 fragments, this many keep their hi parts in shared memory too (12 x 4 = 48 registers stay resident:
+                                      // with all 64 in registers ptxas spilled ~30 of them to local memory and reloaded them every step)
+constexpr int LF_SMEM_BYTES = 4 * (2 * U * RB + 4 * LC * RB + RING * 4 * (UPC * RB)) + 8 * LFR * NT + 16 * LHS * NT + 32;
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
 lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, const float* __restrict__ U1,
@@ -422,7 +424,8 @@ lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, 
     extern __shared__ __align__(16) float sm[];
     float* hT = sm;                                 // [2][256][8]
     float* part = hT + 2 * U * RB;                  // [4 k-quarters][128 cols (gate-major)][8 rows]
-    uint2* los = reinterpret_cast<uint2*>(part + 4 * LC * RB);     // [16 frags][512 threads]
+    uint4* his = reinterpret_cast<uint4*>(part + 4 * LC * RB);     // [4 frags][512 threads]  hi parts of k-steps 6, 7
+    uint2* los = reinterpret_cast<uint2*>(his + LHS * NT);         // [16 frags][512 threads]
     float* xring = reinterpret_cast<float*>(los + LFR * NT);       // [RING][4 gates][256]
     uint64_t* barH = reinterpret_cast<uint64_t*>(xring + RING * 4 * (UPC * RB));   // [2]
     cg::cluster_group cluster = cg::this_cluster();
@@ -432,7 +435,7 @@ lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     const int kq = warp & 3, g = warp >> 2;
 
-    uint32_t fh[2][8][4];                           // tf32 hi parts of the A fragments (m-tile, k-step)
+    uint32_t fh[2][6][4];                           // tf32 hi parts of the A fragments (m-tile, k-step 0..5); k-steps 6, 7 live in `his`
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
         const float* r0 = Um + (size_t)(64 * kq + 8 * kk + tig) * (LG * U);
@@ -441,8 +444,10 @@ lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, 
         for (int mt = 0; mt < 2; ++mt) {
             const int c = g * U + crank * UPC + 16 * mt + gid;
             AFrag f; afrag_set(f, __ldg(r0 + c), __ldg(r0 + c + 8), __ldg(r1 + c), __ldg(r1 + c + 8));
+            if (kk < 6) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) fh[mt][kk][i] = f.hi[i];
+                for (int i = 0; i < 4; ++i) fh[mt][kk][i] = f.hi[i];
+            } else his[(mt * 2 + kk - 6) * NT + tid] = make_uint4(f.hi[0], f.hi[1], f.hi[2], f.hi[3]);
             los[(mt * 8 + kk) * NT + tid] = make_uint2(f.lo[0], f.lo[1]);
         }
     }
@@ -482,21 +487,26 @@ lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, 
         prefetch(s + PF);
         if (s > 0) bar_wait(&barH[(s - 1) & 1], ((s - 1) >> 1) & 1);      // h_{t-1} of all 256 units has landed
         {
-            float am[2][4] = {};                           // one chain per m-tile: 4 warps per scheduler keep the tensor pipe busy
+            float am[2][4] = {}, ax[2][4] = {};
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const BFrag bf = bfrag(hcur, 64 * kq + 8 * kk, gid, tig);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint2 lo = los[(mt * 8 + kk) * NT + tid];
-                    mma2(am[mt], am[mt], fh[mt][kk], lo.x, lo.y, bf);
+                    if (kk < 6) mma2(am[mt], ax[mt], fh[mt][kk], lo.x, lo.y, bf);
+                    else {
+                        const uint4 hv = his[(mt * 2 + kk - 6) * NT + tid];
+                        const uint32_t hi[4] = {hv.x, hv.y, hv.z, hv.w};
+                        mma2(am[mt], ax[mt], hi, lo.x, lo.y, bf);
+                    }
                 }
             }
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 float* p = part + ((kq * LC + g * UPC + 16 * mt + gid) * RB + 2 * tig);
-                *reinterpret_cast<float2*>(p) = make_float2(am[mt][0], am[mt][1]);
-                *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[mt][2], am[mt][3]);
+                *reinterpret_cast<float2*>(p) = make_float2(am[mt][0] + ax[mt][0], am[mt][1] + ax[mt][1]);
+                *reinterpret_cast<float2*>(p + 8 * RB) = make_float2(am[mt][2] + ax[mt][2], am[mt][3] + ax[mt][3]);
             }
         }
         cp_async_wait_pf();
@@ -530,7 +540,7 @@ lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, 
 
 // ---- backward.  warp w owns hidden units [16 w, 16 w + 16) for all 128 shard columns (16 k-steps, gate-major)
 // smem: da[2][4][32][8] | recv[2][8][32][8] | lo[16][512] uint2 | gring[RING][8][256] | 2 mbarriers
-constexpr int LB_SMEM_BYTES = 4 * (2 * LC * RB + 2 * NCTA * UPC * RB + RING * 8 * (UPC * RB)) + 8 * LFR * NT + 32;
+constexpr int LB_SMEM_BYTES = 4 * (2 * LC * RB + 2 * NCTA * UPC * RB + RING * 8 * (UPC * RB)) + 8 * LFR * NT + 16 * LHS * NT + 32;
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
 lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs, const float* __restrict__ gates,
@@ -540,7 +550,8 @@ lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs
     extern __shared__ __align__(16) float sm[];
     float* da = sm;                                 // [2][4 gates i,f,g,o][32 units][8 rows]
     float* recv = da + 2 * LC * RB;                 // [2][8 src][32][8]
-    uint2* los = reinterpret_cast<uint2*>(recv + 2 * NCTA * UPC * RB);
+    uint4* his = reinterpret_cast<uint4*>(recv + 2 * NCTA * UPC * RB);   // hi parts of k-steps 12..15
+    uint2* los = reinterpret_cast<uint2*>(his + LHS * NT);
     float* gring = reinterpret_cast<float*>(los + LFR * NT);       // [RING][8: i, f, g, o, c, c_prev, h_prev, dout][256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(gring + RING * 8 * (UPC * RB));   // [2]
     cg::cluster_group cluster = cg::this_cluster();
@@ -549,7 +560,7 @@ lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs
     const float* Um = dir ? U1 : U0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
 
-    uint32_t fh[LFR][4];
+    uint32_t fh[LFR - LHS][4];
     {
         const float* r0 = Um + (size_t)(16 * warp + gid) * (LG * U);
         const float* r1 = r0 + (size_t)8 * (LG * U);
@@ -558,8 +569,10 @@ lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs
             const int c = 8 * kk + tig;
             const int cg0 = (c >> 5) * U + crank * UPC + (c & 31), cg1 = ((c + 4) >> 5) * U + crank * UPC + ((c + 4) & 31);
             AFrag f; afrag_set(f, __ldg(r0 + cg0), __ldg(r1 + cg0), __ldg(r0 + cg1), __ldg(r1 + cg1));
+            if (kk < LFR - LHS) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) fh[kk][i] = f.hi[i];
+                for (int i = 0; i < 4; ++i) fh[kk][i] = f.hi[i];
+            } else his[(kk - (LFR - LHS)) * NT + tid] = make_uint4(f.hi[0], f.hi[1], f.hi[2], f.hi[3]);
             los[kk * NT + tid] = make_uint2(f.lo[0], f.lo[1]);
         }
     }
@@ -632,7 +645,12 @@ lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs
 #pragma unroll
             for (int kk = 0; kk < LFR; ++kk) {
                 const uint2 lo = los[kk * NT + tid];
-                mma2(am, ax, fh[kk], lo.x, lo.y, bfrag(dab, 8 * kk, gid, tig));
+                if (kk < LFR - LHS) mma2(am, ax, fh[kk], lo.x, lo.y, bfrag(dab, 8 * kk, gid, tig));
+                else {
+                    const uint4 hv = his[(kk - (LFR - LHS)) * NT + tid];
+                    const uint32_t hi[4] = {hv.x, hv.y, hv.z, hv.w};
+                    mma2(am, ax, hi, lo.x, lo.y, bfrag(dab, 8 * kk, gid, tig));
+                }
             }
             const float c[4] = {am[0] + ax[0], am[1] + ax[1], am[2] + ax[2], am[3] + ax[3]};
             push_tile(c, rcv, &bar[buf], owner, crank, ubase, gid, tig);

@@ -151,10 +151,14 @@ class CRNNModel:
 
     def tensor(self, name) -> torch.Tensor:
         """Torch view (no copy) of a named tensor of the workspace: weights, 'grad/<w>', 'act/<x>', 'arena/<a>'."""
-        info = _lib.TensorInfo()
-        _lib.check(self.lib.crnn_tensor_lookup(self.handle, name.encode(), ctypes.byref(info)))
-        raw = self.workspace[info.offset: info.offset + info.numel * 4]
-        return raw.view(torch.int32 if info.is_int else torch.float32)
+        cache = self.__dict__.setdefault("_tensor_cache", {})
+        t = cache.get(name)
+        if t is None:
+            info = _lib.TensorInfo()
+            _lib.check(self.lib.crnn_tensor_lookup(self.handle, name.encode(), ctypes.byref(info)))
+            raw = self.workspace[info.offset: info.offset + info.numel * 4]
+            t = cache[name] = raw.view(torch.int32 if info.is_int else torch.float32)
+        return t
 
     def tensor_names(self):
         return [self.lib.crnn_tensor_name(self.handle, i).decode() for i in range(self.lib.crnn_num_tensors(self.handle))]
@@ -318,12 +322,17 @@ class CRNNModel:
         loss = self.train_fwd_bwd_device(xd, lab, ll, il, dropout_seed=self._step_seed if self.dropout else 0)
         scale = self.allreduce_grads()
         self.optimizer_step(scale)
-        val = float(loss.mean().item())          # D2H of the step's result
-        st = ctypes.c_int32()
-        _lib.check(self.lib.crnn_ctc_status(self.handle, ctypes.byref(st), self._stream()))
-        if st.value != 0:
-            raise ValueError(f"Not enough time for target transition sequence (batch element {-st.value - 1})")
-        return val
+        # D2H of the step's result: per-sample losses + the CTC feasibility status in one pinned buffer, ONE stream synchronisation
+        pin = self.__dict__.get("_result_pin")
+        if pin is None or pin[0].numel() < B:
+            pin = self._result_pin = (torch.empty(max(B, self.max_batch), dtype=torch.float32).pin_memory(), torch.empty(1, dtype=torch.int32).pin_memory())
+        pin[0][:B].copy_(loss, non_blocking=True)
+        pin[1].copy_(self.tensor("act/status")[:1].view(torch.int32), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        st = int(pin[1][0])
+        if st != 0:
+            raise ValueError(f"Not enough time for target transition sequence (batch element {-st - 1})")
+        return float(pin[0][:B].numpy().mean(dtype=np.float64))
 
     def test_on_batch(self, inputs, outputs=None):
         """Validation loss: inference-mode forward + CTC loss (no gradient)."""
