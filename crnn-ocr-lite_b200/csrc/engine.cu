@@ -592,7 +592,7 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
         rrp = &rr; rbuf = bn_red(h, pbn);
     }
     int done = 0;
-    ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st, h->rv(), rrp, rbuf, &done));
+    ST(ST_DWCONV_BWD, (rrp ? 12.0 : 8.0) * Mi * b.cin /* + one read of the block-below's raw activation for the fused reduction */, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st, h->rv(), rrp, rbuf, &done));
     if (i >= 2) h->bn2_red_done[i - 1] = done;
     return CRNN_OK;
 }
