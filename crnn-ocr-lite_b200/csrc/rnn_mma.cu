@@ -143,6 +143,9 @@ gru_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, c
     const int dir = blockIdx.y, b0 = (blockIdx.x / NCTA) * RB;
     const float* Um = dir ? U1 : U0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    // (tried: r gate alone before the exchange and the z gate's MMAs deferred into the r*h exchange window -- 8 fewer MMAs per warp on
+    // the critical path, step time unchanged at 4.2 us: the step is a chain of many small latencies (two exchanges 27 %, MMA phases 34 %,
+    // element-wise + push 20 %, barriers 7 %, ncu r1n), not MMA-bound.)
     // MMA identity: warp = (k-slice of 32, column group mp).  Phase A: the 32 columns of gate mp (0: z, 1: r) = 2 m-tiles;
     // phase B: columns [16 mp, 16 mp + 16) of the candidate gate = 1 m-tile.
     const int mp = warp & 1, ks = warp >> 1;
