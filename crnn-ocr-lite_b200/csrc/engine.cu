@@ -914,6 +914,34 @@ int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps
     return decode_host(false, probs_host, B, T, V, eps, 0, 1, out_host, out_len_host, score_host, stream);
 }
 
+// Evaluation step (utils.py:262-298): Levenshtein distance of N (prediction, truth) pairs of int32 symbol sequences padded to maxlen.
+int crnn_edit_distance(const int32_t* a_dev, const int32_t* alen_dev, const int32_t* b_dev, const int32_t* blen_dev, int N, int maxlen,
+                       int32_t* dist_dev, void* stream) {
+    if (N < 0 || (N > 0 && (!a_dev || !alen_dev || !b_dev || !blen_dev || !dist_dev))) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    return launch_edit_distance(a_dev, alen_dev, b_dev, blen_dev, N, maxlen, dist_dev, static_cast<cudaStream_t>(stream));
+}
+// host buffers in, host buffer out (H2D + kernel + D2H + stream synchronisation)
+int crnn_edit_distance_host(const int32_t* a, const int32_t* alen, const int32_t* b, const int32_t* blen, int N, int maxlen, int32_t* dist, void* stream) {
+    if (N < 0 || (N > 0 && (!a || !alen || !b || !blen || !dist))) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    if (N == 0) return CRNN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t seq = sizeof(int32_t) * (size_t)N * maxlen, len = sizeof(int32_t) * (size_t)N;
+    char* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 2 * seq + 3 * len));
+    int32_t* da = reinterpret_cast<int32_t*>(d); int32_t* db = reinterpret_cast<int32_t*>(d + seq);
+    int32_t* dal = reinterpret_cast<int32_t*>(d + 2 * seq); int32_t* dbl = dal + N; int32_t* dout = dbl + N;
+    int rc = CRNN_OK;
+    if (cudaMemcpyAsync(da, a, seq, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaMemcpyAsync(db, b, seq, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(dal, alen, len, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaMemcpyAsync(dbl, blen, len, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        crnn_set_error("edit_distance_host: H2D copy failed"); rc = CRNN_ERR_CUDA;
+    }
+    if (rc == CRNN_OK) rc = launch_edit_distance(da, dal, db, dbl, N, maxlen, dout, st);
+    if (rc == CRNN_OK && (cudaMemcpyAsync(dist, dout, len, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)) {
+        crnn_set_error("edit_distance_host: D2H copy failed"); rc = CRNN_ERR_CUDA;
+    }
+    cudaFree(d);
+    return rc;
+}
 int crnn_gemm_tc(const float* X, int ldx, const float* W, int ldw, int w_transposed, float* out, int ldo, int M, int N, int K,
                  const float* x_scale, const float* x_shift, double* stats, float* img_scratch, void* stream) {
     if (!X || !W || !out || !img_scratch) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }

@@ -146,3 +146,6 @@ int launch_adam(float* w, const float* g, float* m, float* v, long long n, const
                 float lr_t, float b1, float b2, float eps, float gscale, cudaStream_t st);
 int launch_sgd_nesterov(float* w, const float* g, float* vel, long long n, const double* sumsq, float clipnorm,
                         float lr_i, float momentum, float gscale, cudaStream_t st);
+
+// ---- eval.cu : batched Levenshtein distance (utils.py:262-298), one thread per pair, sequences padded to maxlen <= 128 ----
+int launch_edit_distance(const int32_t* a, const int32_t* alen, const int32_t* b, const int32_t* blen, int N, int maxlen, int32_t* out, cudaStream_t st);

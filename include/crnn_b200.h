@@ -112,6 +112,16 @@ int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, 
 int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps,
                          int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream);
 
+/* ---------------------------------------------------------------- evaluation step
+ * Replaces the Python loops of utils.py:262-298 (levenshtein / edit_distance / normalized_edit_distance, called from predict.py:183-191):
+ * Levenshtein distance of N (prediction, truth) pairs.  Sequences are int32 symbols (character codes or class indices) padded to
+ * `maxlen` (<= 128) per row; lengths are clamped to [0, maxlen].  dist[i] is the exact integer the reference's matrix fill produces;
+ * the two means are formed by the caller in the reference's order (sum_i dist_i / N, sum_i dist_i / (len(truth_i) * N)). */
+int crnn_edit_distance(const int32_t* a_dev, const int32_t* alen_dev, const int32_t* b_dev, const int32_t* blen_dev, int N, int maxlen,
+                       int32_t* dist_dev, void* stream);
+int crnn_edit_distance_host(const int32_t* a_host, const int32_t* alen_host, const int32_t* b_host, const int32_t* blen_host, int N, int maxlen,
+                            int32_t* dist_host, void* stream);
+
 /* ---------------------------------------------------------------- building blocks exposed for parity tests */
 /* C[M,N] = op(A) op(B) (+bias, relu); see csrc/gemm_simt.cu */
 int crnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,

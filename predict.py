@@ -96,8 +96,8 @@ def main():
         start = time.time()
         true_text = [decoder.labels_to_text(y) for y in y_true]
         print(" [INFO] Example pairs (predicted, true): \n", list(zip(predicted_text[:10], true_text[:10])))
-        ed = U.edit_distance(predicted_text, true_text)
-        ned = U.normalized_edit_distance(predicted_text, true_text)
+        ed = U.edit_distance_cuda(predicted_text, true_text)                 # utils.py:289-299 on the GPU (bit-identical distances)
+        ned = U.normalized_edit_distance_cuda(predicted_text, true_text)
         print(f" [INFO] edit distances calculated in {round(time.time() - start, 2)} sec. ")
         print(f" [INFO] mean edit distance: {ed} ")
         print(f" [INFO] mean normalized edit distance: {ned} ")

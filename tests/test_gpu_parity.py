@@ -2,6 +2,7 @@
 on identical seeded inputs.  Integer outputs (decode indices) must be bit-exact; floating point within the stated
 fp32 tolerances.  Run with `pytest -m gpu` on a B200 (gpurun)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -486,3 +487,29 @@ def test_graph_replay_matches_eager(cb):
         np.testing.assert_array_equal(s, sm[0])
     ref = N.forward(N.to_torch(m.get_weights()), torch.tensor(x), cfg, training=False)["softmax"].numpy()
     _cmp("softmax(graph)", sm[3], ref, 3e-4)
+
+
+@pytest.mark.gpu
+def test_edit_distance_cuda_golden(cb):
+    """crnn_edit_distance_host (C ABI) vs the reference's own levenshtein / edit_distance / normalized_edit_distance outputs
+    (tests/golden/metrics_golden.json) -- integer distances and the two float64 means must be bit-identical -- plus random pairs
+    against the host mirror, empty strings, label sequences and the maximum supported length (128)."""
+    import json
+    import random
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.json")))
+    pred = [p for p, _ in g["pairs"]]; true = [t for _, t in g["pairs"]]
+    d = cb.levenshtein_batch_cuda(pred, true)
+    assert d.dtype == np.int32 and d.tolist() == [int(v) for v in g["levenshtein"]]
+    assert cb.edit_distance_cuda(pred, true) == g["edit_distance"]
+    assert cb.normalized_edit_distance_cuda(pred, true) == g["normalized_edit_distance"]
+    rng = random.Random(7)
+    A = ["".join(rng.choice("abcd") for _ in range(rng.randint(0, 128))) for _ in range(2000)]
+    Bs = ["".join(rng.choice("abcd") for _ in range(rng.randint(1, 128))) for _ in range(2000)]
+    got = cb.levenshtein_batch_cuda(A, Bs)
+    for i in range(0, 2000, 37):
+        assert got[i] == int(cb.levenshtein(A[i], Bs[i])), i
+    assert cb.levenshtein_batch_cuda(["", "x" * 128, ""], ["", "y" * 128, "abc"]).tolist() == [0, 128, 3]
+    assert cb.levenshtein_batch_cuda([[1, 2, 3, 4]], [[1, 3, 4, 5]]).tolist() == [2]
+    assert cb.levenshtein_batch_cuda([], []).size == 0
+    with pytest.raises(ValueError):
+        cb.levenshtein_batch_cuda(["a" * 129], ["b"])

@@ -165,3 +165,16 @@ def test_dp_world2_gloo(tmp_path):
                         "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_metrics_reproduce_reference_golden(cb):
+    """Evaluation step: the host mirror of utils.py:262-298 against outputs of the REFERENCE's own functions
+    (tests/golden/metrics_golden.json, produced by tests/golden/make_metrics_golden.py from /root/reference/utils.py)."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.json")))
+    pred = [p for p, _ in g["pairs"]]; true = [t for _, t in g["pairs"]]
+    assert [cb.levenshtein(p, t) for p, t in g["pairs"]] == g["levenshtein"]
+    assert cb.edit_distance(pred, true) == g["edit_distance"]                       # same summation order -> bit-identical float64
+    assert cb.normalized_edit_distance(pred, true) == g["normalized_edit_distance"]
+    # label sequences (lists of ints) work like strings
+    assert cb.levenshtein([1, 2, 3, 4], [1, 3, 4, 5]) == 2.0

@@ -19,6 +19,8 @@ save_model_json = _cb.save_model_json
 Readf, open_img, read_img, norm = _cb.Readf, _cb.open_img, _cb.read_img, _cb.norm
 parse_mjsynth, get_lexicon, get_lengths, make_ohe = _cb.parse_mjsynth, _cb.get_lexicon, _cb.get_lengths, _cb.make_ohe
 levenshtein, edit_distance, normalized_edit_distance = _cb.levenshtein, _cb.edit_distance, _cb.normalized_edit_distance
+# GPU-batched evaluation step (include/crnn_b200.h crnn_edit_distance_host): same numbers, one kernel instead of O(N L^2) Python
+levenshtein_batch_cuda, edit_distance_cuda, normalized_edit_distance_cuda = _cb.levenshtein_batch_cuda, _cb.edit_distance_cuda, _cb.normalized_edit_distance_cuda
 EarlyStoppingIter, ModelCheckpoint = _cb.EarlyStoppingIter, _cb.ModelCheckpoint
 optimizers = types.SimpleNamespace(Adam=_cb.Adam, SGD=_cb.SGD)   # keras.optimizers subset (train.py:188-190)
 
