@@ -914,6 +914,11 @@ int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps
     return decode_host(false, probs_host, B, T, V, eps, 0, 1, out_host, out_len_host, score_host, stream);
 }
 
+// Input pipeline (utils.py:415-416): out[i] = (float32(in[i]) - mean) / std on the device; `out` is then fed to crnn_forward / crnn_train_fwd_bwd.
+int crnn_normalize_u8(const uint8_t* x_u8_dev, float* out_dev, long long n, float mean, float std, void* stream) {
+    if (n < 0 || (n > 0 && (!x_u8_dev || !out_dev)) || !(std != 0.f)) { crnn_set_error("bad argument"); return CRNN_ERR_INVALID; }
+    return launch_normalize_u8(x_u8_dev, out_dev, n, mean, std, static_cast<cudaStream_t>(stream));
+}
 // Evaluation step (utils.py:262-298): Levenshtein distance of N (prediction, truth) pairs of int32 symbol sequences padded to maxlen.
 int crnn_edit_distance(const int32_t* a_dev, const int32_t* alen_dev, const int32_t* b_dev, const int32_t* blen_dev, int N, int maxlen,
                        int32_t* dist_dev, void* stream) {

@@ -149,3 +149,5 @@ int launch_sgd_nesterov(float* w, const float* g, float* vel, long long n, const
 
 // ---- eval.cu : batched Levenshtein distance (utils.py:262-298), one thread per pair, sequences padded to maxlen <= 128 ----
 int launch_edit_distance(const int32_t* a, const int32_t* alen, const int32_t* b, const int32_t* blen, int N, int maxlen, int32_t* out, cudaStream_t st);
+// input normalisation of 8-bit line images on the device (utils.py:415-416), bit-identical to numpy's float32 arithmetic
+int launch_normalize_u8(const uint8_t* in, float* out, long long n, float mean, float stdv, cudaStream_t st);

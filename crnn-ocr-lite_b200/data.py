@@ -100,7 +100,11 @@ class Readf:
     """utils.py:418-511: batch generator yielding ({'the_input','the_labels','input_length','label_length',
     'source_str'}, {'ctc'}) with X float64 (B,H,W,1) and labels padded with blank=len(classes)."""
 
-    def __init__(self, img_size=(40, 40), max_len=30, normed=False, batch_size=32, classes={}, mean=MJ_MEAN, std=MJ_STD, transform_p=0.7):
+    def __init__(self, img_size=(40, 40), max_len=30, normed=False, batch_size=32, classes={}, mean=MJ_MEAN, std=MJ_STD, transform_p=0.7,
+                 device_norm=False):
+        # device_norm (NEW, SURVEY 8f-2): with normed=True, yield the 8-bit crops ('the_input' uint8) and let the model normalise them on the
+        # GPU (crnn_normalize_u8, bit-identical to norm()): a quarter of the host->device bytes and no float64 batch on the host
+        self.device_norm = bool(device_norm) and bool(normed)
         self.batch_size, self.transform_p, self.img_size, self.normed = batch_size, transform_p, img_size, normed
         self.classes, self.max_len, self.mean, self.std = classes, max_len, mean, std
         self.voc = list(classes.keys())
@@ -120,7 +124,7 @@ class Readf:
         return Y
 
     def get_blank_matrices(self):
-        X = np.empty((self.batch_size,) + tuple(self.img_size))
+        X = np.empty((self.batch_size,) + tuple(self.img_size), np.uint8 if getattr(self, "device_norm", False) else np.float64)
         Y = np.full([self.batch_size, self.max_len], self.blank)
         return X, Y, np.ones((self.batch_size, 1)), np.zeros((self.batch_size, 1))
 
@@ -150,7 +154,7 @@ class Readf:
                     Y[i, :len(t)] = t
                     ll[i] = len(t)
                     il[i] = in_len
-                    X[i] = (norm(crop, self.mean, self.std) if self.normed else crop)[:, :, np.newaxis]
+                    X[i] = (norm(crop, self.mean, self.std) if (self.normed and not self.device_norm) else crop)[:, :, np.newaxis]
                     i += 1
                     batch = ({"the_input": X, "the_labels": Y, "input_length": il, "label_length": ll, "source_str": np.array(words)},
                              {"ctc": np.zeros([self.batch_size])})

@@ -246,6 +246,13 @@ class CRNNModel:
 
     def predict_on_batch(self, x) -> np.ndarray:
         """Host numpy (B,imgh,imgw,1) -> host numpy softmax (B,T,V): H2D + forward + D2H through the C ABI."""
+        if np.asarray(x).dtype == np.uint8:                      # raw 8-bit line images: upload bytes, normalise + forward on the device
+            x = np.asarray(x)
+            out = []
+            for s in range(0, x.shape[0], self.max_batch):
+                sm = self.forward_device(self._stage_input(x[s:s + self.max_batch]))
+                out.append(sm.cpu().numpy().copy())
+            return np.concatenate(out, 0)
         x = np.ascontiguousarray(x, np.float32)
         out = []
         for s in range(0, x.shape[0], self.max_batch):
@@ -310,11 +317,26 @@ class CRNNModel:
         dev[:arr.size].copy_(pin[:arr.size], non_blocking=True)
         return dev[:arr.size]
 
+    input_mean, input_std = 118.24236953981779, 36.72835353999682      # utils.py:421 (norm constants of the mjsynth runs)
+
+    def _stage_input(self, x):
+        """Host images -> device float32 (B,imgh,imgw,1).  float input: as the reference's generator yields it (already normalised).
+        uint8 input (NEW): the raw 8-bit line images are uploaded and `norm` (utils.py:415-416) runs on the device."""
+        x = np.asarray(x)
+        B = x.shape[0]
+        if x.dtype == np.uint8:
+            xu = self._stage("x_u8", x, torch.uint8)
+            t = self._pinned.get("x_f32")
+            if t is None or t.numel() < xu.numel():
+                t = self._pinned["x_f32"] = torch.empty(max(xu.numel(), self.max_batch * self.imgh * self.imgw), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.crnn_normalize_u8(xu.data_ptr(), t.data_ptr(), xu.numel(), float(np.float32(self.input_mean)), float(np.float32(self.input_std)), self._stream()))
+            return t[:xu.numel()].view(B, self.imgh, self.imgw, 1)
+        return self._stage("x", x.astype(np.float32, copy=False), torch.float32).view(B, self.imgh, self.imgw, 1)
+
     def train_on_batch(self, inputs, outputs=None):
         """Keras train_on_batch on the generator's dict (utils.py:495-502): host buffers in, scalar mean loss out."""
-        x = np.asarray(inputs["the_input"], np.float32)
-        B = x.shape[0]
-        xd = self._stage("x", x, torch.float32).view(B, self.imgh, self.imgw, 1)
+        xd = self._stage_input(inputs["the_input"])
+        B = xd.shape[0]
         lab = self._stage("labels", np.asarray(inputs["the_labels"]).astype(np.int32), torch.int32)
         ll = self._stage("label_len", np.asarray(inputs["label_length"]).reshape(-1).astype(np.int32), torch.int32)
         il = self._stage("input_len", np.asarray(inputs["input_length"]).reshape(-1).astype(np.int32), torch.int32)
@@ -336,9 +358,8 @@ class CRNNModel:
 
     def test_on_batch(self, inputs, outputs=None):
         """Validation loss: inference-mode forward + CTC loss (no gradient)."""
-        x = np.asarray(inputs["the_input"], np.float32)
-        B = x.shape[0]
-        xd = self._stage("x", x, torch.float32).view(B, self.imgh, self.imgw, 1)
+        xd = self._stage_input(inputs["the_input"])
+        B = xd.shape[0]
         sm = self.forward_device(xd)
         lab = self._stage("labels", np.asarray(inputs["the_labels"]).astype(np.int32), torch.int32)
         ll = self._stage("label_len", np.asarray(inputs["label_length"]).reshape(-1).astype(np.int32), torch.int32)

@@ -112,6 +112,11 @@ int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, 
 int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps,
                          int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream);
 
+/* ---------------------------------------------------------------- input pipeline
+ * Device-side `norm` of utils.py:415-416 (called per image at utils.py:490): out = (float32(u8) - mean) / std in fp32, bit-identical to
+ * numpy.  The host uploads the 8-bit line images produced by open_img (B*imgh*imgw bytes) instead of float32. */
+int crnn_normalize_u8(const uint8_t* x_u8_dev, float* out_dev, long long n, float mean, float std, void* stream);
+
 /* ---------------------------------------------------------------- evaluation step
  * Replaces the Python loops of utils.py:262-298 (levenshtein / edit_distance / normalized_edit_distance, called from predict.py:183-191):
  * Levenshtein distance of N (prediction, truth) pairs.  Sequences are int32 symbols (character codes or class indices) padded to

@@ -513,3 +513,28 @@ def test_edit_distance_cuda_golden(cb):
     assert cb.levenshtein_batch_cuda([], []).size == 0
     with pytest.raises(ValueError):
         cb.levenshtein_batch_cuda(["a" * 129], ["b"])
+
+
+@pytest.mark.gpu
+def test_uint8_input_device_norm(cb):
+    """Input pipeline: crnn_normalize_u8 is bit-identical to the reference's norm() (utils.py:415-416, float32 arithmetic),
+    and feeding the raw 8-bit images gives exactly the outputs of feeding the host-normalised float images."""
+    lib = cb._lib.load()
+    rng = np.random.default_rng(11)
+    u8 = rng.integers(0, 256, (5, 100, 32, 1), dtype=np.uint8)
+    mean, std = 118.24236953981779, 36.72835353999682
+    ref = (u8.astype("float32") - mean) / std                      # the reference's expression, verbatim
+    assert ref.dtype == np.float32
+    xin = torch.tensor(u8, device="cuda")
+    out = torch.empty(u8.size, dtype=torch.float32, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cb._lib.check(lib.crnn_normalize_u8(xin.data_ptr(), out.data_ptr(), u8.size, float(np.float32(mean)), float(np.float32(std)), st))
+    np.testing.assert_array_equal(out.cpu().numpy().reshape(u8.shape), ref)
+    odd = torch.empty(7, dtype=torch.float32, device="cuda")       # n % 4 != 0 tail
+    cb._lib.check(lib.crnn_normalize_u8(xin.data_ptr(), odd.data_ptr(), 7, float(np.float32(mean)), float(np.float32(std)), st))
+    np.testing.assert_array_equal(odd.cpu().numpy(), ref.reshape(-1)[:7])
+    cfg = N.Cfg(imgh=100)
+    w, m = _make(cb, cfg, 5, 3)
+    a = m.predict_on_batch(ref)
+    b = m.predict_on_batch(u8)
+    np.testing.assert_array_equal(a, b)
