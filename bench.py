@@ -167,12 +167,21 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def _emit(line, fd):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def run_ours(args):
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. "NCCL version ..." at communicator
+    # creation) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the line is written to the saved descriptor
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: this path has no CPU fallback"}), flush=True)
+        _emit({"error": "no CUDA device: this path has no CPU fallback"}, out_fd)
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -384,7 +393,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
             "roofline": roof, "cpu_baseline": cpu, "beam_decode": beam, "extra": extra,
             "stages_top": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.items()} for s in stages[:8]]}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    _emit(line, out_fd)
     if world > 1:
         dist.destroy_process_group()
     return 0
