@@ -637,6 +637,7 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     dims_h[1] = h->Hp; dims_w[1] = h->Wp;
     for (int i = 1; i < 7; ++i) { dims_h[i + 1] = dims_h[i] / kBlocks[i - 1].ph; dims_w[i + 1] = dims_w[i] / kBlocks[i - 1].pw; }
     h->defer_bn_grads = true;
+    for (int i = 0; i < 8; ++i) h->bn2_red_done[i] = 0;     // no stale "reduction already done" flag from a step that failed half-way
     for (int i = 7; i >= 1; --i) {
         const int rc = block_backward(h, i, dims_h[i], dims_w[i], cur, other, B, drop, seed, st);
         if (rc != CRNN_OK) { h->defer_bn_grads = false; return rc; }
