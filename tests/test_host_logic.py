@@ -178,3 +178,30 @@ def test_metrics_reproduce_reference_golden(cb):
     assert cb.normalized_edit_distance(pred, true) == g["normalized_edit_distance"]
     # label sequences (lists of ints) work like strings
     assert cb.levenshtein([1, 2, 3, 4], [1, 3, 4, 5]) == 2.0
+
+
+def test_early_stopping_iter_reproduces_reference_traces(cb):
+    """Training-driver policy: EarlyStoppingIter against per-iteration traces of the REFERENCE's own class
+    (tests/golden/callback_golden.json, produced by tests/golden/make_callback_golden.py from /root/reference/utils.py:535-614):
+    stop decision, best value, stop iteration, cumulative sum and the restore_best_weights side effects must match exactly."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "callback_golden.json")))
+
+    class Model:
+        def __init__(self): self.stop_training = False; self.w = 0; self.sets = []
+        def get_weights(self): return self.w
+        def set_weights(self, w): self.sets.append(w); self.w = w
+
+    for case in g["cases"]:
+        c = cb.EarlyStoppingIter(**case["kwargs"]); m = Model(); c.model = m
+        c.on_train_begin()
+        trace = []
+        for i, v in enumerate(case["losses"]):
+            m.w = i
+            c.on_batch_end(i, {case["key"]: v} if v is not None else {})
+            trace.append([bool(m.stop_training), float(c.best), int(c.stopped_iter), int(c.cycle_iterations), float(c.sum_monitor)])
+            if m.stop_training:
+                break
+        c.on_train_end()
+        assert trace == case["trace"], case["kwargs"]
+        assert m.sets == case["sets"] and m.w == case["final_w"], case["kwargs"]
