@@ -205,3 +205,21 @@ def test_early_stopping_iter_reproduces_reference_traces(cb):
         c.on_train_end()
         assert trace == case["trace"], case["kwargs"]
         assert m.sets == case["sets"] and m.w == case["final_w"], case["kwargs"]
+
+
+def test_input_pipeline_reproduces_reference(cb):
+    """Host input pipeline: open_img / norm / get_lexicon / parse_mjsynth against outputs of the REFERENCE's own functions
+    (tests/golden/pipeline_golden.npz, produced by tests/golden/make_pipeline_golden.py from /root/reference/utils.py:359-416 with seeded
+    np.random): padding placement, inversion, up-scaling and the resize must be bit-identical."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pipeline_golden.npz"))
+    for i in range(int(g["n"])):
+        np.random.seed(int(g["seed_%d" % i]))
+        got, lab = cb.open_img(g["in_%d" % i].copy(), tuple(int(v) for v in g["size_%d" % i]), p=float(g["p_%d" % i]))
+        assert lab is False
+        np.testing.assert_array_equal(np.asarray(got), g["out_%d" % i], err_msg="case %d" % i)
+    out = cb.norm(g["norm_in"], 118.24236953981779, 36.72835353999682)
+    assert out.dtype == g["norm_out"].dtype
+    np.testing.assert_array_equal(out, g["norm_out"])
+    assert sorted(cb.get_lexicon()) == list(g["lexicon_default"])
+    assert sorted(cb.get_lexicon(non_intersecting_chars=True)) == list(g["lexicon_non_intersecting"])
+    assert cb.parse_mjsynth("/data/mj", ["./2194/2/334_EFFLORESCENT_24742.jpg 24742", "./3000/7/1_a_1.jpg 1"]) == list(g["mjsynth"])
