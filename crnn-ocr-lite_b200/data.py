@@ -136,9 +136,13 @@ class Readf:
             n_items = len(names)
         full, rem = divmod(n_items, self.batch_size)
         in_len = (self.img_size[0] + 4) // downsample_factor - 2          # utils.py:487
+        # State machine of utils.py:462-511, kept as is: the counters and buffers are NOT reset between passes over `names`, so only the
+        # first pass ends with a partial batch (tail rows stale, trimmed by the caller); from then on the stream is full batches that
+        # wrap around the end of the list (the first one after the wrap starts with the `rem` samples of the partial batch again).
+        # Pinned against the reference's own class in tests/test_host_logic.py::test_readf_generator_reproduces_reference.
+        done, i, words = 0, 0, []
+        X, Y, il, ll = self.get_blank_matrices()
         while True:
-            done, i, words = 0, 0, []
-            X, Y, il, ll = self.get_blank_matrices()
             for name in names:
                 whole = bboxs[name][0] == name
                 if whole:
@@ -159,7 +163,7 @@ class Readf:
                     batch = ({"the_input": X, "the_labels": Y, "input_length": il, "label_length": ll, "source_str": np.array(words)},
                              {"ctc": np.zeros([self.batch_size])})
                     if done == full and i == rem:
-                        yield batch            # last, partially filled batch (tail rows are stale; trimmed by the caller)
+                        yield batch            # last, partially filled batch of the FIRST pass
                     elif i == self.batch_size:
                         done += 1; i = 0; words = []
                         X, Y, il, ll = self.get_blank_matrices()

@@ -223,3 +223,32 @@ def test_input_pipeline_reproduces_reference(cb):
     assert sorted(cb.get_lexicon()) == list(g["lexicon_default"])
     assert sorted(cb.get_lexicon(non_intersecting_chars=True)) == list(g["lexicon_non_intersecting"])
     assert cb.parse_mjsynth("/data/mj", ["./2194/2/334_EFFLORESCENT_24742.jpg 24742", "./3000/7/1_a_1.jpg 1"]) == list(g["mjsynth"])
+
+
+def test_readf_generator_reproduces_reference(cb, tmp_path):
+    """Batch generator: Readf.run_generator against batches produced by the REFERENCE's own class over three passes
+    (tests/golden/readf_golden.npz from tests/golden/make_readf_golden.py): images, labels padded with the blank, input/label lengths,
+    source strings, the partial batch of the first pass and the reference's wrap-around from the second pass on."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_readf_golden", os.path.join(os.path.dirname(__file__), "golden", "make_readf_golden.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "readf_golden.npz"))
+    lex = cb.get_lexicon()
+    assert lex == list(g["lexicon"])
+    classes = {j: i for i, j in enumerate(lex)}
+    names = mk.make_images(str(tmp_path))
+    got = mk.collect(cb.Readf, classes, names, n=int(g["n"]))
+    for k, b in enumerate(got):
+        assert list(b["source_str"]) == list(g["str_%d" % k]), k
+        nv = len(b["source_str"])
+        np.testing.assert_array_equal(b["the_labels"][:nv], g["labels_%d" % k][:nv])
+        np.testing.assert_array_equal(b["input_length"][:nv], g["il_%d" % k][:nv])
+        np.testing.assert_array_equal(b["label_length"][:nv], g["ll_%d" % k][:nv])
+        assert b["the_input"].dtype == np.float64 and b["the_input"].shape == (4, 100, 32, 1)
+        np.testing.assert_array_equal(b["the_input"][:nv].astype(np.float32), g["x_%d" % k])
+    # device_norm=True yields the same crops as raw uint8 (normalised later on the GPU by crnn_normalize_u8)
+    np.random.seed(42)
+    gen = cb.Readf(img_size=(100, 32, 1), max_len=23, normed=True, batch_size=4, classes=classes, transform_p=0.7, device_norm=True).run_generator(names)
+    raw, _ = next(gen)
+    assert raw["the_input"].dtype == np.uint8
+    np.testing.assert_array_equal(cb.norm(raw["the_input"], 118.24236953981779, 36.72835353999682), g["x_0"])
