@@ -9,9 +9,11 @@ from PIL import Image
 
 REF = "/root/reference/utils.py"
 mod = ast.parse(open(REF).read())
-want = {"read_img", "open_img", "norm", "get_lexicon", "parse_mjsynth"}
-ns = {"np": np, "cv2": cv2, "Image": Image, "os": os, "string": string}
-exec(compile(ast.Module(body=[n for n in mod.body if isinstance(n, ast.FunctionDef) and n.name in want], type_ignores=[]), REF, "exec"), ns)
+from tqdm import tqdm
+want = {"read_img", "open_img", "norm", "get_lexicon", "parse_mjsynth", "labels_to_text", "get_lengths"}
+ns = {"np": np, "cv2": cv2, "Image": Image, "os": os, "string": string, "tqdm": tqdm}
+body = [n for n in mod.body if (isinstance(n, ast.FunctionDef) and n.name in want) or (isinstance(n, ast.ClassDef) and n.name == "DecodeCTCPred")]
+exec(compile(ast.Module(body=body, type_ignores=[]), REF, "exec"), ns)
 
 rng = np.random.default_rng(5)
 out = {}
@@ -37,5 +39,14 @@ out["norm_out"] = ns["norm"](x, 118.24236953981779, 36.72835353999682)
 out["lexicon_default"] = np.array(sorted(ns["get_lexicon"]()))
 out["lexicon_non_intersecting"] = np.array(sorted(ns["get_lexicon"](non_intersecting_chars=True)))
 out["mjsynth"] = np.array(ns["parse_mjsynth"]("/data/mj", ["./2194/2/334_EFFLORESCENT_24742.jpg 24742", "./3000/7/1_a_1.jpg 1"]))
+# label <-> text helpers (utils.py:314-345, 518-522): blank (= len(inverse_classes)) and -1 padding are dropped
+lex = ns["get_lexicon"]()
+inv = {i: c for i, c in enumerate(lex)}
+lab = np.array([[17, 14, 21, 21, 24, 37, -1, -1], [37, 37, 0, 9, 36, 37, 1, -1], [-1, -1, -1, -1, -1, -1, -1, -1]])
+out["l2t_labels"] = lab
+out["l2t_text_fn"] = np.array([ns["labels_to_text"](r, inverse_classes=inv) for r in lab])
+out["l2t_text_cls"] = np.array([ns["DecodeCTCPred"](top_paths=1, beam_width=3, inverse_classes=inv).labels_to_text(r) for r in lab])
+gl = ns["get_lengths"](["/a/b/12_hello_3.png", "7_x_1.jpg", "/q/0_abcdefghij_99.png"])
+out["get_lengths_keys"] = np.array(list(gl.keys())); out["get_lengths_vals"] = np.array(list(gl.values()))
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_golden.npz"), **out)
 print(n, "open_img cases")

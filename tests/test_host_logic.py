@@ -223,6 +223,13 @@ def test_input_pipeline_reproduces_reference(cb):
     assert sorted(cb.get_lexicon()) == list(g["lexicon_default"])
     assert sorted(cb.get_lexicon(non_intersecting_chars=True)) == list(g["lexicon_non_intersecting"])
     assert cb.parse_mjsynth("/data/mj", ["./2194/2/334_EFFLORESCENT_24742.jpg 24742", "./3000/7/1_a_1.jpg 1"]) == list(g["mjsynth"])
+    # label <-> text helpers (utils.py:314-345, 518-522), reference-produced
+    inv = {i: c for i, c in enumerate(cb.get_lexicon())}
+    for row, t_fn, t_cls in zip(g["l2t_labels"], g["l2t_text_fn"], g["l2t_text_cls"]):
+        assert cb.labels_to_text(row, inverse_classes=inv) == str(t_fn)
+        assert cb.DecodeCTCPred(top_paths=1, beam_width=3, inverse_classes=inv).labels_to_text(row) == str(t_cls)
+    gl = cb.get_lengths([str(k) for k in g["get_lengths_keys"]])
+    assert list(gl.keys()) == [str(k) for k in g["get_lengths_keys"]] and list(gl.values()) == [int(v) for v in g["get_lengths_vals"]]
 
 
 def test_readf_generator_reproduces_reference(cb, tmp_path):
