@@ -8,9 +8,10 @@ restated forward (CTC gradient = the TF CTCLoss op gradient from oracle/ctc_orac
 PARITY: Keras/TF cannot run in this image and the reference has no tests.  forward() + beam decode are PINNED
 against the reference's own example predictions (7 figure-extracted inputs through the shipped weights give the labels
 the reference printed, e.g. "cellist" -> "celist"; tests/test_golden.py, tests/golden/make_reference_examples.py).
+bilinear_sampler() is PINNED bit-exactly on the reference's own BilinearInterpolation source (utils.py:116-232) executed over a numpy
+shim of its backend ops (tests/golden/make_sampler_golden.py, tests/test_golden.py).
 The training half (CTC gradient, backward, Adam) is PARITY UNPINNED: pinned by structure (parameter counts /
-shapes of the shipped weight files, model_summary.txt), closed-form sampler invariants (tests/test_oracle_net.py) and
-torch cross-checks only.
+shapes of the shipped weight files, model_summary.txt), closed-form sampler invariants and torch cross-checks only.
 
 Tensor layout follows the reference: NHWC, axis 1 ("H") = text-line width = time, axis 2 ("W") = 32.
 Weight names are "<keras layer>/<weight>" exactly as stored in models/<name>/final_weights.h5.
