@@ -259,3 +259,27 @@ def test_readf_generator_reproduces_reference(cb, tmp_path):
     raw, _ = next(gen)
     assert raw["the_input"].dtype == np.uint8
     np.testing.assert_array_equal(cb.norm(raw["the_input"], 118.24236953981779, 36.72835353999682), g["x_0"])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/train.py"), reason="the reference checkout only exists in the build container")
+def test_cli_flags_match_reference():
+    """train.py / predict.py keep the reference's command line (train.py:83-109, predict.py:62-82): every flag of the reference exists
+    with the same default / type / action; the only additions are the documented extensions --cell and --greedy."""
+    import ast
+
+    def args_of(path):
+        out = {}
+        for n in ast.walk(ast.parse(open(path).read())):
+            if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr == "add_argument":
+                flags = [a.value for a in n.args if isinstance(a, ast.Constant)]
+                out[flags[0]] = {k.arg: ast.unparse(k.value) for k in n.keywords}
+        return out
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f, extra in (("train.py", {"--cell"}), ("predict.py", {"--greedy"})):
+        ref, ours = args_of("/root/reference/" + f), args_of(os.path.join(root, f))
+        assert set(ours) - set(ref) == extra, f
+        for flag, kw in ref.items():
+            assert flag in ours, (f, flag)
+            for key in ("default", "type", "action"):
+                assert kw.get(key) == ours[flag].get(key), (f, flag, key)
