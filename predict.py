@@ -13,24 +13,30 @@ import numpy as np
 from numpy.random import RandomState
 
 
-def main():
+# The reference's command line (predict.py:62-82), one row per flag: (name, type or None for a store_true switch, default, required).
+_FLAGS = [
+    ("--model_path", str, None, True), ("--image_path", str, None, True), ("--result_path", str, None, False), ("--max_len", int, 23, False),
+    ("--boxes", str, None, False), ("--val_fname", str, None, False), ("--num_instances", int, None, False), ("--G", int, -1, False),
+    ("--batch_size", int, 64, False), ("--random_state", int, 42, False), ("--train_portion", float, .9, False),
+    ("--validate", None, False, False), ("--mjsynth", None, False, False), ("--imgh", int, 100, False), ("--imgW", int, 32, False),
+]
+
+
+def build_parser():
     parser = argparse.ArgumentParser()
-    parser.add_argument("--model_path", type=str, required=True)
-    parser.add_argument("--image_path", type=str, required=True)
-    parser.add_argument("--result_path", type=str, default=None)
-    parser.add_argument("--max_len", type=int, default=23)
-    parser.add_argument("--boxes", type=str, default=None)
-    parser.add_argument("--val_fname", type=str, default=None)
-    parser.add_argument("--num_instances", type=int, default=None)
-    parser.add_argument("--G", type=int, default=-1)
-    parser.add_argument("--batch_size", type=int, default=64)
-    parser.add_argument("--random_state", type=int, default=42)
-    parser.add_argument("--train_portion", type=float, default=.9)
-    parser.add_argument("--validate", action="store_true")
-    parser.add_argument("--mjsynth", action="store_true")
-    parser.add_argument("--imgh", type=int, default=100)
-    parser.add_argument("--imgW", type=int, default=32)
+    for name, typ, default, required in _FLAGS:
+        if typ is None:
+            parser.add_argument(name, action="store_true")
+        elif required:
+            parser.add_argument(name, type=typ, required=True)
+        else:
+            parser.add_argument(name, type=typ, default=default)
     parser.add_argument("--greedy", action="store_true", help="extension: greedy CTC decode instead of beam width 10")
+    return parser
+
+
+def main():
+    parser = build_parser()
     args = parser.parse_args()
 
     import torch

@@ -20,30 +20,33 @@ import numpy as np
 from numpy.random import RandomState
 
 
-def main():
+# The reference's command line (train.py:83-106), one row per flag: (names, type or None for a store_true switch, default, required).
+_FLAGS = [
+    (("-p", "--path"), str, None, True), (("--training_fname",), str, None, False), (("--val_fname",), str, "", False),
+    (("--save_path",), str, None, True), (("--model_name",), str, None, True), (("--pretrained_path",), str, None, False),
+    (("--nbepochs",), int, 20, False), (("--G",), str, "1", False), (("--random_state",), int, 42, False),
+    (("--train_portion",), float, 0.9, False), (("--time_dense_size",), int, 128, False), (("--n_units",), int, 256, False),
+    (("--batch_size",), int, 64, False), (("--opt",), str, "sgd", False), (("--lr",), float, 0.001, False),
+    (("--early_stopping",), int, 0, False), (("--norm",), None, False, False), (("--mjsynth",), None, False, False),
+    (("--GRU",), None, False, False), (("--imgh",), int, 100, False), (("--imgW",), int, 32, False),
+]
+
+
+def build_parser():
     parser = argparse.ArgumentParser(description="crnn_ctc_loss")
-    parser.add_argument("-p", "--path", type=str, required=True)
-    parser.add_argument("--training_fname", type=str, default=None)
-    parser.add_argument("--val_fname", type=str, default="")
-    parser.add_argument("--save_path", type=str, required=True)
-    parser.add_argument("--model_name", type=str, required=True)
-    parser.add_argument("--pretrained_path", default=None, type=str)
-    parser.add_argument("--nbepochs", type=int, default=20)
-    parser.add_argument("--G", type=str, default="1")
-    parser.add_argument("--random_state", type=int, default=42)
-    parser.add_argument("--train_portion", type=float, default=0.9)
-    parser.add_argument("--time_dense_size", type=int, default=128)
-    parser.add_argument("--n_units", type=int, default=256)
-    parser.add_argument("--batch_size", type=int, default=64)
-    parser.add_argument("--opt", type=str, default="sgd")
-    parser.add_argument("--lr", type=float, default=0.001)
-    parser.add_argument("--early_stopping", type=int, default=0)
-    parser.add_argument("--norm", action="store_true")
-    parser.add_argument("--mjsynth", action="store_true")
-    parser.add_argument("--GRU", action="store_true")
-    parser.add_argument("--imgh", type=int, default=100)
-    parser.add_argument("--imgW", type=int, default=32)
+    for names, typ, default, required in _FLAGS:
+        if typ is None:
+            parser.add_argument(*names, action="store_true")
+        elif required:
+            parser.add_argument(*names, type=typ, required=True)
+        else:
+            parser.add_argument(*names, type=typ, default=default)
     parser.add_argument("--cell", choices=["gru", "lstm"], default="gru", help="extension: recurrent cell (reference CLI always builds GRU)")
+    return parser
+
+
+def main():
+    parser = build_parser()
     args = parser.parse_args()
 
     if "LOCAL_RANK" not in os.environ:
