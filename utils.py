@@ -36,3 +36,31 @@ def STN(*_a, **_k):
 
 
 BilinearInterpolation = STN
+
+
+def get_initial_weights(output_size):
+    """utils.py:239-245: [W = 0, b = identity affine] of the localisation head's last Dense layer."""
+    b = np.zeros((2, 3), dtype="float32")
+    b[0, 0] = 1
+    b[1, 1] = 1
+    return [np.zeros((output_size, 6), dtype="float32"), b.flatten()]
+
+
+def K_linspace(start, stop, num):
+    """utils.py:113-114 (tf.linspace) as the sampler kernels evaluate it: start + step * i in float32."""
+    step = np.float32((np.float32(stop) - np.float32(start)) / np.float32(num - 1))
+    return (np.float32(start) + step * np.arange(num, dtype=np.float32)).astype(np.float32)
+
+
+def K_meshgrid(x, y):
+    """utils.py:110-111 (tf.meshgrid)."""
+    return np.meshgrid(x, y)
+
+
+class GRU:       # noqa: D401 - names that `from utils import *` used to bring in from keras.layers (utils.py:20): the reference's train.py
+    """passes `GRU` to CRNN(GRU=...) AFTER the star import, i.e. this (truthy) class object and never the --GRU flag."""
+
+
+class LSTM:
+    """see GRU."""
+
