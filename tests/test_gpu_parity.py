@@ -538,3 +538,14 @@ def test_uint8_input_device_norm(cb):
     a = m.predict_on_batch(ref)
     b = m.predict_on_batch(u8)
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end():
+    """Drop-in command lines: `train.py` (1 epoch on synthetic word images) writes the reference's files, `predict.py --validate`
+    on that directory writes prediction.csv and reports the edit distances (tools/cli_smoke.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "cli_smoke.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "CLI SMOKE OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
