@@ -346,12 +346,19 @@ class _Writer:
         payload = b"".join(msgs)
         return struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(payload)) + payload
 
+    @staticmethod
+    def dt_int64():
+        # class 0 (fixed point) v1, little-endian, signed (bit 3); size 8; bit offset 0, precision 64
+        return bytes([0x10, 0x08, 0x00, 0x00]) + struct.pack("<I", 8) + struct.pack("<HH", 0, 64)
+
     def write_dataset(self, arr: np.ndarray):
-        arr = np.ascontiguousarray(arr, dtype="<f4")
+        arr = np.asarray(arr)
+        is_int = arr.dtype.kind in "iu"
+        arr = np.array(arr, dtype="<i8" if is_int else "<f4", order="C")      # (np.ascontiguousarray would turn a 0-d scalar into shape (1,))
         daddr = self.alloc(arr.tobytes())
         msgs = [
             self.msg(0x0001, self.ds_simple(list(arr.shape))),
-            self.msg(0x0003, self.dt_float32(), flags=1),
+            self.msg(0x0003, self.dt_int64() if is_int else self.dt_float32(), flags=1),
             self.msg(0x0008, struct.pack("<BBQQ", 3, 1, daddr, arr.nbytes)),
         ]
         return self.alloc(self.object_header(msgs))
@@ -439,3 +446,89 @@ def save_keras_weights(path, layers, extra_root_attrs=None):
     root, bt, hp = w.write_group(top, attrs)
     with open(path, "wb") as f:
         f.write(w.finish(root, bt, hp))
+
+
+# ------------------------------------------------------------------------------------------
+# Full-model files (`model.save`, reference train.py:216): /model_weights + /optimizer_weights, Keras 2.2.2 layout
+# ------------------------------------------------------------------------------------------
+def _emit_tree(w, named_arrays):
+    """named_arrays: OrderedDict "a/b/c" -> ndarray; returns the symbol-table entries of the top level."""
+    tree = OrderedDict()
+    for name, arr in named_arrays.items():
+        node = tree
+        parts = name.split("/")
+        for p in parts[:-1]:
+            node = node.setdefault(p, OrderedDict())
+        node[parts[-1]] = arr
+
+    def emit(node):
+        ents = []
+        for k, v in node.items():
+            ents.append((k, w.write_group(emit(v), [])[0]) if isinstance(v, OrderedDict) else (k, w.write_dataset(v)))
+        return ents
+    return emit(tree)
+
+
+def keras_adam_weight_names(n_trainable):
+    """Names Keras 2.2.2 gives the Adam slots: iterations, then m_k, v_k and the (1,)-shaped vhat placeholders, numbered in creation order."""
+    var = lambda k: "training/Adam/Variable:0" if k == 0 else "training/Adam/Variable_%d:0" % k
+    return ["Adam/iterations:0"] + [var(k) for k in range(3 * n_trainable)]
+
+
+def save_keras_model(path, layers, adam=None, root_attrs=None):
+    """Write `final_model.h5` with the layout of the reference's files (models/*/final_model.h5): root attrs keras_version / backend /
+    model_config / training_config; /model_weights = what save_keras_weights writes at the root; /optimizer_weights with attr
+    weight_names = [Adam/iterations:0, training/Adam/Variable:0 ...] in Keras' order (m of every trainable weight in layer/weight order,
+    then v, then one zero of shape (1,) per weight for the unused amsgrad slot), iterations as an int64 scalar.
+
+    layers: as for save_keras_weights.  adam: None or (iterations, [m arrays], [v arrays]) in trainable-weight order."""
+    w = _Writer()
+    top = []
+    for lname, weights in layers.items():
+        ents = _emit_tree(w, weights)
+        top.append((lname, w.write_group(ents, [w.attr_strings("weight_names", list(weights.keys()))] if weights else [])[0]))
+    mw = w.write_group(top, [w.attr_strings("layer_names", list(layers.keys())), w.attr_scalar_string("backend", "tensorflow"),
+                             w.attr_scalar_string("keras_version", "2.2.2")])[0]
+    root_entries = [("model_weights", mw)]
+    if adam is not None:
+        it, ms, vs = adam
+        if len(ms) != len(vs):
+            raise ValueError("adam: m and v lists differ in length")
+        names = keras_adam_weight_names(len(ms))
+        arrays = [np.asarray(int(it), np.int64)] + [np.asarray(a, np.float32) for a in ms] + [np.asarray(a, np.float32) for a in vs] + \
+                 [np.zeros((1,), np.float32) for _ in ms]
+        ents = _emit_tree(w, OrderedDict(zip(names, arrays)))
+        root_entries.append(("optimizer_weights", w.write_group(ents, [w.attr_strings("weight_names", names)])[0]))
+    attrs = [w.attr_scalar_string("keras_version", "2.2.2"), w.attr_scalar_string("backend", "tensorflow")]
+    for k, v in (root_attrs or {}).items():
+        attrs.append(w.attr_scalar_string(k, v))
+    root, bt, hp = w.write_group(root_entries, attrs)
+    with open(path, "wb") as f:
+        f.write(w.finish(root, bt, hp))
+
+
+def load_keras_adam_state(path):
+    """(iterations, OrderedDict "<layer>/<weight>" -> m, same -> v) of a Keras-2.2.2 `final_model.h5` (the reference's or ours): the k-th
+    trainable weight in layer_names / weight_names order (BatchNorm moving statistics are not trainable) owns Variable_k (m) and
+    Variable_{k+n} (v).  Shapes are checked."""
+    root = read_h5(path)
+    if "optimizer_weights" not in root.children:
+        raise ValueError("no optimizer_weights group in %s" % path)
+    ow, mw = root["optimizer_weights"], root["model_weights"]
+    trainable = []
+    for layer in mw.attrs.get("layer_names", list(mw.children)):
+        lg = mw.children[layer]
+        for wname in lg.attrs.get("weight_names", []):
+            if "moving_mean" in wname or "moving_variance" in wname:
+                continue
+            trainable.append((f"{layer}/{_short(layer, wname)}", lg[wname].shape))
+    n = len(trainable)
+    names = keras_adam_weight_names(n)
+    m, v = OrderedDict(), OrderedDict()
+    for k, (name, shape) in enumerate(trainable):
+        mk, vk = np.ascontiguousarray(ow[names[1 + k]]), np.ascontiguousarray(ow[names[1 + n + k]])
+        if mk.shape != tuple(shape) or vk.shape != tuple(shape):
+            raise ValueError("optimizer slot %d does not match %s %s" % (k, name, shape))
+        m[name], v[name] = mk, vk
+    return int(np.asarray(ow["Adam/iterations:0"]).reshape(-1)[0]), m, v
+

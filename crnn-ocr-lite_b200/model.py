@@ -200,8 +200,20 @@ class CRNNModel:
         hdf5_lite.save_keras_weights(path, self._keras_layers())
 
     def save(self, path):
-        """model.save (train.py:216): weights + optimizer moments + training_config in one file."""
+        """model.save (train.py:216): weights + optimizer moments + training_config in one file, laid out like the reference's
+        models/*/final_model.h5 (/model_weights, /optimizer_weights with Keras' Adam slot names and order; hdf5_lite.save_keras_model)."""
         extra = {"training_config": json.dumps(self._training_config()), "model_config": self.to_json()}
+        try:
+            adam = None
+            if self.optimizer is not None and self.optimizer.kind == "adam":
+                tr = [(n, s) for n, s in self.shapes.items() if not n.endswith(("moving_mean", "moving_variance"))]
+                adam = (int(self.iterations()), [self.tensor("adam_m/" + n).cpu().numpy().reshape(s) for n, s in tr],
+                        [self.tensor("adam_v/" + n).cpu().numpy().reshape(s) for n, s in tr])
+            hdf5_lite.save_keras_model(path, self._keras_layers(), adam=adam, root_attrs=extra)
+            return
+        except Exception as e:   # keep train.py's last step alive whatever happens: fall back to the flat layout below
+            import warnings
+            warnings.warn("save(): Keras-layout writer failed (%r), writing the flat layout" % (e,), RuntimeWarning)
         layers = self._keras_layers()
         if self.optimizer is not None and self.optimizer.kind == "adam":
             opt = OrderedDict()
@@ -213,6 +225,16 @@ class CRNNModel:
                 opt[f"training/Adam/v/{n}:0"] = self.tensor("adam_v/" + n).cpu().numpy().reshape(s)
             layers["optimizer_weights"] = opt
         hdf5_lite.save_keras_weights(path, layers, extra_root_attrs=extra)
+
+    def load_optimizer_state(self, path):
+        """Resume Adam from a Keras-2.2.2 `final_model.h5` (the reference's own files or ours): iterations and the m / v slots of every
+        trainable weight (hdf5_lite.load_keras_adam_state).  The reference itself only reloads weights (train.py:170-171)."""
+        it, m, v = hdf5_lite.load_keras_adam_state(path)
+        for n, a in m.items():
+            self.tensor("adam_m/" + n).copy_(torch.from_numpy(np.ascontiguousarray(a, np.float32).reshape(-1)))
+            self.tensor("adam_v/" + n).copy_(torch.from_numpy(np.ascontiguousarray(v[n], np.float32).reshape(-1)))
+        _lib.check(self.lib.crnn_set_iterations(self.handle, int(it)))
+        return it
 
     def _training_config(self):
         o = self.optimizer

@@ -310,3 +310,41 @@ def test_utils_shim_exports_reference_surface():
     W, b = U.get_initial_weights(50)
     assert W.shape == (50, 6) and not W.any() and b.tolist() == [1, 0, 0, 0, 1, 0] and W.dtype == b.dtype == np.float32
     np.testing.assert_array_equal(U.K_linspace(-1., 1., 32)[[0, 31]], np.array([-1, 1], np.float32))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/OCR_mjsynth_FULL_2/final_model.h5"), reason="the reference checkout only exists in the build container")
+def test_final_model_layout_matches_reference(cb, tmp_path):
+    """Checkpoint round trip: `model.save` writes the layout of the reference's own models/*/final_model.h5 -- /model_weights,
+    /optimizer_weights with Keras' Adam slot names in Keras' order, iterations as an int64 scalar -- and the Adam state of the reference's
+    file (61 iterations, m / v of the 66 trainable weights) can be read back for a resume."""
+    from collections import OrderedDict
+    h5 = cb.hdf5_lite
+    ref = "/root/reference/models/OCR_mjsynth_FULL_2/final_model.h5"
+    it, m, v = h5.load_keras_adam_state(ref)
+    assert it == 61 and len(m) == len(v) == 66
+    shapes = cb.model.weight_shapes(100, 32, 38, "gru")
+    trainable = [n for n in shapes if not n.endswith(("moving_mean", "moving_variance"))]
+    assert list(m) == trainable and all(m[n].shape == tuple(shapes[n]) == v[n].shape for n in trainable)     # our slot order == Keras' order
+    assert all((v[n] >= 0).all() for n in trainable) and any(np.abs(m[n]).max() > 0 for n in trainable)
+    W = h5.load_keras_weights(ref)                                           # /model_weights of the full-model file
+    layers = OrderedDict()
+    for name, arr in W.items():
+        layer, leaf = name.split("/", 1)
+        layers.setdefault(layer, OrderedDict())["%s/%s:0" % (layer, leaf)] = arr
+    out = str(tmp_path / "final_model.h5")
+    h5.save_keras_model(out, layers, adam=(it, list(m.values()), list(v.values())), root_attrs={"training_config": "{}", "model_config": "{}"})
+    r1, r2 = h5.read_h5(ref), h5.read_h5(out)
+    assert list(r2.children) == ["model_weights", "optimizer_weights"] and set(r2.attrs) == set(r1.attrs)
+    o1, o2 = r1["optimizer_weights"], r2["optimizer_weights"]
+    assert list(o2.attrs["weight_names"]) == list(o1.attrs["weight_names"])
+    assert sorted(p for p, _ in o1.walk()) == sorted(p for p, _ in o2.walk())
+    i2 = o2["Adam/iterations:0"]
+    assert i2.dtype == o1["Adam/iterations:0"].dtype == np.int64 and i2.shape == o1["Adam/iterations:0"].shape == () and int(i2) == 61
+    for pth, a in o1.walk():
+        np.testing.assert_array_equal(o2[pth], a)
+    for lname in layers:                                                      # per-layer groups: same weight_names attribute, same data
+        assert list(r2["model_weights"][lname].attrs["weight_names"]) == list(r1["model_weights"][lname].attrs["weight_names"])
+    it2, m2, v2 = h5.load_keras_adam_state(out)
+    assert it2 == it and all(np.array_equal(m[n], m2[n]) and np.array_equal(v[n], v2[n]) for n in m)
+    W2 = h5.load_keras_weights(out)
+    assert list(W2) == list(W) and all(np.array_equal(W[n], W2[n]) for n in W)
