@@ -161,8 +161,17 @@ def test_dp_world2_gloo(tmp_path):
     script = tmp_path / "dp.py"
     script.write_text(_DP_SCRIPT % {"root": ROOT})
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
+
+    def free_port():
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            return sk.getsockname()[1]
+    for attempt in range(2):                       # a fixed rendezvous port can still be in TIME_WAIT from a run seconds earlier
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                            "--master-port", str(free_port()), str(script)], capture_output=True, text=True, timeout=300, env=env)
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
 
