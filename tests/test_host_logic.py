@@ -262,6 +262,15 @@ def test_readf_generator_reproduces_reference(cb, tmp_path):
         np.testing.assert_array_equal(b["label_length"][:nv], g["ll_%d" % k][:nv])
         assert b["the_input"].dtype == np.float64 and b["the_input"].shape == (4, 100, 32, 1)
         np.testing.assert_array_equal(b["the_input"][:nv].astype(np.float32), g["x_%d" % k])
+    # --boxes path (utils.py:475-481): crops of page images, words from the box list ("-" when None)
+    pages, boxes = mk.make_pages(str(tmp_path))
+    gotb = mk.collect(cb.Readf, classes, pages, n=int(g["nb"]), bboxs=boxes)
+    for k, b in enumerate(gotb):
+        assert list(b["source_str"]) == list(g["b_str_%d" % k]), k
+        nv = len(b["source_str"])
+        np.testing.assert_array_equal(b["the_labels"][:nv], g["b_labels_%d" % k][:nv])
+        np.testing.assert_array_equal(b["label_length"][:nv], g["b_ll_%d" % k][:nv])
+        np.testing.assert_array_equal(b["the_input"][:nv].astype(np.float32), g["b_x_%d" % k])
     # device_norm=True yields the same crops as raw uint8 (normalised later on the GPU by crnn_normalize_u8)
     np.random.seed(42)
     gen = cb.Readf(img_size=(100, 32, 1), max_len=23, normed=True, batch_size=4, classes=classes, transform_p=0.7, device_norm=True).run_generator(names)
