@@ -10,7 +10,7 @@ from PIL import Image
 REF = "/root/reference/utils.py"
 mod = ast.parse(open(REF).read())
 from tqdm import tqdm
-want = {"read_img", "open_img", "norm", "get_lexicon", "parse_mjsynth", "labels_to_text", "get_lengths"}
+want = {"read_img", "open_img", "norm", "get_lexicon", "parse_mjsynth", "labels_to_text", "get_lengths", "make_ohe"}
 ns = {"np": np, "cv2": cv2, "Image": Image, "os": os, "string": string, "tqdm": tqdm}
 body = [n for n in mod.body if (isinstance(n, ast.FunctionDef) and n.name in want) or (isinstance(n, ast.ClassDef) and n.name == "DecodeCTCPred")]
 exec(compile(ast.Module(body=body, type_ignores=[]), REF, "exec"), ns)
@@ -48,5 +48,6 @@ out["l2t_text_fn"] = np.array([ns["labels_to_text"](r, inverse_classes=inv) for 
 out["l2t_text_cls"] = np.array([ns["DecodeCTCPred"](top_paths=1, beam_width=3, inverse_classes=inv).labels_to_text(r) for r in lab])
 gl = ns["get_lengths"](["/a/b/12_hello_3.png", "7_x_1.jpg", "/q/0_abcdefghij_99.png"])
 out["get_lengths_keys"] = np.array(list(gl.keys())); out["get_lengths_vals"] = np.array(list(gl.values()))
+out["ohe_in"] = np.array([3, 0, 5, 5, 1]); out["ohe_out"] = ns["make_ohe"](out["ohe_in"], 6)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_golden.npz"), **out)
 print(n, "open_img cases")

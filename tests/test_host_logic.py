@@ -237,6 +237,9 @@ def test_input_pipeline_reproduces_reference(cb):
     for row, t_fn, t_cls in zip(g["l2t_labels"], g["l2t_text_fn"], g["l2t_text_cls"]):
         assert cb.labels_to_text(row, inverse_classes=inv) == str(t_fn)
         assert cb.DecodeCTCPred(top_paths=1, beam_width=3, inverse_classes=inv).labels_to_text(row) == str(t_cls)
+    ohe = cb.make_ohe(g["ohe_in"], 6)
+    assert ohe.dtype == g["ohe_out"].dtype
+    np.testing.assert_array_equal(ohe, g["ohe_out"])
     gl = cb.get_lengths([str(k) for k in g["get_lengths_keys"]])
     assert list(gl.keys()) == [str(k) for k in g["get_lengths_keys"]] and list(gl.values()) == [int(v) for v in g["get_lengths_vals"]]
 
