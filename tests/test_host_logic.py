@@ -265,6 +265,14 @@ def test_readf_generator_reproduces_reference(cb, tmp_path):
         np.testing.assert_array_equal(b["label_length"][:nv], g["ll_%d" % k][:nv])
         assert b["the_input"].dtype == np.float64 and b["the_input"].shape == (4, 100, 32, 1)
         np.testing.assert_array_equal(b["the_input"][:nv].astype(np.float32), g["x_%d" % k])
+    # threaded loader (workers > 1): decode / resize on a pool, random placement in order on this thread -> the same batches, bit for bit
+    for workers in (2, 5):
+        par = mk.collect(cb.Readf, classes, names, n=int(g["n"]), workers=workers)
+        for k, b in enumerate(par):
+            nv = len(b["source_str"])
+            assert list(b["source_str"]) == list(g["str_%d" % k]), (workers, k)
+            np.testing.assert_array_equal(b["the_labels"][:nv], g["labels_%d" % k][:nv])
+            np.testing.assert_array_equal(b["the_input"][:nv].astype(np.float32), g["x_%d" % k])
     # --boxes path (utils.py:475-481): crops of page images, words from the box list ("-" when None)
     pages, boxes = mk.make_pages(str(tmp_path))
     gotb = mk.collect(cb.Readf, classes, pages, n=int(g["nb"]), bboxs=boxes)
@@ -369,3 +377,21 @@ def test_final_model_layout_matches_reference(cb, tmp_path):
     assert it2 == it and all(np.array_equal(m[n], m2[n]) and np.array_equal(v[n], v2[n]) for n in m)
     W2 = h5.load_keras_weights(out)
     assert list(W2) == list(W) and all(np.array_equal(W[n], W2[n]) for n in W)
+
+
+def test_parallel_loader_size_probe(cb, tmp_path):
+    """The parallel loader's parent decides the random placement from each file's header: the probe must agree with what cv2.imread decodes
+    (PNG, baseline / progressive JPEG, odd sizes)."""
+    import cv2
+    from crnn_ocr_lite_b200 import data as D
+    rng = np.random.default_rng(1)
+    for i in range(25):
+        h, w = int(rng.integers(5, 300)), int(rng.integers(5, 400))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for ext, params in ((".png", []), (".jpg", []), (".jpg", [cv2.IMWRITE_JPEG_PROGRESSIVE, 1]), (".jpeg", [cv2.IMWRITE_JPEG_QUALITY, 40])):
+            p = str(tmp_path / ("a%d%s" % (i, ext)))
+            cv2.imwrite(p, img, params)
+            dec = cv2.imread(p).shape
+            assert D._file_image_size(p) == (dec[1], dec[0]), p
+            gray = cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2GRAY)
+            assert D._shape_after_load(p, (100, 32, 1)) == D._open_load(p, (100, 32, 1))[0].shape
