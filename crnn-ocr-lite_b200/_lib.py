@@ -24,7 +24,7 @@ class TensorInfo(ctypes.Structure):
 SYMBOLS = ["crnn_last_error", "crnn_version", "crnn_workspace_bytes", "crnn_create", "crnn_destroy", "crnn_num_tensors",
            "crnn_tensor_name", "crnn_tensor_lookup", "crnn_forward", "crnn_forward_host", "crnn_train_fwd_bwd", "crnn_adam_step",
            "crnn_sgd_step", "crnn_get_iterations", "crnn_set_iterations", "crnn_ctc_status", "crnn_ctc_loss_grad", "crnn_ctc_greedy",
-           "crnn_ctc_beam", "crnn_ctc_beam_host", "crnn_ctc_greedy_host", "crnn_edit_distance", "crnn_edit_distance_host", "crnn_normalize_u8", "crnn_gemm", "crnn_debug_block_backward", "crnn_gemm_tc", "crnn_gemm_tc_dw", "crnn_gemm_tc_scratch_floats", "crnn_launch_count",
+           "crnn_ctc_beam", "crnn_ctc_beam_topk", "crnn_ctc_beam_host", "crnn_ctc_greedy_host", "crnn_edit_distance", "crnn_edit_distance_host", "crnn_normalize_u8", "crnn_gemm", "crnn_debug_block_backward", "crnn_gemm_tc", "crnn_gemm_tc_dw", "crnn_gemm_tc_scratch_floats", "crnn_launch_count",
            "crnn_profile_enable", "crnn_profile_num_stages", "crnn_profile_stage_name", "crnn_profile_report"]
 
 _lib = None
@@ -63,6 +63,7 @@ def load():
     lib.crnn_ctc_loss_grad.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp, vp, f32, vp, vp, vp, f32, vp, vp]
     lib.crnn_ctc_greedy.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]
     lib.crnn_ctc_beam.argtypes = [vp, vp, i32, i32, i32, f32, i32, i32, vp, vp, vp, vp]
+    lib.crnn_ctc_beam_topk.argtypes = [vp, vp, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp]
     lib.crnn_ctc_beam_host.argtypes = [vp, i32, i32, i32, f32, i32, i32, vp, vp, vp, vp]
     lib.crnn_ctc_greedy_host.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp]
     lib.crnn_normalize_u8.argtypes = [vp, vp, ctypes.c_longlong, f32, f32, vp]

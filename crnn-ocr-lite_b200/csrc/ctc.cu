@@ -313,7 +313,7 @@ struct TrieNode { short parent, label, first_child, next_sib; };
 #define BEAM_MAX_W 32
 
 __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __restrict__ seq_len,
-                                int B, int T, int V, float eps, int W, int merge_repeated,
+                                int B, int T, int V, float eps, int W, int merge_repeated, int P,
                                 int* __restrict__ out, int* __restrict__ out_len, float* __restrict__ logprob,
                                 int smem_per_warp_bytes)
 {
@@ -463,28 +463,34 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
         __syncwarp();
     }
 
-    // top path = best total = slot 0 (slots are sorted); before the first step it is the root
+    // top paths = slots 0..P-1 (slots are sorted by total, best first = TF BeamSearch::TopPaths); before the first step slot 0 is the root.
+    // out (B,P,T), out_len / logprob (B,P); a path beyond the number of leaves comes back empty with logprob = -inf.
     const float* fpt = bpt + cur * 32; const int* fn = bnode + cur * 32;
-    int n = 0;
-    if (lane == 0) {
-        // TF BeamEntry::LabelSeq: walk leaf -> root, drop a label equal to the previously visited one
-        int prev = -1;
-        for (int c = fn[0]; nodes[c].parent >= 0; c = nodes[c].parent) {
-            int l = nodes[c].label;
-            if (!merge_repeated || l != prev) ++n;
-            prev = l;
+    for (int pth = 0; pth < P; ++pth) {
+        int* o = out + ((size_t)b * P + pth) * T;
+        int n = 0;
+        if (lane == 0) {
+            if (pth < nb) {
+                // TF BeamEntry::LabelSeq: walk leaf -> root, drop a label equal to the previously visited one
+                int prev = -1;
+                for (int c = fn[pth]; nodes[c].parent >= 0; c = nodes[c].parent) {
+                    int l = nodes[c].label;
+                    if (!merge_repeated || l != prev) ++n;
+                    prev = l;
+                }
+                int i = n; prev = -1;
+                for (int c = fn[pth]; nodes[c].parent >= 0; c = nodes[c].parent) {
+                    int l = nodes[c].label;
+                    if (!merge_repeated || l != prev) o[--i] = l;
+                    prev = l;
+                }
+            }
+            out_len[(size_t)b * P + pth] = n;
+            if (logprob) logprob[(size_t)b * P + pth] = pth < nb ? fpt[pth] : NEG_INF;
         }
-        int i = n; prev = -1;
-        for (int c = fn[0]; nodes[c].parent >= 0; c = nodes[c].parent) {
-            int l = nodes[c].label;
-            if (!merge_repeated || l != prev) out[(size_t)b * T + (--i)] = l;
-            prev = l;
-        }
-        out_len[b] = n;
-        if (logprob) logprob[b] = fpt[0];
+        n = __shfl_sync(FULL, n, 0);
+        for (int t = n + lane; t < T; t += 32) o[t] = -1;
     }
-    n = __shfl_sync(FULL, n, 0);
-    for (int t = n + lane; t < T; t += 32) out[(size_t)b * T + t] = -1;
 }
 
 // =================================================================================================
@@ -533,9 +539,10 @@ int launch_ctc_greedy(const float* probs, const int* seq_len, int B, int T, int 
 }
 
 int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V, float eps, int W, int merge_repeated,
-                    int* out, int* out_len, float* logprob, cudaStream_t st)
+                    int* out, int* out_len, float* logprob, cudaStream_t st, int top_paths)
 {
     if (B <= 0) return CRNN_OK;
+    if (top_paths < 1 || top_paths > W) { crnn_set_error("ctc_beam: top_paths %d not in [1, beam width %d]", top_paths, W); return CRNN_ERR_INVALID; }
     if (W < 1 || W > BEAM_MAX_W) { crnn_set_error("ctc_beam: beam width %d not in [1,%d]", W, BEAM_MAX_W); return CRNN_ERR_INVALID; }
     if ((size_t)1 + (size_t)W * T > 32000) { crnn_set_error("ctc_beam: W*T too large"); return CRNN_ERR_INVALID; }
     size_t per = sizeof(float) * ((V + 3) & ~3) + sizeof(TrieNode) * (((size_t)1 + (size_t)W * T + 1) & ~1)
@@ -550,7 +557,7 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
         CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    ctc_beam_kernel<<<ceil_div(B, warps), warps * 32, smem, st>>>(probs, seq_len, B, T, V, eps, W, merge_repeated,
+    ctc_beam_kernel<<<ceil_div(B, warps), warps * 32, smem, st>>>(probs, seq_len, B, T, V, eps, W, merge_repeated, top_paths,
                                                                   out, out_len, logprob, (int)per);
     LAUNCH_CHECK();
     return CRNN_OK;

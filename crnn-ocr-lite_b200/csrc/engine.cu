@@ -858,6 +858,12 @@ int crnn_ctc_beam(const float* probs_dev, const int32_t* seq_len_dev, int B, int
     return launch_ctc_beam(probs_dev, seq_len_dev, B, T, V, eps, beam_width, merge_repeated, out_dev, out_len_dev, logprob_dev, static_cast<cudaStream_t>(stream));
 }
 
+int crnn_ctc_beam_topk(const float* probs_dev, const int32_t* seq_len_dev, int B, int T, int V, float eps, int beam_width, int merge_repeated,
+                       int top_paths, int32_t* out_dev, int32_t* out_len_dev, float* logprob_dev, void* stream) {
+    if (!probs_dev || !out_dev || !out_len_dev) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    return launch_ctc_beam(probs_dev, seq_len_dev, B, T, V, eps, beam_width, merge_repeated, out_dev, out_len_dev, logprob_dev, static_cast<cudaStream_t>(stream), top_paths);
+}
+
 // Host-buffer decode (DecodeCTCPred.decode, utils.py:347-357, takes host softmax rows): grow-only device scratch owned by the
 // library (cudaMallocAsync's default pool hands its memory back at every synchronise: 39 MB re-allocated per call cost ~10 ms),
 // and the batch is cut into chunks whose H2D copies (copy stream) overlap the decode of the previous chunk (caller's stream).

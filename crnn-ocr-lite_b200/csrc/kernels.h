@@ -43,8 +43,9 @@ int launch_ctc_loss_grad(const float* probs, int t_off, const int* labels, int m
                          float* grad_logits, float scale, int* status, cudaStream_t st);
 int launch_ctc_greedy(const float* probs, const int* seq_len, int B, int T, int V, float eps,
                       int* out, int* out_len, float* score, cudaStream_t st);
+// top_paths P: out (B,P,T), out_len / logprob (B,P), best path first
 int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V, float eps, int W, int merge_repeated,
-                    int* out, int* out_len, float* logprob, cudaStream_t st);
+                    int* out, int* out_len, float* logprob, cudaStream_t st, int top_paths = 1);
 
 // ---- conv.cu (depthwise conv, BN statistics, activation/pool, elementwise) ----
 // rev (here and below): walk the tensor from its end (serpentine traversal: a kernel starts where its producer finished, in L2)

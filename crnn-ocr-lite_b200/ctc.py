@@ -18,7 +18,7 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def ctc_batch_cost_device(probs, labels, label_len, input_len, t_off=0, want_grad_u=False, want_grad_logits=False, scale=1.0):
+def ctc_batch_cost_device(probs, labels, label_len, input_len, t_off=0, want_grad_u=False, want_grad_logits=False, scale=1.0, eps=K_EPS):
     """K.ctc_batch_cost on probs[:, t_off:, :] (utils.py:102-103).  probs (B,T,V) CUDA f32; labels (B,maxL) i32."""
     lib = _lib.load()
     B, T, V = probs.shape
@@ -31,7 +31,7 @@ def ctc_batch_cost_device(probs, labels, label_len, input_len, t_off=0, want_gra
     gz = torch.empty(B, T, V, dtype=torch.float32, device=dev) if want_grad_logits else None
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.check(lib.crnn_ctc_loss_grad(_ptr(probs), B, T, V, t_off, _ptr(labels), labels.shape[1], _ptr(label_len), _ptr(input_len),
-                                      K_EPS, _ptr(loss), _ptr(gu), _ptr(gz), float(scale), _ptr(status), _stream(dev)))
+                                      float(eps), _ptr(loss), _ptr(gu), _ptr(gz), float(scale), _ptr(status), _stream(dev)))
     st = int(status.item())
     if st != 0:
         raise ValueError(f"Not enough time for target transition sequence (batch element {-st - 1})")
@@ -40,8 +40,9 @@ def ctc_batch_cost_device(probs, labels, label_len, input_len, t_off=0, want_gra
     return loss
 
 
-def ctc_decode_device(probs, seq_len=None, greedy=True, beam_width=100, merge_repeated=True):
-    """K.ctc_decode(y_pred, input_length, greedy, beam_width, top_paths=1): returns (dense (B,T) padded -1, lengths, score)."""
+def ctc_decode_device(probs, seq_len=None, greedy=True, beam_width=100, merge_repeated=True, top_paths=1):
+    """K.ctc_decode(y_pred, input_length, greedy, beam_width, top_paths): returns (dense (B,T) padded -1, lengths (B,), score (B,)); with
+    top_paths = P > 1 (beam search only) the shapes are (B,P,T), (B,P), (B,P), best path first."""
     lib = _lib.load()
     B, T, V = probs.shape
     assert probs.is_cuda and probs.dtype == torch.float32 and probs.is_contiguous()
@@ -52,6 +53,13 @@ def ctc_decode_device(probs, seq_len=None, greedy=True, beam_width=100, merge_re
     sl = seq_len.to(torch.int32).contiguous() if seq_len is not None else None
     if greedy:
         _lib.check(lib.crnn_ctc_greedy(_ptr(probs), _ptr(sl), B, T, V, K_EPS, _ptr(out), _ptr(n), _ptr(score), _stream(dev)))
+    elif int(top_paths) > 1:
+        P = int(top_paths)
+        out = torch.empty(B, P, T, dtype=torch.int32, device=dev)
+        n = torch.empty(B, P, dtype=torch.int32, device=dev)
+        score = torch.empty(B, P, dtype=torch.float32, device=dev)
+        _lib.check(lib.crnn_ctc_beam_topk(_ptr(probs), _ptr(sl), B, T, V, K_EPS, max(int(beam_width), P), int(bool(merge_repeated)), P,
+                                          _ptr(out), _ptr(n), _ptr(score), _stream(dev)))
     else:
         _lib.check(lib.crnn_ctc_beam(_ptr(probs), _ptr(sl), B, T, V, K_EPS, int(beam_width), int(bool(merge_repeated)),
                                      _ptr(out), _ptr(n), _ptr(score), _stream(dev)))
@@ -100,8 +108,7 @@ class DecodeCTCPred:
         return labels_to_text(labels, self.inverse_classes)
 
     def decode(self, result):
-        if self.top_paths != 1:
-            raise NotImplementedError("only top_paths=1 (what predict.py:111 uses)")
+        # top_paths > 1 only widens the beam in the reference: decode() still keeps `[0][0]`, the best path (utils.py:353-356)
         if self.beam_width < self.top_paths:
             self.beam_width = self.top_paths
         result = np.asarray(result, np.float32)

@@ -370,6 +370,16 @@ class CRNNModel:
         pin = self.__dict__.get("_result_pin")
         if pin is None or pin[0].numel() < B:
             pin = self._result_pin = (torch.empty(max(B, self.max_batch), dtype=torch.float32).pin_memory(), torch.empty(1, dtype=torch.int32).pin_memory())
+        from . import parallel
+        if parallel.world_size() > 1:
+            # data parallel: every rank reports the GLOBAL mean loss, so loss-driven callbacks (EarlyStoppingIter, ModelCheckpoint) decide
+            # identically on all ranks and nobody leaves the loop while the others wait in the next gradient all-reduce
+            gl = self.__dict__.get("_global_loss")
+            if gl is None:
+                gl = self._global_loss = torch.empty(1, dtype=torch.float32, device=self.device)
+            gl.copy_(loss.mean(dtype=torch.float32).reshape(1))
+            parallel.allreduce_mean_(gl)
+            loss = gl.expand(B)
         pin[0][:B].copy_(loss, non_blocking=True)
         pin[1].copy_(self.tensor("act/status")[:1].view(torch.int32), non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -16,7 +16,8 @@ def init_distributed(backend=None, device=None):
     if world <= 1 or dist.is_initialized():
         return
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    # CRNN_DIST_BACKEND=gloo: several ranks share one GPU (NCCL refuses duplicate devices) -- used by the 2-rank test on 1-GPU boxes
+    backend = backend or os.environ.get("CRNN_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
     kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
     dist.init_process_group(backend, **kw)
 
@@ -35,6 +36,22 @@ def allreduce_sum_(flat: torch.Tensor) -> float:
     if w > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     return 1.0 / w
+
+
+def allreduce_mean_(t: torch.Tensor) -> torch.Tensor:
+    """In-place mean over ranks of a small tensor (the monitored loss: every rank must take the same early-stopping / checkpoint decisions)."""
+    w = world_size()
+    if w > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t /= w
+    return t
+
+
+def steps_per_epoch(n_items: int, batch_size: int, w=None) -> int:
+    """Number of optimiser steps per epoch, IDENTICAL on every rank: derived from the largest shard (ceil(n/world)), never from the local one --
+    ranks issuing different numbers of gradient all-reduces would hang the job (the batch generator wraps around its file list, utils.py:454-511)."""
+    w = world_size() if w is None else w
+    return -(-(-(-n_items // w)) // batch_size)
 
 
 def broadcast_(flat: torch.Tensor, src=0):

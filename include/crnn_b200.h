@@ -106,6 +106,10 @@ int crnn_ctc_greedy(const float* probs_dev, const int32_t* seq_len_dev, int B, i
 /* K.ctc_decode(greedy=False, beam_width, top_paths=1) as used by DecodeCTCPred.decode (utils.py:347-357) */
 int crnn_ctc_beam(const float* probs_dev, const int32_t* seq_len_dev, int B, int T, int V, float eps, int beam_width,
                   int merge_repeated, int32_t* out_dev, int32_t* out_len_dev, float* logprob_dev, void* stream);
+/* K.ctc_decode(greedy=False, beam_width, top_paths = P <= beam_width) (utils.py:353-354): out (B,P,T), out_len / logprob (B,P), best path
+ * first (TF BeamSearch::TopPaths order); paths beyond the number of leaves come back empty with logprob = -inf */
+int crnn_ctc_beam_topk(const float* probs_dev, const int32_t* seq_len_dev, int B, int T, int V, float eps, int beam_width,
+                       int merge_repeated, int top_paths, int32_t* out_dev, int32_t* out_len_dev, float* logprob_dev, void* stream);
 /* host-buffer variant: copies probs H2D, decodes, copies labels D2H, synchronises */
 int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, int beam_width, int merge_repeated,
                        int32_t* out_host, int32_t* out_len_host, float* logprob_host, void* stream);

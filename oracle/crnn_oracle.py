@@ -317,6 +317,12 @@ def forward(w, x, cfg: Cfg, training=False, masks=None, new_stats=None):
     h = F.pad(s, (0, 0, 2, 2, 2, 2))              # ZeroPadding2D((2,2)), utils.py:63
     for i, (_, _, pool) in enumerate(BLOCK_PLAN, 1):
         h = conv_block(w, i, h, pool, training, masks, new_stats, keep)
+    return head(w, h, cfg, training, masks, keep)
+
+
+def head(w, h, cfg: Cfg, training=False, masks=None, keep=None):
+    """Everything after the conv stack (utils.py:72-86): block-7 output (B,T,9,512) -> reshape -> dense1 -> 2 x Bi-RNN -> dense2 -> softmax."""
+    keep = OrderedDict() if keep is None else keep
     B, T = h.shape[0], h.shape[1]
     h = h.reshape(B, T, -1)                        # feature index = w*512 + c, utils.py:72-73
     h = torch.relu(h @ w["dense1/kernel"] + w["dense1/bias"])

@@ -186,11 +186,13 @@ static int leaves_bottom(const Tree* tr, const int* leaves, int n) {
     return bi;
 }
 
-/*   probs (B,T,V) -> out (B,T) int32 padded -1 (top-1 path, merge_repeated as given), out_len (B),
- *   log_prob (B) = best new.total (TF 1.8: max-subtracted, un-normalised).                         */
-void ctc_oracle_beam(const float* probs, int B, int T, int V, const int* seq_len, float eps,
-                     int beam_width, int merge_repeated, int* out, int* out_len, float* log_prob)
+/*   probs (B,T,V) -> out (B,P,T) int32 padded -1 (the P = top_paths best paths, best first; merge_repeated as given), out_len (B,P),
+ *   log_prob (B,P) = new.total of each path (TF 1.8: max-subtracted, un-normalised).  TF BeamSearch::TopPaths: leaves sorted by
+ *   total, descending.  Paths beyond the number of leaves come back empty with log_prob = -inf (TF raises an error there).       */
+void ctc_oracle_beam_topk(const float* probs, int B, int T, int V, const int* seq_len, float eps,
+                          int beam_width, int merge_repeated, int top_paths, int* out, int* out_len, float* log_prob)
 {
+    const int P = top_paths;
     const int blank = V - 1, W = beam_width;
     float* in = (float*)malloc(sizeof(float) * V);
     int* leaves = (int*)malloc(sizeof(int) * (W + 1));
@@ -274,21 +276,35 @@ void ctc_oracle_beam(const float* probs, int B, int T, int V, const int* seq_len
                 }
             }
         }
-        /* top path */
-        int best = 0;
-        for (int i = 1; i < nleaves; ++i) if (tr.e[leaves[i]].nt > tr.e[leaves[best]].nt) best = i;
-        int n = 0, prev = -1;
-        for (int t = 0; t < T; ++t) out[b * T + t] = -1;
-        /* walk leaf -> root collecting labels, dropping a label equal to the previously visited one */
-        int* tmp = (int*)malloc(sizeof(int) * (T + 1));
-        for (int c = leaves[best]; tr.e[c].parent >= 0; c = tr.e[c].parent) {
-            if (!merge_repeated || tr.e[c].label != prev) tmp[n++] = tr.e[c].label;
-            prev = tr.e[c].label;
+        /* top paths: leaves sorted by total, best first (stable insertion sort) */
+        for (int i = 1; i < nleaves; ++i) {
+            int x = leaves[i], j = i - 1;
+            while (j >= 0 && tr.e[leaves[j]].nt < tr.e[x].nt) { leaves[j + 1] = leaves[j]; --j; }
+            leaves[j + 1] = x;
         }
-        for (int i = 0; i < n; ++i) out[b * T + i] = tmp[n - 1 - i];
+        int* tmp = (int*)malloc(sizeof(int) * (T + 1));
+        for (int pth = 0; pth < P; ++pth) {
+            int* o = out + ((size_t)b * P + pth) * T;
+            for (int t = 0; t < T; ++t) o[t] = -1;
+            if (pth >= nleaves) { out_len[b * P + pth] = 0; if (log_prob) log_prob[b * P + pth] = LOGZERO; continue; }
+            int n = 0, prev = -1;
+            /* walk leaf -> root collecting labels, dropping a label equal to the previously visited one */
+            for (int c = leaves[pth]; tr.e[c].parent >= 0; c = tr.e[c].parent) {
+                if (!merge_repeated || tr.e[c].label != prev) tmp[n++] = tr.e[c].label;
+                prev = tr.e[c].label;
+            }
+            for (int i = 0; i < n; ++i) o[i] = tmp[n - 1 - i];
+            out_len[b * P + pth] = n;
+            if (log_prob) log_prob[b * P + pth] = tr.e[leaves[pth]].nt;
+        }
         free(tmp);
-        out_len[b] = n;
-        if (log_prob) log_prob[b] = tr.e[leaves[best]].nt;
     }
     free(in); free(leaves); free(branches); free(tr.e); free(tr.kids);
+}
+
+/* top_paths = 1 (what DecodeCTCPred.decode uses, utils.py:353-356) */
+void ctc_oracle_beam(const float* probs, int B, int T, int V, const int* seq_len, float eps,
+                     int beam_width, int merge_repeated, int* out, int* out_len, float* log_prob)
+{
+    ctc_oracle_beam_topk(probs, B, T, V, seq_len, eps, beam_width, merge_repeated, 1, out, out_len, log_prob);
 }

@@ -68,6 +68,20 @@ def beam(probs, seq_len=None, beam_width=10, merge_repeated=True, eps=1e-7):
     return out, out_len, lp
 
 
+def beam_topk(probs, top_paths, seq_len=None, beam_width=10, merge_repeated=True, eps=1e-7):
+    """K.ctc_decode(greedy=False, beam_width, top_paths): out (B,P,T), out_len (B,P), log_prob (B,P), best path first."""
+    probs = np.ascontiguousarray(probs, np.float32)
+    B, T, V = probs.shape
+    P = int(top_paths)
+    seq_len = np.full(B, T, np.int32) if seq_len is None else np.ascontiguousarray(seq_len, np.int32)
+    out = np.empty((B, P, T), np.int32)
+    out_len = np.empty((B, P), np.int32)
+    lp = np.empty((B, P), np.float32)
+    lib().ctc_oracle_beam_topk(_p(probs), B, T, V, _p(seq_len), ctypes.c_float(eps), int(beam_width), int(bool(merge_repeated)), P,
+                               _p(out), _p(out_len), _p(lp))
+    return out, out_len, lp
+
+
 def beam_threaded(probs, n_threads, **kw):
     """Batch-parallel driver (ctypes releases the GIL): the oracle run on `n_threads` host threads."""
     from concurrent.futures import ThreadPoolExecutor

@@ -63,6 +63,58 @@ def test_ctc_loss_grad(cb, T, V, maxL, t_off):
     assert np.all(gz.cpu().numpy()[:, :t_off] == 0)
 
 
+def test_tf_upstream_vectors_cuda(cb):
+    """The CUDA CTC kernels against TensorFlow's own unit-test known answers (tests/golden/tf_upstream_ctc.json, recalled constants that the
+    C oracle reproduces digit for digit): ctc_loss_op_test testBasic (losses + gradient matrices), ctc_decoder_ops_test greedy and
+    beam-search (beam_width 2, top_paths 2, merge_repeated False: both paths exact, both scores)."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tf_upstream_ctc.json")))
+    d = "cuda"
+    cl = g["ctc_loss"]
+    probs = np.asarray(cl["input_prob_matrix"], np.float32)
+    maxL = max(len(t) for t in cl["targets"])
+    labels = np.full((2, maxL), cl["depth"] - 1, np.int32)
+    for b, t in enumerate(cl["targets"]):
+        labels[b, :len(t)] = t
+    lens = np.array([len(t) for t in cl["targets"]], np.int32)
+    il = np.full(2, cl["seq_len"], np.int32)
+    for eps, tl, tg in ((0.0, 1.5e-5, 2e-6), (1e-7, 3e-5, 5e-6)):      # TF op itself / the Keras call path (epsilon before the log)
+        loss, gu, _ = cb.ctc_batch_cost_device(torch.tensor(probs, device=d), torch.tensor(labels, device=d), torch.tensor(lens, device=d),
+                                               torch.tensor(il, device=d), want_grad_u=True, eps=eps)
+        np.testing.assert_allclose(loss.cpu().numpy(), cl["loss"], rtol=0, atol=tl)
+        np.testing.assert_allclose(gu.cpu().numpy(), np.asarray(cl["gradient"], np.float32), rtol=0, atol=tg)
+    gr = g["greedy"]
+    gp = torch.tensor(np.asarray(gr["input_prob_matrix"], np.float32), device=d)
+    out, n, sc = cb.ctc_decode_device(gp, seq_len=torch.tensor(gr["seq_len"], device=d), greedy=True)
+    out, n = out.cpu().numpy(), n.cpu().numpy()
+    for b, want in enumerate(gr["decoded"]):
+        assert out[b, :n[b]].tolist() == want and np.all(out[b, n[b]:] == -1)
+    np.testing.assert_allclose(sc.cpu().numpy(), [np.sum(-np.log(f)) for f in gr["neg_log_prob_factors"]], rtol=1e-5)
+    bm = g["beam"]
+    bp = torch.tensor(np.asarray(bm["input_prob_matrix"], np.float32)[None], device=d)
+    out, n, lp = cb.ctc_decode_device(bp, seq_len=torch.tensor([bm["seq_len"]], device=d), greedy=False, beam_width=bm["beam_width"],
+                                      merge_repeated=bm["merge_repeated"], top_paths=bm["top_paths"])
+    out, n = out.cpu().numpy(), n.cpu().numpy()
+    for pth, want in enumerate(bm["decoded"]):
+        assert out[0, pth, :n[0, pth]].tolist() == want and np.all(out[0, pth, n[0, pth]:] == -1)
+    np.testing.assert_allclose(lp.cpu().numpy()[0], bm["log_prob"], rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("B,T,V,W,P", [(16, 25, 96, 10, 10), (8, 52, 38, 10, 3), (4, 5, 4, 4, 4)])
+def test_beam_top_paths_exact(cb, B, T, V, W, P):
+    """K.ctc_decode(top_paths = P > 1) (utils.py:353-354): all P paths, lengths and scores against the C restatement; path 0 equals the
+    top-1 entry point.  (4, 5, 4, 4, 4): fewer leaves than requested paths early on must not crash."""
+    rng = np.random.default_rng(B * 31 + T)
+    probs = _rand_probs(rng, B, T, V, 3.0)
+    want, wn, wl = O.beam_topk(probs, P, beam_width=W)
+    out, n, lp = cb.ctc_decode_device(torch.tensor(probs, device="cuda"), greedy=False, beam_width=W, top_paths=P)
+    np.testing.assert_array_equal(n.cpu().numpy(), wn)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    np.testing.assert_allclose(lp.cpu().numpy(), wl, rtol=1e-5, atol=1e-5)
+    o1, n1, _ = cb.ctc_decode_device(torch.tensor(probs, device="cuda"), greedy=False, beam_width=W)
+    np.testing.assert_array_equal(o1.cpu().numpy(), want[:, 0])
+
+
 def test_ctc_loss_infeasible(cb):
     probs = torch.tensor(_rand_probs(np.random.default_rng(0), 2, 4, 5), device="cuda")
     lab = torch.tensor([[1, 2, 4], [1, 1, 2]], dtype=torch.int32, device="cuda")
@@ -285,15 +337,14 @@ def test_sampler_bitexact_given_theta(cb):
             assert np.all(a0[:, -1] == 0) and np.abs(a0[:, :, -1]).max() < 1e-6 and np.all(a0[:, 0, 0] == x[:, 0, 0, 0])
 
 
-@pytest.mark.parametrize("imgh,cell", [(100, "gru"), (128, "lstm")])
-def test_train_step_parity(cb, imgh, cell):
+@pytest.mark.parametrize("imgh,cell,B", [(100, "gru", 6), (128, "lstm", 6), (100, "lstm", 6), (128, "gru", 6), (128, "gru", 64)])
+def test_train_step_parity(cb, imgh, cell, B):
     """Full training forward/backward (BN batch statistics, CTC, BPTT, STN) + Adam vs torch autograd on the oracle.
     Dropout disabled on both sides (RNG streams cannot match TF).
     Reference = the oracle run in float64; the fp32 oracle (what Keras/TF computes in) gives the yardstick: the CUDA
     gradient of every tensor must be within max(3e-3, 4 x fp32-oracle error) of the fp64 truth, relative to the
     tensor's max-abs entry (these sums cancel heavily: 1e5..4e5 terms of random sign)."""
     cfg = N.Cfg(imgh=imgh, cell=cell)
-    B = 6
     w, m = _make(cb, cfg, B, 3)
     x, lab, L, il = N.synth_batch(cfg, B, 33)
     loss_o, per_o, g32, stats_o, keep = N.loss_and_grads(w, x, lab, L, il, cfg)
@@ -310,16 +361,20 @@ def test_train_step_parity(cb, imgh, cell):
         rows.append((e_gpu, e_ref, scale, k))
         if e_ref > 1e-4:
             ratios.append(e_gpu / e_ref)
-        if e_gpu > max(3e-3, 10 * e_ref):
+        if e_gpu > max(3e-3, 4 * e_ref):
             bad.append(k)
     report = "\n".join("%-55s gpu %.2e  fp32-oracle %.2e  max|g| %.3e" % (k, a, r, sc) for a, r, sc, k in sorted(rows, reverse=True))
     import os
     os.makedirs("gpurun_out", exist_ok=True)
-    open("gpurun_out/grad_parity_%d_%s.txt" % (imgh, cell), "w").write(report + "\nmedian gpu/fp32-oracle error ratio: %.2f\n" % np.median(ratios))
-    # end-to-end gradients of this net are chaotic (a 1e-7 input perturbation moves them by 1-4 %): the CUDA path
-    # must be as close to the fp64 truth as the fp32 CPU oracle is -- per tensor within 10x, in the median within 2.5x
+    open("gpurun_out/grad_parity_%d_%s_B%d.txt" % (imgh, cell, B), "w").write(report + "\nmedian gpu/fp32-oracle error ratio: %.2f\n" % np.median(ratios))
+    # End-to-end gradients of this net are ill-conditioned through its DISCRETE decisions, not through arithmetic: the fp32 and fp64 forward
+    # passes agree to ~2e-5, but ReLU6 gates / max-pool winners within that distance of a threshold flip, and one flipped gate moves an entry
+    # of a weight gradient (a sum over only B*H*W = 4e3..3e5 positions of random sign) by ~1/sqrt(positions) of its size -- the fp32 CPU oracle
+    # itself is 0.5-5 % from the fp64 truth.  So this test checks the WIRING end to end with the fp32 oracle as yardstick (per tensor within
+    # 4x, median within 2x); the arithmetic of every backward kernel is checked to 3e-3 with the decisions teacher-forced in
+    # test_block_backward_isolated / test_stn_backward_isolated / test_head_backward_isolated, at this test's shapes.
     assert not bad, "gradients out of tolerance: %s\n%s" % (bad, report[:3000])
-    assert np.median(ratios) < 2.5, np.median(ratios)
+    assert np.median(ratios) < 2.0, np.median(ratios)
     for a, r, sc, k in rows:   # the recurrent head is well conditioned: tight bound
         if k.startswith(("dense2", "bidirectional")):
             assert a < 2e-3, (k, a)
@@ -344,14 +399,16 @@ def _trained_forward(cb, cfg, B, seed):
     return w, m, x
 
 
+@pytest.mark.parametrize("imgh,B", [(100, 4), (128, 64)])
 @pytest.mark.parametrize("block", [1, 2, 3, 4, 5, 6, 7])
-def test_block_backward_isolated(cb, block):
+def test_block_backward_isolated(cb, block, imgh, B):
     """Teacher-forced backward of ONE depthwise-separable block (act/pool/BN backward, pointwise dW / dX GEMMs, ReLU6+BN backward,
     depthwise dW / dX): the oracle re-runs that single block in fp64 on the CUDA path's own block input, so the end-to-end chaos
     (test_train_step_parity) cannot hide a kernel bug.  Tolerance 3e-3 of each tensor's max-abs entry, with the upstream gradient
-    zeroed at the (few) elements whose ReLU6 / max-pool decision is numerically ambiguous."""
-    cfg = N.Cfg(imgh=100, cell="gru")
-    B = 4
+    zeroed at the (few) elements whose ReLU6 / max-pool decision is numerically ambiguous.  (128, 64) is the bench configuration: the
+    strip scheduling of the row-marching depthwise kernels, the RED-fused backward-data instances, the dX-epilogue reduction and the
+    split-K choices of the dW GEMMs only take their bench shapes there."""
+    cfg = N.Cfg(imgh=imgh, cell="gru")
     w, m, x = _trained_forward(cb, cfg, B, 7)
     lib = cb._lib.load()
     hh, ww = cfg.imgh + 4, cfg.imgw + 4
@@ -405,10 +462,10 @@ def test_block_backward_isolated(cb, block):
     assert err < 3e-3, f"block {block} d(input): {err:.2e}"
 
 
-def test_stn_backward_isolated(cb):
+@pytest.mark.parametrize("imgh,B", [(100, 4), (128, 64)])
+def test_stn_backward_isolated(cb, imgh, B):
     """Sampler backward (d theta) + localisation-net backward, teacher-forced with the CUDA path's own d(STN output)."""
-    cfg = N.Cfg(imgh=100, cell="gru")
-    B = 4
+    cfg = N.Cfg(imgh=imgh, cell="gru")
     w, m, x = _trained_forward(cb, cfg, B, 9)
     Hp, Wp = cfg.imgh + 4, cfg.imgw + 4
     da0 = m.activation("gB")[:B * Hp * Wp].reshape(B, Hp, Wp, 1).copy()     # gradient buffer after the 7th (odd) ping-pong swap
@@ -422,6 +479,33 @@ def test_stn_backward_isolated(cb):
         sc = max(np.abs(want).max(), 1e-9)
         err = np.abs(g[k] - want).max() / sc
         assert err < 2e-3, f"{k}: {err:.2e} (max |g| {sc:.3e})"
+
+
+@pytest.mark.parametrize("imgh,cell,B", [(100, "lstm", 4), (128, "gru", 64)])
+def test_head_backward_isolated(cb, imgh, cell, B):
+    """Teacher-forced backward of everything after the conv stack (dense1 -> 2 x Bi-RNN -> dense2 -> softmax -> ctc_batch_cost): the fp64
+    oracle re-runs the head on the CUDA path's own block-7 output, so the weight gradients of dense1 / both recurrent layers / dense2 of a
+    full training step are checked without the conv stack's discrete decisions in the way.  3e-3 of each tensor's max-abs entry."""
+    cfg = N.Cfg(imgh=imgh, cell=cell)
+    w, m = _make(cb, cfg, B, 6)
+    x, lab, L, il = N.synth_batch(cfg, B, 66)
+    d = "cuda"
+    per = m.train_fwd_bwd_device(torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d), dropout_seed=0).cpu().numpy().copy()
+    g = m.get_grads()
+    T = cfg.T
+    feat = m.activation("block7")[:B * T * 9 * 512].reshape(B, T, 9, 512).copy()
+    wt = N.to_torch(w, torch.float64, grad=True)
+    keep = N.head(wt, torch.tensor(feat, dtype=torch.float64), cfg, training=True)
+    per64 = N.ctc_batch_cost(keep["softmax"], lab, L, il, exact64=True)
+    per64.mean().backward()
+    np.testing.assert_allclose(per, per64.detach().numpy(), rtol=1e-4, atol=1e-3)
+    names = [k for k in g if k.startswith(("dense1/", "bidirectional_", "dense2/"))]
+    assert len(names) == 2 + 12 + 2
+    for k in names:
+        want = wt[k].grad.numpy()
+        sc = max(np.abs(want).max(), 1e-9)
+        err = np.abs(g[k] - want).max() / sc
+        assert err < 3e-3, f"{k}: {err:.2e} (max |g| {sc:.3e})"
 
 
 def test_dropout_statistics(cb):
@@ -552,8 +636,6 @@ def test_cli_end_to_end():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("CRNN_RUN_UNVALIDATED") != "1",
-                    reason="written after round 1's GPU minutes were spent: run once with CRNN_RUN_UNVALIDATED=1 on a B200, then drop this gate")
 def test_sgd_nesterov_step_parity(cb):
     """Reference default optimiser (train.py:190: SGD(lr, decay=1e-6, momentum=.9, nesterov=True, clipnorm=5), Keras 2.2.2): two successive
     steps on the CUDA gradients against the oracle's sgd_step (velocity carried over, lr decay by the iteration counter, global-norm clip)."""
@@ -578,8 +660,6 @@ def test_sgd_nesterov_step_parity(cb):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("CRNN_RUN_UNVALIDATED") != "1",
-                    reason="written after round 1's GPU minutes were spent: run once with CRNN_RUN_UNVALIDATED=1 on a B200, then drop this gate")
 def test_full_model_checkpoint_roundtrip_on_device(cb, tmp_path):
     """model.save (train.py:216) after two Adam steps writes the Keras full-model layout; the Adam moments and the iteration counter read
     back from the file equal the device state, and load_optimizer_state() restores them into a fresh model."""

@@ -121,6 +121,16 @@ def test_shard_batch(cb):
         assert cover == list(range(n))
 
 
+def test_steps_per_epoch_identical_on_all_ranks(cb):
+    """ADVICE r1 (train.py:83): 129 files, world 2, batch 64 gave local step counts 2 and 1 -> the ranks' all-reduces went out of step."""
+    par = cb.parallel
+    for n, w, bs in ((129, 2, 64), (17, 2, 8), (1000, 8, 64), (5, 8, 64), (512, 4, 64)):
+        local = [-(-(par.shard_batch(n, r, w)[1] - par.shard_batch(n, r, w)[0]) // bs) for r in range(w)]
+        steps = par.steps_per_epoch(n, bs, w)
+        assert steps == max(local) and steps >= 1, (n, w, bs, local, steps)
+    assert par.steps_per_epoch(129, 64, 1) == 3
+
+
 _DP_SCRIPT = r'''
 import os, sys, numpy as np, torch
 sys.path.insert(0, %(root)r)
@@ -152,7 +162,10 @@ assert abs(norm - norm_ref) < 1e-3 and norm > 5.0
 for k in ref: np.testing.assert_allclose(neww[k], ref[k], rtol=1e-5, atol=1e-9)
 lo, hi = par.shard_batch(64)
 assert (lo, hi) == (32 * r, 32 * r + 32)
-print("rank", r, "ok")
+# the monitored loss every rank reports is the mean over ranks (same early-stopping decision everywhere)
+lm = par.allreduce_mean_(torch.tensor([1.0 + 2.0 * r]))
+assert abs(float(lm) - 2.0) < 1e-6
+sys.stdout.write("rank %%d ok\n" %% r); sys.stdout.flush()
 '''
 
 

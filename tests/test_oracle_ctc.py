@@ -147,3 +147,49 @@ def test_threaded_driver_matches():
     b = O.beam_threaded(probs, 4)
     for x, y in zip(a, b):
         np.testing.assert_array_equal(x, y)
+
+
+def _tf_upstream():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tf_upstream_ctc.json")))
+
+
+def test_oracle_reproduces_tf_upstream_ctc_loss_vectors():
+    """TensorFlow's own ctc_loss_op_test.py::testBasic known answers (recalled constants, tests/golden/make_tf_upstream_golden.py): the C
+    restatement of TF CTCLoss gives both losses and all 60 gradient entries to the 6 printed digits -- this pins the TRAINING half of the
+    oracle (loss + gradient wrt the logits) on upstream-published vectors."""
+    g = _tf_upstream()["ctc_loss"]
+    probs = np.asarray(g["input_prob_matrix"], np.float32)
+    maxL = max(len(t) for t in g["targets"])
+    labels = np.full((2, maxL), g["depth"] - 1, np.int32)
+    for b, t in enumerate(g["targets"]):
+        labels[b, :len(t)] = t
+    lens = [len(t) for t in g["targets"]]
+    loss, grad = O.ctc_loss_grad(probs, labels, lens, [g["seq_len"]] * 2, eps=0.0)     # TF feeds log(p) as logits: softmax(log p) = p
+    np.testing.assert_allclose(loss, g["loss"], rtol=0, atol=1.5e-5)
+    np.testing.assert_allclose(grad, np.asarray(g["gradient"], np.float32), rtol=0, atol=1.5e-6)
+    # the Keras path adds epsilon()=1e-7 before the log (utils.py:103 -> K.ctc_batch_cost): a 1e-6-level perturbation of the same numbers
+    loss_k, grad_k = O.ctc_loss_grad(probs, labels, lens, [g["seq_len"]] * 2, eps=1e-7)
+    np.testing.assert_allclose(loss_k, g["loss"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(grad_k, np.asarray(g["gradient"], np.float32), rtol=0, atol=5e-6)
+
+
+def test_oracle_reproduces_tf_upstream_decoder_vectors():
+    """TF ctc_decoder_ops_test.py::testCTCGreedyDecoder / testCTCDecoderBeamSearch known answers (recalled constants): decoded paths exact,
+    scores to the printed digits; the beam test needs top_paths = 2 (both paths and both scores)."""
+    g = _tf_upstream()
+    gr = g["greedy"]
+    out, n, sc = O.greedy(np.asarray(gr["input_prob_matrix"], np.float32), seq_len=gr["seq_len"], eps=1e-30)
+    for b, want in enumerate(gr["decoded"]):
+        assert out[b, :n[b]].tolist() == want and np.all(out[b, n[b]:] == -1)
+    np.testing.assert_allclose(sc, [np.sum(-np.log(f)) for f in gr["neg_log_prob_factors"]], rtol=1e-6)
+    bm = g["beam"]
+    probs = np.asarray(bm["input_prob_matrix"], np.float32)[None]
+    out, n, lp = O.beam_topk(probs, bm["top_paths"], seq_len=[bm["seq_len"]], beam_width=bm["beam_width"], merge_repeated=bm["merge_repeated"], eps=0.0)
+    for pth, want in enumerate(bm["decoded"]):
+        assert out[0, pth, :n[0, pth]].tolist() == want
+    np.testing.assert_allclose(lp[0], bm["log_prob"], rtol=0, atol=1.5e-6)
+    # top-1 entry point agrees with path 0 of the top-k one
+    o1, n1, l1 = O.beam(probs, seq_len=[bm["seq_len"]], beam_width=bm["beam_width"], merge_repeated=bm["merge_repeated"], eps=0.0)
+    assert o1[0, :n1[0]].tolist() == bm["decoded"][0] and abs(l1[0] - lp[0, 0]) == 0

@@ -54,7 +54,7 @@ def main():
     import torch
     import utils as U
     import crnn_b200 as cb
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())   # several ranks may share a GPU (gloo test mode)
     torch.cuda.set_device(local)
     cb.parallel.init_distributed(device=torch.device("cuda", local))
     rank, world = cb.parallel.rank(), cb.parallel.world_size()
@@ -80,6 +80,7 @@ def main():
         cut = int(len(train) * args.train_portion)
         train, val = train[:cut], train[cut:]
     max_len = max(U.get_lengths(train).values())
+    n_train_global = len(train)
     if world > 1:                                   # text lines are independent: shard the file list, no data-path collective
         lo, hi = cb.parallel.shard_batch(len(train))
         train = train[lo:hi]
@@ -96,7 +97,8 @@ def main():
         model.load_weights(args.pretrained_path)
     cb.parallel.broadcast_(model.tensor("arena/params"))
 
-    train_steps = -(-len(train) // args.batch_size)
+    # identical on every rank (from the largest shard); the generator wraps around its list, so a shorter shard just re-uses its first files
+    train_steps = cb.parallel.steps_per_epoch(n_train_global, args.batch_size, world)
     test_steps = -(-len(val) // args.batch_size)
     start_time = time.time()
     if rank == 0:
@@ -117,6 +119,8 @@ def main():
     H = model.fit_generator(generator=reader.run_generator(train, downsample_factor=ds), steps_per_epoch=train_steps, epochs=args.nbepochs,
                             validation_data=reader.run_generator(val, downsample_factor=ds) if test_steps else None, validation_steps=test_steps,
                             shuffle=False, verbose=1 if rank == 0 else 0, callbacks=callbacks)
+    if os.environ.get("CRNN_DP_DUMP_PARAMS"):          # test hook: every rank dumps its final parameters (replicas must be identical)
+        np.save("%s.rank%d.npy" % (os.environ["CRNN_DP_DUMP_PARAMS"], rank), model.tensor("arena/params").cpu().numpy())
     if rank == 0:
         pickle.dump(H.history, open(os.path.join(out_dir, "loss_history.pickle.dat"), "wb"))
         print(" [INFO] Training finished in %i sec.!" % (round(time.time() - start_time, 2)))
