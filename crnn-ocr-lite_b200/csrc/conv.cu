@@ -808,15 +808,6 @@ __global__ void softmax_rows_kernel(const float* __restrict__ z, float* __restri
     s = warp_sum(s);
     for (int k = lane; k < V; k += 32) pr[k] = expf(zr[k] - mx) / s;
 }
-__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C)
-{
-    __shared__ float tile[32][33];
-    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) { int r = r0 + i; if (r < R && c < C) tile[i][threadIdx.x] = in[(size_t)r * C + c]; }
-    __syncthreads();
-    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) { int cc = c0 + i; if (r < R && cc < C) out[(size_t)cc * R + r] = tile[threadIdx.x][i]; }
-}
 
 inline bool too_big(long long n) { if (n >= (1ll << 31)) { crnn_set_error("tensor too large for 32-bit indexing (%lld elements)", n); return true; } return false; }
 inline int grid1d(long long total, int threads, int max_blocks = 148 * 16) {
@@ -1037,7 +1028,4 @@ int launch_dup_dirs(const float* g, float* out, long long rows, int U, cudaStrea
 }
 int launch_softmax_rows(const float* z, float* p, long long rows, int V, cudaStream_t st) {
     softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, p, rows, V); LAUNCH_CHECK(); return CRNN_OK;
-}
-int launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st) {
-    transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32)), dim3(32, 8), 0, st>>>(in, out, R, C); LAUNCH_CHECK(); return CRNN_OK;
 }

@@ -81,11 +81,9 @@ struct crnn_handle {
     std::vector<std::pair<std::string, int64_t>> stats;     // BN moving statistics
     Prof prof;
     bool gemm_simt = false;   // CRNN_GEMM_SIMT=1: fp32 SIMT GEMM for the pointwise convs instead of the tcgen05 3xTF32 kernel
-    bool rnn_v1 = false;   // CRNN_RNN_V1=1: use the L2-streaming recurrent kernels (rnn.cu) instead of the cluster kernels
     int bn2_red_done[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [block]: reduction pass of the block's BN2 backward already accumulated by the producer of its dy
     bool defer_bn_grads = false;   // full backward: dgamma/dbeta of all 14 BN layers in one launch at the end instead of 14 tiny ones
     bool fuse_bn_red = true;   // CRNN_FUSE_BN_RED=0: separate reduction pass for the ReLU6+BN backward after the depthwise conv
-    bool rnn_simt_cluster = false;   // CRNN_RNN_SIMT_CLUSTER=1: cluster kernels with U in shared memory + FFMA (rnn_cluster.cu) instead of rnn_mma.cu
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
     // stream = a parallel branch of the graph.  CRNN_GRAPH=0 / CRNN_OVERLAP=0 switch either off; profiling runs eager + serial.
@@ -266,7 +264,6 @@ void plan(crnn_handle* h) {
         snprintf(nm2, sizeof(nm2), "hprev%d", layer); A(nm2, M * 2 * h->U);
         snprintf(nm2, sizeof(nm2), "rh%d", layer); A(nm2, M * 2 * h->U);
     }
-    A("UT", (int64_t)2 * h->G * h->U * h->U);
     A("dtheta", B * 6); A("dd1", B * 50); A("dflat", B * h->sd.F); A("ddense1", M * h->TD);
     // pre-swizzled hi/lo weight images of the tcgen05 kernels (gemm_tc.cu), one per GEMM: prepared once per step on the side branch
     A("wimg_d1f", (int64_t)tc_weight_image_floats(h->TD, h->FEAT)); A("wimg_d1b", (int64_t)tc_weight_image_floats(h->FEAT, h->TD));
@@ -455,10 +452,8 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
             const float* U0 = h->w(h->rnn(layer, 0) + "/recurrent_kernel"); const float* U1 = h->w(h->rnn(layer, 1) + "/recurrent_kernel");
             float* gsave = training ? h->a(nm("gates%d", layer)) : nullptr;
             const double work = 4.0 * B * T * 2 * (G * U + U + (training ? h->GS * U : 0));
-            if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1 && h->rnn_simt_cluster) ST(ST_RNN_FWD, work, launch_gru_fwd_cluster(xp, U0, U1, hs, gsave, B, T, st));
-            else if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) ST(ST_RNN_FWD, work, launch_gru_fwd_mma(xp, U0, U1, hs, gsave, B, T, st));
-            else if (h->cfg.cell == CRNN_CELL_LSTM && !h->rnn_v1 && U == 256) ST(ST_RNN_FWD, work, launch_lstm_fwd_mma(xp, U0, U1, hs, gsave, B, T, st));
-            else ST(ST_RNN_FWD, work, launch_rnn_fwd(h->cfg.cell, xp, U0, U1, hs, gsave, B, T, U, st));
+            if (h->cfg.cell == CRNN_CELL_GRU) ST(ST_RNN_FWD, work, launch_gru_fwd_mma(xp, U0, U1, hs, gsave, B, T, st));
+            else ST(ST_RNN_FWD, work, launch_lstm_fwd_mma(xp, U0, U1, hs, gsave, B, T, st));
         }
         if (layer == 1) { ST(ST_MISC, 0, launch_sum_dirs(hs, h->a("rnn1"), M, U, st)); rin = h->a("rnn1"); kin = U; }   // merge_mode='sum'
     }
@@ -477,21 +472,14 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
 // gradients per direction + the bias column sums.
 int rnn_backward(crnn_handle* h, int layer, const float* dout /*(M,2,U)*/, const float* rin, int kin, float* dx /*(M,kin)*/, int B, cudaStream_t st) {
     const int U = h->U, G = h->G, T = h->T, M = B * T;
-    float* UT = h->a("UT"); float* dxp = h->a(nm("dxp%d", layer)); float* hprev = h->a(nm("hprev%d", layer)); float* rh = h->a(nm("rh%d", layer));
+    float* dxp = h->a(nm("dxp%d", layer)); float* hprev = h->a(nm("hprev%d", layer)); float* rh = h->a(nm("rh%d", layer));
     const double bwork = 4.0 * B * T * 2 * (2 * U + h->GS * U + G * U + 2 * U);
-    if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1 && !h->rnn_simt_cluster) {
+    if (h->cfg.cell == CRNN_CELL_GRU) {
         ST(ST_RNN_BWD, bwork, launch_gru_bwd_mma(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
                                                  h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, rh, B, T, st));
-    } else if (h->cfg.cell == CRNN_CELL_LSTM && !h->rnn_v1 && U == 256) {
+    } else {
         ST(ST_RNN_BWD, bwork, launch_lstm_bwd_mma(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
                                                   h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, B, T, st));
-    } else if (h->cfg.cell == CRNN_CELL_GRU && !h->rnn_v1) {
-        ST(ST_RNN_BWD, bwork, launch_gru_bwd_cluster(dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), h->w(h->rnn(layer, 0) + "/recurrent_kernel"),
-                                                     h->w(h->rnn(layer, 1) + "/recurrent_kernel"), dxp, hprev, rh, B, T, st));
-    } else {
-        for (int d = 0; d < 2; ++d)
-            ST(ST_MISC, 0, launch_transpose(h->w(h->rnn(layer, d) + "/recurrent_kernel"), UT + (size_t)d * G * U * U, U, G * U, st));
-        ST(ST_RNN_BWD, bwork, launch_rnn_bwd(h->cfg.cell, dout, h->a(nm("hs%d", layer)), h->a(nm("gates%d", layer)), UT, dxp, hprev, rh, B, T, U, st));
     }
     cudaStream_t ss = side_after(h, st);
     for (int d = 0; d < 2; ++d) {
@@ -736,8 +724,6 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     crnn_handle* h = new crnn_handle(); h->cfg = *cfg; plan(h);
     if ((size_t)h->L.cursor > workspace_bytes) { crnn_set_error("workspace too small: need %lld bytes", (long long)h->L.cursor); delete h; return CRNN_ERR_NOMEM; }
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
-    { const char* e = getenv("CRNN_RNN_V1"); h->rnn_v1 = e && e[0] == '1'; }
-    { const char* e = getenv("CRNN_RNN_SIMT_CLUSTER"); h->rnn_simt_cluster = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_FUSE_BN_RED"); h->fuse_bn_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }

@@ -4,23 +4,24 @@
 //   forward : X = raw depthwise output (M pixels x Cin), f = BatchNorm + ReLU6 fused on load, Wop = kernel^T (Cout x Cin)
 //   dX      : X = dY (M x Cout), f = identity, Wop = kernel (Cin x Cout)
 //
-// fp32 fidelity on TF32 tensor cores: every operand is split a = hi + lo (hi = RN-to-tf32(a), lo = a - hi, exact) and
-// three MMAs  hi*hi + lo*hi + hi*lo  are accumulated in fp32 in TMEM ("3xTF32"; the dropped lo*lo term is 2^-22 relative),
-// which keeps the stack inside the fp32 tolerance of the parity tests.
+// fp32 fidelity on the tensor cores: every operand is split a = hi + lo (hi = RN-to-tf32(a), lo = a - hi) and the product is formed by
+// TWO UMMAs per 8-wide k group (tf32 main term + one bf16 UMMA carrying both cross terms, see TC_IDESC_BF16); the dW kernel still uses
+// the three-term 3xTF32 form.  Either keeps the stack inside the fp32 tolerance of the parity tests (tools/two_mma_error_model.py).
 //
 // The problem is computed TRANSPOSED on the tensor core:  D[n][m] (128 channels = TMEM lanes, 128 pixels = TMEM columns)
-//   UMMA A operand (128 x K, K-major) = 16 KB pre-swizzled weight images (hi, lo) written once per step by
-//                                       prep_weight_images_kernel, staged by ONE cp.async.bulk (TMA engine) per image;
-//   UMMA B operand (128 pixels x K, K-major) = the activation tile: 4 producer warps load it (coalesced 128-byte rows), apply
+//   UMMA A operand (128 x K, K-major) = 16 KB pre-swizzled weight images (hi, x) written once per step by prep_weight_images_kernel,
+//                                       streamed by cp.async.bulk (TMA engine) from a dedicated loader warp;
+//   UMMA B operand (128 pixels x K, K-major) = the activation tile: 8 producer warps fetch it with cp.async into a raw ring, apply
 //                                       BN+ReLU6, split hi/lo and store it into the canonical SWIZZLE_128B layout.
-// so the epilogue is free of transposes: a warp owns 32 consecutive channels (its TMEM lane quarter), each thread reads its
-// channel's 128 pixel values with tcgen05.ld and (a) stores are 128-byte coalesced per pixel row, (b) the BatchNorm batch
-// statistics of the output (sum, sum of squares per channel) are plain in-thread reductions -> fused, no extra pass.
-//
-// Pipeline: 3 smem stages of {Whi, Wlo, Xhi, Xlo} x (128 rows x 32 fp32) = 64 KB; mbarriers full[s] (128 producer arrivals + 1 expect_tx +
-// bulk-copy transaction bytes), empty[s] (tcgen05.commit), acc (tcgen05.commit after the last k-block).
-// Warp 4 = TMEM allocator + single-thread MMA issuer.  One CTA per SM (192 KB smem), grid = (channel tiles, pixel tiles).
+// so the epilogue is free of transposes: a warp owns 32 consecutive channels (its TMEM lane quarter), each thread reads its channel's
+// pixel values with tcgen05.ld and (a) stores are 128-byte coalesced per pixel row, (b) the BatchNorm batch statistics of the output
+// (sum, sum of squares per channel) -- or the reduction pass of the following BN backward -- are plain in-thread reductions.
+// Persistent CTAs (one per SM) walk a static tile schedule; two TMEM accumulator buffers overlap a tile's epilogue with the next tile's
+// MMAs (xw_gemm_tc_v2_kernel below).  The MMA warp issues through the "lean" path (umma_kblock): before it, the issuing thread itself
+// (descriptor assembly + per-instruction waterfall loops, ~1400 cycles per 512 cycles of tensor work) paced the kernel -- ncu r1n.
 #include <stdlib.h>
+
+#include <cuda.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -30,11 +31,7 @@ namespace {
 constexpr int TC_BP = 128;        // pixels per CTA  (UMMA N)
 constexpr int TC_BC = 128;        // channels per CTA (UMMA M)
 constexpr int TC_BK = 32;         // fp32 per k-block = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_FLOATS = 128 * TC_BK;            // 4096 floats = 16 KB
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_FLOATS * 4; // Whi, Wlo, Xhi, Xlo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 160;
 
 // ---- canonical K-major SWIZZLE_128B placement of element (row r, k) inside a 128 x 32 fp32 tile (float offset)
 __host__ __device__ __forceinline__ int sw128_off(int r, int k) {
@@ -86,39 +83,63 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64) | [46,48) version=1 | [61,64) layout=2
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
+// (assembled as {low word, constant high word} by umma_desc_lo / TC_DESC_HI below)
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BP >> 3) << 17) | ((uint32_t)(TC_BC >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
-}
-// fp32-faithful product in TWO UMMAs per 8-wide k group instead of the three of 3xTF32 (the kernel is paced by the tensor pipe and by
-// its shared-memory operand reads, ncu r1f: l1tex data_pipe_tc wavefronts 41 % with 3 UMMAs):
+// fp32-faithful product in TWO UMMAs per 8-wide k group instead of the three of 3xTF32:
 //   w.x = w_hi.x_hi (kind::tf32, K = 8)  +  [ w_hi'.x_lo + w_lo.x_hi' ] (ONE kind::f16 bf16 UMMA, K = 16)
 // The cross terms are 2^-11 of the main term, so bf16 operands suffice for them (error <= ~2^-19 of a product).  They share one UMMA by
 // interleaving along K: the "x" tiles hold, per (row, k), one 32-bit word {bf16 slot 2k, bf16 slot 2k+1} = {w_hi', w_lo} for the weights
 // and {x_lo, x_hi'} for the activations -- same bytes per row, same SWIZZLE_128B geometry and the same 32-byte K advance as the tf32 tile.
 constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BP >> 3) << 17) | ((uint32_t)(TC_BC >> 4) << 24);
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC_BF16), "r"(accumulate) : "memory");
-}
 // {slot0 -> bits 15:0, slot1 -> bits 31:16}, round to nearest
 __device__ __forceinline__ float pack_bf16x2(float slot0, float slot1) {
     uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(slot1), "f"(slot0)); return __uint_as_float(r);
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+
+// ---- lean MMA issue path (v2 kernel).  ncu r1n showed the single MMA-issuing thread, not shared memory, pacing the kernel: ~170 SASS
+// instructions per 8 UMMAs (descriptor re-assembly on the uniform datapath, one ELECT / R2UR.BROADCAST "waterfall" loop per instruction
+// because the operands were not provably warp-uniform) = ~1400 cycles per (k-block, channel sub-tile) against 512 cycles of tensor work.
+// Here the whole warp executes the issue code (uniform values), ONE elect.sync per k-block picks the issuing lane, the 64-bit descriptors
+// are {low word, constant high word} pairs whose low words advance by plain adds (smem addresses < 256 KB: no carry out of the 14-bit field).
+constexpr uint32_t TC_DESC_HI = 64u | (1u << 14) | (2u << 29);      // SBO = 1024 B >> 4, version 1, SWIZZLE_128B  (bits 32..63 of umma_desc)
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+// the four k-groups (8 fp32 each) of one 32-wide k-block: per group one bf16 cross-term UMMA + one tf32 main-term UMMA.
+//   wl / xl: descriptor low words of the stage's Whi / Xhi tiles (the x / lo tiles follow 16 KB = 1024 descriptor units later)
+//   first: 0 -> the very first UMMA overwrites the accumulator (start of a tile's k range)
+__device__ __forceinline__ void umma_kblock(uint32_t tacc, uint32_t wl, uint32_t xl, uint32_t first_acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %3, 0;\n\t"
+        "add.u32 a, %1, 1024;\n\tadd.u32 b, %2, 1024;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t"
+        "add.u32 a, %1, 1026;\n\tadd.u32 b, %2, 1026;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, 1;\n\t"
+        "add.u32 a, %1, 2;\n\tadd.u32 b, %2, 2;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t"
+        "add.u32 a, %1, 1028;\n\tadd.u32 b, %2, 1028;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, 1;\n\t"
+        "add.u32 a, %1, 4;\n\tadd.u32 b, %2, 4;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t"
+        "add.u32 a, %1, 1030;\n\tadd.u32 b, %2, 1030;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, 1;\n\t"
+        "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t}"
+        ::"r"(tacc), "r"(wl), "r"(xl), "r"(first_acc), "r"(TC_DESC_HI), "r"(TC_IDESC), "r"(TC_IDESC_BF16) : "memory");
+}
+// tcgen05.commit by one elected lane of a converged warp (up to three barriers; 0 = skip)
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar0, uint32_t bar1, uint32_t bar2) {
+    asm volatile(
+        "{\n\t.reg .pred q, r1, r2;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.and.b32 r1, %1, 0, q;\n\tsetp.ne.and.b32 r2, %2, 0, q;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "@r1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t"
+        "@r2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%2];\n\t}"
+        ::"r"(bar0), "r"(bar1), "r"(bar2) : "memory");
 }
 
 struct TcArgs {
@@ -133,146 +154,7 @@ struct TcArgs {
     // v2, optional: fused reduction pass of the BatchNorm+ReLU6 backward that consumes `out` (= dL/d relu6(bn(y))): with y = red_y[m][n]
     // (same shape / row stride as out) the epilogue accumulates stats[n] += dz, stats[N + n] += dz * xhat, dz = out * 1[0 <= y*sc+sh <= 6]
     const float* red_y; const float* red_scale; const float* red_shift; const float* red_mean; const float* red_invstd;
-    int diag;                         // CRNN_GEMM_DIAG (timing experiments only, results are garbage): 1 no epilogue stores, 2 no transform, 4 no MMA, 8 no activation fetch
 };
-
-__global__ void __launch_bounds__(TC_THREADS, 1) xw_gemm_tc_kernel(TcArgs a)
-{
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024-B alignment
-    float* stage_base = (float*)smem;
-    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* full = bars; uint64_t* empty = bars + TC_STAGES; uint64_t* accb = bars + 2 * TC_STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ct = blockIdx.x;                 // channel tile
-    const int m0 = blockIdx.y * TC_BP;         // first pixel
-    const int KB = a.K / TC_BK;
-
-    if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }   // 128 producers + the expect_tx arrival
-        mbar_init(accb, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 4) {   // TMEM: 128 columns (fp32 accumulator 128 lanes x 128 columns)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < 4) {
-        // =========================== producers: activation tile transform + weight bulk copies ===========================
-        const int c8 = tid & 7;                 // 16-byte chunk (4 k) inside the 128-byte row
-        const int r0 = tid >> 3;                // first row handled by this thread (rows r0 + 16*i)
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (kb / TC_STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);       // first pass returns immediately (fresh barrier, parity 1)
-            float* Whi = stage_base + (size_t)s * (4 * TC_TILE_FLOATS);
-            float* Wlo = Whi + TC_TILE_FLOATS; float* Xhi = Wlo + TC_TILE_FLOATS; float* Xlo = Xhi + TC_TILE_FLOATS;
-            if (tid == 0) {
-                const float* src = a.Wimg + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
-                mbar_arrive_expect_tx(&full[s], 2 * TC_TILE_FLOATS * 4);
-                bulk_g2s(Whi, src, TC_TILE_FLOATS * 4, &full[s]);
-                bulk_g2s(Wlo, src + TC_TILE_FLOATS, TC_TILE_FLOATS * 4, &full[s]);
-            }
-            const int k = kb * TC_BK + c8 * 4;
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.x_scale) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + k)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + k)); }
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = m0 + r0 + 16 * i;
-                v[i] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.X + (size_t)m * a.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 16 * i;
-                float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                if (a.x_scale) {
-                    x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
-                    x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
-                    if (m0 + r >= a.M) { x[0] = x[1] = x[2] = x[3] = 0.f; }
-                }
-                uint32_t hi[4]; float lo[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { hi[q] = to_tf32(x[q]); lo[q] = x[q] - __uint_as_float(hi[q]); }
-                const int off = (r >> 3) * 256 + (r & 7) * 32 + ((c8 ^ (r & 7)) << 2);
-                *reinterpret_cast<uint4*>(Xhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(Xlo + off) = make_float4(pack_bf16x2(lo[0], __uint_as_float(hi[0])), pack_bf16x2(lo[1], __uint_as_float(hi[1])),
-                                                                    pack_bf16x2(lo[2], __uint_as_float(hi[2])), pack_bf16x2(lo[3], __uint_as_float(hi[3])));   // {x_lo, x_hi'}
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
-            mbar_arrive(&full[s]);
-        }
-        // =========================== epilogue: TMEM -> registers -> coalesced global stores (+ BN statistics) ===========================
-        mbar_wait(accb, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int n = ct * TC_BC + warp * 32 + lane;          // this thread's output channel
-        const bool n_ok = n < a.N;
-        const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC_BP; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const int m = m0 + c0 + p;
-                if (m < a.M && n_ok) {
-                    float val = __uint_as_float(r[p]) + bias;
-                    if (a.relu) val = fmaxf(val, 0.f);
-                    float* dst = a.out + (size_t)m * a.ldo + n;   // 32 lanes = 32 consecutive channels: 128-byte coalesced
-                    if (a.accumulate) val += *dst;
-                    *dst = val;
-                    s1 += val; s2 = fmaf(val, val, s2);
-                }
-            }
-        }
-        if (a.stats && n_ok) { atomicAdd(a.stats + n, (double)s1); atomicAdd(a.stats + a.N + n, (double)s2); }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else {
-        // =========================== warp 4: single-thread MMA issue ===========================
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (kb / TC_STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t whi = smem_u32(stage_base + (size_t)s * (4 * TC_TILE_FLOATS));
-                const uint32_t wlo = whi + TC_TILE_FLOATS * 4, xhi = wlo + TC_TILE_FLOATS * 4, xlo = xhi + TC_TILE_FLOATS * 4;
-#pragma unroll
-                for (int ks = 0; ks < TC_BK / 8; ++ks) {      // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the swizzle atom
-                    const uint32_t o = ks * 32;
-                    umma_bf16(tmem_base, umma_desc(wlo + o), umma_desc(xlo + o), (kb | ks) ? 1u : 0u);   // cross terms first
-                    umma_tf32(tmem_base, umma_desc(whi + o), umma_desc(xhi + o), 1u);
-                }
-                umma_commit(&empty[s]);                       // frees the stage when these MMAs have read it
-                if (kb == KB - 1) umma_commit(accb);          // accumulator complete
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
-    }
-}
 
 // =====================================================================================================================
 // Weight gradient of the pointwise conv:  dW[ci][co] += sum_m f(X[m][ci]) * dY[m][co]     (contraction over PIXELS)
@@ -291,21 +173,33 @@ template <int NB> struct DwCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4 + 1024 + 256;
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {   // MN-major SWIZZLE_128B_BASE32B: LBO = 4096 B, SBO = 512 B
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
-}
+// MN-major SWIZZLE_128B_BASE32B descriptor: LBO = 4096 B, SBO = 512 B, version 1, layout type 1 (low word / TC_DESC_MN_HI below)
 // float offset of (pixel row pl in 0..31, 16-byte chunk c16 in 0..7) inside one 32-channel mn-block of an MN-major tile
 __device__ __forceinline__ int mn_off(int pl, int c16) {
     const int kr = pl & 3, kg = pl >> 2;
     return kg * 128 + kr * 32 + ((((c16 >> 1) ^ kr) << 3) | ((c16 & 1) << 2));
 }
-template <uint32_t IDESC>
-__device__ __forceinline__ void umma_tf32_i(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// one 32-pixel k-block of the dW kernel on the lean issue path: 4 groups of 8 pixels (two 4-row atoms = 64 descriptor units apart), per group
+// the three 3xTF32 terms lo*hi, hi*lo, hi*hi.  ahi = descriptor low word of the stage's A_hi tile; A_lo follows 1024 units later, B_hi 2048,
+// B_lo 2048 + BLO units.  MN-major SWIZZLE_128B_BASE32B high word: SBO = 512 B >> 4, version 1, layout type 1.
+constexpr uint32_t TC_DESC_MN_HI = 32u | (1u << 14) | (1u << 29);
+template <uint32_t IDESC, uint32_t BLO>
+__device__ __forceinline__ void umma_kblock_mn(uint32_t tacc, uint32_t ahi, uint32_t not_first) {
+#define XTY_GROUP(G, P0)                                                                                                              \
+        "add.u32 a, %1, " #G "*64+1024;\n\tadd.u32 b, %1, " #G "*64+2048;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"                 \
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, " P0 ";\n\t"                                                        \
+        "add.u32 a, %1, " #G "*64;\n\tadd.u32 b, %1, " #G "*64+2048+%5;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"                    \
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, 1;\n\t"                                                            \
+        "add.u32 b, %1, " #G "*64+2048;\n\tmov.b64 db, {b, %3};\n\t"                                                                  \
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, 1;\n\t"
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        XTY_GROUP(0, "p") XTY_GROUP(1, "1") XTY_GROUP(2, "1") XTY_GROUP(3, "1")
+        "}"
+        ::"r"(tacc), "r"(ahi), "r"(not_first), "r"(TC_DESC_MN_HI), "r"(IDESC), "n"(BLO) : "memory");
+#undef XTY_GROUP
 }
 
 struct DwArgs {
@@ -463,26 +357,19 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
-        // ------------------------------------------------ warp 8: MMA issue
+        // ------------------------------------------------ warp 8: MMA issue (lean path: whole warp, uniform operands, one elected lane --
+        // see umma_kblock; the per-instruction descriptor assembly + waterfall loops cost ~110 cycles per UMMA against 64 (NB = 128))
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t adesc0 = ((smem_u32(stage_base) >> 4) & 0x3FFFu) | (256u << 16);      // MN-major: LBO = 4096 B in the low word
+        const uint32_t bar_empty = smem_u32(empty), bar_acc = smem_u32(accb);
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % C::STAGES;
             const uint32_t ph = (kb / C::STAGES) & 1;
             mbar_wait(&full[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t ahi = smem_u32(stage_base + (size_t)s * C::STAGE_FLOATS);
-                const uint32_t alo = ahi + C::A_FLOATS * 4, bhi = alo + C::A_FLOATS * 4, blo = bhi + C::B_FLOATS * 4;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {                  // 8 pixels (two 4-row atoms, 1024 B) per MMA
-                    const uint32_t o = g * 1024;
-                    umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(alo + o), umma_desc_mn(bhi + o), (kb | g) ? 1u : 0u);
-                    umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(ahi + o), umma_desc_mn(blo + o), 1u);
-                    umma_tf32_i<C::IDESC>(tmem_base, umma_desc_mn(ahi + o), umma_desc_mn(bhi + o), 1u);
-                }
-                umma_commit(&empty[s]);
-                if (kb == KB - 1) umma_commit(accb);
-            }
-            __syncwarp();
+            const uint32_t ahi = adesc0 + (uint32_t)s * (uint32_t)(C::STAGE_FLOATS * 4 / 16);
+            umma_kblock_mn<C::IDESC, C::B_FLOATS * 4 / 16>(tb, ahi, (uint32_t)kb);
+            umma_commit_elect(bar_empty + 8u * s, kb == KB - 1 ? bar_acc : 0u, 0u);
         }
     }
     __syncthreads();
@@ -501,21 +388,23 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
 //   * two TMEM accumulator buffers (2 x 128 columns) and dedicated epilogue warps (9-16), so the TMEM->HBM epilogue of tile i
 //     overlaps the MMAs of tile i+1;  barriers: full/empty per smem stage, tmem_full/tmem_empty per accumulator buffer.
 // =====================================================================================================================
-constexpr int TC2_PROD_WARPS = 8;                // activation-producer warps 0..7
+constexpr int TC2_PROD_WARPS = 8;                // activation-transform warps 0..7
 constexpr int TC2_MMA_WARP = TC2_PROD_WARPS;     // warp 8 issues the MMAs (and owns the TMEM allocation)
 constexpr int TC2_EPI_WARP0 = TC2_MMA_WARP + 1;  // epilogue warps 9..16 (two per TMEM lane quarter)
-constexpr int TC2_LOAD_WARP = TC2_EPI_WARP0 + 8; // warp 17 streams the weight images
-constexpr int TC2_THREADS = (TC2_LOAD_WARP + 1) * 32;
+constexpr int TC2_LOAD_WARP = TC2_EPI_WARP0 + 8; // warp 17 streams the weight images (1-D bulk copies)
+constexpr int TC2_XLOAD_WARP = TC2_LOAD_WARP + 1; // warp 18 streams the raw activation tiles (2-D tensor-map TMA)
+constexpr int TC2_THREADS = (TC2_XLOAD_WARP + 1) * 32;
 constexpr int TC2_XSTAGES = 2;                  // {Xhi, Xlo} tiles consumed by the tensor core
 constexpr int TC2_WRING = 3;                    // {Whi, Wlo} weight tiles, streamed by the loader warp ahead of the MMA
-constexpr int TC2_RAW = 3;                      // raw fp32 activation ring filled by cp.async
-constexpr int TC2_SMEM_BYTES = (TC2_WRING * 2 + TC2_XSTAGES * 2 + TC2_RAW) * TC_TILE_FLOATS * 4 + 1024 + 256;
+constexpr int TC2_RAW = 3;                      // raw fp32 activation ring filled by the tensor-map TMA loads
+constexpr int TC2_BN_MAXK = 512;                // BN+ReLU6 prologue: per-k scale/shift table kept in shared memory (conv stack: K <= 512)
+constexpr int TC2_SMEM_BYTES = (TC2_WRING * 2 + TC2_XSTAGES * 2 + TC2_RAW) * TC_TILE_FLOATS * 4 + 2 * TC2_BN_MAXK * 4 + 1024 + 256;
 
-__device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src, uint32_t src_bytes) {   // src_bytes = 0 -> zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+// 2-D tiled TMA load: box {32 fp32 along k, 128 pixel rows} of X at (k0, m0) -> dense [128][32] fp32 tile; rows >= M arrive as zeros
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // store + BN-backward reduction: dz = val * 1[0 <= y*sc+sh <= 6]; s1 += dz; s2 += dz * (y*xa + xb)
 template <int LDO>
 __device__ __forceinline__ void epi_store_red(float* dst, const float* __restrict__ ysrc, const uint32_t (&r)[32], int ldo_rt,
@@ -545,18 +434,20 @@ __device__ __forceinline__ void epi_store(float* dst, const uint32_t (&r)[32], i
 // KS > 1: split-K.  Work item t = (CTA tile t / KS, k-slice t % KS); every slice contracts KBS k-blocks and stores its partial tile
 // into its own copy of the output (out + slice * split_stride) -- the caller sums the copies in a fixed order (deterministic, no atomics).
 // Used for the head GEMMs whose 128-pixel x 128-channel tiling yields only 33-66 tiles for 148 SMs (dense1: M=4224, N=128, K=4608).
-__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, int NTP, int MT, int NSUB, int KS, long long split_stride)
+__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmx, int NTP, int MT, int NSUB, int KS, long long split_stride)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     float* w_base = (float*)smem;                                               // [WRING][Whi | Wlo]
     float* x_base = w_base + (size_t)TC2_WRING * 2 * TC_TILE_FLOATS;            // [XSTAGES][Xhi | Xlo]
     float* raw_base = x_base + (size_t)TC2_XSTAGES * 2 * TC_TILE_FLOATS;        // [RAW][128 x 32 fp32]
-    uint64_t* bars = (uint64_t*)(raw_base + (size_t)TC2_RAW * TC_TILE_FLOATS);
+    float* bn_tab = raw_base + (size_t)TC2_RAW * TC_TILE_FLOATS;                // [scale K | shift K] of the BN+ReLU6 prologue
+    uint64_t* bars = (uint64_t*)(bn_tab + 2 * TC2_BN_MAXK);
     uint64_t* wfull = bars; uint64_t* wempty = wfull + TC2_WRING;
     uint64_t* xfull = wempty + TC2_WRING; uint64_t* xempty = xfull + TC2_XSTAGES;
     uint64_t* tfull = xempty + TC2_XSTAGES; uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint64_t* rawfull = tempty + 2; uint64_t* rawempty = rawfull + TC2_RAW;
+    uint32_t* tmem_slot = (uint32_t*)(rawempty + TC2_RAW);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KB = a.K / TC_BK;
@@ -569,6 +460,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         for (int s = 0; s < TC2_WRING; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
         for (int s = 0; s < TC2_XSTAGES; ++s) { mbar_init(&xfull[s], TC2_PROD_WARPS); mbar_init(&xempty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256); }
+        for (int s = 0; s < TC2_RAW; ++s) { mbar_init(&rawfull[s], 1); mbar_init(&rawempty[s], TC2_PROD_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC2_MMA_WARP) {
@@ -581,43 +473,22 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < TC2_PROD_WARPS) {
-        // =========================== activation producers ===========================
-        // Each thread owns the same 4 (row, 16-byte chunk) slots in every ring entry, so it only ever waits for ITS OWN cp.async
-        // groups: no cross-thread synchronisation between the asynchronous fill and the transform.  (ncu source view of the 4-warp
-        // version: the MMA warp spun on x_full 45x more than on w_full, i.e. this transform paced the kernel - each k-block waited a
-        // full L2 round trip for the BN scale/shift, and the generic-address ST->LD ordering serialised the chunks.  Hence: 8 warps,
-        // scale/shift prefetched one k-block ahead, all raw chunks loaded before the first store, shared-space 32-bit addressing.)
+        // =========================== activation transform warps ===========================
+        // The raw fp32 tile of every k-block arrives in the ring by ONE tensor-map TMA load issued by warp 18 (rows >= M zero-filled by the
+        // TMA unit); these warps only read it back (each thread the same 4 (row, 16-byte chunk) slots of every entry), apply BN+ReLU6, split
+        // into {hi, {lo, hi'}} and store the two SWIZZLE_128B operand tiles.  They have NO global loads of their own in flight, which is the
+        // point: the generic->async proxy fence below compiles to MEMBAR.ALL.CTA, and while these warps still issued the cp.async prefetches
+        // themselves (round 1) that membar waited for the prefetched k-blocks to land -- ncu r2b: long-scoreboard stalls on the fence, one
+        // full memory latency per k-block, x_full the barrier the MMA warp waited on.
         const int c8 = tid & 7, r0 = tid >> 3;                                   // r0 in 0..31; rows r0 + 32 i
         const uint32_t raw_u32 = smem_u32(raw_base) + (uint32_t)(r0 * TC_BK + c8 * 4) * 4u;
         const uint32_t x_u32 = smem_u32(x_base) + (uint32_t)((r0 >> 3) * 256 + (r0 & 7) * 32 + ((c8 ^ (r0 & 7)) << 2)) * 4u;
         const bool bn = a.x_scale != nullptr;
-        // fetch state: the 4 row pointers of the tile being fetched are computed once per tile, a k-block fetch is 4 x (64-bit add + LDGSTS)
-        const float* frp[4]; uint32_t fsz[4];
-        auto set_fetch_tile = [&](int tt) {
-            const int m0 = (a.rev ? MT - 1 - (tt / KS) / NTP : (tt / KS) / NTP) * TC_BP;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = m0 + r0 + 32 * i;
-                const bool ok = m < a.M;
-                frp[i] = a.X + (size_t)(ok ? m : 0) * a.ldx + c8 * 4;
-                fsz[i] = (ok && !(a.diag & 8)) ? 16u : 0u;                      // 0 -> zero fill (rows >= M)
-            }
-        };
-        auto issue = [&](int kk, int slot) {             // raw[slot][r][c8*4..] <- X[m0+r][kk*32 + c8*4 ..]
-            const uint32_t dst = raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cp_async16_s(dst + (uint32_t)i * (32u * TC_BK * 4u), frp[i] + kk * TC_BK, fsz[i]);
-        };
-        int ft = blockIdx.x, fk = 0, fke = 0;             // next (tile, k-block) to FETCH, end of that tile's k range
-        if (ft < total) { set_fetch_tile(ft); fk = kb_lo(ft); fke = kb_hi(ft); }
-        auto fetch_advance = [&]() { if (++fk == fke) { ft += gridDim.x; if (ft < total) { set_fetch_tile(ft); fk = kb_lo(ft); fke = kb_hi(ft); } } };
-#pragma unroll
-        for (int d = 0; d < TC2_RAW; ++d) {
-            if (ft < total) { issue(fk, d); fetch_advance(); }
-            cp_async_commit();                            // (possibly empty) group keeps the group count uniform
+        if (bn) {                                                                // per-k scale / shift table (K <= TC2_BN_MAXK, checked by the launcher)
+            for (int k = tid; k < a.K; k += TC2_PROD_WARPS * 32) { bn_tab[k] = __ldg(a.x_scale + k); bn_tab[TC2_BN_MAXK + k] = __ldg(a.x_shift + k); }
+            asm volatile("bar.sync 2, 256;" ::: "memory");                       // the 8 transform warps only
         }
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bn) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + c8 * 4)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + c8 * 4)); }
+        const uint32_t bn_u32 = smem_u32(bn_tab) + (uint32_t)(c8 * 4) * 4u;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
@@ -627,14 +498,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 const int s = it % TC2_XSTAGES;
                 const uint32_t ph = (it / TC2_XSTAGES) & 1;
                 const int slot = it % TC2_RAW;
-                float4 scn = sc, shn = sh;                // next k-block's scale/shift: in flight during this block's transform
-                if (bn) {
-                    const int kn = (kb + 1 == KB ? 0 : kb + 1) * TC_BK + c8 * 4;
-                    scn = __ldg(reinterpret_cast<const float4*>(a.x_scale + kn)); shn = __ldg(reinterpret_cast<const float4*>(a.x_shift + kn));
-                }
-                cp_async_wait<TC2_RAW - 1>();             // this thread's chunks of ring entry `slot` have landed
-                if (a.diag & 2) { mbar_wait(&xempty[s], ph ^ 1); __syncwarp(); if (lane == 0) mbar_arrive(&xfull[s]); }
-                else {
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bn) { sc = lds128(bn_u32 + (uint32_t)kb * (TC_BK * 4u)); sh = lds128(bn_u32 + (uint32_t)(TC2_BN_MAXK + kb * TC_BK) * 4u); }
+                mbar_wait(&rawfull[slot], (it / TC2_RAW) & 1);                   // the TMA load of ring entry `slot` has landed
                 float4 v[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[i] = lds128(raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u) + (uint32_t)i * (32u * TC_BK * 4u));
@@ -649,25 +515,43 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                         for (int i = 0; i < 4; ++i) if (m0 + r0 + 32 * i >= a.M) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+                float4 hv[4], lv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float l0, l1, l2, l3;
+                    split_tf32(v[i].x, hv[i].x, l0); split_tf32(v[i].y, hv[i].y, l1); split_tf32(v[i].z, hv[i].z, l2); split_tf32(v[i].w, hv[i].w, l3);
+                    lv[i] = make_float4(pack_bf16x2(l0, hv[i].x), pack_bf16x2(l1, hv[i].y), pack_bf16x2(l2, hv[i].z), pack_bf16x2(l3, hv[i].w));   // {x_lo, x_hi'}
+                }
+                __syncwarp();                                                    // every lane's reads of the ring entry have been consumed above
+                if (lane == 0) mbar_arrive(&rawempty[slot]);                     // -> the TMA warp may refill it
                 mbar_wait(&xempty[s], ph ^ 1);
                 const uint32_t xhi = x_u32 + (uint32_t)s * (2u * TC_TILE_FLOATS * 4u), xlo = xhi + TC_TILE_FLOATS * 4u;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float h0, h1, h2, h3, l0, l1, l2, l3;
-                    split_tf32(v[i].x, h0, l0); split_tf32(v[i].y, h1, l1); split_tf32(v[i].z, h2, l2); split_tf32(v[i].w, h3, l3);
-                    sts128(xhi + (uint32_t)i * 4096u, h0, h1, h2, h3);       // row r0 + 32 i: 4 eight-row groups = 4 x 1024 B further
-                    sts128(xlo + (uint32_t)i * 4096u, pack_bf16x2(l0, h0), pack_bf16x2(l1, h1), pack_bf16x2(l2, h2), pack_bf16x2(l3, h3));   // {x_lo, x_hi'}
+                    sts128(xhi + (uint32_t)i * 4096u, hv[i].x, hv[i].y, hv[i].z, hv[i].w);       // row r0 + 32 i: 4 eight-row groups = 4 x 1024 B further
+                    sts128(xlo + (uint32_t)i * 4096u, lv[i].x, lv[i].y, lv[i].z, lv[i].w);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xfull[s]);
-                }
-                if (ft < total) { issue(fk, slot); fetch_advance(); }   // refill the ring entry just consumed
-                cp_async_commit();
-                sc = scn; sh = shn;
             }
         }
-        cp_async_wait<0>();
+    } else if (warp == TC2_XLOAD_WARP) {
+        // =========================== raw activation loader: one thread, one tensor-map TMA load per k-block ===========================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
+                const int kb0 = kb_lo(t), kb1 = kb_hi(t);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int slot = it % TC2_RAW;
+                    mbar_wait(&rawempty[slot], ((it / TC2_RAW) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&rawfull[slot], TC_TILE_FLOATS * 4);
+                    tma_load_2d(raw_base + (size_t)slot * TC_TILE_FLOATS, &tmx, kb * TC_BK, m0, &rawfull[slot]);
+                }
+            }
+        }
     } else if (warp == TC2_LOAD_WARP) {
         // =========================== weight loader: one thread streams the pre-swizzled hi/lo images (TMA bulk copies) ===========================
         if (lane == 0) {
@@ -689,6 +573,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         }
     } else if (warp == TC2_MMA_WARP) {
         // =========================== MMA issuer ===========================
+        // the whole warp runs this code with warp-uniform values; one elected lane issues (umma_kblock / umma_commit_elect)
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t wdesc0 = umma_desc_lo(smem_u32(w_base)), xdesc0 = umma_desc_lo(smem_u32(x_base));
+        const uint32_t bar_wempty = smem_u32(wempty), bar_xempty = smem_u32(xempty), bar_tfull = smem_u32(tfull);
         uint32_t it = 0, wit = 0;
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
@@ -699,28 +587,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int xs = it % TC2_XSTAGES;
                 mbar_wait(&xfull[xs], (it / TC2_XSTAGES) & 1);
+                const uint32_t xl = xdesc0 + (uint32_t)xs * (2u * TC_TILE_FLOATS * 4u / 16u);
                 for (int h = 0; h < NSUB; ++h, ++wit) {
                     const int ws = wit % TC2_WRING;
-                    const uint32_t tacc = tmem_base + (uint32_t)(buf * 256 + h * TC_BP);
+                    const uint32_t tacc = tb + (uint32_t)(buf * 256 + h * TC_BP);
                     mbar_wait(&wfull[ws], (wit / TC2_WRING) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (lane == 0) {
-                        const uint32_t whi = smem_u32(w_base + (size_t)ws * (2 * TC_TILE_FLOATS)), wlo = whi + TC_TILE_FLOATS * 4;
-                        const uint32_t xhi = smem_u32(x_base + (size_t)xs * (2 * TC_TILE_FLOATS)), xlo = xhi + TC_TILE_FLOATS * 4;
-#pragma unroll
-                        for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                            if (a.diag & 4) break;
-                            const uint32_t o = ks * 32;
-                            umma_bf16(tacc, umma_desc(wlo + o), umma_desc(xlo + o), ((kb - kb0) | ks) ? 1u : 0u);   // cross terms first
-                            umma_tf32(tacc, umma_desc(whi + o), umma_desc(xhi + o), 1u);
-                        }
-                        umma_commit(&wempty[ws]);
-                        if (h == NSUB - 1) {
-                            umma_commit(&xempty[xs]);
-                            if (kb == kb1 - 1) umma_commit(&tfull[buf]);
-                        }
-                    }
-                    __syncwarp();
+                    umma_kblock(tacc, wdesc0 + (uint32_t)ws * (2u * TC_TILE_FLOATS * 4u / 16u), xl, (uint32_t)(kb - kb0));
+                    const bool last_h = h == NSUB - 1;
+                    umma_commit_elect(bar_wempty + 8u * ws, last_h ? bar_xempty + 8u * xs : 0u, (last_h && kb == kb1 - 1) ? bar_tfull + 8u * buf : 0u);
                 }
             }
         }
@@ -786,8 +661,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float* dst = outp + (size_t)(m0 + c0) * a.ldo + n;      // 32 lanes = 32 consecutive channels: 128-byte coalesced rows
-                if (a.diag & 1) {
-                } else if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast paths: full 32-pixel chunk, no per-element predicate
+                if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast paths: full 32-pixel chunk, no per-element predicate
                     // row stride known at compile time for the conv-stack widths -> the 32 stores use immediate offsets (the generic
                     // loop costs a 64-bit add per store; the epilogue warps share the issue slots with the activation producers)
                     if (a.red_y) {                                              // dX + reduction pass of the following BN/ReLU6 backward
@@ -921,22 +795,37 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
         if (!stats || bias || relu || accumulate || ksplit > 1) { crnn_set_error("gemm_tc: the fused BN-backward reduction needs stats and the plain-store epilogue"); return CRNN_ERR_INVALID; }
         a.red_y = red->y; a.red_scale = red->scale; a.red_shift = red->shift; a.red_mean = red->mean; a.red_invstd = red->invstd;
     }
-    static int diag = -1, nsub_env = -1;
-    if (diag < 0) { const char* e = getenv("CRNN_GEMM_DIAG"); diag = e ? atoi(e) : 0; const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; }
-    a.diag = diag;
-    static int use_v1 = -1;
-    if (use_v1 < 0) { const char* e = getenv("CRNN_GEMM_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+    if (x_scale && K > TC2_BN_MAXK) { crnn_set_error("gemm_tc: the BN+ReLU6 prologue supports K <= %d (K = %d)", TC2_BN_MAXK, K); return CRNN_ERR_INVALID; }
+    // tensor map of X for the raw-tile TMA loads: dims {K, M} fp32, row stride ldx, box {32, 128}, no swizzle, out-of-range rows read as 0
+    CUtensorMap tmx;
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+                cudaGetLastError(); crnn_set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver"); return CRNN_ERR_CUDA;
+            }
+            encode = reinterpret_cast<EncodeFn>(fn);
+        }
+        const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+        const cuuint64_t gstr[1] = {(cuuint64_t)ldx * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BP};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { crnn_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for X %p, M %d, K %d, ldx %d", (int)r, (const void*)X, M, K, ldx); return CRNN_ERR_CUDA; }
+    }
+    static int nsub_env = -1;
+    if (nsub_env < 0) { const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; }
     const int NT = (N + TC_BC - 1) / TC_BC, MT = (M + TC_BP - 1) / TC_BP;
-    if (ksplit > 1 && (use_v1 || x_scale || stats || bias || relu || accumulate || split_stride < (long long)M * ldo - (ldo - N) || ksplit > K / TC_BK)) {
+    if (ksplit > 1 && (x_scale || stats || bias || relu || accumulate || split_stride < (long long)M * ldo - (ldo - N) || ksplit > K / TC_BK)) {
         crnn_set_error("gemm_tc: split-K needs the plain-store epilogue (no BN prologue / statistics / bias / relu / accumulate) and disjoint output copies");
         return CRNN_ERR_INVALID;
     }
     if (ksplit < 1) ksplit = 1;
-    if (use_v1) {
-        static bool configured = false;
-        if (!configured) { CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); configured = true; }
-        xw_gemm_tc_kernel<<<dim3(NT, MT), TC_THREADS, TC_SMEM_BYTES, st>>>(a);
-    } else {
+    {
         static bool configured2 = false;
         static int num_sms = 148;
         if (!configured2) {
@@ -950,7 +839,7 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
         const int NTP = NT / NSUB;
         const long long total = (long long)NTP * MT * ksplit;
         const int grid = (int)(total < num_sms ? total : num_sms);
-        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, NTP, MT, NSUB, ksplit, split_stride);
+        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, tmx, NTP, MT, NSUB, ksplit, split_stride);
     }
     LAUNCH_CHECK();
     return CRNN_OK;

@@ -104,7 +104,6 @@ int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const
 int launch_sum_dirs(const float* hs, float* out, long long rows, int U, cudaStream_t st);               // out[r][u] = hs[r][0][u]+hs[r][1][u]
 int launch_dup_dirs(const float* g, float* out, long long rows, int U, cudaStream_t st);                // out[r][d][u] = g[r][u]
 int launch_softmax_rows(const float* z, float* p, long long rows, int V, cudaStream_t st);
-int launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);                       // out[C][R] = in[R][C]^T
 
 // ---- stn.cu ----
 struct StnDims { int H, W, H1, W1, P1h, P1w, C1h, C1w, P2h, P2w, C2h, C2w, F; };
@@ -122,25 +121,15 @@ int launch_stn_head_bwd(const float* dtheta, const float* loc_d1, const float* W
 int launch_stn_sample_fwd(const float* x, const float* theta, float* out, int B, int H, int W, int pad, cudaStream_t st);
 int launch_stn_sample_bwd(const float* x, const float* theta, const float* dout_padded, float* dtheta, int B, int H, int W, int pad, cudaStream_t st);
 
-// ---- rnn.cu ----
-// xp (B,T,2,G*U) input projections (+bias), U0/U1 (U,G*U) recurrent kernels of the two directions; hs (B,T,2,U) outputs; gates (B,T,2,GS*U) saved for BPTT (may be null)
-int launch_rnn_fwd(int cell, const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, int U, cudaStream_t st);
-// dout (B,T,2,U) gradient wrt hs; UcatT (2,G*U,U) transposed recurrent kernels; outputs dxp (B,T,2,G*U), hprev (B,T,2,U), rh (B,T,2,U) (GRU only)
-int launch_rnn_bwd(int cell, const float* dout, const float* hs, const float* gates, const float* UcatT,
-                   float* dxp, float* hprev, float* rh, int B, int T, int U, cudaStream_t st);
-
-// ---- rnn_mma.cu : cluster-resident GRU with U held in registers as mma.sync tf32 fragments (3xTF32), state via DSMEM ----
+// ---- rnn_mma.cu : cluster-resident GRU / LSTM recurrence with U held in registers as mma.sync fragments, state via DSMEM ----
+// xp (B,T,2,G*U) input projections (+bias), U0/U1 (U,G*U) recurrent kernels of the two directions; hs (B,T,2,U) outputs; gates (B,T,2,GS*U) saved
+// for BPTT (may be null).  Backward: dout (B,T,2,U) gradient wrt hs -> dxp (B,T,2,G*U), hprev (B,T,2,U), rh (B,T,2,U) (GRU only)
 int launch_gru_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
 int launch_gru_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
                        float* dxp, float* hprev, float* rh, int B, int T, cudaStream_t st);
 int launch_lstm_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
 int launch_lstm_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
                         float* dxp, float* hprev, int B, int T, cudaStream_t st);
-// ---- rnn_cluster.cu : cluster-resident GRU (U column-sharded over 8 CTAs' shared memory, state via DSMEM) ----
-int launch_gru_fwd_cluster(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st);
-int launch_gru_bwd_cluster(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
-                           float* dxp, float* hprev, float* rh, int B, int T, cudaStream_t st);
-
 // ---- optim.cu ----
 int launch_sumsq(const float* g, long long n, double* out /*pre-zeroed*/, cudaStream_t st);
 int launch_adam(float* w, const float* g, float* m, float* v, long long n, const double* sumsq, float clipnorm,

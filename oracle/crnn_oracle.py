@@ -244,12 +244,20 @@ def relu6(y):
     return torch.clamp(y, 0.0, 6.0)
 
 
-def conv_block(w, i, x, pool, training, masks, new_stats, keep):
-    """CRNN.depthwise_conv_block, utils.py:43-56 (i = 1..7)."""
+def _forced_gate(z, act, gate):
+    """Teacher-forced piecewise-linear activation for the isolated backward tests: same forward value as act(z) (up to the rounding-level
+    difference at the elements whose decision differs), but the derivative is 1 exactly where `gate` (the decision the device path took in
+    ITS forward, read back by the test) is set -- so a fp32-vs-fp64 rounding flip of a ReLU gate cannot masquerade as a kernel error."""
+    return torch.where(gate, z, act(z).detach())
+
+
+def conv_block(w, i, x, pool, training, masks, new_stats, keep, gate1=None):
+    """CRNN.depthwise_conv_block, utils.py:43-56 (i = 1..7).  gate1 (tests only): forced ReLU6 pass-through mask of the FIRST activation."""
     c = x.shape[-1]
     y1 = _nhwc(F.conv2d(_nchw(x), w[f"depthwise_conv2d_{i}/depthwise_kernel"].permute(2, 3, 0, 1), padding=1, groups=c))
     keep[f"dw{i}"] = y1
-    a1 = relu6(batchnorm(w, 2 * i - 1, y1, training, new_stats))
+    z1 = batchnorm(w, 2 * i - 1, y1, training, new_stats)
+    a1 = relu6(z1) if gate1 is None else _forced_gate(z1, relu6, gate1)
     y2 = a1 @ w[f"conv2d_{i + 2}/kernel"][0, 0]
     keep[f"pw{i}"] = y2
     a2 = relu6(batchnorm(w, 2 * i, y2, training, new_stats))
@@ -320,12 +328,14 @@ def forward(w, x, cfg: Cfg, training=False, masks=None, new_stats=None):
     return head(w, h, cfg, training, masks, keep)
 
 
-def head(w, h, cfg: Cfg, training=False, masks=None, keep=None):
-    """Everything after the conv stack (utils.py:72-86): block-7 output (B,T,9,512) -> reshape -> dense1 -> 2 x Bi-RNN -> dense2 -> softmax."""
+def head(w, h, cfg: Cfg, training=False, masks=None, keep=None, dense1_gate=None):
+    """Everything after the conv stack (utils.py:72-86): block-7 output (B,T,9,512) -> reshape -> dense1 -> 2 x Bi-RNN -> dense2 -> softmax.
+    dense1_gate (tests only): forced ReLU pass-through mask of dense1, see _forced_gate."""
     keep = OrderedDict() if keep is None else keep
     B, T = h.shape[0], h.shape[1]
     h = h.reshape(B, T, -1)                        # feature index = w*512 + c, utils.py:72-73
-    h = torch.relu(h @ w["dense1/kernel"] + w["dense1/bias"])
+    h = h @ w["dense1/kernel"] + w["dense1/bias"]
+    h = torch.relu(h) if dense1_gate is None else _forced_gate(h, torch.relu, dense1_gate)
     if training and masks is not None and "dropout_8" in masks:
         h = h * masks["dropout_8"]
     keep["dense1"] = h
