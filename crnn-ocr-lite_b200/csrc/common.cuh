@@ -27,6 +27,10 @@ void crnn_set_error(const char* fmt, ...);
 
 extern long long g_crnn_launches;   // kernels launched by this library (engine.cu)
 #define LAUNCH_CHECK() do { ++g_crnn_launches; CUDA_TRY(cudaGetLastError()); } while (0)
+// kernel family of the launch being issued (per-kernel roofline of bench.py: one kernel serves several stages of the step); a launcher of
+// a tracked kernel sets it, the engine's profiling scope reads it back when the launcher returns
+enum { CRNN_FAM_OTHER = 0, CRNN_FAM_XW_TC, CRNN_FAM_XTY_TC, CRNN_FAM_RNN_MMA, CRNN_FAM_DWROWS, CRNN_FAM_COUNT };
+extern int g_crnn_family;
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -291,6 +291,7 @@ int launch_dwconv_rows(const float* x, const float* k, float* y, int B, int H, i
                        const DwRowsRed* red)
 {
     if (!rows_enabled() || C % 4 || W % SEG || W < SEG || (flip && stats && !red) || (red && (!flip || !stats))) return 1;
+    g_crnn_family = CRNN_FAM_DWROWS;
     dim3 grid, block; int nseg, nstrips, RS, nitems;
     plan_rows(B, H, W, C / 4, 2, SEG, grid, block, nseg, nstrips, RS, nitems);
     const size_t sm = std::max(sizeof(float4) * 13 * block.x, (stats ? sizeof(double) * 8 * NTHR : (size_t)0));
@@ -308,6 +309,7 @@ int launch_dwconv_rows(const float* x, const float* k, float* y, int B, int H, i
 int launch_dwconv_rows_bwd_weight(const float* x, const float* dy, float* dk, int B, int H, int W, int C, cudaStream_t st)
 {
     if (!rows_enabled() || C % 4) return 1;
+    g_crnn_family = CRNN_FAM_DWROWS;
     dim3 grid, block; int nseg, nstrips, RS, nitems;
     plan_rows(B, H, W, C / 4, 2, SEGW, grid, block, nseg, nstrips, RS, nitems);
     dwconv3x3_rows_bwd_weight_kernel<<<grid, block, sizeof(float) * 36 * NTHR, st>>>(x, dy, dk, H, W, C / 4, nseg, nstrips, RS, nitems);

@@ -15,6 +15,7 @@
 #include "kernels.h"
 
 long long g_crnn_launches = 0;
+int g_crnn_family = CRNN_FAM_OTHER;
 static thread_local char g_err[512] = "";
 void crnn_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -33,12 +34,13 @@ struct Tensor { std::string name; int64_t offset; int64_t numel; int is_int; };
 enum Stage { ST_STN = 0, ST_DWCONV, ST_BN_STATS, ST_GEMM_PW_FWD, ST_ACT_POOL, ST_GEMM_HEAD_FWD, ST_RNN_FWD, ST_SOFTMAX, ST_CTC,
              ST_GEMM_HEAD_BWD, ST_RNN_BWD, ST_ACT_BWD, ST_BN_BWD, ST_GEMM_PW_DW, ST_GEMM_PW_DX, ST_DWCONV_BWD, ST_STN_BWD,
              ST_OPTIM, ST_MISC, ST_COUNT };
+const char* kFamilyNames[CRNN_FAM_COUNT] = {"(other)", "xw_gemm_tc_v2_kernel", "xty_gemm_tc_kernel", "gru/lstm_{fwd,bwd}_mma_kernel", "dwconv3x3_rows_*"};
 const char* kStageNames[ST_COUNT] = {"stn_fwd", "dwconv_fwd", "bn_stats", "gemm_pw_fwd", "act_pool_fwd", "gemm_head_fwd", "rnn_fwd", "softmax",
                                      "ctc_loss_grad", "gemm_head_bwd", "rnn_bwd", "act_pool_bwd", "bn_bwd", "gemm_pw_dw", "gemm_pw_dx",
                                      "dwconv_bwd", "stn_bwd", "optimizer", "misc"};
 struct Prof {
     bool on = false;
-    struct Rec { int stage; cudaEvent_t a, b; double work; long long launches; };
+    struct Rec { int stage, fam; cudaEvent_t a, b; double work; long long launches; };
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
@@ -123,12 +125,12 @@ struct Scope {   // records a [start, stop] event pair around a stage when profi
     crnn_handle* h; cudaStream_t st; int idx = -1; long long l0;
     Scope(crnn_handle* h_, cudaStream_t st_, int stage, double work) : h(h_), st(st_) {
         if (!h->prof.on) return;
-        Prof::Rec r; r.stage = stage; r.a = h->prof.ev(); r.b = h->prof.ev(); r.work = work; r.launches = 0;
-        l0 = g_crnn_launches;
+        Prof::Rec r; r.stage = stage; r.fam = CRNN_FAM_OTHER; r.a = h->prof.ev(); r.b = h->prof.ev(); r.work = work; r.launches = 0;
+        l0 = g_crnn_launches; g_crnn_family = CRNN_FAM_OTHER;
         cudaEventRecord(r.a, st);
         idx = (int)h->prof.recs.size(); h->prof.recs.push_back(r);
     }
-    ~Scope() { if (idx >= 0) { cudaEventRecord(h->prof.recs[idx].b, st); h->prof.recs[idx].launches = g_crnn_launches - l0; } }
+    ~Scope() { if (idx >= 0) { cudaEventRecord(h->prof.recs[idx].b, st); h->prof.recs[idx].launches = g_crnn_launches - l0; h->prof.recs[idx].fam = g_crnn_family; } }
 };
 #define ST(stage, work, call) do { Scope _s(h, st, stage, (double)(work)); int _r = (call); if (_r != CRNN_OK) return _r; } while (0)
 
@@ -984,13 +986,24 @@ int crnn_profile_num_stages(void) { return ST_COUNT; }
 const char* crnn_profile_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : nullptr; }
 // synchronises the device, aggregates the event pairs recorded since the last enable/report, then clears them
 int crnn_profile_report(crnn_handle* h, double* ms, double* work, long long* launches) {
+    return crnn_profile_report2(h, ms, work, launches, nullptr, nullptr, nullptr);
+}
+int crnn_profile_num_families(void) { return CRNN_FAM_COUNT; }
+const char* crnn_profile_family_name(int fam) { return (fam >= 0 && fam < CRNN_FAM_COUNT) ? kFamilyNames[fam] : nullptr; }
+// per stage AND per (stage, kernel family): fam_* are [num_stages * num_families] row-major (stage, family); family 0 = kernels not tracked
+int crnn_profile_report2(crnn_handle* h, double* ms, double* work, long long* launches, double* fam_ms, double* fam_work, long long* fam_launches) {
     if (!h || !ms || !work || !launches) return CRNN_ERR_INVALID;
     CUDA_TRY(cudaDeviceSynchronize());
     for (int i = 0; i < ST_COUNT; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+    if (fam_ms) for (int i = 0; i < ST_COUNT * CRNN_FAM_COUNT; ++i) { fam_ms[i] = 0; if (fam_work) fam_work[i] = 0; if (fam_launches) fam_launches[i] = 0; }
     for (auto& r : h->prof.recs) {
         float t = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
         ms[r.stage] += t; work[r.stage] += r.work; launches[r.stage] += r.launches;
+        if (fam_ms) {
+            const int k = r.stage * CRNN_FAM_COUNT + r.fam;
+            fam_ms[k] += t; if (fam_work) fam_work[k] += r.work; if (fam_launches) fam_launches[k] += r.launches;
+        }
     }
     h->prof.recs.clear(); h->prof.used = 0;
     return CRNN_OK;

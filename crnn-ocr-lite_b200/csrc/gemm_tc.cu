@@ -785,6 +785,7 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
                       const float* x_scale, const float* x_shift, double* stats, cudaStream_t st,
                       const float* bias, int relu, int accumulate, int rev, int ksplit, long long split_stride, const TcBnRed* red)
 {
+    g_crnn_family = CRNN_FAM_XW_TC;
     if (M <= 0 || N <= 0) return CRNN_OK;
     if (K % TC_BK || K <= 0) { crnn_set_error("gemm_tc: K=%d must be a positive multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
     if ((ldx % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(Wimg) & 15)) { crnn_set_error("gemm_tc: X/Wimg must be 16-byte aligned, ldx %% 4 == 0"); return CRNN_ERR_INVALID; }
@@ -848,6 +849,7 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
 int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
                        const float* x_scale, const float* x_shift, cudaStream_t st)
 {
+    g_crnn_family = CRNN_FAM_XTY_TC;
     if (M <= 0 || Cin <= 0 || Cout <= 0) return CRNN_OK;
     if ((Cin % 4) || (Cout % 4) || (ldx % 4) || (ldy % 4) || (reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(dY) & 15)) {
         crnn_set_error("gemm_tc dW: channels / leading dims must be multiples of 4 and pointers 16-byte aligned"); return CRNN_ERR_INVALID;

@@ -681,6 +681,7 @@ lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs
 
 int launch_gru_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st)
 {
+    g_crnn_family = CRNN_FAM_RNN_MMA;
     if (B <= 0) return CRNN_OK;
     const size_t smem = sizeof(float) * FWD_SMEM_FLOATS;
     static bool configured = false;
@@ -694,6 +695,7 @@ int launch_gru_fwd_mma(const float* xp, const float* U0, const float* U1, float*
 int launch_gru_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
                        float* dxp, float* hprev, float* rh, int B, int T, cudaStream_t st)
 {
+    g_crnn_family = CRNN_FAM_RNN_MMA;
     if (B <= 0) return CRNN_OK;
     const size_t smem = sizeof(float) * BWD_SMEM_FLOATS;
     static bool configured = false;
@@ -706,6 +708,7 @@ int launch_gru_bwd_mma(const float* dout, const float* hs, const float* gates, c
 
 int launch_lstm_fwd_mma(const float* xp, const float* U0, const float* U1, float* hs, float* gates, int B, int T, cudaStream_t st)
 {
+    g_crnn_family = CRNN_FAM_RNN_MMA;
     if (B <= 0) return CRNN_OK;
     static bool configured = false;
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(lstm_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES)); configured = true; }
@@ -718,6 +721,7 @@ int launch_lstm_fwd_mma(const float* xp, const float* U0, const float* U1, float
 int launch_lstm_bwd_mma(const float* dout, const float* hs, const float* gates, const float* U0, const float* U1,
                         float* dxp, float* hprev, int B, int T, cudaStream_t st)
 {
+    g_crnn_family = CRNN_FAM_RNN_MMA;
     if (B <= 0) return CRNN_OK;
     static bool configured = false;
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM_BYTES)); configured = true; }

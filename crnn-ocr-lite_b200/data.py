@@ -105,10 +105,20 @@ def _file_image_size(name):
             if head[:2] == b"\xff\xd8":
                 f.seek(2)
                 while True:
-                    b = f.read(4)
-                    if len(b) < 4 or b[0] != 0xFF:
+                    b = f.read(1)
+                    if len(b) < 1 or b[0] != 0xFF:
                         break
-                    marker, seglen = b[1], struct.unpack(">H", b[2:4])[0]
+                    m = f.read(1)
+                    while m == b"\xff":                      # fill bytes before a marker
+                        m = f.read(1)
+                    if len(m) < 1:
+                        break
+                    if m[0] == 0x01 or 0xD0 <= m[0] <= 0xD7:   # stand-alone markers (TEM, RSTn) carry no length
+                        continue
+                    ln = f.read(2)
+                    if len(ln) < 2:
+                        break
+                    marker, seglen = m[0], struct.unpack(">H", ln)[0]
                     if marker == 0xE1:                       # APP1 (EXIF): let PIL decide the orientation
                         break
                     if 0xC0 <= marker <= 0xCF and marker not in (0xC4, 0xC8, 0xCC):
@@ -253,7 +263,11 @@ class Readf:
             for job, crop in zip(jobs, res.get()):
                 if crop is None:        # header and decoder disagreed on the size (never seen on mjsynth / IAM): do it here with the same decisions
                     img, fill, _ = _open_load(job[0], self.img_size)
-                    w_dec, h_dec = _placement_draws(img.shape, self.img_size, 0.)   # decisions already drawn for a wrong shape: default placement
+                    # the decisions were drawn for a wrong shape: default placement, built WITHOUT touching np.random (the stream must stay
+                    # exactly where the sequential generator would have it, or every later crop differs -- ADVICE r1)
+                    H_, W_ = int(self.img_size[0]), int(self.img_size[1])
+                    w_dec = ("default",) if W_ - img.shape[1] > 2 else None
+                    h_dec = ("default",) if H_ - img.shape[0] > 2 else None
                     crop = _open_finish(_apply_placement(img, fill, self.img_size, w_dec, h_dec), self.img_size)
                 yield crop, _label_of(job[0])
 

@@ -475,13 +475,20 @@ def keras_adam_weight_names(n_trainable):
     return ["Adam/iterations:0"] + [var(k) for k in range(3 * n_trainable)]
 
 
-def save_keras_model(path, layers, adam=None, root_attrs=None):
+def keras_sgd_weight_names(n_trainable):
+    """Names Keras 2.2.2 gives the SGD slots (`SGD.weights = [iterations] + moments`): iterations, then one velocity per trainable weight."""
+    var = lambda k: "training/SGD/Variable:0" if k == 0 else "training/SGD/Variable_%d:0" % k
+    return ["SGD/iterations:0"] + [var(k) for k in range(n_trainable)]
+
+
+def save_keras_model(path, layers, adam=None, root_attrs=None, sgd=None):
     """Write `final_model.h5` with the layout of the reference's files (models/*/final_model.h5): root attrs keras_version / backend /
     model_config / training_config; /model_weights = what save_keras_weights writes at the root; /optimizer_weights with attr
     weight_names = [Adam/iterations:0, training/Adam/Variable:0 ...] in Keras' order (m of every trainable weight in layer/weight order,
     then v, then one zero of shape (1,) per weight for the unused amsgrad slot), iterations as an int64 scalar.
 
-    layers: as for save_keras_weights.  adam: None or (iterations, [m arrays], [v arrays]) in trainable-weight order."""
+    layers: as for save_keras_weights.  adam: None or (iterations, [m arrays], [v arrays]) in trainable-weight order;
+    sgd: None or (iterations, [velocity arrays]) -- the reference's default optimiser (train.py:190), slots named as Keras' SGD names them."""
     w = _Writer()
     top = []
     for lname, weights in layers.items():
@@ -497,6 +504,12 @@ def save_keras_model(path, layers, adam=None, root_attrs=None):
         names = keras_adam_weight_names(len(ms))
         arrays = [np.asarray(int(it), np.int64)] + [np.asarray(a, np.float32) for a in ms] + [np.asarray(a, np.float32) for a in vs] + \
                  [np.zeros((1,), np.float32) for _ in ms]
+        ents = _emit_tree(w, OrderedDict(zip(names, arrays)))
+        root_entries.append(("optimizer_weights", w.write_group(ents, [w.attr_strings("weight_names", names)])[0]))
+    elif sgd is not None:
+        it, vel = sgd
+        names = keras_sgd_weight_names(len(vel))
+        arrays = [np.asarray(int(it), np.int64)] + [np.asarray(a, np.float32) for a in vel]
         ents = _emit_tree(w, OrderedDict(zip(names, arrays)))
         root_entries.append(("optimizer_weights", w.write_group(ents, [w.attr_strings("weight_names", names)])[0]))
     attrs = [w.attr_scalar_string("keras_version", "2.2.2"), w.attr_scalar_string("backend", "tensorflow")]

@@ -79,7 +79,14 @@ def keras_initial_weights(shapes, cell, n_units=256, seed=None):
             else:
                 fan_in, fan_out = shp
             if name.startswith("bidirectional") or name.startswith("dense2"):   # he_normal (utils.py:78-85)
-                a = np.clip(rng.standard_normal(shp), -2, 2) * (math.sqrt(2.0 / fan_in) / 0.87962566103423978)
+                # Keras 2.2.2 VarianceScaling(scale=2, fan_in, 'normal') = K.truncated_normal(stddev=sqrt(2/fan_in)): TF re-draws every
+                # sample beyond 2 stddev (no clipping), and 2.2.2 predates the 1/0.8796 stddev correction of later Keras releases
+                a = rng.standard_normal(shp)
+                out = np.abs(a) > 2
+                while out.any():
+                    a[out] = rng.standard_normal(int(out.sum()))
+                    out = np.abs(a) > 2
+                a = a * math.sqrt(2.0 / fan_in)
             else:                                                                 # glorot_uniform
                 lim = math.sqrt(6.0 / (fan_in + fan_out))
                 a = rng.uniform(-lim, lim, shp)
@@ -200,31 +207,18 @@ class CRNNModel:
         hdf5_lite.save_keras_weights(path, self._keras_layers())
 
     def save(self, path):
-        """model.save (train.py:216): weights + optimizer moments + training_config in one file, laid out like the reference's
-        models/*/final_model.h5 (/model_weights, /optimizer_weights with Keras' Adam slot names and order; hdf5_lite.save_keras_model)."""
-        extra = {"training_config": json.dumps(self._training_config()), "model_config": self.to_json()}
-        try:
-            adam = None
-            if self.optimizer is not None and self.optimizer.kind == "adam":
-                tr = [(n, s) for n, s in self.shapes.items() if not n.endswith(("moving_mean", "moving_variance"))]
-                adam = (int(self.iterations()), [self.tensor("adam_m/" + n).cpu().numpy().reshape(s) for n, s in tr],
-                        [self.tensor("adam_v/" + n).cpu().numpy().reshape(s) for n, s in tr])
-            hdf5_lite.save_keras_model(path, self._keras_layers(), adam=adam, root_attrs=extra)
-            return
-        except Exception as e:   # keep train.py's last step alive whatever happens: fall back to the flat layout below
-            import warnings
-            warnings.warn("save(): Keras-layout writer failed (%r), writing the flat layout" % (e,), RuntimeWarning)
-        layers = self._keras_layers()
+        """model.save (train.py:216): weights + optimizer slots + training_config in one file, laid out like the reference's
+        models/*/final_model.h5 (/model_weights, /optimizer_weights with Keras' slot names and order; hdf5_lite.save_keras_model), root
+        attribute `model_config` = the Keras-2.2.2 model JSON (to_json).  Errors propagate: there is no second layout to fall back to."""
+        extra = {"model_config": self.to_json(), "training_config": json.dumps(self._training_config())}
+        tr = [(n, s) for n, s in self.shapes.items() if not n.endswith(("moving_mean", "moving_variance"))]
+        adam = sgd = None
         if self.optimizer is not None and self.optimizer.kind == "adam":
-            opt = OrderedDict()
-            opt["Adam/iterations:0"] = np.array([self.iterations()], np.float32)
-            for n, s in self.shapes.items():
-                if n.endswith(("moving_mean", "moving_variance")):
-                    continue
-                opt[f"training/Adam/m/{n}:0"] = self.tensor("adam_m/" + n).cpu().numpy().reshape(s)
-                opt[f"training/Adam/v/{n}:0"] = self.tensor("adam_v/" + n).cpu().numpy().reshape(s)
-            layers["optimizer_weights"] = opt
-        hdf5_lite.save_keras_weights(path, layers, extra_root_attrs=extra)
+            adam = (int(self.iterations()), [self.tensor("adam_m/" + n).cpu().numpy().reshape(s) for n, s in tr],
+                    [self.tensor("adam_v/" + n).cpu().numpy().reshape(s) for n, s in tr])
+        elif self.optimizer is not None and self.optimizer.kind == "sgd":      # the velocities live in the first optimiser arena
+            sgd = (int(self.iterations()), [self.tensor("adam_m/" + n).cpu().numpy().reshape(s) for n, s in tr])
+        hdf5_lite.save_keras_model(path, self._keras_layers(), adam=adam, sgd=sgd, root_attrs=extra)
 
     def load_optimizer_state(self, path):
         """Resume Adam from a Keras-2.2.2 `final_model.h5` (the reference's own files or ours): iterations and the m / v slots of every
@@ -237,17 +231,24 @@ class CRNNModel:
         return it
 
     def _training_config(self):
+        """`training_config` attribute as Keras 2.2.2 `model.save` writes it (models/*/final_model.h5)."""
         o = self.optimizer
         if o is None:
             return {}
-        cfgd = {k: v for k, v in vars(o).items() if k != "kind"}
-        return {"optimizer_config": {"class_name": "Adam" if o.kind == "adam" else "SGD", "config": cfgd}, "loss": {"ctc": "lambda"}}
+        f32 = lambda v: float(np.float32(v))            # Keras stores the float32 value of its backend variables
+        if o.kind == "adam":
+            oc = OrderedDict([("clipnorm", o.clipnorm), ("lr", f32(o.lr)), ("beta_1", f32(o.beta_1)), ("beta_2", f32(o.beta_2)), ("decay", 0.0),
+                              ("epsilon", o.epsilon), ("amsgrad", False)])
+        else:
+            oc = OrderedDict([("clipnorm", o.clipnorm), ("lr", f32(o.lr)), ("momentum", f32(o.momentum)), ("decay", f32(o.decay)), ("nesterov", True)])
+        return OrderedDict([("optimizer_config", OrderedDict([("class_name", "Adam" if o.kind == "adam" else "SGD"), ("config", oc)])),
+                            ("loss", {"ctc": "<lambda>"}), ("metrics", []), ("sample_weight_mode", None), ("loss_weights", None)])
 
     def to_json(self):
-        return json.dumps({"class_name": "Model", "keras_version": "2.2.2", "backend": "crnn_b200",
-                           "config": {"name": "crnn_b200", "num_classes": self.num_classes, "max_string_len": self.max_len,
-                                      "shape": [self.imgh, self.imgw, 1], "time_dense_size": self.time_dense,
-                                      "GRU": self.cell == "gru", "n_units": self.n_units}})
+        """Keras-2.2.2 functional-model JSON of this graph: byte-identical to the reference's models/*/model.json for the same
+        hyper-parameters (keras_json.py), so directories written by either side load on the other."""
+        from . import keras_json
+        return json.dumps(keras_json.keras_model_config(self.imgh, self.imgw, self.num_classes, self.max_len, self.time_dense, self.n_units, self.cell))
 
     def summary(self, print_fn=print):
         tot = sum(int(np.prod(s)) for s in self.shapes.values())

@@ -161,6 +161,11 @@ int crnn_profile_enable(crnn_handle* h, int on);
 int crnn_profile_num_stages(void);
 const char* crnn_profile_stage_name(int stage);
 int crnn_profile_report(crnn_handle* h, double* ms, double* work, long long* launches);
+/* the same records broken down by kernel family as well (one kernel, e.g. xw_gemm_tc_v2_kernel, serves several stages): fam_* arrays are
+ * [num_stages * num_families], row-major (stage, family); family 0 collects the kernels that are not tracked individually */
+int crnn_profile_num_families(void);
+const char* crnn_profile_family_name(int family);
+int crnn_profile_report2(crnn_handle* h, double* ms, double* work, long long* launches, double* fam_ms, double* fam_work, long long* fam_launches);
 
 #ifdef __cplusplus
 }

@@ -408,3 +408,39 @@ def test_parallel_loader_size_probe(cb, tmp_path):
             assert D._file_image_size(p) == (dec[1], dec[0]), p
             gray = cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2GRAY)
             assert D._shape_after_load(p, (100, 32, 1)) == D._open_load(p, (100, 32, 1))[0].shape
+
+
+def test_to_json_is_the_reference_model_json(cb):
+    """CRNNModel.to_json() (keras_json.keras_model_config) for the shipped hyper-parameters is byte-identical to the reference's own
+    models/OCR_mjsynth_FULL_2/model.json (utils.py:530-533; fixture copied verbatim), and the loader recovers the hyper-parameters from
+    it for both cells -- directories written by either side load on the other (VERDICT r1 item 5 / ADVICE train.py:4)."""
+    import json
+    from crnn_ocr_lite_b200 import loader
+    want = open(os.path.join(os.path.dirname(__file__), "golden", "reference_mjsynth_model.json")).read()
+    got = json.dumps(cb.keras_json.keras_model_config(100, 32, 38, 23, 128, 256, "gru"))
+    assert got == want
+    for cell, imgh, V, ml in (("gru", 100, 38, 23), ("lstm", 128, 97, 17)):
+        cfg = loader._config_from_json(json.dumps(cb.keras_json.keras_model_config(imgh, 32, V, ml, 128, 256, cell)))
+        assert cfg == dict(max_string_len=ml, time_dense_size=128, n_units=256, GRU=(cell == "gru"), num_classes=V, shape=(imgh, 32, 1))
+    lstm = cb.keras_json.keras_model_config(100, 32, 38, 23, cell="lstm")["config"]["layers"]
+    cellcfg = [l for l in lstm if l["name"] == "bidirectional_2"][0]["config"]["layer"]
+    assert cellcfg["class_name"] == "LSTM" and cellcfg["config"]["unit_forget_bias"] is True and "reset_after" not in cellcfg["config"]
+
+
+def test_full_model_file_with_sgd_slots(cb, tmp_path):
+    """model.save with the reference's default optimiser (train.py:190): /optimizer_weights carries SGD/iterations:0 + one velocity per
+    trainable weight under Keras' names; the file re-reads bit-exactly."""
+    h5 = cb.hdf5_lite
+    rng = np.random.default_rng(0)
+    layers = {"dense_1": {"dense_1/kernel:0": rng.standard_normal((7, 5)).astype(np.float32), "dense_1/bias:0": rng.standard_normal(5).astype(np.float32)},
+              "batch_normalization_1": {"batch_normalization_1/gamma:0": np.ones(3, np.float32), "batch_normalization_1/moving_mean:0": np.zeros(3, np.float32)}}
+    vel = [rng.standard_normal((7, 5)).astype(np.float32), rng.standard_normal(5).astype(np.float32), rng.standard_normal(3).astype(np.float32)]
+    out = str(tmp_path / "m.h5")
+    h5.save_keras_model(out, layers, sgd=(12, vel), root_attrs={"training_config": "{}", "model_config": "{}"})
+    root = h5.read_h5(out)
+    ow = root["optimizer_weights"]
+    names = list(ow.attrs["weight_names"])
+    assert names == ["SGD/iterations:0", "training/SGD/Variable:0", "training/SGD/Variable_1:0", "training/SGD/Variable_2:0"]
+    assert int(np.asarray(ow[names[0]]).reshape(-1)[0]) == 12
+    for n, v in zip(names[1:], vel):
+        np.testing.assert_array_equal(np.asarray(ow[n]), v)
