@@ -72,6 +72,8 @@ def workload_config(args, world):
                         "batch %d per GPU, 128x32 gray, V=38, fp32, random-init, dropout on" % (cfgname, args.cell.upper(), pb),
             "global_batch": pb * world, "per_gpu_batch": pb, "imgh": IMGH, "imgw": IMGW, "num_classes": V, "cell": args.cell,
             "parallelism": "dp%d" % world,
+            "gradient_exchange": ("none (1 GPU)" if world == 1 else "2-bucket NCCL all-reduce issued by the step itself (head bucket overlapped with the conv-stack backward), "
+                                  "or one torch.distributed all-reduce after the step when CRNN_DP_NATIVE=0"),
             "l2": "per-step working set (~2.5 GB of activations/gradients rewritten every step) >> 126 MB L2; no explicit flush"}
 
 
@@ -230,8 +232,10 @@ def run_ours(args):
     PB = per_gpu_batch(args, world)                          # images per GPU per step (64; 512 / N with --scaling strong)
     model = cb.CRNN(V, MAXLEN, (IMGH, IMGW, 1), 128, args.cell == "gru", 256, max_batch=PB, seed=1234).get_model()
     model.compile(optimizer=cb.Adam(lr=1e-4, beta_1=0.5, beta_2=0.999, epsilon=1e-7, clipnorm=5.0))
-    if world > 1:   # identical replicas
+    dp_mode = None
+    if world > 1:   # identical replicas; the engine's own NCCL communicator reduces the gradients inside the step (CRNN_DP_NATIVE=0: torch.distributed)
         dist.broadcast(model.tensor("arena/params"), src=0)
+        dp_mode = model.enable_native_dp()
     x, lab, L, il = synth_batch(PB, 2 + rank)
     x_u8 = synth_batch.last_u8
     xd, labd, Ld, ild = (torch.tensor(a, device=dev) for a in (x, lab, L, il))
@@ -311,6 +315,7 @@ def run_ours(args):
             ms_model = cb.CRNN(V, MAXLEN, (IMGH, IMGW, 1), 128, args.cell == "gru", 256, max_batch=sb, seed=1234).get_model()
             ms_model.compile(optimizer=cb.Adam(lr=1e-4, beta_1=0.5, beta_2=0.999, epsilon=1e-7, clipnorm=5.0))
             dist.broadcast(ms_model.tensor("arena/params"), src=0)
+            ms_model.enable_native_dp()
             sx, slab, sL, sil = synth_batch(sb, 1000 + rank)
             sargs = [torch.tensor(a_, device=dev) for a_ in (sx, slab, sL, sil)]
 
@@ -339,7 +344,9 @@ def run_ours(args):
     if world == 1:
         for _ in range(nprof):
             step_device()
-    else:   # keep the collective pattern of the other ranks untouched: profile forward/backward only
+    else:   # the other ranks are done: profile forward/backward only, without the in-step gradient exchange (nobody would answer it)
+        if dp_mode == "fused":
+            cb._lib.check(lib.crnn_set_dp_fused(model.handle, 0))
         for _ in range(nprof):
             model.train_fwd_bwd_device(xd, labd, Ld, ild, dropout_seed=seed_base)
     nf = lib.crnn_profile_num_families()
@@ -490,7 +497,7 @@ def run_ours(args):
                     "api": "CRNNModel.train_on_batch(host numpy dict) == Keras train_on_batch (train.py:201-209)",
                     "uint8_input": {"value": e2e_u8_val, "h2d_bytes_per_step": int(x_u8.nbytes + lab.nbytes + L.nbytes + il.nbytes),
                                     "note": "same call with 'the_input' as the raw 8-bit images; utils.py:415 norm() runs on the device (crnn_normalize_u8)"}},
-            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "dp_mode": dp_mode,
             "roofline": roof, "step_level": step_level, "configs4_strong": strong, "cpu_baseline": cpu, "beam_decode": beam, "extra": extra,
             "kernels_top": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in e.items()} for e in klist[:8]],
             "stages_top": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.items()} for s in stages[:8]]}

@@ -2,6 +2,7 @@
 // (include/crnn_b200.h).  Mirrors CRNN.get_model (reference utils.py:58-96): STN -> ZeroPadding2D -> 7 depthwise-
 // separable blocks -> dense1 -> 2 x Bidirectional GRU/LSTM -> dense2 -> softmax -> CTC (utils.py:98-103), the full
 // backward of that graph and the Keras optimiser step (train.py:187-192).
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -70,6 +71,39 @@ struct Layout {
 };
 }  // namespace
 
+// ---- NCCL, bound at run time (no link-time dependency: single-GPU users never load it).  Only the handful of entry points the data-parallel
+// step needs; the ABI constants (ncclUniqueId = 128 bytes, ncclFloat32 = 7, ncclSum = 0, ncclSuccess = 0) are stable across NCCL 2.x.
+struct crnn_nccl_id { char internal[128]; };      // ncclUniqueId (passed by value to ncclCommInitRank)
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, crnn_nccl_id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_api() {
+    if (g_nccl.lib) return CRNN_OK;
+    // prefer the instance that is already in the process (PyTorch loads its bundled libnccl.so.2): one NCCL per process
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { crnn_set_error("NCCL not found: dlopen(libnccl.so.2) failed (%s)", dlerror()); return CRNN_ERR_INVALID; }
+    NcclApi a; a.lib = lib;
+    *(void**)&a.GetUniqueId = dlsym(lib, "ncclGetUniqueId");
+    *(void**)&a.CommInitRank = dlsym(lib, "ncclCommInitRank");
+    *(void**)&a.CommDestroy = dlsym(lib, "ncclCommDestroy");
+    *(void**)&a.AllReduce = dlsym(lib, "ncclAllReduce");
+    *(void**)&a.GetErrorString = dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce) { crnn_set_error("libnccl lacks a required symbol"); return CRNN_ERR_INVALID; }
+    g_nccl = a;
+    return CRNN_OK;
+}
+#define NCCL_TRY(expr) do { int _r = (expr); if (_r != 0) { crnn_set_error("%s:%d: %s -> NCCL error %d (%s)", __FILE__, __LINE__, #expr, _r, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); return CRNN_ERR_CUDA; } } while (0)
+}  // namespace
+
 struct crnn_handle {
     crnn_config cfg;
     char* base = nullptr;
@@ -94,6 +128,13 @@ struct crnn_handle {
                     // one starts on the bytes its producer touched last (still in the 126 MB L2) -- CRNN_SERPENTINE=0 disables
     int rv() { const int r = serp ? flip : 0; flip ^= 1; return r; }
     cudaStream_t side = nullptr, cap = nullptr;
+    // ---- data parallel (NEW capability): NCCL communicator (owned when created by crnn_comm_init_rank, else borrowed) and the
+    // stream its all-reduces run on.  With `dp_fused` the training step itself issues the exchange, in two buckets: the head gradients
+    // (dense1 .. dense2 = the tail of the arena, ~70 % of the bytes) as soon as their weight-gradient GEMMs are done, overlapping the whole
+    // conv-stack backward; the conv-stack + STN bucket at the end of the step.
+    void* comm = nullptr; bool comm_owned = false; int comm_ranks = 1; bool dp_fused = false;
+    cudaStream_t comm_stream = nullptr;
+    int64_t head_off = 0;     // first float of dense1/kernel inside the arenas
     std::vector<cudaEvent_t> evs; size_t ev_used = 0;
     const uint64_t* seed_ptr = nullptr;   // non-null while capturing: dropout kernels read the seed from device memory
     struct StepGraph { int kind, B; const void* p[6]; int drop; int calls; cudaGraphExec_t exec; long long launches; };
@@ -149,6 +190,34 @@ void side_join(crnn_handle* h, cudaStream_t st) {
     cudaEventRecord(e, h->side); cudaStreamWaitEvent(st, e, 0);
 }
 
+// ---- data-parallel exchange inside the step (dp_fused): sum all-reduce of arena/grads[off, off + n) on stream s
+int dp_allreduce(crnn_handle* h, int64_t off, int64_t n, cudaStream_t s) {
+    if (n <= 0) return CRNN_OK;
+    float* g = h->f("arena/grads") + off;
+    NCCL_TRY(g_nccl.AllReduce(g, g, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, s));
+    return CRNN_OK;
+}
+// head bucket (dense1 .. dense2): everything that writes it was issued on the side branch before this call; the reduce runs on the comm
+// stream, concurrently with the conv-stack backward that follows on `st` (and its weight-gradient kernels on the side branch)
+int dp_reduce_head(crnn_handle* h, cudaStream_t st) {
+    if (!h->dp_fused || !h->comm) return CRNN_OK;
+    const bool branch = h->overlap && !h->prof.on && h->side && h->comm_stream;
+    if (!branch) return dp_allreduce(h, h->head_off, h->n_params - h->head_off, st);
+    cudaEvent_t e = h->ev();
+    cudaEventRecord(e, h->side); cudaStreamWaitEvent(h->comm_stream, e, 0);
+    return dp_allreduce(h, h->head_off, h->n_params - h->head_off, h->comm_stream);
+}
+// conv-stack + STN bucket at the end of the backward pass (after the side branch has been joined), then join the comm stream
+int dp_reduce_tail(crnn_handle* h, cudaStream_t st) {
+    if (!h->dp_fused || !h->comm) return CRNN_OK;
+    TRY(dp_allreduce(h, 0, h->head_off, st));
+    if (h->overlap && !h->prof.on && h->side && h->comm_stream) {
+        cudaEvent_t e = h->ev();
+        cudaEventRecord(e, h->comm_stream); cudaStreamWaitEvent(st, e, 0);
+    }
+    return CRNN_OK;
+}
+
 int validate(const crnn_config* c) {
     if (!c) { crnn_set_error("null config"); return CRNN_ERR_INVALID; }
     if (c->imgw != 32) { crnn_set_error("imgW must be 32 (the conv stack reduces it to 9 columns)"); return CRNN_ERR_INVALID; }
@@ -202,7 +271,7 @@ void plan(crnn_handle* h) {
     // arenas: every weight padded to a multiple of 4 floats so that all tensors stay 16-byte aligned
     int64_t n = 0;
     std::vector<int64_t> offs;
-    for (auto& p : h->weights) { offs.push_back(n); n += (p.second + 3) & ~(int64_t)3; }
+    for (auto& p : h->weights) { if (p.first == "dense1/kernel") h->head_off = n; offs.push_back(n); n += (p.second + 3) & ~(int64_t)3; }
     h->n_params = n;
     const char* arenas[4] = {"arena/params", "arena/grads", "arena/opt_m", "arena/opt_v"};
     const char* prefix[4] = {"", "grad/", "adam_m/", "adam_v/"};
@@ -619,6 +688,7 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
         else TRY(gemm_tn(h, ST_GEMM_HEAD_BWD, h->a("block7"), h->FEAT, dd, h->TD, h->g("dense1/kernel"), h->TD, h->FEAT, h->TD, M, nullptr, nullptr, ss));
         ST(ST_MISC, 0, launch_colsum(dd, M, h->TD, h->TD, h->g("dense1/bias"), ss));
     }
+    TRY(dp_reduce_head(h, st));                                          // data parallel: the head gradients are complete on the side branch
     if (tc_ok(h, h->FEAT, h->TD)) TRY(tc_xw(h, ST_GEMM_HEAD_BWD, dd, h->TD, h->a("wimg_d1b"), gA, h->FEAT, M, h->FEAT, h->TD, nullptr, 0, 0, st));
     else TRY(gemm_nt(h, ST_GEMM_HEAD_BWD, dd, h->TD, h->w("dense1/kernel"), h->TD, gA, h->FEAT, M, h->FEAT, h->TD, 0, st));
     // ---- conv stack, reverse
@@ -657,6 +727,7 @@ int backward(crnn_handle* h, const float* x, const int* labels, const int* label
     ST(ST_STN_BWD, 0, launch_stn_trunk_bwd(h->a("dflat"), h->a("p1"), h->a("p2"), reinterpret_cast<const int*>(h->a("p2arg")), h->w("conv2d_2/kernel"),
                              h->g("conv2d_1/kernel"), h->g("conv2d_1/bias"), h->g("conv2d_2/kernel"), h->g("conv2d_2/bias"), nullptr, B, h->H, h->W, st));
     side_join(h, st);
+    TRY(dp_reduce_tail(h, st));                                          // data parallel: conv-stack + STN bucket, then wait for the head bucket
     return CRNN_OK;
 }
 
@@ -743,6 +814,8 @@ int crnn_destroy(crnn_handle* h) {
     for (auto e : h->prof.pool) cudaEventDestroy(e);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->cap) cudaStreamDestroy(h->cap);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     delete h;
     return CRNN_OK;
 }
@@ -818,6 +891,57 @@ int crnn_sgd_step(crnn_handle* h, float lr, float decay, float momentum, float c
     h->iterations += 1;
     return CRNN_OK;
 }
+// ---------------------------------------------------------------- data parallel (NEW capability; the reference is single-device, train.py:111,116)
+static void drop_graphs(crnn_handle* h) {
+    for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+    h->graphs.clear();
+}
+int crnn_nccl_unique_id(void* id128_out) {
+    if (!id128_out) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    TRY(nccl_api());
+    NCCL_TRY(g_nccl.GetUniqueId(id128_out));
+    return CRNN_OK;
+}
+int crnn_comm_init_rank(crnn_handle* h, const void* id128, int nranks, int rank) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { crnn_set_error("bad argument"); return CRNN_ERR_INVALID; }
+    TRY(nccl_api());
+    if (h->comm && h->comm_owned) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    crnn_nccl_id id; memcpy(&id, id128, sizeof(id));
+    void* comm = nullptr;
+    NCCL_TRY(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    h->comm = comm; h->comm_owned = true; h->comm_ranks = nranks;
+    if (!h->comm_stream && cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess) { h->comm_stream = nullptr; cudaGetLastError(); }
+    drop_graphs(h);
+    return CRNN_OK;
+}
+int crnn_set_comm(crnn_handle* h, void* nccl_comm, int nranks) {
+    if (!h || nranks < 1) { crnn_set_error("bad argument"); return CRNN_ERR_INVALID; }
+    if (nccl_comm) TRY(nccl_api());
+    if (h->comm && h->comm_owned) g_nccl.CommDestroy(h->comm);
+    h->comm = nccl_comm; h->comm_owned = false; h->comm_ranks = nccl_comm ? nranks : 1;
+    if (nccl_comm && !h->comm_stream && cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess) { h->comm_stream = nullptr; cudaGetLastError(); }
+    if (!nccl_comm) h->dp_fused = false;
+    drop_graphs(h);
+    return CRNN_OK;
+}
+int crnn_set_dp_fused(crnn_handle* h, int on) {
+    if (!h) { crnn_set_error("null handle"); return CRNN_ERR_INVALID; }
+    if (on && !h->comm) { crnn_set_error("crnn_set_dp_fused: no communicator (crnn_comm_init_rank / crnn_set_comm first)"); return CRNN_ERR_INVALID; }
+    h->dp_fused = on != 0;
+    drop_graphs(h);
+    return CRNN_OK;
+}
+int crnn_comm_ranks(const crnn_handle* h) { return (h && h->comm) ? h->comm_ranks : 1; }
+int crnn_allreduce_grads(crnn_handle* h, void* nccl_comm, void* stream) {
+    if (!h) { crnn_set_error("null handle"); return CRNN_ERR_INVALID; }
+    void* comm = nccl_comm ? nccl_comm : h->comm;
+    if (!comm) { crnn_set_error("crnn_allreduce_grads: no communicator"); return CRNN_ERR_INVALID; }
+    TRY(nccl_api());
+    float* g = h->f("arena/grads");
+    NCCL_TRY(g_nccl.AllReduce(g, g, (size_t)h->n_params, 7, 0, comm, static_cast<cudaStream_t>(stream)));
+    return CRNN_OK;
+}
+
 int crnn_get_iterations(const crnn_handle* h, int64_t* it) { if (!h || !it) return CRNN_ERR_INVALID; *it = h->iterations; return CRNN_OK; }
 int crnn_set_iterations(crnn_handle* h, int64_t it) { if (!h) return CRNN_ERR_INVALID; h->iterations = it; return CRNN_OK; }
 int crnn_ctc_status(crnn_handle* h, int32_t* status_host, void* stream) {

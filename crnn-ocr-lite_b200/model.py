@@ -320,12 +320,29 @@ class CRNNModel:
         else:
             _lib.check(self.lib.crnn_sgd_step(self.handle, o.lr, o.decay, o.momentum, o.clipnorm or 0.0, grad_scale, self._stream()))
 
-    def allreduce_grads(self):
-        """Data-parallel exchange (NEW capability): one NCCL sum all-reduce of the flat gradient arena."""
+    def enable_native_dp(self, fused=True):
+        """Data parallel through the engine's own NCCL communicator (parallel.native_comm_for): with `fused` the training step reduces its
+        gradients itself -- head bucket overlapped with the conv-stack backward -- and allreduce_grads() only returns the 1/world scale."""
         from . import parallel
-        if parallel.world_size() > 1:
-            return parallel.allreduce_sum_(self.tensor("arena/grads"))
-        return 1.0
+        ok = parallel.native_comm_for(self, fused)
+        self._native_dp = ("fused" if fused else "call") if ok else None
+        return self._native_dp
+
+    def allreduce_grads(self):
+        """Data-parallel exchange (NEW capability): one sum all-reduce of the flat gradient arena.  Returns the scale (1/world)
+        the optimiser must apply.  Fused native mode: already done inside the step; native call mode: crnn_allreduce_grads (C ABI, NCCL);
+        otherwise torch.distributed (gloo in the CPU / shared-GPU tests)."""
+        from . import parallel
+        w = parallel.world_size()
+        if w <= 1:
+            return 1.0
+        mode = self.__dict__.get("_native_dp")
+        if mode == "fused":
+            return 1.0 / w
+        if mode == "call":
+            _lib.check(self.lib.crnn_allreduce_grads(self.handle, None, self._stream()))
+            return 1.0 / w
+        return parallel.allreduce_sum_(self.tensor("arena/grads"))
 
     def _stage(self, key, arr, dtype):
         """host numpy -> pinned staging -> device (async on the current stream)."""

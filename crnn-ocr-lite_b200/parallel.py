@@ -22,6 +22,32 @@ def init_distributed(backend=None, device=None):
     dist.init_process_group(backend, **kw)
 
 
+def backend():
+    return dist.get_backend() if dist.is_available() and dist.is_initialized() else None
+
+
+def native_comm_for(model, fused=True):
+    """Give `model`'s engine its own NCCL communicator over the ranks of the default process group (ncclUniqueId created by the C ABI on rank
+    0 and broadcast through torch.distributed) and, with `fused`, let the training step issue its bucketed gradient all-reduce itself
+    (include/crnn_b200.h: crnn_comm_init_rank / crnn_set_dp_fused).  Returns False when not applicable: single process, a non-NCCL process
+    group (the CPU / shared-GPU test modes), or CRNN_DP_NATIVE=0 (A/B against the torch.distributed all-reduce)."""
+    if world_size() <= 1 or backend() != "nccl" or os.environ.get("CRNN_DP_NATIVE") == "0":
+        return False
+    from . import _lib
+    lib = model.lib
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank() == 0:
+        _lib.check(lib.crnn_nccl_unique_id(uid.data_ptr()))
+    uid_dev = uid.to(model.device)
+    dist.broadcast(uid_dev, src=0)
+    uid = uid_dev.cpu().contiguous()
+    with torch.cuda.device(model.device):
+        _lib.check(lib.crnn_comm_init_rank(model.handle, uid.data_ptr(), world_size(), rank()))
+        if fused:
+            _lib.check(lib.crnn_set_dp_fused(model.handle, 1))
+    return True
+
+
 def world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 

@@ -93,6 +93,26 @@ int crnn_set_iterations(crnn_handle* h, int64_t it);
 /* status of the last CTC loss launch (read after a stream sync): 0 or -(b+1) for the first infeasible sample */
 int crnn_ctc_status(crnn_handle* h, int32_t* status_host, void* stream);
 
+/* ---------------------------------------------------------------- data parallel (NEW capability: the reference is single-device,
+ * train.py:111,116 import multi_gpu_model and never call it -- SURVEY 0.8 / 8e).  One process per GPU, batch sharded by rank, the only
+ * exchange of the step is a sum all-reduce of the flat fp32 gradient arena (NCCL over NVLink/NVSwitch); 1/world is applied by the optimiser
+ * entry points (`grad_scale`), clip-by-global-norm + update run after the reduce, identically on every rank.  libnccl.so.2 is bound at run
+ * time (dlopen; the instance already loaded in the process is preferred), so there is no link-time dependency.
+ *   crnn_nccl_unique_id   rank 0: 128-byte ncclUniqueId to hand to the other ranks by any side channel
+ *   crnn_comm_init_rank   ncclCommInitRank on the current device; the communicator is owned by the handle
+ *   crnn_set_comm         alternatively: borrow the caller's ncclComm_t (NULL detaches)
+ *   crnn_allreduce_grads  in-place sum all-reduce of arena/grads on `stream` (comm NULL = the handle's) -- SURVEY 8b's entry point
+ *   crnn_set_dp_fused     1: crnn_train_fwd_bwd issues the exchange itself, in two buckets: the head gradients (dense1 .. dense2, ~70 % of
+ *                         the bytes) on a private stream as soon as their weight-gradient GEMMs are done -- overlapping the whole conv-stack
+ *                         backward -- and the conv-stack + STN bucket at the end; part of the captured step graph.  The caller then skips
+ *                         crnn_allreduce_grads and passes grad_scale = 1 / world to the optimiser step. */
+int crnn_nccl_unique_id(void* id128_out);
+int crnn_comm_init_rank(crnn_handle* h, const void* id128, int nranks, int rank);
+int crnn_set_comm(crnn_handle* h, void* nccl_comm, int nranks);
+int crnn_set_dp_fused(crnn_handle* h, int on);
+int crnn_comm_ranks(const crnn_handle* h);
+int crnn_allreduce_grads(crnn_handle* h, void* nccl_comm, void* stream);
+
 /* ---------------------------------------------------------------- stand-alone CTC ops on device buffers */
 /* K.ctc_batch_cost (utils.py:103) on probs[:, t_off:, :]; grad_u / grad_logits may be NULL.
  * status_dev: one int32, 0 or -(b+1). */

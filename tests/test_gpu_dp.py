@@ -29,7 +29,11 @@ def grads_of(m, seed):
     m.train_fwd_bwd_device(torch.tensor(x, device=d), torch.tensor(lab, device=d), torch.tensor(L, device=d), torch.tensor(il, device=d), dropout_seed=0)
     return m.tensor("arena/grads").clone()
 m = make()
+mode = m.enable_native_dp(fused=(os.environ.get("CRNN_TEST_DP_FUSED", "1") == "1"))   # NCCL group: the engine's own communicator; gloo: None
 grads_of(m, 100 + r)
+if mode == "fused":           # the step already reduced its gradients (two buckets): every rank holds the same SUM
+    gsum = m.tensor("arena/grads").clone(); ref_g = gsum.clone(); cb.parallel.broadcast_(ref_g, 0)
+    assert torch.equal(ref_g, gsum), "fused all-reduce left different gradients on the ranks"
 scale = m.allreduce_grads()
 assert scale == 1.0 / w
 m.optimizer_step(scale)
@@ -44,7 +48,7 @@ m2.tensor("arena/grads").copy_(g)
 m2.optimizer_step(1.0 / w)
 diff = (m2.tensor("arena/params") - mine).abs().max().item()
 assert diff < 1e-6, diff     # gradient atomics make the two evaluations differ by rounding only
-sys.stdout.write("rank %%d ok %%g\n" %% (r, diff)); sys.stdout.flush()
+sys.stdout.write("rank %%d ok %%g mode %%s\n" %% (r, diff, mode)); sys.stdout.flush()
 '''
 
 
@@ -59,12 +63,18 @@ def _torchrun(args, port, extra_env=None, timeout=600):
 
 
 @pytest.mark.gpu
-def test_dp_two_ranks(tmp_path):
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_dp_two_ranks(tmp_path, fused):
+    """fused=1: the step's own bucketed NCCL all-reduce (crnn_set_dp_fused); fused=0: crnn_allreduce_grads called after the step.  On a
+    1-GPU box both variants run the torch.distributed/gloo exchange (NCCL cannot put two ranks on one device)."""
+    import torch
     script = tmp_path / "dp_gpu.py"
     script.write_text(_SCRIPT % {"root": ROOT})
-    r = _torchrun([str(script)], 29544)
+    r = _torchrun([str(script)], 29544 + int(fused), extra_env={"CRNN_TEST_DP_FUSED": fused})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    if torch.cuda.device_count() >= 2:
+        assert ("mode fused" if fused == "1" else "mode call") in r.stdout, r.stdout[-500:]
 
 
 @pytest.mark.gpu

@@ -96,6 +96,7 @@ def main():
     if args.pretrained_path is not None:
         model.load_weights(args.pretrained_path)
     cb.parallel.broadcast_(model.tensor("arena/params"))
+    model.enable_native_dp()                        # NCCL process group: the step reduces its gradients itself (bucketed, overlapped); no-op otherwise
 
     # identical on every rank (from the largest shard); the generator wraps around its list, so a shorter shard just re-uses its first files
     train_steps = cb.parallel.steps_per_epoch(n_train_global, args.batch_size, world)
