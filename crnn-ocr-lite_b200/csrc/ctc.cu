@@ -325,6 +325,7 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
     const int blank = V - 1, NC = V - 1;
     const int Tb = seq_len ? seq_len[b] : T;
     const int NOID = 0x7fffffff;
+    const bool fast = W <= 16;     // sorted-candidate walk (see (a') below); wider beams scan all labels per parent
 
     unsigned char* base = smraw + (size_t)wib * smem_per_warp_bytes;
     float* in_ = (float*)base;                                           // V (padded)
@@ -343,15 +344,67 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
     }
     __syncwarp();
 
+    // the probabilities of step t + 1 are fetched while step t is processed (V <= 128: four registers per lane); the global-load
+    // latency sat at the top of every step's dependency chain (ncu r2f: most-sampled line of the kernel)
+    const bool pre = V <= 128;
+    float nx[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pre && Tb > 0) {
+        const float* p0 = probs + (size_t)b * T * V;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (lane + 32 * i < V) nx[i] = __ldg(p0 + lane + 32 * i);
+    }
     for (int t = 0; t < Tb; ++t) {
         const float* p = probs + ((size_t)b * T + t) * V;
         // (a) normalised step input: u - max(u)   (TF 1.8: max-subtraction only)
         float mx = -INFINITY;
-        for (int k = lane; k < V; k += 32) { float u = logf(p[k] + eps); in_[k] = u; mx = fmaxf(mx, u); }
+        if (pre) {
+            float cur4[4] = {nx[0], nx[1], nx[2], nx[3]};
+            if (t + 1 < Tb) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (lane + 32 * i < V) nx[i] = __ldg(p + V + lane + 32 * i);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (lane + 32 * i < V) { float u = logf(cur4[i] + eps); in_[lane + 32 * i] = u; mx = fmaxf(mx, u); }
+        } else {
+            for (int k = lane; k < V; k += 32) { float u = logf(p[k] + eps); in_[k] = u; mx = fmaxf(mx, u); }
+        }
         mx = warp_max(mx);
         __syncwarp();
         for (int k = lane; k < V; k += 32) in_[k] -= mx;
         __syncwarp();
+        // (a') the 32 best non-blank labels of this step, sorted (score descending, label ascending): lane j holds the j-th best.  Every
+        // parent scores its children as in_[k] + const, so ONE sorted list serves all parents: a parent then walks its candidates best
+        // first and stops at the first one that does not beat the bottom leaf -- the work per parent is (#insertions + 1) instead of a
+        // scan of all V-1 labels with an insertion attempt for every label above the bottom it started with (ncu r2a: 53 % of the
+        // kernel's instructions were that scan; candidates inserted early were evicted again by better siblings).
+        float tv = NEG_INF; int tk = 0x7fff0000 + lane;
+        if (fast) {
+            auto before = [](float va, int ka, float vb, int kb) { return va > vb || (va == vb && ka < kb); };
+            for (int k0 = 0; k0 < NC; k0 += 32) {
+                float cv = (k0 + lane < NC) ? in_[k0 + lane] : NEG_INF; int ck = (k0 + lane < NC) ? k0 + lane : 0x7ffe0000 + lane;
+                // bitonic sort of the chunk, descending
+#pragma unroll
+                for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        const float ov = __shfl_xor_sync(FULL, cv, stride); const int ok = __shfl_xor_sync(FULL, ck, stride);
+                        const bool desc = (lane & size) == 0, low = (lane & stride) == 0;
+                        const bool other_first = before(ov, ok, cv, ck);
+                        if ((low == desc) ? other_first : !other_first) { cv = ov; ck = ok; }
+                    }
+                }
+                // merge with the running top 32: max(A_i, B_{31-i}) is bitonic and holds the 32 best of the union; 5 merge stages sort it
+                const float rv = __shfl_sync(FULL, cv, 31 - lane); const int rk = __shfl_sync(FULL, ck, 31 - lane);
+                if (before(rv, rk, tv, tk)) { tv = rv; tk = rk; }
+#pragma unroll
+                for (int stride = 16; stride > 0; stride >>= 1) {
+                    const float ov = __shfl_xor_sync(FULL, tv, stride); const int ok = __shfl_xor_sync(FULL, tk, stride);
+                    const bool low = (lane & stride) == 0;
+                    const bool other_first = before(ov, ok, tv, tk);
+                    if (low ? other_first : !other_first) { tv = ov; tk = ok; }
+                }
+            }
+        }
 
         const int* on = bnode + cur * 32; const float* opb = bpb + cur * 32; const float* opl = bpl + cur * 32; const float* opt = bpt + cur * 32;
         // ---- phase 1: survivors (lane e < nb)
@@ -374,7 +427,7 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
             s_nb = opt[lane] + in_[blank];
             s_nt = lse2(s_nb, nl);
         }
-        // ---- leaves list L over the lanes: (Lv, Lid); id<0: survivor -1-e, id>=0: child q*NC+k
+        // ---- leaves list L over the lanes: (Lv, Lid); id<0: survivor -1-e, id>=0: child (q << 10) | k  (V <= 1024)
         float Lv = NEG_INF; int Lid = NOID; int nL = 0;
         auto insert = [&](float v, int id) {     // warp-uniform call; keeps L sorted (descending), capacity W
             int pos = __popc(__ballot_sync(FULL, Lv > v));
@@ -391,7 +444,8 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
             const bool r_blocked = __shfl_sync(FULL, (int)blocked, r) != 0;
             const float ot = opt[r], ob = opb[r];
             float bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
-            if (r_blocked || !(ot > bottom)) continue;     // is_candidate(b->oldp)
+            if (r_blocked) continue;
+            if (!(ot > bottom)) break;     // is_candidate(b->oldp) fails; the parents after r have smaller totals and the bottom never drops
             const int lab_r = nodes[on[r]].label;
             const unsigned km = __ballot_sync(FULL, lane < nb && s_q == r);   // survivors that are children of r
             // blocking test for every such survivor
@@ -416,16 +470,39 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
                 if (blk && lane == c) blocked = true;
             }
             // insert the eligible children of r
-            for (int k0 = 0; k0 < NC; k0 += 32) {
-                const int k = k0 + lane;
-                float x = (k < NC) ? in_[k] + ((k == lab_r) ? ob : ot) : NEG_INF;
-                for (unsigned m2 = km; m2; m2 &= m2 - 1) { int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (k == kk) x = NEG_INF; }
+            if (fast) {
+                // the child that repeats the parent's own label is scored with the parent's blank probability: handled apart
+                bool lab_ok = lab_r >= 0;
+                bool valid = tk < NC && tk != lab_r;
+                for (unsigned m2 = km; m2; m2 &= m2 - 1) { const int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (tk == kk) valid = false; if (kk == lab_r) lab_ok = false; }
+                if (lab_ok) {
+                    const float v = in_[lab_r] + ob;
+                    bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
+                    if (v > bottom) insert(v, (r << 10) + lab_r);
+                }
+                // all other children, best first (lane order); equal scores keep the label order TF visits them in.  With W <= 16 the
+                // 32 sorted labels always suffice: at most W - 1 of them are survivors of this parent, one is its own label, W get in.
+                const float x = valid ? tv + ot : NEG_INF;
                 bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
                 for (unsigned m = __ballot_sync(FULL, x > bottom); m; m &= m - 1) {
                     const int src = __ffs(m) - 1;
                     const float v = __shfl_sync(FULL, x, src);
                     bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
-                    if (v > bottom) insert(v, r * NC + k0 + src);
+                    if (!(v > bottom)) break;                        // sorted: nothing after it can beat the bottom either
+                    insert(v, (r << 10) + __shfl_sync(FULL, tk, src));
+                }
+            } else {
+                for (int k0 = 0; k0 < NC; k0 += 32) {
+                    const int k = k0 + lane;
+                    float x = (k < NC) ? in_[k] + ((k == lab_r) ? ob : ot) : NEG_INF;
+                    for (unsigned m2 = km; m2; m2 &= m2 - 1) { int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (k == kk) x = NEG_INF; }
+                    bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
+                    for (unsigned m = __ballot_sync(FULL, x > bottom); m; m &= m - 1) {
+                        const int src = __ffs(m) - 1;
+                        const float v = __shfl_sync(FULL, x, src);
+                        bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
+                        if (v > bottom) insert(v, (r << 10) + k0 + src);
+                    }
                 }
             }
         }
@@ -440,24 +517,36 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
             if (Lid < 0) { nnode[lane] = g_node; npb[lane] = g_nb; npl[lane] = g_nl; npt[lane] = g_nt; }
             else { npb[lane] = NEG_INF; npl[lane] = Lv; npt[lane] = Lv; }
         }
-        for (int i = 0; i < nL; ++i) {     // trie find-or-create for the new children (lane 0, sequential)
-            const int id = __shfl_sync(FULL, Lid, i);
-            if (id >= 0 && lane == 0) {
-                const int q = id / NC, k = id - q * NC;
-                const int par = on[q];
-                int c = nodes[par].first_child;
+        {   // trie find-or-create for the new children, one lane per leaf: the search of the parent's sibling list is read-only; the nodes
+            // that have to be created get consecutive indices (prefix count over the creating lanes) and are pushed at the head of their
+            // parent's list -- lanes that share a parent chain their nodes in lane order, the last of them becomes the new head
+            const bool child = lane < nL && Lid >= 0;
+            int par = -1, k = 0, c = -1;
+            if (child) {
+                par = on[Lid >> 10]; k = Lid & 1023;
+                c = nodes[par].first_child;
                 while (c >= 0 && nodes[c].label != k) c = nodes[c].next_sib;
-                if (c < 0) {
-                    c = nn;
-                    nodes[c].parent = (short)par; nodes[c].label = (short)k;
-                    nodes[c].first_child = -1; nodes[c].next_sib = nodes[par].first_child;
-                    nodes[par].first_child = (short)c;
-                    ++nn;
-                }
-                nnode[i] = c;
             }
+            const unsigned mk = __ballot_sync(FULL, child && c < 0);
+            if (mk) {
+                const unsigned lt = (1u << lane) - 1u;
+                const bool mine = (mk >> lane) & 1u;
+                const unsigned grp = __match_any_sync(FULL, mine ? par : -2 - lane) & mk;     // creating lanes with the same parent
+                int old_head = -1;
+                if (mine) old_head = nodes[par].first_child;
+                __syncwarp();
+                if (mine) {
+                    c = nn + __popc(mk & lt);
+                    const unsigned below = grp & lt;
+                    const int prev = below ? nn + __popc(mk & ((1u << (31 - __clz(below))) - 1u)) : old_head;
+                    TrieNode nd; nd.parent = (short)par; nd.label = (short)k; nd.first_child = -1; nd.next_sib = (short)prev;
+                    nodes[c] = nd;
+                    if (!(grp >> lane >> 1)) nodes[par].first_child = (short)c;                 // highest lane of the group
+                }
+                nn += __popc(mk);
+            }
+            if (child) nnode[lane] = c;
         }
-        nn = __shfl_sync(FULL, nn, 0);
         nb = nL;
         cur = nxt;
         __syncwarp();
@@ -544,6 +633,7 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
     if (B <= 0) return CRNN_OK;
     if (top_paths < 1 || top_paths > W) { crnn_set_error("ctc_beam: top_paths %d not in [1, beam width %d]", top_paths, W); return CRNN_ERR_INVALID; }
     if (W < 1 || W > BEAM_MAX_W) { crnn_set_error("ctc_beam: beam width %d not in [1,%d]", W, BEAM_MAX_W); return CRNN_ERR_INVALID; }
+    if (V < 2 || V > 1024) { crnn_set_error("ctc_beam: %d classes not in [2,1024]", V); return CRNN_ERR_INVALID; }
     if ((size_t)1 + (size_t)W * T > 32000) { crnn_set_error("ctc_beam: W*T too large"); return CRNN_ERR_INVALID; }
     size_t per = sizeof(float) * ((V + 3) & ~3) + sizeof(TrieNode) * (((size_t)1 + (size_t)W * T + 1) & ~1)
                + sizeof(int) * 64 + sizeof(float) * 64 * 3;

@@ -144,8 +144,11 @@ def _beam_compare(cb, probs, W=10, merge=True, seq_len=None):
 
 @pytest.mark.parametrize("B,T,V,scale,W", [(64, 25, 96, 3.0, 10), (32, 52, 38, 6.0, 10), (16, 66, 38, 1.0, 10), (16, 25, 96, 3.0, 3),
                                            (9, 12, 7, 1.0, 32), (4, 1, 5, 1.0, 10), (64, 40, 38, 0.5, 10), (64, 30, 20, 1.5, 5),
-                                           (32, 25, 96, 1.0, 10), (256, 52, 38, 2.0, 10)])
+                                           (32, 25, 96, 1.0, 10), (256, 52, 38, 2.0, 10), (16, 25, 96, 2.0, 16), (16, 25, 96, 2.0, 17),
+                                           (8, 20, 200, 1.0, 20), (32, 30, 38, 12.0, 10)])
 def test_beam_exact(cb, B, T, V, scale, W):
+    """W <= 16 takes the sorted-candidate walk of ctc_beam_kernel, wider beams the full label scan; scale 12 gives saturated frames whose
+    hopeless classes tie exactly at log(eps) -- the label-order tie rule of the TF children loop decides which of them enter the beam."""
     probs = _rand_probs(np.random.default_rng(B * 7 + T), B, T, V, scale)
     bad, (o, n, lp), (out, cnt, score) = _beam_compare(cb, probs, W)
     assert not bad, (bad, o[bad[0]], out[bad[0]])
