@@ -107,7 +107,7 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((sadd
 // the four k-groups (8 fp32 each) of one 32-wide k-block: per group one bf16 cross-term UMMA + one tf32 main-term UMMA.
 //   wl / xl: descriptor low words of the stage's Whi / Xhi tiles (the x / lo tiles follow 16 KB = 1024 descriptor units later)
 //   first: 0 -> the very first UMMA overwrites the accumulator (start of a tile's k range)
-__device__ __forceinline__ void umma_kblock(uint32_t tacc, uint32_t wl, uint32_t xl, uint32_t first_acc) {
+__device__ __forceinline__ void umma_kblock(uint32_t tacc, uint32_t wl, uint32_t xl, uint32_t first_acc, uint32_t idesc_tf32, uint32_t idesc_bf16) {
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
         "elect.sync _|q, 0xffffffff;\n\t"
@@ -128,7 +128,7 @@ __device__ __forceinline__ void umma_kblock(uint32_t tacc, uint32_t wl, uint32_t
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, 1;\n\t"
         "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t}"
-        ::"r"(tacc), "r"(wl), "r"(xl), "r"(first_acc), "r"(TC_DESC_HI), "r"(TC_IDESC), "r"(TC_IDESC_BF16) : "memory");
+        ::"r"(tacc), "r"(wl), "r"(xl), "r"(first_acc), "r"(TC_DESC_HI), "r"(idesc_tf32), "r"(idesc_bf16) : "memory");
 }
 // tcgen05.commit by one elected lane of a converged warp (up to three barriers; 0 = skip)
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar0, uint32_t bar1, uint32_t bar2) {
@@ -434,7 +434,7 @@ __device__ __forceinline__ void epi_store(float* dst, const uint32_t (&r)[32], i
 // KS > 1: split-K.  Work item t = (CTA tile t / KS, k-slice t % KS); every slice contracts KBS k-blocks and stores its partial tile
 // into its own copy of the output (out + slice * split_stride) -- the caller sums the copies in a fixed order (deterministic, no atomics).
 // Used for the head GEMMs whose 128-pixel x 128-channel tiling yields only 33-66 tiles for 148 SMs (dense1: M=4224, N=128, K=4608).
-__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmx, int NTP, int MT, int NSUB, int KS, long long split_stride)
+__global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmx, int NTP, int MT, int NSUB, int KS, long long split_stride, int BP)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -491,8 +491,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         const uint32_t bn_u32 = smem_u32(bn_tab) + (uint32_t)(c8 * 4) * 4u;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
-            const bool tail = m0 + TC_BP > a.M;
+            const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * BP;
+            const bool tail = m0 + BP > a.M;
             const int kb0 = kb_lo(t), kb1 = kb_hi(t);
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % TC2_XSTAGES;
@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 mbar_wait(&rawfull[slot], (it / TC2_RAW) & 1);                   // the TMA load of ring entry `slot` has landed
                 float4 v[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = lds128(raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u) + (uint32_t)i * (32u * TC_BK * 4u));
+                for (int i = 0; i < 4; ++i)      // rows >= BP (pixel tiles narrower than 128) are neither loaded by the TMA box nor read by the UMMAs
+                    v[i] = (r0 + 32 * i < BP) ? lds128(raw_u32 + (uint32_t)slot * (TC_TILE_FLOATS * 4u) + (uint32_t)i * (32u * TC_BK * 4u)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 if (bn) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -528,6 +529,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 const uint32_t xhi = x_u32 + (uint32_t)s * (2u * TC_TILE_FLOATS * 4u), xlo = xhi + TC_TILE_FLOATS * 4u;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    if (r0 + 32 * i >= BP) continue;
                     sts128(xhi + (uint32_t)i * 4096u, hv[i].x, hv[i].y, hv[i].z, hv[i].w);       // row r0 + 32 i: 4 eight-row groups = 4 x 1024 B further
                     sts128(xlo + (uint32_t)i * 4096u, lv[i].x, lv[i].y, lv[i].z, lv[i].w);
                 }
@@ -542,12 +544,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
+                const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * BP;
                 const int kb0 = kb_lo(t), kb1 = kb_hi(t);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int slot = it % TC2_RAW;
                     mbar_wait(&rawempty[slot], ((it / TC2_RAW) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&rawfull[slot], TC_TILE_FLOATS * 4);
+                    mbar_arrive_expect_tx(&rawfull[slot], (uint32_t)BP * TC_BK * 4);        // the box is BP rows x 32 fp32
                     tma_load_2d(raw_base + (size_t)slot * TC_TILE_FLOATS, &tmx, kb * TC_BK, m0, &rawfull[slot]);
                 }
             }
@@ -577,6 +579,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t wdesc0 = umma_desc_lo(smem_u32(w_base)), xdesc0 = umma_desc_lo(smem_u32(x_base));
         const uint32_t bar_wempty = smem_u32(wempty), bar_xempty = smem_u32(xempty), bar_tfull = smem_u32(tfull);
+        // UMMA N = pixels per tile (a multiple of 16 chosen by the launcher, see pick_pixel_tile): idesc bits [17,23) = N >> 3
+        const uint32_t idesc_tf32 = (TC_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(BP >> 3) << 17);
+        const uint32_t idesc_bf16 = (TC_IDESC_BF16 & ~(0x3Fu << 17)) | ((uint32_t)(BP >> 3) << 17);
         uint32_t it = 0, wit = 0;
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
@@ -590,10 +595,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 const uint32_t xl = xdesc0 + (uint32_t)xs * (2u * TC_TILE_FLOATS * 4u / 16u);
                 for (int h = 0; h < NSUB; ++h, ++wit) {
                     const int ws = wit % TC2_WRING;
-                    const uint32_t tacc = tb + (uint32_t)(buf * 256 + h * TC_BP);
+                    const uint32_t tacc = tb + (uint32_t)(buf * 256 + h * 128);
                     mbar_wait(&wfull[ws], (wit / TC2_WRING) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    umma_kblock(tacc, wdesc0 + (uint32_t)ws * (2u * TC_TILE_FLOATS * 4u / 16u), xl, (uint32_t)(kb - kb0));
+                    umma_kblock(tacc, wdesc0 + (uint32_t)ws * (2u * TC_TILE_FLOATS * 4u / 16u), xl, (uint32_t)(kb - kb0), idesc_tf32, idesc_bf16);
                     const bool last_h = h == NSUB - 1;
                     umma_commit_elect(bar_wempty + 8u * ws, last_h ? bar_xempty + 8u * xs : 0u, (last_h && kb == kb1 - 1) ? bar_tfull + 8u * buf : 0u);
                 }
@@ -621,7 +626,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         int j = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
             const int buf = j & 1;
-            const int ct0 = ((t / KS) % NTP) * NSUB, m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * TC_BP;
+            const int ct0 = ((t / KS) % NTP) * NSUB, m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * BP;
+            const int m_end = m0 + BP < a.M ? m0 + BP : a.M;                          // first pixel row NOT in this tile
             float* const outp = a.out + (size_t)(t % KS) * (size_t)split_stride;      // this k-slice's copy of the output
             if (ct0 != cur_ct0) { flush_stats(); cur_ct0 = ct0; }
             if (a.red_y) {
@@ -632,7 +638,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 #pragma unroll
                     for (int pp = 0; pp < 64; pp += 32) {
                         const int m = m0 + half * 64 + pp + lane;
-                        if (m < a.M && nb < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.red_y + (size_t)m * a.ldo + nb));
+                        if (m < m_end && nb < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.red_y + (size_t)m * a.ldo + nb));
                     }
                 }
             }
@@ -647,9 +653,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             if (a.red_y && n_ok) { rsc = __ldg(a.red_scale + n); rsh = __ldg(a.red_shift + n); rxa = __ldg(a.red_invstd + n); rxb = -__ldg(a.red_mean + n) * rxa; }
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-            for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+            for (int c0 = half * 64; c0 < half * 64 + 64 && c0 < BP; c0 += 32) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + h * TC_BP + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + h * 128 + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -661,7 +667,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float* dst = outp + (size_t)(m0 + c0) * a.ldo + n;      // 32 lanes = 32 consecutive channels: 128-byte coalesced rows
-                if (n_ok && m0 + c0 + 32 <= a.M && !a.accumulate) {     // fast paths: full 32-pixel chunk, no per-element predicate
+                if (n_ok && m0 + c0 + 32 <= m_end && !a.accumulate) {   // fast paths: full 32-pixel chunk, no per-element predicate
                     // row stride known at compile time for the conv-stack widths -> the 32 stores use immediate offsets (the generic
                     // loop costs a 64-bit add per store; the epilogue warps share the issue slots with the activation producers)
                     if (a.red_y) {                                              // dX + reduction pass of the following BN/ReLU6 backward
@@ -699,7 +705,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 } else if (n_ok) {
 #pragma unroll
                     for (int p = 0; p < 32; ++p) {
-                        if (m0 + c0 + p < a.M) {
+                        if (m0 + c0 + p < m_end) {
                             float val = __uint_as_float(r[p]) + bias;
                             if (a.relu) val = fmaxf(val, 0.f);
                             if (a.accumulate) val += *dst;
@@ -797,7 +803,32 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
         a.red_y = red->y; a.red_scale = red->scale; a.red_shift = red->shift; a.red_mean = red->mean; a.red_invstd = red->invstd;
     }
     if (x_scale && K > TC2_BN_MAXK) { crnn_set_error("gemm_tc: the BN+ReLU6 prologue supports K <= %d (K = %d)", TC2_BN_MAXK, K); return CRNN_ERR_INVALID; }
-    // tensor map of X for the raw-tile TMA loads: dims {K, M} fp32, row stride ldx, box {32, 128}, no swizzle, out-of-range rows read as 0
+    static int nsub_env = -1, bp_env = -1;     // A/B switches: CRNN_GEMM_NSUB=1 (one channel tile per CTA tile), CRNN_GEMM_BP=<pixels per tile, multiple of 16>
+    if (nsub_env < 0) { const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; const char* g = getenv("CRNN_GEMM_BP"); bp_env = g ? atoi(g) : 0; if (bp_env % 16 || bp_env > 128 || bp_env < 16) bp_env = 0; }
+    const int NT = (N + TC_BC - 1) / TC_BC;
+    if (ksplit > 1 && (x_scale || stats || bias || relu || accumulate || split_stride < (long long)M * ldo - (ldo - N) || ksplit > K / TC_BK)) {
+        crnn_set_error("gemm_tc: split-K needs the plain-store epilogue (no BN prologue / statistics / bias / relu / accumulate) and disjoint output copies");
+        return CRNN_ERR_INVALID;
+    }
+    if (ksplit < 1) ksplit = 1;
+    static bool configured2 = false;
+    static int num_sms = 148;
+    if (!configured2) {
+        CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        configured2 = true;
+    }
+    // two channel tiles per CTA tile when there are enough tiles to fill the SMs anyway: the BN/ReLU6 + hi/lo transform of the
+    // activation tile (the instruction-issue bottleneck, ncu r1d) is then shared by 2 x 128 output channels
+    const int NSUB = (NT % 2 == 0 && (long long)(NT / 2) * ((M + TC_BP - 1) / TC_BP) >= num_sms && nsub_env != 1) ? 2 : 1;
+    const int NTP = NT / NSUB;
+    // pixels per tile (UMMA N, any multiple of 16; CRNN_GEMM_BP for A/B runs).  The persistent CTAs walk a static schedule, so 594 tiles of
+    // 128 pixels on 148 SMs (blocks 4, 6, 7 at batch 64) last 5 rounds for 4.01 rounds of work; narrower tiles pack the rounds better (112:
+    // 4.6 of 5) but MEASURED slower (block 6 forward 86 -> 91 us, block 5 with 96-pixel tiles 85 -> 98 us, r2h): the weight tiles are
+    // re-streamed through shared memory once per pixel tile, and that traffic -- not the tensor pipe -- bounds the kernel.  128 stays.
+    const int BP = bp_env > 0 ? bp_env : TC_BP;
+    const int MT = (M + BP - 1) / BP;
+    // tensor map of X for the raw-tile TMA loads: dims {K, M} fp32, row stride ldx, box {32, BP}, no swizzle, out-of-range rows read as 0
     CUtensorMap tmx;
     {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -812,35 +843,16 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
         }
         const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
         const cuuint64_t gstr[1] = {(cuuint64_t)ldx * sizeof(float)};
-        const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BP};
+        const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BP};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { crnn_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for X %p, M %d, K %d, ldx %d", (int)r, (const void*)X, M, K, ldx); return CRNN_ERR_CUDA; }
     }
-    static int nsub_env = -1;
-    if (nsub_env < 0) { const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; }
-    const int NT = (N + TC_BC - 1) / TC_BC, MT = (M + TC_BP - 1) / TC_BP;
-    if (ksplit > 1 && (x_scale || stats || bias || relu || accumulate || split_stride < (long long)M * ldo - (ldo - N) || ksplit > K / TC_BK)) {
-        crnn_set_error("gemm_tc: split-K needs the plain-store epilogue (no BN prologue / statistics / bias / relu / accumulate) and disjoint output copies");
-        return CRNN_ERR_INVALID;
-    }
-    if (ksplit < 1) ksplit = 1;
     {
-        static bool configured2 = false;
-        static int num_sms = 148;
-        if (!configured2) {
-            CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
-            int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            configured2 = true;
-        }
-        // two channel tiles per CTA tile when there are enough tiles to fill the SMs anyway: the BN/ReLU6 + hi/lo transform of the
-        // activation tile (the instruction-issue bottleneck, ncu r1d) is then shared by 2 x 128 output channels
-        const int NSUB = (NT % 2 == 0 && (long long)(NT / 2) * MT >= num_sms && nsub_env != 1) ? 2 : 1;
-        const int NTP = NT / NSUB;
         const long long total = (long long)NTP * MT * ksplit;
         const int grid = (int)(total < num_sms ? total : num_sms);
-        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, tmx, NTP, MT, NSUB, ksplit, split_stride);
+        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, tmx, NTP, MT, NSUB, ksplit, split_stride, BP);
     }
     LAUNCH_CHECK();
     return CRNN_OK;
