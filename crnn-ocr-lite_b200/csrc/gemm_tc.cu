@@ -130,6 +130,66 @@ __device__ __forceinline__ void umma_kblock(uint32_t tacc, uint32_t wl, uint32_t
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t}"
         ::"r"(tacc), "r"(wl), "r"(xl), "r"(first_acc), "r"(TC_DESC_HI), "r"(idesc_tf32), "r"(idesc_bf16) : "memory");
 }
+// The same k-block issued for a CTA PAIR (cta_group::2, UMMA M = 256 channels x N = 256 pixels): each CTA of the pair holds its 128 weight
+// rows (A) and its 128 pixel rows (B) at the SAME shared-memory offsets, the leader CTA issues, both tensor cores run, each CTA's TMEM
+// receives its 128 channels x all 256 pixels.  Per MAC the pair streams half the weight bytes and reads half the B bytes a lone CTA does.
+__device__ __forceinline__ void umma_kblock_pair(uint32_t tacc, uint32_t wl, uint32_t xl, uint32_t first_acc, uint32_t idesc_tf32, uint32_t idesc_bf16) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %3, 0;\n\t"
+        "add.u32 a, %1, 1024;\n\tadd.u32 b, %2, 1024;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, p;\n\t"
+        "mov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, 1;\n\t"
+        "add.u32 a, %1, 1026;\n\tadd.u32 b, %2, 1026;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, 1;\n\t"
+        "add.u32 a, %1, 2;\n\tadd.u32 b, %2, 2;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, 1;\n\t"
+        "add.u32 a, %1, 1028;\n\tadd.u32 b, %2, 1028;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, 1;\n\t"
+        "add.u32 a, %1, 4;\n\tadd.u32 b, %2, 4;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, 1;\n\t"
+        "add.u32 a, %1, 1030;\n\tadd.u32 b, %2, 1030;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, 1;\n\t"
+        "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %4};\n\tmov.b64 db, {b, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, 1;\n\t}"
+        ::"r"(tacc), "r"(wl), "r"(xl), "r"(first_acc), "r"(TC_DESC_HI), "r"(idesc_tf32), "r"(idesc_bf16) : "memory");
+}
+// pair commit: the arrival is multicast to the barrier at the same offset in BOTH CTAs (mask 0b11)
+__device__ __forceinline__ void umma_commit_elect_pair(uint32_t bar0, uint32_t bar1, uint32_t bar2) {
+    asm volatile(
+        "{\n\t.reg .pred q, r1, r2;\n\t.reg .b16 m;\n\t"
+        "mov.b16 m, 3;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.and.b32 r1, %1, 0, q;\n\tsetp.ne.and.b32 r2, %2, 0, q;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+        "@r1 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%1], m;\n\t"
+        "@r2 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%2], m;\n\t}"
+        ::"r"(bar0), "r"(bar1), "r"(bar2) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// wait with cluster-scope acquire: for barriers that the peer CTA arrives on
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
 // tcgen05.commit by one elected lane of a converged warp (up to three barriers; 0 = skip)
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar0, uint32_t bar1, uint32_t bar2) {
     asm volatile(
@@ -397,8 +457,11 @@ constexpr int TC2_THREADS = (TC2_XLOAD_WARP + 1) * 32;
 constexpr int TC2_XSTAGES = 2;                  // {Xhi, Xlo} tiles consumed by the tensor core
 constexpr int TC2_WRING = 3;                    // {Whi, Wlo} weight tiles, streamed by the loader warp ahead of the MMA
 constexpr int TC2_RAW = 3;                      // raw fp32 activation ring filled by the tensor-map TMA loads
-constexpr int TC2_BN_MAXK = 512;                // BN+ReLU6 prologue: per-k scale/shift table kept in shared memory (conv stack: K <= 512)
-constexpr int TC2_SMEM_BYTES = (TC2_WRING * 2 + TC2_XSTAGES * 2 + TC2_RAW) * TC_TILE_FLOATS * 4 + 2 * TC2_BN_MAXK * 4 + 1024 + 256;
+// Stage budget (227 KB).  Measured alternatives (gemm_bench, block 6 forward / dX, us): 2 X stages + 3 raw entries 86 / 83 (kept);
+// 3 X stages + 2 raw entries 91 / 85 -- the k-block period (~2000 cycles for 1024 cycles of tensor work) is NOT a handshake latency that a
+// deeper X ring would hide; it matches the shared-memory traffic model (per k-block and CTA, in 128-byte port cycles: UMMA operand reads 1024,
+// weight-tile TMA writes 512, transformed-tile stores 512, raw-ring write + read 256).
+constexpr int TC2_SMEM_BYTES = (TC2_WRING * 2 + TC2_XSTAGES * 2 + TC2_RAW) * TC_TILE_FLOATS * 4 + 1024 + 256;
 
 // 2-D tiled TMA load: box {32 fp32 along k, 128 pixel rows} of X at (k0, m0) -> dense [128][32] fp32 tile; rows >= M arrive as zeros
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -434,6 +497,12 @@ __device__ __forceinline__ void epi_store(float* dst, const uint32_t (&r)[32], i
 // KS > 1: split-K.  Work item t = (CTA tile t / KS, k-slice t % KS); every slice contracts KBS k-blocks and stores its partial tile
 // into its own copy of the output (out + slice * split_stride) -- the caller sums the copies in a fixed order (deterministic, no atomics).
 // Used for the head GEMMs whose 128-pixel x 128-channel tiling yields only 33-66 tiles for 148 SMs (dense1: M=4224, N=128, K=4608).
+// PAIR = true: launched in clusters of two CTAs; a CTA pair computes 256 channels x 256 pixels per tile with cta_group::2 UMMAs (see
+// umma_kblock_pair).  Every role below keeps working on "its" 128 channel rows / 128 pixel rows; only the MMA warp differs: the leader
+// (cluster rank 0) issues for both CTAs once BOTH have their operand stages ready, the peer's MMA warp is a relay that forwards its CTA's
+// x_full / w_full / tmem_empty events to the leader with one remote arrive each.  Stage / accumulator releases come back by multicast commit.
+// NTP = channel PAIR groups (N / 256), MT = pixel tiles of 256, NSUB = KS = 1, BP = 128.
+template <bool PAIR>
 __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmx, int NTP, int MT, int NSUB, int KS, long long split_stride, int BP)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -441,13 +510,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     float* w_base = (float*)smem;                                               // [WRING][Whi | Wlo]
     float* x_base = w_base + (size_t)TC2_WRING * 2 * TC_TILE_FLOATS;            // [XSTAGES][Xhi | Xlo]
     float* raw_base = x_base + (size_t)TC2_XSTAGES * 2 * TC_TILE_FLOATS;        // [RAW][128 x 32 fp32]
-    float* bn_tab = raw_base + (size_t)TC2_RAW * TC_TILE_FLOATS;                // [scale K | shift K] of the BN+ReLU6 prologue
-    uint64_t* bars = (uint64_t*)(bn_tab + 2 * TC2_BN_MAXK);
+    uint64_t* bars = (uint64_t*)(raw_base + (size_t)TC2_RAW * TC_TILE_FLOATS);
     uint64_t* wfull = bars; uint64_t* wempty = wfull + TC2_WRING;
     uint64_t* xfull = wempty + TC2_WRING; uint64_t* xempty = xfull + TC2_XSTAGES;
     uint64_t* tfull = xempty + TC2_XSTAGES; uint64_t* tempty = tfull + 2;
     uint64_t* rawfull = tempty + 2; uint64_t* rawempty = rawfull + TC2_RAW;
-    uint32_t* tmem_slot = (uint32_t*)(rawempty + TC2_RAW);
+    uint64_t* pxfull = rawempty + TC2_RAW; uint64_t* pwfull = pxfull + TC2_XSTAGES; uint64_t* ptempty = pwfull + TC2_WRING;   // PAIR, leader: the peer's events
+    uint32_t* tmem_slot = (uint32_t*)(ptempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KB = a.K / TC_BK;
@@ -455,20 +524,36 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     const int total = NTP * MT * KS;   // CTA tile = 128 pixels x (NSUB x 128) channels: the transformed X stage feeds NSUB accumulators
     auto kb_lo = [&](int t) { return (t % KS) * KBS; };
     auto kb_hi = [&](int t) { const int e = (t % KS) * KBS + KBS; return e < KB ? e : KB; };
+    const int crank = PAIR ? (int)cluster_ctarank() : 0;                   // rank inside the CTA pair
+    const int wid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // worker = CTA, or CTA pair
+    const int nwork = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // first channel tile this CTA computes / first pixel row of the (pair) tile / first pixel row this CTA stages as the B operand
+    auto tile_ct0 = [&](int t) { return PAIR ? (t % NTP) * 2 + crank : ((t / KS) % NTP) * NSUB; };
+    auto tile_m0 = [&](int t) { const int mt = (t / KS) / NTP; return (a.rev ? MT - 1 - mt : mt) * (PAIR ? 2 * TC_BP : BP); };
+    auto tile_m0_own = [&](int t) { return tile_m0(t) + (PAIR ? crank * TC_BP : 0); };
 
     if (tid == 0) {
         for (int s = 0; s < TC2_WRING; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
         for (int s = 0; s < TC2_XSTAGES; ++s) { mbar_init(&xfull[s], TC2_PROD_WARPS); mbar_init(&xempty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256); }
         for (int s = 0; s < TC2_RAW; ++s) { mbar_init(&rawfull[s], 1); mbar_init(&rawempty[s], TC2_PROD_WARPS); }
+        for (int s = 0; s < TC2_XSTAGES; ++s) mbar_init(&pxfull[s], 1);
+        for (int s = 0; s < TC2_WRING; ++s) mbar_init(&pwfull[s], 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&ptempty[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC2_MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before anybody arrives on a remote one
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -484,22 +569,24 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         const uint32_t raw_u32 = smem_u32(raw_base) + (uint32_t)(r0 * TC_BK + c8 * 4) * 4u;
         const uint32_t x_u32 = smem_u32(x_base) + (uint32_t)((r0 >> 3) * 256 + (r0 & 7) * 32 + ((c8 ^ (r0 & 7)) << 2)) * 4u;
         const bool bn = a.x_scale != nullptr;
-        if (bn) {                                                                // per-k scale / shift table (K <= TC2_BN_MAXK, checked by the launcher)
-            for (int k = tid; k < a.K; k += TC2_PROD_WARPS * 32) { bn_tab[k] = __ldg(a.x_scale + k); bn_tab[TC2_BN_MAXK + k] = __ldg(a.x_shift + k); }
-            asm volatile("bar.sync 2, 256;" ::: "memory");                       // the 8 transform warps only
-        }
-        const uint32_t bn_u32 = smem_u32(bn_tab) + (uint32_t)(c8 * 4) * 4u;
+        // BN scale / shift of this thread's 4 k-columns: fetched one k-block ahead from the (L2-resident) per-channel vectors; these small
+        // loads have long landed when the proxy fence below executes
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bn) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + c8 * 4)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + c8 * 4)); }
         uint32_t it = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * BP;
+        for (int t = wid; t < total; t += nwork) {
+            const int m0 = tile_m0_own(t);
             const bool tail = m0 + BP > a.M;
             const int kb0 = kb_lo(t), kb1 = kb_hi(t);
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % TC2_XSTAGES;
                 const uint32_t ph = (it / TC2_XSTAGES) & 1;
                 const int slot = it % TC2_RAW;
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bn) { sc = lds128(bn_u32 + (uint32_t)kb * (TC_BK * 4u)); sh = lds128(bn_u32 + (uint32_t)(TC2_BN_MAXK + kb * TC_BK) * 4u); }
+                float4 scn = sc, shn = sh;                // next k-block's scale/shift (k-blocks of one tile are consecutive; a new tile restarts at kb0)
+                if (bn) {
+                    const int kn = (kb + 1 == kb1 ? kb0 : kb + 1) * TC_BK + c8 * 4;
+                    scn = __ldg(reinterpret_cast<const float4*>(a.x_scale + kn)); shn = __ldg(reinterpret_cast<const float4*>(a.x_shift + kn));
+                }
                 mbar_wait(&rawfull[slot], (it / TC2_RAW) & 1);                   // the TMA load of ring entry `slot` has landed
                 float4 v[4];
 #pragma unroll
@@ -536,6 +623,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xfull[s]);
+                sc = scn; sh = shn;
             }
         }
     } else if (warp == TC2_XLOAD_WARP) {
@@ -543,8 +631,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * BP;
+            for (int t = wid; t < total; t += nwork) {
+                const int m0 = tile_m0_own(t);
                 const int kb0 = kb_lo(t), kb1 = kb_hi(t);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int slot = it % TC2_RAW;
@@ -558,8 +646,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         // =========================== weight loader: one thread streams the pre-swizzled hi/lo images (TMA bulk copies) ===========================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int ct0 = ((t / KS) % NTP) * NSUB;
+            for (int t = wid; t < total; t += nwork) {
+                const int ct0 = tile_ct0(t);
                 const int kb0 = kb_lo(t), kb1 = kb_hi(t);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     for (int h = 0; h < NSUB; ++h, ++it) {
@@ -584,25 +672,54 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
         const uint32_t idesc_bf16 = (TC_IDESC_BF16 & ~(0x3Fu << 17)) | ((uint32_t)(BP >> 3) << 17);
         uint32_t it = 0, wit = 0;
         int j = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+        if (PAIR && crank != 0) {
+            // peer CTA of a pair: relay.  Forwards "my accumulator buffer is drained / my X stage is written / my W tile has landed" to
+            // the leader, which issues the UMMAs for both CTAs.
+            for (int t = wid; t < total; t += nwork, ++j) {
+                const int buf = j & 1;
+                mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);
+                if (lane == 0) mbar_arrive_remote(&ptempty[buf], 0);
+                for (int kb = 0; kb < KB; ++kb, ++it, ++wit) {
+                    const int xs = it % TC2_XSTAGES, ws = wit % TC2_WRING;
+                    mbar_wait(&xfull[xs], (it / TC2_XSTAGES) & 1);
+                    if (lane == 0) mbar_arrive_remote(&pxfull[xs], 0);
+                    mbar_wait(&wfull[ws], (wit / TC2_WRING) & 1);
+                    if (lane == 0) mbar_arrive_remote(&pwfull[ws], 0);
+                }
+            }
+        } else {
+        const uint32_t pidesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);      // cta_group::2: M = N = 256
+        const uint32_t pidesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+        for (int t = wid; t < total; t += nwork, ++j) {
             const int buf = j & 1;
             mbar_wait(&tempty[buf], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator buffer
+            if (PAIR) mbar_wait_cluster(&ptempty[buf], (j >> 1) & 1);   // ... and so has the peer's (one relay arrival per use of the buffer)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int kb0 = kb_lo(t), kb1 = kb_hi(t);
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int xs = it % TC2_XSTAGES;
                 mbar_wait(&xfull[xs], (it / TC2_XSTAGES) & 1);
+                if (PAIR) mbar_wait_cluster(&pxfull[xs], (it / TC2_XSTAGES) & 1);
                 const uint32_t xl = xdesc0 + (uint32_t)xs * (2u * TC_TILE_FLOATS * 4u / 16u);
                 for (int h = 0; h < NSUB; ++h, ++wit) {
                     const int ws = wit % TC2_WRING;
                     const uint32_t tacc = tb + (uint32_t)(buf * 256 + h * 128);
                     mbar_wait(&wfull[ws], (wit / TC2_WRING) & 1);
+                    if (PAIR) mbar_wait_cluster(&pwfull[ws], (wit / TC2_WRING) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    umma_kblock(tacc, wdesc0 + (uint32_t)ws * (2u * TC_TILE_FLOATS * 4u / 16u), xl, (uint32_t)(kb - kb0), idesc_tf32, idesc_bf16);
+                    const uint32_t wl = wdesc0 + (uint32_t)ws * (2u * TC_TILE_FLOATS * 4u / 16u);
                     const bool last_h = h == NSUB - 1;
-                    umma_commit_elect(bar_wempty + 8u * ws, last_h ? bar_xempty + 8u * xs : 0u, (last_h && kb == kb1 - 1) ? bar_tfull + 8u * buf : 0u);
+                    const uint32_t b1 = last_h ? bar_xempty + 8u * xs : 0u, b2 = (last_h && kb == kb1 - 1) ? bar_tfull + 8u * buf : 0u;
+                    if (PAIR) {
+                        umma_kblock_pair(tacc, wl, xl, (uint32_t)(kb - kb0), pidesc_tf32, pidesc_bf16);
+                        umma_commit_elect_pair(bar_wempty + 8u * ws, b1, b2);
+                    } else {
+                        umma_kblock(tacc, wl, xl, (uint32_t)(kb - kb0), idesc_tf32, idesc_bf16);
+                        umma_commit_elect(bar_wempty + 8u * ws, b1, b2);
+                    }
                 }
             }
+        }
         }
     } else {
         // =========================== epilogue warps 9..16 ===========================
@@ -624,10 +741,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             }
         };
         int j = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+        const int NCOL = PAIR ? 2 * TC_BP : BP;                                       // pixel columns of one accumulator
+        const int HC = PAIR ? TC_BP : 64;                                             // columns per epilogue warp (two warps per lane quarter)
+        for (int t = wid; t < total; t += nwork, ++j) {
             const int buf = j & 1;
-            const int ct0 = ((t / KS) % NTP) * NSUB, m0 = (a.rev ? MT - 1 - (t / KS) / NTP : (t / KS) / NTP) * BP;
-            const int m_end = m0 + BP < a.M ? m0 + BP : a.M;                          // first pixel row NOT in this tile
+            const int ct0 = tile_ct0(t), m0 = tile_m0(t);
+            const int m_end = m0 + NCOL < a.M ? m0 + NCOL : a.M;                      // first pixel row NOT in this tile
             float* const outp = a.out + (size_t)(t % KS) * (size_t)split_stride;      // this k-slice's copy of the output
             if (ct0 != cur_ct0) { flush_stats(); cur_ct0 = ct0; }
             if (a.red_y) {
@@ -635,9 +754,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
                 // L2 while the tensor core is still working on the tile (the loads sit on the epilogue's critical path otherwise)
                 for (int h = 0; h < NSUB; ++h) {
                     const int nb = (ct0 + h) * TC_BC + q * 32;
-#pragma unroll
-                    for (int pp = 0; pp < 64; pp += 32) {
-                        const int m = m0 + half * 64 + pp + lane;
+                    for (int pp = 0; pp < HC; pp += 32) {
+                        const int m = m0 + half * HC + pp + lane;
                         if (m < m_end && nb < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.red_y + (size_t)m * a.ldo + nb));
                     }
                 }
@@ -653,7 +771,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
             if (a.red_y && n_ok) { rsc = __ldg(a.red_scale + n); rsh = __ldg(a.red_shift + n); rxa = __ldg(a.red_invstd + n); rxb = -__ldg(a.red_mean + n) * rxa; }
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-            for (int c0 = half * 64; c0 < half * 64 + 64 && c0 < BP; c0 += 32) {
+            for (int c0 = half * HC; c0 < half * HC + HC && c0 < NCOL; c0 += 32) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + h * 128 + c0);
                 asm volatile(
@@ -730,9 +848,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();            // neither CTA leaves (or frees TMEM) while the other may still signal its barriers / read its tiles
     if (warp == TC2_MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }
 
@@ -802,9 +922,12 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
         if (!stats || bias || relu || accumulate || ksplit > 1) { crnn_set_error("gemm_tc: the fused BN-backward reduction needs stats and the plain-store epilogue"); return CRNN_ERR_INVALID; }
         a.red_y = red->y; a.red_scale = red->scale; a.red_shift = red->shift; a.red_mean = red->mean; a.red_invstd = red->invstd;
     }
-    if (x_scale && K > TC2_BN_MAXK) { crnn_set_error("gemm_tc: the BN+ReLU6 prologue supports K <= %d (K = %d)", TC2_BN_MAXK, K); return CRNN_ERR_INVALID; }
-    static int nsub_env = -1, bp_env = -1;     // A/B switches: CRNN_GEMM_NSUB=1 (one channel tile per CTA tile), CRNN_GEMM_BP=<pixels per tile, multiple of 16>
-    if (nsub_env < 0) { const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0; const char* g = getenv("CRNN_GEMM_BP"); bp_env = g ? atoi(g) : 0; if (bp_env % 16 || bp_env > 128 || bp_env < 16) bp_env = 0; }
+    static int nsub_env = -1, bp_env = -1, pair_env = 0;     // A/B switches: CRNN_GEMM_NSUB=1 (one channel tile per CTA tile), CRNN_GEMM_BP=<pixels per tile, multiple of 16>, CRNN_GEMM_PAIR=1
+    if (nsub_env < 0) {
+        const char* f = getenv("CRNN_GEMM_NSUB"); nsub_env = f ? atoi(f) : 0;
+        const char* g = getenv("CRNN_GEMM_BP"); bp_env = g ? atoi(g) : 0; if (bp_env % 16 || bp_env > 128 || bp_env < 16) bp_env = 0;
+        const char* q = getenv("CRNN_GEMM_PAIR"); pair_env = (q && q[0] == '1') ? 1 : 0;
+    }
     const int NT = (N + TC_BC - 1) / TC_BC;
     if (ksplit > 1 && (x_scale || stats || bias || relu || accumulate || split_stride < (long long)M * ldo - (ldo - N) || ksplit > K / TC_BK)) {
         crnn_set_error("gemm_tc: split-K needs the plain-store epilogue (no BN prologue / statistics / bias / relu / accumulate) and disjoint output copies");
@@ -814,20 +937,27 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     static bool configured2 = false;
     static int num_sms = 148;
     if (!configured2) {
-        CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(xw_gemm_tc_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured2 = true;
     }
+    // CTA pairs (cta_group::2, 256 channels x 256 pixels per pair tile) whenever the output is at least 256 channels wide and there are
+    // enough pair tiles to keep the pairs busy.  OFF by default (CRNN_GEMM_PAIR=1 enables it): results are exact (test_gemm_tc runs both
+    // schedules), and per MAC the pair moves ~45 % less through shared memory, but it MEASURED 1.6x slower (block 6 forward 140 us against
+    // 86 us; ncu r2k: tensor pipe 37 %, producers waiting on x_empty): every stage hand-over crosses the CTA boundary twice (multicast
+    // commit to the peer, relay arrive back to the leader) and two X stages cannot cover that round trip.
+    const bool pair = pair_env == 1 && ksplit == 1 && N % 256 == 0 && (long long)(N / 256) * ((M + 255) / 256) >= num_sms / 4;
     // two channel tiles per CTA tile when there are enough tiles to fill the SMs anyway: the BN/ReLU6 + hi/lo transform of the
     // activation tile (the instruction-issue bottleneck, ncu r1d) is then shared by 2 x 128 output channels
-    const int NSUB = (NT % 2 == 0 && (long long)(NT / 2) * ((M + TC_BP - 1) / TC_BP) >= num_sms && nsub_env != 1) ? 2 : 1;
-    const int NTP = NT / NSUB;
+    const int NSUB = pair ? 1 : ((NT % 2 == 0 && (long long)(NT / 2) * ((M + TC_BP - 1) / TC_BP) >= num_sms && nsub_env != 1) ? 2 : 1);
+    const int NTP = pair ? NT / 2 : NT / NSUB;
     // pixels per tile (UMMA N, any multiple of 16; CRNN_GEMM_BP for A/B runs).  The persistent CTAs walk a static schedule, so 594 tiles of
     // 128 pixels on 148 SMs (blocks 4, 6, 7 at batch 64) last 5 rounds for 4.01 rounds of work; narrower tiles pack the rounds better (112:
     // 4.6 of 5) but MEASURED slower (block 6 forward 86 -> 91 us, block 5 with 96-pixel tiles 85 -> 98 us, r2h): the weight tiles are
     // re-streamed through shared memory once per pixel tile, and that traffic -- not the tensor pipe -- bounds the kernel.  128 stays.
-    const int BP = bp_env > 0 ? bp_env : TC_BP;
-    const int MT = (M + BP - 1) / BP;
+    const int BP = (bp_env > 0 && !pair) ? bp_env : TC_BP;
+    const int MT = pair ? (M + 2 * TC_BP - 1) / (2 * TC_BP) : (M + BP - 1) / BP;
     // tensor map of X for the raw-tile TMA loads: dims {K, M} fp32, row stride ldx, box {32, BP}, no swizzle, out-of-range rows read as 0
     CUtensorMap tmx;
     {
@@ -849,10 +979,19 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { crnn_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for X %p, M %d, K %d, ldx %d", (int)r, (const void*)X, M, K, ldx); return CRNN_ERR_CUDA; }
     }
-    {
+    if (pair) {
+        const long long total = (long long)NTP * MT;
+        const int pairs = (int)(total < num_sms / 2 ? total : num_sms / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = TC2_SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, xw_gemm_tc_v2_kernel<true>, a, tmx, NTP, MT, 1, 1, (long long)0, TC_BP));
+    } else {
         const long long total = (long long)NTP * MT * ksplit;
         const int grid = (int)(total < num_sms ? total : num_sms);
-        xw_gemm_tc_v2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, tmx, NTP, MT, NSUB, ksplit, split_stride, BP);
+        xw_gemm_tc_v2_kernel<false><<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, tmx, NTP, MT, NSUB, ksplit, split_stride, BP);
     }
     LAUNCH_CHECK();
     return CRNN_OK;

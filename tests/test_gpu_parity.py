@@ -228,9 +228,12 @@ def test_gemm(cb, M, N, K, tA, tB):
 
 
 @pytest.mark.parametrize("M,N,K,transposed,prologue", [(1000, 128, 64, 1, True), (4097, 256, 128, 1, True), (300, 512, 512, 1, False),
-                                                      (777, 64, 128, 0, False), (2500, 128, 256, 0, False), (128, 256, 32, 0, True)])
+                                                      (777, 64, 128, 0, False), (2500, 128, 256, 0, False), (128, 256, 32, 0, True),
+                                                      (20001, 256, 128, 1, True), (9473, 512, 256, 0, False), (38016, 512, 512, 1, True)])
 def test_gemm_tc(cb, M, N, K, transposed, prologue):
-    """tcgen05 3xTF32 pointwise kernel vs an fp64 matmul: fp32-level accuracy (not TF32-level), fused BN statistics."""
+    """tcgen05 pointwise kernel vs an fp64 matmul: fp32-level accuracy (not TF32-level), fused BN statistics.  The last three shapes are wide
+    and tall enough for the CTA-pair schedule (cta_group::2, 256 channels x 256 pixels per pair tile), with pixel tails that are not a
+    multiple of 256 / 128 and the bench shape of blocks 6 / 7."""
     lib = cb._lib.load()
     g = torch.Generator().manual_seed(M + N + K)
     X = torch.randn(M, K, generator=g) * 2
