@@ -27,7 +27,7 @@ SYMBOLS = ["crnn_last_error", "crnn_version", "crnn_workspace_bytes", "crnn_crea
            "crnn_ctc_beam", "crnn_ctc_beam_topk", "crnn_ctc_beam_host", "crnn_ctc_greedy_host", "crnn_edit_distance", "crnn_edit_distance_host", "crnn_normalize_u8", "crnn_gemm", "crnn_debug_block_backward", "crnn_gemm_tc", "crnn_gemm_tc_dw", "crnn_gemm_tc_scratch_floats", "crnn_launch_count",
            "crnn_profile_enable", "crnn_profile_num_stages", "crnn_profile_stage_name", "crnn_profile_report",
            "crnn_profile_num_families", "crnn_profile_family_name", "crnn_profile_report2",
-           "crnn_nccl_unique_id", "crnn_comm_init_rank", "crnn_set_comm", "crnn_set_dp_fused", "crnn_comm_ranks", "crnn_allreduce_grads"]
+           "crnn_bilinear_sample", "crnn_nccl_unique_id", "crnn_comm_init_rank", "crnn_set_comm", "crnn_set_dp_fused", "crnn_comm_ranks", "crnn_allreduce_grads"]
 
 _lib = None
 
@@ -85,6 +85,7 @@ def load():
     lib.crnn_profile_family_name.restype = ctypes.c_char_p
     lib.crnn_profile_family_name.argtypes = [i32]
     lib.crnn_profile_report2.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.crnn_bilinear_sample.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.crnn_nccl_unique_id.argtypes = [vp]
     lib.crnn_comm_init_rank.argtypes = [vp, vp, i32, i32]
     lib.crnn_set_comm.argtypes = [vp, vp, i32]

@@ -1033,6 +1033,13 @@ int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps
     return decode_host(false, probs_host, B, T, V, eps, 0, 1, out_host, out_len_host, score_host, stream);
 }
 
+// Stand-alone bilinear sampler (BilinearInterpolation.call, utils.py:140-232) on device buffers: x (B,H,W) fp32, theta (B,6) -> out (B,H,W);
+// the same kernel the engine runs inside the step (there it writes the zero-padded buffer of the conv stack directly)
+int crnn_bilinear_sample(const float* x_dev, const float* theta_dev, float* out_dev, int B, int H, int W, void* stream) {
+    if (!x_dev || !theta_dev || !out_dev || B < 1 || H < 2 || W < 2) { crnn_set_error("bad argument"); return CRNN_ERR_INVALID; }
+    return launch_stn_sample_fwd(x_dev, theta_dev, out_dev, B, H, W, 0, static_cast<cudaStream_t>(stream));
+}
+
 // Input pipeline (utils.py:415-416): out[i] = (float32(in[i]) - mean) / std on the device; `out` is then fed to crnn_forward / crnn_train_fwd_bwd.
 int crnn_normalize_u8(const uint8_t* x_u8_dev, float* out_dev, long long n, float mean, float std, void* stream) {
     if (n < 0 || (n > 0 && (!x_u8_dev || !out_dev)) || !(std != 0.f)) { crnn_set_error("bad argument"); return CRNN_ERR_INVALID; }

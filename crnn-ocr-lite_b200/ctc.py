@@ -116,3 +116,55 @@ class DecodeCTCPred:
             result = result[None]
         labels, n, _ = ctc_decode_host(result, greedy=self.greedy, beam_width=self.beam_width, merge_repeated=True)
         return [self.labels_to_text(labels[i, :n[i]]) for i in range(labels.shape[0])]
+
+
+class BilinearInterpolation:
+    """utils.py:116-237 as a callable on arrays: `BilinearInterpolation(output_size)([image, theta])` -> sampled image, run by the engine's
+    sampler kernel (csrc/stn.cu through crnn_bilinear_sample).  image (B,H,W,1) or (B,H,W), theta (B,6); torch CUDA tensors are processed in
+    place on the device, numpy arrays are copied there and back.  output_size must equal the image size (the only use in the reference:
+    STN(image, sampling_size) with sampling_size = the input size, utils.py:59-62,257)."""
+
+    def __init__(self, output_size, **_):
+        self.output_size = tuple(int(v) for v in output_size)
+
+    def compute_output_shape(self, input_shapes):
+        return (None, self.output_size[0], self.output_size[1], input_shapes[0][-1])
+
+    def get_config(self):
+        return {"output_size": self.output_size}
+
+    def __call__(self, tensors):
+        X, theta = tensors
+        if not torch.cuda.is_available():
+            raise _lib.CrnnError("BilinearInterpolation needs a CUDA device: no CPU fallback on this path")
+        lib = _lib.load()
+        as_numpy = not torch.is_tensor(X)
+        x = torch.as_tensor(np.ascontiguousarray(X, np.float32) if as_numpy else X, dtype=torch.float32, device="cuda")
+        th = torch.as_tensor(np.ascontiguousarray(theta, np.float32) if not torch.is_tensor(theta) else theta, dtype=torch.float32, device=x.device).reshape(-1, 6).contiguous()
+        shp = tuple(x.shape)
+        if len(shp) == 4:
+            if shp[-1] != 1:
+                raise ValueError("BilinearInterpolation: single-channel images only (the CRNN input is grayscale)")
+            x3 = x.reshape(shp[:3])
+        else:
+            x3 = x
+        B, H, W = x3.shape
+        if (H, W) != self.output_size:
+            raise ValueError("BilinearInterpolation: output_size %s must equal the image size %s" % (self.output_size, (H, W)))
+        if th.shape[0] != B:
+            raise ValueError("BilinearInterpolation: theta must be (B, 6)")
+        x3 = x3.contiguous()
+        out = torch.empty_like(x3)
+        _lib.check(lib.crnn_bilinear_sample(_ptr(x3), _ptr(th), _ptr(out), B, H, W, _stream(x3.device)))
+        out = out.reshape(shp)
+        return out.cpu().numpy() if as_numpy else out
+
+
+def STN(image, sampling_size):
+    """utils.py:247-258 at construction time: the localisation head's last Dense layer starts as W = 0, b = identity affine
+    (get_initial_weights), so a freshly built STN resamples with theta = [1,0,0,0,1,0] whatever its conv weights are -- which, with the
+    reference's sampler (scale by size, not size - 1), is NOT the identity map.  Inside a model the trained localisation net is part of
+    the engine's forward (csrc/stn.cu)."""
+    B = int(image.shape[0])
+    theta = np.tile(np.array([1, 0, 0, 0, 1, 0], np.float32), (B, 1))
+    return BilinearInterpolation(tuple(sampling_size))([image, theta])

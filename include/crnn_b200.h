@@ -136,6 +136,10 @@ int crnn_ctc_beam_host(const float* probs_host, int B, int T, int V, float eps, 
 int crnn_ctc_greedy_host(const float* probs_host, int B, int T, int V, float eps,
                          int32_t* out_host, int32_t* out_len_host, float* score_host, void* stream);
 
+/* BilinearInterpolation.call (utils.py:140-232) as a stand-alone op: x (B,H,W) fp32, theta (B,6) -> out (B,H,W), output size = input size
+ * (what STN() asks for, utils.py:257); all sampler quirks of the reference kept */
+int crnn_bilinear_sample(const float* x_dev, const float* theta_dev, float* out_dev, int B, int H, int W, void* stream);
+
 /* ---------------------------------------------------------------- input pipeline
  * Device-side `norm` of utils.py:415-416 (called per image at utils.py:490): out = (float32(u8) - mean) / std in fp32, bit-identical to
  * numpy.  The host uploads the 8-bit line images produced by open_img (B*imgh*imgw bytes) instead of float32. */

@@ -21,7 +21,7 @@ def table(items):
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]): out.append("| %s | %d | %.1f | %.1f%% |" % (k, v[0], v[1], 100 * v[1] / tot))
     return out, tot
 with open(dst, 'w') as f:
-    f.write("# ncu launch list of `%s` (first %d launches), round 1\n\n" % (cmd, len(L)))
+    f.write("# ncu launch list of `%s` (first %d launches), round 2\n\n" % (cmd, len(L)))
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES, not absolutes).\n\n")
     if len(idx) >= 2:
         step = L[idx[0] + 1: idx[1] + 1]

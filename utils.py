@@ -31,11 +31,7 @@ def ctc_lambda_func(args):
     return _cb.ctc_batch_cost_device(y_pred, labels, label_length, input_length, t_off=2).view(-1, 1)
 
 
-def STN(*_a, **_k):
-    raise NotImplementedError("STN / BilinearInterpolation are fused stages of the engine (csrc/stn.cu); build the model with CRNN(...).get_model()")
-
-
-BilinearInterpolation = STN
+BilinearInterpolation, STN = _cb.BilinearInterpolation, _cb.STN    # utils.py:116-258 as callables on arrays (csrc/stn.cu sampler kernel)
 
 
 def get_initial_weights(output_size):
