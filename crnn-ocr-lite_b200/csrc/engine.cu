@@ -120,6 +120,7 @@ struct crnn_handle {
     int bn2_red_done[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [block]: reduction pass of the block's BN2 backward already accumulated by the producer of its dy
     bool defer_bn_grads = false;   // full backward: dgamma/dbeta of all 14 BN layers in one launch at the end instead of 14 tiny ones
     bool fuse_bn_red = true;   // CRNN_FUSE_BN_RED=0: separate reduction pass for the ReLU6+BN backward after the depthwise conv
+    bool dw_red = true;        // CRNN_DW_RED=0: the depthwise backward-data kernel does not accumulate the BN2-backward reduction of the block below
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
     // stream = a parallel branch of the graph.  CRNN_GRAPH=0 / CRNN_OVERLAP=0 switch either off; profiling runs eager + serial.
@@ -422,27 +423,29 @@ int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool 
                               h->a(actbn(bn, "scale")), h->a(actbn(bn, "shift")), h->a(actbn(bn, "mean")), h->a(actbn(bn, "invstd")), st);
 }
 
-// hi/lo weight images of every tcgen05 GEMM of the step (forward ones; plus the dX ones when training), issued on `ss`
+// hi/lo weight images of every tcgen05 GEMM of the step (forward ones; plus the dX ones when training): ONE launch on `ss`
 int prep_images(crnn_handle* h, bool training, cudaStream_t ss) {
     cudaStream_t st = ss;
     if (h->gemm_simt) return CRNN_OK;
     const int U = h->U, G = h->G;
+    TcPrepBatch t;
     for (int i = 2; i <= 7; ++i) {
         const BlockPlan& b = kBlocks[i - 1];
         const float* W = h->w(nm("conv2d_%d/kernel", i + 2));
-        ST(ST_MISC, 0, launch_prep_weight_images(W, b.cout, b.cout, b.cin, 1, h->a(nm("wimg_fwd%d", i)), ss));
-        if (training) ST(ST_MISC, 0, launch_prep_weight_images(W, b.cout, b.cin, b.cout, 0, h->a(nm("wimg_dx%d", i)), ss));
+        TRY(tc_prep_batch_add(t, W, b.cout, b.cout, b.cin, 1, h->a(nm("wimg_fwd%d", i))));
+        if (training) TRY(tc_prep_batch_add(t, W, b.cout, b.cin, b.cout, 0, h->a(nm("wimg_dx%d", i))));
     }
-    if (tc_ok(h, h->TD, h->FEAT)) ST(ST_MISC, 0, launch_prep_weight_images(h->w("dense1/kernel"), h->TD, h->TD, h->FEAT, 1, h->a("wimg_d1f"), ss));
-    if (training && tc_ok(h, h->FEAT, h->TD)) ST(ST_MISC, 0, launch_prep_weight_images(h->w("dense1/kernel"), h->TD, h->FEAT, h->TD, 0, h->a("wimg_d1b"), ss));
+    if (tc_ok(h, h->TD, h->FEAT)) TRY(tc_prep_batch_add(t, h->w("dense1/kernel"), h->TD, h->TD, h->FEAT, 1, h->a("wimg_d1f")));
+    if (training && tc_ok(h, h->FEAT, h->TD)) TRY(tc_prep_batch_add(t, h->w("dense1/kernel"), h->TD, h->FEAT, h->TD, 0, h->a("wimg_d1b")));
     for (int layer = 1; layer <= 2; ++layer)
         for (int d = 0; d < 2; ++d) {
             const int kin = layer == 1 ? h->TD : U;
             const float* W = h->w(h->rnn(layer, d) + "/kernel");
             char nf[32], nb[32]; snprintf(nf, sizeof(nf), "wimg_r%d%df", layer, d); snprintf(nb, sizeof(nb), "wimg_r%d%db", layer, d);
-            if (tc_ok(h, G * U, kin)) ST(ST_MISC, 0, launch_prep_weight_images(W, G * U, G * U, kin, 1, h->a(nf), ss));
-            if (training && tc_ok(h, kin, G * U)) ST(ST_MISC, 0, launch_prep_weight_images(W, G * U, kin, G * U, 0, h->a(nb), ss));
+            if (tc_ok(h, G * U, kin)) TRY(tc_prep_batch_add(t, W, G * U, G * U, kin, 1, h->a(nf)));
+            if (training && tc_ok(h, kin, G * U)) TRY(tc_prep_batch_add(t, W, G * U, kin, G * U, 0, h->a(nb)));
         }
+    ST(ST_MISC, 0, launch_prep_weight_images_batch(t, ss));
     return CRNN_OK;
 }
 
@@ -644,7 +647,7 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
     }
     // `other` becomes d(output of block i-1): when that block is not pooled, its BN2-backward reduction pass is accumulated by this kernel
     DwRowsRed rr; const DwRowsRed* rrp = nullptr; double* rbuf = nullptr;
-    if (i >= 2 && h->fuse_bn_red && h->defer_bn_grads && kBlocks[i - 2].ph == 1 && kBlocks[i - 2].pw == 1) {
+    if (i >= 2 && h->fuse_bn_red && h->dw_red && h->defer_bn_grads && kBlocks[i - 2].ph == 1 && kBlocks[i - 2].pw == 1) {
         const int pbn = 2 * (i - 1);
         rr.y = h->a(nm("pw%d", i - 1)); rr.scale = h->a(actbn(pbn, "scale")); rr.shift = h->a(actbn(pbn, "shift")); rr.mean = h->a(actbn(pbn, "mean"));
         rr.invstd = h->a(actbn(pbn, "invstd")); rr.rate = drop ? kDropBlock : 0.f; rr.seed = seed; rr.layer = (uint32_t)(i - 1); rr.seed_ptr = h->seed_ptr;
@@ -798,6 +801,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     if ((size_t)h->L.cursor > workspace_bytes) { crnn_set_error("workspace too small: need %lld bytes", (long long)h->L.cursor); delete h; return CRNN_ERR_NOMEM; }
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_FUSE_BN_RED"); h->fuse_bn_red = !(e && e[0] == '0'); }
+    { const char* e = getenv("CRNN_DW_RED"); h->dw_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }

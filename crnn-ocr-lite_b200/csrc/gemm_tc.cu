@@ -878,7 +878,52 @@ __global__ void prep_weight_images_kernel(const float* __restrict__ W, int ldw, 
         t[TC_TILE_FLOATS + off] = pack_bf16x2(__uint_as_float(hi), lo);          // {w_hi', w_lo}
     }
 }
+// all weight images of a step in ONE launch (22 tiny kernels on the side branch before): job j covers the flat index range
+// [start[j], start[j+1]) of its (channel-tile-padded N) x K element space
+__global__ void prep_weight_images_batch_kernel(TcPrepBatch t)
+{
+    const long long total = t.start[t.n];
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (g >= t.start[j + 1]) ++j;
+        const long long i = g - t.start[j];
+        const int N = t.N[j], K = t.K[j], ldw = t.ldw[j];
+        const int KB = K / TC_BK, NT = (N + TC_BC - 1) / TC_BC;
+        int n, k;
+        if (t.transposed[j]) { n = (int)(i % (NT * TC_BC)); k = (int)(i / (NT * TC_BC)); }
+        else                 { k = (int)(i % K); n = (int)(i / K); }
+        float w = 0.f;
+        if (n < N) w = t.transposed[j] ? t.W[j][(size_t)k * ldw + n] : t.W[j][(size_t)n * ldw + k];
+        const uint32_t hi = to_tf32(w);
+        const float lo = w - __uint_as_float(hi);
+        const int ct = n / TC_BC, r = n % TC_BC, kb = k / TC_BK, kk = k % TC_BK;
+        float* dst = t.img[j] + ((size_t)(ct * KB + kb) * 2) * TC_TILE_FLOATS;
+        const int off = sw128_off(r, kk);
+        dst[off] = __uint_as_float(hi);
+        dst[TC_TILE_FLOATS + off] = pack_bf16x2(__uint_as_float(hi), lo);
+    }
+}
 }  // namespace
+
+int tc_prep_batch_add(TcPrepBatch& t, const float* W, int ldw, int N, int K, int transposed, float* img)
+{
+    if (K % TC_BK) { crnn_set_error("gemm_tc: K=%d must be a multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
+    if (t.n >= TcPrepBatch::MAXJ) { crnn_set_error("gemm_tc: more than %d weight images in one batch", TcPrepBatch::MAXJ); return CRNN_ERR_INVALID; }
+    const int j = t.n++;
+    if (j == 0) t.start[0] = 0;
+    t.W[j] = W; t.img[j] = img; t.ldw[j] = ldw; t.N[j] = N; t.K[j] = K; t.transposed[j] = transposed;
+    t.start[j + 1] = t.start[j] + (long long)((N + TC_BC - 1) / TC_BC) * TC_BC * K;
+    return CRNN_OK;
+}
+int launch_prep_weight_images_batch(const TcPrepBatch& t, cudaStream_t st)
+{
+    if (t.n <= 0) return CRNN_OK;
+    const long long total = t.start[t.n];
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    prep_weight_images_batch_kernel<<<blocks, 256, 0, st>>>(t);
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
 
 size_t tc_weight_image_floats(int N, int K) { return (size_t)((N + TC_BC - 1) / TC_BC) * (K / TC_BK) * 2 * TC_TILE_FLOATS; }
 

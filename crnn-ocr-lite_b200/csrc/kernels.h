@@ -20,6 +20,10 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 // ---- gemm_tc.cu : tcgen05 / TMEM 3xTF32 kernel, out[m][n] = sum_k f(X[m][k]) * Wop[n][k] ----
 size_t tc_weight_image_floats(int N, int K);
 int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transposed, float* img, cudaStream_t st);
+// the same for up to MAXJ weight matrices in one launch (all images of a training step)
+struct TcPrepBatch { static constexpr int MAXJ = 28; const float* W[MAXJ]; float* img[MAXJ]; int ldw[MAXJ], N[MAXJ], K[MAXJ], transposed[MAXJ]; long long start[MAXJ + 1]; int n = 0; };
+int tc_prep_batch_add(TcPrepBatch& t, const float* W, int ldw, int N, int K, int transposed, float* img);
+int launch_prep_weight_images_batch(const TcPrepBatch& t, cudaStream_t st);
 // fused reduction pass of the BatchNorm+ReLU6 backward consuming the GEMM output (see TcArgs::red_y); y has the output's shape / stride
 struct TcBnRed { const float* y; const float* scale; const float* shift; const float* mean; const float* invstd; };
 int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, int ldo, int M, int N, int K,
