@@ -968,6 +968,10 @@ int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, con
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
 }
+int launch_bn_param_grads(const double* red, float* dgamma, float* dbeta, int C, cudaStream_t st) {
+    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
+    LAUNCH_CHECK(); return CRNN_OK;
+}
 int launch_bn_param_grads_all(const BnGradTable& t, cudaStream_t st) {
     if (t.n <= 0) return CRNN_OK;
     bn_param_grads_all_kernel<<<dim3(2, t.n), 256, 0, st>>>(t);

@@ -1,0 +1,277 @@
+// dwconv_bwd_fused.cu -- ONE kernel for everything between the pointwise dX GEMM and the block below in the backward pass of a
+// depthwise-separable block (utils.py:43-52: DepthwiseConv2D 3x3 -> BatchNormalization -> ReLU6), sm_100a, NHWC fp32:
+//     dz  = BN backward( dA * 1[0 <= bn(z) <= 6] )          (was relu6_bn_bwd apply: read dA, z; write dz)
+//     dx  = depthwise3x3^T(dz)                               (was dwconv3x3_rows<FLIP>: read dz; write dx)
+//     dk += sum x (*) dz                                     (was dwconv3x3_rows_bwd_weight on the side stream: read x, dz)
+//     red(block below) += [dx*mask*gate, . * xhat]           (was the RED instance of the backward-data kernel: read y of the block below)
+// Eight tensor passes over [B,H,W,C] become four or five: dA, z and the block input are read once, dx is written once, dz never
+// reaches HBM.  When the block below is not pooled its output (this block's input x) is a pure function of its raw pointwise
+// output y -- x = dropout(relu6(bn(y))) -- and y is needed for the fused reduction anyway, so x is RECOMPUTED from y (same fma / mask
+// as act_pool_fwd_kernel, bit-identical) and the `block{i-1}` tensor is not read at all.
+//
+// Layout: a CTA owns (image b, strip of RS rows, FQ channel quads); 192 threads = FQ quads x FP position slots, a slot = (one of G = 2
+// rows, one three-column segment).  FQ is the largest of 8 / 16 / 32 whose 192 / FQ slots still hold two rows of W / 3 segments (W = 36 -> 8,
+// 18 -> 16, 9 -> 32), so a warp is uniform in its row, every image gives H / 2 iterations and strips stay long (a first version with
+// 8-row iterations at W = 9 ran 2 iterations per CTA at 55 % lane utilisation: ncu r2q, 3.1 TB/s).  dz lives in a shared-memory ring
+// of 6 rows (+ zero halo columns): iteration k PRODUCES rows P_k = hs-1+2k .. (each thread its own 3 columns, from registers loaded
+// one iteration earlier), one __syncthreads, then CONSUMES output rows O_k = hs-2+2k .. : the 3x5 dz neighbourhood of the
+// thread's 3 columns is read once from shared memory (15 LDS.128) and used twice -- 27 fma4 into dx with the taps, 27 fma4 into the
+// nine dk accumulators with x.  O_k only touches P_{k-1} and P_k, P_{k+1} goes to the third ring slot, so one barrier per iteration
+// is enough.  All global loads of iteration k+1 are issued before the arithmetic of iteration k (9-12 x 16 B per thread in flight).
+#include <algorithm>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, const float4 x, const float4 k) {
+    a.x = fmaf(x.x, k.x, a.x); a.y = fmaf(x.y, k.y, a.y); a.z = fmaf(x.z, k.z, a.z); a.w = fmaf(x.w, k.w, a.w);
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+constexpr int FT = 192;          // threads per CTA = FQ channel quads x FP position slots
+constexpr int G = 2, NR = 3 * G; // rows per iteration, rows of the dz ring
+constexpr int NCONST = 9 + 7 + 4;   // taps | BN1: scale shift mean invstd gamma*invstd mean(dz) mean(dz*xhat) | BN2 below: scale shift xa xb
+
+struct FusedArgs {
+    const float* dA; const float* z; const float* x; const float* k; float* dx; float* dk;
+    const float* scale; const float* shift; const float* mean; const float* invstd; const float* gamma; const double* red1; double invM;
+    const float* pscale; const float* pshift; const float* pmean; const float* pinvstd; double* pred;
+    float rate, inv_keep; uint64_t seed; uint32_t layer; const uint64_t* seed_ptr;
+    int H, W, C4, NS, RS, nstrips, niter, nitems, rev;
+};
+
+// RED: a.x is the RAW pointwise output y of the block below (x is recomputed from it) and the BN2-backward reduction of that block is
+// accumulated into a.pred;  !RED: a.x is the block input itself.
+template <int FQ, bool RED>
+__global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr int FP = FT / FQ;
+    const int NS = a.NS, W = a.W, H = a.H, C4 = a.C4, C = C4 * 4;
+    const int WP = W + 2;
+    float4* ring = reinterpret_cast<float4*>(smraw);            // [NR][WP][FQ]
+    float4* cs = ring + (size_t)NR * WP * FQ;                   // [NCONST][FQ]
+    const int tq = threadIdx.x, tp = threadIdx.y;
+    const int g = tp / NS, seg = tp - g * NS, w0 = seg * 3;
+    const int c4 = blockIdx.x * FQ + tq;
+    const bool cok = c4 < C4, act = cok && g < G;
+    int item = blockIdx.y;
+    if (a.rev) item = a.nitems - 1 - item;
+    const int strip = item % a.nstrips, b = item / a.nstrips;
+    const int hs = strip * a.RS, he = min(H, hs + a.RS);
+
+    if (cok) for (int task = tp; task < (RED ? 11 : 10); task += FP) {
+        if (task < 9) cs[task * FQ + tq] = ldg4(a.k + (size_t)task * C + c4 * 4);
+        else if (task == 9) {
+            const float4 is = ldg4(a.invstd + c4 * 4), ga = ldg4(a.gamma + c4 * 4);
+            cs[9 * FQ + tq] = ldg4(a.scale + c4 * 4); cs[10 * FQ + tq] = ldg4(a.shift + c4 * 4);
+            cs[11 * FQ + tq] = ldg4(a.mean + c4 * 4); cs[12 * FQ + tq] = is;
+            cs[13 * FQ + tq] = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
+            const double* r1 = a.red1 + c4 * 4; const double* r2 = a.red1 + C + c4 * 4;
+            cs[14 * FQ + tq] = make_float4((float)(r1[0] * a.invM), (float)(r1[1] * a.invM), (float)(r1[2] * a.invM), (float)(r1[3] * a.invM));
+            cs[15 * FQ + tq] = make_float4((float)(r2[0] * a.invM), (float)(r2[1] * a.invM), (float)(r2[2] * a.invM), (float)(r2[3] * a.invM));
+        } else {
+            const float4 xa = ldg4(a.pinvstd + c4 * 4), mu = ldg4(a.pmean + c4 * 4);
+            cs[16 * FQ + tq] = ldg4(a.pscale + c4 * 4); cs[17 * FQ + tq] = ldg4(a.pshift + c4 * 4);
+            cs[18 * FQ + tq] = xa;                                                        // xhat = y*xa + xb
+            cs[19 * FQ + tq] = make_float4(-mu.x * xa.x, -mu.y * xa.y, -mu.z * xa.z, -mu.w * xa.w);
+        }
+    }
+    for (int r = tp; r < NR; r += FP) { ring[((size_t)r * WP) * FQ + tq] = zero4(); ring[((size_t)r * WP + W + 1) * FQ + tq] = zero4(); }
+    const uint64_t rseed = (RED && a.seed_ptr) ? *a.seed_ptr : a.seed;
+    __syncthreads();
+
+    const size_t rstride = (size_t)W * C;
+    const size_t col0 = ((size_t)b * H * W + w0) * C + (size_t)c4 * 4;      // (b, row 0, w0, c4): add row * rstride
+    float4 pa[3], pz[3], px[3];
+    auto load_p = [&](int rho) {
+        const bool v = act && rho >= 0 && rho < H;
+        const size_t o = col0 + (size_t)(v ? rho : 0) * rstride;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { pa[t] = v ? ldg4(a.dA + o + (size_t)t * C) : zero4(); pz[t] = v ? ldg4(a.z + o + (size_t)t * C) : zero4(); }
+    };
+    auto load_x = [&](int r) {
+        const bool v = act && r >= hs && r < he;
+        const size_t o = col0 + (size_t)(v ? r : 0) * rstride;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) px[t] = v ? ldg4(a.x + o + (size_t)t * C) : zero4();
+    };
+    float4 acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = zero4();
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+
+    load_p(hs - 1 + g);
+    load_x(hs - 2 + g);
+    int pslot = g, cslot = g + NR - 2;       // ring rows of P_k's row (2k+g) and of the first row O_k needs (2k+g-2), mod NR
+    for (int k = 0; k < a.niter; ++k) {
+        // ---- produce dz row hs-1+kG+g (columns w0..w0+2) into the ring
+        if (act) {
+            const int rho = hs - 1 + k * G + g;
+            float4* dst = ring + ((size_t)pslot * WP + w0 + 1) * FQ + tq;
+            if (rho >= 0 && rho < H) {
+                const float4 sc = cs[9 * FQ + tq], sh = cs[10 * FQ + tq], mu = cs[11 * FQ + tq], is = cs[12 * FQ + tq];
+                const float4 gs = cs[13 * FQ + tq], m1 = cs[14 * FQ + tq], m2 = cs[15 * FQ + tq];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    float4 o;
+#define DZ1(f) { const float zz = fmaf(pz[t].f, sc.f, sh.f); const float d = (zz >= 0.f && zz <= 6.f) ? pa[t].f : 0.f; \
+                 const float xh = (pz[t].f - mu.f) * is.f; o.f = gs.f * (d - m1.f - xh * m2.f); }
+                    DZ1(x) DZ1(y) DZ1(z) DZ1(w)
+#undef DZ1
+                    dst[t * FQ] = o;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) dst[t * FQ] = zero4();
+            }
+        }
+        if (k + 1 < a.niter) load_p(hs - 1 + (k + 1) * G + g);
+        float4 xc[3] = {px[0], px[1], px[2]};
+        if (k + 1 < a.niter) load_x(hs - 2 + (k + 1) * G + g);
+        __syncthreads();
+        // ---- consume: output row r = hs-2+kG+g needs dz rows r-1..r+1 = ring rows (kG+g-2 .. kG+g) mod NR
+        const int r = hs - 2 + k * G + g;
+        if (act && r >= hs && r < he) {
+            float dm[3][4];
+            float4 yv[3];
+            if (RED) {
+                const float4 psc = cs[16 * FQ + tq], psh = cs[17 * FQ + tq];
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    yv[o] = xc[o];
+                    if (a.rate > 0.f) crnn_dropout_mask4(rseed, a.layer, (uint64_t)(((size_t)(b * H + r) * W + w0 + o) * C4 + c4), a.rate, a.inv_keep, dm[o]);
+                    else { dm[o][0] = dm[o][1] = dm[o][2] = dm[o][3] = 1.f; }
+                    xc[o].x = relu6f(fmaf(yv[o].x, psc.x, psh.x)); xc[o].y = relu6f(fmaf(yv[o].y, psc.y, psh.y));
+                    xc[o].z = relu6f(fmaf(yv[o].z, psc.z, psh.z)); xc[o].w = relu6f(fmaf(yv[o].w, psc.w, psh.w));
+                    if (a.rate > 0.f) { xc[o].x *= dm[o][0]; xc[o].y *= dm[o][1]; xc[o].z *= dm[o][2]; xc[o].w *= dm[o][3]; }
+                }
+            }
+            float4 dxv[3] = {zero4(), zero4(), zero4()};
+#pragma unroll
+            for (int ar = 0; ar < 3; ++ar) {
+                const int rs = cslot + ar;
+                const float4* src = ring + ((size_t)(rs >= NR ? rs - NR : rs) * WP + w0) * FQ + tq;
+                float4 D[5];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) D[c] = src[c * FQ];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 kt = cs[(8 - (ar * 3 + c)) * FQ + tq];
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) { fma4(dxv[o], D[c + o], kt); fma4(acc[8 - (ar * 3 + c)], xc[o], D[c + o]); }
+                }
+            }
+            float* dst = a.dx + col0 + (size_t)r * rstride;
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                *reinterpret_cast<float4*>(dst + (size_t)o * C) = dxv[o];
+                if (RED) {
+                    const float4 psc = cs[16 * FQ + tq], psh = cs[17 * FQ + tq], xa = cs[18 * FQ + tq], xb = cs[19 * FQ + tq];
+                    const float d[4] = {dxv[o].x * dm[o][0], dxv[o].y * dm[o][1], dxv[o].z * dm[o][2], dxv[o].w * dm[o][3]};
+                    const float yy[4] = {yv[o].x, yv[o].y, yv[o].z, yv[o].w};
+                    const float scv[4] = {psc.x, psc.y, psc.z, psc.w}, shv[4] = {psh.x, psh.y, psh.z, psh.w};
+                    const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float zz = fmaf(yy[e], scv[e], shv[e]);
+                        const float dz = (zz >= 0.f && zz <= 6.f) ? d[e] : 0.f;
+                        s[e] += dz; sq[e] = fmaf(dz, fmaf(yy[e], xav[e], xbv[e]), sq[e]);
+                    }
+                }
+            }
+        }
+        pslot = pslot + G >= NR ? pslot + G - NR : pslot + G;
+        cslot = cslot + G >= NR ? cslot + G - NR : cslot + G;
+    }
+    // ---- CTA reductions: nine taps x 4 channels per thread -> one fp32 atomic per tap/channel; RED sums -> one fp64 atomic pair per channel
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smraw);               // [FP][36][FQ]
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        red[((tp * 36) + q * 4 + 0) * FQ + tq] = acc[q].x; red[((tp * 36) + q * 4 + 1) * FQ + tq] = acc[q].y;
+        red[((tp * 36) + q * 4 + 2) * FQ + tq] = acc[q].z; red[((tp * 36) + q * 4 + 3) * FQ + tq] = acc[q].w;
+    }
+    __syncthreads();
+    if (cok)
+        for (int e = tp; e < 36; e += FP) {
+            float sum = 0.f;
+            for (int yy = 0; yy < FP; ++yy) sum += red[(yy * 36 + e) * FQ + tq];
+            atomicAdd(a.dk + (size_t)(e >> 2) * C + c4 * 4 + (e & 3), sum);
+        }
+    if (!RED) return;
+    __syncthreads();
+    double* dsm = reinterpret_cast<double*>(smraw);             // [FP][8][FQ]
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dsm[(tp * 8 + e) * FQ + tq] = (double)s[e]; dsm[(tp * 8 + 4 + e) * FQ + tq] = (double)sq[e]; }
+    __syncthreads();
+    if (cok)
+        for (int e = tp; e < 8; e += FP) {
+            double t = 0.0;
+            for (int i = 0; i < FP; ++i) t += dsm[(i * 8 + e) * FQ + tq];
+            atomicAdd(a.pred + (e >> 2) * C + c4 * 4 + (e & 3), t);
+        }
+}
+
+int g_fused_off = -1;
+
+// channel quads per CTA for an image width: the largest of 8 / 16 / 32 that leaves 2 rows x W/3 position slots in 192 threads
+int fused_fq(int W) { const int ns = W / 3; return ns <= 3 ? 32 : (ns <= 6 ? 16 : 8); }
+
+}  // namespace
+
+// shapes the fused kernel handles (CRNN_DW_FUSED=0: none -> the caller keeps the separate kernels)
+int dwconv_bwd_fused_covers(int H, int W, int C) {
+    if (g_fused_off < 0) { const char* e = getenv("CRNN_DW_FUSED"); g_fused_off = (e && e[0] == '0') ? 1 : 0; }
+    return !(g_fused_off || C % 4 || W % 3 || W < 3 || W > 36 || H < 1);
+}
+
+int launch_dwconv_bwd_fused(const float* dA, const float* z, const float* x_or_y, const float* k, float* dx, float* dk,
+                            const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma, const double* red1,
+                            int B, int H, int W, int C, int rev, const DwRowsRed* red, double* red_buf, cudaStream_t st)
+{
+    if (!dwconv_bwd_fused_covers(H, W, C)) { crnn_set_error("dwconv_bwd_fused: shape not covered"); return CRNN_ERR_INVALID; }
+    if ((long long)B * H * W * C >= (1LL << 31)) { crnn_set_error("dwconv_bwd_fused: tensor too large"); return CRNN_ERR_INVALID; }
+    FusedArgs a = {};
+    a.dA = dA; a.z = z; a.x = x_or_y; a.k = k; a.dx = dx; a.dk = dk;
+    a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.red1 = red1; a.invM = 1.0 / ((double)B * H * W);
+    a.H = H; a.W = W; a.C4 = C / 4; a.NS = W / 3; a.rev = rev;
+    if (red) {
+        a.pscale = red->scale; a.pshift = red->shift; a.pmean = red->mean; a.pinvstd = red->invstd; a.pred = red_buf;
+        a.rate = red->rate; a.inv_keep = red->rate > 0.f ? 1.f / (1.f - red->rate) : 1.f; a.seed = red->seed; a.layer = red->layer; a.seed_ptr = red->seed_ptr;
+    }
+    const int FQ = fused_fq(W);
+    // strips: RS rows cost ceil((RS+2)/2) iterations of 2 rows plus a prologue / epilogue worth ~3 iterations (constants, first loads, the dk
+    // reduction); choose the count that maximises (useful rows per row-time) x (fill of the waves of 148 SMs x 2 resident CTAs); ties -> longer strips
+    const int gx = (a.C4 + FQ - 1) / FQ;
+    double best = -1.0; int best_rs = H;
+    for (int n = 1; n <= H; ++n) {
+        const int rs = (H + n - 1) / n;
+        if (rs < 4 * G && n > 1) break;
+        const int d = (H + rs - 1) / rs, it = (rs + 2 + G - 1) / G;
+        const long long ctas = (long long)gx * B * d, cap = 148LL * 2;
+        const double eff = (double)H / ((double)d * (it + 3) * G) * (double)ctas / (double)(((ctas + cap - 1) / cap) * cap);
+        if (eff > best + 1e-9) { best = eff; best_rs = rs; }
+    }
+    a.RS = best_rs; a.nstrips = (H + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G; a.nitems = B * a.nstrips;
+    const size_t ring = sizeof(float4) * ((size_t)NR * (W + 2) + NCONST) * FQ;
+    const size_t sm = std::max(ring, sizeof(float) * 36 * FT);
+    static bool attr_done = false;
+    if (!attr_done) {
+#define FATTR(FQ_, R_) cudaFuncSetAttribute(dwconv3x3_bwd_fused_kernel<FQ_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)
+        FATTR(8, false); FATTR(8, true); FATTR(16, false); FATTR(16, true); FATTR(32, false); FATTR(32, true);
+#undef FATTR
+        attr_done = true;
+    }
+    g_crnn_family = CRNN_FAM_DWROWS;
+    const dim3 grid(gx, (unsigned)a.nitems), block(FQ, FT / FQ);
+#define FLAUNCH(FQ_) do { if (red) dwconv3x3_bwd_fused_kernel<FQ_, true><<<grid, block, sm, st>>>(a); else dwconv3x3_bwd_fused_kernel<FQ_, false><<<grid, block, sm, st>>>(a); } while (0)
+    if (FQ == 8) FLAUNCH(8); else if (FQ == 16) FLAUNCH(16); else FLAUNCH(32);
+#undef FLAUNCH
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}

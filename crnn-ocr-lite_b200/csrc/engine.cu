@@ -120,6 +120,7 @@ struct crnn_handle {
     int bn2_red_done[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [block]: reduction pass of the block's BN2 backward already accumulated by the producer of its dy
     bool defer_bn_grads = false;   // full backward: dgamma/dbeta of all 14 BN layers in one launch at the end instead of 14 tiny ones
     bool fuse_bn_red = true;   // CRNN_FUSE_BN_RED=0: separate reduction pass for the ReLU6+BN backward after the depthwise conv
+    bool dw_fused = true;      // CRNN_DW_FUSED=0: separate ReLU6+BN-backward apply / depthwise backward-data / backward-weight kernels
     bool dw_red = true;        // CRNN_DW_RED=0: the depthwise backward-data kernel does not accumulate the BN2-backward reduction of the block below
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
@@ -636,22 +637,35 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
             TRY(gemm_nt(h, ST_GEMM_PW_DX, dpw, b.cout, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, ddw, b.cin, (int)Mi, b.cin, b.cout, 0, st));
         }
     }
-    ST(ST_BN_BWD, 20.0 * Mi * b.cin,
-       launch_relu6_bn_bwd(ddw, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
-                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st, h->rv(), fused_red ? 1 : 0, h->defer_bn_grads ? 0 : 1));
-    h->rv();
     const float* bin = i == 1 ? h->a("a0") : h->a(nm("block%d", i - 1));
-    {
-        cudaStream_t ss = side_after(h, st);
-        ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, ddw, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, ss));
-    }
-    // `other` becomes d(output of block i-1): when that block is not pooled, its BN2-backward reduction pass is accumulated by this kernel
+    // `other` becomes d(output of block i-1): when that block is not pooled, its BN2-backward reduction pass is accumulated by the kernel that writes it
     DwRowsRed rr; const DwRowsRed* rrp = nullptr; double* rbuf = nullptr;
-    if (i >= 2 && h->fuse_bn_red && h->dw_red && h->defer_bn_grads && kBlocks[i - 2].ph == 1 && kBlocks[i - 2].pw == 1) {
+    const bool prev_plain = i >= 2 && h->fuse_bn_red && h->dw_red && kBlocks[i - 2].ph == 1 && kBlocks[i - 2].pw == 1;
+    if (prev_plain) {
         const int pbn = 2 * (i - 1);
         rr.y = h->a(nm("pw%d", i - 1)); rr.scale = h->a(actbn(pbn, "scale")); rr.shift = h->a(actbn(pbn, "shift")); rr.mean = h->a(actbn(pbn, "mean"));
         rr.invstd = h->a(actbn(pbn, "invstd")); rr.rate = drop ? kDropBlock : 0.f; rr.seed = seed; rr.layer = (uint32_t)(i - 1); rr.seed_ptr = h->seed_ptr;
         rrp = &rr; rbuf = bn_red(h, pbn);
+    }
+    if (fused_red && h->dw_fused && dwconv_bwd_fused_covers(hh, ww, b.cin)) {
+        // one pass: ReLU6+BN backward apply, depthwise backward-data and backward-weight (dwconv_bwd_fused.cu); with `rrp` the block input is
+        // recomputed from the raw activation of the block below, whose BN2-backward reduction is accumulated on the way
+        ST(ST_DWCONV_BWD, 16.0 * Mi * b.cin,
+           launch_dwconv_bwd_fused(ddw, dw, rrp ? rr.y : bin, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)),
+                                   h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")), h->w(bnname(bn1, "gamma")),
+                                   bn_red(h, bn1), B, hh, ww, b.cin, h->rv(), rrp, rbuf, st));
+        if (!h->defer_bn_grads) ST(ST_BN_BWD, 0, launch_bn_param_grads(bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), b.cin, st));
+        if (i >= 2) h->bn2_red_done[i - 1] = rrp ? 1 : 0;
+        return CRNN_OK;
+    }
+    if (!h->defer_bn_grads) { rrp = nullptr; rbuf = nullptr; }      // the separate kernels only fuse that reduction inside the full backward
+    ST(ST_BN_BWD, 20.0 * Mi * b.cin,
+       launch_relu6_bn_bwd(ddw, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
+                           h->w(bnname(bn1, "gamma")), ddw, bn_red(h, bn1), h->g(bnname(bn1, "gamma")), h->g(bnname(bn1, "beta")), Mi, b.cin, st, h->rv(), fused_red ? 1 : 0, h->defer_bn_grads ? 0 : 1));
+    h->rv();
+    {
+        cudaStream_t ss = side_after(h, st);
+        ST(ST_DWCONV_BWD, 8.0 * Mi * b.cin, launch_dwconv_bwd_weight(bin, ddw, h->g(nm("depthwise_conv2d_%d/depthwise_kernel", i)), B, hh, ww, b.cin, ss));
     }
     int done = 0;
     ST(ST_DWCONV_BWD, (rrp ? 12.0 : 8.0) * Mi * b.cin /* + one read of the block-below's raw activation for the fused reduction */, launch_dwconv_bwd_data(ddw, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), other, B, hh, ww, b.cin, 0, st, h->rv(), rrp, rbuf, &done));
@@ -802,6 +816,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_FUSE_BN_RED"); h->fuse_bn_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_DW_RED"); h->dw_red = !(e && e[0] == '0'); }
+    { const char* e = getenv("CRNN_DW_FUSED"); h->dw_fused = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }
@@ -1097,6 +1112,7 @@ int crnn_debug_block_backward(crnn_handle* h, int block, const float* dout_dev, 
     CUDA_TRY(cudaMemsetAsync(h->a("red"), 0, sizeof(double) * h->bn_off[15], st));
     CUDA_TRY(cudaMemcpyAsync(h->a("gA"), dout_dev, sizeof(float) * n_out, cudaMemcpyDeviceToDevice, st));
     h->ev_used = 0;
+    for (int i = 0; i < 8; ++i) h->bn2_red_done[i] = 0;
     TRY(block_backward(h, block, hh, ww, h->a("gA"), h->a("gB"), B, dropout_seed != 0, dropout_seed, st));
     side_join(h, st);
     CUDA_TRY(cudaMemcpyAsync(din_dev, h->a("gB"), sizeof(float) * n_in, cudaMemcpyDeviceToDevice, st));

@@ -726,12 +726,15 @@ def test_switch_paths_stay_correct():
     """The A/B switches that select alternative kernels are read once per process, so each configuration re-runs a slice of this file in a
     subprocess: CRNN_DWCONV_V1=1 (channel-block depthwise kernels for every block, not only C = 1), CRNN_GEMM_PAIR=1 (cta_group::2
     schedule of the tcgen05 GEMM inside the real step), CRNN_FUSE_BN_RED=0 / CRNN_DW_RED=0 (unfused BatchNorm-backward reductions),
-    CRNN_GRAPH=0 CRNN_OVERLAP=0 (eager, single stream).  Every path must pass the same forward / isolated-backward parity tests."""
+    CRNN_DW_FUSED=0 (separate BN-apply / depthwise backward-data / backward-weight kernels instead of dwconv_bwd_fused.cu),
+    CRNN_GRAPH=0 CRNN_OVERLAP=0 (eager, single stream).  Every path must pass the same forward / isolated-backward / train-step parity tests."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sel = "test_forward_inference_parity and 128-gru or test_block_backward_isolated and 100-4 or test_block_backward_isolated and 6-128-64"
-    for env in ({"CRNN_DWCONV_V1": "1"}, {"CRNN_GEMM_PAIR": "1"}, {"CRNN_FUSE_BN_RED": "0"}, {"CRNN_DW_RED": "0"}, {"CRNN_GRAPH": "0", "CRNN_OVERLAP": "0"}):
+    sel = ("test_forward_inference_parity and 128-gru or test_block_backward_isolated and 100-4 or test_block_backward_isolated and 6-128-64"
+           " or test_train_step_parity and 128-gru-6")
+    for env in ({"CRNN_DWCONV_V1": "1"}, {"CRNN_GEMM_PAIR": "1"}, {"CRNN_FUSE_BN_RED": "0"}, {"CRNN_DW_RED": "0"}, {"CRNN_DW_FUSED": "0"},
+                {"CRNN_DW_FUSED": "0", "CRNN_DW_RED": "0"}, {"CRNN_GRAPH": "0", "CRNN_OVERLAP": "0"}):
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k", sel],
                            capture_output=True, text=True, timeout=900, env=dict(os.environ, **env), cwd=root)
         assert r.returncode == 0 and " passed" in r.stdout, "%s: %s" % (env, r.stdout[-1500:] + r.stderr[-500:])
