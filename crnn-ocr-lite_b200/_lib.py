@@ -20,9 +20,15 @@ class TensorInfo(ctypes.Structure):
     _fields_ = [("offset", ctypes.c_int64), ("numel", ctypes.c_int64), ("is_int", ctypes.c_int32)]
 
 
+class Optimizer(ctypes.Structure):
+    """struct crnn_optimizer (include/crnn_b200.h)."""
+    _fields_ = [("kind", ctypes.c_int), ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
+                ("decay", ctypes.c_float), ("momentum", ctypes.c_float), ("clipnorm", ctypes.c_float)]
+
+
 # every symbol include/crnn_b200.h declares
 SYMBOLS = ["crnn_last_error", "crnn_version", "crnn_workspace_bytes", "crnn_create", "crnn_destroy", "crnn_num_tensors",
-           "crnn_tensor_name", "crnn_tensor_lookup", "crnn_forward", "crnn_forward_host", "crnn_train_fwd_bwd", "crnn_adam_step",
+           "crnn_tensor_name", "crnn_tensor_lookup", "crnn_forward", "crnn_forward_host", "crnn_train_fwd_bwd", "crnn_train_on_batch_host", "crnn_adam_step",
            "crnn_sgd_step", "crnn_get_iterations", "crnn_set_iterations", "crnn_ctc_status", "crnn_ctc_loss_grad", "crnn_ctc_greedy",
            "crnn_ctc_beam", "crnn_ctc_beam_topk", "crnn_ctc_beam_host", "crnn_ctc_greedy_host", "crnn_edit_distance", "crnn_edit_distance_host", "crnn_normalize_u8", "crnn_gemm", "crnn_debug_block_backward", "crnn_gemm_tc", "crnn_gemm_tc_dw", "crnn_gemm_tc_scratch_floats", "crnn_launch_count",
            "crnn_profile_enable", "crnn_profile_num_stages", "crnn_profile_stage_name", "crnn_profile_report",
@@ -57,6 +63,8 @@ def load():
     lib.crnn_forward.argtypes = [vp, vp, i32, vp, vp]
     lib.crnn_forward_host.argtypes = [vp, vp, i32, vp, vp]
     lib.crnn_train_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, i32, vp, u64, vp]
+    lib.crnn_train_on_batch_host.argtypes = [vp, vp, i32, f32, f32, vp, vp, vp, i32, u64, ctypes.POINTER(Optimizer), f32, vp,
+                                             ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), vp]
     lib.crnn_adam_step.argtypes = [vp, f32, f32, f32, f32, f32, f32, vp]
     lib.crnn_sgd_step.argtypes = [vp, f32, f32, f32, f32, f32, vp]
     lib.crnn_get_iterations.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]

@@ -134,6 +134,8 @@ struct crnn_handle {
     // stream its all-reduces run on.  With `dp_fused` the training step itself issues the exchange, in two buckets: the head gradients
     // (dense1 .. dense2 = the tail of the arena, ~70 % of the bytes) as soon as their weight-gradient GEMMs are done, overlapping the whole
     // conv-stack backward; the conv-stack + STN bucket at the end of the step.
+    // pinned host staging of crnn_train_on_batch_host: [x (float or u8) | labels | label_len | input_len | losses | status]
+    unsigned char* pin = nullptr; size_t pin_bytes = 0;
     void* comm = nullptr; bool comm_owned = false; int comm_ranks = 1; bool dp_fused = false;
     cudaStream_t comm_stream = nullptr;
     int64_t head_off = 0;     // first float of dense1/kernel inside the arenas
@@ -363,6 +365,7 @@ void plan(crnn_handle* h) {
     L.add("act/sumsq", 1, 8); L.add("act/seed", 1, 8);
     L.add("act/status", 1, 4, 1);
     L.add("act/labels", B * c.max_len, 4, 1); L.add("act/label_len", B, 4, 1); L.add("act/input_len", B, 4, 1);
+    L.add("act/x_u8", (B * h->H * h->W + 3) / 4, 4, 1);           // raw 8-bit images of crnn_train_on_batch_host (normalised on the device)
     L.cursor = (L.cursor + 255) & ~(int64_t)255;
 }
 
@@ -835,6 +838,7 @@ int crnn_destroy(crnn_handle* h) {
     if (h->cap) cudaStreamDestroy(h->cap);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->pin) cudaFreeHost(h->pin);
     delete h;
     return CRNN_OK;
 }
@@ -910,6 +914,56 @@ int crnn_sgd_step(crnn_handle* h, float lr, float decay, float momentum, float c
     h->iterations += 1;
     return CRNN_OK;
 }
+// model.train_on_batch (train.py:201-209 through fit_generator) in ONE call on host buffers: staging into pinned memory (skipped for a
+// buffer that already is pinned / registered), H2D, the graphed forward + backward (+ in-step gradient exchange under data parallel),
+// the optimiser step, D2H of the per-sample losses and the CTC status, one stream synchronisation.
+int crnn_train_on_batch_host(crnn_handle* h, const void* x_host, int x_is_u8, float mean, float stdv, const int32_t* labels_host,
+                             const int32_t* label_len_host, const int32_t* input_len_host, int B, uint64_t dropout_seed,
+                             const crnn_optimizer* opt, float grad_scale, float* losses_host, float* mean_loss, int32_t* ctc_status, void* stream) {
+    if (!h || !x_host || !labels_host || !label_len_host || !input_len_host || !opt) { crnn_set_error("null argument"); return CRNN_ERR_INVALID; }
+    if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
+    if (opt->kind != CRNN_OPT_ADAM && opt->kind != CRNN_OPT_SGD) { crnn_set_error("unknown optimizer kind %d", opt->kind); return CRNN_ERR_INVALID; }
+    if (x_is_u8 && !(stdv != 0.f)) { crnn_set_error("std must be non-zero"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t npx = (size_t)h->H * h->W, ML = (size_t)h->cfg.max_len, mB = (size_t)h->maxB;
+    const size_t off_lab = (mB * npx * 4 + 255) / 256 * 256, off_ll = off_lab + mB * ML * 4, off_il = off_ll + mB * 4, off_loss = off_il + mB * 4,
+                 off_st = off_loss + mB * 4, total = off_st + 64;
+    if (!h->pin) { CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->pin), total, cudaHostAllocDefault)); h->pin_bytes = total; }
+    const size_t xbytes = (size_t)B * npx * (x_is_u8 ? 1 : 4);
+    const void* xsrc = x_host;
+    {   // large operand: copy through the pinned buffer unless the caller's memory already is page-locked
+        cudaPointerAttributes at; const cudaError_t e = cudaPointerGetAttributes(&at, x_host);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (e != cudaSuccess || at.type != cudaMemoryTypeHost) { memcpy(h->pin, x_host, xbytes); xsrc = h->pin; }
+    }
+    memcpy(h->pin + off_lab, labels_host, (size_t)B * ML * 4); memcpy(h->pin + off_ll, label_len_host, (size_t)B * 4); memcpy(h->pin + off_il, input_len_host, (size_t)B * 4);
+    int32_t* lab = reinterpret_cast<int32_t*>(h->f("act/labels")); int32_t* ll = reinterpret_cast<int32_t*>(h->f("act/label_len"));
+    int32_t* il = reinterpret_cast<int32_t*>(h->f("act/input_len"));
+    if (x_is_u8) {
+        uint8_t* xu = reinterpret_cast<uint8_t*>(h->f("act/x_u8"));
+        CUDA_TRY(cudaMemcpyAsync(xu, xsrc, xbytes, cudaMemcpyHostToDevice, st));
+        TRY(launch_normalize_u8(xu, h->a("x"), (long long)B * npx, mean, stdv, st));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(h->a("x"), xsrc, xbytes, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(lab, h->pin + off_lab, (size_t)B * ML * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ll, h->pin + off_ll, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(il, h->pin + off_il, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    TRY(crnn_train_fwd_bwd(h, h->a("x"), lab, ll, il, B, nullptr, dropout_seed, stream));
+    if (opt->kind == CRNN_OPT_ADAM) TRY(crnn_adam_step(h, opt->lr, opt->beta1, opt->beta2, opt->eps, opt->clipnorm, grad_scale, stream));
+    else TRY(crnn_sgd_step(h, opt->lr, opt->decay, opt->momentum, opt->clipnorm, grad_scale, stream));
+    CUDA_TRY(cudaMemcpyAsync(h->pin + off_loss, h->a("loss"), (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->pin + off_st, h->a("status"), 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const float* lh = reinterpret_cast<const float*>(h->pin + off_loss);
+    double acc = 0.0;
+    for (int b = 0; b < B; ++b) acc += (double)lh[b];
+    if (losses_host) memcpy(losses_host, lh, (size_t)B * 4);
+    if (mean_loss) *mean_loss = (float)(acc / B);
+    if (ctc_status) *ctc_status = *reinterpret_cast<const int32_t*>(h->pin + off_st);
+    return CRNN_OK;
+}
+
 // ---------------------------------------------------------------- data parallel (NEW capability; the reference is single-device, train.py:111,116)
 static void drop_graphs(crnn_handle* h) {
     for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);

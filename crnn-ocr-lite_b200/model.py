@@ -375,6 +375,14 @@ class CRNNModel:
 
     def train_on_batch(self, inputs, outputs=None):
         """Keras train_on_batch on the generator's dict (utils.py:495-502): host buffers in, scalar mean loss out."""
+        from . import parallel
+        if parallel.world_size() <= 1:
+            return self._train_on_batch_host(inputs)
+        return self._train_on_batch_staged(inputs)
+
+    def _train_on_batch_staged(self, inputs):
+        """The same step assembled from the device-level entry points (torch pinned staging, crnn_train_fwd_bwd, gradient exchange,
+        optimiser step): the data-parallel path, where the monitored loss is all-reduced between the step and the read-back."""
         xd = self._stage_input(inputs["the_input"])
         B = xd.shape[0]
         lab = self._stage("labels", np.asarray(inputs["the_labels"]).astype(np.int32), torch.int32)
@@ -405,6 +413,42 @@ class CRNNModel:
         if st != 0:
             raise ValueError(f"Not enough time for target transition sequence (batch element {-st - 1})")
         return float(pin[0][:B].numpy().mean(dtype=np.float64))
+
+    def _train_on_batch_host(self, inputs):
+        """Single process: the whole step is ONE C-ABI call on the host arrays (crnn_train_on_batch_host: staging, H2D, forward + backward,
+        optimiser, D2H of losses + CTC status, one synchronisation)."""
+        o = self.optimizer
+        if o is None:
+            raise RuntimeError("compile(optimizer=...) first")
+        x = np.ascontiguousarray(inputs["the_input"])
+        if x.dtype != np.uint8:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        B = int(x.shape[0])
+        if x.size != B * self.imgh * self.imgw:
+            raise ValueError(f"the_input has {x.size} elements, expected {B}x{self.imgh}x{self.imgw}")
+        lab = np.ascontiguousarray(inputs["the_labels"], dtype=np.int32).reshape(B, -1)
+        if lab.shape[1] != self.max_len:
+            raise ValueError(f"the_labels must be (B, {self.max_len}), got {lab.shape}")
+        ll = np.ascontiguousarray(inputs["label_length"], dtype=np.int32).reshape(-1)
+        il = np.ascontiguousarray(inputs["input_length"], dtype=np.int32).reshape(-1)
+        if ll.size != B or il.size != B:
+            raise ValueError("label_length / input_length must have one entry per sample")
+        self._step_seed = (int(self._step_seed) * 6364136223846793005 + 1442695040888963407) % (1 << 64) | 1
+        so = self.__dict__.get("_opt_struct")
+        if so is None:
+            so = self._opt_struct = _lib.Optimizer()
+        if o.kind == "adam":
+            so.kind, so.lr, so.beta1, so.beta2, so.eps, so.clipnorm = 0, o.lr, o.beta_1, o.beta_2, o.epsilon, o.clipnorm or 0.0
+        else:
+            so.kind, so.lr, so.decay, so.momentum, so.clipnorm = 1, o.lr, o.decay, o.momentum, o.clipnorm or 0.0
+        mean, st = ctypes.c_float(), ctypes.c_int32()
+        _lib.check(self.lib.crnn_train_on_batch_host(
+            self.handle, x.ctypes.data, 1 if x.dtype == np.uint8 else 0, float(np.float32(self.input_mean)), float(np.float32(self.input_std)),
+            lab.ctypes.data, ll.ctypes.data, il.ctypes.data, B, ctypes.c_uint64(self._step_seed if self.dropout else 0), ctypes.byref(so), 1.0, None,
+            ctypes.byref(mean), ctypes.byref(st), self._stream()))
+        if st.value != 0:
+            raise ValueError(f"Not enough time for target transition sequence (batch element {-st.value - 1})")
+        return float(mean.value)
 
     def test_on_batch(self, inputs, outputs=None):
         """Validation loss: inference-mode forward + CTC loss (no gradient)."""

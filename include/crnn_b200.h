@@ -90,6 +90,20 @@ int crnn_adam_step(crnn_handle* h, float lr, float beta1, float beta2, float eps
 int crnn_sgd_step(crnn_handle* h, float lr, float decay, float momentum, float clipnorm, float grad_scale, void* stream);
 int crnn_get_iterations(const crnn_handle* h, int64_t* it);
 int crnn_set_iterations(crnn_handle* h, int64_t it);
+/* model.train_on_batch on HOST buffers in one call (train.py:201-209: what fit_generator does per batch of the generator's dict,
+ * utils.py:495-502): x_host = B*imgh*imgw float32 (already normalised, utils.py:415) or, with x_is_u8, the raw 8-bit images (norm() with
+ * mean/std runs on the device); labels (B*max_len), label_len (B), input_len (B) int32.  Copies through an internal pinned buffer (a
+ * page-locked x_host is used in place), runs crnn_train_fwd_bwd + the optimiser step, reads back the per-sample losses (optional,
+ * B floats), their mean and the CTC status (0, or -(b+1) for the first sample whose labels do not fit its input length), synchronises. */
+#define CRNN_OPT_ADAM 0
+#define CRNN_OPT_SGD 1
+typedef struct crnn_optimizer {
+    int kind;                       /* CRNN_OPT_ADAM: lr, beta1, beta2, eps, clipnorm;  CRNN_OPT_SGD (Nesterov): lr, decay, momentum, clipnorm */
+    float lr, beta1, beta2, eps, decay, momentum, clipnorm;
+} crnn_optimizer;
+int crnn_train_on_batch_host(crnn_handle* h, const void* x_host, int x_is_u8, float mean, float std, const int32_t* labels_host,
+                             const int32_t* label_len_host, const int32_t* input_len_host, int B, uint64_t dropout_seed,
+                             const crnn_optimizer* opt, float grad_scale, float* losses_host, float* mean_loss, int32_t* ctc_status, void* stream);
 /* status of the last CTC loss launch (read after a stream sync): 0 or -(b+1) for the first infeasible sample */
 int crnn_ctc_status(crnn_handle* h, int32_t* status_host, void* stream);
 

@@ -722,6 +722,49 @@ def test_full_model_checkpoint_roundtrip_on_device(cb, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("opt,u8", [("adam", False), ("sgd", True)])
+def test_train_on_batch_host_call_equals_staged_path(cb, opt, u8):
+    """crnn_train_on_batch_host (one C-ABI call on host arrays: what train_on_batch uses in a single process) against the same step assembled
+    from the device-level entry points (the data-parallel path), float32 and raw uint8 input, both optimisers: same loss, same gradients and
+    same updated parameters after one step up to the run-to-run noise of the fp32 atomics (two runs of ONE path differ by the same amount;
+    after a few steps of this randomised net that noise is amplified chaotically, so the comparison is per step from identical weights).
+    An infeasible label sequence raises the reference's error through the status word."""
+    cfg = N.Cfg(imgh=128)
+    B = 6
+    rng = np.random.RandomState(11)
+    models = []
+    for _ in range(2):
+        _, m = _make(cb, cfg, B, 5)
+        m.compile(optimizer=cb.Adam(lr=1e-3, beta_1=0.5, beta_2=0.999, clipnorm=5.0) if opt == "adam" else cb.SGD(lr=0.02, decay=1e-6, momentum=0.9, nesterov=True, clipnorm=5))
+        m._step_seed = 0x1234567       # same dropout-mask sequence in both models
+        models.append(m)
+    xs = rng.randint(0, 256, size=(2, B, cfg.imgh, cfg.imgw, 1)).astype(np.uint8)
+    labs = rng.randint(0, 37, size=(2, B, cfg.max_len)).astype(np.int32)
+    L = rng.randint(3, 12, size=(2, B, 1)).astype(np.int32)
+    il = np.full((B, 1), cfg.T - 2, np.int32)
+    w0 = models[0].get_weights()
+    for s in range(2):
+        x = xs[s] if u8 else ((xs[s].astype(np.float32) - np.float32(models[0].input_mean)) / np.float32(models[0].input_std))
+        d = {"the_input": x, "the_labels": labs[s], "input_length": il, "label_length": L[s]}
+        la = models[0]._train_on_batch_host(d)
+        lb = models[1]._train_on_batch_staged(d)
+        assert abs(la - lb) <= (1e-5 if s == 0 else 2e-2) * max(1.0, abs(lb)), (s, la, lb)
+        if s == 0:
+            ga, gb = models[0].get_grads(), models[1].get_grads()
+            assert list(ga) == list(gb)
+            for k in ga:
+                np.testing.assert_allclose(ga[k], gb[k], rtol=1e-3, atol=1e-4 * max(1e-3, float(np.abs(gb[k]).max())), err_msg=k)
+            if opt == "sgd":            # linear in the gradient (Adam's first step is lr * sign(g): noise flips it where g ~ 0)
+                wa, wb = models[0].get_weights(), models[1].get_weights()
+                for k in ga:
+                    np.testing.assert_allclose(wa[k] - w0[k], wb[k] - w0[k], rtol=1e-3, atol=2e-4 * max(1e-6, float(np.abs(wb[k] - w0[k]).max())), err_msg=k)
+    assert models[0].iterations() == models[1].iterations() == 2
+    bad = {"the_input": xs[0], "the_labels": labs[0], "input_length": np.full((B, 1), 4, np.int32), "label_length": np.full((B, 1), 12, np.int32)}
+    with pytest.raises(ValueError, match="Not enough time for target transition sequence"):
+        models[0]._train_on_batch_host(bad)
+
+
+@pytest.mark.gpu
 def test_switch_paths_stay_correct():
     """The A/B switches that select alternative kernels are read once per process, so each configuration re-runs a slice of this file in a
     subprocess: CRNN_DWCONV_V1=1 (channel-block depthwise kernels for every block, not only C = 1), CRNN_GEMM_PAIR=1 (cta_group::2
