@@ -30,7 +30,7 @@ class Optimizer(ctypes.Structure):
 SYMBOLS = ["crnn_last_error", "crnn_version", "crnn_workspace_bytes", "crnn_create", "crnn_destroy", "crnn_num_tensors",
            "crnn_tensor_name", "crnn_tensor_lookup", "crnn_forward", "crnn_forward_host", "crnn_train_fwd_bwd", "crnn_train_on_batch_host", "crnn_adam_step",
            "crnn_sgd_step", "crnn_get_iterations", "crnn_set_iterations", "crnn_ctc_status", "crnn_ctc_loss_grad", "crnn_ctc_greedy",
-           "crnn_ctc_beam", "crnn_ctc_beam_topk", "crnn_ctc_beam_host", "crnn_ctc_greedy_host", "crnn_edit_distance", "crnn_edit_distance_host", "crnn_normalize_u8", "crnn_gemm", "crnn_debug_block_backward", "crnn_gemm_tc", "crnn_gemm_tc_dw", "crnn_gemm_tc_scratch_floats", "crnn_launch_count",
+           "crnn_ctc_beam", "crnn_ctc_beam_topk", "crnn_ctc_beam_host", "crnn_ctc_greedy_host", "crnn_edit_distance", "crnn_edit_distance_host", "crnn_normalize_u8", "crnn_gemm", "crnn_debug_block_backward", "crnn_debug_materialize_blocks", "crnn_gemm_tc", "crnn_gemm_tc_dw", "crnn_gemm_tc_scratch_floats", "crnn_launch_count",
            "crnn_profile_enable", "crnn_profile_num_stages", "crnn_profile_stage_name", "crnn_profile_report",
            "crnn_profile_num_families", "crnn_profile_family_name", "crnn_profile_report2",
            "crnn_bilinear_sample", "crnn_nccl_unique_id", "crnn_comm_init_rank", "crnn_set_comm", "crnn_set_dp_fused", "crnn_comm_ranks", "crnn_allreduce_grads"]
@@ -83,6 +83,7 @@ def load():
     lib.crnn_launch_count.restype = ctypes.c_longlong
     lib.crnn_gemm_tc.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.crnn_debug_block_backward.argtypes = [vp, i32, vp, vp, i32, u64, vp]
+    lib.crnn_debug_materialize_blocks.argtypes = [vp, vp]
     lib.crnn_gemm_tc_dw.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.crnn_gemm_tc_scratch_floats.restype = ctypes.c_longlong
     lib.crnn_gemm_tc_scratch_floats.argtypes = [i32, i32]

@@ -1,4 +1,4 @@
-// dwconv_bwd_fused.cu -- ONE kernel for everything between the pointwise dX GEMM and the block below in the backward pass of a
+// dwconv_fused.cu -- (1) backward: ONE kernel for everything between the pointwise dX GEMM and the block below in the backward pass of a
 // depthwise-separable block (utils.py:43-52: DepthwiseConv2D 3x3 -> BatchNormalization -> ReLU6), sm_100a, NHWC fp32:
 //     dz  = BN backward( dA * 1[0 <= bn(z) <= 6] )          (was relu6_bn_bwd apply: read dA, z; write dz)
 //     dx  = depthwise3x3^T(dz)                               (was dwconv3x3_rows<FLIP>: read dz; write dx)
@@ -217,7 +217,137 @@ __global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedA
         }
 }
 
+// ================================================================================================= forward
+// (2) forward: the depthwise conv of block i reads the RAW pointwise output y of a non-pooled block i-1 and applies that block's
+// BatchNorm + ReLU6 + Dropout (utils.py:53-56) while staging its input rows in shared memory, so the `block{i-1}` tensor is neither
+// written (act_pool_fwd launch gone) nor read: two tensor passes (y in, conv out) instead of four.  Same CTA layout and ring as above;
+// every input element is transformed exactly once (the register-marching kernel in dwconv_rows.cu re-loads halo columns, which would
+// repeat the mask hash 1.67x).  Also accumulates the BatchNorm statistics of its output (training).
+struct FwdArgs {
+    const float* y; const float* k; float* out; double* stats;
+    const float* pscale; const float* pshift; float rate, inv_keep; uint64_t seed; uint32_t layer; const uint64_t* seed_ptr;
+    int H, W, C4, NS, RS, nstrips, niter, nitems, rev;
+};
+
+template <int FQ>
+__global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr int FP = FT / FQ;
+    const int NS = a.NS, W = a.W, H = a.H, C4 = a.C4, C = C4 * 4;
+    const int WP = W + 2;
+    float4* ring = reinterpret_cast<float4*>(smraw);            // [NR][WP][FQ]
+    float4* cs = ring + (size_t)NR * WP * FQ;                   // [9 taps + scale + shift][FQ]
+    const int tq = threadIdx.x, tp = threadIdx.y;
+    const int g = tp / NS, seg = tp - g * NS, w0 = seg * 3;
+    const int c4 = blockIdx.x * FQ + tq;
+    const bool cok = c4 < C4, act = cok && g < G;
+    int item = blockIdx.y;
+    if (a.rev) item = a.nitems - 1 - item;
+    const int strip = item % a.nstrips, b = item / a.nstrips;
+    const int hs = strip * a.RS, he = min(H, hs + a.RS);
+    if (cok) for (int task = tp; task < 11; task += FP)
+        cs[task * FQ + tq] = task < 9 ? ldg4(a.k + (size_t)task * C + c4 * 4) : ldg4((task == 9 ? a.pscale : a.pshift) + c4 * 4);
+    for (int r = tp; r < NR; r += FP) { ring[((size_t)r * WP) * FQ + tq] = zero4(); ring[((size_t)r * WP + W + 1) * FQ + tq] = zero4(); }
+    const uint64_t rseed = a.seed_ptr ? *a.seed_ptr : a.seed;
+    __syncthreads();
+
+    const size_t rstride = (size_t)W * C;
+    const size_t col0 = ((size_t)b * H * W + w0) * C + (size_t)c4 * 4;
+    float4 py[3];
+    auto load_y = [&](int rho) {
+        const bool v = act && rho >= 0 && rho < H;
+        const size_t o = col0 + (size_t)(v ? rho : 0) * rstride;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) py[t] = v ? ldg4(a.y + o + (size_t)t * C) : zero4();
+    };
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    load_y(hs - 1 + g);
+    int pslot = g, cslot = g + NR - 2;
+    for (int k = 0; k < a.niter; ++k) {
+        if (act) {
+            const int rho = hs - 1 + k * G + g;
+            float4* dst = ring + ((size_t)pslot * WP + w0 + 1) * FQ + tq;
+            if (rho >= 0 && rho < H) {
+                const float4 sc = cs[9 * FQ + tq], sh = cs[10 * FQ + tq];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    float4 o;
+                    o.x = relu6f(fmaf(py[t].x, sc.x, sh.x)); o.y = relu6f(fmaf(py[t].y, sc.y, sh.y));
+                    o.z = relu6f(fmaf(py[t].z, sc.z, sh.z)); o.w = relu6f(fmaf(py[t].w, sc.w, sh.w));
+                    if (a.rate > 0.f) {
+                        float dm[4];
+                        crnn_dropout_mask4(rseed, a.layer, (uint64_t)(((size_t)(b * H + rho) * W + w0 + t) * C4 + c4), a.rate, a.inv_keep, dm);
+                        o.x *= dm[0]; o.y *= dm[1]; o.z *= dm[2]; o.w *= dm[3];
+                    }
+                    dst[t * FQ] = o;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) dst[t * FQ] = zero4();
+            }
+        }
+        if (k + 1 < a.niter) load_y(hs - 1 + (k + 1) * G + g);
+        __syncthreads();
+        const int r = hs - 2 + k * G + g;
+        if (act && r >= hs && r < he) {
+            float4 ov[3] = {zero4(), zero4(), zero4()};
+#pragma unroll
+            for (int ar = 0; ar < 3; ++ar) {
+                const int rs = cslot + ar;
+                const float4* src = ring + ((size_t)(rs >= NR ? rs - NR : rs) * WP + w0) * FQ + tq;
+                float4 D[5];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) D[c] = src[c * FQ];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 kt = cs[(ar * 3 + c) * FQ + tq];
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) fma4(ov[o], D[c + o], kt);
+                }
+            }
+            float* dst = a.out + col0 + (size_t)r * rstride;
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                *reinterpret_cast<float4*>(dst + (size_t)o * C) = ov[o];
+                s[0] += ov[o].x; s[1] += ov[o].y; s[2] += ov[o].z; s[3] += ov[o].w;
+                sq[0] = fmaf(ov[o].x, ov[o].x, sq[0]); sq[1] = fmaf(ov[o].y, ov[o].y, sq[1]);
+                sq[2] = fmaf(ov[o].z, ov[o].z, sq[2]); sq[3] = fmaf(ov[o].w, ov[o].w, sq[3]);
+            }
+        }
+        pslot = pslot + G >= NR ? pslot + G - NR : pslot + G;
+        cslot = cslot + G >= NR ? cslot + G - NR : cslot + G;
+    }
+    if (!a.stats) return;
+    __syncthreads();
+    double* dsm = reinterpret_cast<double*>(smraw);             // [FP][8][FQ]
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dsm[(tp * 8 + e) * FQ + tq] = (double)s[e]; dsm[(tp * 8 + 4 + e) * FQ + tq] = (double)sq[e]; }
+    __syncthreads();
+    if (cok)
+        for (int e = tp; e < 8; e += FP) {
+            double t = 0.0;
+            for (int i = 0; i < FP; ++i) t += dsm[(i * 8 + e) * FQ + tq];
+            atomicAdd(a.stats + (e >> 2) * C + c4 * 4 + (e & 3), t);
+        }
+}
+
 int g_fused_off = -1;
+
+// strips: RS rows cost ceil((RS+2)/2) iterations of 2 rows plus a prologue / epilogue worth ~3 iterations (constants, first loads, the CTA
+// reductions); choose the count that maximises (useful rows per row-time) x (fill of the waves of 148 SMs x `occ` resident CTAs); ties -> longer strips
+int plan_strips(int B, int H, int gx, int occ) {
+    double best = -1.0; int best_rs = H;
+    for (int n = 1; n <= H; ++n) {
+        const int rs = (H + n - 1) / n;
+        if (rs < 4 * G && n > 1) break;
+        const int d = (H + rs - 1) / rs, it = (rs + 2 + G - 1) / G;
+        const long long ctas = (long long)gx * B * d, cap = 148LL * occ;
+        const double eff = (double)H / ((double)d * (it + 3) * G) * (double)ctas / (double)(((ctas + cap - 1) / cap) * cap);
+        if (eff > best + 1e-9) { best = eff; best_rs = rs; }
+    }
+    return best_rs;
+}
 
 // channel quads per CTA for an image width: the largest of 8 / 16 / 32 that leaves 2 rows x W/3 position slots in 192 threads
 int fused_fq(int W) { const int ns = W / 3; return ns <= 3 ? 32 : (ns <= 6 ? 16 : 8); }
@@ -245,19 +375,8 @@ int launch_dwconv_bwd_fused(const float* dA, const float* z, const float* x_or_y
         a.rate = red->rate; a.inv_keep = red->rate > 0.f ? 1.f / (1.f - red->rate) : 1.f; a.seed = red->seed; a.layer = red->layer; a.seed_ptr = red->seed_ptr;
     }
     const int FQ = fused_fq(W);
-    // strips: RS rows cost ceil((RS+2)/2) iterations of 2 rows plus a prologue / epilogue worth ~3 iterations (constants, first loads, the dk
-    // reduction); choose the count that maximises (useful rows per row-time) x (fill of the waves of 148 SMs x 2 resident CTAs); ties -> longer strips
     const int gx = (a.C4 + FQ - 1) / FQ;
-    double best = -1.0; int best_rs = H;
-    for (int n = 1; n <= H; ++n) {
-        const int rs = (H + n - 1) / n;
-        if (rs < 4 * G && n > 1) break;
-        const int d = (H + rs - 1) / rs, it = (rs + 2 + G - 1) / G;
-        const long long ctas = (long long)gx * B * d, cap = 148LL * 2;
-        const double eff = (double)H / ((double)d * (it + 3) * G) * (double)ctas / (double)(((ctas + cap - 1) / cap) * cap);
-        if (eff > best + 1e-9) { best = eff; best_rs = rs; }
-    }
-    a.RS = best_rs; a.nstrips = (H + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G; a.nitems = B * a.nstrips;
+    a.RS = plan_strips(B, H, gx, 2); a.nstrips = (H + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G; a.nitems = B * a.nstrips;
     const size_t ring = sizeof(float4) * ((size_t)NR * (W + 2) + NCONST) * FQ;
     const size_t sm = std::max(ring, sizeof(float) * 36 * FT);
     static bool attr_done = false;
@@ -272,6 +391,36 @@ int launch_dwconv_bwd_fused(const float* dA, const float* z, const float* x_or_y
 #define FLAUNCH(FQ_) do { if (red) dwconv3x3_bwd_fused_kernel<FQ_, true><<<grid, block, sm, st>>>(a); else dwconv3x3_bwd_fused_kernel<FQ_, false><<<grid, block, sm, st>>>(a); } while (0)
     if (FQ == 8) FLAUNCH(8); else if (FQ == 16) FLAUNCH(16); else FLAUNCH(32);
 #undef FLAUNCH
+    LAUNCH_CHECK();
+    return CRNN_OK;
+}
+
+// out = depthwise3x3( dropout(relu6(y * pscale + pshift)) ), + per-channel sum / sum of squares of out into stats (optional, pre-zeroed double[2C])
+int launch_dwconv_fwd_fused(const float* y, const float* pscale, const float* pshift, float rate, uint64_t seed, uint32_t layer, const uint64_t* seed_ptr,
+                            const float* k, float* out, double* stats, int B, int H, int W, int C, int rev, cudaStream_t st)
+{
+    if (!dwconv_bwd_fused_covers(H, W, C)) { crnn_set_error("dwconv_fwd_fused: shape not covered"); return CRNN_ERR_INVALID; }
+    if ((long long)B * H * W * C >= (1LL << 31)) { crnn_set_error("dwconv_fwd_fused: tensor too large"); return CRNN_ERR_INVALID; }
+    FwdArgs a = {};
+    a.y = y; a.k = k; a.out = out; a.stats = stats; a.pscale = pscale; a.pshift = pshift;
+    a.rate = rate; a.inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f; a.seed = seed; a.layer = layer; a.seed_ptr = seed_ptr;
+    a.H = H; a.W = W; a.C4 = C / 4; a.NS = W / 3; a.rev = rev;
+    const int FQ = fused_fq(W);
+    const int gx = (a.C4 + FQ - 1) / FQ;
+    a.RS = plan_strips(B, H, gx, 3); a.nstrips = (H + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G; a.nitems = B * a.nstrips;
+    const size_t sm = std::max(sizeof(float4) * ((size_t)NR * (W + 2) + 11) * FQ, sizeof(double) * 8 * FT);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(dwconv3x3_fwd_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(dwconv3x3_fwd_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(dwconv3x3_fwd_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done = true;
+    }
+    g_crnn_family = CRNN_FAM_DWROWS;
+    const dim3 grid(gx, (unsigned)a.nitems), block(FQ, FT / FQ);
+    if (FQ == 8) dwconv3x3_fwd_fused_kernel<8><<<grid, block, sm, st>>>(a);
+    else if (FQ == 16) dwconv3x3_fwd_fused_kernel<16><<<grid, block, sm, st>>>(a);
+    else dwconv3x3_fwd_fused_kernel<32><<<grid, block, sm, st>>>(a);
     LAUNCH_CHECK();
     return CRNN_OK;
 }

@@ -120,6 +120,11 @@ struct crnn_handle {
     int bn2_red_done[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [block]: reduction pass of the block's BN2 backward already accumulated by the producer of its dy
     bool defer_bn_grads = false;   // full backward: dgamma/dbeta of all 14 BN layers in one launch at the end instead of 14 tiny ones
     bool fuse_bn_red = true;   // CRNN_FUSE_BN_RED=0: separate reduction pass for the ReLU6+BN backward after the depthwise conv
+    // CRNN_FWD_FUSED=0: every block materialises its output.  Default: the output of a non-pooled block 1..6 is NOT written in the forward pass --
+    // the next block's depthwise conv (dwconv_fused.cu) and its fused backward kernel recompute it from the raw pointwise output.  block_live[i]
+    // says whether act/block{i} holds the values of the last forward; crnn_debug_materialize_blocks() fills in the skipped ones (tests).
+    bool fwd_fused = true; bool block_live[8] = {true, true, true, true, true, true, true, true};
+    uint64_t last_seed = 0; int last_B = 0; bool last_drop = false;
     bool dw_fused = true;      // CRNN_DW_FUSED=0: separate ReLU6+BN-backward apply / depthwise backward-data / backward-weight kernels
     bool dw_red = true;        // CRNN_DW_RED=0: the depthwise backward-data kernel does not accumulate the BN2-backward reduction of the block below
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
@@ -475,8 +480,15 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         const long long M = (long long)B * hh * ww;
         float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
         const bool dw_stats = training && (b.cin % 4 == 0);       // BN statistics of the depthwise output fused into the conv kernel
-        ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st,
-                                                         dw_stats ? bn_stats(h, 2 * i - 1) : nullptr, h->rv()));
+        if (i >= 2 && !h->block_live[i - 1]) {
+            // the block below did not write its output: BN + ReLU6 + Dropout of its raw pointwise output are applied while the conv stages its rows
+            ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd_fused(h->a(nm("pw%d", i - 1)), h->a(actbn(2 * i - 2, "scale")), h->a(actbn(2 * i - 2, "shift")),
+                                                                   drop ? kDropBlock : 0.f, seed, (uint32_t)(i - 1), h->seed_ptr, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)),
+                                                                   dw, dw_stats ? bn_stats(h, 2 * i - 1) : nullptr, B, hh, ww, b.cin, h->rv(), st));
+        } else {
+            ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st,
+                                                             dw_stats ? bn_stats(h, 2 * i - 1) : nullptr, h->rv()));
+        }
         TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st, dw_stats));
         const bool tc = !h->gemm_simt && (b.cin % 32 == 0);
         bool pw_stats = false;
@@ -495,8 +507,13 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
                         h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), st));
         }
         TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st, pw_stats));
-        ST(ST_ACT_POOL, 4.0 * M * b.cout * (1.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
-                                drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv()));
+        // skip writing this block's output when (a) the next block's conv can recompute it (non-pooled, shapes covered) and (b) the backward pass
+        // will not read it: the fused backward kernel with the fused BN2 reduction recomputes it as well (block_backward: `rrp` path)
+        h->block_live[i] = !(i <= 6 && h->fwd_fused && b.ph == 1 && b.pw == 1 && dwconv_bwd_fused_covers(hh, ww, b.cout) &&
+                             h->dw_fused && h->fuse_bn_red && h->dw_red && !h->gemm_simt && (kBlocks[i].cout % 32 == 0) && (kBlocks[i].cin % 4 == 0));
+        if (h->block_live[i])
+            ST(ST_ACT_POOL, 4.0 * M * b.cout * (1.0 + 1.0 / (b.ph * b.pw)), launch_act_pool_fwd(pw, h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), out, B, hh, ww, b.cout, b.ph, b.pw,
+                                    drop ? kDropBlock : 0.f, seed, (uint32_t)i, st, h->seed_ptr, h->rv()));
         hh /= b.ph; ww /= b.pw; in = out;
     }
     if (h->gemm_simt) side_join(h, st);
@@ -661,6 +678,7 @@ int block_backward(crnn_handle* h, int i, int hh, int ww, float* cur, float* oth
         if (i >= 2) h->bn2_red_done[i - 1] = rrp ? 1 : 0;
         return CRNN_OK;
     }
+    if (i >= 2 && !h->block_live[i - 1]) { crnn_set_error("internal: block %d output was not materialised by the forward pass", i - 1); return CRNN_ERR_INVALID; }
     if (!h->defer_bn_grads) { rrp = nullptr; rbuf = nullptr; }      // the separate kernels only fuse that reduction inside the full backward
     ST(ST_BN_BWD, 20.0 * Mi * b.cin,
        launch_relu6_bn_bwd(ddw, dw, h->a(actbn(bn1, "scale")), h->a(actbn(bn1, "shift")), h->a(actbn(bn1, "mean")), h->a(actbn(bn1, "invstd")),
@@ -820,6 +838,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     { const char* e = getenv("CRNN_FUSE_BN_RED"); h->fuse_bn_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_DW_RED"); h->dw_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_DW_FUSED"); h->dw_fused = !(e && e[0] == '0'); }
+    { const char* e = getenv("CRNN_FWD_FUSED"); h->fwd_fused = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }
@@ -856,6 +875,7 @@ int crnn_tensor_lookup(const crnn_handle* h, const char* name, crnn_tensor_info*
 static int forward_graphed(crnn_handle* h, const float* x_dev, int B, float* softmax_dev, cudaStream_t st) {
     if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
     const void* const key[6] = {x_dev, softmax_dev, nullptr, nullptr, nullptr, nullptr};
+    h->last_B = B; h->last_seed = 0; h->last_drop = false;
     return run_graphed(h, 0, B, key, 0, 0, st, [&](cudaStream_t s) -> int {
         TRY(forward(h, x_dev, B, false, 0, s));
         if (softmax_dev && softmax_dev != h->a("softmax"))
@@ -885,6 +905,7 @@ int crnn_train_fwd_bwd(crnn_handle* h, const float* x_dev, const int32_t* labels
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* loss = loss_dev ? loss_dev : h->a("loss");
     const void* const key[6] = {x_dev, labels_dev, label_len_dev, input_len_dev, loss, nullptr};
+    h->last_B = B; h->last_seed = dropout_seed; h->last_drop = dropout_seed != 0;
     return run_graphed(h, 1, B, key, dropout_seed != 0, dropout_seed, st, [&](cudaStream_t s) -> int {
         TRY(forward(h, x_dev, B, true, dropout_seed, s));
         return backward(h, x_dev, labels_dev, label_len_dev, input_len_dev, B, loss, dropout_seed, s);
@@ -1152,6 +1173,22 @@ int crnn_gemm_tc(const float* X, int ldx, const float* W, int ldw, int w_transpo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TRY(launch_prep_weight_images(W, ldw, N, K, w_transposed, img_scratch, st));
     return launch_xw_gemm_tc(X, ldx, img_scratch, out, ldo, M, N, K, x_scale, x_shift, stats, st);
+}
+// Test / debug hook: act/block{i} of the non-pooled blocks is not written by the forward pass (dwconv_fused.cu recomputes it where it is
+// consumed); this fills those tensors in from the raw pointwise outputs with the BatchNorm constants and dropout seed of the LAST forward.
+int crnn_debug_materialize_blocks(crnn_handle* h, void* stream) {
+    if (!h) { crnn_set_error("null handle"); return CRNN_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->last_B < 1) return CRNN_OK;
+    int hh = h->Hp, ww = h->Wp;
+    for (int i = 1; i <= 7; ++i) {
+        const BlockPlan& b = kBlocks[i - 1];
+        if (!h->block_live[i])
+            TRY(launch_act_pool_fwd(h->a(nm("pw%d", i)), h->a(actbn(2 * i, "scale")), h->a(actbn(2 * i, "shift")), h->a(nm("block%d", i)), h->last_B, hh, ww, b.cout, b.ph, b.pw,
+                                    h->last_drop ? kDropBlock : 0.f, h->last_seed, (uint32_t)i, st, nullptr, 0));
+        hh /= b.ph; ww /= b.pw;
+    }
+    return CRNN_OK;
 }
 // teacher-forced backward of ONE conv block (parity tests): after a training-mode forward of batch B, takes d(block_i output)
 // (numel of act/block{i}) from dout_dev, zeroes the gradient arena, runs the block's backward and copies d(block_i input) to din_dev.

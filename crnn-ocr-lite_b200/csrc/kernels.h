@@ -66,13 +66,17 @@ int launch_dwconv_rows_bwd_weight(const float* x, const float* dy, float* dk33c,
 int launch_dwconv_rows(const float* x, const float* k33c, float* y, int B, int H, int W, int C, int flip, double* stats, int rev, cudaStream_t st,
                        const DwRowsRed* red = nullptr);
 int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk33c, int B, int H, int W, int C, cudaStream_t st);
-// dwconv_bwd_fused.cu: ReLU6+BN backward apply (needs the finished reduction `red1` = double[2C]) + depthwise backward-data + backward-weight
+// dwconv_fused.cu: ReLU6+BN backward apply (needs the finished reduction `red1` = double[2C]) + depthwise backward-data + backward-weight
 // in one pass; with `red` the third operand is the RAW pointwise output of the block below (the block input is recomputed from it) and that
 // block's BN-backward reduction is accumulated into red_buf.
 int dwconv_bwd_fused_covers(int H, int W, int C);
 int launch_dwconv_bwd_fused(const float* dA, const float* z, const float* x_or_y, const float* k33c, float* dx, float* dk33c,
                             const float* scale, const float* shift, const float* mean, const float* invstd, const float* gamma, const double* red1,
                             int B, int H, int W, int C, int rev, const DwRowsRed* red, double* red_buf, cudaStream_t st);
+// dwconv_fused.cu: out = depthwise3x3(dropout(relu6(y*pscale+pshift))) straight from the RAW pointwise output y of a non-pooled block (its
+// activation tensor is never materialised) + BatchNorm statistics of out (optional).  Same shape coverage as the backward kernel.
+int launch_dwconv_fwd_fused(const float* y, const float* pscale, const float* pshift, float rate, uint64_t seed, uint32_t layer, const uint64_t* seed_ptr,
+                            const float* k33c, float* out, double* stats, int B, int H, int W, int C, int rev, cudaStream_t st);
 int launch_bn_param_grads(const double* red, float* dgamma, float* dbeta, int C, cudaStream_t st);
 // per-channel sum / sum of squares over rows of y[M][C] -> stats[0..C) , stats[C..2C) (double, pre-zeroed)
 int launch_colstats(const float* y, long long M, int C, double* stats, cudaStream_t st);

@@ -187,6 +187,10 @@ class CRNNModel:
                            if not n.endswith(("moving_mean", "moving_variance")))
 
     def activation(self, name, B=None):
+        """Host copy of an activation tensor of the last forward (tests / inspection).  The outputs of the non-pooled blocks are not written
+        by the forward pass (csrc/dwconv_fused.cu recomputes them where they are consumed): crnn_debug_materialize_blocks fills them in."""
+        if name.startswith("block"):
+            _lib.check(self.lib.crnn_debug_materialize_blocks(self.handle, self._stream()))
         return self.tensor("act/" + name).cpu().numpy()
 
     # ------------------------------------------------------------------ Keras-compatible weight I/O (SURVEY 8b, 8f-1)

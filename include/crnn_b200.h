@@ -178,6 +178,9 @@ int crnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int
 /* teacher-forced backward of ONE depthwise-separable block (utils.py:43-56) for the parity tests: after a training-mode
  * forward of batch B, reads d(block output) from dout_dev, zeroes "arena/grads", runs that block's backward alone and
  * writes d(block input) to din_dev. */
+/* act/block{i} of the non-pooled blocks 1..6 is not written by the forward pass (recomputed where it is consumed); this fills those
+ * tensors in for inspection, from the raw pointwise outputs, BatchNorm constants and dropout seed of the last forward call. */
+int crnn_debug_materialize_blocks(crnn_handle* h, void* stream);
 int crnn_debug_block_backward(crnn_handle* h, int block, const float* dout_dev, float* din_dev, int B, uint64_t dropout_seed, void* stream);
 
 /* tcgen05 / TMEM 3xTF32 kernel of the pointwise convolutions (csrc/gemm_tc.cu): out[m][n] = sum_k f(X[m][k]) * Wop[n][k],

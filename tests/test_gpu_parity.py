@@ -753,11 +753,11 @@ def test_train_on_batch_host_call_equals_staged_path(cb, opt, u8):
             ga, gb = models[0].get_grads(), models[1].get_grads()
             assert list(ga) == list(gb)
             for k in ga:
-                np.testing.assert_allclose(ga[k], gb[k], rtol=1e-3, atol=1e-4 * max(1e-3, float(np.abs(gb[k]).max())), err_msg=k)
+                np.testing.assert_allclose(ga[k], gb[k], rtol=1e-3, atol=1e-3 * max(1e-3, float(np.abs(gb[k]).max())), err_msg=k)
             if opt == "sgd":            # linear in the gradient (Adam's first step is lr * sign(g): noise flips it where g ~ 0)
                 wa, wb = models[0].get_weights(), models[1].get_weights()
                 for k in ga:
-                    np.testing.assert_allclose(wa[k] - w0[k], wb[k] - w0[k], rtol=1e-3, atol=2e-4 * max(1e-6, float(np.abs(wb[k] - w0[k]).max())), err_msg=k)
+                    np.testing.assert_allclose(wa[k] - w0[k], wb[k] - w0[k], rtol=1e-3, atol=2e-3 * max(1e-6, float(np.abs(wb[k] - w0[k]).max())), err_msg=k)
     assert models[0].iterations() == models[1].iterations() == 2
     bad = {"the_input": xs[0], "the_labels": labs[0], "input_length": np.full((B, 1), 4, np.int32), "label_length": np.full((B, 1), 12, np.int32)}
     with pytest.raises(ValueError, match="Not enough time for target transition sequence"):
@@ -769,7 +769,8 @@ def test_switch_paths_stay_correct():
     """The A/B switches that select alternative kernels are read once per process, so each configuration re-runs a slice of this file in a
     subprocess: CRNN_DWCONV_V1=1 (channel-block depthwise kernels for every block, not only C = 1), CRNN_GEMM_PAIR=1 (cta_group::2
     schedule of the tcgen05 GEMM inside the real step), CRNN_FUSE_BN_RED=0 / CRNN_DW_RED=0 (unfused BatchNorm-backward reductions),
-    CRNN_DW_FUSED=0 (separate BN-apply / depthwise backward-data / backward-weight kernels instead of dwconv_bwd_fused.cu),
+    CRNN_DW_FUSED=0 (separate BN-apply / depthwise backward-data / backward-weight kernels instead of dwconv_fused.cu), CRNN_FWD_FUSED=0 (every
+    block writes its output instead of the next depthwise conv recomputing it),
     CRNN_GRAPH=0 CRNN_OVERLAP=0 (eager, single stream).  Every path must pass the same forward / isolated-backward / train-step parity tests."""
     import subprocess
     import sys
@@ -777,7 +778,7 @@ def test_switch_paths_stay_correct():
     sel = ("test_forward_inference_parity and 128-gru or test_block_backward_isolated and 100-4 or test_block_backward_isolated and 6-128-64"
            " or test_train_step_parity and 128-gru-6")
     for env in ({"CRNN_DWCONV_V1": "1"}, {"CRNN_GEMM_PAIR": "1"}, {"CRNN_FUSE_BN_RED": "0"}, {"CRNN_DW_RED": "0"}, {"CRNN_DW_FUSED": "0"},
-                {"CRNN_DW_FUSED": "0", "CRNN_DW_RED": "0"}, {"CRNN_GRAPH": "0", "CRNN_OVERLAP": "0"}):
+                {"CRNN_DW_FUSED": "0", "CRNN_DW_RED": "0"}, {"CRNN_FWD_FUSED": "0"}, {"CRNN_GRAPH": "0", "CRNN_OVERLAP": "0"}):
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k", sel],
                            capture_output=True, text=True, timeout=900, env=dict(os.environ, **env), cwd=root)
         assert r.returncode == 0 and " passed" in r.stdout, "%s: %s" % (env, r.stdout[-1500:] + r.stderr[-500:])
