@@ -254,15 +254,18 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
 
     const size_t rstride = (size_t)W * C;
     const size_t col0 = ((size_t)b * H * W + w0) * C + (size_t)c4 * 4;
-    float4 py[3];
-    auto load_y = [&](int rho) {
+    // input rows are loaded TWO iterations ahead (the conv of one iteration is too short to cover a DRAM round trip: ncu r2s, 17 % barrier +
+    // 10 % long-scoreboard stalls with a distance of one)
+    float4 py[3], pn[3];
+    auto load_y = [&](float4 (&d)[3], int rho) {
         const bool v = act && rho >= 0 && rho < H;
         const size_t o = col0 + (size_t)(v ? rho : 0) * rstride;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) py[t] = v ? ldg4(a.y + o + (size_t)t * C) : zero4();
+        for (int t = 0; t < 3; ++t) d[t] = v ? ldg4(a.y + o + (size_t)t * C) : zero4();
     };
     float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
-    load_y(hs - 1 + g);
+    load_y(py, hs - 1 + g);
+    load_y(pn, hs - 1 + G + g);
     int pslot = g, cslot = g + NR - 2;
     for (int k = 0; k < a.niter; ++k) {
         if (act) {
@@ -287,7 +290,9 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
                 for (int t = 0; t < 3; ++t) dst[t * FQ] = zero4();
             }
         }
-        if (k + 1 < a.niter) load_y(hs - 1 + (k + 1) * G + g);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) py[t] = pn[t];
+        if (k + 2 < a.niter) load_y(pn, hs - 1 + (k + 2) * G + g);
         __syncthreads();
         const int r = hs - 2 + k * G + g;
         if (act && r >= hs && r < he) {
