@@ -494,7 +494,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": getattr(args, "scaling", "weak"), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "CRNNModel.train_on_batch(host numpy dict) == Keras train_on_batch (train.py:201-209)",
+                    "api": "CRNNModel.train_on_batch(host numpy dict) == Keras train_on_batch (train.py:201-209); single process: one C-ABI call, crnn_train_on_batch_host (pageable numpy -> pinned staging -> H2D -> step -> optimiser -> D2H of losses + status)",
                     "uint8_input": {"value": e2e_u8_val, "h2d_bytes_per_step": int(x_u8.nbytes + lab.nbytes + L.nbytes + il.nbytes),
                                     "note": "same call with 'the_input' as the raw 8-bit images; utils.py:415 norm() runs on the device (crnn_normalize_u8)"}},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps, "dp_mode": dp_mode,
