@@ -339,6 +339,9 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
 
 int g_fused_off = -1;
 
+// (Tried: strips cut from ONE column of B * (H + 1) "virtual" rows with a zero separator row between images, so that exactly 296 equal
+// CTAs fill every slot instead of 256 whole-image CTAs on 296 slots.  Exact, and 20 % SLOWER (83 -> 103 us, 63 -> 77 us): the kernels are
+// bound by issue / DRAM, not by slot fill, and the per-row image decode adds instructions.  Whole-image strips stay.)
 // strips: RS rows cost ceil((RS+2)/2) iterations of 2 rows plus a prologue / epilogue worth ~3 iterations (constants, first loads, the CTA
 // reductions); choose the count that maximises (useful rows per row-time) x (fill of the waves of 148 SMs x `occ` resident CTAs); ties -> longer strips
 int plan_strips(int B, int H, int gx, int occ) {
