@@ -9,10 +9,10 @@
 // output y -- x = dropout(relu6(bn(y))) -- and y is needed for the fused reduction anyway, so x is RECOMPUTED from y (same fma / mask
 // as act_pool_fwd_kernel, bit-identical) and the `block{i-1}` tensor is not read at all.
 //
-// Layout: a CTA owns (image b, strip of RS rows, FQ channel quads); 192 threads = FQ quads x FP position slots, a slot = (one of G = 2
+// Layout: a CTA owns (strip of RS rows of the batch's column of B * (H + 1) virtual rows -- see the kernel --, FQ channel quads); 192 threads = FQ quads x FP position slots, a slot = (one of G = 2
 // rows, one three-column segment).  FQ is the largest of 8 / 16 / 32 whose 192 / FQ slots still hold two rows of W / 3 segments (W = 36 -> 8,
-// 18 -> 16, 9 -> 32), so a warp is uniform in its row, every image gives H / 2 iterations and strips stay long (a first version with
-// 8-row iterations at W = 9 ran 2 iterations per CTA at 55 % lane utilisation: ncu r2q, 3.1 TB/s).  dz lives in a shared-memory ring
+// 18 -> 16, 9 -> 32), so a warp is uniform in its row and strips stay long (a first version with 8-row iterations at W = 9 and short
+// per-image strips ran 2 iterations per CTA at 55 % lane utilisation: ncu r2q, 3.1 TB/s).  dz lives in a shared-memory ring
 // of 6 rows (+ zero halo columns): iteration k PRODUCES rows P_k = hs-1+2k .. (each thread its own 3 columns, from registers loaded
 // one iteration earlier), one __syncthreads, then CONSUMES output rows O_k = hs-2+2k .. : the 3x5 dz neighbourhood of the
 // thread's 3 columns is read once from shared memory (15 LDS.128) and used twice -- 27 fma4 into dx with the taps, 27 fma4 into the
@@ -41,7 +41,7 @@ struct FusedArgs {
     const float* scale; const float* shift; const float* mean; const float* invstd; const float* gamma; const double* red1; double invM;
     const float* pscale; const float* pshift; const float* pmean; const float* pinvstd; double* pred;
     float rate, inv_keep; uint64_t seed; uint32_t layer; const uint64_t* seed_ptr;
-    int H, W, C4, NS, RS, nstrips, niter, nitems, rev;
+    int H, W, C4, NS, RS, nstrips, niter, V, rev;      // V = B * (H + 1) virtual rows
 };
 
 // RED: a.x is the RAW pointwise output y of the block below (x is recomputed from it) and the BN2-backward reduction of that block is
@@ -59,10 +59,18 @@ __global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedA
     const int g = tp / NS, seg = tp - g * NS, w0 = seg * 3;
     const int c4 = blockIdx.x * FQ + tq;
     const bool cok = c4 < C4, act = cok && g < G;
-    int item = blockIdx.y;
-    if (a.rev) item = a.nitems - 1 - item;
-    const int strip = item % a.nstrips, b = item / a.nstrips;
-    const int hs = strip * a.RS, he = min(H, hs + a.RS);
+    // The batch is one column of V = B * (H + 1) VIRTUAL rows: image b owns rows b(H+1) .. b(H+1)+H-1, row b(H+1)+H is an all-zero separator
+    // (the bottom padding of image b and the top padding of image b+1 at once).  A strip is any RS consecutive virtual rows, so the launcher
+    // can cut the batch into exactly as many equal strips as there are CTA slots (whole-image strips: 256 CTAs on 296 slots).  A row cursor
+    // {v, r = v mod (H+1), prow = v - image} is advanced by G rows per iteration WITHOUT divisions: decoding v / (H+1) per row made the
+    // kernels 20 % slower than whole-image strips (issue-bound), the cursor makes them 2-9 % faster.
+    const int HP1 = H + 1, V = a.V;
+    const int strip = a.rev ? a.nstrips - 1 - (int)blockIdx.y : (int)blockIdx.y;
+    const int hs = strip * a.RS, he = min(V, hs + a.RS);
+    struct Cur { int v, r, prow; };
+    auto cur_at = [&](int v) { Cur c; const int bb = (v + HP1) / HP1 - 1; c.v = v; c.r = v - bb * HP1; c.prow = v - bb; return c; };
+    auto cur_adv = [&](Cur& c) { c.v += G; c.r += G; c.prow += G; if (c.r >= HP1) { c.r -= HP1; c.prow -= 1; } };
+    auto cur_ok = [&](const Cur& c) { return c.v >= 0 && c.v < V && c.r != H; };
 
     if (cok) for (int task = tp; task < (RED ? 11 : 10); task += FP) {
         if (task < 9) cs[task * FQ + tq] = ldg4(a.k + (size_t)task * C + c4 * 4);
@@ -86,34 +94,38 @@ __global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedA
     __syncthreads();
 
     const size_t rstride = (size_t)W * C;
-    const size_t col0 = ((size_t)b * H * W + w0) * C + (size_t)c4 * 4;      // (b, row 0, w0, c4): add row * rstride
+    const size_t col0 = (size_t)w0 * C + (size_t)c4 * 4;      // (pixel row 0, w0, c4): add pixel row * rstride
     float4 pa[3], pz[3], px[3];
-    auto load_p = [&](int rho) {
-        const bool v = act && rho >= 0 && rho < H;
-        const size_t o = col0 + (size_t)(v ? rho : 0) * rstride;
+    bool p_ok = false, x_ok = false; int x_row = 0;           // validity / pixel row of the rows whose loads are in flight
+    Cur cp = cur_at(hs - 1 + g), cx = cur_at(hs - 2 + g);     // next produce row, next output row
+    auto load_p = [&]() {
+        p_ok = cur_ok(cp) && act;
+        const size_t o = col0 + (size_t)(p_ok ? cp.prow : 0) * rstride;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) { pa[t] = v ? ldg4(a.dA + o + (size_t)t * C) : zero4(); pz[t] = v ? ldg4(a.z + o + (size_t)t * C) : zero4(); }
+        for (int t = 0; t < 3; ++t) { pa[t] = p_ok ? ldg4(a.dA + o + (size_t)t * C) : zero4(); pz[t] = p_ok ? ldg4(a.z + o + (size_t)t * C) : zero4(); }
+        cur_adv(cp);
     };
-    auto load_x = [&](int r) {
-        const bool v = act && r >= hs && r < he;
-        const size_t o = col0 + (size_t)(v ? r : 0) * rstride;
+    auto load_x = [&]() {
+        x_ok = cx.v >= hs && cx.v < he && cur_ok(cx) && act;
+        x_row = cx.prow;
+        const size_t o = col0 + (size_t)(x_ok ? cx.prow : 0) * rstride;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) px[t] = v ? ldg4(a.x + o + (size_t)t * C) : zero4();
+        for (int t = 0; t < 3; ++t) px[t] = x_ok ? ldg4(a.x + o + (size_t)t * C) : zero4();
+        cur_adv(cx);
     };
     float4 acc[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc[q] = zero4();
     float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
 
-    load_p(hs - 1 + g);
-    load_x(hs - 2 + g);
+    load_p();
+    load_x();
     int pslot = g, cslot = g + NR - 2;       // ring rows of P_k's row (2k+g) and of the first row O_k needs (2k+g-2), mod NR
     for (int k = 0; k < a.niter; ++k) {
         // ---- produce dz row hs-1+kG+g (columns w0..w0+2) into the ring
         if (act) {
-            const int rho = hs - 1 + k * G + g;
             float4* dst = ring + ((size_t)pslot * WP + w0 + 1) * FQ + tq;
-            if (rho >= 0 && rho < H) {
+            if (p_ok) {
                 const float4 sc = cs[9 * FQ + tq], sh = cs[10 * FQ + tq], mu = cs[11 * FQ + tq], is = cs[12 * FQ + tq];
                 const float4 gs = cs[13 * FQ + tq], m1 = cs[14 * FQ + tq], m2 = cs[15 * FQ + tq];
 #pragma unroll
@@ -130,13 +142,13 @@ __global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedA
                 for (int t = 0; t < 3; ++t) dst[t * FQ] = zero4();
             }
         }
-        if (k + 1 < a.niter) load_p(hs - 1 + (k + 1) * G + g);
+        if (k + 1 < a.niter) load_p();
         float4 xc[3] = {px[0], px[1], px[2]};
-        if (k + 1 < a.niter) load_x(hs - 2 + (k + 1) * G + g);
+        const bool c_ok = x_ok; const int r = x_row;          // this iteration's output row (pixel-row index), before the next load overwrites them
+        if (k + 1 < a.niter) load_x(); else x_ok = false;
         __syncthreads();
-        // ---- consume: output row r = hs-2+kG+g needs dz rows r-1..r+1 = ring rows (kG+g-2 .. kG+g) mod NR
-        const int r = hs - 2 + k * G + g;
-        if (act && r >= hs && r < he) {
+        // ---- consume: virtual output row hs-2+kG+g needs dz rows -1..+1 around it = ring rows (kG+g-2 .. kG+g) mod NR
+        if (c_ok) {
             float dm[3][4];
             float4 yv[3];
             if (RED) {
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedA
 #pragma unroll
                 for (int o = 0; o < 3; ++o) {
                     yv[o] = xc[o];
-                    if (a.rate > 0.f) crnn_dropout_mask4(rseed, a.layer, (uint64_t)(((size_t)(b * H + r) * W + w0 + o) * C4 + c4), a.rate, a.inv_keep, dm[o]);
+                    if (a.rate > 0.f) crnn_dropout_mask4(rseed, a.layer, (uint64_t)(((size_t)r * W + w0 + o) * C4 + c4), a.rate, a.inv_keep, dm[o]);
                     else { dm[o][0] = dm[o][1] = dm[o][2] = dm[o][3] = 1.f; }
                     xc[o].x = relu6f(fmaf(yv[o].x, psc.x, psh.x)); xc[o].y = relu6f(fmaf(yv[o].y, psc.y, psh.y));
                     xc[o].z = relu6f(fmaf(yv[o].z, psc.z, psh.z)); xc[o].w = relu6f(fmaf(yv[o].w, psc.w, psh.w));
@@ -226,7 +238,7 @@ __global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedA
 struct FwdArgs {
     const float* y; const float* k; float* out; double* stats;
     const float* pscale; const float* pshift; float rate, inv_keep; uint64_t seed; uint32_t layer; const uint64_t* seed_ptr;
-    int H, W, C4, NS, RS, nstrips, niter, nitems, rev;
+    int H, W, C4, NS, RS, nstrips, niter, V, rev;
 };
 
 template <int FQ>
@@ -242,10 +254,17 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
     const int g = tp / NS, seg = tp - g * NS, w0 = seg * 3;
     const int c4 = blockIdx.x * FQ + tq;
     const bool cok = c4 < C4, act = cok && g < G;
-    int item = blockIdx.y;
-    if (a.rev) item = a.nitems - 1 - item;
-    const int strip = item % a.nstrips, b = item / a.nstrips;
-    const int hs = strip * a.RS, he = min(H, hs + a.RS);
+    // The batch is one column of V = B * (H + 1) VIRTUAL rows: image b owns rows b(H+1) .. b(H+1)+H-1, row b(H+1)+H is an all-zero separator
+    // (the bottom padding of image b and the top padding of image b+1 at once).  A strip is any RS consecutive virtual rows, so the launcher
+    // can cut the batch into exactly as many equal strips as there are CTA slots.  A row cursor {v, r = v mod (H+1), prow = v - image} is
+    // advanced by G rows per iteration without divisions.
+    const int HP1 = H + 1, V = a.V;
+    const int strip = a.rev ? a.nstrips - 1 - (int)blockIdx.y : (int)blockIdx.y;
+    const int hs = strip * a.RS, he = min(V, hs + a.RS);
+    struct Cur { int v, r, prow; };
+    auto cur_at = [&](int v) { Cur c; const int bb = (v + HP1) / HP1 - 1; c.v = v; c.r = v - bb * HP1; c.prow = v - bb; return c; };
+    auto cur_adv = [&](Cur& c) { c.v += G; c.r += G; c.prow += G; if (c.r >= HP1) { c.r -= HP1; c.prow -= 1; } };
+    auto cur_ok = [&](const Cur& c) { return c.v >= 0 && c.v < V && c.r != H; };
     if (cok) for (int task = tp; task < 11; task += FP)
         cs[task * FQ + tq] = task < 9 ? ldg4(a.k + (size_t)task * C + c4 * 4) : ldg4((task == 9 ? a.pscale : a.pshift) + c4 * 4);
     for (int r = tp; r < NR; r += FP) { ring[((size_t)r * WP) * FQ + tq] = zero4(); ring[((size_t)r * WP + W + 1) * FQ + tq] = zero4(); }
@@ -253,25 +272,29 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
     __syncthreads();
 
     const size_t rstride = (size_t)W * C;
-    const size_t col0 = ((size_t)b * H * W + w0) * C + (size_t)c4 * 4;
+    const size_t col0 = (size_t)w0 * C + (size_t)c4 * 4;
     // input rows are loaded TWO iterations ahead (the conv of one iteration is too short to cover a DRAM round trip: ncu r2s, 17 % barrier +
     // 10 % long-scoreboard stalls with a distance of one)
     float4 py[3], pn[3];
-    auto load_y = [&](float4 (&d)[3], int rho) {
-        const bool v = act && rho >= 0 && rho < H;
-        const size_t o = col0 + (size_t)(v ? rho : 0) * rstride;
+    int rowy = -1, rown = -1;                                 // pixel rows of the two loads in flight (-1: padding row)
+    Cur cp = cur_at(hs - 1 + g), co = cur_at(hs - 2 + g);     // next row to load, next output row
+    auto load_y = [&](float4 (&d)[3], int& row) {
+        const bool ok = cur_ok(cp) && act;
+        row = ok ? cp.prow : -1;
+        const size_t o = col0 + (size_t)(ok ? cp.prow : 0) * rstride;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) d[t] = v ? ldg4(a.y + o + (size_t)t * C) : zero4();
+        for (int t = 0; t < 3; ++t) d[t] = ok ? ldg4(a.y + o + (size_t)t * C) : zero4();
+        cur_adv(cp);
     };
     float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
-    load_y(py, hs - 1 + g);
-    load_y(pn, hs - 1 + G + g);
+    load_y(py, rowy);
+    load_y(pn, rown);
     int pslot = g, cslot = g + NR - 2;
     for (int k = 0; k < a.niter; ++k) {
         if (act) {
-            const int rho = hs - 1 + k * G + g;
+            const int rho = rowy;
             float4* dst = ring + ((size_t)pslot * WP + w0 + 1) * FQ + tq;
-            if (rho >= 0 && rho < H) {
+            if (rho >= 0) {
                 const float4 sc = cs[9 * FQ + tq], sh = cs[10 * FQ + tq];
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
@@ -280,7 +303,7 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
                     o.z = relu6f(fmaf(py[t].z, sc.z, sh.z)); o.w = relu6f(fmaf(py[t].w, sc.w, sh.w));
                     if (a.rate > 0.f) {
                         float dm[4];
-                        crnn_dropout_mask4(rseed, a.layer, (uint64_t)(((size_t)(b * H + rho) * W + w0 + t) * C4 + c4), a.rate, a.inv_keep, dm);
+                        crnn_dropout_mask4(rseed, a.layer, (uint64_t)(((size_t)rho * W + w0 + t) * C4 + c4), a.rate, a.inv_keep, dm);
                         o.x *= dm[0]; o.y *= dm[1]; o.z *= dm[2]; o.w *= dm[3];
                     }
                     dst[t * FQ] = o;
@@ -292,10 +315,13 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
         }
 #pragma unroll
         for (int t = 0; t < 3; ++t) py[t] = pn[t];
-        if (k + 2 < a.niter) load_y(pn, hs - 1 + (k + 2) * G + g);
+        rowy = rown;
+        if (k + 2 < a.niter) load_y(pn, rown); else rown = -1;
         __syncthreads();
-        const int r = hs - 2 + k * G + g;
-        if (act && r >= hs && r < he) {
+        const bool o_ok = act && co.v >= hs && co.v < he && cur_ok(co);
+        const int r = co.prow;
+        cur_adv(co);
+        if (o_ok) {
             float4 ov[3] = {zero4(), zero4(), zero4()};
 #pragma unroll
             for (int ar = 0; ar < 3; ++ar) {
@@ -339,19 +365,18 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
 
 int g_fused_off = -1;
 
-// (Tried: strips cut from ONE column of B * (H + 1) "virtual" rows with a zero separator row between images, so that exactly 296 equal
-// CTAs fill every slot instead of 256 whole-image CTAs on 296 slots.  Exact, and 20 % SLOWER (83 -> 103 us, 63 -> 77 us): the kernels are
-// bound by issue / DRAM, not by slot fill, and the per-row image decode adds instructions.  Whole-image strips stay.)
-// strips: RS rows cost ceil((RS+2)/2) iterations of 2 rows plus a prologue / epilogue worth ~3 iterations (constants, first loads, the CTA
-// reductions); choose the count that maximises (useful rows per row-time) x (fill of the waves of 148 SMs x `occ` resident CTAs); ties -> longer strips
-int plan_strips(int B, int H, int gx, int occ) {
-    double best = -1.0; int best_rs = H;
-    for (int n = 1; n <= H; ++n) {
-        const int rs = (H + n - 1) / n;
+// strips of RS virtual rows (V = B * (H + 1) in total) cost ceil((RS+2)/2) iterations of 2 rows plus a prologue / epilogue worth ~3 iterations
+// (constants, first loads, the CTA reductions): choose the strip count that maximises (useful rows per row-time) x (fill of the waves of
+// 148 SMs x `occ` resident CTAs); ties -> fewer, longer strips
+int plan_strips(int V, int gx, int occ) {
+    double best = -1.0; int best_rs = V;
+    const long long cap = 148LL * occ;
+    for (int n = 1; n <= V; ++n) {
+        const int rs = (V + n - 1) / n;
         if (rs < 4 * G && n > 1) break;
-        const int d = (H + rs - 1) / rs, it = (rs + 2 + G - 1) / G;
-        const long long ctas = (long long)gx * B * d, cap = 148LL * occ;
-        const double eff = (double)H / ((double)d * (it + 3) * G) * (double)ctas / (double)(((ctas + cap - 1) / cap) * cap);
+        const int d = (V + rs - 1) / rs, it = (rs + 2 + G - 1) / G;
+        const long long ctas = (long long)gx * d;
+        const double eff = (double)V / ((double)d * (it + 3) * G) * (double)ctas / (double)(((ctas + cap - 1) / cap) * cap);
         if (eff > best + 1e-9) { best = eff; best_rs = rs; }
     }
     return best_rs;
@@ -384,7 +409,8 @@ int launch_dwconv_bwd_fused(const float* dA, const float* z, const float* x_or_y
     }
     const int FQ = fused_fq(W);
     const int gx = (a.C4 + FQ - 1) / FQ;
-    a.RS = plan_strips(B, H, gx, 2); a.nstrips = (H + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G; a.nitems = B * a.nstrips;
+    a.V = B * (H + 1);
+    a.RS = plan_strips(a.V, gx, 2); a.nstrips = (a.V + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G;
     const size_t ring = sizeof(float4) * ((size_t)NR * (W + 2) + NCONST) * FQ;
     const size_t sm = std::max(ring, sizeof(float) * 36 * FT);
     static bool attr_done = false;
@@ -395,7 +421,7 @@ int launch_dwconv_bwd_fused(const float* dA, const float* z, const float* x_or_y
         attr_done = true;
     }
     g_crnn_family = CRNN_FAM_DWROWS;
-    const dim3 grid(gx, (unsigned)a.nitems), block(FQ, FT / FQ);
+    const dim3 grid(gx, (unsigned)a.nstrips), block(FQ, FT / FQ);
 #define FLAUNCH(FQ_) do { if (red) dwconv3x3_bwd_fused_kernel<FQ_, true><<<grid, block, sm, st>>>(a); else dwconv3x3_bwd_fused_kernel<FQ_, false><<<grid, block, sm, st>>>(a); } while (0)
     if (FQ == 8) FLAUNCH(8); else if (FQ == 16) FLAUNCH(16); else FLAUNCH(32);
 #undef FLAUNCH
@@ -415,7 +441,8 @@ int launch_dwconv_fwd_fused(const float* y, const float* pscale, const float* ps
     a.H = H; a.W = W; a.C4 = C / 4; a.NS = W / 3; a.rev = rev;
     const int FQ = fused_fq(W);
     const int gx = (a.C4 + FQ - 1) / FQ;
-    a.RS = plan_strips(B, H, gx, 3); a.nstrips = (H + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G; a.nitems = B * a.nstrips;
+    a.V = B * (H + 1);
+    a.RS = plan_strips(a.V, gx, 3); a.nstrips = (a.V + a.RS - 1) / a.RS; a.niter = (a.RS + 2 + G - 1) / G;
     const size_t sm = std::max(sizeof(float4) * ((size_t)NR * (W + 2) + 11) * FQ, sizeof(double) * 8 * FT);
     static bool attr_done = false;
     if (!attr_done) {
@@ -425,7 +452,7 @@ int launch_dwconv_fwd_fused(const float* y, const float* pscale, const float* ps
         attr_done = true;
     }
     g_crnn_family = CRNN_FAM_DWROWS;
-    const dim3 grid(gx, (unsigned)a.nitems), block(FQ, FT / FQ);
+    const dim3 grid(gx, (unsigned)a.nstrips), block(FQ, FT / FQ);
     if (FQ == 8) dwconv3x3_fwd_fused_kernel<8><<<grid, block, sm, st>>>(a);
     else if (FQ == 16) dwconv3x3_fwd_fused_kernel<16><<<grid, block, sm, st>>>(a);
     else dwconv3x3_fwd_fused_kernel<32><<<grid, block, sm, st>>>(a);
