@@ -777,8 +777,14 @@ def test_switch_paths_stay_correct():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = ("test_forward_inference_parity and 128-gru or test_block_backward_isolated and 100-4 or test_block_backward_isolated and 6-128-64"
            " or test_train_step_parity and 128-gru-6")
-    for env in ({"CRNN_DWCONV_V1": "1"}, {"CRNN_GEMM_PAIR": "1"}, {"CRNN_FUSE_BN_RED": "0"}, {"CRNN_DW_RED": "0"}, {"CRNN_DW_FUSED": "0"},
-                {"CRNN_DW_FUSED": "0", "CRNN_DW_RED": "0"}, {"CRNN_FWD_FUSED": "0"}, {"CRNN_GRAPH": "0", "CRNN_OVERLAP": "0"}):
-        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k", sel],
-                           capture_output=True, text=True, timeout=900, env=dict(os.environ, **env), cwd=root)
+    envs = ({"CRNN_DWCONV_V1": "1"}, {"CRNN_GEMM_PAIR": "1"}, {"CRNN_FUSE_BN_RED": "0"}, {"CRNN_DW_RED": "0"}, {"CRNN_DW_FUSED": "0"},
+            {"CRNN_DW_FUSED": "0", "CRNN_DW_RED": "0"}, {"CRNN_FWD_FUSED": "0"}, {"CRNN_GRAPH": "0", "CRNN_OVERLAP": "0"})
+
+    def run(env):
+        return subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
+                              capture_output=True, text=True, timeout=900, env=dict(os.environ, **env), cwd=root)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(4) as ex:           # four configurations at a time share the GPU (small shapes)
+        results = list(ex.map(run, envs))
+    for env, r in zip(envs, results):
         assert r.returncode == 0 and " passed" in r.stdout, "%s: %s" % (env, r.stdout[-1500:] + r.stderr[-500:])
