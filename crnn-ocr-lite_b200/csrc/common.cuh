@@ -32,6 +32,56 @@ extern long long g_crnn_launches;   // kernels launched by this library (engine.
 enum { CRNN_FAM_OTHER = 0, CRNN_FAM_XW_TC, CRNN_FAM_XTY_TC, CRNN_FAM_RNN_MMA, CRNN_FAM_DWROWS, CRNN_FAM_COUNT };
 extern int g_crnn_family;
 
+// Programmatic dependent launch (PDL), an A/B switch that stays OFF (CRNN_PDL=0 is the default): every kernel of this library starts with
+// pdl_enter() -- wait for the full completion (memory flushed) of the kernel before it in the stream, then allow the kernel after it to be
+// scheduled -- and crnn_launch() can add the programmatic-stream-serialization attribute, so the CTAs of the next kernel are placed on SMs
+// as the last wave of the current one drains (captured into the step's CUDA graph as programmatic edges).  Everything a kernel does to
+// global memory happens after its wait, so the data dependencies are exactly those of plain stream order; without the attribute the two
+// instructions are no-ops (4.982 ms/step with them, 4.984 before).
+// Measured on B200 (bench.py, step graph, 30 steps): CRNN_PDL=0 4.98 ms | 1 (every launch) 5.21 | 2 (not after the recurrence) 5.27 |
+// 3 (only while no side branch is open, i.e. most of the forward pass + optimiser) 5.08.  Two effects, both against it here: (a) the
+// early-placed CTAs of the next main-stream kernel take the SM slots that free up in the tail of the current one -- exactly the slots in
+// which the side branch (weight-gradient GEMMs) makes its progress -- and during the recurrence (128 of 148 SMs) they park on the 20 idle
+// SMs; (b) kernels whose grids are cut to fill the CTA slots exactly (dwconv_fused.cu: 296 strips = 148 SMs x 2) get their CTAs placed
+// greedily on whichever SMs drain first, up to the occupancy limit, instead of evenly -- the launch gap PDL saves (~1-2 us) is smaller
+// than the imbalance it creates.
+extern int g_crnn_pdl;               // CRNN_PDL: 0 off (default), 1 every launch, 2 not for the launch that follows a kernel that leaves SMs idle, 3 = 2 + not while a side branch is open
+extern int g_crnn_side_open;         // engine: work is pending on the side stream (between side_after and side_join)
+extern cudaStream_t g_crnn_pdl_sparse; extern int g_crnn_pdl_sparse_set;
+// the kernel just launched on `st` does not fill the GPU (recurrence: 128 of 148 SMs for ~280 us; one CTA per image): a dependent kernel placed
+// early would sit on the idle SMs for its whole duration and keep the side branch's kernels off them
+static inline void crnn_pdl_mark_sparse(cudaStream_t st) { g_crnn_pdl_sparse = st; g_crnn_pdl_sparse_set = 1; }
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+template <typename... KA, typename... A>
+static inline cudaError_t crnn_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    bool on = g_crnn_pdl != 0;
+    if (g_crnn_pdl_sparse_set && g_crnn_pdl_sparse == st) { if (g_crnn_pdl >= 2) on = false; g_crnn_pdl_sparse_set = 0; }
+    if (g_crnn_pdl >= 3 && g_crnn_side_open) on = false;
+    cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+#endif
+
+// BatchNorm finalize folded into the kernel that accumulates the batch statistics (training): the CTA that finishes last (ticket counter,
+// zeroed together with the statistics) turns [sum | sumsq] into scale / shift / mean / invstd and updates the moving statistics -- what
+// bn_finalize_kernel does as a launch of its own (14 per step on the critical path).  The engine offers the job through g_crnn_bn_fin right
+// before it calls the launcher of the producing kernel; a launcher that supports the tail takes it (sets the pointer back to nullptr), any
+// other path leaves it and the engine launches bn_finalize_kernel as before.
+struct BnFin {
+    const double* stats; unsigned int* ticket; double M; int C;
+    const float* gamma; const float* beta; float* mm; float* mv; float eps, momentum;
+    float* scale; float* shift; float* save_mean; float* save_invstd;
+};
+extern const BnFin* g_crnn_bn_fin;
+static inline BnFin crnn_take_bn_fin() { BnFin f = {}; if (g_crnn_bn_fin) { f = *g_crnn_bn_fin; g_crnn_bn_fin = nullptr; } return f; }
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
@@ -51,6 +101,45 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+// one channel of the BatchNorm finalize (training: batch statistics + Keras 2.2.2 moving-average update, SURVEY A.4: fused-op Bessel correction
+// times n/(n-(1+eps)); inference: moving statistics); shared by bn_finalize_kernel and the last-CTA tail so both give the same bits
+__device__ __forceinline__ void bn_finalize_channel(int c, double sum, double sumsq, double M, int training, const float* gamma, const float* beta,
+                                                    float* mm, float* mv, float eps, float momentum, float* scale, float* shift,
+                                                    float* save_mean, float* save_invstd) {
+    double mean, var;
+    if (training) {
+        mean = sum / M;
+        var = sumsq / M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double var_mov = var * (M / (M - 1.0)) * (M / (M - (1.0 + (double)eps)));
+        float om = 1.0f - momentum;
+        mm[c] = mm[c] - (mm[c] - (float)mean) * om;
+        mv[c] = mv[c] - (mv[c] - (float)var_mov) * om;
+    } else {
+        mean = mm[c]; var = mv[c];
+    }
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = invstd; }
+}
+// Called by ALL threads of EVERY CTA at the very end of a statistics-producing kernel (after the CTA's atomics on f.stats).
+__device__ __forceinline__ void bn_finalize_tail(const BnFin& f) {
+    if (!f.ticket) return;                                   // uniform for the grid
+    __shared__ int s_last;
+    const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    __threadfence();                                         // this thread's statistics atomics are performed before the ticket is taken
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(f.ticket, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = tid; c < f.C; c += nthr)
+        bn_finalize_channel(c, __ldcg(f.stats + c), __ldcg(f.stats + f.C + c), f.M, 1, f.gamma, f.beta, f.mm, f.mv, f.eps, f.momentum,
+                            f.scale, f.shift, f.save_mean, f.save_invstd);
 }
 __device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6.f); }
 __device__ __forceinline__ float hard_sigmoid(float v) { return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, v), 0.5f), 0.f), 1.f); }

@@ -24,7 +24,7 @@ __device__ __forceinline__ void fma4(float4& a, const float4 x, const float4 k) 
 template <bool FLIP>
 __global__ void dwconv3x3_vec4(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                                int B, int H, int W, int C4, long long total)
-{
+{ pdl_enter();
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         int c4 = (int)(idx % C4); long long r = idx / C4;
         int w = (int)(r % W); r /= W;
@@ -50,7 +50,7 @@ __global__ void dwconv3x3_vec4(const float* __restrict__ x, const float* __restr
 template <bool FLIP>
 __global__ void __launch_bounds__(256) dwconv3x3_vec4_w4(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                                                          int B, int H, int W, int C4, int WG, long long total)
-{
+{ pdl_enter();
     const int C = C4 * 4;
     const int total32 = (int)total;                 // < 2^31 (checked by the launcher)
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += gridDim.x * blockDim.x) {
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_vec4_w4(const float* __restrict
 template <bool FLIP, bool STATS>
 __global__ void __launch_bounds__(256, DWCONV_MIN_CTAS) dwconv3x3_cb_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                                                            int H, int W, int C4, int WG, int ngroups, double* __restrict__ stats, int rev)
-{
+{ pdl_enter();
     extern __shared__ double dsm[];   // STATS: [PY][8][CQ]
     const int CQ = blockDim.x, PY = blockDim.y;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256, DWCONV_MIN_CTAS) dwconv3x3_cb_kernel(cons
 template <bool FLIP>
 __global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                              int B, int H, int W, long long total)
-{
+{ pdl_enter();
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         int w = (int)(idx % W); long long r = idx / W;
         int h = (int)(r % H); int b = (int)(r / H);
@@ -189,7 +189,7 @@ __global__ void dwconv3x3_c1(const float* __restrict__ x, const float* __restric
 // dk[i][j][c] = sum_{b,h,w} x[b,h+i-1,w+j-1,c] * dy[b,h,w,c].  blockDim = (CQ channel-quads | CT channels, PY pixel lanes)
 __global__ void __launch_bounds__(256, DWCONV_MIN_CTAS) dwconv3x3_bwd_weight_vec4(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
                                           int B, int H, int W, int C4, int WG, long long ngroups)
-{
+{ pdl_enter();
     extern __shared__ float red[];   // [PY][36][CQ]
     const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256, DWCONV_MIN_CTAS) dwconv3x3_bwd_weight_vec
 }
 __global__ void dwconv3x3_bwd_weight(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
                                      int B, int H, int W, int C, long long npix)
-{
+{ pdl_enter();
     extern __shared__ float red[];   // [PY][9][CT]
     const int CT = blockDim.x, PY = blockDim.y;
     const int c = blockIdx.x * CT + threadIdx.x;
@@ -280,8 +280,8 @@ __global__ void dwconv3x3_bwd_weight(const float* __restrict__ x, const float* _
 
 // ------------------------------------------------------------------ per-channel statistics
 // blockDim = (CT, PY); stats[c] += sum y, stats[C+c] += sum y^2 (double)
-__global__ void colstats_kernel(const float* __restrict__ y, long long M, int C, double* __restrict__ stats)
-{
+__global__ void colstats_kernel(const float* __restrict__ y, long long M, int C, double* __restrict__ stats, const BnFin fin)
+{ pdl_enter();
     extern __shared__ double dred[];  // [PY][2][CT]
     const int CT = blockDim.x, PY = blockDim.y;
     const int c = blockIdx.x * CT + threadIdx.x;
@@ -299,33 +299,17 @@ __global__ void colstats_kernel(const float* __restrict__ y, long long M, int C,
         for (int i = 0; i < PY; ++i) { ts += dred[(i * 2) * CT + threadIdx.x]; tq += dred[(i * 2 + 1) * CT + threadIdx.x]; }
         atomicAdd(stats + c, ts); atomicAdd(stats + C + c, tq);
     }
+    bn_finalize_tail(fin);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double M, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ mm, float* __restrict__ mv,
                                    float eps, float momentum, int training, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd)
-{
+{ pdl_enter();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    double mean, var;
-    if (training) {
-        mean = stats[c] / M;
-        var = stats[C + c] / M - mean * mean;
-        if (var < 0.0) var = 0.0;
-        // Keras 2.2.2 moving-average update: fused-op Bessel correction times n/(n-(1+eps))
-        double var_mov = var * (M / (M - 1.0)) * (M / (M - (1.0 + (double)eps)));
-        float om = 1.0f - momentum;
-        mm[c] = mm[c] - (mm[c] - (float)mean) * om;
-        mv[c] = mv[c] - (mv[c] - (float)var_mov) * om;
-    } else {
-        mean = mm[c]; var = mv[c];
-    }
-    float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    float sc = gamma[c] * invstd;
-    scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
-    if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = invstd; }
+    bn_finalize_channel(c, training ? stats[c] : 0.0, training ? stats[C + c] : 0.0, M, training, gamma, beta, mm, mv, eps, momentum, scale, shift, save_mean, save_invstd);
 }
 
 // ------------------------------------------------------------------ BN + ReLU6 + MaxPool + Dropout forward
@@ -336,7 +320,7 @@ template <int PH, int PW>
 __global__ void __launch_bounds__(256) act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                     float* __restrict__ a, int W, int C4, int Wo, int npix,
                                     float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr, int rev)
-{
+{ pdl_enter();
     const int CQ = blockDim.x, PY = blockDim.y;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
     if (c4 >= C4) return;
@@ -379,7 +363,7 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
                                     const float* __restrict__ gamma, float* __restrict__ dy, double* __restrict__ red,
                                     int B, int H, int W, int C4, double invM,
                                     float rate, float inv_keep, uint64_t seed, uint32_t layer, long long npix_ll, const uint64_t* __restrict__ seed_ptr, int rev)
-{
+{ pdl_enter();
     extern __shared__ float sred[];   // [PY][8][CQ]
     if (seed_ptr) seed = *seed_ptr;
     constexpr int ph = PH, pw = PW, NW = PH * PW;
@@ -478,12 +462,12 @@ __global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restri
 
 // dgamma += sum(dz*xhat), dbeta += sum(dz) from the reduction buffer
 __global__ void bn_param_grads_kernel(const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta, int C)
-{
+{ pdl_enter();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) { dbeta[c] += (float)red[c]; dgamma[c] += (float)red[C + c]; }
 }
 __global__ void bn_param_grads_all_kernel(BnGradTable t)       // blockIdx.y = layer
-{
+{ pdl_enter();
     const int l = blockIdx.y, C = t.C[l];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) { t.dbeta[l][c] += (float)t.red[l][c]; t.dgamma[l][c] += (float)t.red[l][C + c]; }
 }
@@ -494,7 +478,7 @@ template <bool APPLY>
 __global__ void relu6_bwd_scalar_kernel(const float* da /* may alias dy */, const float* __restrict__ y, const float* __restrict__ scale,
                                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                  const float* __restrict__ gamma, float* dy, double* __restrict__ red, long long M, int C, double invM)
-{
+{ pdl_enter();
     extern __shared__ float sred[];   // [PY][2][CT]
     const int CT = blockDim.x, PY = blockDim.y;
     const int c = blockIdx.x * CT + threadIdx.x;
@@ -528,7 +512,7 @@ template <bool APPLY>
 __global__ void __launch_bounds__(256) relu6_bwd_kernel(const float* da /* may alias dy */, const float* __restrict__ y, const float* __restrict__ scale,
                                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                  const float* __restrict__ gamma, float* dy, double* __restrict__ red, long long M, int C4, double invM, int rev)
-{
+{ pdl_enter();
     extern __shared__ float sred[];   // [PY][8][CQ]
     const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
@@ -594,7 +578,7 @@ __global__ void __launch_bounds__(256, 3) bn_relu6_reduce_kernel(const float* __
                                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                  double* __restrict__ red, int M, int C4, int rev,
                                  float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr)
-{
+{ pdl_enter();
     extern __shared__ float sred[];   // [PY][8][CQ]
     const int CQ = blockDim.x, PY = blockDim.y, C = C4 * 4;
     const int c4 = blockIdx.x * CQ + threadIdx.x;
@@ -657,7 +641,7 @@ __global__ void __launch_bounds__(256, 3) bn_relu6_reduce_kernel(const float* __
 __global__ void bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restrict__ y, const double* __restrict__ red,
                                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C, long long total)
-{
+{ pdl_enter();
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] += (float)red[c]; dgamma[c] += (float)red[C + c]; }
     const double invM = 1.0 / (double)M;
@@ -672,7 +656,7 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restr
 
 // ------------------------------------------------------------------ misc element-wise
 __global__ void colsum_kernel(const float* __restrict__ y, long long M, int C, int ldy, float* __restrict__ out)
-{
+{ pdl_enter();
     extern __shared__ float sred[];   // [PY][CT]
     const int CT = blockDim.x, PY = blockDim.y;
     const int c = blockIdx.x * CT + threadIdx.x;
@@ -688,13 +672,13 @@ __global__ void colsum_kernel(const float* __restrict__ y, long long M, int C, i
     }
 }
 __global__ void relu_dropout_bwd_kernel(float* __restrict__ g, const float* __restrict__ act, long long n, float inv_keep)
-{
+{ pdl_enter();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         g[i] = act[i] > 0.f ? g[i] * inv_keep : 0.f;
 }
 __global__ void dropout_kernel(const float* in, float* x, long long n, float rate, float inv_keep, uint64_t seed, uint32_t layer,
                                const uint64_t* __restrict__ seed_ptr)
-{
+{ pdl_enter();
     if (seed_ptr) seed = *seed_ptr;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         x[i] = in[i] * crnn_dropout_mask(seed, layer, (uint64_t)i, rate, inv_keep);
@@ -702,7 +686,7 @@ __global__ void dropout_kernel(const float* in, float* x, long long n, float rat
 // Fixed-order sum of the S split-K copies of a GEMM output, fused with bias, ReLU and (training) the inverted-dropout mask of the layer.
 __global__ void sum_partials_kernel(const float* __restrict__ part, int S, long long stride, int N4, long long total4, const float* __restrict__ bias, int relu,
                                     float* __restrict__ out, int ldo, float rate, float inv_keep, uint64_t seed, uint32_t layer, const uint64_t* __restrict__ seed_ptr)
-{
+{ pdl_enter();
     if (seed_ptr) seed = *seed_ptr;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / N4; const int n4 = (int)(i - m * N4);
@@ -718,8 +702,8 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int S, long 
 // blockDim = 256 = 16 pixel lanes x 16 channel quads (Cout = 64); a warp covers 2 pixels x 64 channels = 2 x 256 B contiguous.
 // BN statistics of the output in closed form: sum_m f_m w_c = w_c * S1, sum_m (f_m w_c)^2 = w_c^2 * S2 (S1, S2 accumulated in double per CTA).
 __global__ void __launch_bounds__(256) pw1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                                                      const float* __restrict__ w, float* __restrict__ out, int M, int C4, double* __restrict__ stats, int rev)
-{
+                                                      const float* __restrict__ w, float* __restrict__ out, int M, int C4, double* __restrict__ stats, int rev, const BnFin fin)
+{ pdl_enter();
     __shared__ float s1s[8], s2s[8];
     const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, PL = blockDim.x / C4;
     const float sc = __ldg(scale), sh = __ldg(shift);
@@ -743,12 +727,13 @@ __global__ void __launch_bounds__(256) pw1_fwd_kernel(const float* __restrict__ 
         atomicAdd(stats + threadIdx.x, wc * a);
         atomicAdd(stats + C + threadIdx.x, wc * wc * b);
     }
+    bn_finalize_tail(fin);
 }
 // backward in one pass over dY: dX[m] = sum_c dY[m][c] w[c] (16-lane shuffle reduce), dW[c] += sum_m f(x[m]) dY[m][c]
 __global__ void __launch_bounds__(256) pw1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                                       const float* __restrict__ dY, const float* __restrict__ w, float* __restrict__ dX,
                                                       float* __restrict__ dW, int M, int rev)
-{
+{ pdl_enter();
     __shared__ float4 sacc[256];
     const int c4 = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const float sc = __ldg(scale), sh = __ldg(shift);
@@ -775,9 +760,9 @@ __global__ void __launch_bounds__(256) pw1_bwd_kernel(const float* __restrict__ 
         atomicAdd(dW + threadIdx.x * 4 + 2, t.z); atomicAdd(dW + threadIdx.x * 4 + 3, t.w);
     }
 }
-__global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }
+__global__ void set_u64_kernel(uint64_t* p, uint64_t v) { pdl_enter(); *p = v; }
 __global__ void sum_dirs_kernel(const float* __restrict__ hs, float* __restrict__ out, long long rows, int U)
-{
+{ pdl_enter();
     long long n = rows * U;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         long long r = i / U; int u = (int)(i % U);
@@ -785,7 +770,7 @@ __global__ void sum_dirs_kernel(const float* __restrict__ hs, float* __restrict_
     }
 }
 __global__ void dup_dirs_kernel(const float* __restrict__ g, float* __restrict__ out, long long rows, int U)
-{
+{ pdl_enter();
     long long n = rows * U;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         long long r = i / U; int u = (int)(i % U);
@@ -795,7 +780,7 @@ __global__ void dup_dirs_kernel(const float* __restrict__ g, float* __restrict__
 }
 // softmax over the last axis, one warp per row (same formula as Keras softmax: exp(z-max)/sum)
 __global__ void softmax_rows_kernel(const float* __restrict__ z, float* __restrict__ p, long long rows, int V)
-{
+{ pdl_enter();
     const int lane = threadIdx.x & 31;
     long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -836,10 +821,10 @@ int launch_dwconv_fwd(const float* x, const float* k, float* y, int B, int H, in
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
         dim3 grid, block; chan_block(C / 4, ngroups, grid, block);
-        if (stats) dwconv3x3_cb_kernel<false, true><<<grid, block, sizeof(double) * 8 * 256, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, stats, rev);
-        else dwconv3x3_cb_kernel<false, false><<<grid, block, 0, st>>>(x, k, y, H, W, C / 4, WG, (int)ngroups, nullptr, rev);
+        if (stats) (void)crnn_launch(dwconv3x3_cb_kernel<false, true>, grid, block, sizeof(double) * 8 * 256, st, x, k, y, H, W, C / 4, WG, (int)ngroups, stats, rev);
+        else (void)crnn_launch(dwconv3x3_cb_kernel<false, false>, grid, block, 0, st, x, k, y, H, W, C / 4, WG, (int)ngroups, nullptr, rev);
     }
-    else if (C == 1 && !stats) { long long total = (long long)B * H * W; dwconv3x3_c1<false><<<grid1d(total, 256), 256, 0, st>>>(x, k, y, B, H, W, total); }
+    else if (C == 1 && !stats) { long long total = (long long)B * H * W; (void)crnn_launch(dwconv3x3_c1<false>, grid1d(total, 256), 256, 0, st, x, k, y, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4 (fused statistics need C %% 4 == 0)"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;
 }
@@ -857,9 +842,9 @@ int launch_dwconv_bwd_data(const float* dy, const float* k, float* dx, int B, in
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
         dim3 grid, block; chan_block(C / 4, ngroups, grid, block);
-        dwconv3x3_cb_kernel<true, false><<<grid, block, 0, st>>>(dy, k, dx, H, W, C / 4, WG, (int)ngroups, nullptr, rev);
+        (void)crnn_launch(dwconv3x3_cb_kernel<true, false>, grid, block, 0, st, dy, k, dx, H, W, C / 4, WG, (int)ngroups, nullptr, rev);
     }
-    else if (C == 1) { long long total = (long long)B * H * W; dwconv3x3_c1<true><<<grid1d(total, 256), 256, 0, st>>>(dy, k, dx, B, H, W, total); }
+    else if (C == 1) { long long total = (long long)B * H * W; (void)crnn_launch(dwconv3x3_c1<true>, grid1d(total, 256), 256, 0, st, dy, k, dx, B, H, W, total); }
     else { crnn_set_error("dwconv: C must be 1 or a multiple of 4"); return CRNN_ERR_INVALID; }
     LAUNCH_CHECK(); return CRNN_OK;
 }
@@ -869,21 +854,22 @@ int launch_dwconv_bwd_weight(const float* x, const float* dy, float* dk, int B, 
     if (C % 4 == 0) {
         const int WG = (W + 3) / 4; const long long ngroups = (long long)B * H * WG;
         chan_block(C / 4, ngroups, grid, block);
-        dwconv3x3_bwd_weight_vec4<<<grid, block, sizeof(float) * 36 * 256, st>>>(x, dy, dk, B, H, W, C / 4, WG, ngroups);
+        (void)crnn_launch(dwconv3x3_bwd_weight_vec4, grid, block, sizeof(float) * 36 * 256, st, x, dy, dk, B, H, W, C / 4, WG, ngroups);
     } else {
         chan_block(C, npix, grid, block);
-        dwconv3x3_bwd_weight<<<grid, block, sizeof(float) * block.y * 9 * block.x, st>>>(x, dy, dk, B, H, W, C, npix);
+        (void)crnn_launch(dwconv3x3_bwd_weight, grid, block, sizeof(float) * block.y * 9 * block.x, st, x, dy, dk, B, H, W, C, npix);
     }
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_colstats(const float* y, long long M, int C, double* stats, cudaStream_t st) {
     dim3 grid, block; chan_block(C, M, grid, block);
-    colstats_kernel<<<grid, block, sizeof(double) * 2 * 256, st>>>(y, M, C, stats);
+    const BnFin fin = crnn_take_bn_fin();
+    (void)crnn_launch(colstats_kernel, grid, block, sizeof(double) * 2 * 256, st, y, M, C, stats, fin);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_bn_finalize(const double* stats, long long M, int C, const float* gamma, const float* beta, float* mm, float* mv,
                        float eps, float momentum, int training, float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(stats, (double)M, C, gamma, beta, mm, mv, eps, momentum, training, scale, shift, save_mean, save_invstd);
+    (void)crnn_launch(bn_finalize_kernel, ceil_div(C, 128), 128, 0, st, stats, (double)M, C, gamma, beta, mm, mv, eps, momentum, training, scale, shift, save_mean, save_invstd);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, float* a, int B, int H, int W, int C, int ph, int pw,
@@ -894,7 +880,7 @@ int launch_act_pool_fwd(const float* y, const float* scale, const float* shift, 
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
     grid.y = (unsigned)std::min<long long>((npix + block.y - 1) / block.y, (long long)grid.y * 2);     // ~8 CTAs per SM: short dependent chains, many loads in flight
-#define APF(PH_, PW_) act_pool_fwd_kernel<PH_, PW_><<<grid, block, 0, st>>>(y, scale, shift, a, W, C / 4, W / pw, (int)npix, rate, ik, seed, layer, seed_ptr, rev)
+#define APF(PH_, PW_) (void)crnn_launch(act_pool_fwd_kernel<PH_, PW_>, grid, block, 0, st, y, scale, shift, a, W, C / 4, W / pw, (int)npix, rate, ik, seed, layer, seed_ptr, rev)
     if (ph == 1 && pw == 1) APF(1, 1);
     else if (ph == 2 && pw == 2) APF(2, 2);
     else if (ph == 1 && pw == 2) APF(1, 2);
@@ -913,8 +899,8 @@ static int launch_bn_relu6_reduce(const float* da, const float* y, const float* 
     if (gy < 1) gy = 1;
     const dim3 grid(gx, (unsigned)gy), block(CQ, PY);
     const size_t sm = sizeof(float) * 8 * 256;
-    if (rate > 0.f) bn_relu6_reduce_kernel<true><<<grid, block, sm, st>>>(da, y, scale, shift, mean, invstd, red, (int)M, C4, rev, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
-    else bn_relu6_reduce_kernel<false><<<grid, block, sm, st>>>(da, y, scale, shift, mean, invstd, red, (int)M, C4, rev, 0.f, 1.f, 0, 0, nullptr);
+    if (rate > 0.f) (void)crnn_launch(bn_relu6_reduce_kernel<true>, grid, block, sm, st, da, y, scale, shift, mean, invstd, red, (int)M, C4, rev, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
+    else (void)crnn_launch(bn_relu6_reduce_kernel<false>, grid, block, sm, st, da, y, scale, shift, mean, invstd, red, (int)M, C4, rev, 0.f, 1.f, 0, 0, nullptr);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 // two launches: reductions, then apply (+ a tiny launch for dgamma/dbeta); `red` (double[2C]) must be pre-zeroed
@@ -928,7 +914,7 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
     const double invM = 1.0 / ((double)B * H * W);
     const float ik = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
     dim3 grid, block; chan_block(C / 4, npix, grid, block);
-#define APB(A_, PH_, PW_, SM_) act_pool_bwd_kernel<A_, PH_, PW_><<<grid, block, SM_, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix, seed_ptr, (A_) ? !rev : rev)
+#define APB(A_, PH_, PW_, SM_) (void)crnn_launch(act_pool_bwd_kernel<A_, PH_, PW_>, grid, block, SM_, st, da, y, scale, shift, mean, invstd, gamma, dy, red, B, H, W, C / 4, invM, rate, ik, seed, layer, npix, seed_ptr, (A_) ? !rev : rev)
     const size_t sm = sizeof(float) * 8 * 256;
     if (reduce_done && (ph != 1 || pw != 1)) { crnn_set_error("act_pool_bn_bwd: a fused reduction only exists for the non-pooled blocks"); return CRNN_ERR_INVALID; }
     if (ph == 1 && pw == 1) {
@@ -944,7 +930,7 @@ int launch_act_pool_bn_bwd(const float* da, const float* y, const float* scale, 
 #undef APB
     LAUNCH_CHECK();
     if (!emit_param_grads) return CRNN_OK;
-    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
+    (void)crnn_launch(bn_param_grads_kernel, ceil_div(C, 128), 128, 0, st, red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, const float* shift, const float* mean, const float* invstd,
@@ -956,80 +942,81 @@ int launch_relu6_bn_bwd(const float* da, const float* y, const float* scale, con
         chan_block(C / 4, (M + 1) / 2, grid, block);
         if (too_big(M * C)) return CRNN_ERR_INVALID;
         if (!reduce_done) { const int rc = launch_bn_relu6_reduce(da, y, scale, shift, mean, invstd, red, M, C, rev, 0.f, 0, 0, nullptr, st); if (rc != CRNN_OK) return rc; }
-        relu6_bwd_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM, !rev);
+        (void)crnn_launch(relu6_bwd_kernel<true>, grid, block, 0, st, da, y, scale, shift, mean, invstd, gamma, dy, red, M, C / 4, invM, !rev);
     } else {
         chan_block(C, M, grid, block);
-        relu6_bwd_scalar_kernel<false><<<grid, block, sizeof(float) * 2 * 256, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
+        (void)crnn_launch(relu6_bwd_scalar_kernel<false>, grid, block, sizeof(float) * 2 * 256, st, da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
         LAUNCH_CHECK();
-        relu6_bwd_scalar_kernel<true><<<grid, block, 0, st>>>(da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
+        (void)crnn_launch(relu6_bwd_scalar_kernel<true>, grid, block, 0, st, da, y, scale, shift, mean, invstd, gamma, dy, red, M, C, invM);
     }
     LAUNCH_CHECK();
     if (!emit_param_grads) return CRNN_OK;
-    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
+    (void)crnn_launch(bn_param_grads_kernel, ceil_div(C, 128), 128, 0, st, red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_bn_param_grads(const double* red, float* dgamma, float* dbeta, int C, cudaStream_t st) {
-    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(red, dgamma, dbeta, C);
+    (void)crnn_launch(bn_param_grads_kernel, ceil_div(C, 128), 128, 0, st, red, dgamma, dbeta, C);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_bn_param_grads_all(const BnGradTable& t, cudaStream_t st) {
     if (t.n <= 0) return CRNN_OK;
-    bn_param_grads_all_kernel<<<dim3(2, t.n), 256, 0, st>>>(t);
+    (void)crnn_launch(bn_param_grads_all_kernel, dim3(2, t.n), 256, 0, st, t);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_bn_bwd_apply(float* dz, const float* y, const double* red, const float* gamma, const float* mean, const float* invstd,
                         float* dgamma, float* dbeta, long long M, int C, cudaStream_t st) {
     long long total = M * C;
-    bn_bwd_apply_kernel<<<grid1d(total, 256), 256, 0, st>>>(dz, y, red, gamma, mean, invstd, dgamma, dbeta, M, C, total);
+    (void)crnn_launch(bn_bwd_apply_kernel, grid1d(total, 256), 256, 0, st, dz, y, red, gamma, mean, invstd, dgamma, dbeta, M, C, total);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_colsum(const float* y, long long M, int C, int ldy, float* out, cudaStream_t st) {
     dim3 grid, block; chan_block(C, M, grid, block);
-    colsum_kernel<<<grid, block, sizeof(float) * 256, st>>>(y, M, C, ldy, out);
+    (void)crnn_launch(colsum_kernel, grid, block, sizeof(float) * 256, st, y, M, C, ldy, out);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_relu_dropout_bwd(float* g, const float* act, long long n, float rate, uint64_t, uint32_t, cudaStream_t st) {
-    relu_dropout_bwd_kernel<<<grid1d(n, 256), 256, 0, st>>>(g, act, n, rate > 0.f ? 1.f / (1.f - rate) : 1.f);
+    (void)crnn_launch(relu_dropout_bwd_kernel, grid1d(n, 256), 256, 0, st, g, act, n, rate > 0.f ? 1.f / (1.f - rate) : 1.f);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_dropout_fwd(float* x, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
     if (rate <= 0.f) return CRNN_OK;
-    dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(x, x, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
+    (void)crnn_launch(dropout_kernel, grid1d(n, 256), 256, 0, st, x, x, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_sum_partials(const float* part, int S, long long stride, long long M, int N, const float* bias, int relu, float* out, int ldo,
                         float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
     if ((N % 4) || (ldo % 4) || (stride % 4) || S < 1) { crnn_set_error("sum_partials: N, ldo and stride must be multiples of 4"); return CRNN_ERR_INVALID; }
     const long long total4 = M * (N / 4);
-    sum_partials_kernel<<<grid1d(total4, 256), 256, 0, st>>>(part, S, stride, N / 4, total4, bias, relu, out, ldo, rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, seed_ptr);
+    (void)crnn_launch(sum_partials_kernel, grid1d(total4, 256), 256, 0, st, part, S, stride, N / 4, total4, bias, relu, out, ldo, rate, rate > 0.f ? 1.f / (1.f - rate) : 1.f, seed, layer, seed_ptr);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_dropout_copy(const float* in, float* out, long long n, float rate, uint64_t seed, uint32_t layer, cudaStream_t st, const uint64_t* seed_ptr) {
-    dropout_kernel<<<grid1d(n, 256), 256, 0, st>>>(in, out, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
+    (void)crnn_launch(dropout_kernel, grid1d(n, 256), 256, 0, st, in, out, n, rate, 1.f / (1.f - rate), seed, layer, seed_ptr);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_pw1_fwd(const float* x, const float* scale, const float* shift, const float* w, float* out, long long M, int Cout, double* stats, cudaStream_t st, int rev) {
     if (Cout != 64 || too_big(M * Cout)) { crnn_set_error("pw1_fwd: Cout must be 64"); return CRNN_ERR_INVALID; }
     const int grid = (int)std::min<long long>((M + 15) / 16, 148 * 8);
-    pw1_fwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, w, out, (int)M, Cout / 4, stats, rev);
+    BnFin fin = {}; if (stats) fin = crnn_take_bn_fin();
+    (void)crnn_launch(pw1_fwd_kernel, grid, 256, 0, st, x, scale, shift, w, out, (int)M, Cout / 4, stats, rev, fin);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_pw1_bwd(const float* x, const float* scale, const float* shift, const float* dY, const float* w, float* dX, float* dW, long long M, int Cout, cudaStream_t st, int rev) {
     if (Cout != 64 || too_big(M * Cout)) { crnn_set_error("pw1_bwd: Cout must be 64"); return CRNN_ERR_INVALID; }
     const int grid = (int)std::min<long long>((M + 15) / 16, 148 * 8);
-    pw1_bwd_kernel<<<grid, 256, 0, st>>>(x, scale, shift, dY, w, dX, dW, (int)M, rev);
+    (void)crnn_launch(pw1_bwd_kernel, grid, 256, 0, st, x, scale, shift, dY, w, dX, dW, (int)M, rev);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_set_u64(uint64_t* p, uint64_t v, cudaStream_t st) {
-    set_u64_kernel<<<1, 1, 0, st>>>(p, v);
+    (void)crnn_launch(set_u64_kernel, 1, 1, 0, st, p, v);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_sum_dirs(const float* hs, float* out, long long rows, int U, cudaStream_t st) {
-    sum_dirs_kernel<<<grid1d(rows * U, 256), 256, 0, st>>>(hs, out, rows, U); LAUNCH_CHECK(); return CRNN_OK;
+    (void)crnn_launch(sum_dirs_kernel, grid1d(rows * U, 256), 256, 0, st, hs, out, rows, U); LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_dup_dirs(const float* g, float* out, long long rows, int U, cudaStream_t st) {
-    dup_dirs_kernel<<<grid1d(rows * U, 256), 256, 0, st>>>(g, out, rows, U); LAUNCH_CHECK(); return CRNN_OK;
+    (void)crnn_launch(dup_dirs_kernel, grid1d(rows * U, 256), 256, 0, st, g, out, rows, U); LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_softmax_rows(const float* z, float* p, long long rows, int V, cudaStream_t st) {
-    softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(z, p, rows, V); LAUNCH_CHECK(); return CRNN_OK;
+    (void)crnn_launch(softmax_rows_kernel, ceil_div(rows, 8), 256, 0, st, z, p, rows, V); LAUNCH_CHECK(); return CRNN_OK;
 }

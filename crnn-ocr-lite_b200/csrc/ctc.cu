@@ -43,7 +43,7 @@ ctc_loss_grad_kernel(const float* __restrict__ probs,   // (B, T, V) softmax out
                      float* __restrict__ grad_u,         // (B, T-t_off, V) or null : d loss_b / d u
                      float* __restrict__ grad_logits,    // (B, T, V) or null : scale * d loss_b / d dense2-logits
                      float scale, int* __restrict__ status)
-{
+{ pdl_enter();
     extern __shared__ float sm[];
     constexpr unsigned FULL = 0xffffffffu;
     const int b = blockIdx.x;
@@ -263,7 +263,7 @@ ctc_loss_grad_kernel(const float* __restrict__ probs,   // (B, T, V) softmax out
 __global__ void ctc_greedy_kernel(const float* __restrict__ probs, const int* __restrict__ seq_len,
                                   int B, int T, int V, float eps,
                                   int* __restrict__ out, int* __restrict__ out_len, float* __restrict__ score)
-{
+{ pdl_enter();
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * warps + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -316,7 +316,7 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
                                 int B, int T, int V, float eps, int W, int merge_repeated, int P,
                                 int* __restrict__ out, int* __restrict__ out_len, float* __restrict__ logprob,
                                 int smem_per_warp_bytes)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) unsigned char smraw[];
     const int warps = blockDim.x >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int b = blockIdx.x * warps + wib;
@@ -608,7 +608,7 @@ int launch_ctc_loss_grad(const float* probs, int t_off, const int* labels, int m
             CUDA_TRY(cudaFuncSetAttribute(ctc_loss_grad_kernel<NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
             configured = smem;                                                                                                            \
         }                                                                                                                                 \
-        ctc_loss_grad_kernel<NS_><<<B, CTC_WARPS * 32, smem, st>>>(probs, t_off, labels, maxL, label_len, input_len, B, T, V, eps,        \
+        (void)crnn_launch(ctc_loss_grad_kernel<NS_>, B, CTC_WARPS * 32, smem, st, probs, t_off, labels, maxL, label_len, input_len, B, T, V, eps,        \
                                                                    loss, grad_u, grad_logits, scale, status);                             \
     } while (0)
     if (ns <= 1) CTC_LAUNCH(1); else if (ns <= 2) CTC_LAUNCH(2); else if (ns <= 4) CTC_LAUNCH(4); else CTC_LAUNCH(8);
@@ -622,7 +622,7 @@ int launch_ctc_greedy(const float* probs, const int* seq_len, int B, int T, int 
 {
     if (B <= 0) return CRNN_OK;
     const int warps = 4;
-    ctc_greedy_kernel<<<ceil_div(B, warps), warps * 32, 0, st>>>(probs, seq_len, B, T, V, eps, out, out_len, score);
+    (void)crnn_launch(ctc_greedy_kernel, ceil_div(B, warps), warps * 32, 0, st, probs, seq_len, B, T, V, eps, out, out_len, score);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -647,7 +647,7 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
         CUDA_TRY(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    ctc_beam_kernel<<<ceil_div(B, warps), warps * 32, smem, st>>>(probs, seq_len, B, T, V, eps, W, merge_repeated, top_paths,
+    (void)crnn_launch(ctc_beam_kernel, ceil_div(B, warps), warps * 32, smem, st, probs, seq_len, B, T, V, eps, W, merge_repeated, top_paths,
                                                                   out, out_len, logprob, (int)per);
     LAUNCH_CHECK();
     return CRNN_OK;

@@ -48,7 +48,7 @@ struct FusedArgs {
 // accumulated into a.pred;  !RED: a.x is the block input itself.
 template <int FQ, bool RED>
 __global__ void __launch_bounds__(FT, 2) dwconv3x3_bwd_fused_kernel(const FusedArgs a)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int FP = FT / FQ;
     const int NS = a.NS, W = a.W, H = a.H, C4 = a.C4, C = C4 * 4;
@@ -239,11 +239,12 @@ struct FwdArgs {
     const float* y; const float* k; float* out; double* stats;
     const float* pscale; const float* pshift; float rate, inv_keep; uint64_t seed; uint32_t layer; const uint64_t* seed_ptr;
     int H, W, C4, NS, RS, nstrips, niter, V, rev;
+    BnFin fin;                 // BatchNorm finalize of the output's statistics, done by the last CTA (common.cuh)
 };
 
 template <int FQ>
 __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArgs a)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int FP = FT / FQ;
     const int NS = a.NS, W = a.W, H = a.H, C4 = a.C4, C = C4 * 4;
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(FT, 3) dwconv3x3_fwd_fused_kernel(const FwdArg
             for (int i = 0; i < FP; ++i) t += dsm[(i * 8 + e) * FQ + tq];
             atomicAdd(a.stats + (e >> 2) * C + c4 * 4 + (e & 3), t);
         }
+    bn_finalize_tail(a.fin);
 }
 
 int g_fused_off = -1;
@@ -422,7 +424,7 @@ int launch_dwconv_bwd_fused(const float* dA, const float* z, const float* x_or_y
     }
     g_crnn_family = CRNN_FAM_DWROWS;
     const dim3 grid(gx, (unsigned)a.nstrips), block(FQ, FT / FQ);
-#define FLAUNCH(FQ_) do { if (red) dwconv3x3_bwd_fused_kernel<FQ_, true><<<grid, block, sm, st>>>(a); else dwconv3x3_bwd_fused_kernel<FQ_, false><<<grid, block, sm, st>>>(a); } while (0)
+#define FLAUNCH(FQ_) do { if (red) (void)crnn_launch(dwconv3x3_bwd_fused_kernel<FQ_, true>, grid, block, sm, st, a); else (void)crnn_launch(dwconv3x3_bwd_fused_kernel<FQ_, false>, grid, block, sm, st, a); } while (0)
     if (FQ == 8) FLAUNCH(8); else if (FQ == 16) FLAUNCH(16); else FLAUNCH(32);
 #undef FLAUNCH
     LAUNCH_CHECK();
@@ -439,6 +441,7 @@ int launch_dwconv_fwd_fused(const float* y, const float* pscale, const float* ps
     a.y = y; a.k = k; a.out = out; a.stats = stats; a.pscale = pscale; a.pshift = pshift;
     a.rate = rate; a.inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f; a.seed = seed; a.layer = layer; a.seed_ptr = seed_ptr;
     a.H = H; a.W = W; a.C4 = C / 4; a.NS = W / 3; a.rev = rev;
+    if (stats) a.fin = crnn_take_bn_fin();
     const int FQ = fused_fq(W);
     const int gx = (a.C4 + FQ - 1) / FQ;
     a.V = B * (H + 1);
@@ -453,9 +456,9 @@ int launch_dwconv_fwd_fused(const float* y, const float* pscale, const float* ps
     }
     g_crnn_family = CRNN_FAM_DWROWS;
     const dim3 grid(gx, (unsigned)a.nstrips), block(FQ, FT / FQ);
-    if (FQ == 8) dwconv3x3_fwd_fused_kernel<8><<<grid, block, sm, st>>>(a);
-    else if (FQ == 16) dwconv3x3_fwd_fused_kernel<16><<<grid, block, sm, st>>>(a);
-    else dwconv3x3_fwd_fused_kernel<32><<<grid, block, sm, st>>>(a);
+    if (FQ == 8) (void)crnn_launch(dwconv3x3_fwd_fused_kernel<8>, grid, block, sm, st, a);
+    else if (FQ == 16) (void)crnn_launch(dwconv3x3_fwd_fused_kernel<16>, grid, block, sm, st, a);
+    else (void)crnn_launch(dwconv3x3_fwd_fused_kernel<32>, grid, block, sm, st, a);
     LAUNCH_CHECK();
     return CRNN_OK;
 }

@@ -40,8 +40,8 @@ struct RowsRed { const float* y; const float* scale; const float* shift; const f
 template <bool FLIP, bool STATS, bool RED>
 __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y,
                                                                  int H, int W, int C4, int nseg, int nstrips, int RS, int nitems,
-                                                                 double* __restrict__ stats, int rev, RowsRed rr)
-{
+                                                                 double* __restrict__ stats, int rev, RowsRed rr, const BnFin fin)
+{ pdl_enter();
     extern __shared__ __align__(16) unsigned char smraw[];
     float4* ks = reinterpret_cast<float4*>(smraw);              // [9][CQ] taps of this CTA's channel quads (+ [4][CQ] BN constants with RED)
     const int CQ = blockDim.x, PY = blockDim.y;
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __
         for (int i = 0; i < PY; ++i) t += dsm[(i * 8 + e) * CQ + threadIdx.x];
         atomicAdd(stats + (e >> 2) * C + c4 * 4 + (e & 3), t);
     }
+    if (STATS) bn_finalize_tail(fin);
 }
 
 // Backward-weight: dk[i][j][c] = sum_{b,r,w} x[r+i-1][w+j-1][c] * dy[r][w][c].  Same marching scheme with 2 output columns per thread:
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_kernel(const float* __
 constexpr int SEGW = 2;
 __global__ void __launch_bounds__(NTHR, 2) dwconv3x3_rows_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dk,
                                                                             int H, int W, int C4, int nseg, int nstrips, int RS, int nitems)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) unsigned char smraw[];
     float* red = reinterpret_cast<float*>(smraw);               // [PY][36][CQ]
     const int CQ = blockDim.x, PY = blockDim.y;
@@ -296,12 +297,13 @@ int launch_dwconv_rows(const float* x, const float* k, float* y, int B, int H, i
     plan_rows(B, H, W, C / 4, 2, SEG, grid, block, nseg, nstrips, RS, nitems);
     const size_t sm = std::max(sizeof(float4) * 13 * block.x, (stats ? sizeof(double) * 8 * NTHR : (size_t)0));
     RowsRed rr = {};
+    BnFin fin = {}; if (stats && !flip && !red) fin = crnn_take_bn_fin();
     if (red) { rr.y = red->y; rr.scale = red->scale; rr.shift = red->shift; rr.mean = red->mean; rr.invstd = red->invstd; rr.rate = red->rate;
                rr.inv_keep = red->rate > 0.f ? 1.f / (1.f - red->rate) : 1.f; rr.seed = red->seed; rr.layer = red->layer; rr.seed_ptr = red->seed_ptr; }
-    if (red) dwconv3x3_rows_kernel<true, false, true><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev, rr);
-    else if (flip) dwconv3x3_rows_kernel<true, false, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev, rr);
-    else if (stats) dwconv3x3_rows_kernel<false, true, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev, rr);
-    else dwconv3x3_rows_kernel<false, false, false><<<grid, block, sm, st>>>(x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev, rr);
+    if (red) (void)crnn_launch(dwconv3x3_rows_kernel<true, false, true>, grid, block, sm, st, x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev, rr, fin);
+    else if (flip) (void)crnn_launch(dwconv3x3_rows_kernel<true, false, false>, grid, block, sm, st, x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev, rr, fin);
+    else if (stats) (void)crnn_launch(dwconv3x3_rows_kernel<false, true, false>, grid, block, sm, st, x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, stats, rev, rr, fin);
+    else (void)crnn_launch(dwconv3x3_rows_kernel<false, false, false>, grid, block, sm, st, x, k, y, H, W, C / 4, nseg, nstrips, RS, nitems, nullptr, rev, rr, fin);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -312,7 +314,7 @@ int launch_dwconv_rows_bwd_weight(const float* x, const float* dy, float* dk, in
     g_crnn_family = CRNN_FAM_DWROWS;
     dim3 grid, block; int nseg, nstrips, RS, nitems;
     plan_rows(B, H, W, C / 4, 2, SEGW, grid, block, nseg, nstrips, RS, nitems);
-    dwconv3x3_rows_bwd_weight_kernel<<<grid, block, sizeof(float) * 36 * NTHR, st>>>(x, dy, dk, H, W, C / 4, nseg, nstrips, RS, nitems);
+    (void)crnn_launch(dwconv3x3_rows_bwd_weight_kernel, grid, block, sizeof(float) * 36 * NTHR, st, x, dy, dk, H, W, C / 4, nseg, nstrips, RS, nitems);
     LAUNCH_CHECK();
     return CRNN_OK;
 }

@@ -17,6 +17,10 @@
 
 long long g_crnn_launches = 0;
 int g_crnn_family = CRNN_FAM_OTHER;
+int g_crnn_pdl = []() { const char* e = getenv("CRNN_PDL"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0; }();   // common.cuh: programmatic dependent launch (OFF by default: measured slower in every mode)
+int g_crnn_side_open = 0;
+cudaStream_t g_crnn_pdl_sparse = nullptr; int g_crnn_pdl_sparse_set = 0;
+const BnFin* g_crnn_bn_fin = nullptr;   // common.cuh: BatchNorm finalize offered to the next statistics-producing launch
 static thread_local char g_err[512] = "";
 void crnn_set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -126,6 +130,7 @@ struct crnn_handle {
     bool fwd_fused = true; bool block_live[8] = {true, true, true, true, true, true, true, true};
     uint64_t last_seed = 0; int last_B = 0; bool last_drop = false;
     bool dw_fused = true;      // CRNN_DW_FUSED=0: separate ReLU6+BN-backward apply / depthwise backward-data / backward-weight kernels
+    bool bn_tail = true;       // CRNN_BN_TAIL=0: BatchNorm finalize as a launch of its own instead of the last-CTA tail of the kernel that accumulates the statistics
     bool dw_red = true;        // CRNN_DW_RED=0: the depthwise backward-data kernel does not accumulate the BN2-backward reduction of the block below
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
@@ -190,6 +195,7 @@ cudaStream_t side_after(crnn_handle* h, cudaStream_t st) {
     if (!h->overlap || h->prof.on || !h->side) return st;
     cudaEvent_t e = h->ev();
     cudaEventRecord(e, st); cudaStreamWaitEvent(h->side, e, 0);
+    g_crnn_side_open = 1;
     return h->side;
 }
 // everything issued on the side branch so far completes before what follows on `st`
@@ -197,6 +203,7 @@ void side_join(crnn_handle* h, cudaStream_t st) {
     if (!h->overlap || h->prof.on || !h->side) return;
     cudaEvent_t e = h->ev();
     cudaEventRecord(e, h->side); cudaStreamWaitEvent(st, e, 0);
+    g_crnn_side_open = 0;
 }
 
 // ---- data-parallel exchange inside the step (dp_fused): sum all-reduce of arena/grads[off, off + n) on stream s
@@ -365,7 +372,8 @@ void plan(crnn_handle* h) {
         for (int i = 1; i <= 7; ++i)
             for (int k = 0; k < 2; ++k) { h->bn_off[2 * i - 1 + k] = off; off += 2 * (k ? kBlocks[i - 1].cout : kBlocks[i - 1].cin); }
         h->bn_off[15] = off;
-        L.add("act/stats", off, 8); L.add("act/red", off, 8);
+        L.add("act/stats", off + 16, 8);           // + one ticket counter per BN (last-CTA finalize, common.cuh), zeroed with the sums
+        L.add("act/red", off, 8);
     }
     L.add("act/sumsq", 1, 8); L.add("act/seed", 1, 8);
     L.add("act/status", 1, 4, 1);
@@ -424,9 +432,26 @@ double* bn_stats(crnn_handle* h, int bn) { return reinterpret_cast<double*>(h->a
 double* bn_red(crnn_handle* h, int bn) { return reinterpret_cast<double*>(h->a("red")) + h->bn_off[bn]; }
 
 // act/stats is zeroed once at the start of a training forward; stats_ready = the producer kernel already accumulated into the slot
-int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool training, cudaStream_t st, bool stats_ready = false) {
+// Offer the finalize of BN `bn` to the kernel that is about to accumulate its batch statistics (training only; CRNN_BN_TAIL=0: never).
+// `f` must outlive the producer launch and the bn_forward call that follows.
+void bn_offer(crnn_handle* h, int bn, long long M, int C, bool training, BnFin& f) {
+    g_crnn_bn_fin = nullptr;
+    if (!training || !h->bn_tail) return;
+    f.stats = bn_stats(h, bn);
+    f.ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(h->a("stats")) + h->bn_off[15] + bn);
+    f.M = (double)M; f.C = C;
+    f.gamma = h->w(bnname(bn, "gamma")); f.beta = h->w(bnname(bn, "beta"));
+    f.mm = h->w(bnname(bn, "moving_mean")); f.mv = h->w(bnname(bn, "moving_variance"));
+    f.eps = kBnEps; f.momentum = kBnMomentum;
+    f.scale = h->a(actbn(bn, "scale")); f.shift = h->a(actbn(bn, "shift")); f.save_mean = h->a(actbn(bn, "mean")); f.save_invstd = h->a(actbn(bn, "invstd"));
+    g_crnn_bn_fin = &f;
+}
+int bn_forward(crnn_handle* h, int bn, const float* y, long long M, int C, bool training, cudaStream_t st, bool stats_ready = false, bool offered = false) {
     double* stats = bn_stats(h, bn);
     if (training && !stats_ready) ST(ST_BN_STATS, 4.0 * M * C, launch_colstats(y, M, C, stats, st));
+    const bool folded = offered && g_crnn_bn_fin == nullptr;     // a producer took the job: its last CTA finalizes
+    g_crnn_bn_fin = nullptr;
+    if (folded) return CRNN_OK;
     return launch_bn_finalize(stats, M, C, h->w(bnname(bn, "gamma")), h->w(bnname(bn, "beta")), h->w(bnname(bn, "moving_mean")),
                               h->w(bnname(bn, "moving_variance")), kBnEps, kBnMomentum, training ? 1 : 0,
                               h->a(actbn(bn, "scale")), h->a(actbn(bn, "shift")), h->a(actbn(bn, "mean")), h->a(actbn(bn, "invstd")), st);
@@ -462,10 +487,10 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
     if (B < 1 || B > h->maxB) { crnn_set_error("batch %d outside [1,%d]", B, h->maxB); return CRNN_ERR_INVALID; }
     const bool drop = training && seed != 0;
     const int H = h->H, W = h->W, U = h->U, G = h->G, T = h->T, V = h->V;
-    h->ev_used = 0; h->flip = 0;
+    h->ev_used = 0; h->flip = 0; g_crnn_side_open = 0;
     // ---- side branch: weight images of all tensor-core GEMMs of this step (weights only change in the optimiser)
     TRY(prep_images(h, training, side_after(h, st)));
-    if (training) CUDA_TRY(cudaMemsetAsync(h->a("stats"), 0, sizeof(double) * h->bn_off[15], st));
+    if (training) CUDA_TRY(cudaMemsetAsync(h->a("stats"), 0, sizeof(double) * (h->bn_off[15] + 16), st));
     // ---- STN (utils.py:247-258)
     ST(ST_STN, 0, launch_stn_trunk_fwd(x, h->w("conv2d_1/kernel"), h->w("conv2d_1/bias"), h->w("conv2d_2/kernel"), h->w("conv2d_2/bias"),
                              h->a("p1"), h->a("p2"), reinterpret_cast<int*>(h->a("p2arg")), h->a("flat"), B, H, W, st));
@@ -480,6 +505,8 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
         const long long M = (long long)B * hh * ww;
         float* dw = h->a(nm("dw%d", i)); float* pw = h->a(nm("pw%d", i)); float* out = h->a(nm("block%d", i));
         const bool dw_stats = training && (b.cin % 4 == 0);       // BN statistics of the depthwise output fused into the conv kernel
+        BnFin fin1, fin2;
+        bn_offer(h, 2 * i - 1, M, b.cin, training, fin1);
         if (i >= 2 && !h->block_live[i - 1]) {
             // the block below did not write its output: BN + ReLU6 + Dropout of its raw pointwise output are applied while the conv stages its rows
             ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd_fused(h->a(nm("pw%d", i - 1)), h->a(actbn(2 * i - 2, "scale")), h->a(actbn(2 * i - 2, "shift")),
@@ -489,7 +516,8 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
             ST(ST_DWCONV, 8.0 * M * b.cin, launch_dwconv_fwd(in, h->w(nm("depthwise_conv2d_%d/depthwise_kernel", i)), dw, B, hh, ww, b.cin, st,
                                                              dw_stats ? bn_stats(h, 2 * i - 1) : nullptr, h->rv()));
         }
-        TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st, dw_stats));
+        TRY(bn_forward(h, 2 * i - 1, dw, M, b.cin, training, st, dw_stats, training && h->bn_tail));
+        bn_offer(h, 2 * i, M, b.cout, training, fin2);
         const bool tc = !h->gemm_simt && (b.cin % 32 == 0);
         bool pw_stats = false;
         if (tc) {
@@ -506,7 +534,7 @@ int forward(crnn_handle* h, const float* x, int B, bool training, uint64_t seed,
             TRY(gemm_nn(h, ST_GEMM_PW_FWD, dw, b.cin, h->w(nm("conv2d_%d/kernel", i + 2)), b.cout, pw, b.cout, (int)M, b.cout, b.cin, nullptr, 0,
                         h->a(actbn(2 * i - 1, "scale")), h->a(actbn(2 * i - 1, "shift")), st));
         }
-        TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st, pw_stats));
+        TRY(bn_forward(h, 2 * i, pw, M, b.cout, training, st, pw_stats, training && h->bn_tail));
         // skip writing this block's output when (a) the next block's conv can recompute it (non-pooled, shapes covered) and (b) the backward pass
         // will not read it: the fused backward kernel with the fused BN2 reduction recomputes it as well (block_backward: `rrp` path)
         h->block_live[i] = !(i <= 6 && h->fwd_fused && b.ph == 1 && b.pw == 1 && dwconv_bwd_fused_covers(hh, ww, b.cout) &&
@@ -837,6 +865,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_FUSE_BN_RED"); h->fuse_bn_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_DW_RED"); h->dw_red = !(e && e[0] == '0'); }
+    { const char* e = getenv("CRNN_BN_TAIL"); h->bn_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_DW_FUSED"); h->dw_fused = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_FWD_FUSED"); h->fwd_fused = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }

@@ -10,7 +10,7 @@ constexpr int ED_MAXLEN = 128;
 
 __global__ void edit_distance_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ alen, const int32_t* __restrict__ b,
                                      const int32_t* __restrict__ blen, int N, int maxlen, int32_t* __restrict__ out)
-{
+{ pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int n = min(max(alen[i], 0), maxlen), m = min(max(blen[i], 0), maxlen);
@@ -38,7 +38,7 @@ __global__ void edit_distance_kernel(const int32_t* __restrict__ a, const int32_
 // reference's order -> bit-identical to numpy; lets the host upload the 8-bit line images (4x fewer H2D bytes) instead of float32.
 namespace {
 __global__ void normalize_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, long long n, float mean, float stdv)
-{
+{ pdl_enter();
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const uchar4 v = reinterpret_cast<const uchar4*>(in)[i];
@@ -56,7 +56,7 @@ int launch_normalize_u8(const uint8_t* in, float* out, long long n, float mean, 
     if (n <= 0) return CRNN_OK;
     if ((reinterpret_cast<uintptr_t>(in) & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) { crnn_set_error("normalize_u8: in must be 4-byte, out 16-byte aligned"); return CRNN_ERR_INVALID; }
     long long blocks = ((n >> 2) + 255) / 256; if (blocks < 1) blocks = 1; if (blocks > 148 * 8) blocks = 148 * 8;
-    normalize_u8_kernel<<<(int)blocks, 256, 0, st>>>(in, out, n, mean, stdv);
+    (void)crnn_launch(normalize_u8_kernel, (int)blocks, 256, 0, st, in, out, n, mean, stdv);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -65,7 +65,7 @@ int launch_edit_distance(const int32_t* a, const int32_t* alen, const int32_t* b
 {
     if (N <= 0) return CRNN_OK;
     if (maxlen < 1 || maxlen > ED_MAXLEN) { crnn_set_error("edit_distance: maxlen must be in 1..%d", ED_MAXLEN); return CRNN_ERR_INVALID; }
-    edit_distance_kernel<<<ceil_div(N, 128), 128, 0, st>>>(a, alen, b, blen, N, maxlen, out);
+    (void)crnn_launch(edit_distance_kernel, ceil_div(N, 128), 128, 0, st, a, alen, b, blen, N, maxlen, out);
     LAUNCH_CHECK();
     return CRNN_OK;
 }

@@ -96,7 +96,7 @@ __device__ __forceinline__ void store_xcontig(float (*S)[LD], const float (&v)[B
 
 template <int BM, int BN, int CM, int CN>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs p)
-{
+{ pdl_enter();
     constexpr int LDA = BM + 4, LDB = BN + 4;
     constexpr int TX = BN / (4 * CN);
     static_assert(TX * (BM / (4 * CM)) == NT, "thread grid");
@@ -210,7 +210,7 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t st)
     if (split > ktiles) split = ktiles;
     auto run = [&](auto kern, int BM, int BN) {
         dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM), split);
-        kern<<<grid, NT, 0, st>>>(p);
+        (void)crnn_launch(kern, grid, NT, 0, st, p);
     };
     const long long big_ctas = (long long)ceil_div(a.M, 128) * ceil_div(a.N, 128) * split;
     if (a.N > 64 && big_ctas >= 148) run(gemm_simt_kernel<128, 128, 2, 2>, 128, 128);

@@ -214,6 +214,7 @@ struct TcArgs {
     // v2, optional: fused reduction pass of the BatchNorm+ReLU6 backward that consumes `out` (= dL/d relu6(bn(y))): with y = red_y[m][n]
     // (same shape / row stride as out) the epilogue accumulates stats[n] += dz, stats[N + n] += dz * xhat, dz = out * 1[0 <= y*sc+sh <= 6]
     const float* red_y; const float* red_scale; const float* red_shift; const float* red_mean; const float* red_invstd;
+    BnFin fin;                        // v2, forward statistics only: BatchNorm finalize done by the last CTA (common.cuh)
 };
 
 // =====================================================================================================================
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
     const int p_begin = blockIdx.z * a.px_per_cta;
     int p_end = p_begin + a.px_per_cta; if (p_end > a.M) p_end = a.M;
     const int KB = (p_end - p_begin + 31) / 32;
-    if (KB <= 0) return;                       // uniform for the whole CTA
+    if (KB <= 0) { pdl_enter(); return; }      // uniform for the whole CTA
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 256); mbar_init(&empty[s], 1); }
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();            // barriers + TMEM are set up while the previous kernel of the stream drains; no global access above this line
 
     if (warp < 8) {
         // ------------------------------------------------ producers (next k-block's loads stay in flight in registers)
@@ -556,6 +558,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     if (PAIR) cluster_sync_all();            // both CTAs' barriers are initialised before anybody arrives on a remote one
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();            // barriers + TMEM are set up while the previous kernel of the stream drains; no global access above this line
 
     if (warp < TC2_PROD_WARPS) {
         // =========================== activation transform warps ===========================
@@ -848,6 +851,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    bn_finalize_tail(a.fin);                 // every CTA of the grid gets here, its statistics flushed
     if (PAIR) cluster_sync_all();            // neither CTA leaves (or frees TMEM) while the other may still signal its barriers / read its tiles
     if (warp == TC2_MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -859,7 +863,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) xw_gemm_tc_v2_kernel(TcArgs a,
 // Wimg[((ct*KB + kb)*2 + hl)*4096 + sw128_off(r, kk)] for Wop[n = ct*128 + r][k = kb*32 + kk]; rows n >= N are zero.
 //   transposed=1: Wop[n][k] = W[k*ldw + n]  (forward: Keras kernel is (Cin, Cout));  0: Wop[n][k] = W[n*ldw + k]  (dX)
 __global__ void prep_weight_images_kernel(const float* __restrict__ W, int ldw, int N, int K, int transposed, float* __restrict__ img)
-{
+{ pdl_enter();
     const int KB = K / TC_BK;
     const int NT = (N + TC_BC - 1) / TC_BC;
     const long long total = (long long)NT * TC_BC * K;
@@ -881,7 +885,7 @@ __global__ void prep_weight_images_kernel(const float* __restrict__ W, int ldw, 
 // all weight images of a step in ONE launch (22 tiny kernels on the side branch before): job j covers the flat index range
 // [start[j], start[j+1]) of its (channel-tile-padded N) x K element space
 __global__ void prep_weight_images_batch_kernel(TcPrepBatch t)
-{
+{ pdl_enter();
     const long long total = t.start[t.n];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
         int j = 0;
@@ -920,7 +924,7 @@ int launch_prep_weight_images_batch(const TcPrepBatch& t, cudaStream_t st)
     if (t.n <= 0) return CRNN_OK;
     const long long total = t.start[t.n];
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    prep_weight_images_batch_kernel<<<blocks, 256, 0, st>>>(t);
+    (void)crnn_launch(prep_weight_images_batch_kernel, blocks, 256, 0, st, t);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -932,7 +936,7 @@ int launch_prep_weight_images(const float* W, int ldw, int N, int K, int transpo
     if (K % TC_BK) { crnn_set_error("gemm_tc: K=%d must be a multiple of %d", K, TC_BK); return CRNN_ERR_INVALID; }
     long long total = (long long)((N + TC_BC - 1) / TC_BC) * TC_BC * K;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    prep_weight_images_kernel<<<blocks, 256, 0, st>>>(W, ldw, N, K, transposed, img);
+    (void)crnn_launch(prep_weight_images_kernel, blocks, 256, 0, st, W, ldw, N, K, transposed, img);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -963,6 +967,7 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     TcArgs a; a.X = X; a.ldx = ldx; a.Wimg = Wimg; a.out = out; a.ldo = ldo; a.M = M; a.N = N; a.K = K;
     a.x_scale = x_scale; a.x_shift = x_shift; a.stats = stats; a.bias = bias; a.relu = relu; a.accumulate = accumulate; a.rev = rev;
     a.red_y = nullptr; a.red_scale = a.red_shift = a.red_mean = a.red_invstd = nullptr;
+    a.fin = BnFin{}; if (stats && !red) a.fin = crnn_take_bn_fin();
     if (red) {
         if (!stats || bias || relu || accumulate || ksplit > 1) { crnn_set_error("gemm_tc: the fused BN-backward reduction needs stats and the plain-store epilogue"); return CRNN_ERR_INVALID; }
         a.red_y = red->y; a.red_scale = red->scale; a.red_shift = red->shift; a.red_mean = red->mean; a.red_invstd = red->invstd;
@@ -1036,7 +1041,7 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     } else {
         const long long total = (long long)NTP * MT * ksplit;
         const int grid = (int)(total < num_sms ? total : num_sms);
-        xw_gemm_tc_v2_kernel<false><<<grid, TC2_THREADS, TC2_SMEM_BYTES, st>>>(a, tmx, NTP, MT, NSUB, ksplit, split_stride, BP);
+        (void)crnn_launch(xw_gemm_tc_v2_kernel<false>, grid, TC2_THREADS, TC2_SMEM_BYTES, st, a, tmx, NTP, MT, NSUB, ksplit, split_stride, BP);
     }
     LAUNCH_CHECK();
     return CRNN_OK;
@@ -1069,10 +1074,10 @@ int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ld
     static bool c128 = false, c256 = false;
     if (NB == 256) {
         if (!c256) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<256>::SMEM_BYTES)); c256 = true; }
-        xty_gemm_tc_kernel<256><<<grid, DW_THREADS, DwCfg<256>::SMEM_BYTES, st>>>(a);
+        (void)crnn_launch(xty_gemm_tc_kernel<256>, grid, DW_THREADS, DwCfg<256>::SMEM_BYTES, st, a);
     } else {
         if (!c128) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<128>::SMEM_BYTES)); c128 = true; }
-        xty_gemm_tc_kernel<128><<<grid, DW_THREADS, DwCfg<128>::SMEM_BYTES, st>>>(a);
+        (void)crnn_launch(xty_gemm_tc_kernel<128>, grid, DW_THREADS, DwCfg<128>::SMEM_BYTES, st, a);
     }
     LAUNCH_CHECK();
     return CRNN_OK;

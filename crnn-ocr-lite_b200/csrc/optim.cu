@@ -6,7 +6,7 @@
 
 namespace {
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out)
-{
+{ pdl_enter();
     double s = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double v = (double)g[i]; s = fma(v, v, s);
@@ -29,7 +29,7 @@ __device__ __forceinline__ float clipped(float g, float gscale, float norm, floa
 }
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, const double* __restrict__ sumsq, float clipnorm, float lr_t, float b1, float b2, float eps, float gscale)
-{
+{ pdl_enter();
     const float norm = (float)(sqrt(*sumsq) * (double)gscale);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = clipped(g[i], gscale, norm, clipnorm);
@@ -41,7 +41,7 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
 }
 __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ vel, long long n,
                            const double* __restrict__ sumsq, float clipnorm, float lr_i, float mom, float gscale)
-{
+{ pdl_enter();
     const float norm = (float)(sqrt(*sumsq) * (double)gscale);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = clipped(g[i], gscale, norm, clipnorm);
@@ -53,13 +53,13 @@ __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, f
 }  // namespace
 
 int launch_sumsq(const float* g, long long n, double* out, cudaStream_t st) {
-    sumsq_kernel<<<148 * 4, 256, 0, st>>>(g, n, out); LAUNCH_CHECK(); return CRNN_OK;
+    (void)crnn_launch(sumsq_kernel, 148 * 4, 256, 0, st, g, n, out); LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_adam(float* w, const float* g, float* m, float* v, long long n, const double* sumsq, float clipnorm,
                 float lr_t, float b1, float b2, float eps, float gscale, cudaStream_t st) {
-    adam_kernel<<<148 * 4, 256, 0, st>>>(w, g, m, v, n, sumsq, clipnorm, lr_t, b1, b2, eps, gscale); LAUNCH_CHECK(); return CRNN_OK;
+    (void)crnn_launch(adam_kernel, 148 * 4, 256, 0, st, w, g, m, v, n, sumsq, clipnorm, lr_t, b1, b2, eps, gscale); LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_sgd_nesterov(float* w, const float* g, float* vel, long long n, const double* sumsq, float clipnorm,
                         float lr_i, float momentum, float gscale, cudaStream_t st) {
-    sgd_kernel<<<148 * 4, 256, 0, st>>>(w, g, vel, n, sumsq, clipnorm, lr_i, momentum, gscale); LAUNCH_CHECK(); return CRNN_OK;
+    (void)crnn_launch(sgd_kernel, 148 * 4, 256, 0, st, w, g, vel, n, sumsq, clipnorm, lr_i, momentum, gscale); LAUNCH_CHECK(); return CRNN_OK;
 }

@@ -129,7 +129,7 @@ constexpr int FWD_SMEM_FLOATS = 2 * U * RB + 2 * U * RB + 8 * 64 * RB + 8 * 32 *
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
 gru_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, const float* __restrict__ U1,
                    float* __restrict__ hs, float* __restrict__ gates, int B, int T)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* hT = sm;                                 // [2][256][8]  h_{t-1} of all units (k-major, rows fastest)
     float* rhT = hT + 2 * U * RB;                   // [2][256][8]  r * h_{t-1}
@@ -278,7 +278,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
 gru_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs, const float* __restrict__ gates,
                    const float* __restrict__ U0, const float* __restrict__ U1,
                    float* __restrict__ dxp, float* __restrict__ hprev_out, float* __restrict__ rh_out, int B, int T)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* da = sm;                                 // [3 gates z,r,h][32 units][8 rows]
     float* recvA = da + 3 * UPC * RB;               // [8 src][32][8]
@@ -423,7 +423,7 @@ constexpr int LF_SMEM_BYTES = 4 * (2 * U * RB + 4 * LC * RB + RING * 4 * (UPC * 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
 lstm_fwd_mma_kernel(const float* __restrict__ xp, const float* __restrict__ U0, const float* __restrict__ U1,
                     float* __restrict__ hs, float* __restrict__ gates, int B, int T)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* hT = sm;                                 // [2][256][8]
     float* part = hT + 2 * U * RB;                  // [4 k-quarters][128 cols (gate-major)][8 rows]
@@ -549,7 +549,7 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(NT, 1)
 lstm_bwd_mma_kernel(const float* __restrict__ dout, const float* __restrict__ hs, const float* __restrict__ gates,
                     const float* __restrict__ U0, const float* __restrict__ U1,
                     float* __restrict__ dxp, float* __restrict__ hprev_out, int B, int T)
-{
+{ pdl_enter();
     extern __shared__ __align__(16) float sm[];
     float* da = sm;                                 // [2][4 gates i,f,g,o][32 units][8 rows]
     float* recv = da + 2 * LC * RB;                 // [2][8 src][32][8]
@@ -687,7 +687,8 @@ int launch_gru_fwd_mma(const float* xp, const float* U0, const float* U1, float*
     static bool configured = false;
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(gru_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     dim3 grid(NCTA * ceil_div(B, RB), 2);
-    gru_fwd_mma_kernel<<<grid, NT, smem, st>>>(xp, U0, U1, hs, gates, B, T);
+    (void)crnn_launch(gru_fwd_mma_kernel, grid, NT, smem, st, xp, U0, U1, hs, gates, B, T);
+    crnn_pdl_mark_sparse(st);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -701,7 +702,8 @@ int launch_gru_bwd_mma(const float* dout, const float* hs, const float* gates, c
     static bool configured = false;
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(gru_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     dim3 grid(NCTA * ceil_div(B, RB), 2);
-    gru_bwd_mma_kernel<<<grid, NT, smem, st>>>(dout, hs, gates, U0, U1, dxp, hprev, rh, B, T);
+    (void)crnn_launch(gru_bwd_mma_kernel, grid, NT, smem, st, dout, hs, gates, U0, U1, dxp, hprev, rh, B, T);
+    crnn_pdl_mark_sparse(st);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -713,7 +715,8 @@ int launch_lstm_fwd_mma(const float* xp, const float* U0, const float* U1, float
     static bool configured = false;
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(lstm_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM_BYTES)); configured = true; }
     dim3 grid(NCTA * ceil_div(B, RB), 2);
-    lstm_fwd_mma_kernel<<<grid, NT, LF_SMEM_BYTES, st>>>(xp, U0, U1, hs, gates, B, T);
+    (void)crnn_launch(lstm_fwd_mma_kernel, grid, NT, LF_SMEM_BYTES, st, xp, U0, U1, hs, gates, B, T);
+    crnn_pdl_mark_sparse(st);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
@@ -726,7 +729,8 @@ int launch_lstm_bwd_mma(const float* dout, const float* hs, const float* gates, 
     static bool configured = false;
     if (!configured) { CUDA_TRY(cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM_BYTES)); configured = true; }
     dim3 grid(NCTA * ceil_div(B, RB), 2);
-    lstm_bwd_mma_kernel<<<grid, NT, LB_SMEM_BYTES, st>>>(dout, hs, gates, U0, U1, dxp, hprev, B, T);
+    (void)crnn_launch(lstm_bwd_mma_kernel, grid, NT, LB_SMEM_BYTES, st, dout, hs, gates, U0, U1, dxp, hprev, B, T);
+    crnn_pdl_mark_sparse(st);
     LAUNCH_CHECK();
     return CRNN_OK;
 }

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(1024)
 stn_trunk_fwd_kernel(const float* __restrict__ x, const float* __restrict__ k1, const float* __restrict__ b1,
                      const float* __restrict__ k2, const float* __restrict__ b2,
                      float* __restrict__ p1g, float* __restrict__ p2g, int* __restrict__ p2arg, float* __restrict__ flat, StnDims d)
-{
+{ pdl_enter();
     extern __shared__ float sm[];
     float* p1 = sm;                           // P1h*P1w
     float* sk1 = p1 + d.P1h * d.P1w;          // 25*20
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(1024)
 stn_trunk_bwd_kernel(const float* __restrict__ dflat, const float* __restrict__ p1g, const float* __restrict__ p2g,
                      const int* __restrict__ p2arg, const float* __restrict__ k2,
                      float* __restrict__ dk1, float* __restrict__ db1, float* __restrict__ dk2, float* __restrict__ db2, StnDims d)
-{
+{ pdl_enter();
     extern __shared__ float sm[];
     const int n2 = d.P2h * d.P2w * NC;
     float* p1 = sm;                       // P1h*P1w
@@ -187,7 +187,7 @@ __device__ __forceinline__ SamplePt sample_point(const float* __restrict__ th, i
 
 __global__ void stn_sample_fwd_kernel(const float* __restrict__ x, const float* __restrict__ theta, float* __restrict__ out,
                                       int B, int H, int W, int pad, long long total)
-{
+{ pdl_enter();
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         int jp = (int)(idx % Wp); long long r = idx / Wp;
@@ -207,7 +207,7 @@ __global__ void stn_sample_fwd_kernel(const float* __restrict__ x, const float* 
 // dtheta[b][0..5] = sum_pix dout * d out / d theta ; gradient flows through xf,yf inside the weights only
 __global__ void stn_sample_bwd_kernel(const float* __restrict__ x, const float* __restrict__ theta, const float* __restrict__ dout,
                                       float* __restrict__ dtheta, int H, int W, int pad)
-{
+{ pdl_enter();
     const int b = blockIdx.y;
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
     const float* xb = x + (size_t)b * H * W;
@@ -240,7 +240,7 @@ constexpr int ND1 = 50, NTH = 6;
 __global__ void __launch_bounds__(512)
 stn_head_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                     const float* __restrict__ b2, float* __restrict__ loc_d1, float* __restrict__ theta, int F)
-{
+{ pdl_enter();
     extern __shared__ float hsm[];            // flat row [F] | d1 [64] | partial (double) [8][64]
     float* row = hsm; float* d1 = row + ((F + 1) & ~1); double* part = reinterpret_cast<double*>(d1 + 64);
     const int b = blockIdx.x, tid = threadIdx.x, n = tid & 63, ks = tid >> 6;
@@ -278,7 +278,7 @@ stn_head_fwd_kernel(const float* __restrict__ flat, const float* __restrict__ W1
 __global__ void __launch_bounds__(256)
 stn_head_bwd_kernel(const float* __restrict__ dtheta, const float* __restrict__ loc_d1, const float* __restrict__ W1, const float* __restrict__ W2,
                     float* __restrict__ dd1, float* __restrict__ dflat, int F)
-{
+{ pdl_enter();
     __shared__ float g[ND1];
     const int b = blockIdx.x, tid = threadIdx.x;
     if (tid < ND1) {
@@ -307,7 +307,7 @@ int launch_stn_trunk_fwd(const float* x, const float* k1, const float* b1, const
     size_t smem = sizeof(float) * ((size_t)d.P1h * d.P1w + 25 * NC + (size_t)d.P2h * d.P2w * NC);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) { CUDA_TRY(cudaFuncSetAttribute(stn_trunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-    stn_trunk_fwd_kernel<<<B, 1024, smem, st>>>(x, k1, b1, k2, b2, p1, p2, p2arg, flat, d);
+    (void)crnn_launch(stn_trunk_fwd_kernel, B, 1024, smem, st, x, k1, b1, k2, b2, p1, p2, p2arg, flat, d);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_stn_trunk_bwd(const float* dflat, const float* p1, const float* p2, const int* p2arg, const float* k2,
@@ -318,20 +318,20 @@ int launch_stn_trunk_bwd(const float* dflat, const float* p1, const float* p2, c
     size_t smem = sizeof(float) * ((size_t)d.P1h * d.P1w + 2 * n2 + d.F + 25 * NC * NC) + ((n2 + 15) / 16) * 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) { CUDA_TRY(cudaFuncSetAttribute(stn_trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
-    stn_trunk_bwd_kernel<<<dim3(B, 2), 1024, smem, st>>>(dflat, p1, p2, p2arg, k2, dk1, db1, dk2, db2, d);
+    (void)crnn_launch(stn_trunk_bwd_kernel, dim3(B, 2), 1024, smem, st, dflat, p1, p2, p2arg, k2, dk1, db1, dk2, db2, d);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_stn_sample_fwd(const float* x, const float* theta, float* out, int B, int H, int W, int pad, cudaStream_t st)
 {
     long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad);
     long long blocks = (total + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    stn_sample_fwd_kernel<<<(int)blocks, 256, 0, st>>>(x, theta, out, B, H, W, pad, total);
+    (void)crnn_launch(stn_sample_fwd_kernel, (int)blocks, 256, 0, st, x, theta, out, B, H, W, pad, total);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_stn_sample_bwd(const float* x, const float* theta, const float* dout, float* dtheta, int B, int H, int W, int pad, cudaStream_t st)
 {
     dim3 grid(ceil_div((long long)H * W, 256 * 4), B);
-    stn_sample_bwd_kernel<<<grid, 256, 0, st>>>(x, theta, dout, dtheta, H, W, pad);
+    (void)crnn_launch(stn_sample_bwd_kernel, grid, 256, 0, st, x, theta, dout, dtheta, H, W, pad);
     LAUNCH_CHECK(); return CRNN_OK;
 }
 
@@ -340,14 +340,14 @@ int launch_stn_head_fwd(const float* flat, const float* W1, const float* b1, con
     if (B <= 0) return CRNN_OK;
     const size_t smem = sizeof(float) * (((size_t)F + 1) / 2 * 2 + 64) + sizeof(double) * 8 * 64;
     if (smem > 48 * 1024) { crnn_set_error("stn_head: flatten size %d too large", F); return CRNN_ERR_INVALID; }
-    stn_head_fwd_kernel<<<B, 512, smem, st>>>(flat, W1, b1, W2, b2, loc_d1, theta, F);
+    (void)crnn_launch(stn_head_fwd_kernel, B, 512, smem, st, flat, W1, b1, W2, b2, loc_d1, theta, F);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
 int launch_stn_head_bwd(const float* dtheta, const float* loc_d1, const float* W1, const float* W2, float* dd1, float* dflat, int B, int F, cudaStream_t st)
 {
     if (B <= 0) return CRNN_OK;
-    stn_head_bwd_kernel<<<B, 256, 0, st>>>(dtheta, loc_d1, W1, W2, dd1, dflat, F);
+    (void)crnn_launch(stn_head_bwd_kernel, B, 256, 0, st, dtheta, loc_d1, W1, W2, dd1, dflat, F);
     LAUNCH_CHECK();
     return CRNN_OK;
 }
