@@ -312,7 +312,7 @@ struct TrieNode { short parent, label, first_child, next_sib; };
 
 #define BEAM_MAX_W 32
 
-__global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __restrict__ seq_len,
+__global__ void __launch_bounds__(256, 4) ctc_beam_kernel(const float* __restrict__ probs, const int* __restrict__ seq_len,
                                 int B, int T, int V, float eps, int W, int merge_repeated, int P,
                                 int* __restrict__ out, int* __restrict__ out_len, float* __restrict__ logprob,
                                 int smem_per_warp_bytes)
@@ -334,6 +334,8 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
     float* bpb = (float*)(bnode + 64);                                   // [2][32] blank
     float* bpl = bpb + 64;                                               // [2][32] label
     float* bpt = bpl + 64;                                               // [2][32] total
+    float* sv = bpt + 64;                                                // [32] + int [32]: scratch for the compactions / permutations of a step
+    int* sk = (int*)(sv + 32);
 
     int nn = 1;        // nodes in the trie (uniform)
     int nb = 1;        // beam entries (uniform); slots are in descending-total order
@@ -372,40 +374,6 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
         __syncwarp();
         for (int k = lane; k < V; k += 32) in_[k] -= mx;
         __syncwarp();
-        // (a') the 32 best non-blank labels of this step, sorted (score descending, label ascending): lane j holds the j-th best.  Every
-        // parent scores its children as in_[k] + const, so ONE sorted list serves all parents: a parent then walks its candidates best
-        // first and stops at the first one that does not beat the bottom leaf -- the work per parent is (#insertions + 1) instead of a
-        // scan of all V-1 labels with an insertion attempt for every label above the bottom it started with (ncu r2a: 53 % of the
-        // kernel's instructions were that scan; candidates inserted early were evicted again by better siblings).
-        float tv = NEG_INF; int tk = 0x7fff0000 + lane;
-        if (fast) {
-            auto before = [](float va, int ka, float vb, int kb) { return va > vb || (va == vb && ka < kb); };
-            for (int k0 = 0; k0 < NC; k0 += 32) {
-                float cv = (k0 + lane < NC) ? in_[k0 + lane] : NEG_INF; int ck = (k0 + lane < NC) ? k0 + lane : 0x7ffe0000 + lane;
-                // bitonic sort of the chunk, descending
-#pragma unroll
-                for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                        const float ov = __shfl_xor_sync(FULL, cv, stride); const int ok = __shfl_xor_sync(FULL, ck, stride);
-                        const bool desc = (lane & size) == 0, low = (lane & stride) == 0;
-                        const bool other_first = before(ov, ok, cv, ck);
-                        if ((low == desc) ? other_first : !other_first) { cv = ov; ck = ok; }
-                    }
-                }
-                // merge with the running top 32: max(A_i, B_{31-i}) is bitonic and holds the 32 best of the union; 5 merge stages sort it
-                const float rv = __shfl_sync(FULL, cv, 31 - lane); const int rk = __shfl_sync(FULL, ck, 31 - lane);
-                if (before(rv, rk, tv, tk)) { tv = rv; tk = rk; }
-#pragma unroll
-                for (int stride = 16; stride > 0; stride >>= 1) {
-                    const float ov = __shfl_xor_sync(FULL, tv, stride); const int ok = __shfl_xor_sync(FULL, tk, stride);
-                    const bool low = (lane & stride) == 0;
-                    const bool other_first = before(ov, ok, tv, tk);
-                    if (low ? other_first : !other_first) { tv = ov; tk = ok; }
-                }
-            }
-        }
-
         const int* on = bnode + cur * 32; const float* opb = bpb + cur * 32; const float* opl = bpl + cur * 32; const float* opt = bpt + cur * 32;
         // ---- phase 1: survivors (lane e < nb)
         float s_nb = NEG_INF, s_nl = NEG_INF, s_nt = NEG_INF;
@@ -436,7 +404,84 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
             if (lane >= W) { Lv = NEG_INF; Lid = NOID; }
             if (nL < W) ++nL;
         };
-        for (int e = 0; e < nb; ++e) insert(__shfl_sync(FULL, s_nt, e), -1 - e);
+        {   // the survivors enter in slot order; insert() puts a new leaf BEFORE the leaves of equal total, so sequential insertion = sort by
+            // (total descending, slot descending): every survivor counts the ones that rank before it and the leaves are permuted through
+            // shared memory in one go (ncu r2u: 10 one-by-one insertions were 7 % of the instructions)
+            int rk = 0;
+            for (int e = 0; e < nb; ++e) { const float o = __shfl_sync(FULL, s_nt, e); rk += (o > s_nt || (o == s_nt && e > lane)) ? 1 : 0; }
+            if (lane < nb) { sv[rk] = s_nt; sk[rk] = -1 - lane; }
+            __syncwarp();
+            nL = nb < W ? nb : W;
+            if (lane < nL) { Lv = sv[lane]; Lid = sk[lane]; }
+            __syncwarp();
+        }
+
+        // (a') the best non-blank labels of this step, sorted (score descending, label ascending): lane j holds the j-th best.  Every
+        // parent scores its children as in_[k] + const, so ONE sorted list serves all parents: a parent then walks its candidates best
+        // first and stops at the first one that does not beat the bottom leaf -- the work per parent is (#insertions + 1) instead of a
+        // scan of all V-1 labels with an insertion attempt for every label above the bottom it started with (ncu r2a: 53 % of the
+        // kernel's instructions were that scan; candidates inserted early were evicted again by better siblings).
+        // Pruning (ncu r2u: the three 32-wide bitonic sorts + merges were 21 % of the instructions): once the leaves are full, a child scores at
+        // most in_[k] + opt[0] (best parent, and its blank probability is below its total) while insertion and the blocking count both need a
+        // score above a leaf, i.e. above the bottom after phase 1 (the bottom never drops).  Labels that fail in_[k] + opt[0] > bottom0 are
+        // dead for every parent; the survivors of that test are compacted through shared memory and sorted in ONE network of just their
+        // power-of-two size.  More than 32 survivors: the chunked sort below -- on configs[3] (N(0,9) logits) that is still the common case
+        // (ncu r2v: chunked sort 12 % of the instructions, pruned sort 1.5 %): the bottom after phase 1 carries this step's blank / repeat
+        // probability of a survivor, which is far below the best new label, so the test is weak until the first parent has inserted its
+        // children; peaked inputs (a trained model's softmax) are where it pays.
+        float tv = NEG_INF; int tk = 0x7fff0000 + lane;
+        if (fast) {
+            auto before = [](float va, int ka, float vb, int kb) { return va > vb || (va == vb && ka < kb); };
+            const float bottom0 = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
+            const float ot0 = opt[0];
+            int cnt = 0;
+            for (int k0 = 0; k0 < NC; k0 += 32) {
+                const int k = k0 + lane;
+                const float cv = (k < NC) ? in_[k] : NEG_INF;
+                const bool pass = k < NC && cv + ot0 > bottom0;
+                const unsigned bal = __ballot_sync(FULL, pass);
+                if (pass) { const int pos = cnt + __popc(bal & ((1u << lane) - 1u)); if (pos < 32) { sv[pos] = cv; sk[pos] = k; } }
+                cnt += __popc(bal);
+            }
+            if (cnt <= 32) {
+                __syncwarp();
+                float cv = (lane < cnt) ? sv[lane] : NEG_INF; int ck = (lane < cnt) ? sk[lane] : 0x7ffe0000 + lane;
+                // bitonic sort (descending) of the first 2^ceil(log2 cnt) lanes; the padding beyond them is already in place
+                for (int size = 2; (size >> 1) < cnt; size <<= 1) {
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        const float ov = __shfl_xor_sync(FULL, cv, stride); const int ok = __shfl_xor_sync(FULL, ck, stride);
+                        const bool desc = (lane & size) == 0, low = (lane & stride) == 0;
+                        const bool other_first = before(ov, ok, cv, ck);
+                        if ((low == desc) ? other_first : !other_first) { cv = ov; ck = ok; }
+                    }
+                }
+                tv = cv; tk = ck;
+            } else
+            for (int k0 = 0; k0 < NC; k0 += 32) {
+                float cv = (k0 + lane < NC) ? in_[k0 + lane] : NEG_INF; int ck = (k0 + lane < NC) ? k0 + lane : 0x7ffe0000 + lane;
+                // bitonic sort of the chunk, descending
+#pragma unroll
+                for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        const float ov = __shfl_xor_sync(FULL, cv, stride); const int ok = __shfl_xor_sync(FULL, ck, stride);
+                        const bool desc = (lane & size) == 0, low = (lane & stride) == 0;
+                        const bool other_first = before(ov, ok, cv, ck);
+                        if ((low == desc) ? other_first : !other_first) { cv = ov; ck = ok; }
+                    }
+                }
+                // merge with the running top 32: max(A_i, B_{31-i}) is bitonic and holds the 32 best of the union; 5 merge stages sort it
+                const float rv = __shfl_sync(FULL, cv, 31 - lane); const int rk = __shfl_sync(FULL, ck, 31 - lane);
+                if (before(rv, rk, tv, tk)) { tv = rv; tk = rk; }
+#pragma unroll
+                for (int stride = 16; stride > 0; stride >>= 1) {
+                    const float ov = __shfl_xor_sync(FULL, tv, stride); const int ok = __shfl_xor_sync(FULL, tk, stride);
+                    const bool low = (lane & stride) == 0;
+                    const bool other_first = before(ov, ok, tv, tk);
+                    if (low ? other_first : !other_first) { tv = ov; tk = ok; }
+                }
+            }
+        }
 
         // ---- phase 2: parents in beam order
         bool blocked = false;     // lane e: survivor e lost its t-1 probabilities (cannot expand children)
@@ -448,33 +493,52 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
             if (!(ot > bottom)) break;     // is_candidate(b->oldp) fails; the parents after r have smaller totals and the bottom never drops
             const int lab_r = nodes[on[r]].label;
             const unsigned km = __ballot_sync(FULL, lane < nb && s_q == r);   // survivors that are children of r
+            // this parent's view of the sorted candidates (fast path): lane j's label is a child still to be created iff it is not the
+            // parent's own label (scored apart, with the blank probability) and not one of its surviving children
+            bool lab_ok = lab_r >= 0;
+            bool valid = tk < NC && tk != lab_r;
+            if (fast)
+                for (unsigned m2 = km; m2; m2 &= m2 - 1) { const int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (tk == kk) valid = false; if (kk == lab_r) lab_ok = false; }
+            const float x = valid ? tv + ot : NEG_INF;
             // blocking test for every such survivor
-            for (unsigned m = km; m; m &= m - 1) {
-                const int c = __ffs(m) - 1;
-                const int k_c = __shfl_sync(FULL, s_k, c);
-                const float s_c = __shfl_sync(FULL, s_nt, c);
-                const unsigned pm = __ballot_sync(FULL, Lid == -1 - c);
-                bool blk;
-                if (pm == 0) blk = true;                     // already evicted from the leaves
-                else {
-                    int cnt = __ffs(pm) - 1;                 // rank of c in L
-                    for (int k0 = 0; k0 < k_c; k0 += 32) {
-                        const int k = k0 + lane;
-                        bool ok = k < k_c;
-                        for (unsigned m2 = km; m2; m2 &= m2 - 1) { const int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (k == kk) ok = false; }
-                        float x = ok ? in_[k] + ((k == lab_r) ? ob : ot) : NEG_INF;
-                        cnt += __popc(__ballot_sync(FULL, x > s_c));
+            if (km) {
+                const float vlab = (fast && lab_ok) ? in_[lab_r] + ob : NEG_INF;
+                const float x31 = __shfl_sync(FULL, tv, 31) + ot;           // no label outside the sorted 32 scores above this
+                for (unsigned m = km; m; m &= m - 1) {
+                    const int c = __ffs(m) - 1;
+                    const int k_c = __shfl_sync(FULL, s_k, c);
+                    const float s_c = __shfl_sync(FULL, s_nt, c);
+                    const unsigned pm = __ballot_sync(FULL, Lid == -1 - c);
+                    bool blk;
+                    if (pm == 0) blk = true;                     // already evicted from the leaves
+                    else {
+                        const int rank = __ffs(pm) - 1;          // rank of c in L
+                        int cnt = W;
+                        bool counted = false;
+                        if (fast) {
+                            // eligible children with a smaller label and a larger total, counted on the sorted list: exact unless the list's
+                            // last entry still beats s_c (then labels beyond it might, too) and the count has not reached W yet
+                            cnt = rank + __popc(__ballot_sync(FULL, x > s_c && tk < k_c)) + ((lab_r < k_c && vlab > s_c) ? 1 : 0);
+                            counted = cnt >= W || NC <= 32 || !(x31 > s_c);
+                        }
+                        if (!counted) {
+                            cnt = rank;
+                            for (int k0 = 0; k0 < k_c; k0 += 32) {
+                                const int k = k0 + lane;
+                                bool ok = k < k_c;
+                                for (unsigned m2 = km; m2; m2 &= m2 - 1) { const int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (k == kk) ok = false; }
+                                float xk = ok ? in_[k] + ((k == lab_r) ? ob : ot) : NEG_INF;
+                                cnt += __popc(__ballot_sync(FULL, xk > s_c));
+                            }
+                        }
+                        blk = cnt >= W;
                     }
-                    blk = cnt >= W;
+                    if (blk && lane == c) blocked = true;
                 }
-                if (blk && lane == c) blocked = true;
             }
             // insert the eligible children of r
             if (fast) {
                 // the child that repeats the parent's own label is scored with the parent's blank probability: handled apart
-                bool lab_ok = lab_r >= 0;
-                bool valid = tk < NC && tk != lab_r;
-                for (unsigned m2 = km; m2; m2 &= m2 - 1) { const int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (tk == kk) valid = false; if (kk == lab_r) lab_ok = false; }
                 if (lab_ok) {
                     const float v = in_[lab_r] + ob;
                     bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
@@ -482,7 +546,9 @@ __global__ void ctc_beam_kernel(const float* __restrict__ probs, const int* __re
                 }
                 // all other children, best first (lane order); equal scores keep the label order TF visits them in.  With W <= 16 the
                 // 32 sorted labels always suffice: at most W - 1 of them are survivors of this parent, one is its own label, W get in.
-                const float x = valid ? tv + ot : NEG_INF;
+                // (Tried in round 2: the number of insertions in closed form -- candidate j gets in iff it beats old leaf W-1-j -- which removes the
+                // bottom shuffle / compare / break per candidate: 1.6 % fewer instructions, but 5 % SLOWER together with 64-bit packed sort keys
+                // (ncu r2w vs r2v: issue-active 74 -> 69 %; longer dependent chains in a latency-bound warp).  Reverted.)
                 bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
                 for (unsigned m = __ballot_sync(FULL, x > bottom); m; m &= m - 1) {
                     const int src = __ffs(m) - 1;
@@ -636,9 +702,13 @@ int launch_ctc_beam(const float* probs, const int* seq_len, int B, int T, int V,
     if (V < 2 || V > 1024) { crnn_set_error("ctc_beam: %d classes not in [2,1024]", V); return CRNN_ERR_INVALID; }
     if ((size_t)1 + (size_t)W * T > 32000) { crnn_set_error("ctc_beam: W*T too large"); return CRNN_ERR_INVALID; }
     size_t per = sizeof(float) * ((V + 3) & ~3) + sizeof(TrieNode) * (((size_t)1 + (size_t)W * T + 1) & ~1)
-               + sizeof(int) * 64 + sizeof(float) * 64 * 3;
+               + sizeof(int) * 64 + sizeof(float) * 64 * 3 + sizeof(float) * 64;
     per = (per + 15) & ~(size_t)15;
-    int warps = 8;
+    // 4 warps per CTA: the kernel is bound by instruction issue, i.e. by the SM with the most resident warps; 4096 sequences in CTAs of 8 put
+    // 32 warps on some SMs and 24 on others (512 CTAs over 148 SMs), in CTAs of 4 they spread 28 / 24.  The register cap of 64
+    // (__launch_bounds__(256, 4)) keeps the whole batch resident in one wave: at 67 registers the last 68 CTAs ran as a second wave
+    // (ncu r2u: 554 us instead of 441 us with 17 % FEWER instructions)
+    int warps = 4;
     while (warps > 1 && per * warps > 200 * 1024) warps >>= 1;
     size_t smem = per * warps;
     if (smem > 227 * 1024) { crnn_set_error("ctc_beam: per-sequence state %zu B exceeds shared memory", per); return CRNN_ERR_INVALID; }

@@ -130,6 +130,7 @@ struct crnn_handle {
     bool fwd_fused = true; bool block_live[8] = {true, true, true, true, true, true, true, true};
     uint64_t last_seed = 0; int last_B = 0; bool last_drop = false;
     bool dw_fused = true;      // CRNN_DW_FUSED=0: separate ReLU6+BN-backward apply / depthwise backward-data / backward-weight kernels
+    int prio = 0;              // CRNN_PRIO: stream / graph-node priorities of the critical path vs the side branch (0 = none)
     bool bn_tail = true;       // CRNN_BN_TAIL=0: BatchNorm finalize as a launch of its own instead of the last-CTA tail of the kernel that accumulates the statistics
     bool dw_red = true;        // CRNN_DW_RED=0: the depthwise backward-data kernel does not accumulate the BN2-backward reduction of the block below
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
@@ -828,7 +829,7 @@ int run_graphed(crnn_handle* h, int kind, int B, const void* const (&ptrs)[6], i
         const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
         g->launches = g_crnn_launches - l0; g_crnn_launches = l0;
         cudaError_t ie = cudaSuccess;
-        if (rc == CRNN_OK && ce == cudaSuccess && graph) ie = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (rc == CRNN_OK && ce == cudaSuccess && graph) ie = cudaGraphInstantiate(&g->exec, graph, h->prio ? (unsigned long long)cudaGraphInstantiateFlagUseNodePriority : 0ull);
         if (graph) cudaGraphDestroy(graph);
         if (rc != CRNN_OK) { g->calls = -1; cudaGetLastError(); return rc; }
         if (ce != cudaSuccess || ie != cudaSuccess || !g->exec) {   // could not capture: stay eager for this key
@@ -872,8 +873,17 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     { const char* e = getenv("CRNN_GRAPH"); h->use_graph = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_OVERLAP"); h->overlap = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_SERPENTINE"); h->serp = !(e && e[0] == '0'); }
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
-    if (cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking) != cudaSuccess) { h->cap = nullptr; cudaGetLastError(); }
+    // CRNN_PRIO=1: the critical path (capture stream) at the highest stream priority, the side branch at the lowest; =2 the other way round;
+    // the step graph is then instantiated with per-node priorities (kernel nodes inherit the priority of the stream they were captured on)
+    // Measured (B200, bench.py, 40 steps, twice): 0 (none, default) 5.000 / 4.999 ms, 1 5.099 / 5.099 ms, 2 5.036 ms: the plain launch-order
+    // arbitration between the two branches is the best of the three -- favouring the critical path starves the weight-gradient GEMMs until
+    // the end of the backward pass, where nothing is left to overlap them with.
+    { const char* e = getenv("CRNN_PRIO"); h->prio = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }
+    int p_least = 0, p_greatest = 0;
+    if (h->prio && cudaDeviceGetStreamPriorityRange(&p_least, &p_greatest) != cudaSuccess) { h->prio = 0; cudaGetLastError(); }
+    const int p_side = h->prio == 1 ? p_least : p_greatest, p_cap = h->prio == 1 ? p_greatest : p_least;
+    if ((h->prio ? cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, p_side) : cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking)) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
+    if ((h->prio ? cudaStreamCreateWithPriority(&h->cap, cudaStreamNonBlocking, p_cap) : cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking)) != cudaSuccess) { h->cap = nullptr; cudaGetLastError(); }
     *out = h;
     return CRNN_OK;
 }

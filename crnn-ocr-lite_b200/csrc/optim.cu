@@ -27,28 +27,51 @@ __device__ __forceinline__ float clipped(float g, float gscale, float norm, floa
     if (clipnorm > 0.f && norm >= clipnorm) g = g * clipnorm / norm;   // Keras clip_norm: g * c / n
     return g;
 }
+// Both update kernels walk the arenas as float4 (the arenas are 256-byte aligned and every tensor in them is padded to 16 bytes; the
+// launcher falls back to the scalar tail for a length that is not a multiple of 4): 4 x fewer load / store instructions in flight per byte --
+// the scalar version reached 2.7 TB/s (29 us for 79 MB, ncu r2a) with 1024 threads per SM.  Per-element arithmetic unchanged.
+__device__ __forceinline__ void adam_one(float& w, float g, float& m, float& v, float gscale, float norm, float clipnorm, float lr_t, float b1, float b2, float eps)
+{
+    float gi = clipped(g, gscale, norm, clipnorm);
+    float mi = b1 * m + (1.f - b1) * gi;
+    float vi = b2 * v + (1.f - b2) * gi * gi;
+    m = mi; v = vi;
+    w = w - lr_t * mi / (sqrtf(vi) + eps);
+}
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, const double* __restrict__ sumsq, float clipnorm, float lr_t, float b1, float b2, float eps, float gscale)
 { pdl_enter();
     const float norm = (float)(sqrt(*sumsq) * (double)gscale);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float gi = clipped(g[i], gscale, norm, clipnorm);
-        float mi = b1 * m[i] + (1.f - b1) * gi;
-        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        w[i] = w[i] - lr_t * mi / (sqrtf(vi) + eps);
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long i = t0; i < n4; i += stride) {
+        float4 wq = reinterpret_cast<float4*>(w)[i], mq = reinterpret_cast<float4*>(m)[i], vq = reinterpret_cast<float4*>(v)[i];
+        const float4 gq = reinterpret_cast<const float4*>(g)[i];
+        adam_one(wq.x, gq.x, mq.x, vq.x, gscale, norm, clipnorm, lr_t, b1, b2, eps); adam_one(wq.y, gq.y, mq.y, vq.y, gscale, norm, clipnorm, lr_t, b1, b2, eps);
+        adam_one(wq.z, gq.z, mq.z, vq.z, gscale, norm, clipnorm, lr_t, b1, b2, eps); adam_one(wq.w, gq.w, mq.w, vq.w, gscale, norm, clipnorm, lr_t, b1, b2, eps);
+        reinterpret_cast<float4*>(m)[i] = mq; reinterpret_cast<float4*>(v)[i] = vq; reinterpret_cast<float4*>(w)[i] = wq;
     }
+    for (long long i = (n4 << 2) + t0; i < n; i += stride) adam_one(w[i], g[i], m[i], v[i], gscale, norm, clipnorm, lr_t, b1, b2, eps);
+}
+__device__ __forceinline__ void sgd_one(float& w, float g, float& vel, float gscale, float norm, float clipnorm, float lr_i, float mom)
+{
+    float gi = clipped(g, gscale, norm, clipnorm);
+    float ve = mom * vel - lr_i * gi;
+    vel = ve;
+    w = w + mom * ve - lr_i * gi;
 }
 __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ vel, long long n,
                            const double* __restrict__ sumsq, float clipnorm, float lr_i, float mom, float gscale)
 { pdl_enter();
     const float norm = (float)(sqrt(*sumsq) * (double)gscale);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float gi = clipped(g[i], gscale, norm, clipnorm);
-        float ve = mom * vel[i] - lr_i * gi;
-        vel[i] = ve;
-        w[i] = w[i] + mom * ve - lr_i * gi;
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long i = t0; i < n4; i += stride) {
+        float4 wq = reinterpret_cast<float4*>(w)[i], vq = reinterpret_cast<float4*>(vel)[i];
+        const float4 gq = reinterpret_cast<const float4*>(g)[i];
+        sgd_one(wq.x, gq.x, vq.x, gscale, norm, clipnorm, lr_i, mom); sgd_one(wq.y, gq.y, vq.y, gscale, norm, clipnorm, lr_i, mom);
+        sgd_one(wq.z, gq.z, vq.z, gscale, norm, clipnorm, lr_i, mom); sgd_one(wq.w, gq.w, vq.w, gscale, norm, clipnorm, lr_i, mom);
+        reinterpret_cast<float4*>(vel)[i] = vq; reinterpret_cast<float4*>(w)[i] = wq;
     }
+    for (long long i = (n4 << 2) + t0; i < n; i += stride) sgd_one(w[i], g[i], vel[i], gscale, norm, clipnorm, lr_i, mom);
 }
 }  // namespace
 
@@ -57,9 +80,11 @@ int launch_sumsq(const float* g, long long n, double* out, cudaStream_t st) {
 }
 int launch_adam(float* w, const float* g, float* m, float* v, long long n, const double* sumsq, float clipnorm,
                 float lr_t, float b1, float b2, float eps, float gscale, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) { crnn_set_error("adam: arenas must be 16-byte aligned"); return CRNN_ERR_INVALID; }
     (void)crnn_launch(adam_kernel, 148 * 4, 256, 0, st, w, g, m, v, n, sumsq, clipnorm, lr_t, b1, b2, eps, gscale); LAUNCH_CHECK(); return CRNN_OK;
 }
 int launch_sgd_nesterov(float* w, const float* g, float* vel, long long n, const double* sumsq, float clipnorm,
                         float lr_i, float momentum, float gscale, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(vel)) & 15) { crnn_set_error("sgd: arenas must be 16-byte aligned"); return CRNN_ERR_INVALID; }
     (void)crnn_launch(sgd_kernel, 148 * 4, 256, 0, st, w, g, vel, n, sumsq, clipnorm, lr_i, momentum, gscale); LAUNCH_CHECK(); return CRNN_OK;
 }
