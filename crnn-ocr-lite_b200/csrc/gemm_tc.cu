@@ -232,7 +232,8 @@ template <int NB> struct DwCfg {
     static constexpr int B_FLOATS = NB * 32;             // dY tile (hi or lo): 32 pixels x NB co
     static constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
     static constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4 + 1024 + 256;
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // cross-term UMMA of the two-instruction product (TWO = true below): D = F32, A = B = BF16, both MN-major
+    static constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 // MN-major SWIZZLE_128B_BASE32B descriptor: LBO = 4096 B, SBO = 512 B, version 1, layout type 1 (low word / TC_DESC_MN_HI below)
 // float offset of (pixel row pl in 0..31, 16-byte chunk c16 in 0..7) inside one 32-channel mn-block of an MN-major tile
@@ -263,17 +264,92 @@ __device__ __forceinline__ void umma_kblock_mn(uint32_t tacc, uint32_t ahi, uint
 #undef XTY_GROUP
 }
 
+// The same k-block as TWO UMMAs per group of 8 pixels (the product scheme of the xw kernel, TC_IDESC_BF16 above): hi*hi as kind::tf32 (K = 8
+// pixels) + ONE kind::f16 bf16 UMMA (K = 16) that carries both cross terms, K-interleaved per pixel p: slot 2p = {X_hi', dY_lo}, slot 2p+1 =
+// {X_lo, dY_hi'}.  The cross-term tiles take the place of the lo tiles (same bytes: 64 K-rows x 2 B instead of 32 x 4 B per channel) but are
+// MN-major *16-bit* tiles, whose canonical form is the plain SWIZZLE_128B one (cute Layout_MN_SW128_Atom): [mn-block of 64 channels = 128-byte
+// rows][k-group of 8 K-rows][8 rows x 128 B], 16-byte chunk index XOR row; SBO = k-group stride 1024 B (high word = TC_DESC_HI), LBO = mn-block
+// stride 8192 B (low word: 512 << 16 instead of the tf32 tiles' 256 << 16).  A group of 8 pixels = 16 K-rows = 2 k-groups = 128 descriptor units.
+template <uint32_t IDESC, uint32_t IDESC_BF16, uint32_t BLO>
+__device__ __forceinline__ void umma_kblock_mn2(uint32_t tacc, uint32_t ahi, uint32_t not_first) {
+#define XTY2_GROUP(G, P0)                                                                                                             \
+        "add.u32 a, %1, " #G "*64;\n\tadd.u32 b, %1, " #G "*64+2048;\n\tmov.b64 da, {a, %3};\n\tmov.b64 db, {b, %3};\n\t"                      \
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, " P0 ";\n\t"                                                        \
+        "add.u32 a, %1, " #G "*128+1024+16777216;\n\tadd.u32 b, %1, " #G "*128+2048+16777216+%7;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, 1;\n\t"
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        XTY2_GROUP(0, "p") XTY2_GROUP(1, "1") XTY2_GROUP(2, "1") XTY2_GROUP(3, "1")
+        "}"
+        ::"r"(tacc), "r"(ahi), "r"(not_first), "r"(TC_DESC_MN_HI), "r"(IDESC), "r"(TC_DESC_HI), "r"(IDESC_BF16), "n"(BLO) : "memory");
+#undef XTY2_GROUP
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
 struct DwArgs {
     const float* X; int ldx; int Cin;       // (M, Cin) raw activations (+ optional BN/ReLU6 per ci)
     const float* dY; int ldy; int Cout;     // (M, Cout)
     float* dW; int ldw;                     // (Cin, Cout), pre-zeroed / accumulated with atomics
     int M; int px_per_cta;                  // pixel range per CTA (multiple of 32)
     const float* x_scale; const float* x_shift;
+    int l2_pfd;                             // k-blocks of L2 prefetch distance (0 = none; CRNN_XTY_PFD)
 };
 
 constexpr int DW_THREADS = 288;     // 8 producer warps + 1 MMA warp
 
+// Epilogue of the dW kernels (warps 0-7, 256 threads): TMEM -> smem transpose -> coalesced red.global.add.v4.f32 into dW.
+// (ncu r1d: scalar REDs straight from the TMEM layout -- lane = dW row, 1 KB apart -- were 32 sectors per instruction and ~1/3
+// of the kernel; the split-K head GEMMs were pure epilogue.)  The pipeline stages are idle once acc_full fires and hold the tile.
 template <int NB>
+__device__ __forceinline__ void xty_epilogue(const DwArgs& a, uint64_t* accb, uint32_t tmem_base, float* stage_base, int warp, int lane, int ci0, int co0) {
+    constexpr int NG = NB / 128;
+    mbar_wait(accb, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    constexpr int SROW = NB + 4;                      // padded row: 16-byte aligned, conflict-free STS.128 / LDS.128
+    const uint32_t S = smem_u32(stage_base);
+    const int lq = warp & 3;
+    const int cbeg = (warp >> 2) * (NB / 2);
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + NB / 2; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const uint32_t dst = S + (uint32_t)((lq * 32 + lane) * SROW + c0) * 4u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            sts128(dst + j * 16, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");    // the 8 producer/epilogue warps only (the MMA warp is not part of it)
+#pragma unroll 1
+    for (int i = 0; i < 16; ++i) {
+        const int row = warp + 8 * i, grow = ci0 + row;
+        if (grow >= a.Cin) continue;
+#pragma unroll
+        for (int h = 0; h < NG; ++h) {
+            const int col = h * 128 + lane * 4, co = co0 + col;
+            if (co < a.Cout) {
+                const float4 v = lds128(S + (uint32_t)(row * SROW + col) * 4u);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dW + (size_t)grow * a.ldw + co), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
+template <int NB, bool TWO>
 __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
 {
     using C = DwCfg<NB>;
@@ -330,8 +406,33 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 }
             }
         };
+        // Optional L2 prefetch of the k-block `l2_pfd` steps ahead (CRNN_XTY_PFD, one lane per 128-byte line; OFF).  What ncu r2y shows for this
+        // kernel (block 6: 103 us, tensor pipe 63 %, 53 % of the producers' stall samples are long-scoreboard waits at the first use of the
+        // registers prefetched one k-block ahead; 467 MB arrive from L2 at 4.5 TB/s = 32 GB/s per SM with 48 KB of loads in flight per SM) and what
+        // did NOT move it (B200, bench.py, dW kernels per step): a third less tensor work (CRNN_XTY_2MMA) 0.839 vs 0.835 ms; TMA-fed producers
+        // whose proxy fence has no loads to wait for (CRNN_XTY_TMA) 0.860 ms; this L2 prefetch at distance 2 / 3 / 5 / 8: 0.864 / 0.865 / 0.886 /
+        // 0.912 ms against 0.843 ms without.  So neither the tensor pipe, nor the fence, nor DRAM latency paces it; the remaining suspect is the
+        // number of outstanding L1 misses an SM can hold (1536 sectors requested per k-block and SM).
+        const bool pf_lane = (q & 7) == 0;
+        auto l2_prefetch = [&](int kb) {
+            if (!pf_lane || kb >= KB) return;
+            const int pbase = p_begin + kb * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int p = pbase + pr0 + 8 * i;
+                if (p >= p_end) continue;
+                if (ci_ok) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.X + (size_t)p * a.ldx + ci));
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const int co = co0 + g * 128 + q * 4;
+                    if (co < a.Cout) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dY + (size_t)p * a.ldy + co));
+                }
+            }
+        };
+        if (a.l2_pfd > 0) for (int d = 1; d < a.l2_pfd; ++d) l2_prefetch(d);
         prefetch(0, xv, yv);
         for (int kb = 0; kb < KB; ++kb) {
+            if (a.l2_pfd > 0) l2_prefetch(kb + a.l2_pfd);
             if (kb + 1 < KB) prefetch(kb + 1, xn, yn);
             const int s = kb % C::STAGES;
             const uint32_t ph = (kb / C::STAGES) & 1;
@@ -354,7 +455,16 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[e], lo[e]);
                 const uint32_t off = (uint32_t)(mb * 1024 + mn_off(pl, chunk)) * 4u;
                 sts128(ahi + off, hi[0], hi[1], hi[2], hi[3]);
-                sts128(alo + off, lo[0], lo[1], lo[2], lo[3]);
+                // cross-term tile (TWO): K-rows 2 pl (slot 0) and 2 pl + 1 (slot 1) of this thread's 4 channels = 8 bytes each
+                const int r0 = 2 * pl, kr0 = r0 & 7;
+                const uint32_t offc = (uint32_t)((q >> 4) * 8192 + (r0 >> 3) * 1024 + kr0 * 128 + ((q & 1) << 3));
+                const uint32_t c0 = (uint32_t)((((q & 15) >> 1) ^ kr0) << 4), c1 = (uint32_t)((((q & 15) >> 1) ^ (kr0 + 1)) << 4);
+                if (TWO) {
+                    sts64(alo + offc + c0, pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));               // slot 0: X_hi'
+                    sts64(alo + offc + 128u + c1, pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));        // slot 1: X_lo
+                } else {
+                    sts128(alo + off, lo[0], lo[1], lo[2], lo[3]);
+                }
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const float y[4] = {yv[g][i].x, yv[g][i].y, yv[g][i].z, yv[g][i].w};
@@ -363,7 +473,13 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                     for (int e = 0; e < 4; ++e) split_tf32(y[e], yh[e], yl[e]);
                     const uint32_t offb = off + (uint32_t)(g * 4) * 4096u;
                     sts128(bhi + offb, yh[0], yh[1], yh[2], yh[3]);
-                    sts128(blo + offb, yl[0], yl[1], yl[2], yl[3]);
+                    if (TWO) {
+                        const uint32_t offcb = offc + (uint32_t)(g * 2) * 8192u;
+                        sts64(blo + offcb + c0, pack_bf16x2(yl[0], yl[1]), pack_bf16x2(yl[2], yl[3]));          // slot 0: dY_lo
+                        sts64(blo + offcb + 128u + c1, pack_bf16x2(yh[0], yh[1]), pack_bf16x2(yh[2], yh[3]));   // slot 1: dY_hi'
+                    } else {
+                        sts128(blo + offb, yl[0], yl[1], yl[2], yl[3]);
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -375,49 +491,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
                 for (int g = 0; g < NG; ++g) yv[g][i] = yn[g][i];
             }
         }
-        // ------------------------------------------------ epilogue: TMEM -> smem transpose -> coalesced red.global.add.v4.f32 into dW.
-        // (ncu r1d: scalar REDs straight from the TMEM layout -- lane = dW row, 1 KB apart -- were 32 sectors per instruction and ~1/3
-        // of the kernel; the split-K head GEMMs were pure epilogue.)  The pipeline stages are idle once acc_full fires and hold the tile.
-        mbar_wait(accb, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        constexpr int SROW = NB + 4;                      // padded row: 16-byte aligned, conflict-free STS.128 / LDS.128
-        const uint32_t S = smem_u32(stage_base);
-        const int lq = warp & 3;
-        const int cbeg = (warp >> 2) * (NB / 2);
-#pragma unroll 1
-        for (int c0 = cbeg; c0 < cbeg + NB / 2; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const uint32_t dst = S + (uint32_t)((lq * 32 + lane) * SROW + c0) * 4u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                sts128(dst + j * 16, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");    // the 8 producer/epilogue warps only (the MMA warp is not part of it)
-#pragma unroll 1
-        for (int i = 0; i < 16; ++i) {
-            const int row = warp + 8 * i, grow = ci0 + row;
-            if (grow >= a.Cin) continue;
-#pragma unroll
-            for (int h = 0; h < NG; ++h) {
-                const int col = h * 128 + lane * 4, co = co0 + col;
-                if (co < a.Cout) {
-                    const float4 v = lds128(S + (uint32_t)(row * SROW + col) * 4u);
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dW + (size_t)grow * a.ldw + co), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        xty_epilogue<NB>(a, accb, tmem_base, stage_base, warp, lane, ci0, co0);
     } else {
         // ------------------------------------------------ warp 8: MMA issue (lean path: whole warp, uniform operands, one elected lane --
         // see umma_kblock; the per-instruction descriptor assembly + waterfall loops cost ~110 cycles per UMMA against 64 (NB = 128))
@@ -430,8 +504,153 @@ __global__ void __launch_bounds__(DW_THREADS, 1) xty_gemm_tc_kernel(DwArgs a)
             mbar_wait(&full[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ahi = adesc0 + (uint32_t)s * (uint32_t)(C::STAGE_FLOATS * 4 / 16);
-            umma_kblock_mn<C::IDESC, C::B_FLOATS * 4 / 16>(tb, ahi, (uint32_t)kb);
+            if (TWO) umma_kblock_mn2<C::IDESC, C::IDESC_BF16, C::B_FLOATS * 4 / 16>(tb, ahi, (uint32_t)kb);
+            else umma_kblock_mn<C::IDESC, C::B_FLOATS * 4 / 16>(tb, ahi, (uint32_t)kb);
             umma_commit_elect(bar_empty + 8u * s, kb == KB - 1 ? bar_acc : 0u, 0u);
+        }
+    }
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NB) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// dW kernel, TMA-fed (round 2, CRNN_XTY_TMA=1; exact, measured 3 % SLOWER than the kernel below, so off): same tiles, descriptors, MMA issue and epilogue as xty_gemm_tc_kernel below, different PRODUCERS.
+// ncu r2z showed the register-prefetching producers of that kernel paced by global-load latency: their generic->async proxy fence
+// (MEMBAR.ALL.CTA) waits for the NEXT k-block's loads they have in flight, so every k-block exposes a full memory latency (3300 cycles per
+// k-block against 1536 of tensor work; two UMMAs instead of three changed nothing, CRNN_XTY_2MMA).  Here the loads are the TMA unit's:
+//   warp 9  (one lane)  per k-block: dY box {32 channels, 32 pixels} x NB/32 with SWIZZLE_128B_ATOM_32B straight into the stage's B_hi tile
+//                       (the tensor-map swizzle IS the MN-major SWIZZLE_128B_BASE32B operand layout: 32-byte chunk XOR row-in-4; the tensor
+//                       core reads the top 19 bits of each fp32 word, i.e. hi = truncation to tf32), and the raw X box {128, 32} into a ring;
+//   warps 0-7           X: raw ring -> BatchNorm + ReLU6 -> {hi, lo} operand tiles;  dY: read the landed B_hi tile in place and store only
+//                       lo = y - trunc_tf32(y) -- no global loads in flight in these warps, so their proxy fence costs nothing;
+//   warp 8              3xTF32 issue (umma_kblock_mn) as before.
+// Rows >= M and channels >= Cin / Cout arrive as zeros from the TMA unit.  2 operand stages (96 KB each at NB = 256) + 2 raw X entries = 224 KB.
+// =====================================================================================================================
+constexpr int DW2_THREADS = 320;    // warps 0-7 transform (+ epilogue), warp 8 MMA issue, warp 9 TMA
+template <int NB> struct Dw2Cfg {
+    static constexpr int STAGES = 2;
+    static constexpr int RAWX = NB == 256 ? 2 : 3;
+    static constexpr int A_BYTES = 128 * 32 * 4, B_BYTES = NB * 32 * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAWX * A_BYTES + 1024 + 256;
+};
+__device__ __forceinline__ void tma_box_2d(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+template <int NB>
+__global__ void __launch_bounds__(DW2_THREADS, 1) xty_gemm_tma_kernel(DwArgs a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY)
+{
+    using C = Dw2Cfg<NB>;
+    using C1 = DwCfg<NB>;
+    constexpr int NG = NB / 128;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* stage_base = (float*)smem;
+    unsigned char* rawx = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(rawx + C::RAWX * C::A_BYTES);
+    uint64_t* full = bars; uint64_t* empty = full + C::STAGES; uint64_t* bfull = empty + C::STAGES;
+    uint64_t* rfull = bfull + C::STAGES; uint64_t* rempty = rfull + C::RAWX; uint64_t* accb = rempty + C::RAWX;
+    uint32_t* tmem_slot = (uint32_t*)(accb + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ci0 = blockIdx.x * 128, co0 = blockIdx.y * NB;
+    const int p_begin = blockIdx.z * a.px_per_cta;
+    int p_end = p_begin + a.px_per_cta; if (p_end > a.M) p_end = a.M;
+    const int KB = (p_end - p_begin + 31) / 32;
+    if (KB <= 0) { pdl_enter(); return; }      // uniform for the whole CTA
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); mbar_init(&bfull[s], 1); }
+        for (int r = 0; r < C::RAWX; ++r) { mbar_init(&rfull[r], 1); mbar_init(&rempty[r], 8); }
+        mbar_init(accb, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NB) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();
+
+    if (warp < 8) {
+        // ------------------------------------------------ transform warps: a warp = one pixel row x 128 channels per step (q = channel quad)
+        const int q = tid & 31, pr0 = tid >> 5;
+        const int ci = ci0 + q * 4;
+        const bool ci_ok = ci < a.Cin;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.x_scale && ci_ok) { sc = __ldg(reinterpret_cast<const float4*>(a.x_scale + ci)); sh = __ldg(reinterpret_cast<const float4*>(a.x_shift + ci)); }
+        const int mb = q >> 3, chunk = q & 7;
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % C::STAGES, r = kb % C::RAWX;
+            const uint32_t ahi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+            const uint32_t alo = ahi + C::A_BYTES, bhi = alo + C::A_BYTES, blo = bhi + C::B_BYTES;
+            const uint32_t rx = smem_u32(rawx + (size_t)r * C::A_BYTES);
+            const int pbase = p_begin + kb * 32;
+            mbar_wait(&rfull[r], (kb / C::RAWX) & 1);
+            mbar_wait(&bfull[s], (kb / C::STAGES) & 1);          // implies empty[s]: the loader waited for it before it issued this box
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pl = pr0 + 8 * i;
+                const float4 xr = lds128(rx + (uint32_t)(pl * 128 + q * 4) * 4u);
+                float x[4] = {xr.x, xr.y, xr.z, xr.w};
+                if (a.x_scale) {
+                    x[0] = relu6f(fmaf(x[0], sc.x, sh.x)); x[1] = relu6f(fmaf(x[1], sc.y, sh.y));
+                    x[2] = relu6f(fmaf(x[2], sc.z, sh.z)); x[3] = relu6f(fmaf(x[3], sc.w, sh.w));
+                    if (pbase + pl >= p_end || !ci_ok) { x[0] = x[1] = x[2] = x[3] = 0.f; }
+                }
+                float hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(x[e], hi[e], lo[e]);
+                const uint32_t off = (uint32_t)(mb * 1024 + mn_off(pl, chunk)) * 4u;
+                sts128(ahi + off, hi[0], hi[1], hi[2], hi[3]);
+                sts128(alo + off, lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t offb = off + (uint32_t)(g * 4) * 4096u;
+                    const float4 y = lds128(bhi + offb);
+                    sts128(blo + offb, y.x - __uint_as_float(__float_as_uint(y.x) & 0xffffe000u), y.y - __uint_as_float(__float_as_uint(y.y) & 0xffffe000u),
+                                       y.z - __uint_as_float(__float_as_uint(y.z) & 0xffffe000u), y.w - __uint_as_float(__float_as_uint(y.w) & 0xffffe000u));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&full[s]); mbar_arrive(&rempty[r]); }
+        }
+        xty_epilogue<NB>(a, accb, tmem_base, stage_base, warp, lane, ci0, co0);
+    } else if (warp == 8) {
+        // ------------------------------------------------ MMA issue (lean path, see umma_kblock)
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t adesc0 = ((smem_u32(stage_base) >> 4) & 0x3FFFu) | (256u << 16);      // MN-major: LBO = 4096 B in the low word
+        const uint32_t bar_empty = smem_u32(empty), bar_acc = smem_u32(accb);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % C::STAGES;
+            mbar_wait(&bfull[s], (kb / C::STAGES) & 1);      // the TMA-written B_hi tile (long complete: the transform warps waited for it)
+            mbar_wait(&full[s], (kb / C::STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ahi = adesc0 + (uint32_t)s * (uint32_t)(C::STAGE_BYTES / 16);
+            umma_kblock_mn<C1::IDESC, C::B_BYTES / 16>(tb, ahi, (uint32_t)kb);
+            umma_commit_elect(bar_empty + 8u * s, kb == KB - 1 ? bar_acc : 0u, 0u);
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------ TMA loader
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % C::STAGES, r = kb % C::RAWX;
+            const int p0 = p_begin + kb * 32;
+            const uint32_t bhi = smem_u32(smem + (size_t)s * C::STAGE_BYTES) + 2u * C::A_BYTES;
+            mbar_wait(&empty[s], ((kb / C::STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bfull[s], (uint32_t)C::B_BYTES);
+#pragma unroll
+            for (int j = 0; j < NB / 32; ++j) tma_box_2d(bhi + (uint32_t)j * 4096u, &tmY, co0 + j * 32, p0, smem_u32(&bfull[s]));
+            mbar_wait(&rempty[r], ((kb / C::RAWX) & 1) ^ 1);
+            mbar_arrive_expect_tx(&rfull[r], (uint32_t)C::A_BYTES);
+            tma_box_2d(smem_u32(rawx + (size_t)r * C::A_BYTES), &tmX, ci0, p0, smem_u32(&rfull[r]));
         }
     }
     __syncthreads();
@@ -1047,6 +1266,29 @@ int launch_xw_gemm_tc(const float* X, int ldx, const float* Wimg, float* out, in
     return CRNN_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda): 2-D fp32 tensor {dim0 contiguous, dim1 rows
+// of stride ld floats}, box {box0, box1}, out-of-range elements read as 0
+static int tc_encode_2d(CUtensorMap* tm, const float* base, long long dim0, long long dim1, long long ld, int box0, int box1, CUtensorMapSwizzle swz) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError(); crnn_set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver"); return CRNN_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { crnn_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for %p, dims %lld x %lld, ld %lld, box %d x %d", (int)r, (const void*)base, dim0, dim1, ld, box0, box1); return CRNN_ERR_CUDA; }
+    return CRNN_OK;
+}
+
 int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ldy, int Cout, float* dW, int ldw, int M,
                        const float* x_scale, const float* x_shift, cudaStream_t st)
 {
@@ -1070,14 +1312,49 @@ int launch_xty_gemm_tc(const float* X, int ldx, int Cin, const float* dY, int ld
     splits = (M + per - 1) / per;
     DwArgs a; a.X = X; a.ldx = ldx; a.Cin = Cin; a.dY = dY; a.ldy = ldy; a.Cout = Cout; a.dW = dW; a.ldw = ldw; a.M = M; a.px_per_cta = per;
     a.x_scale = x_scale; a.x_shift = x_shift;
+    static int pfd = -1;
+    if (pfd < 0) { const char* e = getenv("CRNN_XTY_PFD"); pfd = e ? atoi(e) : 0; if (pfd < 0 || pfd > 16) pfd = 0; }
+    a.l2_pfd = pfd;
     dim3 grid((Cin + 127) / 128, (Cout + NB - 1) / NB, splits);
-    static bool c128 = false, c256 = false;
+    // CRNN_XTY_TMA=1: the TMA-fed kernel (xty_gemm_tma_kernel) instead of the register-prefetching producers
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("CRNN_XTY_TMA"); v1 = (e && e[0] == '1') ? 0 : 1; }
+    if (!v1) {
+        CUtensorMap tmX, tmY;
+        { const int rc = tc_encode_2d(&tmX, X, Cin, M, ldx, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc != CRNN_OK) return rc; }
+        { const int rc = tc_encode_2d(&tmY, dY, Cout, M, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); if (rc != CRNN_OK) return rc; }
+        static bool conf2 = false;
+        if (!conf2) {
+            CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dw2Cfg<256>::SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dw2Cfg<128>::SMEM_BYTES));
+            conf2 = true;
+        }
+        if (NB == 256) (void)crnn_launch(xty_gemm_tma_kernel<256>, grid, DW2_THREADS, Dw2Cfg<256>::SMEM_BYTES, st, a, tmX, tmY);
+        else (void)crnn_launch(xty_gemm_tma_kernel<128>, grid, DW2_THREADS, Dw2Cfg<128>::SMEM_BYTES, st, a, tmX, tmY);
+        LAUNCH_CHECK();
+        return CRNN_OK;
+    }
+    // CRNN_XTY_2MMA=1: the two-UMMA product (tf32 main term + one bf16 UMMA with both cross terms, umma_kblock_mn2) instead of 3xTF32.  Exact to the
+    // same tolerance (test_gemm_tc_dw passes either way) and a third less tensor work, but NOT faster -- measured in the step (B200, bench.py,
+    // 40 steps, twice each): dW kernels 0.835 / 0.837 ms per step with 3xTF32, 0.839 / 0.839 ms with two UMMAs; step 4.986 / 4.988 vs 4.990 /
+    // 4.989 ms.  The kernel is paced by its producers' operand traffic (block 6: 456 MB from L2 in 112 us = 4.1 TB/s, every X tile is read by
+    // the 2 CTAs of the other output-channel tiles and every dY tile by 4), not by the tensor pipe -- so the more accurate 3xTF32 form stays.
+    static int three = -1;
+    if (three < 0) { const char* e = getenv("CRNN_XTY_2MMA"); three = (e && e[0] == '1') ? 0 : 1; }
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<256>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<256>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<128>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<128>::SMEM_BYTES));
+        configured = true;
+    }
     if (NB == 256) {
-        if (!c256) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<256>::SMEM_BYTES)); c256 = true; }
-        (void)crnn_launch(xty_gemm_tc_kernel<256>, grid, DW_THREADS, DwCfg<256>::SMEM_BYTES, st, a);
+        if (three) (void)crnn_launch(xty_gemm_tc_kernel<256, false>, grid, DW_THREADS, DwCfg<256>::SMEM_BYTES, st, a);
+        else (void)crnn_launch(xty_gemm_tc_kernel<256, true>, grid, DW_THREADS, DwCfg<256>::SMEM_BYTES, st, a);
     } else {
-        if (!c128) { CUDA_TRY(cudaFuncSetAttribute(xty_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<128>::SMEM_BYTES)); c128 = true; }
-        (void)crnn_launch(xty_gemm_tc_kernel<128>, grid, DW_THREADS, DwCfg<128>::SMEM_BYTES, st, a);
+        if (three) (void)crnn_launch(xty_gemm_tc_kernel<128, false>, grid, DW_THREADS, DwCfg<128>::SMEM_BYTES, st, a);
+        else (void)crnn_launch(xty_gemm_tc_kernel<128, true>, grid, DW_THREADS, DwCfg<128>::SMEM_BYTES, st, a);
     }
     LAUNCH_CHECK();
     return CRNN_OK;
