@@ -98,7 +98,7 @@ def profiled_traffic(kernel):
             continue
         recs = [r for r in json.load(open(p)) if r.get("capture") == want and "dram_read_MB" in r]
         if recs:
-            r = recs[-1]
+            r = recs[0]            # the summaries are kept newest capture set first (tools/profiles_merge.py)
             return {"bytes_per_launch": (r["dram_read_MB"] + r["dram_write_MB"]) * 1e6, "launch": "%s (%s), %.1f us under ncu" % (r["kernel"].strip(), want, r["time_us"]),
                     "tensor_pipe_pct_ncu": r.get("tensor_pipe_pct"), "source": "profiles/" + name}
     return None
