@@ -430,18 +430,62 @@ __global__ void __launch_bounds__(256, 4) ctc_beam_kernel(const float* __restric
         // probability of a survivor, which is far below the best new label, so the test is weak until the first parent has inserted its
         // children; peaked inputs (a trained model's softmax) are where it pays.
         float tv = NEG_INF; int tk = 0x7fff0000 + lane;
+        float list_floor = NEG_INF;      // the sorted list holds every label whose child score can reach this value (see the second floor below)
         if (fast) {
             auto before = [](float va, int ka, float vb, int kb) { return va > vb || (va == vb && ka < kb); };
             const float bottom0 = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
             const float ot0 = opt[0];
-            int cnt = 0;
-            for (int k0 = 0; k0 < NC; k0 += 32) {
-                const int k = k0 + lane;
-                const float cv = (k < NC) ? in_[k] : NEG_INF;
-                const bool pass = k < NC && cv + ot0 > bottom0;
-                const unsigned bal = __ballot_sync(FULL, pass);
-                if (pass) { const int pos = cnt + __popc(bal & ((1u << lane) - 1u)); if (pos < 32) { sv[pos] = cv; sk[pos] = k; } }
-                cnt += __popc(bal);
+            // labels whose best possible child score passes `thr` (strictly above, or >= when `incl`), compacted into sv / sk; returns their number
+            auto compact = [&](float thr, bool incl) {
+                int n = 0;
+                for (int k0 = 0; k0 < NC; k0 += 32) {
+                    const int k = k0 + lane;
+                    const float cv = (k < NC) ? in_[k] : NEG_INF;
+                    const float x0 = cv + ot0;
+                    const bool pass = k < NC && (incl ? x0 >= thr : x0 > thr);
+                    const unsigned bal = __ballot_sync(FULL, pass);
+                    if (pass) { const int pos = n + __popc(bal & ((1u << lane) - 1u)); if (pos < 32) { sv[pos] = cv; sk[pos] = k; } }
+                    n += __popc(bal);
+                }
+                return n;
+            };
+            int cnt = compact(bottom0, false);
+            if (cnt > 32 && nL == W) {
+                // Second, stronger floor B <= the bottom leaf AFTER parent 0 (the best entry, visited first, never blocked) has inserted its
+                // children: the leaves are then the top W of {survivors} U {its new children}, and the W-th largest of any SUBSET of that union
+                // bounds it from below.  Subset = the survivors + one new child per lane (the lane's best label, not the parent's own label --
+                // scored apart with the blank probability -- and not a label of one of its surviving children, whose total is already a leaf).
+                // B = W-th largest of two sorted lists a (leaves) and b (the 32 lane-best child scores, sorted here by value only)
+                //   = max over i of min(a[i-1], b[W-1-i]).  Labels with in_[k] + opt[0] < B are dead: parent 0 never inserts a child below the
+                // bottom it ends with (children are inserted best first and never evicted by a later, smaller one), later parents need to beat
+                // a bottom >= B with a smaller total, and the blocking count is taken on the list only when the survivor's total is >= B
+                // (list_floor below; otherwise the full scan).
+                const unsigned km0 = __ballot_sync(FULL, lane < nb && s_q == 0);
+                const int lab0 = nodes[on[0]].label;
+                float lm = NEG_INF;
+                for (int k0 = 0; k0 < NC; k0 += 32) {
+                    const int k = k0 + lane;
+                    float v = (k < NC && k != lab0) ? in_[k] : NEG_INF;
+                    for (unsigned m2 = km0; m2; m2 &= m2 - 1) { const int kk = __shfl_sync(FULL, s_k, __ffs(m2) - 1); if (k == kk) v = NEG_INF; }
+                    lm = fmaxf(lm, v);
+                }
+                float c = lm + ot0;
+#pragma unroll
+                for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        const float o = __shfl_xor_sync(FULL, c, stride);
+                        c = (((lane & size) == 0) == ((lane & stride) == 0)) ? fmaxf(c, o) : fminf(c, o);      // descending
+                    }
+                }
+                const float a1 = __shfl_up_sync(FULL, Lv, 1);
+                const float b1 = __shfl_sync(FULL, c, lane < W ? W - 1 - lane : 0);
+                float t = (lane <= W) ? fminf(lane == 0 ? INFINITY : a1, lane < W ? b1 : INFINITY) : NEG_INF;
+                const float Bf = warp_max(t);
+                if (Bf > bottom0) {
+                    const int cnt2 = compact(Bf, true);
+                    if (cnt2 <= 32) { cnt = cnt2; list_floor = Bf; }
+                }
             }
             if (cnt <= 32) {
                 __syncwarp();
@@ -519,7 +563,7 @@ __global__ void __launch_bounds__(256, 4) ctc_beam_kernel(const float* __restric
                             // eligible children with a smaller label and a larger total, counted on the sorted list: exact unless the list's
                             // last entry still beats s_c (then labels beyond it might, too) and the count has not reached W yet
                             cnt = rank + __popc(__ballot_sync(FULL, x > s_c && tk < k_c)) + ((lab_r < k_c && vlab > s_c) ? 1 : 0);
-                            counted = cnt >= W || NC <= 32 || !(x31 > s_c);
+                            counted = cnt >= W || (s_c >= list_floor && (NC <= 32 || !(x31 > s_c)));
                         }
                         if (!counted) {
                             cnt = rank;
