@@ -590,16 +590,24 @@ __global__ void __launch_bounds__(256, 4) ctc_beam_kernel(const float* __restric
                 }
                 // all other children, best first (lane order); equal scores keep the label order TF visits them in.  With W <= 16 the
                 // 32 sorted labels always suffice: at most W - 1 of them are survivors of this parent, one is its own label, W get in.
-                // (Tried in round 2: the number of insertions in closed form -- candidate j gets in iff it beats old leaf W-1-j -- which removes the
-                // bottom shuffle / compare / break per candidate: 1.6 % fewer instructions, but 5 % SLOWER together with 64-bit packed sort keys
-                // (ncu r2w vs r2v: issue-active 74 -> 69 %; longer dependent chains in a latency-bound warp).  Reverted.)
+                // How many get in is known up front: candidates only ever evict old leaves, from the end (a candidate cannot beat the bottom if
+                // the bottom is an earlier, larger candidate), so after j insertions the bottom is old leaf W-1-j (or candidate j-1 if that is
+                // smaller, and then candidate j fails both tests): candidate j gets in iff it beats old leaf W-1-j, and once one fails all
+                // later ones do.  No bottom shuffle / compare / break per candidate (ncu r2v: this loop was 20 % of the instructions).
+                // Measured alone: 12.2 -> 12.8 M lines/s on configs[3] (when first tried together with 64-bit packed sort keys the pair was 5 % slower --
+                // the packed keys were the loss).
                 bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
-                for (unsigned m = __ballot_sync(FULL, x > bottom); m; m &= m - 1) {
-                    const int src = __ffs(m) - 1;
-                    const float v = __shfl_sync(FULL, x, src);
-                    bottom = (nL == W) ? __shfl_sync(FULL, Lv, W - 1) : NEG_INF;
-                    if (!(v > bottom)) break;                        // sorted: nothing after it can beat the bottom either
-                    insert(v, (r << 10) + __shfl_sync(FULL, tk, src));
+                const unsigned vm = __ballot_sync(FULL, x > bottom);
+                if (vm) {
+                    const int j = __popc(vm & ((1u << lane) - 1u));
+                    const float thr = __shfl_sync(FULL, Lv, j < W ? W - 1 - j : 0);
+                    unsigned im = __ballot_sync(FULL, ((vm >> lane) & 1u) && j < W && x > thr);
+                    const unsigned fail = vm & ~im;
+                    if (fail) im &= (fail & (0u - fail)) - 1u;            // keep the prefix (it is one by the argument above)
+                    for (unsigned m = im; m; m &= m - 1) {
+                        const int src = __ffs(m) - 1;
+                        insert(__shfl_sync(FULL, x, src), (r << 10) + __shfl_sync(FULL, tk, src));
+                    }
                 }
             } else {
                 for (int k0 = 0; k0 < NC; k0 += 32) {
