@@ -394,6 +394,13 @@ class CRNNModel:
         il = self._stage("input_len", np.asarray(inputs["input_length"]).reshape(-1).astype(np.int32), torch.int32)
         self._step_seed = (int(self._step_seed) * 6364136223846793005 + 1442695040888963407) % (1 << 64) | 1
         loss = self.train_fwd_bwd_device(xd, lab, ll, il, dropout_seed=self._step_seed if self.dropout else 0)
+        if os.environ.get("CRNN_DBG_NAN"):                  # debug hook (tools/dbg_dp_cli.py): where does a non-finite gradient first appear
+            self._dbg_step = self.__dict__.get("_dbg_step", 0) + 1
+            bad = [n for n in self.shapes if not n.endswith(("moving_mean", "moving_variance")) and not bool(torch.isfinite(self.tensor("grad/" + n)).all())]
+            if bad:
+                acts = [a for a in ("act/dtheta", "act/dd1", "act/dflat", "act/theta", "act/loc_d1", "act/flat", "act/bn1/scale", "act/bn1/shift", "act/bn1/mean", "act/bn1/invstd",
+                                    "act/ddw1", "act/dpw1", "act/gA", "act/gB", "act/a0") if not bool(torch.isfinite(self.tensor(a)).all())]
+                print("[dbg-nan] step %d B %d loss %s: non-finite grads in %d tensors %s ; non-finite acts %s" % (self._dbg_step, B, float(loss.mean()), len(bad), bad[:12], acts), flush=True)
         scale = self.allreduce_grads()
         self.optimizer_step(scale)
         # D2H of the step's result: per-sample losses + the CTC feasibility status in one pinned buffer, ONE stream synchronisation
