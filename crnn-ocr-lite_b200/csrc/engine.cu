@@ -131,11 +131,7 @@ struct crnn_handle {
     uint64_t last_seed = 0; int last_B = 0; bool last_drop = false;
     bool dw_fused = true;      // CRNN_DW_FUSED=0: separate ReLU6+BN-backward apply / depthwise backward-data / backward-weight kernels
     int prio = 0;              // CRNN_PRIO: stream / graph-node priorities of the critical path vs the side branch (0 = none)
-    // CRNN_BN_TAIL=1: BatchNorm finalize as the last-CTA tail of the kernel that accumulates the statistics instead of a launch of its own
-    // (126 -> 112 launches per step, time neutral).  OFF: all 100 parity tests pass with it, but in the 2-processes-on-one-GPU data-parallel CLI
-    // test (tests/test_gpu_dp.py, tools/dbg_dp_cli.py) 5 of 19 runs ended with non-finite gradients of BatchNorm 1 (C = 1, statistics from
-    // colstats_kernel) and everything below it (STN), against 0 of 8 runs without the tail -- cause not found before the round ended.
-    bool bn_tail = false;
+    bool bn_tail = true;       // CRNN_BN_TAIL=0: BatchNorm finalize as a launch of its own instead of the last-CTA tail of the kernel that accumulates the statistics
     bool dw_red = true;        // CRNN_DW_RED=0: the depthwise backward-data kernel does not accumulate the BN2-backward reduction of the block below
     // ---- step scheduling: the train step / the predictor forward are captured once per (batch, buffers) into a CUDA graph and
     // replayed; work that is off the activation-gradient critical path (weight gradients, weight-image preparation) runs on a side
@@ -870,7 +866,7 @@ int crnn_create(const crnn_config* cfg, void* workspace, size_t workspace_bytes,
     h->base = static_cast<char*>(workspace); h->bytes = workspace_bytes;
     { const char* e = getenv("CRNN_FUSE_BN_RED"); h->fuse_bn_red = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_DW_RED"); h->dw_red = !(e && e[0] == '0'); }
-    { const char* e = getenv("CRNN_BN_TAIL"); h->bn_tail = e && e[0] == '1'; }      // OFF by default, see the handle field
+    { const char* e = getenv("CRNN_BN_TAIL"); h->bn_tail = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_DW_FUSED"); h->dw_fused = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_FWD_FUSED"); h->fwd_fused = !(e && e[0] == '0'); }
     { const char* e = getenv("CRNN_GEMM_SIMT"); h->gemm_simt = e && e[0] == '1'; }

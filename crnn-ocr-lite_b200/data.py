@@ -229,7 +229,12 @@ class Readf:
         return Y
 
     def get_blank_matrices(self):
-        X = np.empty((self.batch_size,) + tuple(self.img_size), np.uint8 if getattr(self, "device_norm", False) else np.float64)
+        # The reference allocates X with np.empty (utils.py:448) and, for the partially filled last batch of the FIRST pass, hands Keras the rows it
+        # never wrote -- uninitialised memory that train_on_batch then trains on.  Zeros here: with recycled heap memory those rows were
+        # sometimes NaN / huge, which ReLU6 masks in the forward pass (finite loss) but not in the BatchNorm-1 / STN backward (found through
+        # tests/test_gpu_dp.py::test_dp_train_cli_uneven_shards_and_early_stopping failing in ~1 of 5 runs; tools/dbg_dp_cli.py).  The valid
+        # rows are unchanged (pinned on the reference's own generator in tests/test_host_logic.py).
+        X = np.zeros((self.batch_size,) + tuple(self.img_size), np.uint8 if getattr(self, "device_norm", False) else np.float64)
         Y = np.full([self.batch_size, self.max_len], self.blank)
         return X, Y, np.ones((self.batch_size, 1)), np.zeros((self.batch_size, 1))
 

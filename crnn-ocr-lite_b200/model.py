@@ -398,9 +398,16 @@ class CRNNModel:
             self._dbg_step = self.__dict__.get("_dbg_step", 0) + 1
             bad = [n for n in self.shapes if not n.endswith(("moving_mean", "moving_variance")) and not bool(torch.isfinite(self.tensor("grad/" + n)).all())]
             if bad:
-                acts = [a for a in ("act/dtheta", "act/dd1", "act/dflat", "act/theta", "act/loc_d1", "act/flat", "act/bn1/scale", "act/bn1/shift", "act/bn1/mean", "act/bn1/invstd",
-                                    "act/ddw1", "act/dpw1", "act/gA", "act/gB", "act/a0") if not bool(torch.isfinite(self.tensor(a)).all())]
-                print("[dbg-nan] step %d B %d loss %s: non-finite grads in %d tensors %s ; non-finite acts %s" % (self._dbg_step, B, float(loss.mean()), len(bad), bad[:12], acts), flush=True)
+                names = ("act/dtheta", "act/dd1", "act/dflat", "act/theta", "act/loc_d1", "act/flat", "act/bn1/scale", "act/bn1/shift", "act/bn1/mean", "act/bn1/invstd",
+                         "act/bn2/scale", "act/bn2/shift", "act/bn2/mean", "act/bn2/invstd", "act/dw1", "act/pw1", "act/ddw1", "act/dpw1", "act/ddw2", "act/dpw2", "act/gA", "act/gB", "act/a0")
+                acts = []
+                for a in names:
+                    t = self.tensor(a)
+                    nf = int((~torch.isfinite(t)).sum())
+                    if nf:
+                        acts.append("%s:%d/%d@%d" % (a, nf, t.numel(), int(torch.nonzero(~torch.isfinite(t))[0])))
+                b1 = [float(self.tensor("act/bn1/" + k)[0]) for k in ("scale", "shift", "mean", "invstd")]
+                print("[dbg-nan] step %d B %d loss %s: non-finite grads in %d tensors %s ; non-finite acts %s ; bn1 %s" % (self._dbg_step, B, float(loss.mean()), len(bad), bad[:12], acts, b1), flush=True)
         scale = self.allreduce_grads()
         self.optimizer_step(scale)
         # D2H of the step's result: per-sample losses + the CTC feasibility status in one pinned buffer, ONE stream synchronisation

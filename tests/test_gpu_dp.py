@@ -98,4 +98,5 @@ def test_dp_train_cli_uneven_shards_and_early_stopping(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert (tmp_path / "m" / "final_weights.h5").exists()
     a = np.load(str(tmp_path / "params.rank0.npy")); b = np.load(str(tmp_path / "params.rank1.npy"))
+    assert np.isfinite(a).all() and np.isfinite(b).all(), "non-finite parameters after training"
     assert a.size > 2_800_000 and np.array_equal(a, b), "replicas diverged"
