@@ -257,6 +257,34 @@ def test_input_pipeline_reproduces_reference(cb):
     assert list(gl.keys()) == [str(k) for k in g["get_lengths_keys"]] and list(gl.values()) == [int(v) for v in g["get_lengths_vals"]]
 
 
+def test_partial_batch_tail_rows_are_zero_not_uninitialised(cb, tmp_path):
+    """The reference allocates its batch with np.empty (utils.py:448) and yields the partially filled last batch of the FIRST pass with the rows it
+    never wrote; train_on_batch then trains on uninitialised memory.  Recycled heap memory there was sometimes NaN, which the network's ReLU6
+    masks in the forward pass and the BatchNorm-1 / STN backward does not (the 2-rank CLI test failed in ~1 of 5 runs).  The mirror zero-fills."""
+    import cv2
+    words = ["hello", "world", "ocr", "lite", "b200", "crnn", "text", "line", "nine"]
+    names = []
+    for i, w in enumerate(words):
+        img = np.full((32, 100), 255, np.uint8)
+        cv2.putText(img, w, (2, 24), cv2.FONT_HERSHEY_SIMPLEX, 0.8, 30, 2)
+        names.append(str(tmp_path / ("%d_%s_%d.png" % (i, w, i))))
+        cv2.imwrite(names[-1], img)
+    classes = {c: i for i, c in enumerate(sorted(set("".join(words) + "-")))}
+    junk = np.full((8, 100, 32, 1), np.nan)          # poison the heap block the next allocation of that size is likely to reuse
+    del junk
+    for device_norm in (False, True):
+        r = cb.Readf(img_size=(100, 32, 1), max_len=10, normed=True, batch_size=8, classes=classes, transform_p=0.0, device_norm=device_norm)
+        g = r.run_generator(names, downsample_factor=2)
+        valid = []
+        for _ in range(4):
+            b, _t = next(g)
+            nv = len(b["source_str"]); valid.append(nv)
+            X = b["the_input"]
+            assert X.shape == (8, 100, 32, 1) and np.isfinite(X.astype(np.float64)).all()
+            assert (X[nv:] == 0).all() and (b["label_length"][nv:] == 0).all() and (b["input_length"][nv:] == 1).all()
+        assert valid == [8, 1, 8, 8]                   # only the first pass ends with a partial batch (utils.py:462-511)
+
+
 def test_readf_generator_reproduces_reference(cb, tmp_path):
     """Batch generator: Readf.run_generator against batches produced by the REFERENCE's own class over three passes
     (tests/golden/readf_golden.npz from tests/golden/make_readf_golden.py): images, labels padded with the blank, input/label lengths,
