@@ -141,6 +141,28 @@ def test_beam_parent_sequential_formulation():
             assert beam_parent_sequential(probs[b], W, True) == list(out[b, :n[b]]), (B, T, V, sc, W, seed, b)
 
 
+def test_beam_kernel_shortcuts_are_exact():
+    """The short cuts of ctc_beam_kernel's fast path (csrc/ctc.cu, beam width <= 16) -- the two pruning floors of the per-step candidate list,
+    the blocking count taken on that list with its completeness test, the number of insertions per parent in closed form, the survivors'
+    (total desc, slot desc) order -- restated in Python (oracle/beam_reference_py.py::beam_parent_sequential_fast) and checked against the
+    literal TF restatement in ctc_oracle.c on far more shapes than the GPU tests run: flat to saturated inputs, vocabularies around the
+    32-lane boundary, widths 1..16.  Every short cut must actually have been taken."""
+    from oracle import beam_reference_py as R
+    R.STATS.clear()
+    rng0 = np.random.default_rng(2024)
+    for i in range(48):
+        V = int(rng0.choice([5, 12, 33, 34, 38, 65, 96, 97, 130]))
+        W = int(rng0.choice([1, 2, 3, 5, 8, 10, 12, 16]))
+        T = int(rng0.integers(1, 32))
+        sc = float(rng0.choice([0.2, 0.5, 1.0, 2.0, 3.0, 6.0, 12.0]))
+        probs = _rand_probs(np.random.default_rng(500 + i), 12, T, V, sc)
+        out, n, _ = O.beam(probs, beam_width=W, merge_repeated=True)
+        for b in range(probs.shape[0]):
+            assert R.beam_parent_sequential_fast(probs[b], W, True) == list(out[b, :n[b]]), (T, V, sc, W, i, b)
+    st = R.STATS
+    assert st["floor1"] > 1000 and st["floor2"] > 500 and st["chunked"] > 50 and st["block_tests"] > 1000 and st["block_fallback"] > 5 and st["inserted"] > 10000, dict(st)
+
+
 def test_threaded_driver_matches():
     probs = _rand_probs(np.random.default_rng(5), 37, 25, 96)
     a = O.beam(probs)
